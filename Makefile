@@ -1,0 +1,29 @@
+# Build of the product library (CUDA, sm_100a) and of the test-only helpers.
+#   make            -> ngspice-sf-mirror_b200/libngb200.so          (nvcc; the product)
+#   make hostsim    -> tests/hostsim/libngb200_hostsim.so           (g++; CPU CI only)
+#   make oracle     -> oracle/libngb_oracle.so + oracle/_ref/*      (gcc; checker only)
+PKG := ngspice-sf-mirror_b200
+CSRC := $(PKG)/csrc
+NVCC ?= nvcc
+NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -Xcompiler -fPIC -std=c++17 \
+           -Xptxas -v -I$(CSRC) -Iinclude
+HOSTC := $(CSRC)/ngb_host.c $(CSRC)/ngb_tran.c
+HDRS := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
+
+all: $(PKG)/libngb200.so
+
+$(PKG)/libngb200.so: $(CSRC)/ngb_cuda.cu $(HOSTC) $(HDRS)
+	gcc -O2 -fPIC -std=gnu99 -Wall -I$(CSRC) -Iinclude -x c -include $(CSRC)/c_compat.h -c $(CSRC)/ngb_host.c -o $(CSRC)/ngb_host.o
+	gcc -O2 -fPIC -std=gnu99 -Wall -I$(CSRC) -Iinclude -x c -include $(CSRC)/c_compat.h -c $(CSRC)/ngb_tran.c -o $(CSRC)/ngb_tran.o
+	$(NVCC) $(NVFLAGS) -c $(CSRC)/ngb_cuda.cu -o $(CSRC)/ngb_cuda.o 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; false)
+	$(NVCC) -shared -o $@ $(CSRC)/ngb_cuda.o $(CSRC)/ngb_host.o $(CSRC)/ngb_tran.o -lcudart
+
+hostsim: tests/hostsim/libngb200_hostsim.so
+tests/hostsim/libngb200_hostsim.so: tests/hostsim/hostsim.cpp $(HOSTC) $(HDRS)
+	gcc -O2 -fPIC -std=gnu99 -Wall -I$(CSRC) -Iinclude -x c -include $(CSRC)/c_compat.h -c $(CSRC)/ngb_host.c -o tests/hostsim/ngb_host.o
+	gcc -O2 -fPIC -std=gnu99 -Wall -I$(CSRC) -Iinclude -x c -include $(CSRC)/c_compat.h -c $(CSRC)/ngb_tran.c -o tests/hostsim/ngb_tran.o
+	g++ -O2 -fPIC -std=c++17 -ffp-contract=off -Wall -I$(CSRC) -Iinclude -x c++ -c tests/hostsim/hostsim.cpp -o tests/hostsim/hostsim.o
+	g++ -shared -o $@ tests/hostsim/hostsim.o tests/hostsim/ngb_host.o tests/hostsim/ngb_tran.o -lm
+
+clean:
+	rm -f $(CSRC)/*.o $(PKG)/*.so tests/hostsim/*.o tests/hostsim/*.so

@@ -1,0 +1,122 @@
+/* ngb200.h -- C ABI of the B200 Newton hot path (libngb200.so).
+ *
+ * Plain pointers and sizes only.  Every entry point names the reference interface it stands
+ * in for (paths relative to the ngspice tree, danchitnis/ngspice-sf-mirror):
+ *
+ *   device table   SPICEdev::DEVload / DEVtrunc      src/include/ngspice/devdefs.h:57,67
+ *   circuit load   CKTload                            src/spicelib/analysis/cktload.c:32
+ *   matrix API     SMPclear/SMPluFac/SMPreorder/SMPsolve/SMPpreOrder
+ *                                                     src/include/ngspice/smpdefs.h:61-86
+ *   Newton loop    NIiter, NIconvTest                 src/maths/ni/niiter.c:28, niconv.c:21
+ *   transient      DCtran, NIcomCof, CKTtrunc/CKTterr src/spicelib/analysis/dctran.c:66,
+ *                                                     src/maths/ni/nicomcof.c:14, cktterr.c:10
+ *
+ * A `ngb_circuit` is the flattened result of CKTsetup + CKTtemp for one netlist (what the
+ * reference keeps in CKTcircuit, the GENinstance lists and the KLU binding table).  A
+ * `ngb_batch` is S device-resident samples of that circuit (Monte-Carlo draws or sweep
+ * points): parameters, solution vectors, state history, matrices.  All array arguments are
+ * HOST pointers unless the name says `dev`; layouts are given per call.
+ *
+ * Return value: 0 (OK) or a code from src/include/ngspice/sperror.h / iferrmsg.h
+ * (E_SINGULAR 102, E_ITERLIM 103, E_ORDER 104, E_METHOD 105, E_TIMESTEP 106, E_UNSUPP 10).
+ * There is no CPU fallback: every compute entry point fails with E_PANIC when the CUDA
+ * device cannot be initialised.
+ */
+#ifndef NGB200_H
+#define NGB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ngb_circuit ngb_circuit;
+typedef struct ngb_batch ngb_batch;
+
+/* ---- library ---- */
+const char *ngbBackend(void);                 /* "cuda-sm_100a" for the product library */
+const char *ngbLastError(void);
+long ngbLaunchCount(void);                    /* kernels launched since load */
+
+/* field-list sizes, so callers can check they were built against the same lists
+ * (bsim4_fields.h): [0]=model [1]=bin [2]=instance [3]=node roles [4]=matrix stamps
+ * [5]=matrix+rhs stamps [6]=states [7]=op-point fields */
+void ngbBsim4Layout(int out[8]);
+const char *ngbBsim4FieldName(int list, int index);
+
+/* ---- circuit description: what DEVsetup/DEVtemperature/DEVbindCSC leave behind ---- */
+ngb_circuit *ngbCircuitCreate(int neq, const int *node_type /* [neq+1], 3=voltage 4=current */);
+void ngbCircuitDestroy(ngb_circuit *c);
+
+/* dopt: reltol abstol vntol chgtol trtol temp vt0 xmu tstep tstop tmax tstart delmin minbreak gmin
+ * iopt: method(1 trap) maxorder itl4 itl1 uic   (cktntask.c:95-146, cktdojob.c:50-125) */
+int ngbCircuitSetOptions(ngb_circuit *c, const double dopt[15], const int iopt[5]);
+
+/* BSIM4 instances in the order of the reference instance lists (cktcrte.c:62-64).
+ * nodes [12][ninst], flags [ninst] (B4F_*), prow [ninst] row of mtab/ptab, inst [NI][ninst],
+ * mtab [nrows][NM], ptab [nrows][NP]            -- replaces the BSIM4instance/BSIM4model walk
+ * of BSIM4load (b4ld.c:251-253) */
+int ngbCircuitAddBsim4(ngb_circuit *c, int ninst, const int *nodes, const int *flags, const int *prow,
+                       const double *inst, int nrows, const double *mtab, const double *ptab);
+int ngbCircuitAddResistors(ngb_circuit *c, int n, const int *nodes /* [2][n] */, const double *g);
+int ngbCircuitAddCapacitors(ngb_circuit *c, int n, const int *nodes /* [2][n] */,
+                            const double *par /* [3][n] C, m, ic */);
+int ngbCircuitAddVsources(ngb_circuit *c, int n, const int *nodes /* [3][n] pos neg branch */,
+                          const int *fn /* [3][n] type order dcGiven */, const double *par /* [9][n] */);
+int ngbCircuitAddIsources(ngb_circuit *c, int n, const int *nodes /* [2][n] */,
+                          const int *fn /* [3][n] */, const double *par /* [10][n] */);
+
+/* SMPmakeElt + SMPconvertCOOtoCSC + DEVbindCSC (klusmp.c:137-323, 417-440): builds the CSC
+ * pattern, the slot map and the per-target contribution lists */
+int ngbCircuitFinalize(ngb_circuit *c);
+int ngbCircuitPatternSize(const ngb_circuit *c, int *n, int *nnz, int *nstamp_rows);
+int ngbCircuitGetPattern(const ngb_circuit *c, int *Ap, int *Ai, int *diag_slot /* [n] */);
+int ngbCircuitGetBsim4Slots(const ngb_circuit *c, int *slots /* [70][ninst], -1 = ground/absent */);
+
+/* SMPpreOrder + first SMPreorder: reuse the KLU symbolic analysis and pivot order
+ * (klu_analyze, klu_factor) -- arrays exactly as in klu_symbolic / klu_numeric, with L/U column
+ * patterns flattened (Lp/Li, Up/Ui in pivotal numbering) */
+int ngbCircuitSetLuPattern(ngb_circuit *c, int n, int nblocks, const int *Q, const int *R,
+                           const int *Pnum, const int *Lp, const int *Li, const int *Up, const int *Ui,
+                           const int *Offp, const int *Offi);
+/* own BTF + fill-reducing ordering + pivoting factor on one sample's matrix values
+ * (host; the role klu_analyze/klu_factor play) */
+int ngbCircuitAnalyze(ngb_circuit *c, const double *Ax);
+/* info: nV nlev npairs ntask nslev nsolvepairs lnz unz nzoff */
+int ngbCircuitLuInfo(const ngb_circuit *c, int info[9]);
+
+/* ---- batch ---- */
+ngb_batch *ngbBatchCreate(ngb_circuit *c, int nsamples, int device);
+void ngbBatchDestroy(ngb_batch *b);
+
+/* named device arrays (tests, the reference-side shim, result download):
+ *   ctl.mode ctl.active ctl.head ctl.order ctl.noncon ctl.xsel ctl.err          int   [S]
+ *   ctl.ag0 ctl.ag1 ctl.delta ctl.time ctl.gmin ctl.diag_gmin ctl.srcfact        f64   [S]
+ *   ctl.delta_old                                                                f64   [7][S]
+ *   x            f64 [2][neq+1][S]      Ax  f64 [S][nnz]      stamp f64 [rows][S]
+ *   b4.inst      f64 [NI][ninst*S]      b4.state f64 [4][29][ninst*S]   b4.op f64 [NO][ninst*S]
+ *   b4.prow      int [ninst*S]          cap.state f64 [4][2][ncap*S]    cap.par f64 [3][ncap*S]
+ *   vsrc.par     f64 [9][nv*S]          lu.V f64 [S][nV]    lu.Rs f64 [S][n]
+ *   lu.nodeconv  int [S]                lu.singular int [S] */
+long ngbBatchArrayBytes(ngb_batch *b, const char *name);
+int ngbBatchUpload(ngb_batch *b, const char *name, const void *host, long bytes, long offset);
+int ngbBatchDownload(ngb_batch *b, const char *name, void *host, long bytes, long offset);
+void *ngbBatchDevPtr(ngb_batch *b, const char *name);
+int ngbBatchSetOpFull(ngb_batch *b, int on);   /* export every B4O_* field (parity runs) */
+
+/* hot path, one call = one step of NIiter for every active sample */
+int ngbLoad(ngb_batch *b);                     /* CKTload: device loads + assembly of Ax / rhs   */
+int ngbLuFac(ngb_batch *b);                    /* SMPluFac: LoadGmin + row scaling + refactor     */
+int ngbSolve(ngb_batch *b);                    /* SMPsolve + node part of NIconvTest              */
+int ngbLuFacSolve(ngb_batch *b);               /* the two above in one launch                     */
+int ngbNewtonStep(ngb_batch *b);               /* ngbLoad + ngbLuFacSolve                         */
+
+/* device-resident transient analysis for the whole batch (DCtran + NIiter, per sample) */
+int ngbTranRun(ngb_batch *b, int max_points, const int *save_eq, int nsave);
+int ngbTranStats(ngb_batch *b, int *accepted, int *rejected, int *numiter, int *npoints /* each [S] */);
+long ngbTranWaveBytes(ngb_batch *b);
+int ngbTranWaves(ngb_batch *b, double *times /* [S][max_points] */, double *values /* [S][max_points][nsave] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,242 @@
+"""ngspice-sf-mirror_b200 -- host-side mirror of the hot-path interface.
+
+Thin ctypes layer over the C ABI of include/ngb200.h (libngb200.so: hand-written sm_100a
+kernels + C host code).  The product path has NO CPU fallback: importing works anywhere, but
+creating a batch needs the CUDA library and a GPU, and fails loudly otherwise.  The names
+mirror the reference entry points they stand in for (CKTload, SMPluFac, SMPsolve, DCtran ...).
+"""
+import ctypes
+import os
+import numpy as np
+from . import ngt  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libngb200.so")
+
+_c_int_p = ctypes.POINTER(ctypes.c_int)
+_c_dbl_p = ctypes.POINTER(ctypes.c_double)
+
+
+class NgbError(RuntimeError):
+    pass
+
+
+def _ip(a):
+    return a.ctypes.data_as(_c_int_p)
+
+
+def _dp(a):
+    return a.ctypes.data_as(_c_dbl_p)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Library:
+    """Loaded libngb200.so (or, in CPU-only tests, the hostsim test double given by path)."""
+
+    def __init__(self, path=None):
+        path = path or LIB_PATH
+        if not os.path.exists(path):
+            raise NgbError(
+                f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the hot path)")
+        self.path = path
+        L = self.L = ctypes.CDLL(path)
+        L.ngbBackend.restype = ctypes.c_char_p
+        L.ngbLastError.restype = ctypes.c_char_p
+        L.ngbLaunchCount.restype = ctypes.c_long
+        L.ngbBsim4FieldName.restype = ctypes.c_char_p
+        L.ngbCircuitCreate.restype = ctypes.c_void_p
+        L.ngbBatchCreate.restype = ctypes.c_void_p
+        L.ngbBatchArrayBytes.restype = ctypes.c_long
+        L.ngbBatchDevPtr.restype = ctypes.c_void_p
+        L.ngbTranWaveBytes.restype = ctypes.c_long
+        lay = (ctypes.c_int * 8)()
+        L.ngbBsim4Layout(lay)
+        self.layout = list(lay)
+        self.fields = {}
+        for li, key in ((0, "model"), (1, "bin"), (2, "inst"), (3, "node"), (5, "stamp"), (7, "op")):
+            n = self.layout[li]
+            self.fields[key] = [L.ngbBsim4FieldName(li, i).decode() for i in range(n)]
+
+    @property
+    def backend(self):
+        return self.L.ngbBackend().decode()
+
+    def check(self, rc, what=""):
+        if rc != 0:
+            raise NgbError(f"{what} failed with code {rc}: {self.L.ngbLastError().decode()}")
+
+    def launch_count(self):
+        return int(self.L.ngbLaunchCount())
+
+
+_default_lib = None
+
+
+def library(path=None):
+    global _default_lib
+    if path is not None:
+        return Library(path)
+    if _default_lib is None:
+        _default_lib = Library()
+    return _default_lib
+
+
+DOPT_KEYS = ["reltol", "abstol", "vntol", "chgtol", "trtol", "temp", "vt0", "xmu", "tstep", "tstop",
+             "tmax", "tstart", "delmin", "minbreak", "gmin"]
+IOPT_KEYS = ["method", "maxorder", "itl4", "itl1", "uic"]
+
+
+class Circuit:
+    """Flattened circuit: what CKTsetup + CKTtemp leave behind (see include/ngb200.h)."""
+
+    def __init__(self, lib, neq, node_type):
+        self.lib = lib
+        self.neq = int(neq)
+        nt = _i32(node_type)
+        self.h = ctypes.c_void_p(lib.L.ngbCircuitCreate(self.neq, _ip(nt)))
+        self.flat = None
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.L.ngbCircuitDestroy(self.h)
+        except Exception:
+            pass
+
+    @classmethod
+    def from_flat(cls, lib, flat, lu_pattern=None):
+        """Build from a flat-circuit dict (oracle dump / fixture / synthetic generator)."""
+        sc = ngt.scalar
+        c = cls(lib, sc(flat, "meta/neq"), flat["node/type"])
+        c.flat = flat
+        d = np.array([sc(flat, "opt/reltol"), sc(flat, "opt/abstol"), sc(flat, "opt/vntol"),
+                      sc(flat, "opt/chgtol"), sc(flat, "opt/trtol"), sc(flat, "opt/temp"), sc(flat, "opt/vt0"),
+                      sc(flat, "opt/xmu"), sc(flat, "tran/tstep", 0.0), sc(flat, "tran/tstop", 0.0),
+                      sc(flat, "tran/tmax", 0.0), sc(flat, "tran/tstart", 0.0), sc(flat, "opt/delmin", 0.0),
+                      sc(flat, "opt/minbreak", 0.0), sc(flat, "opt/gmin")], dtype=np.float64)
+        i = np.array([sc(flat, "opt/method"), sc(flat, "opt/maxorder"), sc(flat, "opt/itl4"),
+                      sc(flat, "opt/itl1"), sc(flat, "tran/uic", 0)], dtype=np.int32)
+        lib.check(lib.L.ngbCircuitSetOptions(c.h, _dp(d), _ip(i)), "ngbCircuitSetOptions")
+        if sc(flat, "opt/bypass", 0):
+            raise NgbError("CKTbypass != 0 is not supported on this path")
+        n = sc(flat, "b4/ninst", 0)
+        if n:
+            nodes, flags, prow = _i32(flat["b4/nodes"]), _i32(flat["b4/flags"]), _i32(flat["b4/prow"])
+            inst, mtab, ptab = _f64(flat["b4/inst"]), _f64(flat["b4/mtab"]), _f64(flat["b4/ptab"])
+            assert inst.shape[0] == lib.layout[2] and mtab.shape[1] == lib.layout[0] and ptab.shape[1] == lib.layout[1], \
+                "fixture built against different BSIM4 field lists"
+            lib.check(lib.L.ngbCircuitAddBsim4(c.h, int(n), _ip(nodes), _ip(flags), _ip(prow), _dp(inst),
+                                               int(mtab.shape[0]), _dp(mtab), _dp(ptab)), "ngbCircuitAddBsim4")
+        n = sc(flat, "res/n", 0)
+        if n:
+            lib.check(lib.L.ngbCircuitAddResistors(c.h, int(n), _ip(_i32(flat["res/nodes"])), _dp(_f64(flat["res/g"]))),
+                      "ngbCircuitAddResistors")
+        n = sc(flat, "cap/n", 0)
+        if n:
+            lib.check(lib.L.ngbCircuitAddCapacitors(c.h, int(n), _ip(_i32(flat["cap/nodes"])), _dp(_f64(flat["cap/par"]))),
+                      "ngbCircuitAddCapacitors")
+        n = sc(flat, "vsrc/n", 0)
+        if n:
+            lib.check(lib.L.ngbCircuitAddVsources(c.h, int(n), _ip(_i32(flat["vsrc/nodes"])), _ip(_i32(flat["vsrc/fn"])),
+                                                  _dp(_f64(flat["vsrc/par"]))), "ngbCircuitAddVsources")
+        n = sc(flat, "isrc/n", 0)
+        if n:
+            lib.check(lib.L.ngbCircuitAddIsources(c.h, int(n), _ip(_i32(flat["isrc/nodes"])), _ip(_i32(flat["isrc/fn"])),
+                                                  _dp(_f64(flat["isrc/par"]))), "ngbCircuitAddIsources")
+        lib.check(lib.L.ngbCircuitFinalize(c.h), "ngbCircuitFinalize")
+        if lu_pattern is not None:
+            c.set_lu_pattern(lu_pattern)
+        return c
+
+    def pattern(self):
+        n, nnz, nrows = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self.lib.check(self.lib.L.ngbCircuitPatternSize(self.h, ctypes.byref(n), ctypes.byref(nnz), ctypes.byref(nrows)))
+        Ap = np.zeros(n.value + 1, np.int32); Ai = np.zeros(nnz.value, np.int32); dg = np.zeros(n.value, np.int32)
+        self.lib.check(self.lib.L.ngbCircuitGetPattern(self.h, _ip(Ap), _ip(Ai), _ip(dg)))
+        return dict(n=n.value, nnz=nnz.value, nrows=nrows.value, Ap=Ap, Ai=Ai, diag=dg)
+
+    def bsim4_slots(self, ninst):
+        s = np.zeros((self.lib.layout[4], ninst), np.int32)
+        self.lib.check(self.lib.L.ngbCircuitGetBsim4Slots(self.h, _ip(s)))
+        return s
+
+    def set_lu_pattern(self, pat, prefix=""):
+        """pat: dict with n nblocks Q R Pnum Lp Li Up Ui Offp Offi (KLU symbolic + numeric pattern)."""
+        g = lambda k: _i32(pat[prefix + k])
+        self._keep = [g(k) for k in ("Q", "R", "Pnum", "Lp", "Li", "Up", "Ui", "Offp", "Offi")]
+        n = int(np.asarray(pat[prefix + "n"]).reshape(-1)[0]); nb = int(np.asarray(pat[prefix + "nblocks"]).reshape(-1)[0])
+        self.lib.check(self.lib.L.ngbCircuitSetLuPattern(self.h, n, nb, *[_ip(a) for a in self._keep]),
+                       "ngbCircuitSetLuPattern")
+
+    def lu_info(self):
+        info = (ctypes.c_int * 9)()
+        self.lib.check(self.lib.L.ngbCircuitLuInfo(self.h, info))
+        return dict(zip(["nV", "nlev", "npairs", "ntask", "nslev", "nsolvepairs", "lnz", "unz", "nzoff"], list(info)))
+
+
+_INT_ARRAYS = {"ctl.mode", "ctl.active", "ctl.head", "ctl.order", "ctl.noncon", "ctl.xsel", "ctl.err",
+               "b4.prow", "lu.nodeconv", "lu.singular", "errflag"}
+
+
+class Batch:
+    """S device-resident samples of one circuit."""
+
+    def __init__(self, circuit, nsamples, device=0):
+        self.c = circuit
+        self.lib = circuit.lib
+        self.S = int(nsamples)
+        h = self.lib.L.ngbBatchCreate(circuit.h, self.S, int(device))
+        if not h:
+            raise NgbError("ngbBatchCreate failed: " + self.lib.L.ngbLastError().decode())
+        self.h = ctypes.c_void_p(h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.L.ngbBatchDestroy(self.h)
+        except Exception:
+            pass
+
+    def nbytes(self, name):
+        n = self.lib.L.ngbBatchArrayBytes(self.h, name.encode())
+        if n < 0:
+            raise NgbError(self.lib.L.ngbLastError().decode())
+        return n
+
+    def put(self, name, arr, offset=0):
+        dt = np.int32 if name in _INT_ARRAYS else np.float64
+        a = np.ascontiguousarray(arr, dtype=dt)
+        self.lib.check(self.lib.L.ngbBatchUpload(self.h, name.encode(), a.ctypes.data_as(ctypes.c_void_p),
+                                                 ctypes.c_long(a.nbytes), ctypes.c_long(offset)), f"upload {name}")
+
+    def get(self, name, shape=None):
+        dt = np.int32 if name in _INT_ARRAYS else np.float64
+        n = self.nbytes(name) // np.dtype(dt).itemsize
+        a = np.zeros(n, dt)
+        self.lib.check(self.lib.L.ngbBatchDownload(self.h, name.encode(), a.ctypes.data_as(ctypes.c_void_p),
+                                                   ctypes.c_long(a.nbytes), ctypes.c_long(0)), f"download {name}")
+        return a.reshape(shape) if shape is not None else a
+
+    def set_op_full(self, on=True):
+        self.lib.L.ngbBatchSetOpFull(self.h, 1 if on else 0)
+
+    # hot path: one call = one step of NIiter for every active sample
+    def load(self):
+        self.lib.check(self.lib.L.ngbLoad(self.h), "ngbLoad (CKTload)")
+
+    def lufac(self):
+        self.lib.check(self.lib.L.ngbLuFac(self.h), "ngbLuFac (SMPluFac)")
+
+    def solve(self):
+        self.lib.check(self.lib.L.ngbSolve(self.h), "ngbSolve (SMPsolve)")
+
+    def lufac_solve(self):
+        self.lib.check(self.lib.L.ngbLuFacSolve(self.h), "ngbLuFacSolve")

@@ -23,6 +23,7 @@
 #define NGB_BSIM4_EVAL_CUH
 
 #include "ngb_common.h"
+#include "ngb_types.h"
 #include "bsim4_fields.h"
 #include "devsup.cuh"
 
@@ -57,17 +58,9 @@ typedef struct B4Ctx {
     double *state;             /* [NGB_NHIST][B4ST_COUNT][T]                             */
     double *op;                /* [B4O_COUNT][T] operating point (von is read back)      */
     int op_full;               /* 0: keep only von ; 1: export every B4O_* (parity runs) */
-    const double *xold;        /* [neq+1][S] previous Newton iterate (CKTrhsOld)         */
-    /* per-sample control block, each [S] */
-    const int *mode;           /* CKTmode                                                */
-    const int *active;         /* 0: sample skips this launch                            */
-    const int *head;           /* ring position of CKTstate0                             */
-    const int *order;          /* CKTorder                                               */
-    const double *ag0, *ag1;   /* CKTag[0], CKTag[1]                                     */
-    const double *delta;       /* CKTdelta                                               */
-    const double *delta_old1;  /* CKTdeltaOld[1]                                         */
-    const double *gmin;        /* CKTgmin (per sample: gmin stepping)                    */
-    int *noncon;               /* CKTnoncon (incremented atomically)                     */
+    const double *x;           /* [2][neq1][S] solution buffers; xsel[s] picks CKTrhsOld  */
+    int neq1;                  /* equations + 1 (row 0 is ground)                         */
+    NgbCtl ctl;                /* per-sample control block                                */
     /* shared scalars */
     double temp;               /* CKTtemp                                                */
     double vt0;                /* CONSTvt0                                               */
@@ -232,6 +225,7 @@ NGB_HD void b4_fetch_limit(const B4Ctx *c, size_t t, int inst, int s, int head, 
     const int off = flags & B4F_OFF;
     const double type = B4M(type);
     const int rdsMod = (int)B4M(rdsMod);
+    const int S = c->S;
     double vds, vgs, vbs, vges, vgms, vdbs, vsbs, vses, vdes, qdef;
     double vbd, vgd, vged, vgmd, vdbd;
     int Check = 1, Check1 = 1, Check2 = 1;
@@ -264,7 +258,7 @@ NGB_HD void b4_fetch_limit(const B4Ctx *c, size_t t, int inst, int s, int head, 
         if (mode_ckt & NGB_MODEINITPRED) {
             /* linear extrapolation from the two previous time points; state0 receives the
              * state1 voltages first (b4ld.c:323-372) */
-            const double xfact = NGB_LDG(&c->delta[s]) / NGB_LDG(&c->delta_old1[s]);
+            const double xfact = NGB_LDG(&c->ctl.delta[s]) / NGB_LDG(&c->ctl.delta_old[(size_t)1 * S + s]);
             double s1, s2;
 #define B4_PRED(K, V) s1 = B4ST(1, K); s2 = B4ST(2, K); B4ST(0, K) = s1; V = (1.0 + xfact) * s1 - (xfact * s2);
             B4_PRED(B4ST_vds, vds)
@@ -282,8 +276,8 @@ NGB_HD void b4_fetch_limit(const B4Ctx *c, size_t t, int inst, int s, int head, 
 #undef B4_PRED
         } else {
             /* gather the previous Newton iterate: x[node][sample] */
-            const int S = c->S;
-#define B4_X(role) NGB_LDG(&c->xold[(size_t)NGB_LDG(&c->nodes[B4N_##role * c->ninst + inst]) * S + s])
+            const double *xo = c->x + (size_t)NGB_LDG(&c->ctl.xsel[s]) * c->neq1 * S;
+#define B4_X(role) NGB_LDG(&xo[(size_t)NGB_LDG(&c->nodes[B4N_##role * c->ninst + inst]) * S + s])
             const double xsp = B4_X(sNodePrime);
             vds  = type * (B4_X(dNodePrime) - xsp);
             vgs  = type * (B4_X(gNodePrime) - xsp);
@@ -402,7 +396,7 @@ NGB_HD void b4_fetch_limit(const B4Ctx *c, size_t t, int inst, int s, int head, 
 NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, const double *Prow,
                        int flags, B4W *w)
 {
-    const double gmin = NGB_LDG(&c->gmin[s]);
+    const double gmin = NGB_LDG(&c->ctl.gmin[s]);
     const double nf = B4I(nf);
     const double vtm = B4M(vtm), vtm0 = B4M(vtm0);
     const int mtrlMod = (int)B4M(mtrlMod);
@@ -2878,10 +2872,10 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
     const int S = c->S;
     const int inst = (int)(t / (size_t)S);
     const int s = (int)(t - (size_t)inst * S);
-    if (!NGB_LDG(&c->active[s])) return NGB_OK;
+    if (!NGB_LDG(&c->ctl.active[s])) return NGB_OK;
 
-    const int mode_ckt = NGB_LDG(&c->mode[s]);
-    const int head = NGB_LDG(&c->head[s]);
+    const int mode_ckt = NGB_LDG(&c->ctl.mode[s]);
+    const int head = NGB_LDG(&c->ctl.head[s]);
     const int flags = NGB_LDG(&c->flags[inst]);
     const int rbodyMod = B4F_RBODY(flags), rgateMod = B4F_RGATE(flags);
     const int prow = c->prow_per_thread ? NGB_LDG(&c->prow[t]) : NGB_LDG(&c->prow[inst]);
@@ -2933,9 +2927,9 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
     if (((flags & B4F_OFF) == 0) || (!(mode_ckt & NGB_MODEINITFIX))) {
         if (w.Check == 1) {
 #ifdef __CUDA_ARCH__
-            atomicAdd(&c->noncon[s], 1);
+            atomicAdd(&c->ctl.noncon[s], 1);
 #else
-            c->noncon[s] += 1;
+            c->ctl.noncon[s] += 1;
 #endif
         }
     }
@@ -2994,7 +2988,7 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
         }
         if (nf != 1.0) { cgdo *= nf; cgso *= nf; qgdo *= nf; qgso *= nf; }
 
-        const double ag0 = NGB_LDG(&c->ag0[s]);
+        const double ag0 = NGB_LDG(&c->ctl.ag0[s]);
         if (w.mode > 0) {
             qdrn -= qgdo;
             if (rgateMod == 3) {
@@ -3130,8 +3124,8 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
     }
 
     if (do_charge) {
-        const int order = NGB_LDG(&c->order[s]);
-        const double ag0 = NGB_LDG(&c->ag0[s]), ag1 = NGB_LDG(&c->ag1[s]);
+        const int order = NGB_LDG(&c->ctl.order[s]);
+        const double ag0 = NGB_LDG(&c->ctl.ag0[s]), ag1 = NGB_LDG(&c->ctl.ag1[s]);
         const int inittran = (mode_ckt & NGB_MODEINITTRAN) != 0;
         double cqgate, cqbody, cqdrn, cqgmid = 0.0, cqbs = 0.0, cqbd = 0.0;
         if (order != 1 && order != 2) return NGB_E_ORDER;

@@ -14,9 +14,10 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <stddef.h>
 
 #ifdef __CUDACC__
-#define NGB_HD __host__ __device__ __forceinline__
+#define NGB_HD __device__ __forceinline__
 #define NGB_D __device__ __forceinline__
 #define NGB_LDG(p) __ldg(p)
 #else

@@ -1,0 +1,214 @@
+/* ngb_cuda.cu -- the CUDA (sm_100a) implementation of the device runtime in ngb_dev.h:
+ * __global__ wrappers around the kernel bodies, launch geometry, memory and stream handling.
+ *
+ * Launch geometry (B200: 148 SMs, 64 K registers/SM, up to 227 KB shared memory per CTA):
+ *   bsim4_load   one thread per (instance, sample), 128-thread CTAs; FP64-pipe/HBM bound
+ *   cap/src/asm  one thread per element, 256-thread CTAs; HBM bound, fully coalesced
+ *   lu           one warp per sample (LU values, scale factors and solve vector in shared
+ *                memory, __syncwarp between dependency levels), or one CTA per sample when a
+ *                sample's LU does not fit a warp's share of shared memory
+ * All kernels are launched on one non-default stream; nothing here falls back to the host.
+ */
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+
+#define NGB_GROUP_SYNC() do { if (nl <= 32) __syncwarp(); else __syncthreads(); } while (0)
+#include "ngb_dev.h"
+#include "ngb_kernels.cuh"
+
+static cudaStream_t g_stream = nullptr;
+static int g_device = -1;
+static long g_launches = 0;
+static int g_smem_optin = 0;
+
+extern "C" void ngb_set_error(const char *fmt, ...);
+
+#define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    ngb_set_error("%s failed: %s", #call, cudaGetErrorString(e_)); return NGB_E_PANIC; } } while (0)
+
+/* ------------------------------------------------------------------ kernels */
+__global__ void __launch_bounds__(128)
+ngb_k_bsim4_load(const B4Ctx c, int *errflag)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)c.T) return;
+    const int e = b4_load_thread(&c, t);
+    if (e) atomicMax(errflag, e);
+}
+
+__global__ void __launch_bounds__(256)
+ngb_k_cap_load(const NgbCapCtx c, int *errflag)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)c.T) return;
+    const int e = ngb_cap_thread(&c, t);
+    if (e) atomicMax(errflag, e);
+}
+
+__global__ void __launch_bounds__(256)
+ngb_k_src_load(const NgbSrcCtx c)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)c.T) return;
+    ngb_src_thread(&c, t);
+}
+
+__global__ void __launch_bounds__(256)
+ngb_k_assemble(const NgbAsmCtx c, size_t total)
+{
+    const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= total) return;
+    ngb_asm_thread(&c, u);
+}
+
+/* one warp per sample: warp w of the CTA owns sample blockIdx.x * warps + w */
+__global__ void ngb_k_lu_warp(const NgbLuCtx c, int per_sample_doubles)
+{
+    extern __shared__ double smem[];
+    const int warps = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * warps + w;
+    if (s >= c.S) return;
+    double *V = smem + (size_t)w * per_sample_doubles;
+    double *Rs = V + c.sch.nV;
+    double *Z = Rs + c.sch.n;
+    ngb_lu_sample(&c, s, lane, 32, V, Rs, Z);
+}
+
+/* one CTA per sample (larger matrices) */
+__global__ void ngb_k_lu_block(const NgbLuCtx c)
+{
+    extern __shared__ double smem[];
+    const int s = blockIdx.x;
+    if (s >= c.S) return;
+    double *V = smem;
+    double *Rs = V + c.sch.nV;
+    double *Z = Rs + c.sch.n;
+    ngb_lu_sample(&c, s, threadIdx.x, blockDim.x, V, Rs, Z);
+}
+
+__global__ void ngb_k_clear_i32(int *p, int value, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = value;
+}
+
+/* ------------------------------------------------------------------ runtime */
+extern "C" {
+
+const char *ngb_dev_backend(void) { return "cuda-sm_100a"; }
+
+int ngb_dev_init(int device)
+{
+    int count = 0;
+    if (g_stream && g_device == device) return 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        ngb_set_error("no CUDA device available");
+        return NGB_E_PANIC;
+    }
+    CUDA_OK(cudaSetDevice(device));
+    if (g_stream) cudaStreamDestroy(g_stream);
+    CUDA_OK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CUDA_OK(cudaFuncSetAttribute(ngb_k_lu_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
+    CUDA_OK(cudaFuncSetAttribute(ngb_k_lu_block, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
+    g_device = device;
+    return 0;
+}
+
+void *ngb_dev_malloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 8) != cudaSuccess) return nullptr;
+    cudaMemsetAsync(p, 0, bytes ? bytes : 8, g_stream);
+    return p;
+}
+void ngb_dev_free(void *p) { if (p) cudaFree(p); }
+int ngb_dev_h2d(void *dst, const void *src, size_t bytes)
+{
+    CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream));
+    CUDA_OK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+int ngb_dev_d2h(void *dst, const void *src, size_t bytes)
+{
+    CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
+    CUDA_OK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+int ngb_dev_memset(void *dst, int byte, size_t bytes)
+{
+    CUDA_OK(cudaMemsetAsync(dst, byte, bytes, g_stream));
+    return 0;
+}
+int ngb_dev_sync(void)
+{
+    CUDA_OK(cudaStreamSynchronize(g_stream));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+long ngb_dev_launch_count(void) { return g_launches; }
+void *ngb_dev_stream(void) { return (void *)g_stream; }
+
+static int post_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    g_launches++;
+    if (e != cudaSuccess) { ngb_set_error("launch of %s failed: %s", what, cudaGetErrorString(e)); return NGB_E_PANIC; }
+    return 0;
+}
+
+int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag)
+{
+    if (c->T <= 0) return 0;
+    const unsigned grid = (unsigned)(((size_t)c->T + 127) / 128);
+    ngb_k_bsim4_load<<<grid, 128, 0, g_stream>>>(*c, errflag);
+    return post_launch("bsim4_load");
+}
+int ngb_launch_cap_load(const NgbCapCtx *c, int *errflag)
+{
+    if (c->T <= 0) return 0;
+    const unsigned grid = (unsigned)(((size_t)c->T + 255) / 256);
+    ngb_k_cap_load<<<grid, 256, 0, g_stream>>>(*c, errflag);
+    return post_launch("cap_load");
+}
+int ngb_launch_src_load(const NgbSrcCtx *c)
+{
+    if (c->T <= 0) return 0;
+    const unsigned grid = (unsigned)(((size_t)c->T + 255) / 256);
+    ngb_k_src_load<<<grid, 256, 0, g_stream>>>(*c);
+    return post_launch("src_load");
+}
+int ngb_launch_assemble(const NgbAsmCtx *c)
+{
+    const size_t total = (size_t)(c->nnz + c->neq1) * c->S;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    ngb_k_assemble<<<grid, 256, 0, g_stream>>>(*c, total);
+    return post_launch("assemble");
+}
+int ngb_launch_lu(const NgbLuCtx *c)
+{
+    const int per = c->sch.nV + c->sch.n + c->sch.ntask;
+    const size_t bytes1 = (size_t)per * sizeof(double);
+    /* warp per sample while four samples fit one CTA's shared memory with room for 2+ CTAs/SM */
+    if (bytes1 * 4 <= (size_t)g_smem_optin / 2) {
+        const int warps = 4;
+        const unsigned grid = (unsigned)((c->S + warps - 1) / warps);
+        ngb_k_lu_warp<<<grid, warps * 32, bytes1 * warps, g_stream>>>(*c, per);
+    } else if (bytes1 <= (size_t)g_smem_optin) {
+        ngb_k_lu_block<<<(unsigned)c->S, 256, bytes1, g_stream>>>(*c);
+    } else {
+        ngb_set_error("LU of order %d (%d values) does not fit shared memory; the multi-CTA LU is not built yet",
+                      c->sch.n, c->sch.nV);
+        return NGB_E_UNSUPP;
+    }
+    return post_launch("lu");
+}
+int ngb_launch_clear_i32(int *p, int value, int n)
+{
+    if (n <= 0) return 0;
+    ngb_k_clear_i32<<<(unsigned)((n + 255) / 256), 256, 0, g_stream>>>(p, value, n);
+    return post_launch("clear_i32");
+}
+
+}  /* extern "C" */

@@ -1,0 +1,36 @@
+/* ngb_dev.h -- the device runtime the host code is written against: memory, copies and
+ * one launcher per kernel.  The product library implements it in ngb_cuda.cu (CUDA, sm_100a,
+ * no fallback).  tests/hostsim implements the same interface on the CPU so the CPU-only CI
+ * can single-step the kernel bodies; that object is never part of the product library. */
+#ifndef NGB_DEV_H
+#define NGB_DEV_H
+#include <stddef.h>
+#include "ngb_types.h"
+#include "bsim4_eval.cuh"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char *ngb_dev_backend(void);              /* "cuda-sm_100a" or "hostsim" */
+int   ngb_dev_init(int device);
+void *ngb_dev_malloc(size_t bytes);             /* zero-filled */
+void  ngb_dev_free(void *p);
+int   ngb_dev_h2d(void *dst, const void *src, size_t bytes);
+int   ngb_dev_d2h(void *dst, const void *src, size_t bytes);
+int   ngb_dev_memset(void *dst, int byte, size_t bytes);
+int   ngb_dev_sync(void);
+long  ngb_dev_launch_count(void);               /* kernels launched so far (bench "gpu_launches") */
+void *ngb_dev_stream(void);                     /* cudaStream_t the kernels are launched on */
+
+int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag);
+int ngb_launch_cap_load(const NgbCapCtx *c, int *errflag);
+int ngb_launch_src_load(const NgbSrcCtx *c);
+int ngb_launch_assemble(const NgbAsmCtx *c);
+int ngb_launch_lu(const NgbLuCtx *c);
+int ngb_launch_clear_i32(int *p, int value, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,967 @@
+/* ngb_host.c -- host side of the hot path (C): circuit flattening results, CSC pattern and
+ * slot map, stamp/contribution lists, LU task schedule, batch memory and the C-ABI calls that
+ * launch the kernels.  Everything device-side goes through ngb_dev.h.
+ *
+ * Reference code whose role this file plays:
+ *   SMPmakeElt / SMPconvertCOOtoCSC / DEVbindCSC   src/maths/KLU/klusmp.c:137-323,417-440,
+ *                                                  src/spicelib/devices/bsim4/b4set.c:2587-2676
+ *   CKTload driver                                 src/spicelib/analysis/cktload.c:32-180
+ *   SMPluFac / SMPsolve wrappers                   src/maths/KLU/klusmp.c:573-624, 950-1011
+ *   klu_refactor column loop (turned into a task schedule here)  src/maths/KLU/klu_refactor.c:285-426
+ *   klu_solve / KLU_lsolve / KLU_usolve (ditto)    src/maths/KLU/klu_solve.c, klu.c:201-345
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include "ngb_dev.h"
+#include "ngb_host.h"
+#include "../../include/ngb200.h"
+
+static char g_err[512] = "";
+void ngb_set_error(const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+}
+const char *ngbLastError(void) { return g_err; }
+const char *ngbBackend(void) { return ngb_dev_backend(); }
+long ngbLaunchCount(void) { return ngb_dev_launch_count(); }
+
+/* ------------------------------------------------------------------ field names */
+#define X(n) #n,
+static const char *b4_model_names[] = { NGB_B4_MODEL_FIELDS(X) NULL };
+static const char *b4_bin_names[] = { NGB_B4_BIN_FIELDS(X) NULL };
+static const char *b4_inst_names[] = { NGB_B4_INST_FIELDS(X) NULL };
+static const char *b4_node_names[] = { NGB_B4_NODE_FIELDS(X) NULL };
+static const char *b4_stamp_names[] = { NGB_B4_MAT_FIELDS(X) NGB_B4_RHS_FIELDS(X) NULL };
+static const char *b4_op_names[] = { NGB_B4_OP_FIELDS(X) NULL };
+#undef X
+
+void ngbBsim4Layout(int out[8])
+{
+    out[0] = B4M_COUNT; out[1] = B4P_COUNT; out[2] = B4I_COUNT; out[3] = B4N_COUNT;
+    out[4] = B4S_MAT_COUNT; out[5] = B4S_COUNT; out[6] = B4ST_COUNT; out[7] = B4O_COUNT;
+}
+const char *ngbBsim4FieldName(int list, int index)
+{
+    const char **t; int n;
+    switch (list) {
+    case 0: t = b4_model_names; n = B4M_COUNT; break;
+    case 1: t = b4_bin_names; n = B4P_COUNT; break;
+    case 2: t = b4_inst_names; n = B4I_COUNT; break;
+    case 3: t = b4_node_names; n = B4N_COUNT; break;
+    case 4: case 5: t = b4_stamp_names; n = B4S_COUNT; break;
+    case 7: t = b4_op_names; n = B4O_COUNT; break;
+    default: return NULL;
+    }
+    return (index >= 0 && index < n) ? t[index] : NULL;
+}
+
+/* (row role, column role) of each BSIM4 matrix stamp position: the TSTALLOC table of
+ * b4set.c:2587-2676 re-expressed over node roles */
+static int b4_role_of(const char *tok, int len)
+{
+    static const struct { const char *t; int role; } map[] = {
+        { "dp", B4N_dNodePrime }, { "gp", B4N_gNodePrime }, { "gm", B4N_gNodeMid },
+        { "ge", B4N_gNodeExt }, { "sp", B4N_sNodePrime }, { "bp", B4N_bNodePrime },
+        { "db", B4N_dbNode }, { "sb", B4N_sbNode }, { "d", B4N_dNode }, { "s", B4N_sNode },
+        { "b", B4N_bNode }, { "q", B4N_qNode } };
+    char low[4]; int i;
+    for (i = 0; i < len && i < 3; i++) low[i] = (char)(tok[i] | 0x20);
+    low[i] = 0;
+    for (i = 0; i < (int)(sizeof map / sizeof map[0]); i++)
+        if (!strcmp(map[i].t, low)) return map[i].role;
+    return -1;
+}
+static void b4_stamp_roles(int k, int *rrow, int *rcol)
+{
+    const char *nm = b4_stamp_names[k];
+    int up = 0;
+    while (nm[up] >= 'A' && nm[up] <= 'Z') up++;
+    *rrow = b4_role_of(nm, up);
+    *rcol = b4_role_of(nm + up, (int)strlen(nm + up));
+}
+static int b4_rhs_role(int k)     /* k in [B4S_MAT_COUNT, B4S_COUNT) */
+{
+    const char *nm = b4_stamp_names[k];
+    return b4_role_of(nm, (int)strlen(nm));
+}
+
+/* is the matrix position allocated by BSIM4setup for these selectors (b4set.c:2587-2676)? */
+static int b4_pos_allocated(int k, int rgateMod, int rbodyMod, int rdsMod)
+{
+    if (k >= B4S_GEge && k <= B4S_BPgm) return rgateMod != 0 || (k >= B4S_GPgp && k <= B4S_GPbp);
+    if (k >= B4S_Dgp && k <= B4S_Sbp) return rdsMod != 0;
+    if (k >= B4S_DPdb && k <= B4S_Bb) return rbodyMod == 1 || rbodyMod == 2;
+    return 1;
+}
+/* does the load write the position (b4ld.c:5235-5388, trnqsMod == 0)? */
+static int b4_pos_written(int k, int rgateMod, int rbodyMod, int rdsMod)
+{
+    if (k >= B4S_MAT_COUNT) {
+        switch (k) {
+        case B4R_dp: case B4R_gp: case B4R_bp: case B4R_sp: return 1;
+        case B4R_ge: return rgateMod == 2;
+        case B4R_gm: return rgateMod == 3;
+        case B4R_db: case B4R_sb: return rbodyMod != 0;
+        case B4R_d: case B4R_s: return rdsMod != 0;
+        default: return 0;   /* q */
+        }
+    }
+    if (k >= B4S_GPgp && k <= B4S_GPbp) return 1;
+    switch (k) {
+    case B4S_GEge: case B4S_GPge: return rgateMod == 1 || rgateMod == 2 || (k == B4S_GEge && rgateMod == 3);
+    case B4S_GEgp: return rgateMod == 1 || rgateMod == 2;
+    case B4S_GEdp: case B4S_GEsp: case B4S_GEbp: return rgateMod == 2;
+    case B4S_GEgm: case B4S_GMge: case B4S_GMgm: case B4S_GMdp: case B4S_GMgp: case B4S_GMsp:
+    case B4S_GMbp: case B4S_DPgm: case B4S_GPgm: case B4S_SPgm: case B4S_BPgm: return rgateMod == 3;
+    default: break;
+    }
+    if (k >= B4S_Dgp && k <= B4S_Sbp) return rdsMod != 0;
+    if (k >= B4S_DPdb && k <= B4S_Bb) return rbodyMod != 0;
+    if (k >= B4S_Qq && k <= B4S_GPq) return 0;
+    return 1;
+}
+
+/* ------------------------------------------------------------------ small containers */
+typedef struct { int *v; int n, cap; } ivec;
+static void iv_push(ivec *a, int x)
+{
+    if (a->n == a->cap) { a->cap = a->cap ? a->cap * 2 : 256; a->v = (int *)realloc(a->v, sizeof(int) * (size_t)a->cap); }
+    a->v[a->n++] = x;
+}
+static void *xcalloc(size_t n, size_t sz) { void *p = calloc(n ? n : 1, sz); if (!p) { fprintf(stderr, "ngb: out of memory\n"); abort(); } return p; }
+static void *xdup(const void *src, size_t bytes) { void *p = xcalloc(bytes ? bytes : 1, 1); if (bytes) memcpy(p, src, bytes); return p; }
+
+/* ------------------------------------------------------------------ circuit */
+ngb_circuit *ngbCircuitCreate(int neq, const int *node_type)
+{
+    ngb_circuit *c = (ngb_circuit *)xcalloc(1, sizeof *c);
+    int i;
+    c->neq = neq;
+    c->node_type = (int *)xcalloc((size_t)neq + 1, sizeof(int));
+    for (i = 0; i <= neq; i++) c->node_type[i] = node_type ? node_type[i] : 3;
+    /* defaults of cktntask.c:95-146 */
+    c->opt.reltol = 1e-3; c->opt.abstol = 1e-12; c->opt.vntol = 1e-6; c->opt.chgtol = 1e-14;
+    c->opt.trtol = 7; c->opt.temp = 300.15; c->opt.vt0 = 1.38064852e-23 * (27.0 + 273.15) / 1.6021766208e-19;
+    c->opt.xmu = 0.5; c->opt.gmin = 1e-12; c->opt.method = NGB_TRAPEZOIDAL; c->opt.maxorder = 2;
+    c->opt.itl4 = 10; c->opt.itl1 = 100;
+    return c;
+}
+
+static void free_sched(NgbLuSched *h)
+{
+#define F(p) free((void *)h->p)
+    F(lev_ptr); F(lev_ent); F(e_aslot); F(e_arow); F(e_div); F(e_pptr); F(pair_l); F(pair_u);
+    F(diag_v); F(row_ptr); F(row_slot); F(slev_ptr); F(slev_task); F(t_kind); F(t_init); F(t_div);
+    F(t_pptr); F(t_val); F(t_src); F(b_eq); F(out_task); F(out_eq);
+#undef F
+    memset(h, 0, sizeof *h);
+}
+
+void ngbCircuitDestroy(ngb_circuit *c)
+{
+    if (!c) return;
+    free(c->node_type);
+    free(c->b4_nodes); free(c->b4_flags); free(c->b4_prow); free(c->b4_inst); free(c->b4_mtab); free(c->b4_ptab);
+    free(c->b4_spos); free(c->b4_slots);
+    free(c->res_nodes); free(c->res_g); free(c->res_spos);
+    free(c->cap_nodes); free(c->cap_par); free(c->cap_spos);
+    free(c->vs_nodes); free(c->vs_fn); free(c->vs_par); free(c->vs_spos); free(c->vs_cspos);
+    free(c->is_nodes); free(c->is_fn); free(c->is_par); free(c->is_spos);
+    free(c->Ap); free(c->Ai); free(c->eq2col); free(c->col2eq); free(c->slot_diag); free(c->diag_slot);
+    free(c->tgt_ptr); free(c->tgt_rows); free(c->const_row); free(c->const_val);
+    free(c->klu_Q); free(c->klu_R); free(c->klu_Pnum);
+    free_sched(&c->sch);
+    free(c);
+}
+
+int ngbCircuitSetOptions(ngb_circuit *c, const double d[15], const int i[5])
+{
+    NgbOpts *o = &c->opt;
+    o->reltol = d[0]; o->abstol = d[1]; o->vntol = d[2]; o->chgtol = d[3]; o->trtol = d[4];
+    o->temp = d[5]; o->vt0 = d[6]; o->xmu = d[7]; o->tstep = d[8]; o->tstop = d[9]; o->tmax = d[10];
+    o->tstart = d[11]; o->delmin = d[12]; o->minbreak = d[13]; o->gmin = d[14];
+    o->method = i[0]; o->maxorder = i[1]; o->itl4 = i[2]; o->itl1 = i[3]; o->uic = i[4];
+    if (o->method != NGB_TRAPEZOIDAL) { ngb_set_error("integration method %d not supported (TRAP only)", o->method); return NGB_E_METHOD; }
+    if (o->maxorder > 2) { ngb_set_error("maxord %d not supported with TRAP", o->maxorder); return NGB_E_ORDER; }
+    return NGB_OK;
+}
+
+int ngbCircuitAddBsim4(ngb_circuit *c, int n, const int *nodes, const int *flags, const int *prow,
+                       const double *inst, int nrows, const double *mtab, const double *ptab)
+{
+    int i;
+    if (c->finalized || c->b4_n) { ngb_set_error("BSIM4 table already set"); return NGB_E_PANIC; }
+    for (i = 0; i < n; i++) {
+        if (flags[i] & 0x300) { ngb_set_error("BSIM4 instance %d: trnqsMod/acnqsMod != 0 is not supported on this path", i); return NGB_E_UNSUPP; }
+        if (prow[i] < 0 || prow[i] >= nrows) { ngb_set_error("BSIM4 instance %d: bad parameter row", i); return NGB_E_PANIC; }
+    }
+    c->b4_n = n; c->b4_nrows = nrows;
+    c->b4_nodes = (int *)xdup(nodes, sizeof(int) * (size_t)n * B4N_COUNT);
+    c->b4_flags = (int *)xdup(flags, sizeof(int) * (size_t)n);
+    c->b4_prow = (int *)xdup(prow, sizeof(int) * (size_t)n);
+    c->b4_inst = (double *)xdup(inst, sizeof(double) * (size_t)n * B4I_COUNT);
+    c->b4_mtab = (double *)xdup(mtab, sizeof(double) * (size_t)nrows * B4M_COUNT);
+    c->b4_ptab = (double *)xdup(ptab, sizeof(double) * (size_t)nrows * B4P_COUNT);
+    return NGB_OK;
+}
+int ngbCircuitAddResistors(ngb_circuit *c, int n, const int *nodes, const double *g)
+{
+    if (c->finalized || c->res_n) return NGB_E_PANIC;
+    c->res_n = n; c->res_nodes = (int *)xdup(nodes, sizeof(int) * 2 * (size_t)n);
+    c->res_g = (double *)xdup(g, sizeof(double) * (size_t)n);
+    return NGB_OK;
+}
+int ngbCircuitAddCapacitors(ngb_circuit *c, int n, const int *nodes, const double *par)
+{
+    if (c->finalized || c->cap_n) return NGB_E_PANIC;
+    c->cap_n = n; c->cap_nodes = (int *)xdup(nodes, sizeof(int) * 2 * (size_t)n);
+    c->cap_par = (double *)xdup(par, sizeof(double) * 3 * (size_t)n);
+    return NGB_OK;
+}
+int ngbCircuitAddVsources(ngb_circuit *c, int n, const int *nodes, const int *fn, const double *par)
+{
+    int i;
+    if (c->finalized || c->vs_n) return NGB_E_PANIC;
+    for (i = 0; i < n; i++)
+        if (fn[i] != 0 && fn[i] != NGB_FN_PULSE && fn[i] != NGB_FN_SINE) {
+            ngb_set_error("voltage source %d: waveform type %d not supported (DC, PULSE, SIN)", i, fn[i]);
+            return NGB_E_UNSUPP;
+        }
+    c->vs_n = n; c->vs_nodes = (int *)xdup(nodes, sizeof(int) * 3 * (size_t)n);
+    c->vs_fn = (int *)xdup(fn, sizeof(int) * 3 * (size_t)n);
+    c->vs_par = (double *)xdup(par, sizeof(double) * 9 * (size_t)n);
+    return NGB_OK;
+}
+int ngbCircuitAddIsources(ngb_circuit *c, int n, const int *nodes, const int *fn, const double *par)
+{
+    int i;
+    if (c->finalized || c->is_n) return NGB_E_PANIC;
+    for (i = 0; i < n; i++)
+        if (fn[i] != 0 && fn[i] != NGB_FN_PULSE && fn[i] != NGB_FN_SINE) {
+            ngb_set_error("current source %d: waveform type %d not supported (DC, PULSE, SIN)", i, fn[i]);
+            return NGB_E_UNSUPP;
+        }
+    c->is_n = n; c->is_nodes = (int *)xdup(nodes, sizeof(int) * 2 * (size_t)n);
+    c->is_fn = (int *)xdup(fn, sizeof(int) * 3 * (size_t)n);
+    c->is_par = (double *)xdup(par, sizeof(double) * 10 * (size_t)n);
+    return NGB_OK;
+}
+
+/* ---- pattern ---- */
+typedef struct { int row, col; } coo_t;
+static int coo_cmp(const void *a, const void *b)
+{
+    const coo_t *x = (const coo_t *)a, *y = (const coo_t *)b;
+    if (x->col != y->col) return x->col < y->col ? -1 : 1;
+    if (x->row != y->row) return x->row < y->row ? -1 : 1;
+    return 0;
+}
+typedef struct { coo_t *v; int n, cap; } coovec;
+static void coo_push(coovec *a, int r, int cl)
+{
+    if (r <= 0 || cl <= 0) return;               /* ground row/column: the trash cell of SMPmakeElt */
+    if (a->n == a->cap) { a->cap = a->cap ? a->cap * 2 : 1024; a->v = (coo_t *)realloc(a->v, sizeof(coo_t) * (size_t)a->cap); }
+    a->v[a->n].row = r - 1; a->v[a->n].col = cl - 1; a->n++;
+}
+static int slot_lookup(const ngb_circuit *c, int req, int ceq)
+{
+    int col, row, lo, hi;
+    if (req <= 0 || ceq <= 0) return -1;
+    col = c->eq2col[ceq]; row = c->eq2col[req];
+    if (col < 0 || row < 0) return -1;
+    lo = c->Ap[col]; hi = c->Ap[col + 1] - 1;
+    while (lo <= hi) { int mid = (lo + hi) / 2; if (c->Ai[mid] == row) return mid; if (c->Ai[mid] < row) lo = mid + 1; else hi = mid - 1; }
+    return -1;
+}
+
+typedef struct { ivec tgt, row; } contribs;
+static int new_row(ngb_circuit *c, contribs *cb, int target)
+{
+    int r;
+    if (target < 0) return -1;
+    r = c->nstamp_rows++;
+    iv_push(&cb->tgt, target); iv_push(&cb->row, r);
+    return r;
+}
+
+int ngbCircuitFinalize(ngb_circuit *c)
+{
+    coovec coo = { 0, 0, 0 };
+    contribs cb = { { 0, 0, 0 }, { 0, 0, 0 } };
+    ivec crow = { 0, 0, 0 };
+    double *cval = NULL; int ncval = 0, capcval = 0;
+    int i, k, n, ncol;
+    int *used;
+    if (c->finalized) return NGB_OK;
+
+    /* 1. structural entries, as the DEVsetup routines would request them */
+    for (i = 0; i < c->b4_n; i++) {
+        const int fl = c->b4_flags[i];
+        const int rg = B4F_RGATE(fl), rb = B4F_RBODY(fl);
+        const int rds = (int)c->b4_mtab[(size_t)c->b4_prow[i] * B4M_COUNT + B4M_rdsMod];
+        for (k = 0; k < B4S_MAT_COUNT; k++) {
+            int rr, rc;
+            if (!b4_pos_allocated(k, rg, rb, rds)) continue;
+            b4_stamp_roles(k, &rr, &rc);
+            coo_push(&coo, c->b4_nodes[rr * c->b4_n + i], c->b4_nodes[rc * c->b4_n + i]);
+        }
+    }
+    for (i = 0; i < c->cap_n; i++) {
+        int p = c->cap_nodes[i], q = c->cap_nodes[c->cap_n + i];
+        coo_push(&coo, p, p); coo_push(&coo, q, q); coo_push(&coo, p, q); coo_push(&coo, q, p);
+    }
+    for (i = 0; i < c->res_n; i++) {
+        int p = c->res_nodes[i], q = c->res_nodes[c->res_n + i];
+        coo_push(&coo, p, p); coo_push(&coo, q, q); coo_push(&coo, p, q); coo_push(&coo, q, p);
+    }
+    for (i = 0; i < c->vs_n; i++) {
+        int p = c->vs_nodes[i], q = c->vs_nodes[c->vs_n + i], br = c->vs_nodes[2 * c->vs_n + i];
+        coo_push(&coo, p, br); coo_push(&coo, q, br); coo_push(&coo, br, q); coo_push(&coo, br, p);
+    }
+    if (coo.n == 0) { ngb_set_error("empty matrix"); return NGB_E_PANIC; }
+
+    /* 2. COO -> CSC: sort by column then row, drop empty columns ("node collapsing"), dedup */
+    qsort(coo.v, (size_t)coo.n, sizeof(coo_t), coo_cmp);
+    ncol = coo.v[coo.n - 1].col + 1;
+    used = (int *)xcalloc((size_t)c->neq + 2, sizeof(int));
+    for (i = 0; i < coo.n; i++) used[coo.v[i].col] = 1;
+    c->eq2col = (int *)xcalloc((size_t)c->neq + 2, sizeof(int));
+    c->col2eq = (int *)xcalloc((size_t)ncol + 1, sizeof(int));
+    c->eq2col[0] = -1;
+    n = 0;
+    for (i = 0; i < c->neq; i++) {
+        if (i < ncol && used[i]) { c->eq2col[i + 1] = n; c->col2eq[n] = i + 1; n++; }
+        else c->eq2col[i + 1] = -1;
+    }
+    free(used);
+    c->n = n;
+    c->Ap = (int *)xcalloc((size_t)n + 1, sizeof(int));
+    c->Ai = (int *)xcalloc((size_t)coo.n, sizeof(int));
+    c->nnz = 0;
+    {
+        int prev_r = -1, prev_c = -1;
+        for (i = 0; i < coo.n; i++) {
+            int cc = c->eq2col[coo.v[i].col + 1], rr = c->eq2col[coo.v[i].row + 1];
+            if (rr < 0) { ngb_set_error("row %d has entries but its column is structurally empty", coo.v[i].row + 1); free(coo.v); return NGB_E_PANIC; }
+            if (cc == prev_c && rr == prev_r) continue;
+            c->Ai[c->nnz] = rr; c->Ap[cc + 1] = c->nnz + 1; c->nnz++;
+            prev_r = rr; prev_c = cc;
+        }
+        for (i = 0; i < n; i++) if (c->Ap[i + 1] < c->Ap[i]) c->Ap[i + 1] = c->Ap[i];
+    }
+    free(coo.v);
+    c->slot_diag = (int *)xcalloc((size_t)c->nnz, sizeof(int));
+    c->diag_slot = (int *)xcalloc((size_t)n, sizeof(int));
+    for (i = 0; i < n; i++) {
+        int p; c->diag_slot[i] = -1;
+        for (p = c->Ap[i]; p < c->Ap[i + 1]; p++) if (c->Ai[p] == i) { c->slot_diag[p] = 1; c->diag_slot[i] = p; }
+    }
+
+    /* 3. stamp rows and contribution lists, in CKTload order: device types by their rank in
+     *    the reference device table (bsim4 < cap < isrc < res < vsrc, dev.c:142-209), instances
+     *    in list order, positions in load order */
+    c->nstamp_rows = 0;
+    c->b4_spos = (int *)xcalloc((size_t)c->b4_n * B4S_COUNT, sizeof(int));
+    c->b4_slots = (int *)xcalloc((size_t)c->b4_n * B4S_MAT_COUNT, sizeof(int));
+    for (i = 0; i < c->b4_n; i++) {
+        const int fl = c->b4_flags[i];
+        const int rg = B4F_RGATE(fl), rb = B4F_RBODY(fl);
+        const int rds = (int)c->b4_mtab[(size_t)c->b4_prow[i] * B4M_COUNT + B4M_rdsMod];
+        /* right-hand side first, then matrix (b4ld.c:5024-5053 then :5235-5388) */
+        for (k = B4S_MAT_COUNT; k < B4S_COUNT; k++) {
+            int eq = c->b4_nodes[b4_rhs_role(k) * c->b4_n + i];
+            c->b4_spos[k * c->b4_n + i] = (b4_pos_written(k, rg, rb, rds) && eq > 0 && c->eq2col[eq] >= 0)
+                                        ? new_row(c, &cb, c->nnz + eq) : -1;
+        }
+        for (k = 0; k < B4S_MAT_COUNT; k++) {
+            int rr, rc, slot = -1;
+            b4_stamp_roles(k, &rr, &rc);
+            if (b4_pos_allocated(k, rg, rb, rds))
+                slot = slot_lookup(c, c->b4_nodes[rr * c->b4_n + i], c->b4_nodes[rc * c->b4_n + i]);
+            c->b4_slots[k * c->b4_n + i] = slot;
+            c->b4_spos[k * c->b4_n + i] = (slot >= 0 && b4_pos_written(k, rg, rb, rds)) ? new_row(c, &cb, slot) : -1;
+        }
+    }
+    c->cap_spos = (int *)xcalloc((size_t)c->cap_n * 6 + 1, sizeof(int));
+    for (i = 0; i < c->cap_n; i++) {
+        int p = c->cap_nodes[i], q = c->cap_nodes[c->cap_n + i], nn = c->cap_n;
+        c->cap_spos[0 * nn + i] = new_row(c, &cb, slot_lookup(c, p, p));
+        c->cap_spos[1 * nn + i] = new_row(c, &cb, slot_lookup(c, q, q));
+        c->cap_spos[2 * nn + i] = new_row(c, &cb, slot_lookup(c, p, q));
+        c->cap_spos[3 * nn + i] = new_row(c, &cb, slot_lookup(c, q, p));
+        c->cap_spos[4 * nn + i] = new_row(c, &cb, p > 0 ? c->nnz + p : -1);
+        c->cap_spos[5 * nn + i] = new_row(c, &cb, q > 0 ? c->nnz + q : -1);
+    }
+    c->is_spos = (int *)xcalloc((size_t)c->is_n * 2 + 1, sizeof(int));
+    for (i = 0; i < c->is_n; i++) {
+        int p = c->is_nodes[i], q = c->is_nodes[c->is_n + i];
+        c->is_spos[i] = new_row(c, &cb, p > 0 ? c->nnz + p : -1);
+        c->is_spos[c->is_n + i] = new_row(c, &cb, q > 0 ? c->nnz + q : -1);
+    }
+#define CONST_ROW(target, value) do { int r_ = new_row(c, &cb, (target)); if (r_ >= 0) { iv_push(&crow, r_); \
+        if (ncval == capcval) { capcval = capcval ? capcval * 2 : 256; cval = (double *)realloc(cval, sizeof(double) * (size_t)capcval); } \
+        cval[ncval++] = (value); } } while (0)
+    c->res_spos = (int *)xcalloc((size_t)c->res_n * 4 + 1, sizeof(int));
+    for (i = 0; i < c->res_n; i++) {
+        int p = c->res_nodes[i], q = c->res_nodes[c->res_n + i];
+        double g = c->res_g[i];
+        CONST_ROW(slot_lookup(c, p, p), g); CONST_ROW(slot_lookup(c, q, q), g);
+        CONST_ROW(slot_lookup(c, p, q), -g); CONST_ROW(slot_lookup(c, q, p), -g);
+    }
+    c->vs_spos = (int *)xcalloc((size_t)c->vs_n + 1, sizeof(int));
+    c->vs_cspos = (int *)xcalloc((size_t)c->vs_n * 4 + 1, sizeof(int));
+    for (i = 0; i < c->vs_n; i++) {
+        int p = c->vs_nodes[i], q = c->vs_nodes[c->vs_n + i], br = c->vs_nodes[2 * c->vs_n + i];
+        CONST_ROW(slot_lookup(c, p, br), 1.0); CONST_ROW(slot_lookup(c, q, br), -1.0);
+        CONST_ROW(slot_lookup(c, br, p), 1.0); CONST_ROW(slot_lookup(c, br, q), -1.0);
+        c->vs_spos[i] = new_row(c, &cb, br > 0 ? c->nnz + br : -1);
+    }
+#undef CONST_ROW
+    c->nconst = crow.n; c->const_row = crow.v; c->const_val = cval;
+
+    /* 4. contributions -> per-target lists (stable: keeps load order inside each target) */
+    c->ntgt = c->nnz + c->neq + 1;
+    c->tgt_ptr = (int *)xcalloc((size_t)c->ntgt + 1, sizeof(int));
+    c->tgt_rows = (int *)xcalloc((size_t)cb.tgt.n, sizeof(int));
+    for (i = 0; i < cb.tgt.n; i++) c->tgt_ptr[cb.tgt.v[i] + 1]++;
+    for (i = 0; i < c->ntgt; i++) c->tgt_ptr[i + 1] += c->tgt_ptr[i];
+    {
+        int *fill = (int *)xdup(c->tgt_ptr, sizeof(int) * ((size_t)c->ntgt + 1));
+        for (i = 0; i < cb.tgt.n; i++) c->tgt_rows[fill[cb.tgt.v[i]]++] = cb.row.v[i];
+        free(fill);
+    }
+    free(cb.tgt.v); free(cb.row.v);
+    c->finalized = 1;
+    return NGB_OK;
+}
+
+int ngbCircuitPatternSize(const ngb_circuit *c, int *n, int *nnz, int *nrows)
+{
+    if (!c->finalized) return NGB_E_PANIC;
+    if (n) *n = c->n;
+    if (nnz) *nnz = c->nnz;
+    if (nrows) *nrows = c->nstamp_rows;
+    return NGB_OK;
+}
+int ngbCircuitGetPattern(const ngb_circuit *c, int *Ap, int *Ai, int *diag)
+{
+    if (!c->finalized) return NGB_E_PANIC;
+    if (Ap) memcpy(Ap, c->Ap, sizeof(int) * ((size_t)c->n + 1));
+    if (Ai) memcpy(Ai, c->Ai, sizeof(int) * (size_t)c->nnz);
+    if (diag) memcpy(diag, c->diag_slot, sizeof(int) * (size_t)c->n);
+    return NGB_OK;
+}
+int ngbCircuitGetBsim4Slots(const ngb_circuit *c, int *slots)
+{
+    if (!c->finalized) return NGB_E_PANIC;
+    memcpy(slots, c->b4_slots, sizeof(int) * (size_t)c->b4_n * B4S_MAT_COUNT);
+    return NGB_OK;
+}
+
+/* ------------------------------------------------------------------ LU task schedule */
+int ngbCircuitSetLuPattern(ngb_circuit *c, int n, int nblocks, const int *Q, const int *R, const int *Pnum,
+                           const int *Lp, const int *Li, const int *Up, const int *Ui,
+                           const int *Offp, const int *Offi)
+{
+    NgbLuSched *h = &c->sch;
+    const int lnz = Lp[n], unz = Up[n], nzoff = Offp[n];
+    const int nV = unz + lnz + n + nzoff;
+    const int idL = unz, idD = unz + lnz, idO = unz + lnz + n;
+    int *Pinv, *e_aslot, *e_arow, *e_div, *e_pptr, *pl, *pu, *pos, *level, *diag_v;
+    int b, k, p, poff = 0, npairs = 0, pass, nlev = 0;
+    if (!c->finalized) { ngb_set_error("circuit not finalized"); return NGB_E_PANIC; }
+    if (n != c->n) { ngb_set_error("LU pattern order %d != matrix order %d", n, c->n); return NGB_E_PANIC; }
+    free_sched(h);
+    free(c->klu_Q); free(c->klu_R); free(c->klu_Pnum);
+    c->klu_Q = (int *)xdup(Q, sizeof(int) * (size_t)n); c->klu_R = (int *)xdup(R, sizeof(int) * ((size_t)nblocks + 1));
+    c->klu_Pnum = (int *)xdup(Pnum, sizeof(int) * (size_t)n); c->klu_nblocks = nblocks;
+    c->lnz = lnz; c->unz = unz; c->nzoff = nzoff;
+
+    Pinv = (int *)xcalloc((size_t)n, sizeof(int));
+    for (k = 0; k < n; k++) Pinv[Pnum[k]] = k;
+    e_aslot = (int *)xcalloc((size_t)nV, sizeof(int)); e_arow = (int *)xcalloc((size_t)nV, sizeof(int));
+    e_div = (int *)xcalloc((size_t)nV, sizeof(int)); e_pptr = (int *)xcalloc((size_t)nV + 1, sizeof(int));
+    diag_v = (int *)xcalloc((size_t)n, sizeof(int));
+    pos = (int *)xcalloc((size_t)n, sizeof(int));
+    level = (int *)xcalloc((size_t)nV, sizeof(int));
+    for (k = 0; k < nV; k++) { e_aslot[k] = -1; e_div[k] = -1; }
+    for (k = 0; k < n; k++) { pos[k] = -1; diag_v[k] = idD + k; }
+
+    /* A -> entry map: the scatter loops of klu_refactor.c:300-372 */
+    for (b = 0; b < nblocks; b++) {
+        const int k1 = R[b], k2 = R[b + 1];
+        for (k = k1; k < k2; k++) {
+            const int oldcol = Q[k];
+            if (k2 - k1 > 1) {
+                for (p = Up[k]; p < Up[k + 1]; p++) pos[Ui[p]] = p;
+                for (p = Lp[k]; p < Lp[k + 1]; p++) pos[Li[p]] = idL + p;
+            }
+            pos[k] = idD + k;
+            for (p = c->Ap[oldcol]; p < c->Ap[oldcol + 1]; p++) {
+                const int oldrow = c->Ai[p], newrow = Pinv[oldrow];
+                int e;
+                if (newrow < k1 && poff < nzoff) {
+                    if (Offi[poff] != newrow) { ngb_set_error("off-diagonal pattern mismatch at column %d", k); goto bad; }
+                    e = idO + poff; poff++;
+                } else {
+                    e = (newrow >= k1 && newrow < k2) ? pos[newrow] : -1;
+                    if (e < 0) { ngb_set_error("A(%d,%d) has no place in the LU pattern", oldrow, oldcol); goto bad; }
+                }
+                e_aslot[e] = p; e_arow[e] = oldrow;
+            }
+            if (k2 - k1 > 1) {
+                for (p = Up[k]; p < Up[k + 1]; p++) pos[Ui[p]] = -1;
+                for (p = Lp[k]; p < Lp[k + 1]; p++) { pos[Li[p]] = -1; e_div[idL + p] = idD + k; }
+            }
+            pos[k] = -1;
+        }
+    }
+    if (poff != nzoff) { ngb_set_error("off-diagonal count mismatch (%d != %d)", poff, nzoff); goto bad; }
+
+    /* pairs in the order of the column loop of klu_refactor.c:377-389; two passes (count, fill) */
+    pl = pu = NULL;
+    for (pass = 0; pass < 2; pass++) {
+        int *cursor = NULL;
+        if (pass == 1) {
+            int acc = 0;
+            for (k = 0; k < nV; k++) { int cnt = e_pptr[k + 1]; e_pptr[k] = acc; acc += cnt; }
+            /* shift: e_pptr[k+1] held counts of entry k */
+            e_pptr[nV] = acc; npairs = acc;
+            pl = (int *)xcalloc((size_t)npairs, sizeof(int)); pu = (int *)xcalloc((size_t)npairs, sizeof(int));
+            cursor = (int *)xdup(e_pptr, sizeof(int) * ((size_t)nV + 1));
+        }
+        for (b = 0; b < nblocks; b++) {
+            const int k1 = R[b], k2 = R[b + 1];
+            if (k2 - k1 == 1) continue;
+            for (k = k1; k < k2; k++) {
+                int up;
+                for (p = Up[k]; p < Up[k + 1]; p++) pos[Ui[p]] = p;
+                for (p = Lp[k]; p < Lp[k + 1]; p++) pos[Li[p]] = idL + p;
+                pos[k] = idD + k;
+                for (up = Up[k]; up < Up[k + 1]; up++) {
+                    const int j = Ui[up];
+                    for (p = Lp[j]; p < Lp[j + 1]; p++) {
+                        const int tgt = pos[Li[p]];
+                        if (tgt < 0) { ngb_set_error("fill outside the LU pattern (col %d)", k); free(cursor); free(pl); free(pu); goto bad; }
+                        if (pass == 0) e_pptr[tgt + 1]++;
+                        else {
+                            pl[cursor[tgt]] = idL + p; pu[cursor[tgt]] = up; cursor[tgt]++;
+                            if (level[idL + p] + 1 > level[tgt]) level[tgt] = level[idL + p] + 1;
+                            if (level[up] + 1 > level[tgt]) level[tgt] = level[up] + 1;
+                        }
+                    }
+                }
+                if (pass == 1) {
+                    /* L entries wait for their pivot */
+                    for (p = Lp[k]; p < Lp[k + 1]; p++)
+                        if (level[idD + k] + 1 > level[idL + p]) level[idL + p] = level[idD + k] + 1;
+                }
+                for (p = Up[k]; p < Up[k + 1]; p++) pos[Ui[p]] = -1;
+                for (p = Lp[k]; p < Lp[k + 1]; p++) pos[Li[p]] = -1;
+                pos[k] = -1;
+            }
+        }
+        free(cursor);
+    }
+    /* NOTE on level correctness: within column k the U entries are visited in topological
+     * order, so when pair (L(i,j), U(j,k)) raises level[target] the level of U(j,k) is final. */
+    for (k = 0; k < nV; k++) if (level[k] + 1 > nlev) nlev = level[k] + 1;
+    h->lev_ptr = (int *)xcalloc((size_t)nlev + 1, sizeof(int));
+    h->lev_ent = (int *)xcalloc((size_t)nV, sizeof(int));
+    {
+        int *lp = (int *)h->lev_ptr, *le = (int *)h->lev_ent, *fill;
+        for (k = 0; k < nV; k++) lp[level[k] + 1]++;
+        for (k = 0; k < nlev; k++) lp[k + 1] += lp[k];
+        fill = (int *)xdup(lp, sizeof(int) * ((size_t)nlev + 1));
+        for (k = 0; k < nV; k++) le[fill[level[k]]++] = k;
+        free(fill);
+    }
+    h->n = n; h->nnz = c->nnz; h->nV = nV; h->nlev = nlev;
+    h->e_aslot = e_aslot; h->e_arow = e_arow; h->e_div = e_div; h->e_pptr = e_pptr;
+    h->pair_l = pl; h->pair_u = pu; h->diag_v = diag_v;
+    c->npairs = npairs;
+
+    /* CSR view of A for the row scale factors */
+    {
+        int *rp = (int *)xcalloc((size_t)n + 1, sizeof(int)), *rs = (int *)xcalloc((size_t)c->nnz, sizeof(int)), *fill;
+        for (p = 0; p < c->nnz; p++) rp[c->Ai[p] + 1]++;
+        for (k = 0; k < n; k++) rp[k + 1] += rp[k];
+        fill = (int *)xdup(rp, sizeof(int) * ((size_t)n + 1));
+        for (k = 0; k < n; k++) for (p = c->Ap[k]; p < c->Ap[k + 1]; p++) rs[fill[c->Ai[p]]++] = p;
+        free(fill);
+        h->row_ptr = rp; h->row_slot = rs;
+    }
+
+    /* triangular solves: tasks y_i = i, x_i = n + i; pairs appended in the chronological order of
+     * klu_solve.c (blocks last to first: L solve, U solve, off-diagonal update) */
+    {
+        const int ntask = 2 * n;
+        int *t_kind = (int *)xcalloc((size_t)ntask, sizeof(int)), *t_init = (int *)xcalloc((size_t)ntask, sizeof(int));
+        int *t_div = (int *)xcalloc((size_t)ntask, sizeof(int)), *t_pptr = (int *)xcalloc((size_t)ntask + 1, sizeof(int));
+        int *tl = (int *)xcalloc((size_t)ntask, sizeof(int));
+        int *t_val = NULL, *t_src = NULL, nsp = 0, nslev = 0;
+        for (k = 0; k < n; k++) {
+            t_kind[k] = 0; t_init[k] = Pnum[k]; t_div[k] = -1;
+            t_kind[n + k] = 1; t_init[n + k] = k; t_div[n + k] = idD + k;
+        }
+        for (pass = 0; pass < 2; pass++) {
+            int *cursor = NULL;
+            if (pass == 1) {
+                int acc = 0;
+                for (k = 0; k < ntask; k++) { int cnt = t_pptr[k + 1]; t_pptr[k] = acc; acc += cnt; }
+                t_pptr[ntask] = acc; nsp = acc;
+                t_val = (int *)xcalloc((size_t)nsp, sizeof(int)); t_src = (int *)xcalloc((size_t)nsp, sizeof(int));
+                cursor = (int *)xdup(t_pptr, sizeof(int) * ((size_t)ntask + 1));
+            }
+#define SOLVE_PAIR(tgt, val, src) do { if (pass == 0) t_pptr[(tgt) + 1]++; else { \
+                t_val[cursor[tgt]] = (val); t_src[cursor[tgt]] = (src); cursor[tgt]++; \
+                if (tl[src] + 1 > tl[tgt]) tl[tgt] = tl[src] + 1; } } while (0)
+            for (b = nblocks - 1; b >= 0; b--) {
+                const int k1 = R[b], k2 = R[b + 1];
+                if (k2 - k1 > 1) {
+                    for (k = k1; k < k2; k++)
+                        for (p = Lp[k]; p < Lp[k + 1]; p++) SOLVE_PAIR(Li[p], idL + p, k);
+                    for (k = k2 - 1; k >= k1; k--) {
+                        if (pass == 1 && tl[k] + 1 > tl[n + k]) tl[n + k] = tl[k] + 1;     /* x_k starts from y_k */
+                        for (p = Up[k]; p < Up[k + 1]; p++) SOLVE_PAIR(n + Ui[p], p, n + k);
+                    }
+                } else if (pass == 1) {
+                    if (tl[k1] + 1 > tl[n + k1]) tl[n + k1] = tl[k1] + 1;
+                }
+                if (b > 0)
+                    for (k = k1; k < k2; k++)
+                        for (p = Offp[k]; p < Offp[k + 1]; p++) SOLVE_PAIR(Offi[p], idO + p, n + k);
+            }
+#undef SOLVE_PAIR
+            free(cursor);
+        }
+        /* The level of x_k must be final before it feeds later rows.  Inside a block the U loop
+         * runs k descending and x_k receives pairs only from larger k, and y rows receive L pairs
+         * from smaller k before being used: the chronological sweep above is a valid order. */
+        for (k = 0; k < ntask; k++) if (tl[k] + 1 > nslev) nslev = tl[k] + 1;
+        {
+            int *sp = (int *)xcalloc((size_t)nslev + 1, sizeof(int)), *st = (int *)xcalloc((size_t)ntask, sizeof(int)), *fill;
+            for (k = 0; k < ntask; k++) sp[tl[k] + 1]++;
+            for (k = 0; k < nslev; k++) sp[k + 1] += sp[k];
+            fill = (int *)xdup(sp, sizeof(int) * ((size_t)nslev + 1));
+            for (k = 0; k < ntask; k++) st[fill[tl[k]]++] = k;
+            free(fill);
+            h->slev_ptr = sp; h->slev_task = st;
+        }
+        free(tl);
+        h->ntask = ntask; h->nslev = nslev; h->t_kind = t_kind; h->t_init = t_init; h->t_div = t_div;
+        h->t_pptr = t_pptr; h->t_val = t_val; h->t_src = t_src;
+        c->nsolvepairs = nsp;
+    }
+    {
+        int *b_eq = (int *)xcalloc((size_t)n, sizeof(int)), *ot = (int *)xcalloc((size_t)n, sizeof(int)), *oe = (int *)xcalloc((size_t)n, sizeof(int));
+        for (k = 0; k < n; k++) { b_eq[k] = c->col2eq[k]; ot[k] = n + k; oe[k] = c->col2eq[Q[k]]; }
+        h->b_eq = b_eq; h->out_task = ot; h->out_eq = oe;
+    }
+    free(Pinv); free(pos); free(level);
+    c->have_lu = 1;
+    return NGB_OK;
+bad:
+    free(Pinv); free(pos); free(level); free(e_aslot); free(e_arow); free(e_div); free(e_pptr); free(diag_v);
+    return NGB_E_PANIC;
+}
+
+int ngbCircuitLuInfo(const ngb_circuit *c, int info[9])
+{
+    if (!c->have_lu) return NGB_E_PANIC;
+    info[0] = c->sch.nV; info[1] = c->sch.nlev; info[2] = c->npairs; info[3] = c->sch.ntask;
+    info[4] = c->sch.nslev; info[5] = c->nsolvepairs; info[6] = c->lnz; info[7] = c->unz; info[8] = c->nzoff;
+    return NGB_OK;
+}
+
+/* ------------------------------------------------------------------ batch */
+static void *dev_dup(const void *host, size_t bytes)
+{
+    void *d = ngb_dev_malloc(bytes ? bytes : 8);
+    if (d && bytes) ngb_dev_h2d(d, host, bytes);
+    return d;
+}
+static void reg(ngb_batch *b, const char *name, void *ptr, size_t bytes)
+{
+    if (b->narr < NGB_MAX_ARR) { b->arr[b->narr].name = name; b->arr[b->narr].ptr = ptr; b->arr[b->narr].bytes = bytes; b->narr++; }
+}
+static void *dalloc(ngb_batch *b, const char *name, size_t bytes)
+{
+    void *p = ngb_dev_malloc(bytes ? bytes : 8);
+    if (!p) { ngb_set_error("device allocation of %zu bytes for %s failed", bytes, name); b->failed = 1; return NULL; }
+    reg(b, name, p, bytes);
+    return p;
+}
+/* replicate a [nf][n] host table to a [nf][n*S] device table (sample index fastest) */
+static void *dalloc_rep(ngb_batch *b, const char *name, const double *host, int nf, int n, int S)
+{
+    size_t T = (size_t)n * S, i; int f, s;
+    double *tmp = (double *)xcalloc((size_t)nf * T, sizeof(double)), *d;
+    for (f = 0; f < nf; f++) for (i = 0; i < (size_t)n; i++) for (s = 0; s < S; s++)
+        tmp[(size_t)f * T + i * S + s] = host[(size_t)f * n + i];
+    d = (double *)dalloc(b, name, sizeof(double) * (size_t)nf * T);
+    if (d) ngb_dev_h2d(d, tmp, sizeof(double) * (size_t)nf * T);
+    free(tmp);
+    return d;
+}
+
+static void sched_to_dev(ngb_batch *b, const ngb_circuit *c)
+{
+    const NgbLuSched *h = &c->sch; NgbLuSched *d = &b->dsch;
+    *d = *h;
+#define D(f, cnt) d->f = (const int *)dev_dup(h->f, sizeof(int) * (size_t)(cnt))
+    D(lev_ptr, h->nlev + 1); D(lev_ent, h->nV); D(e_aslot, h->nV); D(e_arow, h->nV); D(e_div, h->nV);
+    D(e_pptr, h->nV + 1); D(pair_l, c->npairs); D(pair_u, c->npairs); D(diag_v, h->n);
+    D(row_ptr, h->n + 1); D(row_slot, h->nnz); D(slev_ptr, h->nslev + 1); D(slev_task, h->ntask);
+    D(t_kind, h->ntask); D(t_init, h->ntask); D(t_div, h->ntask); D(t_pptr, h->ntask + 1);
+    D(t_val, c->nsolvepairs); D(t_src, c->nsolvepairs); D(b_eq, h->n); D(out_task, h->n); D(out_eq, h->n);
+#undef D
+}
+static void sched_dev_free(NgbLuSched *d)
+{
+#define F(p) ngb_dev_free((void *)d->p)
+    F(lev_ptr); F(lev_ent); F(e_aslot); F(e_arow); F(e_div); F(e_pptr); F(pair_l); F(pair_u);
+    F(diag_v); F(row_ptr); F(row_slot); F(slev_ptr); F(slev_task); F(t_kind); F(t_init); F(t_div);
+    F(t_pptr); F(t_val); F(t_src); F(b_eq); F(out_task); F(out_eq);
+#undef F
+    memset(d, 0, sizeof *d);
+}
+
+ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
+{
+    ngb_batch *b;
+    NgbCtl *k;
+    int i;
+    if (!c->finalized) { ngb_set_error("circuit not finalized"); return NULL; }
+    if (ngb_dev_init(device) != 0) { ngb_set_error("CUDA device %d could not be initialised (no CPU fallback)", device); return NULL; }
+    b = (ngb_batch *)xcalloc(1, sizeof *b);
+    b->c = c; b->S = S; b->neq1 = c->neq + 1;
+    k = &b->ctl; k->S = S;
+    k->mode = (int *)dalloc(b, "ctl.mode", sizeof(int) * (size_t)S);
+    k->active = (int *)dalloc(b, "ctl.active", sizeof(int) * (size_t)S);
+    k->head = (int *)dalloc(b, "ctl.head", sizeof(int) * (size_t)S);
+    k->order = (int *)dalloc(b, "ctl.order", sizeof(int) * (size_t)S);
+    k->noncon = (int *)dalloc(b, "ctl.noncon", sizeof(int) * (size_t)S);
+    k->xsel = (int *)dalloc(b, "ctl.xsel", sizeof(int) * (size_t)S);
+    k->err = (int *)dalloc(b, "ctl.err", sizeof(int) * (size_t)S);
+    k->ag0 = (double *)dalloc(b, "ctl.ag0", sizeof(double) * (size_t)S);
+    k->ag1 = (double *)dalloc(b, "ctl.ag1", sizeof(double) * (size_t)S);
+    k->delta = (double *)dalloc(b, "ctl.delta", sizeof(double) * (size_t)S);
+    k->delta_old = (double *)dalloc(b, "ctl.delta_old", sizeof(double) * 7 * (size_t)S);
+    k->time = (double *)dalloc(b, "ctl.time", sizeof(double) * (size_t)S);
+    k->gmin = (double *)dalloc(b, "ctl.gmin", sizeof(double) * (size_t)S);
+    k->diag_gmin = (double *)dalloc(b, "ctl.diag_gmin", sizeof(double) * (size_t)S);
+    k->srcfact = (double *)dalloc(b, "ctl.srcfact", sizeof(double) * (size_t)S);
+    {
+        int *one = (int *)xcalloc((size_t)S, sizeof(int)); double *dv = (double *)xcalloc((size_t)S, sizeof(double));
+        for (i = 0; i < S; i++) one[i] = 1;
+        ngb_dev_h2d(k->active, one, sizeof(int) * (size_t)S);
+        ngb_dev_h2d(k->order, one, sizeof(int) * (size_t)S);
+        for (i = 0; i < S; i++) dv[i] = c->opt.gmin;
+        ngb_dev_h2d(k->gmin, dv, sizeof(double) * (size_t)S);
+        for (i = 0; i < S; i++) dv[i] = 1.0;
+        ngb_dev_h2d(k->srcfact, dv, sizeof(double) * (size_t)S);
+        free(one); free(dv);
+    }
+    b->x = (double *)dalloc(b, "x", sizeof(double) * 2 * (size_t)b->neq1 * S);
+    b->Ax = (double *)dalloc(b, "Ax", sizeof(double) * (size_t)c->nnz * S);
+    b->stamp = (double *)dalloc(b, "stamp", sizeof(double) * (size_t)c->nstamp_rows * S);
+    b->errflag = (int *)dalloc(b, "errflag", sizeof(int) * 4);
+    b->d_node_type = (int *)dev_dup(c->node_type, sizeof(int) * (size_t)b->neq1);
+    b->d_tgt_ptr = (int *)dev_dup(c->tgt_ptr, sizeof(int) * ((size_t)c->ntgt + 1));
+    b->d_tgt_rows = (int *)dev_dup(c->tgt_rows, sizeof(int) * (size_t)c->tgt_ptr[c->ntgt]);
+    b->d_slot_diag = (int *)dev_dup(c->slot_diag, sizeof(int) * (size_t)c->nnz);
+    /* constant stamp rows (resistors, source incidence): written once */
+    if (c->nconst) {
+        double *row = (double *)xcalloc((size_t)S, sizeof(double));
+        for (i = 0; i < c->nconst; i++) {
+            int s; for (s = 0; s < S; s++) row[s] = c->const_val[i];
+            ngb_dev_h2d(b->stamp + (size_t)c->const_row[i] * S, row, sizeof(double) * (size_t)S);
+        }
+        free(row);
+    }
+    if (c->b4_n) {
+        const size_t T = (size_t)c->b4_n * S;
+        b->b4_inst = (double *)dalloc_rep(b, "b4.inst", c->b4_inst, B4I_COUNT, c->b4_n, S);
+        b->b4_state = (double *)dalloc(b, "b4.state", sizeof(double) * NGB_NHIST * B4ST_COUNT * T);
+        b->b4_op = (double *)dalloc(b, "b4.op", sizeof(double) * B4O_COUNT * T);
+        b->b4_mtab = (double *)dev_dup(c->b4_mtab, sizeof(double) * (size_t)c->b4_nrows * B4M_COUNT);
+        b->b4_ptab = (double *)dev_dup(c->b4_ptab, sizeof(double) * (size_t)c->b4_nrows * B4P_COUNT);
+        reg(b, "b4.mtab", b->b4_mtab, sizeof(double) * (size_t)c->b4_nrows * B4M_COUNT);
+        reg(b, "b4.ptab", b->b4_ptab, sizeof(double) * (size_t)c->b4_nrows * B4P_COUNT);
+        b->b4_prow = (int *)dev_dup(c->b4_prow, sizeof(int) * (size_t)c->b4_n);
+        b->b4_flags = (int *)dev_dup(c->b4_flags, sizeof(int) * (size_t)c->b4_n);
+        b->b4_nodes = (int *)dev_dup(c->b4_nodes, sizeof(int) * (size_t)c->b4_n * B4N_COUNT);
+        b->b4_spos = (int *)dev_dup(c->b4_spos, sizeof(int) * (size_t)c->b4_n * B4S_COUNT);
+    }
+    if (c->cap_n) {
+        const size_t T = (size_t)c->cap_n * S;
+        b->cap_par = (double *)dalloc_rep(b, "cap.par", c->cap_par, 3, c->cap_n, S);
+        b->cap_state = (double *)dalloc(b, "cap.state", sizeof(double) * NGB_NHIST * 2 * T);
+        b->cap_nodes = (int *)dev_dup(c->cap_nodes, sizeof(int) * 2 * (size_t)c->cap_n);
+        b->cap_spos = (int *)dev_dup(c->cap_spos, sizeof(int) * 6 * (size_t)c->cap_n);
+    }
+    if (c->vs_n) {
+        b->vs_par = (double *)dalloc_rep(b, "vsrc.par", c->vs_par, 9, c->vs_n, S);
+        b->vs_fn = (int *)dev_dup(c->vs_fn, sizeof(int) * 3 * (size_t)c->vs_n);
+        b->vs_spos = (int *)dev_dup(c->vs_spos, sizeof(int) * (size_t)c->vs_n);
+    }
+    if (c->is_n) {
+        b->is_par = (double *)dalloc_rep(b, "isrc.par", c->is_par, 10, c->is_n, S);
+        b->is_fn = (int *)dev_dup(c->is_fn, sizeof(int) * 3 * (size_t)c->is_n);
+        b->is_spos = (int *)dev_dup(c->is_spos, sizeof(int) * 2 * (size_t)c->is_n);
+    }
+    if (c->have_lu) {
+        sched_to_dev(b, c);
+        b->V = (double *)dalloc(b, "lu.V", sizeof(double) * (size_t)c->sch.nV * S);
+        b->Rs = (double *)dalloc(b, "lu.Rs", sizeof(double) * (size_t)c->sch.n * S);
+        b->nodeconv = (int *)dalloc(b, "lu.nodeconv", sizeof(int) * (size_t)S);
+        b->singular = (int *)dalloc(b, "lu.singular", sizeof(int) * (size_t)S);
+        b->have_lu = 1;
+    }
+    if (b->failed) { ngbBatchDestroy(b); return NULL; }
+    ngb_dev_sync();
+    return b;
+}
+
+void ngbBatchDestroy(ngb_batch *b)
+{
+    int i;
+    if (!b) return;
+    for (i = 0; i < b->narr; i++)
+        if (strcmp(b->arr[i].name, "b4.mtab") && strcmp(b->arr[i].name, "b4.ptab")) ngb_dev_free(b->arr[i].ptr);
+    ngb_dev_free(b->d_node_type); ngb_dev_free(b->d_tgt_ptr); ngb_dev_free(b->d_tgt_rows); ngb_dev_free(b->d_slot_diag);
+    ngb_dev_free(b->b4_mtab); ngb_dev_free(b->b4_ptab); ngb_dev_free(b->b4_prow); ngb_dev_free(b->b4_flags);
+    ngb_dev_free(b->b4_nodes); ngb_dev_free(b->b4_spos); ngb_dev_free(b->b4_prow_t);
+    ngb_dev_free(b->cap_nodes); ngb_dev_free(b->cap_spos);
+    ngb_dev_free(b->vs_fn); ngb_dev_free(b->vs_spos); ngb_dev_free(b->is_fn); ngb_dev_free(b->is_spos);
+    if (b->have_lu) sched_dev_free(&b->dsch);
+    ngb_tran_free(b);
+    free(b);
+}
+
+static int find_arr(ngb_batch *b, const char *name)
+{
+    int i;
+    for (i = 0; i < b->narr; i++) if (!strcmp(b->arr[i].name, name)) return i;
+    ngb_set_error("no device array named '%s'", name);
+    return -1;
+}
+long ngbBatchArrayBytes(ngb_batch *b, const char *name) { int i = find_arr(b, name); return i < 0 ? -1 : (long)b->arr[i].bytes; }
+void *ngbBatchDevPtr(ngb_batch *b, const char *name) { int i = find_arr(b, name); return i < 0 ? NULL : b->arr[i].ptr; }
+int ngbBatchUpload(ngb_batch *b, const char *name, const void *host, long bytes, long offset)
+{
+    int i = find_arr(b, name);
+    if (i < 0) return NGB_E_PANIC;
+    if (offset < 0 || (size_t)(offset + bytes) > b->arr[i].bytes) { ngb_set_error("upload to %s out of range", name); return NGB_E_PANIC; }
+    return ngb_dev_h2d((char *)b->arr[i].ptr + offset, host, (size_t)bytes);
+}
+int ngbBatchDownload(ngb_batch *b, const char *name, void *host, long bytes, long offset)
+{
+    int i = find_arr(b, name);
+    if (i < 0) return NGB_E_PANIC;
+    if (offset < 0 || (size_t)(offset + bytes) > b->arr[i].bytes) { ngb_set_error("download from %s out of range", name); return NGB_E_PANIC; }
+    return ngb_dev_d2h(host, (char *)b->arr[i].ptr + offset, (size_t)bytes);
+}
+int ngbBatchSetOpFull(ngb_batch *b, int on) { b->op_full = on; return NGB_OK; }
+
+/* per-thread parameter rows (Monte-Carlo with model-parameter mismatch): prow [ninst*S] */
+int ngbBatchSetBsim4Rows(ngb_batch *b, const int *prow_t, int nrows, const double *mtab, const double *ptab)
+{
+    const size_t T = (size_t)b->c->b4_n * b->S;
+    ngb_dev_free(b->b4_prow_t); ngb_dev_free(b->b4_mtab); ngb_dev_free(b->b4_ptab);
+    b->b4_prow_t = (int *)dev_dup(prow_t, sizeof(int) * T);
+    b->b4_mtab = (double *)dev_dup(mtab, sizeof(double) * (size_t)nrows * B4M_COUNT);
+    b->b4_ptab = (double *)dev_dup(ptab, sizeof(double) * (size_t)nrows * B4P_COUNT);
+    return (b->b4_prow_t && b->b4_mtab && b->b4_ptab) ? NGB_OK : NGB_E_PANIC;
+}
+
+/* ------------------------------------------------------------------ hot path launches */
+void ngb_fill_b4ctx(ngb_batch *b, B4Ctx *x)
+{
+    const ngb_circuit *c = b->c;
+    memset(x, 0, sizeof *x);
+    x->ninst = c->b4_n; x->S = b->S; x->T = c->b4_n * b->S;
+    x->mtab = b->b4_mtab; x->ptab = b->b4_ptab;
+    x->prow = b->b4_prow_t ? b->b4_prow_t : b->b4_prow; x->prow_per_thread = b->b4_prow_t ? 1 : 0;
+    x->inst = b->b4_inst; x->flags = b->b4_flags; x->nodes = b->b4_nodes; x->spos = b->b4_spos;
+    x->stamp = b->stamp; x->state = b->b4_state; x->op = b->b4_op; x->op_full = b->op_full;
+    x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl; x->temp = c->opt.temp; x->vt0 = c->opt.vt0;
+}
+void ngb_fill_capctx(ngb_batch *b, NgbCapCtx *x)
+{
+    const ngb_circuit *c = b->c;
+    memset(x, 0, sizeof *x);
+    x->ninst = c->cap_n; x->S = b->S; x->T = c->cap_n * b->S; x->nodes = b->cap_nodes; x->par = b->cap_par;
+    x->spos = b->cap_spos; x->state = b->cap_state; x->stamp = b->stamp; x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl;
+}
+void ngb_fill_srcctx(ngb_batch *b, NgbSrcCtx *x, int is_current)
+{
+    const ngb_circuit *c = b->c;
+    memset(x, 0, sizeof *x);
+    x->S = b->S; x->is_current = is_current; x->stamp = b->stamp; x->tstep = c->opt.tstep; x->tstop = c->opt.tstop; x->ctl = b->ctl;
+    if (is_current) { x->ninst = c->is_n; x->fn = b->is_fn; x->par = b->is_par; x->spos = b->is_spos; }
+    else { x->ninst = c->vs_n; x->fn = b->vs_fn; x->par = b->vs_par; x->spos = b->vs_spos; }
+    x->T = x->ninst * b->S;
+}
+void ngb_fill_asmctx(ngb_batch *b, NgbAsmCtx *x)
+{
+    const ngb_circuit *c = b->c;
+    memset(x, 0, sizeof *x);
+    x->S = b->S; x->nnz = c->nnz; x->neq1 = b->neq1; x->tgt_ptr = b->d_tgt_ptr; x->tgt_rows = b->d_tgt_rows;
+    x->slot_diag = b->d_slot_diag; x->stamp = b->stamp; x->Ax = b->Ax; x->x = b->x; x->add_diag_gmin = 1; x->ctl = b->ctl;
+}
+void ngb_fill_luctx(ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve)
+{
+    const ngb_circuit *c = b->c;
+    memset(x, 0, sizeof *x);
+    x->sch = b->dsch; x->S = b->S; x->neq1 = b->neq1; x->Ax = b->Ax; x->V = b->V; x->Rs = b->Rs; x->x = b->x;
+    x->do_factor = do_factor; x->do_solve = do_solve; x->node_type = b->d_node_type;
+    x->reltol = c->opt.reltol; x->abstol = c->opt.abstol; x->vntol = c->opt.vntol;
+    x->nodeconv = b->nodeconv; x->singular_col = b->singular; x->ctl = b->ctl;
+}
+
+static int check_errflag(ngb_batch *b)
+{
+    int e[4] = { 0, 0, 0, 0 };
+    ngb_dev_d2h(e, b->errflag, sizeof e);
+    if (e[0]) { ngb_set_error("device load reported error %d", e[0]); return e[0]; }
+    return NGB_OK;
+}
+
+int ngb_enqueue_load(ngb_batch *b)
+{
+    const ngb_circuit *c = b->c;
+    int r;
+    if (c->b4_n) { B4Ctx x; ngb_fill_b4ctx(b, &x); if ((r = ngb_launch_bsim4_load(&x, b->errflag))) return r; }
+    if (c->cap_n) { NgbCapCtx x; ngb_fill_capctx(b, &x); if ((r = ngb_launch_cap_load(&x, b->errflag))) return r; }
+    if (c->is_n) { NgbSrcCtx x; ngb_fill_srcctx(b, &x, 1); if ((r = ngb_launch_src_load(&x))) return r; }
+    if (c->vs_n) { NgbSrcCtx x; ngb_fill_srcctx(b, &x, 0); if ((r = ngb_launch_src_load(&x))) return r; }
+    { NgbAsmCtx x; ngb_fill_asmctx(b, &x); if ((r = ngb_launch_assemble(&x))) return r; }
+    return NGB_OK;
+}
+
+int ngbLoad(ngb_batch *b)
+{
+    int r;
+    ngb_dev_memset(b->errflag, 0, sizeof(int) * 4);
+    ngb_launch_clear_i32(b->ctl.noncon, 0, b->S);          /* CKTnoncon = 0 (niiter.c:71) */
+    if ((r = ngb_enqueue_load(b))) return r;
+    if ((r = ngb_dev_sync())) return r;
+    return check_errflag(b);
+}
+static int lu_call(ngb_batch *b, int f, int s)
+{
+    NgbLuCtx x; int r;
+    if (!b->have_lu) { ngb_set_error("no LU pattern: call ngbCircuitSetLuPattern or ngbCircuitAnalyze before ngbBatchCreate"); return NGB_E_PANIC; }
+    ngb_fill_luctx(b, &x, f, s);
+    if (s) ngb_launch_clear_i32(b->nodeconv, 0, b->S);
+    if ((r = ngb_launch_lu(&x))) return r;
+    return ngb_dev_sync();
+}
+int ngbLuFac(ngb_batch *b) { return lu_call(b, 1, 0); }
+int ngbSolve(ngb_batch *b) { return lu_call(b, 0, 1); }
+int ngbLuFacSolve(ngb_batch *b) { return lu_call(b, 1, 1); }
+int ngbNewtonStep(ngb_batch *b) { int r = ngbLoad(b); return r ? r : ngbLuFacSolve(b); }

@@ -1,0 +1,67 @@
+/* ngb_host.h -- host-side objects behind the opaque handles of include/ngb200.h */
+#ifndef NGB_HOST_H
+#define NGB_HOST_H
+#include "ngb_types.h"
+#include "bsim4_eval.cuh"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct ngb_circuit {
+    int neq;                       /* CKTmaxEqNum */
+    int *node_type;                /* [neq+1] */
+    NgbOpts opt;
+    int finalized, have_lu;
+    /* device tables (host copies, instance order = reference list order) */
+    int b4_n, b4_nrows; int *b4_nodes, *b4_flags, *b4_prow; double *b4_inst, *b4_mtab, *b4_ptab;
+    int *b4_spos, *b4_slots;
+    int res_n; int *res_nodes; double *res_g; int *res_spos;
+    int cap_n; int *cap_nodes; double *cap_par; int *cap_spos;
+    int vs_n; int *vs_nodes, *vs_fn; double *vs_par; int *vs_spos, *vs_cspos;
+    int is_n; int *is_nodes, *is_fn; double *is_par; int *is_spos;
+    /* CSC pattern (SMPconvertCOOtoCSC) */
+    int n, nnz; int *Ap, *Ai, *eq2col, *col2eq, *slot_diag, *diag_slot;
+    /* stamp rows and per-target contribution lists */
+    int nstamp_rows, ntgt; int *tgt_ptr, *tgt_rows;
+    int nconst; int *const_row; double *const_val;
+    /* LU: imported or own symbolic objects + task schedule */
+    int klu_nblocks; int *klu_Q, *klu_R, *klu_Pnum;
+    int lnz, unz, nzoff, npairs, nsolvepairs;
+    NgbLuSched sch;                /* host arrays */
+};
+
+#define NGB_MAX_ARR 64
+struct ngb_tran;
+struct ngb_batch {
+    struct ngb_circuit *c;
+    int S, neq1, failed, op_full, have_lu;
+    NgbCtl ctl;
+    double *x, *Ax, *stamp;
+    int *errflag;
+    int *d_node_type, *d_tgt_ptr, *d_tgt_rows, *d_slot_diag;
+    double *b4_inst, *b4_state, *b4_op, *b4_mtab, *b4_ptab; int *b4_prow, *b4_prow_t, *b4_flags, *b4_nodes, *b4_spos;
+    double *cap_par, *cap_state; int *cap_nodes, *cap_spos;
+    double *vs_par; int *vs_fn, *vs_spos;
+    double *is_par; int *is_fn, *is_spos;
+    NgbLuSched dsch;               /* device arrays */
+    double *V, *Rs; int *nodeconv, *singular;
+    struct { const char *name; void *ptr; size_t bytes; } arr[NGB_MAX_ARR];
+    int narr;
+    struct ngb_tran *tran;
+};
+
+void ngb_set_error(const char *fmt, ...);
+void ngb_fill_b4ctx(struct ngb_batch *b, B4Ctx *x);
+void ngb_fill_capctx(struct ngb_batch *b, NgbCapCtx *x);
+void ngb_fill_srcctx(struct ngb_batch *b, NgbSrcCtx *x, int is_current);
+void ngb_fill_asmctx(struct ngb_batch *b, NgbAsmCtx *x);
+void ngb_fill_luctx(struct ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve);
+int ngb_enqueue_load(struct ngb_batch *b);
+void ngb_tran_free(struct ngb_batch *b);
+int ngbBatchSetBsim4Rows(struct ngb_batch *b, const int *prow_t, int nrows, const double *mtab, const double *ptab);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

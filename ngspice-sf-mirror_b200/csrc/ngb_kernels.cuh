@@ -1,0 +1,331 @@
+/* ngb_kernels.cuh -- kernel bodies other than the BSIM4 evaluation: linear elements and
+ * sources, matrix/RHS assembly, numeric LU refactor + triangular solves + node convergence.
+ *
+ * Reference behaviour restated here (file:line under /root/reference/src):
+ *   capacitor load      spicelib/devices/cap/capload.c:15-110
+ *   V/I source load     spicelib/devices/vsrc/vsrcload.c:27-470, isrc/isrcload.c:27-380 (DC, PULSE, SINE)
+ *   zero RHS / SMPclear spicelib/analysis/cktload.c:62-65, maths/KLU/klusmp.c:485-498
+ *   diagonal gmin       maths/KLU/klusmp.c:1764-1777 (LoadGmin_CSC)
+ *   row scaling         maths/KLU/klu_scale.c (scale = 2: Rs[i] = max_j |A_ij|, 0 -> 1)
+ *   numeric refactor    maths/KLU/klu_refactor.c:285-426 (scaled branch)
+ *   triangular solves   maths/KLU/klu_solve.c (nrhs = 1), klu.c:201-250 (lsolve), :304-345 (usolve)
+ *   SMPsolve wrapper    maths/KLU/klusmp.c:950-1011 (node-collapsing map, zeroing of the RHS)
+ *   node convergence    maths/ni/niconv.c:41-77
+ *
+ * The LU is expressed as per-entry tasks: every L/U/diagonal/off-block value is
+ *     v = A[slot]/Rs[row] - sum_k V[pair_l[k]] * V[pair_u[k]]     (then / pivot for L entries)
+ * with the pairs in exactly the order the left-looking KLU loop applies them, so each value
+ * goes through the same sequence of roundings as on the CPU (no FMA contraction); tasks are
+ * grouped in dependency levels that a group of threads executes with a barrier between levels.
+ * The solves are 2n row tasks (forward y_i, backward x_i) built the same way.
+ */
+#ifndef NGB_KERNELS_CUH
+#define NGB_KERNELS_CUH
+
+#include "ngb_types.h"
+#include "devsup.cuh"
+
+#define NGB_SP_VOLTAGE 3
+
+
+/* ------------------------------------------------------------------ capacitors */
+NGB_HD int ngb_cap_thread(const NgbCapCtx *c, size_t t)
+{
+    const int S = c->S;
+    const int inst = (int)(t / (size_t)S);
+    const int s = (int)(t - (size_t)inst * S);
+    if (!NGB_LDG(&c->ctl.active[s])) return NGB_OK;
+    const int mode = NGB_LDG(&c->ctl.mode[s]);
+    const int head = NGB_LDG(&c->ctl.head[s]);
+    const double cap = NGB_LDG(&c->par[(size_t)0 * c->T + t]);
+    const double m = NGB_LDG(&c->par[(size_t)1 * c->T + t]);
+    double geq = 0.0, ceq = 0.0;
+    int stamped = 0;
+#define CST(h, k) c->state[((size_t)(((head) + (h)) % NGB_NHIST) * 2 + (k)) * c->T + t]
+    if (mode & (NGB_MODETRAN | NGB_MODEAC | NGB_MODETRANOP)) {
+        const int cond1 = (((mode & NGB_MODEDC) && (mode & NGB_MODEINITJCT)) ||
+                           ((mode & NGB_MODEUIC) && (mode & NGB_MODEINITTRAN)));
+        double vcap;
+        if (cond1) {
+            vcap = NGB_LDG(&c->par[(size_t)2 * c->T + t]);
+        } else {
+            const double *xo = c->x + (size_t)NGB_LDG(&c->ctl.xsel[s]) * c->neq1 * S;
+            vcap = NGB_LDG(&xo[(size_t)NGB_LDG(&c->nodes[inst]) * S + s])
+                 - NGB_LDG(&xo[(size_t)NGB_LDG(&c->nodes[c->ninst + inst]) * S + s]);
+        }
+        if (mode & (NGB_MODETRAN | NGB_MODEAC)) {
+            const int order = NGB_LDG(&c->ctl.order[s]);
+            const double ag0 = NGB_LDG(&c->ctl.ag0[s]), ag1 = NGB_LDG(&c->ctl.ag1[s]);
+            double q0, q1, cc;
+            if (order != 1 && order != 2) return NGB_E_ORDER;
+            if (mode & NGB_MODEINITPRED) {
+                q0 = CST(1, 0);
+                CST(0, 0) = q0;
+            } else {
+                q0 = cap * vcap;
+                CST(0, 0) = q0;
+                if (mode & NGB_MODEINITTRAN) CST(1, 0) = q0;
+            }
+            q1 = CST(1, 0);
+            cc = ngb_integrate_trap(order, ag0, ag1, q0, q1, (order == 2) ? CST(1, 1) : 0.0);
+            CST(0, 1) = cc;
+            ceq = cc - ag0 * q0;
+            geq = ag0 * cap;
+            if (mode & NGB_MODEINITTRAN) CST(1, 1) = cc;
+            stamped = 1;
+        } else {
+            CST(0, 0) = cap * vcap;
+        }
+    }
+#undef CST
+    {
+        const double g = stamped ? m * geq : 0.0, i = stamped ? m * ceq : 0.0;
+        const double v[6] = { g, g, -g, -g, -i, i };
+        for (int k = 0; k < 6; k++) {
+            int r = NGB_LDG(&c->spos[k * c->ninst + inst]);
+            if (r >= 0) c->stamp[(size_t)r * S + s] = v[k];
+        }
+    }
+    return NGB_OK;
+}
+
+/* ------------------------------------------------------------------ independent sources */
+NGB_HD double ngb_src_value(const NgbSrcCtx *c, size_t t, int inst, int s, int mode, int poff)
+{
+    const int ftype = NGB_LDG(&c->fn[inst]);
+    const int forder = NGB_LDG(&c->fn[c->ninst + inst]);
+    const int dcGiven = NGB_LDG(&c->fn[2 * c->ninst + inst]);
+    const double dc = NGB_LDG(&c->par[(size_t)0 * c->T + t]);
+#define SCO(k) NGB_LDG(&c->par[(size_t)(poff + (k)) * c->T + t])
+    double value, time;
+    if ((mode & (NGB_MODEDCOP | NGB_MODEDCTRANCURVE)) && dcGiven) {
+        value = dc * NGB_LDG(&c->ctl.srcfact[s]);
+    } else {
+        time = (mode & NGB_MODEDC) ? 0.0 : NGB_LDG(&c->ctl.time[s]);
+        switch (ftype) {
+        default:
+            value = dc;
+            break;
+        case NGB_FN_PULSE: {
+            const double V1 = SCO(0), V2 = SCO(1);
+            const double TD = forder > 2 ? SCO(2) : 0.0;
+            const double TR = (forder > 3 && SCO(3) > 0.0) ? SCO(3) : c->tstep;
+            const double TF = (forder > 4 && SCO(4) > 0.0) ? SCO(4) : c->tstep;
+            const double PW = (forder > 5 && SCO(5) >= 0.0) ? SCO(5) : 0.0;
+            const double PER = (forder > 6 && SCO(6) > 0.0) ? SCO(6) : TR + TF + PW;
+            const double PHASE = forder > 7 ? SCO(7) : 0.0;
+            double tmax = 1e99;
+            time -= TD;
+            if (PHASE > 0.0) tmax = PHASE * PER;      /* 8th parameter: number of pulses */
+            if (time > tmax) {
+                value = V1;
+            } else {
+                if (time > PER) {
+                    double basetime = PER * floor(time / PER);
+                    time -= basetime;
+                }
+                if (time <= 0 || time >= TR + PW + TF) value = V1;
+                else if (time >= TR && time <= TR + PW) value = V2;
+                else if (time > 0 && time < TR) value = V1 + (V2 - V1) * (time) / TR;
+                else value = V2 + (V1 - V2) * (time - (TR + PW)) / TF;
+            }
+        } break;
+        case NGB_FN_SINE: {
+            const double PHASE = forder > 5 ? SCO(5) : 0.0;
+            const double phase = PHASE * M_PI / 180.0;
+            const double VO = SCO(0), VA = SCO(1);
+            const double FREQ = (forder > 2 && SCO(2) != 0.0) ? SCO(2) : (1 / c->tstop);
+            const double TD = forder > 3 ? SCO(3) : 0.0;
+            const double THETA = forder > 4 ? SCO(4) : 0.0;
+            time -= TD;
+            if (time <= 0) value = VO + VA * sin(phase);
+            else value = VO + VA * sin(FREQ * time * 2.0 * M_PI + phase) * exp(-time * THETA);
+        } break;
+        }
+    }
+#undef SCO
+    if (mode & NGB_MODETRANOP) value *= NGB_LDG(&c->ctl.srcfact[s]);
+    return value;
+}
+
+NGB_HD int ngb_src_thread(const NgbSrcCtx *c, size_t t)
+{
+    const int S = c->S;
+    const int inst = (int)(t / (size_t)S);
+    const int s = (int)(t - (size_t)inst * S);
+    if (!NGB_LDG(&c->ctl.active[s])) return NGB_OK;
+    const int mode = NGB_LDG(&c->ctl.mode[s]);
+    if (!c->is_current) {
+        const double value = ngb_src_value(c, t, inst, s, mode, 1);
+        int r = NGB_LDG(&c->spos[inst]);
+        if (r >= 0) c->stamp[(size_t)r * S + s] = value;
+    } else {
+        const double m = NGB_LDG(&c->par[(size_t)1 * c->T + t]);
+        const double value = ngb_src_value(c, t, inst, s, mode, 2);
+        int r = NGB_LDG(&c->spos[inst]);
+        if (r >= 0) c->stamp[(size_t)r * S + s] = m * value;           /* rhs[pos] += m*value */
+        r = NGB_LDG(&c->spos[c->ninst + inst]);
+        if (r >= 0) c->stamp[(size_t)r * S + s] = -(m * value);        /* rhs[neg] -= m*value */
+    }
+    return NGB_OK;
+}
+
+/* ------------------------------------------------------------------ assembly */
+/* one thread per (target, sample): u = target * S + s */
+NGB_HD void ngb_asm_thread(const NgbAsmCtx *c, size_t u)
+{
+    const int S = c->S;
+    const int tg = (int)(u / (size_t)S);
+    const int s = (int)(u - (size_t)tg * S);
+    if (!NGB_LDG(&c->ctl.active[s])) return;
+    double acc = 0.0;
+    const int lo = NGB_LDG(&c->tgt_ptr[tg]), hi = NGB_LDG(&c->tgt_ptr[tg + 1]);
+    for (int p = lo; p < hi; p++)
+        acc += NGB_LDG(&c->stamp[(size_t)NGB_LDG(&c->tgt_rows[p]) * S + s]);
+    if (tg < c->nnz) {
+        /* LoadGmin_CSC: CKTdiagGmin on every present diagonal, applied with the factor call */
+        if (c->add_diag_gmin && NGB_LDG(&c->slot_diag[tg])) {
+            const double dg = NGB_LDG(&c->ctl.diag_gmin[s]);
+            if (dg != 0.0) acc += dg;
+        }
+        c->Ax[(size_t)s * c->nnz + tg] = acc;
+    } else {
+        const int eq = tg - c->nnz;
+        double *rhs = c->x + (size_t)(1 - NGB_LDG(&c->ctl.xsel[s])) * c->neq1 * S;
+        rhs[(size_t)eq * S + s] = acc;
+    }
+}
+
+/* ------------------------------------------------------------------ LU */
+#ifndef NGB_GROUP_SYNC
+#define NGB_GROUP_SYNC() ((void)0)     /* hostsim: one "thread" per group */
+#endif
+
+/* Whole SMPluFac/SMPsolve/NIconvTest sequence for sample s, executed by a group of `nl`
+ * threads (`lane` = index in the group).  V, Rs, Z are group-private scratch (shared memory
+ * on the device): V[nV], Rs[n], Z[ntask]. */
+NGB_HD void ngb_lu_sample(const NgbLuCtx *c, int s, int lane, int nl, double *V, double *Rs, double *Z)
+{
+    const NgbLuSched *h = &c->sch;
+    const int S = c->S, n = h->n, nV = h->nV;
+    const int active = NGB_LDG(&c->ctl.active[s]);
+    if (!active) return;
+    const double *Ax = c->Ax + (size_t)s * h->nnz;
+
+    if (c->do_factor) {
+        /* row scale factors */
+        for (int i = lane; i < n; i += nl) {
+            double r = 0.0;
+            const int lo = NGB_LDG(&h->row_ptr[i]), hi = NGB_LDG(&h->row_ptr[i + 1]);
+            for (int p = lo; p < hi; p++) {
+                double a = fabs(Ax[NGB_LDG(&h->row_slot[p])]);
+                r = (r > a) ? r : a;
+            }
+            if (r == 0.0) r = 1.0;
+            Rs[i] = r;
+        }
+        NGB_GROUP_SYNC();
+        for (int lev = 0; lev < h->nlev; lev++) {
+            const int lo = NGB_LDG(&h->lev_ptr[lev]), hi = NGB_LDG(&h->lev_ptr[lev + 1]);
+            for (int q = lo + lane; q < hi; q += nl) {
+                const int e = NGB_LDG(&h->lev_ent[q]);
+                const int as = NGB_LDG(&h->e_aslot[e]);
+                double v = 0.0;
+                if (as >= 0) v = Ax[as] / Rs[NGB_LDG(&h->e_arow[e])];
+                const int p0 = NGB_LDG(&h->e_pptr[e]), p1 = NGB_LDG(&h->e_pptr[e + 1]);
+                for (int p = p0; p < p1; p++) {
+                    /* X[i] -= Lx * ujk : product and difference rounded separately */
+#ifdef __CUDA_ARCH__
+                    v = __dsub_rn(v, __dmul_rn(V[NGB_LDG(&h->pair_l[p])], V[NGB_LDG(&h->pair_u[p])]));
+#else
+                    { volatile double pr = V[h->pair_l[p]] * V[h->pair_u[p]]; v = v - pr; }
+#endif
+                }
+                const int dv = NGB_LDG(&h->e_div[e]);
+                if (dv >= 0) v = v / V[dv];
+                V[e] = v;
+            }
+            NGB_GROUP_SYNC();
+        }
+        /* zero pivot -> E_SINGULAR (klu_refactor.c:390-404) */
+        if (lane == 0) {
+            int sc = -1;
+            for (int k = 0; k < n; k++)
+                if (V[NGB_LDG(&h->diag_v[k])] == 0.0) { sc = k; break; }
+            c->singular_col[s] = sc;
+            if (sc >= 0) c->ctl.err[s] = NGB_E_SINGULAR;
+        }
+        if (c->V) {
+            double *Vg = c->V + (size_t)s * nV;
+            for (int e = lane; e < nV; e += nl) Vg[e] = V[e];
+            double *Rg = c->Rs + (size_t)s * n;
+            for (int i = lane; i < n; i += nl) Rg[i] = Rs[i];
+        }
+        NGB_GROUP_SYNC();
+    } else {
+        const double *Vg = c->V + (size_t)s * nV;
+        for (int e = lane; e < nV; e += nl) V[e] = Vg[e];
+        const double *Rg = c->Rs + (size_t)s * n;
+        for (int i = lane; i < n; i += nl) Rs[i] = Rg[i];
+        NGB_GROUP_SYNC();
+    }
+
+    if (c->do_solve) {
+        const int xs = NGB_LDG(&c->ctl.xsel[s]);
+        double *rhs = c->x + (size_t)(1 - xs) * c->neq1 * S;
+        const double *old = c->x + (size_t)xs * c->neq1 * S;
+        for (int lev = 0; lev < h->nslev; lev++) {
+            const int lo = NGB_LDG(&h->slev_ptr[lev]), hi = NGB_LDG(&h->slev_ptr[lev + 1]);
+            for (int q = lo + lane; q < hi; q += nl) {
+                const int tk = NGB_LDG(&h->slev_task[q]);
+                const int kind = NGB_LDG(&h->t_kind[tk]);
+                const int ini = NGB_LDG(&h->t_init[tk]);
+                double z;
+                if (kind == 0) {
+                    const int eq = NGB_LDG(&h->b_eq[ini]);
+                    z = rhs[(size_t)eq * S + s] / Rs[ini];
+                } else {
+                    z = Z[ini];
+                }
+                const int p0 = NGB_LDG(&h->t_pptr[tk]), p1 = NGB_LDG(&h->t_pptr[tk + 1]);
+                for (int p = p0; p < p1; p++) {
+#ifdef __CUDA_ARCH__
+                    z = __dsub_rn(z, __dmul_rn(V[NGB_LDG(&h->t_val[p])], Z[NGB_LDG(&h->t_src[p])]));
+#else
+                    { volatile double pr = V[h->t_val[p]] * Z[h->t_src[p]]; z = z - pr; }
+#endif
+                }
+                if (kind == 1) z = z / V[NGB_LDG(&h->t_div[tk])];
+                Z[tk] = z;
+            }
+            NGB_GROUP_SYNC();
+        }
+        /* SMPsolve: zero the RHS, scatter the solution back through the column permutation */
+        for (int i = lane; i < c->neq1; i += nl) rhs[(size_t)i * S + s] = 0.0;
+        NGB_GROUP_SYNC();
+        for (int k = lane; k < n; k += nl) {
+            const int eq = NGB_LDG(&h->out_eq[k]);
+            if (eq != 0) rhs[(size_t)eq * S + s] = Z[NGB_LDG(&h->out_task[k])];
+        }
+        NGB_GROUP_SYNC();
+        /* NIconvTest node loop (niconv.c:41-77): result 1 = not converged */
+        if (c->nodeconv) {
+            int bad = 0;
+            for (int i = 1 + lane; i <= n; i += nl) {
+                const double nw = rhs[(size_t)i * S + s], od = old[(size_t)i * S + s];
+                if (nw != nw) { bad = 1; continue; }
+                const double mx = (fabs(od) > fabs(nw)) ? fabs(od) : fabs(nw);
+                const double tol = c->reltol * mx
+                                 + ((NGB_LDG(&c->node_type[i]) == NGB_SP_VOLTAGE) ? c->vntol : c->abstol);
+                if (fabs(nw - od) > tol) bad = 1;
+            }
+#ifdef __CUDA_ARCH__
+            if (bad) atomicOr(&c->nodeconv[s], 1);
+#else
+            if (bad) c->nodeconv[s] = 1;
+#endif
+        }
+    }
+}
+
+#endif

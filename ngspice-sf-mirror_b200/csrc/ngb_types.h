@@ -1,0 +1,136 @@
+/* ngb_types.h -- operand blocks shared by the host code (C) and the kernels (CUDA).
+ *
+ * Layout rules (DESIGN.md "Data layout in HBM"):
+ *   - a batch holds S independent samples (Monte-Carlo draws / sweep points) of ONE circuit
+ *     topology; the sample index is always the fastest-varying one, so a warp that works on
+ *     32 consecutive samples of the same instance/node issues fully coalesced accesses;
+ *   - solution vectors  x[buf][eq][S]      (buf 0/1; xsel[s] says which one is CKTrhsOld);
+ *   - device states     state[hist][k][T]  (T = instances * S), ring-rotated per sample by head[s];
+ *   - stamp buffer      stamp[row][S]      one row per live (instance, stamp position);
+ *   - matrices          Ax[S][nnz]         sample-major: one warp owns one sample's matrix.
+ */
+#ifndef NGB_TYPES_H
+#define NGB_TYPES_H
+
+#include "ngb_common.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* per-sample control block (the per-circuit scalars of CKTcircuit, cktdefs.h:66-331), SoA [S] */
+typedef struct NgbCtl {
+    int S;
+    int *mode;            /* CKTmode                                                    */
+    int *active;          /* 1: sample takes part in this Newton step                   */
+    int *head;            /* ring position of CKTstate0 (CKTstates rotation, dctran.c:659) */
+    int *order;           /* CKTorder                                                   */
+    int *noncon;          /* CKTnoncon                                                  */
+    int *xsel;            /* which x buffer is CKTrhsOld (pointer SWAP of niiter.c:362)  */
+    int *err;             /* sticky NGB_E_* per sample                                  */
+    double *ag0, *ag1;    /* CKTag[0..1]                                                */
+    double *delta;        /* CKTdelta                                                   */
+    double *delta_old;    /* CKTdeltaOld[7][S]                                          */
+    double *time;         /* CKTtime                                                    */
+    double *gmin;         /* CKTgmin                                                    */
+    double *diag_gmin;    /* CKTdiagGmin                                                */
+    double *srcfact;      /* CKTsrcFact                                                 */
+} NgbCtl;
+
+/* source waveform codes (vsrcdefs.h:146-160) */
+#define NGB_FN_PULSE 1
+#define NGB_FN_SINE  2
+
+/* circuit-wide scalars */
+typedef struct NgbOpts {
+    double reltol, abstol, vntol, chgtol, trtol, temp, vt0, xmu;
+    double tstep, tstop, tmax, tstart, delmin, minbreak, gmin;
+    int method, maxorder, itl4, itl1, uic;
+} NgbOpts;
+
+/* two-terminal linear elements and sources */
+typedef struct NgbCapCtx {
+    int ninst, S, T;
+    const int *nodes;       /* [2][ninst] pos, neg                                      */
+    const double *par;      /* [3][T]  capacitance, m, initial condition                */
+    const int *spos;        /* [6][ninst] stamp rows: pp nn pn np rhs_pos rhs_neg        */
+    double *state;          /* [NGB_NHIST][2][T]  q, i                                   */
+    double *stamp;
+    const double *x; int neq1;
+    NgbCtl ctl;
+} NgbCapCtx;
+
+typedef struct NgbSrcCtx {
+    int ninst, S, T;
+    int is_current;         /* 0: VSRC (rhs row = branch), 1: ISRC (rhs rows = pos,neg)  */
+    const int *fn;          /* [3][ninst] function type, order, dcGiven                  */
+    const double *par;      /* VSRC [9][T]: dc, coeffs[8] ; ISRC [10][T]: dc, m, coeffs[8] */
+    const int *spos;        /* VSRC [1][ninst] rhs_branch ; ISRC [2][ninst] rhs_pos rhs_neg */
+    double *stamp;
+    double tstep, tstop;    /* CKTstep, CKTfinalTime (PULSE/SINE defaults)               */
+    NgbCtl ctl;
+} NgbSrcCtx;
+
+/* assembly of Ax / rhs from the stamp buffer: target t sums rows tgt_rows[tgt_ptr[t]..tgt_ptr[t+1])
+ * in that (reference load) order; targets [0,nnz) are CSC slots, [nnz, nnz+neq+1) are rhs rows */
+typedef struct NgbAsmCtx {
+    int S, nnz, neq1;
+    const int *tgt_ptr, *tgt_rows;
+    const int *slot_diag;   /* [nnz] 1 if the slot is a diagonal entry (LoadGmin_CSC)    */
+    const double *stamp;
+    double *Ax;             /* [S][nnz]                                                  */
+    double *x;              /* rhs is assembled into x[1 - xsel]                         */
+    int add_diag_gmin;
+    NgbCtl ctl;
+} NgbAsmCtx;
+
+/* numeric LU on a fixed pattern + pivot order, as element tasks (DESIGN.md "LU") */
+typedef struct NgbLuSched {
+    int n;                  /* matrix order (after node collapsing)                      */
+    int nnz;                /* entries of A                                              */
+    int nV;                 /* LU values: L, U, Udiag, Offx entries                      */
+    int nlev;               /* factor levels                                             */
+    const int *lev_ptr;     /* [nlev+1] into lev_ent                                     */
+    const int *lev_ent;     /* [nV] entry ids by level                                   */
+    const int *e_aslot;     /* [nV] A slot feeding the entry or -1                       */
+    const int *e_arow;      /* [nV] original row (index of Rs) of the entry              */
+    const int *e_div;       /* [nV] value id of the pivot to divide by (L entries) or -1 */
+    const int *e_pptr;      /* [nV+1] into pair_l / pair_u                               */
+    const int *pair_l, *pair_u;
+    const int *diag_v;      /* [n] value id of Udiag[k]                                  */
+    const int *row_ptr;     /* [n+1] CSR view of A for the row scale factors             */
+    const int *row_slot;
+    /* triangular solves as 2n row tasks */
+    int ntask, nslev;
+    const int *slev_ptr;    /* [nslev+1]                                                 */
+    const int *slev_task;   /* [ntask]                                                   */
+    const int *t_kind;      /* 0: y (forward), 1: x (backward, divides by pivot)         */
+    const int *t_init;      /* y: original row of b ; x: task id of y                    */
+    const int *t_div;       /* x: value id of the pivot                                  */
+    const int *t_pptr;      /* [ntask+1]                                                 */
+    const int *t_val, *t_src;
+    const int *b_eq;        /* [n] equation number feeding original row i (node collapsing) */
+    const int *out_task;    /* [n] x-task whose result is the solution of column q       */
+    const int *out_eq;      /* [n] equation number receiving it                          */
+} NgbLuSched;
+
+typedef struct NgbLuCtx {
+    NgbLuSched sch;
+    int S, neq1;
+    const double *Ax;       /* [S][nnz]                                                  */
+    double *V;              /* [S][nV] LU values (kept for a later solve / parity checks) */
+    double *Rs;             /* [S][n]                                                    */
+    double *x;              /* rhs in x[1 - xsel], overwritten by the solution           */
+    int do_factor, do_solve;
+    /* node convergence test of NIconvTest fused after the solve */
+    const int *node_type;   /* [neq1] SP_VOLTAGE(3) / SP_CURRENT(4)                      */
+    double reltol, abstol, vntol;
+    int *nodeconv;          /* [S] 1 if some node failed                                 */
+    int *singular_col;      /* [S] -1 or first zero pivot column                         */
+    NgbCtl ctl;
+} NgbLuCtx;
+
+#ifdef __cplusplus
+}
+#endif
+#endif

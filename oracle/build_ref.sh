@@ -62,3 +62,11 @@ ar rcs "$OUT/libngref$SUF.a" $(ls "$OBJ"/*.o | grep -v "/main.o$")
 LDOMP=""; [ "$FLAV" = omp ] && LDOMP="-fopenmp"
 gcc $LDOMP -o "$OUT/ngspice$SUF" "$MAINOBJ" -Wl,--start-group "$OUT/libngref$SUF.a" -Wl,--end-group -lm -ldl
 echo "built $OUT/ngspice$SUF"
+if [ "$FLAV" = serial ]; then
+  # instrumented flavour: same objects + oracle/ref_hooks.c interposed with ld --wrap
+  gcc -c $CFLAGS $INC -I"$R/spicelib/devices" -I"$R/maths/KLU" "$HERE/ref_hooks.c" -o "$OBJ/y_ref_hooks.o.tmp" && mv "$OBJ/y_ref_hooks.o.tmp" "$OUT/ref_hooks.o"
+  gcc -o "$OUT/ngspice_dump" "$MAINOBJ" "$OUT/ref_hooks.o" \
+      -Wl,--wrap=CKTload,--wrap=SMPsolve,--wrap=SMPluFac,--wrap=SMPreorder,--wrap=DCtran \
+      -Wl,--start-group "$OUT/libngref.a" -Wl,--end-group -lm -ldl
+  echo "built $OUT/ngspice_dump"
+fi

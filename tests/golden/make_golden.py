@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Generates the committed golden fixtures by running the REFERENCE ngspice (compiled by
+oracle/build_ref.sh into oracle/_ref/) on netlists assembled from the reference's own example
+and test files.  Needs /root/reference; the fixtures it writes do not.
+
+  ro17   examples/mos/ro_17_4.cir (17-stage BSIM4 ring oscillator, `.tran .1ns 150ns uic`),
+         model cards switched to `version = 4.8.3` so the BSIM4 4.8.3 code of b4ld.c is the one
+         that runs (4.5.0 would select the separate bsim4v5 device), `.option xmu=0.49 klu`.
+  ro101  same cards, 101 stages (BASELINE config 2).
+  inv    tests/bsim4/{nmos,pmos}/parameters cards, CMOS inverter with PULSE input (config 1).
+
+Outputs (tests/golden/): <name>.flat.ngt  flattened circuit after CKTsetup/CKTtemp
+                         <name>.trace.ngt.gz recorded CKTload / KLU calls (subset)
+                         <name>.wave.ngt  accepted time points, saved waveforms, run statistics
+"""
+import json
+import os
+import re
+import subprocess
+import sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from parity_util import ngt  # noqa: E402
+
+REF = os.environ.get("NGB_REFERENCE", "/root/reference")
+DUMP = os.path.join(ROOT, "oracle", "_ref", "ngspice_dump")
+TMP = os.environ.get("NGB_TMP", "/tmp/ngb_golden")
+
+
+def ro_cards():
+    src = open(os.path.join(REF, "examples/mos/ro_17_4.cir")).read()
+    i = src.index(".model  N1")
+    cards = src[i:]
+    cards = cards.replace("version = 4.5.0", "version = 4.8.3")
+    return cards
+
+
+def ro_netlist(stages, tran=".tran .1ns 150ns uic", extra_opts=""):
+    lines = [f"* {stages}-stage BSIM4 ring oscillator (topology of examples/mos/ro_17_4.cir)", "vdd 1 0 2.0"]
+    for k in range(1, stages + 1):
+        a = k + 1
+        out = k + 2 if k < stages else 2
+        lines.append(f"mp{k} {out} {a} 1 1 p1 l=0.1u w=10u ad=5p pd=6u as=5p ps=6u")
+        lines.append(f"mn{k} {out} {a} 0 0 n1 l=0.1u w=5u ad=5p pd=6u as=5p ps=6u")
+    lines.append(f"c1 {stages + 1} 0 .1p")
+    lines.append(f".option xmu=0.49 klu {extra_opts}")
+    lines.append(tran)
+    return "\n".join(lines) + "\n" + ro_cards() + "\n.end\n"
+
+
+def read_raw(path):
+    data = open(path, "rb").read()
+    i = data.index(b"Binary:\n")
+    head = data[:i].decode(errors="replace")
+    nv = int(re.search(r"No. Variables:\s*(\d+)", head).group(1))
+    npts = int(re.search(r"No. Points:\s*(\d+)", head).group(1))
+    names = []
+    vs = head[head.index("Variables:\n") + len("Variables:\n"):]
+    for ln in vs.strip().splitlines():
+        parts = ln.split()
+        if len(parts) >= 3 and parts[0].isdigit():
+            names.append(parts[1])
+    arr = np.frombuffer(data, dtype=np.float64, count=nv * npts, offset=i + 8).reshape(npts, nv)
+    return names, arr
+
+
+def run(name, netlist, calls, save):
+    os.makedirs(TMP, exist_ok=True)
+    cir = os.path.join(TMP, name + ".cir")
+    open(cir, "w").write(netlist)
+    env = dict(os.environ, NGB_DUMP_FLAT=os.path.join(TMP, name + ".flat"),
+               NGB_DUMP_TRACE=os.path.join(TMP, name + ".trace"), NGB_DUMP_CALLS=calls,
+               NGB_DUMP_STATS=os.path.join(TMP, name + ".stats"))
+    raw = os.path.join(TMP, name + ".raw")
+    subprocess.run([DUMP, "-b", "-r", raw, cir], env=env, check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL)
+    flat = ngt.read(env["NGB_DUMP_FLAT"])
+    trace = ngt.read(env["NGB_DUMP_TRACE"])
+    stats = json.load(open(env["NGB_DUMP_STATS"]))
+    names, arr = read_raw(raw)
+    ngt.write(os.path.join(HERE, name + ".flat.ngt"), flat)
+    ngt.write(os.path.join(HERE, name + ".trace.ngt.gz"), trace)
+    # node name -> equation number from the flat dump
+    nn = bytes(flat["node/names_bytes"].astype(np.uint8)).decode().split("\n")
+    eq_of = {}
+    for ln in nn:
+        if ln.strip():
+            num, nm = ln.split(" ", 1)
+            eq_of[nm.lower()] = int(num)
+    cols, eqs = [], []
+    for s in save:
+        key = s.lower()
+        rawname = f"v({key})" if not key.endswith("#branch") else "i(" + key[:-7] + ")"
+        cand = [i for i, n in enumerate(names) if n.lower() in (rawname, key)]
+        if not cand:
+            raise SystemExit(f"{name}: saved vector {s} not in rawfile ({names[:8]}...)")
+        cols.append(cand[0]); eqs.append(eq_of[key])
+    wave = {"time": arr[:, 0].copy(), "values": arr[:, cols].copy(), "save_eq": np.array(eqs, np.int32),
+            "stats": np.array([stats["accepted"], stats["rejected"], stats["numiter"], stats["timepts"],
+                               stats["load_calls"]], np.int32),
+            "cpu_times": np.array([stats["load_time"], stats["decomp_time"], stats["reorder_time"],
+                                   stats["solve_time"], stats["tran_time"]])}
+    ngt.write(os.path.join(HERE, name + ".wave.ngt"), wave)
+    print(name, "points", arr.shape[0], "stats", stats)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["ro17", "ro101"]
+    if "ro17" in which:
+        run("ro17", ro_netlist(17), "0-3,100,101,5000,5001", ["18", "2", "9", "vdd#branch"])
+    if "ro101" in which:
+        run("ro101", ro_netlist(101), "1,2,3000", ["102", "2", "50", "vdd#branch"])

@@ -1,0 +1,60 @@
+/* tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU stand-in for the device runtime of ngspice-sf-mirror_b200/csrc/ngb_dev.h: the same
+ * kernel bodies (NGB_HD functions) executed by plain loops, one "thread" at a time, so that
+ * the CPU-only CI can check kernel logic against the oracle.  This object is linked only into
+ * tests/hostsim/libngb200_hostsim.so; the product library (libngb200.so) contains the CUDA
+ * implementation and nothing else. */
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "ngb_dev.h"
+#include "ngb_kernels.cuh"
+
+static long g_launches = 0;
+extern "C" {
+const char *ngb_dev_backend(void) { return "hostsim"; }
+int ngb_dev_init(int) { return 0; }
+void *ngb_dev_malloc(size_t bytes) { return calloc(bytes ? bytes : 1, 1); }
+void ngb_dev_free(void *p) { free(p); }
+int ngb_dev_h2d(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
+int ngb_dev_d2h(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
+int ngb_dev_memset(void *d, int v, size_t n) { memset(d, v, n); return 0; }
+int ngb_dev_sync(void) { return 0; }
+long ngb_dev_launch_count(void) { return g_launches; }
+void *ngb_dev_stream(void) { return nullptr; }
+
+int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag)
+{
+    g_launches++;
+    for (size_t t = 0; t < (size_t)c->T; t++) { int e = b4_load_thread(c, t); if (e && errflag && !errflag[0]) errflag[0] = e; }
+    return 0;
+}
+int ngb_launch_cap_load(const NgbCapCtx *c, int *errflag)
+{
+    g_launches++;
+    for (size_t t = 0; t < (size_t)c->T; t++) { int e = ngb_cap_thread(c, t); if (e && errflag && !errflag[0]) errflag[0] = e; }
+    return 0;
+}
+int ngb_launch_src_load(const NgbSrcCtx *c)
+{
+    g_launches++;
+    for (size_t t = 0; t < (size_t)c->T; t++) ngb_src_thread(c, t);
+    return 0;
+}
+int ngb_launch_assemble(const NgbAsmCtx *c)
+{
+    g_launches++;
+    const size_t n = (size_t)(c->nnz + c->neq1) * c->S;
+    for (size_t u = 0; u < n; u++) ngb_asm_thread(c, u);
+    return 0;
+}
+int ngb_launch_lu(const NgbLuCtx *c)
+{
+    g_launches++;
+    std::vector<double> V(c->sch.nV + 1), Rs(c->sch.n + 1), Z(c->sch.ntask + 1);
+    for (int s = 0; s < c->S; s++) ngb_lu_sample(c, s, 0, 1, V.data(), Rs.data(), Z.data());
+    return 0;
+}
+int ngb_launch_clear_i32(int *p, int value, int n) { for (int i = 0; i < n; i++) p[i] = value; return 0; }
+}

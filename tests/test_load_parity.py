@@ -1,0 +1,67 @@
+"""CKTload parity: replay recorded calls of the reference (BSIM4load + CAPload + VSRCload on a
+17- and a 101-stage BSIM4 ring oscillator) through the C ABI and compare Ax, rhs, state0, the
+operating point and CKTnoncon with what the reference produced.
+
+CPU (`not gpu`): kernel bodies compiled for the host (tests/hostsim) -- same libm as the
+reference, so state/op-point must agree bit for bit and Ax/rhs to summation-order rounding.
+GPU: the CUDA library; exp/log differ from glibc in the last place, tolerance 1e-12 relative
+(BASELINE north_star asks 1e-9 on waveforms)."""
+import numpy as np
+import pytest
+from parity_util import GOLDEN, ngt, pkg, relerr, replay_load, trace_calls, first_pattern
+
+CASES = ["ro17", "ro101"]
+
+
+def _load_case(name):
+    flat = ngt.read(f"{GOLDEN}/{name}.flat.ngt")
+    trace = ngt.read(f"{GOLDEN}/{name}.trace.ngt.gz")
+    return flat, trace
+
+
+def _check(lib, name, tol_state, tol_mat, S=1):
+    flat, trace = _load_case(name)
+    circ = pkg.Circuit.from_flat(lib, flat)
+    pat = circ.pattern()
+    # SMPconvertCOOtoCSC + BSIM4bindCSC parity: identical CSC pattern and slot map
+    assert pat["n"] == int(flat["klu/n"][0]) and pat["nnz"] == int(flat["klu/nz"][0])
+    assert np.array_equal(pat["Ap"], flat["klu/Ap"]) and np.array_equal(pat["Ai"], flat["klu/Ai"])
+    assert np.array_equal(pat["diag"], flat["klu/diag"])
+    assert np.array_equal(circ.bsim4_slots(int(flat["b4/ninst"][0])), flat["b4/slots"])
+    calls = trace_calls(trace)
+    assert calls
+    batch = None
+    for call in calls:
+        batch, ours, ref, maps = replay_load(lib, circ, flat, trace, call, S=S, batch=batch)
+        for s in sorted({0, S - 1}):
+            assert relerr(ours["Ax"][s], ref["Ax"], 1e-300).max() <= tol_mat, (name, call, "Ax")
+            assert relerr(ours["x"][1, 1:, s], ref["rhs"][1:], 1e-300).max() <= tol_mat, (name, call, "rhs")
+            st0 = ours["b4_state"][0, :, :, s]
+            assert relerr(st0, ref["state0"][maps["b4"]], 1e-300).max() <= tol_state, (name, call, "state0")
+            assert relerr(ours["cap_state"][0, :, :, s], ref["state0"][maps["cap"]], 1e-300).max() <= tol_state
+            assert relerr(ours["b4_op"][:, :, s], ref["b4_op"], 1e-300).max() <= tol_state, (name, call, "op")
+            assert (ours["noncon"][s] != 0) == (ref["noncon"] != 0), (name, call, "noncon")
+            if ref["mode"] & 0x1000:   # MODEINITTRAN copies q0 -> state1
+                st1 = ours["b4_state"][1, :, :, s]
+                qrows = [11, 13, 15, 19, 21]
+                assert relerr(st1[qrows], ref["b4_state1"][maps["b4"]][qrows], 1e-300).max() <= tol_state
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_load_hostsim_matches_reference(hostsim_lib, name):
+    _check(hostsim_lib, name, tol_state=0.0, tol_mat=1e-14)
+
+
+def test_load_hostsim_batched_samples_identical(hostsim_lib):
+    _check(hostsim_lib, "ro17", tol_state=0.0, tol_mat=1e-14, S=5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_load_gpu_matches_reference(cuda_lib, name):
+    _check(cuda_lib, name, tol_state=1e-11, tol_mat=1e-11, S=1)
+
+
+@pytest.mark.gpu
+def test_load_gpu_batched(cuda_lib):
+    _check(cuda_lib, "ro17", tol_state=1e-11, tol_mat=1e-11, S=67)
