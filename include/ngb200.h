@@ -57,6 +57,9 @@ int ngbCircuitSetOptions(ngb_circuit *c, const double dopt[15], const int iopt[5
  * of BSIM4load (b4ld.c:251-253) */
 int ngbCircuitAddBsim4(ngb_circuit *c, int ninst, const int *nodes, const int *flags, const int *prow,
                        const double *inst, int nrows, const double *mtab, const double *ptab);
+/* 1 (default): Ax/rhs are summed in exactly the reference's statement order (one stamp row per
+ * `+=` of b4ld.c:5235-5388); 0: addends to one pointer are pre-summed (fewer stamp rows) */
+int ngbCircuitSetExactOrder(ngb_circuit *c, int on);
 int ngbCircuitAddResistors(ngb_circuit *c, int n, const int *nodes /* [2][n] */, const double *g);
 int ngbCircuitAddCapacitors(ngb_circuit *c, int n, const int *nodes /* [2][n] */,
                             const double *par /* [3][n] C, m, ic */);

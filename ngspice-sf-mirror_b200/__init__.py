@@ -57,6 +57,8 @@ class Library:
         L.ngbBatchArrayBytes.restype = ctypes.c_long
         L.ngbBatchDevPtr.restype = ctypes.c_void_p
         L.ngbTranWaveBytes.restype = ctypes.c_long
+        L.ngbTranTicks.restype = ctypes.c_long
+        L.ngbTranDevWaves.restype = ctypes.c_void_p
         lay = (ctypes.c_int * 8)()
         L.ngbBsim4Layout(lay)
         self.layout = list(lay)
@@ -240,3 +242,28 @@ class Batch:
 
     def lufac_solve(self):
         self.lib.check(self.lib.L.ngbLuFacSolve(self.h), "ngbLuFacSolve")
+
+    # DCtran for the whole batch, resident on the device
+    def tran(self, max_points, save_eq):
+        """Run the transient analysis (options tstep/tstop/tmax/uic of the circuit) for every
+        sample; returns a TranResult."""
+        se = _i32(save_eq)
+        self.lib.check(self.lib.L.ngbTranRun(self.h, int(max_points), _ip(se), int(len(se))), "ngbTranRun (DCtran)")
+        return TranResult(self, int(max_points), int(len(se)))
+
+
+class TranResult:
+    def __init__(self, batch, max_points, nsave):
+        self.b, self.max_points, self.nsave = batch, max_points, nsave
+        S = batch.S
+        L = batch.lib.L
+        a = [np.zeros(S, np.int32) for _ in range(4)]
+        batch.lib.check(L.ngbTranStats(batch.h, *[_ip(v) for v in a]), "ngbTranStats")
+        self.accepted, self.rejected, self.numiter, self.npoints = a
+        self.ticks = int(L.ngbTranTicks(batch.h))
+
+    def waves(self):
+        S = self.b.S
+        t = np.zeros((S, self.max_points)); v = np.zeros((S, self.max_points, max(self.nsave, 1)))
+        self.b.lib.check(self.b.lib.L.ngbTranWaves(self.b.h, _dp(t), _dp(v)), "ngbTranWaves")
+        return t, v

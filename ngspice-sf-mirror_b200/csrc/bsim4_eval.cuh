@@ -58,6 +58,7 @@ typedef struct B4Ctx {
     double *state;             /* [NGB_NHIST][B4ST_COUNT][T]                             */
     double *op;                /* [B4O_COUNT][T] operating point (von is read back)      */
     int op_full;               /* 0: keep only von ; 1: export every B4O_* (parity runs) */
+    int split;                 /* 1: exact-order stamps (B4X_* rows live), 0: merged      */
     const double *x;           /* [2][neq1][S] solution buffers; xsel[s] picks CKTrhsOld  */
     int neq1;                  /* equations + 1 (row 0 is ground)                         */
     NgbCtl ctl;                /* per-sample control block                                */
@@ -215,7 +216,7 @@ NGB_HD void b4_tat(double vts, double vj, double Nvtmr, double *Tn, double *dTn_
 }
 
 /* state accessors: ring-rotated history, [hist][state][thread] */
-#define B4ST(h, k) c->state[((size_t)(((head) + (h)) % NGB_NHIST) * B4ST_COUNT + (k)) * c->T + t]
+#define B4ST(h, k) c->state[((size_t)(((head) + (h)) % c->ctl.nhist) * B4ST_COUNT + (k)) * c->T + t]
 
 /* Phase A: terminal voltages by INITF mode and Newton step limiting (b4ld.c:257-698). */
 NGB_HD void b4_fetch_limit(const B4Ctx *c, size_t t, int inst, int s, int head, int mode_ckt,
@@ -2885,6 +2886,18 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
 
     if (mode_ckt & NGB_MODEINITSMSIG) return NGB_E_UNSUPP;
 
+    /* deferred whole-state copies of DCtran: this thread owns its 29 states */
+    {
+        const int sop = NGB_LDG(&c->ctl.stateop[s]);
+        if (sop) {
+            for (int k = 0; k < B4ST_COUNT; k++) {
+                if (sop & NGB_OP_COPY01) B4ST(1, k) = B4ST(0, k);
+                if (sop & NGB_OP_COPY1_23) { const double v = B4ST(1, k); B4ST(2, k) = v; if (c->ctl.nhist > 3) B4ST(3, k) = v; }
+                if ((sop & NGB_OP_COPY23) && c->ctl.nhist > 3) B4ST(3, k) = B4ST(2, k);
+            }
+        }
+    }
+
     const int ChargeComputationNeeded =
         ((mode_ckt & (NGB_MODEDCTRANCURVE | NGB_MODEAC | NGB_MODETRAN | NGB_MODEINITSMSIG)) ||
          ((mode_ckt & NGB_MODETRANOP) && (mode_ckt & NGB_MODEUIC))) ? 1 : 0;
@@ -3161,6 +3174,19 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
         if (rbodyMod) {
             ceqqjs = cqbs + gcsbsb * vbs_jct;
             ceqqjd = cqbd + gcdbdb * vbd_jct;
+        }
+
+        /* BSIM4trunc (b4trunc.c:33-71): step-size estimates for CKTtrunc */
+        if (c->ctl.lte) {
+            ngb_lte_state(&c->ctl, s, c->state, B4ST_COUNT, (size_t)c->T, t, head, B4ST_qb, order);
+            ngb_lte_state(&c->ctl, s, c->state, B4ST_COUNT, (size_t)c->T, t, head, B4ST_qg, order);
+            ngb_lte_state(&c->ctl, s, c->state, B4ST_COUNT, (size_t)c->T, t, head, B4ST_qd, order);
+            if (rbodyMod) {
+                ngb_lte_state(&c->ctl, s, c->state, B4ST_COUNT, (size_t)c->T, t, head, B4ST_qbs, order);
+                ngb_lte_state(&c->ctl, s, c->state, B4ST_COUNT, (size_t)c->T, t, head, B4ST_qbd, order);
+            }
+            if (rgateMod == 3)
+                ngb_lte_state(&c->ctl, s, c->state, B4ST_COUNT, (size_t)c->T, t, head, B4ST_qgmid, order);
         }
 
         if (inittran) {
@@ -3466,52 +3492,60 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
     const double ggislg = w.ggislg, ggisls = w.ggisls, ggislb = w.ggislb;
 
     /* rows d', s', b': the reference applies the channel/junction term, then the GIDL and
-     * GISL terms, then (rbodyMod) the body-network term, in that order */
-    B4_STAMP(B4S_DPdp, (mult_i * (gdpr + w.gds + w.gbd - gdtotd + RevSum + gbdpdp - gIdtotd)
-                        + mult_q * (gcddb)) + mult_i * ggidld);
+     * GISL terms, then (rbodyMod) the body-network term, in that order.  B4_STAMP2 emits the
+     * later addend on its own row in exact-order mode and pre-summed otherwise. */
+    const int split = c->split;
+#define B4_STAMP2(K, V, KX, VX) do { if (split) { B4_STAMP(K, V); B4_STAMP(KX, VX); } else B4_STAMP(K, (V) + (VX)); } while (0)
+    B4_STAMP2(B4S_DPdp, (mult_i * (gdpr + w.gds + w.gbd - gdtotd + RevSum + gbdpdp - gIdtotd)
+                         + mult_q * (gcddb)), B4X_DPdp_g, mult_i * ggidld);
     B4_STAMP(B4S_DPd, -(mult_i * (gdpr + gdtot)));
-    B4_STAMP(B4S_DPgp, (mult_i * (Gm - gdtotg + gbdpg - gIdtotg) + mult_q * (gcdgb)) + mult_i * ggidlg);
-    B4_STAMP(B4S_DPsp, -(mult_i * (w.gds + gdtots + gIdtots + FwdSum - gbdpsp) - mult_q * (gcdsb))
-                       - mult_i * (ggidlg + ggidld + ggidlb));
-    B4_STAMP(B4S_DPbp, -(mult_i * (gjbd + gdtotb - Gmbs - gbdpb + gIdtotb) - mult_q * (gcdbb))
-                       + mult_i * ggidlb);
+    B4_STAMP2(B4S_DPgp, (mult_i * (Gm - gdtotg + gbdpg - gIdtotg) + mult_q * (gcdgb)), B4X_DPgp_g, mult_i * ggidlg);
+    B4_STAMP2(B4S_DPsp, -(mult_i * (w.gds + gdtots + gIdtots + FwdSum - gbdpsp) - mult_q * (gcdsb)),
+              B4X_DPsp_g, -(mult_i * (ggidlg + ggidld + ggidlb)));
+    B4_STAMP2(B4S_DPbp, -(mult_i * (gjbd + gdtotb - Gmbs - gbdpb + gIdtotb) - mult_q * (gcdbb)),
+              B4X_DPbp_g, mult_i * ggidlb);
 
     B4_STAMP(B4S_Ddp, -(mult_i * (gdpr - gdtotd)));
     B4_STAMP(B4S_Dd, mult_i * (gdpr + gdtot));
 
-    B4_STAMP(B4S_SPdp, -(mult_i * (w.gds + gstotd + RevSum - gbspdp + gIstotd) - mult_q * (gcsdb))
-                       - mult_i * (ggisls + ggislg + ggislb));
-    B4_STAMP(B4S_SPgp, (mult_q * (gcsgb) + mult_i * (gbspg - Gm - gstotg - gIstotg)) + mult_i * ggislg);
-    B4_STAMP(B4S_SPsp, (mult_i * (gspr + w.gds + w.gbs - gIstots - gstots + FwdSum + gbspsp)
-                        + mult_q * (gcssb)) + mult_i * ggisls);
+    B4_STAMP2(B4S_SPdp, -(mult_i * (w.gds + gstotd + RevSum - gbspdp + gIstotd) - mult_q * (gcsdb)),
+              B4X_SPdp_s, -(mult_i * (ggisls + ggislg + ggislb)));
+    B4_STAMP2(B4S_SPgp, (mult_q * (gcsgb) + mult_i * (gbspg - Gm - gstotg - gIstotg)), B4X_SPgp_s, mult_i * ggislg);
+    B4_STAMP2(B4S_SPsp, (mult_i * (gspr + w.gds + w.gbs - gIstots - gstots + FwdSum + gbspsp)
+                         + mult_q * (gcssb)), B4X_SPsp_s, mult_i * ggisls);
     B4_STAMP(B4S_SPs, -(mult_i * (gspr + gstot)));
-    B4_STAMP(B4S_SPbp, -(mult_i * (gjbs + gstotb + Gmbs - gbspb + gIstotb) - mult_q * (gcsbb))
-                       + mult_i * ggislb);
+    B4_STAMP2(B4S_SPbp, -(mult_i * (gjbs + gstotb + Gmbs - gbspb + gIstotb) - mult_q * (gcsbb)),
+              B4X_SPbp_s, mult_i * ggislb);
 
     B4_STAMP(B4S_Ssp, -(mult_i * (gspr - gstots)));
     B4_STAMP(B4S_Ss, mult_i * (gspr + gstot));
 
     {
-        double bpdp = (mult_q * gcbdb - mult_i * (gjbd - gbbdp + gIbtotd));
-        double bpgp = (mult_q * gcbgb - mult_i * (w.gbgs + gIbtotg));
-        double bpsp = (mult_q * gcbsb - mult_i * (gjbs - gbbsp + gIbtots));
-        double bpbp = (mult_i * (gjbd + gjbs - w.gbbs - gIbtotb) + mult_q * gcbbb);
-        /* gidl */
-        bpdp -= mult_i * ggidld;
-        bpgp -= mult_i * ggidlg;
-        bpsp += mult_i * (ggidlg + ggidld + ggidlb);
-        bpbp -= mult_i * ggidlb;
-        /* gisl */
-        bpdp += mult_i * (ggislg + ggisls + ggislb);
-        bpgp -= mult_i * ggislg;
-        bpsp -= mult_i * ggisls;
-        bpbp -= mult_i * ggislb;
-        if (rbodyMod) bpbp += mult_i * (B4I(grbpd) + B4I(grbps) + B4I(grbpb));
-        B4_STAMP(B4S_BPdp, bpdp);
-        B4_STAMP(B4S_BPgp, bpgp);
-        B4_STAMP(B4S_BPsp, bpsp);
-        B4_STAMP(B4S_BPbp, bpbp);
+        const double bpdp = (mult_q * gcbdb - mult_i * (gjbd - gbbdp + gIbtotd));
+        const double bpgp = (mult_q * gcbgb - mult_i * (w.gbgs + gIbtotg));
+        const double bpsp = (mult_q * gcbsb - mult_i * (gjbs - gbbsp + gIbtots));
+        const double bpbp = (mult_i * (gjbd + gjbs - w.gbbs - gIbtotb) + mult_q * gcbbb);
+        const double rb = rbodyMod ? mult_i * (B4I(grbpd) + B4I(grbps) + B4I(grbpb)) : 0.0;
+        if (split) {
+            B4_STAMP(B4S_BPdp, bpdp); B4_STAMP(B4S_BPgp, bpgp); B4_STAMP(B4S_BPsp, bpsp); B4_STAMP(B4S_BPbp, bpbp);
+            B4_STAMP(B4X_BPdp_g, -(mult_i * ggidld));
+            B4_STAMP(B4X_BPgp_g, -(mult_i * ggidlg));
+            B4_STAMP(B4X_BPsp_g, mult_i * (ggidlg + ggidld + ggidlb));
+            B4_STAMP(B4X_BPbp_g, -(mult_i * ggidlb));
+            B4_STAMP(B4X_BPdp_s, mult_i * (ggislg + ggisls + ggislb));
+            B4_STAMP(B4X_BPgp_s, -(mult_i * ggislg));
+            B4_STAMP(B4X_BPsp_s, -(mult_i * ggisls));
+            B4_STAMP(B4X_BPbp_s, -(mult_i * ggislb));
+            if (rbodyMod) B4_STAMP(B4X_BPbp_r, rb);
+        } else {
+            double v;
+            v = bpdp; v -= mult_i * ggidld; v += mult_i * (ggislg + ggisls + ggislb); B4_STAMP(B4S_BPdp, v);
+            v = bpgp; v -= mult_i * ggidlg; v -= mult_i * ggislg; B4_STAMP(B4S_BPgp, v);
+            v = bpsp; v += mult_i * (ggidlg + ggidld + ggidlb); v -= mult_i * ggisls; B4_STAMP(B4S_BPsp, v);
+            v = bpbp; v -= mult_i * ggidlb; v -= mult_i * ggislb; if (rbodyMod) v += rb; B4_STAMP(B4S_BPbp, v);
+        }
     }
+#undef B4_STAMP2
 
     if (rbodyMod) {
         const double grbpd = B4I(grbpd), grbdb = B4I(grbdb), grbpb = B4I(grbpb);

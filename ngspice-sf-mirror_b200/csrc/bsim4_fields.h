@@ -125,6 +125,21 @@ enum {
   B4S_COUNT               /* matrix + rhs stamp positions per instance */
 };
 
+/* "exact-order" extras: the reference applies several separate `+=` to some pointers (channel
+ * term, then GIDL, then GISL, then the body network: b4ld.c:5294-5364).  In exact-order mode
+ * each addend gets its own stamp row so that Ax is summed in precisely the reference order;
+ * in merged mode these positions are unused (-1) and the addends are pre-summed. */
+#define NGB_B4_EXTRA_FIELDS(X) \
+  X(DPdp_g) X(DPgp_g) X(DPsp_g) X(DPbp_g) X(BPdp_g) X(BPgp_g) X(BPsp_g) X(BPbp_g) \
+  X(SPdp_s) X(SPgp_s) X(SPsp_s) X(SPbp_s) X(BPdp_s) X(BPgp_s) X(BPsp_s) X(BPbp_s) X(BPbp_r)
+enum {
+  B4X_FIRST_ = B4S_COUNT - 1,
+#define X(n) B4X_##n,
+  NGB_B4_EXTRA_FIELDS(X)
+#undef X
+  B4S_TOTAL               /* rows of the per-instance stamp-position table */
+};
+
 /* packed per-instance flags */
 #define B4F_OFF        0x1
 #define B4F_RBODY_SH   1      /* 2 bits */

@@ -10,6 +10,7 @@
 #ifndef NGB_DEVSUP_CUH
 #define NGB_DEVSUP_CUH
 #include "ngb_common.h"
+#include "ngb_types.h"
 
 NGB_HD double ngb_limvds(double vnew, double vold)
 {
@@ -89,5 +90,64 @@ NGB_HD double ngb_integrate_trap(int order, double ag0, double ag1, double q0, d
 {
     if (order == 1) return ag0 * q0 + ag1 * q1;
     return -c1 * ag1 + ag0 * (q0 - q1);
+}
+
+/* CKTterr (src/spicelib/analysis/cktterr.c:10-79), TRAPEZOIDAL: the step size the local
+ * truncation error of one charge state allows.  q[0..order+1] = CKTstates[i][qcap],
+ * cc0/cc1 = CKTstate0/1[ccap], dold = CKTdeltaOld. */
+NGB_HD double ngb_terr(int order, const double *q, double cc0, double cc1, const double *dold,
+                       double delta, double reltol, double abstol, double chgtol, double trtol)
+{
+    double diff[4], deltmp[3], volttol, chargetol, tol, factor, del, a, b;
+    int i, j;
+    a = fabs(cc0); b = fabs(cc1);
+    volttol = abstol + reltol * ((a > b) ? a : b);
+    a = fabs(q[0]); b = fabs(q[1]);
+    chargetol = (a > b) ? a : b;
+    chargetol = reltol * ((chargetol > chgtol) ? chargetol : chgtol) / delta;
+    tol = (volttol > chargetol) ? volttol : chargetol;
+    for (i = order + 1; i >= 0; i--) diff[i] = q[i];
+    for (i = 0; i <= order; i++) deltmp[i] = dold[i];
+    j = order;
+    for (;;) {
+        for (i = 0; i <= j; i++) diff[i] = (diff[i] - diff[i + 1]) / deltmp[i];
+        if (--j < 0) break;
+        for (i = 0; i <= j; i++) deltmp[i] = deltmp[i + 1] + dold[i];
+    }
+    factor = (order == 1) ? .5 : .08333333333;
+    a = factor * fabs(diff[0]);
+    del = trtol * tol / ((abstol > a) ? abstol : a);
+    if (order == 2) del = sqrt(del);
+    return del;
+}
+
+/* atomic min on non-negative doubles (bit patterns of non-negative doubles order like integers) */
+NGB_HD void ngb_atomic_min_pos(double *addr, double v)
+{
+#ifdef __CUDA_ARCH__
+    atomicMin((unsigned long long *)addr, (unsigned long long)__double_as_longlong(v));
+#else
+    if (v < *addr) *addr = v;
+#endif
+}
+
+/* LTE contribution of one charge state of thread t: state array [hist][nstate][T] */
+NGB_HD void ngb_lte_state(const NgbCtl *k, int s, const double *state, int nstate, size_t T, size_t t,
+                          int head, int kq, int order)
+{
+    const int nh = k->nhist, S = k->S;
+    double q[4], dold[3];
+    const double delta = NGB_LDG(&k->delta[s]);
+    int i;
+#define LST(h, kk) state[((size_t)(((head) + (h)) % nh) * nstate + (kk)) * T + t]
+    const double cc0 = LST(0, kq + 1), cc1 = LST(1, kq + 1);
+    for (i = 0; i < 3; i++) dold[i] = NGB_LDG(&k->delta_old[(size_t)i * S + s]);
+    for (i = 0; i <= order + 1 && i < nh; i++) q[i] = LST(i, kq);
+    ngb_atomic_min_pos(&k->lte[s], ngb_terr(order, q, cc0, cc1, dold, delta, k->reltol, k->abstol, k->chgtol, k->trtol));
+    if (order == 1 && nh >= 4) {
+        q[3] = LST(3, kq);
+        ngb_atomic_min_pos(&k->lte2[s], ngb_terr(2, q, cc0, cc1, dold, delta, k->reltol, k->abstol, k->chgtol, k->trtol));
+    }
+#undef LST
 }
 #endif

@@ -87,6 +87,19 @@ __global__ void ngb_k_lu_block(const NgbLuCtx c)
     ngb_lu_sample(&c, s, threadIdx.x, blockDim.x, V, Rs, Z);
 }
 
+__global__ void __launch_bounds__(128)
+ngb_k_tran_control(const NgbTranCtx c)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < c.S) ngb_tran_control(&c, s);
+}
+
+__global__ void ngb_k_fill_f64(double *p, double value, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = value;
+}
+
 __global__ void ngb_k_clear_i32(int *p, int value, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -209,6 +222,18 @@ int ngb_launch_clear_i32(int *p, int value, int n)
     if (n <= 0) return 0;
     ngb_k_clear_i32<<<(unsigned)((n + 255) / 256), 256, 0, g_stream>>>(p, value, n);
     return post_launch("clear_i32");
+}
+
+int ngb_launch_tran_control(const NgbTranCtx *c)
+{
+    ngb_k_tran_control<<<(unsigned)((c->S + 127) / 128), 128, 0, g_stream>>>(*c);
+    return post_launch("tran_control");
+}
+int ngb_launch_fill_f64(double *p, double value, int n)
+{
+    if (n <= 0) return 0;
+    ngb_k_fill_f64<<<(unsigned)((n + 255) / 256), 256, 0, g_stream>>>(p, value, n);
+    return post_launch("fill_f64");
 }
 
 }  /* extern "C" */

@@ -33,7 +33,7 @@ static const char *b4_model_names[] = { NGB_B4_MODEL_FIELDS(X) NULL };
 static const char *b4_bin_names[] = { NGB_B4_BIN_FIELDS(X) NULL };
 static const char *b4_inst_names[] = { NGB_B4_INST_FIELDS(X) NULL };
 static const char *b4_node_names[] = { NGB_B4_NODE_FIELDS(X) NULL };
-static const char *b4_stamp_names[] = { NGB_B4_MAT_FIELDS(X) NGB_B4_RHS_FIELDS(X) NULL };
+static const char *b4_stamp_names[] = { NGB_B4_MAT_FIELDS(X) NGB_B4_RHS_FIELDS(X) NGB_B4_EXTRA_FIELDS(X) NULL };
 static const char *b4_op_names[] = { NGB_B4_OP_FIELDS(X) NULL };
 #undef X
 
@@ -146,6 +146,7 @@ ngb_circuit *ngbCircuitCreate(int neq, const int *node_type)
     c->opt.trtol = 7; c->opt.temp = 300.15; c->opt.vt0 = 1.38064852e-23 * (27.0 + 273.15) / 1.6021766208e-19;
     c->opt.xmu = 0.5; c->opt.gmin = 1e-12; c->opt.method = NGB_TRAPEZOIDAL; c->opt.maxorder = 2;
     c->opt.itl4 = 10; c->opt.itl1 = 100;
+    c->exact_order = 1;
     return c;
 }
 
@@ -185,6 +186,16 @@ int ngbCircuitSetOptions(ngb_circuit *c, const double d[15], const int i[5])
     o->method = i[0]; o->maxorder = i[1]; o->itl4 = i[2]; o->itl1 = i[3]; o->uic = i[4];
     if (o->method != NGB_TRAPEZOIDAL) { ngb_set_error("integration method %d not supported (TRAP only)", o->method); return NGB_E_METHOD; }
     if (o->maxorder > 2) { ngb_set_error("maxord %d not supported with TRAP", o->maxorder); return NGB_E_ORDER; }
+    return NGB_OK;
+}
+
+/* 1 (default): every `+=` of the reference load gets its own stamp row, so Ax/rhs are summed in
+ * exactly the reference order; 0: addends to the same pointer are pre-summed in the kernel
+ * (17 fewer stamp rows per BSIM4 instance, results equal to summation-order rounding) */
+int ngbCircuitSetExactOrder(ngb_circuit *c, int on)
+{
+    if (c->finalized) { ngb_set_error("stamp mode must be chosen before ngbCircuitFinalize"); return NGB_E_PANIC; }
+    c->exact_order = on ? 1 : 0;
     return NGB_OK;
 }
 
@@ -363,25 +374,63 @@ int ngbCircuitFinalize(ngb_circuit *c)
      *    the reference device table (bsim4 < cap < isrc < res < vsrc, dev.c:142-209), instances
      *    in list order, positions in load order */
     c->nstamp_rows = 0;
-    c->b4_spos = (int *)xcalloc((size_t)c->b4_n * B4S_COUNT, sizeof(int));
+    c->b4_spos = (int *)xcalloc((size_t)c->b4_n * B4S_TOTAL, sizeof(int));
     c->b4_slots = (int *)xcalloc((size_t)c->b4_n * B4S_MAT_COUNT, sizeof(int));
     for (i = 0; i < c->b4_n; i++) {
         const int fl = c->b4_flags[i];
         const int rg = B4F_RGATE(fl), rb = B4F_RBODY(fl);
         const int rds = (int)c->b4_mtab[(size_t)c->b4_prow[i] * B4M_COUNT + B4M_rdsMod];
-        /* right-hand side first, then matrix (b4ld.c:5024-5053 then :5235-5388) */
-        for (k = B4S_MAT_COUNT; k < B4S_COUNT; k++) {
-            int eq = c->b4_nodes[b4_rhs_role(k) * c->b4_n + i];
-            c->b4_spos[k * c->b4_n + i] = (b4_pos_written(k, rg, rb, rds) && eq > 0 && c->eq2col[eq] >= 0)
-                                        ? new_row(c, &cb, c->nnz + eq) : -1;
-        }
+        int ord[B4S_TOTAL], no = 0, q;
+        /* statement order of the serial load: right-hand side (b4ld.c:5024-5053), then matrix
+         * (b4ld.c:5235-5388) */
+        ord[no++] = B4R_dp; ord[no++] = B4R_gp;
+        if (rg == 2) ord[no++] = B4R_ge; else if (rg == 3) ord[no++] = B4R_gm;
+        if (!rb) { ord[no++] = B4R_bp; ord[no++] = B4R_sp; }
+        else { ord[no++] = B4R_db; ord[no++] = B4R_bp; ord[no++] = B4R_sb; ord[no++] = B4R_sp; }
+        if (rds) { ord[no++] = B4R_d; ord[no++] = B4R_s; }
+        if (rg == 1) { static const int g[] = { B4S_GEge, B4S_GPge, B4S_GEgp, B4S_GPgp, B4S_GPdp, B4S_GPsp, B4S_GPbp };
+            for (q = 0; q < 7; q++) ord[no++] = g[q]; }
+        else if (rg == 2) { static const int g[] = { B4S_GEge, B4S_GEgp, B4S_GEdp, B4S_GEsp, B4S_GEbp, B4S_GPge, B4S_GPgp, B4S_GPdp, B4S_GPsp, B4S_GPbp };
+            for (q = 0; q < 10; q++) ord[no++] = g[q]; }
+        else if (rg == 3) { static const int g[] = { B4S_GEge, B4S_GEgm, B4S_GMge, B4S_GMgm, B4S_GMdp, B4S_GMgp, B4S_GMsp, B4S_GMbp,
+                                                     B4S_DPgm, B4S_GPgm, B4S_SPgm, B4S_BPgm, B4S_GPgp, B4S_GPdp, B4S_GPsp, B4S_GPbp };
+            for (q = 0; q < 16; q++) ord[no++] = g[q]; }
+        else { static const int g[] = { B4S_GPgp, B4S_GPdp, B4S_GPsp, B4S_GPbp }; for (q = 0; q < 4; q++) ord[no++] = g[q]; }
+        if (rds) { static const int g[] = { B4S_Dgp, B4S_Dsp, B4S_Dbp, B4S_Sdp, B4S_Sgp, B4S_Sbp }; for (q = 0; q < 6; q++) ord[no++] = g[q]; }
+        { static const int g[] = { B4S_DPdp, B4S_DPd, B4S_DPgp, B4S_DPsp, B4S_DPbp, B4S_Ddp, B4S_Dd, B4S_SPdp, B4S_SPgp, B4S_SPsp,
+                                   B4S_SPs, B4S_SPbp, B4S_Ssp, B4S_Ss, B4S_BPdp, B4S_BPgp, B4S_BPsp, B4S_BPbp };
+          for (q = 0; q < 18; q++) ord[no++] = g[q]; }
+        if (c->exact_order) { static const int g[] = { B4X_DPdp_g, B4X_DPgp_g, B4X_DPsp_g, B4X_DPbp_g, B4X_BPdp_g, B4X_BPgp_g, B4X_BPsp_g, B4X_BPbp_g,
+                                                       B4X_SPdp_s, B4X_SPgp_s, B4X_SPsp_s, B4X_SPbp_s, B4X_BPdp_s, B4X_BPgp_s, B4X_BPsp_s, B4X_BPbp_s };
+          for (q = 0; q < 16; q++) ord[no++] = g[q]; }
+        if (rb) { static const int g[] = { B4S_DPdb, B4S_SPsb, B4S_DBdp, B4S_DBdb, B4S_DBbp, B4S_DBb, B4S_BPdb, B4S_BPb, B4S_BPsb, -1,
+                                           B4S_SBsp, B4S_SBbp, B4S_SBb, B4S_SBsb, B4S_Bdb, B4S_Bbp, B4S_Bsb, B4S_Bb };
+          for (q = 0; q < 18; q++) { if (g[q] >= 0) ord[no++] = g[q]; else if (c->exact_order) ord[no++] = B4X_BPbp_r; } }
+        for (k = 0; k < B4S_TOTAL; k++) c->b4_spos[k * c->b4_n + i] = -1;
         for (k = 0; k < B4S_MAT_COUNT; k++) {
             int rr, rc, slot = -1;
             b4_stamp_roles(k, &rr, &rc);
             if (b4_pos_allocated(k, rg, rb, rds))
                 slot = slot_lookup(c, c->b4_nodes[rr * c->b4_n + i], c->b4_nodes[rc * c->b4_n + i]);
             c->b4_slots[k * c->b4_n + i] = slot;
-            c->b4_spos[k * c->b4_n + i] = (slot >= 0 && b4_pos_written(k, rg, rb, rds)) ? new_row(c, &cb, slot) : -1;
+        }
+        for (q = 0; q < no; q++) {
+            k = ord[q];
+            if (k >= B4S_MAT_COUNT && k < B4S_COUNT) {
+                int eq = c->b4_nodes[b4_rhs_role(k) * c->b4_n + i];
+                if (b4_pos_written(k, rg, rb, rds) && eq > 0 && c->eq2col[eq] >= 0)
+                    c->b4_spos[k * c->b4_n + i] = new_row(c, &cb, c->nnz + eq);
+            } else {
+                int base = k, slot;
+                if (k >= B4S_COUNT) {                 /* extra addend: same slot as its base position */
+                    char nm[16]; int kk; const char *x = b4_stamp_names[k]; size_t l = strlen(x) - 2;
+                    memcpy(nm, x, l); nm[l] = 0; base = -1;
+                    for (kk = 0; kk < B4S_MAT_COUNT; kk++) if (!strcmp(b4_stamp_names[kk], nm)) base = kk;
+                }
+                slot = c->b4_slots[base * c->b4_n + i];
+                if (slot >= 0 && b4_pos_written(base, rg, rb, rds))
+                    c->b4_spos[k * c->b4_n + i] = new_row(c, &cb, slot);
+            }
         }
     }
     c->cap_spos = (int *)xcalloc((size_t)c->cap_n * 6 + 1, sizeof(int));
@@ -754,6 +803,12 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
     k->gmin = (double *)dalloc(b, "ctl.gmin", sizeof(double) * (size_t)S);
     k->diag_gmin = (double *)dalloc(b, "ctl.diag_gmin", sizeof(double) * (size_t)S);
     k->srcfact = (double *)dalloc(b, "ctl.srcfact", sizeof(double) * (size_t)S);
+    k->lte = (double *)dalloc(b, "ctl.lte", sizeof(double) * (size_t)S);
+    k->lte2 = (double *)dalloc(b, "ctl.lte2", sizeof(double) * (size_t)S);
+    k->stateop = (int *)dalloc(b, "ctl.stateop", sizeof(int) * (size_t)S);
+    k->nhist = c->opt.maxorder + 2;
+    if (k->nhist > NGB_NHIST) k->nhist = NGB_NHIST;
+    k->reltol = c->opt.reltol; k->abstol = c->opt.abstol; k->chgtol = c->opt.chgtol; k->trtol = c->opt.trtol;
     {
         int *one = (int *)xcalloc((size_t)S, sizeof(int)); double *dv = (double *)xcalloc((size_t)S, sizeof(double));
         for (i = 0; i < S; i++) one[i] = 1;
@@ -763,6 +818,9 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
         ngb_dev_h2d(k->gmin, dv, sizeof(double) * (size_t)S);
         for (i = 0; i < S; i++) dv[i] = 1.0;
         ngb_dev_h2d(k->srcfact, dv, sizeof(double) * (size_t)S);
+        for (i = 0; i < S; i++) dv[i] = 1e300;
+        ngb_dev_h2d(k->lte, dv, sizeof(double) * (size_t)S);
+        ngb_dev_h2d(k->lte2, dv, sizeof(double) * (size_t)S);
         free(one); free(dv);
     }
     b->x = (double *)dalloc(b, "x", sizeof(double) * 2 * (size_t)b->neq1 * S);
@@ -794,7 +852,7 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
         b->b4_prow = (int *)dev_dup(c->b4_prow, sizeof(int) * (size_t)c->b4_n);
         b->b4_flags = (int *)dev_dup(c->b4_flags, sizeof(int) * (size_t)c->b4_n);
         b->b4_nodes = (int *)dev_dup(c->b4_nodes, sizeof(int) * (size_t)c->b4_n * B4N_COUNT);
-        b->b4_spos = (int *)dev_dup(c->b4_spos, sizeof(int) * (size_t)c->b4_n * B4S_COUNT);
+        b->b4_spos = (int *)dev_dup(c->b4_spos, sizeof(int) * (size_t)c->b4_n * B4S_TOTAL);
     }
     if (c->cap_n) {
         const size_t T = (size_t)c->cap_n * S;
@@ -889,6 +947,7 @@ void ngb_fill_b4ctx(ngb_batch *b, B4Ctx *x)
     x->inst = b->b4_inst; x->flags = b->b4_flags; x->nodes = b->b4_nodes; x->spos = b->b4_spos;
     x->stamp = b->stamp; x->state = b->b4_state; x->op = b->b4_op; x->op_full = b->op_full;
     x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl; x->temp = c->opt.temp; x->vt0 = c->opt.vt0;
+    x->split = c->exact_order;
 }
 void ngb_fill_capctx(ngb_batch *b, NgbCapCtx *x)
 {

@@ -12,7 +12,7 @@ struct ngb_circuit {
     int neq;                       /* CKTmaxEqNum */
     int *node_type;                /* [neq+1] */
     NgbOpts opt;
-    int finalized, have_lu;
+    int finalized, have_lu, exact_order;
     /* device tables (host copies, instance order = reference list order) */
     int b4_n, b4_nrows; int *b4_nodes, *b4_flags, *b4_prow; double *b4_inst, *b4_mtab, *b4_ptab;
     int *b4_spos, *b4_slots;

@@ -41,7 +41,17 @@ NGB_HD int ngb_cap_thread(const NgbCapCtx *c, size_t t)
     const double m = NGB_LDG(&c->par[(size_t)1 * c->T + t]);
     double geq = 0.0, ceq = 0.0;
     int stamped = 0;
-#define CST(h, k) c->state[((size_t)(((head) + (h)) % NGB_NHIST) * 2 + (k)) * c->T + t]
+#define CST(h, k) c->state[((size_t)(((head) + (h)) % c->ctl.nhist) * 2 + (k)) * c->T + t]
+    {
+        const int sop = NGB_LDG(&c->ctl.stateop[s]);
+        if (sop) {
+            for (int k = 0; k < 2; k++) {
+                if (sop & NGB_OP_COPY01) CST(1, k) = CST(0, k);
+                if (sop & NGB_OP_COPY1_23) { const double v = CST(1, k); CST(2, k) = v; if (c->ctl.nhist > 3) CST(3, k) = v; }
+                if ((sop & NGB_OP_COPY23) && c->ctl.nhist > 3) CST(3, k) = CST(2, k);
+            }
+        }
+    }
     if (mode & (NGB_MODETRAN | NGB_MODEAC | NGB_MODETRANOP)) {
         const int cond1 = (((mode & NGB_MODEDC) && (mode & NGB_MODEINITJCT)) ||
                            ((mode & NGB_MODEUIC) && (mode & NGB_MODEINITTRAN)));
@@ -71,6 +81,9 @@ NGB_HD int ngb_cap_thread(const NgbCapCtx *c, size_t t)
             CST(0, 1) = cc;
             ceq = cc - ag0 * q0;
             geq = ag0 * cap;
+            /* CAPtrunc -> CKTterr */
+            if (c->ctl.lte)
+                ngb_lte_state(&c->ctl, s, c->state, 2, (size_t)c->T, t, head, 0, order);
             if (mode & NGB_MODEINITTRAN) CST(1, 1) = cc;
             stamped = 1;
         } else {

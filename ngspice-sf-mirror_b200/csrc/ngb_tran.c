@@ -1,9 +1,182 @@
-/* placeholder until the transient driver lands */
+/* ngb_tran.c -- host driver of the device-resident transient analysis.
+ *
+ * The host only enqueues "ticks" (one Newton step for every running sample: device loads,
+ * assembly + LU + solve + node convergence, controller) and polls a done counter; every
+ * decision of NIiter / DCtran is taken on the device per sample (ngb_tran.cuh).
+ * Stands in for DCtran (src/spicelib/analysis/dctran.c:66) called through CKTdoJob, for a
+ * whole batch of circuits at once.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "ngb_dev.h"
 #include "ngb_host.h"
 #include "../../include/ngb200.h"
-void ngb_tran_free(struct ngb_batch *b) { (void)b; }
-int ngbTranRun(ngb_batch *b, int max_points, const int *save_eq, int nsave) { (void)b; (void)max_points; (void)save_eq; (void)nsave; return NGB_E_UNSUPP; }
-int ngbTranStats(ngb_batch *b, int *a, int *r, int *n, int *p) { (void)b; (void)a; (void)r; (void)n; (void)p; return NGB_E_UNSUPP; }
-long ngbTranWaveBytes(ngb_batch *b) { (void)b; return 0; }
-int ngbTranWaves(ngb_batch *b, double *t, double *v) { (void)b; (void)t; (void)v; return NGB_E_UNSUPP; }
-int ngbCircuitAnalyze(ngb_circuit *c, const double *Ax) { (void)c; (void)Ax; return NGB_E_UNSUPP; }
+
+struct ngb_tran {
+    NgbTranCtx x;              /* device pointers */
+    int max_points, nsave;
+    int *d_save_eq;
+    long ticks;
+};
+
+static void *dz(size_t bytes) { return ngb_dev_malloc(bytes ? bytes : 8); }
+
+void ngb_tran_free(struct ngb_batch *b)
+{
+    struct ngb_tran *t = b->tran;
+    if (!t) return;
+    ngb_dev_free(t->x.phase); ngb_dev_free(t->x.iterno); ngb_dev_free(t->x.firsttime); ngb_dev_free(t->x.nbreak);
+    ngb_dev_free(t->x.npts); ngb_dev_free(t->x.brkflag); ngb_dev_free(t->x.accepted); ngb_dev_free(t->x.rejected);
+    ngb_dev_free(t->x.numiter); ngb_dev_free(t->x.timepts); ngb_dev_free(t->x.save_delta); ngb_dev_free(t->x.old_delta);
+    ngb_dev_free(t->x.breaks); ngb_dev_free(t->x.out_time); ngb_dev_free(t->x.out_val); ngb_dev_free(t->x.ndone);
+    ngb_dev_free(t->d_save_eq);
+    free(t);
+    b->tran = NULL;
+}
+
+static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsave)
+{
+    const ngb_circuit *c = b->c;
+    const int S = b->S;
+    struct ngb_tran *t;
+    NgbTranCtx *x;
+    int i, s;
+    ngb_tran_free(b);
+    t = (struct ngb_tran *)calloc(1, sizeof *t);
+    b->tran = t;
+    x = &t->x;
+    x->ctl = b->ctl; x->S = S; x->neq1 = b->neq1; x->x = b->x;
+    x->nodeconv = b->nodeconv; x->nodeconv_w = b->nodeconv;
+    x->phase = (int *)dz(sizeof(int) * S); x->iterno = (int *)dz(sizeof(int) * S);
+    x->firsttime = (int *)dz(sizeof(int) * S); x->nbreak = (int *)dz(sizeof(int) * S);
+    x->npts = (int *)dz(sizeof(int) * S); x->brkflag = (int *)dz(sizeof(int) * S);
+    x->accepted = (int *)dz(sizeof(int) * S); x->rejected = (int *)dz(sizeof(int) * S);
+    x->numiter = (int *)dz(sizeof(int) * S); x->timepts = (int *)dz(sizeof(int) * S);
+    x->save_delta = (double *)dz(sizeof(double) * S); x->old_delta = (double *)dz(sizeof(double) * S);
+    x->breaks = (double *)dz(sizeof(double) * NGB_MAXBRK * S);
+    x->out_time = (double *)dz(sizeof(double) * (size_t)S * max_points);
+    x->out_val = (double *)dz(sizeof(double) * (size_t)S * max_points * (nsave ? nsave : 1));
+    x->ndone = (int *)dz(sizeof(int) * 2);
+    t->d_save_eq = (int *)dz(sizeof(int) * (nsave ? nsave : 1));
+    if (!x->out_val || !x->out_time || !x->breaks) { ngb_set_error("transient buffers: out of device memory"); return NGB_E_PANIC; }
+    if (nsave) ngb_dev_h2d(t->d_save_eq, save_eq, sizeof(int) * (size_t)nsave);
+    x->save_eq = t->d_save_eq; x->max_points = max_points; x->nsave = nsave;
+    t->max_points = max_points; t->nsave = nsave;
+    x->tstep = c->opt.tstep; x->tstop = c->opt.tstop; x->tmax = c->opt.tmax; x->tstart = c->opt.tstart;
+    x->delmin = c->opt.delmin; x->minbreak = c->opt.minbreak; x->xmu = c->opt.xmu;
+    x->maxorder = c->opt.maxorder; x->uic = c->opt.uic; x->max_iter_tran = c->opt.itl4; x->max_iter_dc = c->opt.itl1;
+    if (x->minbreak == 0) x->minbreak = x->tmax * 5e-5;            /* dctran.c:163-164 */
+
+    /* initial per-sample state: DCtran entry (dctran.c:117-236) */
+    {
+        int *iv = (int *)calloc((size_t)S, sizeof(int));
+        double *dv = (double *)calloc((size_t)S * NGB_MAXBRK, sizeof(double));
+        const int mode0 = (c->opt.uic ? NGB_MODEUIC : 0) | NGB_MODETRANOP | NGB_MODEINITJCT;
+        for (s = 0; s < S; s++) iv[s] = mode0;
+        ngb_dev_h2d(b->ctl.mode, iv, sizeof(int) * S);
+        for (s = 0; s < S; s++) iv[s] = c->opt.uic ? NGB_PH_OPUIC : NGB_PH_DCOP;
+        ngb_dev_h2d(x->phase, iv, sizeof(int) * S);
+        for (s = 0; s < S; s++) iv[s] = 1;
+        ngb_dev_h2d(x->firsttime, iv, sizeof(int) * S);
+        ngb_dev_h2d(b->ctl.active, iv, sizeof(int) * S);
+        ngb_dev_h2d(b->ctl.order, iv, sizeof(int) * S);
+        for (s = 0; s < S; s++) iv[s] = 2;
+        ngb_dev_h2d(x->nbreak, iv, sizeof(int) * S);
+        /* NIiter under MODETRANOP|MODEUIC swaps rhs/rhsOld before its single CKTload */
+        for (s = 0; s < S; s++) iv[s] = c->opt.uic ? 1 : 0;
+        ngb_dev_h2d(b->ctl.xsel, iv, sizeof(int) * S);
+        memset(iv, 0, sizeof(int) * S);
+        ngb_dev_h2d(b->ctl.head, iv, sizeof(int) * S);
+        ngb_dev_h2d(b->ctl.noncon, iv, sizeof(int) * S);
+        ngb_dev_h2d(b->ctl.err, iv, sizeof(int) * S);
+        ngb_dev_h2d(b->ctl.stateop, iv, sizeof(int) * S);
+        ngb_dev_h2d(b->nodeconv, iv, sizeof(int) * S);
+        for (i = 0; i < NGB_MAXBRK; i++) for (s = 0; s < S; s++) dv[(size_t)i * S + s] = (i == 0) ? 0.0 : c->opt.tstop;
+        ngb_dev_h2d(x->breaks, dv, sizeof(double) * NGB_MAXBRK * S);
+        memset(dv, 0, sizeof(double) * S);
+        ngb_dev_h2d(b->ctl.time, dv, sizeof(double) * S);
+        ngb_dev_h2d(b->ctl.delta, dv, sizeof(double) * S);
+        ngb_dev_h2d(b->ctl.ag0, dv, sizeof(double) * S);
+        ngb_dev_h2d(b->ctl.ag1, dv, sizeof(double) * S);
+        ngb_dev_h2d(b->ctl.diag_gmin, dv, sizeof(double) * S);
+        free(iv); free(dv);
+    }
+    ngb_launch_fill_f64(b->ctl.lte, 1e300, S);
+    ngb_launch_fill_f64(b->ctl.lte2, 1e300, S);
+    ngb_dev_memset(b->x, 0, sizeof(double) * 2 * (size_t)b->neq1 * S);
+    if (b->b4_state) ngb_dev_memset(b->b4_state, 0, sizeof(double) * NGB_NHIST * B4ST_COUNT * (size_t)c->b4_n * S);
+    if (b->cap_state) ngb_dev_memset(b->cap_state, 0, sizeof(double) * NGB_NHIST * 2 * (size_t)c->cap_n * S);
+    if (b->b4_op) ngb_dev_memset(b->b4_op, 0, sizeof(double) * B4O_COUNT * (size_t)c->b4_n * S);
+    return ngb_dev_sync();
+}
+
+static int enqueue_tick(ngb_batch *b, int with_lu)
+{
+    int r;
+    if ((r = ngb_enqueue_load(b))) return r;
+    if (with_lu) {
+        NgbLuCtx lx;
+        ngb_fill_luctx(b, &lx, 1, 1);
+        if ((r = ngb_launch_lu(&lx))) return r;
+    }
+    return ngb_launch_tran_control(&b->tran->x);
+}
+
+int ngbTranRun(ngb_batch *b, int max_points, const int *save_eq, int nsave)
+{
+    const int S = b->S;
+    int r, done[2] = { 0, 0 }, e[4] = { 0, 0, 0, 0 };
+    long tick = 0, max_ticks;
+    int check_every = 64;
+    if (!b->have_lu) { ngb_set_error("no LU pattern set for this circuit"); return NGB_E_PANIC; }
+    if (b->c->opt.tstop <= 0 || b->c->opt.tstep <= 0) { ngb_set_error("transient parameters not set"); return NGB_E_PANIC; }
+    if ((r = tran_setup(b, max_points, save_eq, nsave))) return r;
+    ngb_dev_memset(b->errflag, 0, sizeof(int) * 4);
+    max_ticks = 64L * max_points + 1024;
+    if (b->c->opt.uic) {
+        /* CKTop under UIC: one CKTload, no factorisation (niiter.c:41-47) */
+        if ((r = enqueue_tick(b, 0))) return r;
+        tick++;
+    }
+    while (tick < max_ticks) {
+        int i;
+        for (i = 0; i < check_every; i++, tick++)
+            if ((r = enqueue_tick(b, 1))) return r;
+        ngb_dev_d2h(done, b->tran->x.ndone, sizeof(int) * 2);
+        ngb_dev_d2h(e, b->errflag, sizeof e);
+        if (e[0]) { ngb_set_error("device load reported error %d", e[0]); return e[0]; }
+        if (done[0] >= S) break;
+    }
+    b->tran->ticks = tick;
+    if (done[0] < S) { ngb_set_error("transient did not finish within %ld Newton steps", max_ticks); return NGB_E_ITERLIM; }
+    return NGB_OK;
+}
+
+int ngbTranStats(ngb_batch *b, int *accepted, int *rejected, int *numiter, int *npoints)
+{
+    struct ngb_tran *t = b->tran;
+    const size_t n = sizeof(int) * (size_t)b->S;
+    if (!t) return NGB_E_PANIC;
+    if (accepted) ngb_dev_d2h(accepted, t->x.accepted, n);
+    if (rejected) ngb_dev_d2h(rejected, t->x.rejected, n);
+    if (numiter) ngb_dev_d2h(numiter, t->x.numiter, n);
+    if (npoints) ngb_dev_d2h(npoints, t->x.npts, n);
+    return NGB_OK;
+}
+long ngbTranWaveBytes(ngb_batch *b)
+{
+    struct ngb_tran *t = b->tran;
+    return t ? (long)(sizeof(double) * (size_t)b->S * t->max_points * (t->nsave ? t->nsave : 1)) : 0;
+}
+int ngbTranWaves(ngb_batch *b, double *times, double *values)
+{
+    struct ngb_tran *t = b->tran;
+    if (!t) return NGB_E_PANIC;
+    if (times) ngb_dev_d2h(times, t->x.out_time, sizeof(double) * (size_t)b->S * t->max_points);
+    if (values && t->nsave) ngb_dev_d2h(values, t->x.out_val, sizeof(double) * (size_t)b->S * t->max_points * t->nsave);
+    return NGB_OK;
+}
+long ngbTranTicks(ngb_batch *b) { return b->tran ? b->tran->ticks : 0; }
+void *ngbTranDevWaves(ngb_batch *b, int which) { return b->tran ? (which ? (void *)b->tran->x.out_val : (void *)b->tran->x.out_time) : NULL; }
+int ngbCircuitAnalyze(ngb_circuit *c, const double *Ax) { (void)c; (void)Ax; ngb_set_error("own symbolic analysis not built yet"); return NGB_E_UNSUPP; }

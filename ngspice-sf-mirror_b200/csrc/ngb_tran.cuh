@@ -1,0 +1,327 @@
+/* ngb_tran.cuh -- per-sample transient controller: the control flow of NIiter and DCtran
+ * executed on the device, one thread per sample, once per Newton step ("tick").
+ *
+ * What it mirrors (paths under /root/reference/src):
+ *   maths/ni/niiter.c:28-367        iteration count, CKTnoncon / NIconvTest decision, the INITF
+ *                                   state machine, the rhs/rhsOld pointer swap
+ *   spicelib/analysis/dctran.c:66-971 (non-XSPICE, non-SHARED_MODULE build)
+ *                                   initial step, breakpoint table, step rejection on
+ *                                   non-convergence (delta/8), CKTtrunc accept/reject with the
+ *                                   order-2 trial, delmin guard, state-ring rotation, output
+ *   maths/ni/nicomcof.c:14-47       TRAPEZOIDAL coefficients
+ *   spicelib/analysis/cktsetbk.c, cktclrbk.c, maths/misc/equality.c  breakpoint helpers
+ *
+ * The heavy parts of a tick (device loads, LU, solve, LTE estimates, node convergence) are
+ * done by the other kernels; this thread only takes the decisions and rewrites the sample's
+ * control block for the next tick.  Every sample has its own time axis.
+ */
+#ifndef NGB_TRAN_CUH
+#define NGB_TRAN_CUH
+#include "ngb_types.h"
+
+#define NGB_PH_IDLE   0
+#define NGB_PH_OPUIC  1      /* the single CKTload of NIiter under MODETRANOP|MODEUIC          */
+#define NGB_PH_DCOP   2      /* Newton iteration of the DC operating point (CKTop)             */
+#define NGB_PH_TRAN   3      /* Newton iteration of a transient time point                     */
+#define NGB_PH_DONE   4
+#define NGB_PH_FAIL   5
+#define NGB_MAXBRK    16
+
+typedef struct NgbTranCtx {
+    NgbCtl ctl;
+    int S, neq1;
+    double *x;                 /* [2][neq1][S] */
+    const int *nodeconv;       /* [S] node part of NIconvTest from the LU kernel */
+    int *nodeconv_w;           /* same array, for the reset */
+    /* per-sample controller state, [S] */
+    int *phase, *iterno, *firsttime, *nbreak, *npts, *brkflag;
+    int *accepted, *rejected, *numiter, *timepts;
+    double *save_delta, *old_delta, *breaks;   /* breaks [NGB_MAXBRK][S] */
+    /* outputs */
+    int max_points, nsave;
+    const int *save_eq;        /* [nsave] */
+    double *out_time;          /* [S][max_points] */
+    double *out_val;           /* [S][max_points][nsave] */
+    int *ndone;                /* [1] samples in DONE or FAIL */
+    /* circuit scalars */
+    double tstep, tstop, tmax, tstart, delmin, minbreak, xmu;
+    int maxorder, uic, max_iter_tran, max_iter_dc;
+} NgbTranCtx;
+
+NGB_HD int ngb_almost_equal_ulps(double A, double B, int maxUlps)
+{
+    long long a, b, d;
+    if (A == B) return 1;
+#ifdef __CUDA_ARCH__
+    a = __double_as_longlong(A); b = __double_as_longlong(B);
+#else
+    union { double d; long long i; } ua, ub; ua.d = A; ub.d = B; a = ua.i; b = ub.i;
+#endif
+    if (a < 0) a = (long long)0x8000000000000000ULL - a;
+    if (b < 0) b = (long long)0x8000000000000000ULL - b;
+    d = a - b; if (d < 0) d = -d;
+    return d <= maxUlps;
+}
+
+#define TBRK(i) c->breaks[(size_t)(i) * S + s]
+
+/* CKTclrBreak */
+NGB_HD void ngb_clr_break(const NgbTranCtx *c, int s)
+{
+    const int S = c->S;
+    int nb = c->nbreak[s];
+    if (nb > 2) {
+        for (int j = 1; j < nb; j++) TBRK(j - 1) = TBRK(j);
+        c->nbreak[s] = nb - 1;
+    } else {
+        TBRK(0) = TBRK(1);
+        TBRK(1) = c->tstop;
+    }
+}
+
+/* CKTsetBreak */
+NGB_HD int ngb_set_break(const NgbTranCtx *c, int s, double time, double now)
+{
+    const int S = c->S;
+    int nb = c->nbreak[s];
+    if (ngb_almost_equal_ulps(time, now, 3)) return NGB_OK;
+    if (now > time) return NGB_E_PANIC;
+    for (int i = 0; i < nb; i++) {
+        if (TBRK(i) > time) {
+            if ((TBRK(i) - time) <= c->minbreak) { TBRK(i) = time; return NGB_OK; }
+            if (i > 0 && time - TBRK(i - 1) <= c->minbreak) return NGB_OK;
+            if (nb >= NGB_MAXBRK) return NGB_E_PANIC;
+            for (int j = nb; j > i; j--) TBRK(j) = TBRK(j - 1);
+            TBRK(i) = time;
+            c->nbreak[s] = nb + 1;
+            return NGB_OK;
+        }
+    }
+    if (time - TBRK(nb - 1) <= c->minbreak) return NGB_OK;
+    if (nb >= NGB_MAXBRK) return NGB_E_PANIC;
+    TBRK(nb) = time;
+    c->nbreak[s] = nb + 1;
+    return NGB_OK;
+}
+
+/* NIcomCof, TRAPEZOIDAL */
+NGB_HD void ngb_comcof(const NgbTranCtx *c, int s, int order, double delta)
+{
+    if (order == 1) {
+        c->ctl.ag0[s] = 1 / delta;
+        c->ctl.ag1[s] = -1 / delta;
+    } else {
+        c->ctl.ag0[s] = 1.0 / delta / (1.0 - c->xmu);
+        c->ctl.ag1[s] = c->xmu / (1.0 - c->xmu);
+    }
+}
+
+/* start the Newton iteration of the next attempt at a time point: top of the for(;;) of
+ * dctran.c:666-707 */
+NGB_HD void ngb_begin_point(const NgbTranCtx *c, int s)
+{
+    const int S = c->S;
+    const double delta = c->ctl.delta[s];
+    c->old_delta[s] = delta;
+    c->ctl.time[s] += delta;
+    c->ctl.delta_old[(size_t)0 * S + s] = delta;
+    ngb_comcof(c, s, c->ctl.order[s], delta);
+    c->iterno[s] = 0;
+    c->phase[s] = NGB_PH_TRAN;
+}
+
+NGB_HD void ngb_finish(const NgbTranCtx *c, int s, int phase, int err)
+{
+    c->phase[s] = phase;
+    c->ctl.active[s] = 0;
+    if (err) c->ctl.err[s] = err;
+#ifdef __CUDA_ARCH__
+    atomicAdd(c->ndone, 1);
+#else
+    c->ndone[0] += 1;
+#endif
+}
+
+/* the nextTime: label of dctran.c:355-665 -- accept the point, output, breakpoints, rotate */
+NGB_HD void ngb_next_time(const NgbTranCtx *c, int s)
+{
+    const int S = c->S;
+    const double time = c->ctl.time[s];
+    const int mode = c->ctl.mode[s];
+    double delta;
+    /* CKTaccept: no breakpoint-generating sources on this path (DC / SIN) */
+    if (time > TBRK(0)) ngb_clr_break(c, s);
+    c->accepted[s] += 1;
+    c->brkflag[s] = 0;
+    /* CKTdump of CKTrhsOld */
+    if (((mode & NGB_MODEUIC) && time > 0 && time >= c->tstart) || (!(mode & NGB_MODEUIC) && time >= c->tstart)) {
+        const int n = c->npts[s];
+        if (n < c->max_points) {
+            const double *xo = c->x + (size_t)c->ctl.xsel[s] * c->neq1 * S;
+            c->out_time[(size_t)s * c->max_points + n] = time;
+            for (int k = 0; k < c->nsave; k++)
+                c->out_val[((size_t)s * c->max_points + n) * c->nsave + k] = xo[(size_t)c->save_eq[k] * S + s];
+        }
+        c->npts[s] = n + 1;
+    }
+    if (ngb_almost_equal_ulps(time, c->tstop, 100)) { ngb_finish(c, s, NGB_PH_DONE, 0); return; }
+
+    /* resume: */
+    delta = c->ctl.delta[s];
+    delta = NGB_MIN(delta, c->tmax);
+    if (ngb_almost_equal_ulps(time, TBRK(0), 100) || TBRK(0) - time <= c->delmin) {
+        double lim = NGB_MIN(c->save_delta[s], TBRK(1) - TBRK(0));
+        c->ctl.order[s] = 1;
+        lim = .1 * lim;
+        delta = NGB_MIN(delta, lim);
+        if (c->firsttime[s]) {
+            if (mode & NGB_MODEUIC) ngb_set_break(c, s, c->tstep, time);
+            delta /= 10;
+        }
+        { const double lo = c->delmin * 2.0; delta = NGB_MAX(delta, lo); }
+    } else if (time + delta >= TBRK(0)) {
+        c->save_delta[s] = delta;
+        delta = TBRK(0) - time;
+        c->brkflag[s] = 1;
+    } else if (time + 1.9 * delta > TBRK(0)) {
+        c->save_delta[s] = delta;
+        delta = (TBRK(0) - time) / 2.;
+    }
+    c->ctl.delta[s] = delta;
+    for (int i = 5; i >= 0; i--)
+        c->ctl.delta_old[(size_t)(i + 1) * S + s] = c->ctl.delta_old[(size_t)i * S + s];
+    c->ctl.delta_old[(size_t)0 * S + s] = delta;
+    /* rotate the state ring: states[i+1] = states[i], states[0] = old states[maxOrder+1] */
+    {
+        const int nh = c->ctl.nhist;
+        const int sop = c->ctl.stateop[s];
+        c->ctl.head[s] = (c->ctl.head[s] + nh - 1) % nh;
+        /* pending copies seen from the rotated frame: state1 = state0 is what the rotation itself
+         * does; state2 = state1, state3 = state1 leaves only state3 = state2 to do */
+        c->ctl.stateop[s] = (sop & NGB_OP_COPY1_23) ? NGB_OP_COPY23 : 0;
+    }
+    ngb_begin_point(c, s);
+}
+
+/* One controller step for sample s, after the load (+ LU + solve) of this tick. */
+NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
+{
+    const int S = c->S;
+    int phase = c->phase[s];
+    if (phase == NGB_PH_IDLE || phase == NGB_PH_DONE || phase == NGB_PH_FAIL) return;
+    /* state copies requested for the load that just ran are done */
+    const int sop_done = c->ctl.stateop[s];
+    c->ctl.stateop[s] = 0;
+    (void)sop_done;
+
+    if (c->ctl.err[s]) { ngb_finish(c, s, NGB_PH_FAIL, c->ctl.err[s]); return; }
+
+    if (phase == NGB_PH_OPUIC) {
+        /* CKTop returned OK after one CKTload; DCtran sets up the transient (dctran.c:271-330) */
+        c->timepts[s] += 1;
+        c->ctl.order[s] = 1;
+        for (int i = 0; i < 7; i++) c->ctl.delta_old[(size_t)i * S + s] = c->tmax;
+        c->ctl.delta[s] = NGB_MIN(c->tstop / 100, c->tstep) / 10;
+        c->save_delta[s] = c->tstop / 50;
+        c->ctl.mode[s] = (c->ctl.mode[s] & NGB_MODEUIC) | NGB_MODETRAN | NGB_MODEINITTRAN;
+        c->ctl.ag0[s] = 0; c->ctl.ag1[s] = 0;
+        c->ctl.stateop[s] = NGB_OP_COPY01;
+        c->ctl.noncon[s] = 0; c->nodeconv_w[s] = 0; c->ctl.lte[s] = 1e300; c->ctl.lte2[s] = 1e300;
+        ngb_next_time(c, s);
+        return;
+    }
+
+    /* ---- NIiter after SMPsolve (niiter.c:254-362) ---- */
+    int iterno = c->iterno[s] + 1;
+    int mode = c->ctl.mode[s];
+    int noncon = c->ctl.noncon[s];
+    const int maxiter = (phase == NGB_PH_DCOP) ? NGB_MAX(c->max_iter_dc, 100) : NGB_MAX(c->max_iter_tran, 100);
+    int niret = -1;                          /* -1: keep iterating, 0: converged, >0: error */
+    c->iterno[s] = iterno;
+    if (iterno > maxiter) {
+        niret = NGB_E_ITERLIM;
+    } else {
+        if ((noncon == 0) && (iterno != 1)) noncon = c->nodeconv[s] ? 1 : 0;   /* NIconvTest */
+        else noncon = 1;
+        if (mode & NGB_MODEINITFLOAT) {
+            if (noncon == 0) niret = NGB_OK;
+        } else if (mode & NGB_MODEINITJCT) {
+            mode = (mode & ~NGB_INITF) | NGB_MODEINITFIX;
+        } else if (mode & NGB_MODEINITFIX) {
+            if (noncon == 0) mode = (mode & ~NGB_INITF) | NGB_MODEINITFLOAT;
+        } else if (mode & (NGB_MODEINITTRAN | NGB_MODEINITPRED | NGB_MODEINITSMSIG)) {
+            mode = (mode & ~NGB_INITF) | NGB_MODEINITFLOAT;
+        } else {
+            niret = NGB_E_PANIC;
+        }
+    }
+    /* reset the per-tick flags for the next load */
+    const double lte = c->ctl.lte[s], lte2 = c->ctl.lte2[s];
+    c->ctl.noncon[s] = 0; c->nodeconv_w[s] = 0; c->ctl.lte[s] = 1e300; c->ctl.lte2[s] = 1e300;
+
+    if (niret < 0) {
+        c->ctl.mode[s] = mode;
+        c->ctl.xsel[s] ^= 1;                 /* SWAP(CKTrhs, CKTrhsOld) */
+        return;
+    }
+    c->numiter[s] += iterno;
+
+    if (phase == NGB_PH_DCOP) {
+        if (niret != NGB_OK) { ngb_finish(c, s, NGB_PH_FAIL, niret); return; }   /* no gmin/source stepping yet */
+        c->timepts[s] += 1;
+        c->ctl.order[s] = 1;
+        for (int i = 0; i < 7; i++) c->ctl.delta_old[(size_t)i * S + s] = c->tmax;
+        c->ctl.delta[s] = NGB_MIN(c->tstop / 100, c->tstep) / 10;
+        c->save_delta[s] = c->tstop / 50;
+        c->ctl.mode[s] = (mode & NGB_MODEUIC) | NGB_MODETRAN | NGB_MODEINITTRAN;
+        c->ctl.ag0[s] = 0; c->ctl.ag1[s] = 0;
+        c->ctl.stateop[s] = NGB_OP_COPY01;
+        ngb_next_time(c, s);
+        return;
+    }
+
+    /* ---- DCtran after NIiter (dctran.c:708-913) ---- */
+    {
+        const int firsttime = c->firsttime[s];
+        double delta = c->ctl.delta[s];
+        c->timepts[s] += 1;
+        c->ctl.mode[s] = (mode & NGB_MODEUIC) | NGB_MODETRAN | NGB_MODEINITPRED;
+        if (firsttime) c->ctl.stateop[s] |= NGB_OP_COPY1_23;
+        if (niret != NGB_OK) {
+            c->ctl.time[s] -= delta;
+            c->rejected[s] += 1;
+            delta = delta / 8;
+            if (firsttime) c->ctl.mode[s] = (mode & NGB_MODEUIC) | NGB_MODETRAN | NGB_MODEINITTRAN;
+            c->ctl.order[s] = 1;
+        } else {
+            if (firsttime) {
+                c->firsttime[s] = 0;
+                ngb_next_time(c, s);
+                return;
+            }
+            /* CKTtrunc: *timeStep = MIN(2 * *timeStep, timetemp) */
+            double newdelta = NGB_MIN(2 * delta, lte);
+            if (newdelta > .9 * delta) {
+                if ((c->ctl.order[s] == 1) && (c->maxorder > 1)) {
+                    newdelta = NGB_MIN(2 * delta, lte2);
+                    c->ctl.order[s] = 2;
+                    if (newdelta <= 1.05 * delta) c->ctl.order[s] = 1;
+                }
+                c->ctl.delta[s] = newdelta;
+                ngb_next_time(c, s);
+                return;
+            }
+            c->ctl.time[s] -= delta;
+            c->rejected[s] += 1;
+            delta = newdelta;
+        }
+        if (delta <= c->delmin) {
+            if (c->old_delta[s] > c->delmin) delta = c->delmin;
+            else { ngb_finish(c, s, NGB_PH_FAIL, NGB_E_TIMESTEP); return; }
+        }
+        c->ctl.delta[s] = delta;
+        ngb_begin_point(c, s);
+    }
+}
+#undef TBRK
+#endif

@@ -35,7 +35,19 @@ typedef struct NgbCtl {
     double *gmin;         /* CKTgmin                                                    */
     double *diag_gmin;    /* CKTdiagGmin                                                */
     double *srcfact;      /* CKTsrcFact                                                 */
+    /* local-truncation-error estimates written by the load kernels (CKTtrunc/CKTterr):
+     * lte for the current CKTorder, lte2 for a trial with order 2 (dctran.c:794, 823) */
+    double *lte, *lte2;
+    int *stateop;         /* pending whole-state copies, applied by the next load (NGB_OP_*) */
+    /* shared scalars */
+    int nhist;            /* state vectors in the ring: CKTmaxOrder + 2 (cktsetup.c:192)  */
+    double reltol, abstol, chgtol, trtol;
 } NgbCtl;
+
+/* deferred state copies of dctran.c (each device thread owns its own state slice) */
+#define NGB_OP_COPY01   1   /* memcpy(CKTstate1, CKTstate0)           dctran.c:319-322 */
+#define NGB_OP_COPY1_23 2   /* state2 = state1; state3 = state1       dctran.c:711-716 */
+#define NGB_OP_COPY23   4   /* the same copy seen after the ring rotated once          */
 
 /* source waveform codes (vsrcdefs.h:146-160) */
 #define NGB_FN_PULSE 1

@@ -57,4 +57,11 @@ int ngb_launch_lu(const NgbLuCtx *c)
     return 0;
 }
 int ngb_launch_clear_i32(int *p, int value, int n) { for (int i = 0; i < n; i++) p[i] = value; return 0; }
+int ngb_launch_fill_f64(double *p, double value, int n) { for (int i = 0; i < n; i++) p[i] = value; return 0; }
+int ngb_launch_tran_control(const NgbTranCtx *c)
+{
+    g_launches++;
+    for (int s = 0; s < c->S; s++) ngb_tran_control(c, s);
+    return 0;
+}
 }
