@@ -38,14 +38,21 @@ def ro_cards():
     return cards
 
 
-def ro_netlist(stages, tran=".tran .1ns 150ns uic", extra_opts=""):
+def ro_netlist(stages, tran=".tran .1ns 150ns uic", extra_opts="", kick=False, delvto=None):
     lines = [f"* {stages}-stage BSIM4 ring oscillator (topology of examples/mos/ro_17_4.cir)", "vdd 1 0 2.0"]
     for k in range(1, stages + 1):
         a = k + 1
         out = k + 2 if k < stages else 2
-        lines.append(f"mp{k} {out} {a} 1 1 p1 l=0.1u w=10u ad=5p pd=6u as=5p ps=6u")
-        lines.append(f"mn{k} {out} {a} 0 0 n1 l=0.1u w=5u ad=5p pd=6u as=5p ps=6u")
+        dp = f" delvto={delvto[2 * (k - 1)]:.17g}" if delvto is not None else ""
+        dn = f" delvto={delvto[2 * (k - 1) + 1]:.17g}" if delvto is not None else ""
+        lines.append(f"mp{k} {out} {a} 1 1 p1 l=0.1u w=10u ad=5p pd=6u as=5p ps=6u{dp}")
+        lines.append(f"mn{k} {out} {a} 0 0 n1 l=0.1u w=5u ad=5p pd=6u as=5p ps=6u{dn}")
     lines.append(f"c1 {stages + 1} 0 .1p")
+    if kick:
+        # deterministic start: alternate the stage outputs between the rails so the oscillation
+        # does not have to grow out of rounding noise (the stock example starts from all-zero)
+        ics = " ".join(f"v({k + 1})={2.0 if k % 2 else 0.0}" for k in range(1, stages + 1))
+        lines.append(".ic " + ics)
     lines.append(f".option xmu=0.49 klu {extra_opts}")
     lines.append(tran)
     return "\n".join(lines) + "\n" + ro_cards() + "\n.end\n"
@@ -108,8 +115,17 @@ def run(name, netlist, calls, save):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ro17", "ro101"]
+    which = sys.argv[1:] or ["ro17", "ro101", "ro17k", "ro17mc"]
     if "ro17" in which:
         run("ro17", ro_netlist(17), "0-3,100,101,5000,5001", ["18", "2", "9", "vdd#branch"])
+    if "ro17k" in which:
+        run("ro17k", ro_netlist(17, tran=".tran .1ns 20ns uic", kick=True), "1,2", ["18", "2", "9", "vdd#branch"])
+    if "ro17mc" in which:
+        # four Monte-Carlo samples with per-instance Vth mismatch (delvto ~ N(0, 15 mV), numpy seed 7)
+        rng = np.random.default_rng(7)
+        dv = rng.normal(0.0, 0.015, size=(4, 34))
+        np.save(os.path.join(HERE, "ro17mc.delvto.npy"), dv)
+        for i in range(4):
+            run(f"ro17mc{i}", ro_netlist(17, tran=".tran .1ns 20ns uic", kick=True, delvto=dv[i]), "1", ["18", "2", "9", "vdd#branch"])
     if "ro101" in which:
         run("ro101", ro_netlist(101), "1,2,3000", ["102", "2", "50", "vdd#branch"])

@@ -1,0 +1,107 @@
+"""DCtran parity: the device-resident transient driver against the reference's accepted time
+points, waveforms (v(out), two internal stage nodes, i(vdd)) and run statistics.
+
+hostsim (CPU): same libm as the reference => everything must be IDENTICAL, bit for bit, even
+for the stock ring oscillator whose start-up grows out of rounding noise.
+GPU: CUDA exp/log differ from glibc in the last place, so the noise-started oscillator cannot
+be compared point by point; the deterministic-start variants (ro17k, Monte-Carlo samples) must
+agree within 1e-9 of the waveform range with identical accepted/rejected/iteration counts."""
+import numpy as np
+import pytest
+from parity_util import GOLDEN, ngt, pkg, first_pattern
+
+
+def _run(lib, name, S=1, inst=None, max_points=8192):
+    flat = ngt.read(f"{GOLDEN}/{name}.flat.ngt")
+    trace = ngt.read(f"{GOLDEN}/{name}.trace.ngt.gz")
+    wave = ngt.read(f"{GOLDEN}/{name}.wave.ngt")
+    circ = pkg.Circuit.from_flat(lib, flat, lu_pattern=first_pattern(trace))
+    b = pkg.Batch(circ, S)
+    if inst is not None:
+        b.put("b4.inst", inst)
+    res = b.tran(max_points, wave["save_eq"])
+    t, v = res.waves()
+    return res, t, v, wave
+
+
+def _compare(res, t, v, wave, s, exact, tol=1e-9):
+    acc, rej, nit = (int(x) for x in wave["stats"][:3])
+    assert int(res.accepted[s]) == acc and int(res.rejected[s]) == rej and int(res.numiter[s]) == nit
+    n = int(res.npoints[s])
+    assert n == len(wave["time"])
+    if exact:
+        assert np.array_equal(t[s, :n], wave["time"])
+        assert np.array_equal(v[s, :n, :], wave["values"])
+    else:
+        assert np.max(np.abs(t[s, :n] - wave["time"]) / wave["time"]) <= tol
+        rng = np.max(np.abs(wave["values"]), axis=0)
+        err = np.max(np.abs(v[s, :n, :] - wave["values"]), axis=0) / rng
+        assert (err <= tol).all(), err
+
+
+@pytest.mark.parametrize("name", ["ro17", "ro17k"])
+def test_tran_hostsim_bit_identical(hostsim_lib, name):
+    res, t, v, wave = _run(hostsim_lib, name)
+    _compare(res, t, v, wave, 0, exact=True)
+
+
+def _mc_inst(lib):
+    base = ngt.read(f"{GOLDEN}/ro17k.flat.ngt")
+    dv_netlist = np.load(f"{GOLDEN}/ro17mc.delvto.npy")       # columns: mp1 mn1 mp2 mn2 ... (netlist order)
+    col = {}
+    for k in range(1, 18):
+        col[f"mp{k}"] = 2 * (k - 1); col[f"mn{k}"] = 2 * (k - 1) + 1
+    order = [col[n.lower()] for n in pkg.mc.instance_names(base)]   # flat tables are in reference list order
+    dv = dv_netlist[:, order]
+    return base, dv, pkg.mc.bsim4_inst_with_delvto(lib, base, dv)
+
+
+def test_mc_mismatch_parameters_match_bsim4temp(hostsim_lib):
+    """the host-side delvto applicator reproduces what BSIM4temp wrote into the instances"""
+    base, dv, inst = _mc_inst(hostsim_lib)
+    for i in range(dv.shape[0]):
+        ref = ngt.read(f"{GOLDEN}/ro17mc{i}.flat.ngt")["b4/inst"]
+        err = np.abs(inst[:, :, i] - ref) / np.maximum(np.abs(ref), 1e-300)
+        assert err.max() <= 4e-16, (i, err.max())
+
+
+def test_tran_hostsim_mc_batch(hostsim_lib):
+    """four mismatch samples advanced in ONE batch, each on its own time axis, each equal to
+    its own sequential reference run"""
+    base, dv, inst = _mc_inst(hostsim_lib)
+    # use the reference's own instance tables so the comparison is exact
+    for i in range(dv.shape[0]):
+        inst[:, :, i] = ngt.read(f"{GOLDEN}/ro17mc{i}.flat.ngt")["b4/inst"]
+    res, t, v, _ = _run(hostsim_lib, "ro17k", S=dv.shape[0], inst=inst)
+    for i in range(dv.shape[0]):
+        wave = ngt.read(f"{GOLDEN}/ro17mc{i}.wave.ngt")
+        _compare(res, t, v, wave, i, exact=True)
+
+
+@pytest.mark.gpu
+def test_tran_gpu_ro17k(cuda_lib):
+    res, t, v, wave = _run(cuda_lib, "ro17k")
+    _compare(res, t, v, wave, 0, exact=False)
+
+
+@pytest.mark.gpu
+def test_tran_gpu_mc_batch(cuda_lib):
+    base, dv, inst = _mc_inst(cuda_lib)
+    reps = 8                                   # 32 samples: every lane of a warp on its own time axis
+    inst = np.tile(inst, (1, 1, reps))
+    res, t, v, _ = _run(cuda_lib, "ro17k", S=dv.shape[0] * reps, inst=inst)
+    for s in range(dv.shape[0] * reps):
+        wave = ngt.read(f"{GOLDEN}/ro17mc{s % dv.shape[0]}.wave.ngt")
+        _compare(res, t, v, wave, s, exact=False)
+
+
+@pytest.mark.gpu
+def test_tran_gpu_ro17_full_length_runs(cuda_lib):
+    """the stock (noise-started) oscillator: same engine, full 150 ns; start-up timing depends on
+    last-place rounding, so only sanity is asserted: it finishes, oscillates rail to rail, and the
+    work done is within a few percent of the reference's"""
+    res, t, v, wave = _run(cuda_lib, "ro17")
+    n = int(res.npoints[0])
+    assert abs(t[0, n - 1] - 150e-9) < 1e-15
+    assert v[0, :n, 0].max() > 1.8 and v[0, :n, 0].min() < 0.2
+    assert abs(int(res.numiter[0]) - int(wave["stats"][2])) < 0.1 * int(wave["stats"][2])
