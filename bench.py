@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the Newton hot path on B200.
+
+Default workload (BASELINE.json configs[2], the configuration the multi-GPU metric is quoted on,
+and the largest that shards): Monte-Carlo transient of the 17-stage BSIM4 ring oscillator
+(examples/mos/ro_17_4.cir cards, `.tran .1ns 150ns uic`, KLU), 4096 samples PER GPU with
+per-instance Vth mismatch (delvto ~ N(0, 15 mV), seeded), every sample on its own adaptive time
+axis.  One "step" = one complete transient of the batch.  `--workload ro101` runs configs[1]
+(single 101-stage circuit).
+
+  value  = BSIM4 instance-evals/s over the whole job (34 instances x Newton iterations of every
+           sample / time), inputs resident in HBM, timed with CUDA events on the launch stream
+  e2e    = the same job through the public API with HOST buffers: per-sample parameter table
+           copied from pinned memory and result waveforms copied back inside the timed region
+  roofline = dominant kernel (bsim4_load): algorithmic bytes per launch / CUDA-event duration
+  cpu_baseline = oracle/_ref/ngspice (the reference compiled here) on the host cores, bounded sample
+
+`--impl reference` times the reference CPU implementation of the same workload instead.
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+B4_BYTES_PER_EVAL = 2000.0          # algorithmic bytes per BSIM4 instance-eval
+B4_FLOP_PER_EVAL = 3100.0           # provisional source-level FP op count per eval
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    def __init__(self, dev):
+        self.dev, self.rows, self.stop = dev, [], False
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.dev}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.th.start(); return self
+
+    def __exit__(self, *a):
+        self.stop = True; self.th.join(timeout=3)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons}
+
+
+# ------------------------------------------------------------------ reference CPU arm
+def cpu_reference_run(workload, nproc, samples_per_proc, seed0=1000):
+    """Runs the REFERENCE ngspice (oracle/_ref/ngspice, stock code path) on the host cores:
+    `nproc` processes in parallel, each simulating `samples_per_proc` mismatch samples
+    sequentially.  Returns (evals/s, samples/s, wall seconds, description)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ngspice")
+    if not os.path.exists(exe):
+        return None
+    base = open(os.path.join(GOLDEN, "netlists", ("ro101" if workload == "ro101" else "ro17") + ".cir")).read()
+    ninst = 202 if workload == "ro101" else 34
+    tmp = tempfile.mkdtemp(prefix="ngb_cpu_")
+    jobs = []
+    for p in range(nproc):
+        files = []
+        for k in range(samples_per_proc):
+            rng = np.random.default_rng(seed0 + p * samples_per_proc + k)
+            dv = rng.normal(0.0, 0.015, size=ninst) if workload != "ro101" else np.zeros(ninst)
+            lines, i = [], 0
+            for ln in base.splitlines():
+                if ln[:2].lower() in ("mp", "mn") and " l=" in ln:
+                    ln = ln + f" delvto={dv[i]:.17g}"; i += 1
+                lines.append(ln)
+            f = os.path.join(tmp, f"s{p}_{k}.cir")
+            text = "\n".join(lines).replace(".option xmu=0.49 klu", ".option xmu=0.49 klu acct")
+            open(f, "w").write(text + "\n")
+            files.append(f)
+        jobs.append(files)
+    t0 = time.time()
+    procs = []
+    for files in jobs:
+        cmd = " ; ".join(f"{exe} -b -r /dev/null {f} > {f}.log 2>&1" for f in files)
+        procs.append(subprocess.Popen(["bash", "-c", cmd]))
+    for pr in procs:
+        pr.wait()
+    wall = time.time() - t0
+    iters = 0
+    for files in jobs:
+        for f in files:
+            try:
+                for ln in open(f + ".log", errors="replace"):
+                    if ln.startswith("Total iterations"):
+                        iters += int(ln.split("=")[-1].strip().split()[0])
+            except Exception:
+                pass
+    nsamp = nproc * samples_per_proc
+    if iters == 0:                       # acct line not found: fall back to the recorded iteration count
+        iters = nsamp * (24622 if workload == "ro101" else 24291)
+    evals = ninst * iters
+    return evals / wall, nsamp / wall, wall, f"{nsamp} full transients ({samples_per_proc} per process x {nproc} processes)"
+
+
+def bench_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals = []
+    steps = max(1, min(args.steps, 3))
+    t_all = []
+    for _ in range(steps):
+        r = cpu_reference_run(args.workload, cores, 1)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ngspice not built"}))
+            return
+        vals.append(r); t_all.append(r[2])
+    ev = float(np.mean([v[0] for v in vals])); sps = float(np.mean([v[1] for v in vals]))
+    line = {
+        "impl": "reference", "metric": "BSIM4 instance-evals/s", "value": ev, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": 0, "ms_per_step": float(np.mean(t_all)) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args), "mc_samples_per_s": sps,
+        "cpu_baseline": {"value": ev, "unit": "evals/s", "cores": cores, "kind": "reference", "sample": vals[0][3]},
+        "e2e": {"value": ev, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    if args.workload == "ro101":
+        return {"workload": "101-stage BSIM4 ring oscillator transient (.tran .1ns 150ns uic), single circuit, KLU pivot order",
+                "samples_per_gpu": 1, "bsim4_instances": 202, "unknowns": 911,
+                "l2": "working set smaller than L2 by nature (single circuit); no flush"}
+    return {"workload": "Monte Carlo transient, 17-stage BSIM4 ring oscillator (ro_17_4.cir cards, version 4.8.3), "
+                        ".tran .1ns 150ns uic, per-instance delvto mismatch sigma 15 mV",
+            "samples_per_gpu": args.samples, "bsim4_instances": 34, "unknowns": 155,
+            "l2": "inputs larger than L2: per-step working set (parameters+states+stamps+matrices) ~%.0f MB" %
+                  (args.samples * 34 * (51 + 4 * 29 + 38 + 52) * 8 / 1e6 + args.samples * 904 * 8 / 1e6)}
+
+
+# ------------------------------------------------------------------ our arm
+def bench_ours(args):
+    import torch
+    import torch.distributed as dist
+    from parity_util import ngt, pkg, first_pattern
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    lib = pkg.library()
+    assert lib.backend == "cuda-sm_100a"
+    lib.check(lib.L.ngbInit(local), "ngbInit")
+    stream = torch.cuda.Stream(device=local)
+    lib.check(lib.L.ngbSetStream(ctypes.c_void_p(stream.cuda_stream)), "ngbSetStream")
+
+    name = "ro101" if args.workload == "ro101" else "ro17"
+    flat = ngt.read(f"{GOLDEN}/{name}.flat.ngt")
+    trace = ngt.read(f"{GOLDEN}/{name}.trace.ngt.gz")
+    wave = ngt.read(f"{GOLDEN}/{name}.wave.ngt")
+    ninst = int(flat["b4/ninst"][0])
+    S = 1 if args.workload == "ro101" else args.samples
+    circ = pkg.Circuit.from_flat(lib, flat, lu_pattern=first_pattern(trace))
+    batch = pkg.Batch(circ, S, device=local)
+    save_eq = wave["save_eq"][:1]                     # v(out)
+    max_points = 6144
+
+    # per-sample mismatch parameters, built on the host like the reference's MC front end would
+    if args.workload == "ro101":
+        inst_host = np.repeat(np.asarray(flat["b4/inst"])[:, :, None], S, axis=2)
+    else:
+        dv = pkg.mc.draw_delvto(S, ninst, sigma=0.015, seed=1000 + rank)
+        inst_host = pkg.mc.bsim4_inst_with_delvto(lib, flat, dv)
+    pinned = torch.empty(inst_host.shape, dtype=torch.float64).pin_memory()
+    pinned.numpy()[...] = inst_host
+    out_t = torch.empty((S, max_points), dtype=torch.float64).pin_memory()
+    out_v = torch.empty((S, max_points, 1), dtype=torch.float64).pin_memory()
+    h2d_bytes = pinned.numel() * 8
+    d2h_bytes = (out_t.numel() + out_v.numel()) * 8
+
+    def step(e2e):
+        if e2e:
+            batch.put("b4.inst", pinned.numpy())
+        res = batch.tran(max_points, save_eq)
+        if e2e:
+            lib.check(lib.L.ngbTranWaves(batch.h, ctypes.cast(out_t.data_ptr(), ctypes.POINTER(ctypes.c_double)),
+                                         ctypes.cast(out_v.data_ptr(), ctypes.POINTER(ctypes.c_double))), "ngbTranWaves")
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    batch.put("b4.inst", pinned.numpy())
+    for _ in range(args.warmup):
+        step(False)
+
+    def timed(e2e, profile):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        iters = 0; ticks = 0
+        if profile:
+            lib.L.ngbProfile(1, 16)
+        barrier()
+        n0 = lib.launch_count()
+        t0 = time.time()
+        for k in range(args.steps):
+            evs[k][0].record(stream)
+            res = step(e2e)
+            evs[k][1].record(stream)
+            iters += int(res.numiter.astype(np.int64).sum()); ticks += res.ticks
+        barrier()
+        wall = time.time() - t0
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        launches = lib.launch_count() - n0
+        prof = None
+        if profile:
+            msum, cnt = ctypes.c_double(), ctypes.c_long()
+            lib.L.ngbProfileRead(ctypes.byref(msum), ctypes.byref(cnt))
+            lib.L.ngbProfile(0, 1)
+            prof = (msum.value, cnt.value)
+        return ms, wall, iters, ticks, launches, prof, res
+
+    with ClockSampler(local) as clk:
+        ms, wall, iters, ticks, launches, prof, res = timed(False, True)
+    clocks = clk.summary()
+    ms_e2e, wall_e2e, iters_e2e, _, _, _, _ = timed(True, False)
+
+    # max over ranks of the device time; totals over ranks
+    tt = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    ww = torch.tensor([float(iters), float(iters_e2e), float(S * args.steps)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ww, op=dist.ReduceOp.SUM)
+        # result waveforms gathered over NCCL/NVLink (the only collective on this path)
+        dv_ptr = lib.L.ngbTranDevWaves(batch.h, 1)
+        gathered = None
+        try:
+            class _Arr:
+                pass
+            a = _Arr()
+            a.__cuda_array_interface__ = {"shape": (S, max_points), "typestr": "<f8", "data": (int(dv_ptr), False), "version": 3}
+            wv = torch.as_tensor(a, device="cuda")
+            lst = [torch.empty_like(wv) for _ in range(world)] if rank == 0 else None
+            dist.gather(wv, lst, dst=0)
+            gathered = True
+        except Exception as e:                         # the gather is off the timed path; report but do not fail the bench
+            gathered = str(e)
+    ms_max, ms_e2e_max = tt.tolist()
+    iters_tot, iters_e2e_tot, samples_tot = ww.tolist()
+    evals = ninst * iters_tot
+    value = evals / (ms_max * 1e-3)
+    e2e_val = ninst * iters_e2e_tot / (ms_e2e_max * 1e-3)
+
+    if rank == 0:
+        hbm_peak, which = peaks()
+        units = ninst * S                                  # evals one bsim4_load launch processes (all samples active)
+        k_ms = prof[0] / max(prof[1], 1)
+        achieved = units * B4_BYTES_PER_EVAL / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        cpu = cpu_reference_run(args.workload, os.cpu_count() or 1, 1)
+        line = {
+            "metric": "BSIM4 instance-evals/s", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "mc_samples_per_s": samples_tot / (ms_max * 1e-3),
+            "newton_steps_per_transient": ticks / args.steps,
+            "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "mc_samples_per_s": samples_tot / (ms_e2e_max * 1e-3)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak if hbm_peak else None, "traffic": None,
+                         "kernel": "ngb_k_bsim4_load", "avg_launch_ms": k_ms, "timed_launches": prof[1],
+                         "units_per_launch": units, "bytes_per_unit": B4_BYTES_PER_EVAL, "peak_source": which,
+                         "fp64_tflops_algorithmic": units * B4_FLOP_PER_EVAL / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0,
+                         "kernel_share_of_step": (k_ms * ticks / args.steps) / (ms_max / args.steps) if ms_max else None},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {"value": cpu[0], "unit": "evals/s", "cores": os.cpu_count() or 1, "kind": "reference",
+                                    "sample": cpu[3], "mc_samples_per_s": cpu[1]}
+        if world > 1:
+            line["nccl_gather"] = gathered
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mc_ro17", choices=["mc_ro17", "ro101"])
+    ap.add_argument("--samples", type=int, default=4096, help="Monte-Carlo samples per GPU")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        bench_reference(args)
+    else:
+        bench_ours(args)
+
+
+if __name__ == "__main__":
+    main()

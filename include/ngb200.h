@@ -36,6 +36,13 @@ typedef struct ngb_batch ngb_batch;
 const char *ngbBackend(void);                 /* "cuda-sm_100a" for the product library */
 const char *ngbLastError(void);
 long ngbLaunchCount(void);                    /* kernels launched since load */
+int ngbInit(int device);                      /* select the CUDA device, create the launch stream */
+int ngbSetStream(void *cuda_stream);          /* launch on a caller-owned cudaStream_t instead */
+int ngbSync(void);
+/* CUDA-event timing of the dominant kernel: every `every`-th BSIM4 load launch is bracketed by
+ * events; ngbProfileRead returns the summed milliseconds and the number of timed launches */
+void ngbProfile(int enable, int every);
+int ngbProfileRead(double *ms_sum, long *count);
 
 /* field-list sizes, so callers can check they were built against the same lists
  * (bsim4_fields.h): [0]=model [1]=bin [2]=instance [3]=node roles [4]=matrix stamps
@@ -118,6 +125,10 @@ int ngbTranRun(ngb_batch *b, int max_points, const int *save_eq, int nsave);
 int ngbTranStats(ngb_batch *b, int *accepted, int *rejected, int *numiter, int *npoints /* each [S] */);
 long ngbTranWaveBytes(ngb_batch *b);
 int ngbTranWaves(ngb_batch *b, double *times /* [S][max_points] */, double *values /* [S][max_points][nsave] */);
+long ngbTranTicks(ngb_batch *b);              /* Newton steps the batch needed */
+void *ngbTranDevWaves(ngb_batch *b, int which /* 0 times, 1 values */);   /* device pointers for a collective gather */
+/* per-thread BSIM4 parameter rows for model-parameter mismatch: prow_t [ninst*S] into new tables */
+int ngbBatchSetBsim4Rows(ngb_batch *b, const int *prow_t, int nrows, const double *mtab, const double *ptab);
 
 #ifdef __cplusplus
 }

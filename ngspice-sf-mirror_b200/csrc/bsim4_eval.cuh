@@ -109,7 +109,7 @@ NGB_HD void b4_dexp(double A, double *B, double *C)
 {
     if (A > B4_EXP_THRESHOLD) { *B = B4_MAX_EXP * (1.0 + A - B4_EXP_THRESHOLD); *C = B4_MAX_EXP; }
     else if (A < -B4_EXP_THRESHOLD) { *B = B4_MIN_EXP; *C = 0; }
-    else { *B = exp(A); *C = *B; }
+    else { *B = ngb_exp(A); *C = *B; }
 }
 
 /* BSIM4polyDepletion, b4ld.c:5402-5433 */
@@ -147,8 +147,8 @@ NGB_HD void b4_junction_dc(int dioMod, double Isat, double Nvtm, double vj, doub
     }
     switch (dioMod) {
     case 0:
-        ev = exp(vj / Nvtm);
-        T1 = xjbv * exp(-(bv + vj) / Nvtm);
+        ev = ngb_exp(vj / Nvtm);
+        T1 = xjbv * ngb_exp(-(bv + vj) / Nvtm);
         *g = Isat * (ev + T1) / Nvtm + gmin;
         *cur = Isat * (ev + XExpBV - T1 - 1.0) + gmin * vj;
         break;
@@ -158,7 +158,7 @@ NGB_HD void b4_junction_dc(int dioMod, double Isat, double Nvtm, double vj, doub
             *g = gmin;
             *cur = Isat * (B4_MIN_EXP - 1.0) + gmin * vj;
         } else if (vj <= vjmFwd) {
-            ev = exp(T2);
+            ev = ngb_exp(T2);
             *g = Isat * ev / Nvtm + gmin;
             *cur = Isat * (ev - 1.0) + gmin * vj;
         } else {
@@ -171,7 +171,7 @@ NGB_HD void b4_junction_dc(int dioMod, double Isat, double Nvtm, double vj, doub
         if (vj < vjmRev) {
             T0 = vj / Nvtm;
             if (T0 < -B4_EXP_THRESHOLD) { ev = B4_MIN_EXP; dev = 0.0; }
-            else { ev = exp(T0); dev = ev / Nvtm; }
+            else { ev = ngb_exp(T0); dev = ev / Nvtm; }
             T1 = ev - 1.0;
             T2 = IVjmRev + slpRev * (vj - vjmRev);
             *g = dev * T2 + T1 * slpRev + gmin;
@@ -179,10 +179,10 @@ NGB_HD void b4_junction_dc(int dioMod, double Isat, double Nvtm, double vj, doub
         } else if (vj <= vjmFwd) {
             T0 = vj / Nvtm;
             if (T0 < -B4_EXP_THRESHOLD) { ev = B4_MIN_EXP; dev = 0.0; }
-            else { ev = exp(T0); dev = ev / Nvtm; }
+            else { ev = ngb_exp(T0); dev = ev / Nvtm; }
             T1 = (bv + vj) / Nvtm;
             if (T1 > B4_EXP_THRESHOLD) { T2 = B4_MIN_EXP; T3 = 0.0; }
-            else { T2 = exp(-T1); T3 = -T2 / Nvtm; }
+            else { T2 = ngb_exp(-T1); T3 = -T2 / Nvtm; }
             *g = Isat * (dev - xjbv * T3) + gmin;
             *cur = Isat * (ev + XExpBV - 1.0 - xjbv * T2) + gmin * vj;
         } else {
@@ -516,7 +516,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     double Theta0, dTheta0_dVb;
     T0 = B4P(dvt1) * Leff / lt1;
     if (T0 < B4_EXP_THRESHOLD) {
-        T1 = exp(T0);
+        T1 = ngb_exp(T0);
         T2 = T1 - 1.0;
         T3 = T2 * T2;
         T4 = T3 + 2.0 * T1 * B4_MIN_EXP;
@@ -533,7 +533,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
 
     T0 = B4P(dvt1w) * weff * Leff / ltw;
     if (T0 < B4_EXP_THRESHOLD) {
-        T1 = exp(T0);
+        T1 = ngb_exp(T0);
         T2 = T1 - 1.0;
         T3 = T2 * T2;
         T4 = T3 + 2.0 * T1 * B4_MIN_EXP;
@@ -603,14 +603,14 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         double dDITS_Sft_dVd, dDITS_Sft_dVb;
         T0 = -B4P(dvtp1) * Vds;
         if (T0 < -B4_EXP_THRESHOLD) { T2 = B4_MIN_EXP; dT2_dVd = 0.0; }
-        else { T2 = exp(T0); dT2_dVd = -B4P(dvtp1) * T2; }
+        else { T2 = ngb_exp(T0); dT2_dVd = -B4P(dvtp1) * T2; }
         T3 = Leff + B4P(dvtp0) * (1.0 + T2);
         dT3_dVd = B4P(dvtp0) * dT2_dVd;
         if (tempMod < 2) {
-            T4 = Vtm * log(Leff / T3);
+            T4 = Vtm * ngb_log(Leff / T3);
             dT4_dVd = -Vtm * dT3_dVd / T3;
         } else {
-            T4 = vtm0 * log(Leff / T3);
+            T4 = vtm0 * ngb_log(Leff / T3);
             dT4_dVd = -vtm0 * dT3_dVd / T3;
         }
         dDITS_Sft_dVd = dn_dVd * T4 + n * dT4_dVd;
@@ -660,14 +660,14 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         dT10_dVd = -dVth_dVd * mstar;
         dT10_dVb = -dVth_dVb * mstar;
     } else if (T2 < -B4_EXP_THRESHOLD) {
-        T10 = Vtm * log(1.0 + B4_MIN_EXP);
+        T10 = Vtm * ngb_log(1.0 + B4_MIN_EXP);
         dT10_dVg = 0.0;
         dT10_dVd = T10 * dn_dVd;
         dT10_dVb = T10 * dn_dVb;
         T10 *= n;
     } else {
-        ExpVgst = exp(T2);
-        T3 = Vtm * log(1.0 + ExpVgst);
+        ExpVgst = ngb_exp(T2);
+        T3 = Vtm * ngb_log(1.0 + ExpVgst);
         T10 = n * T3;
         dT10_dVg = mstar * ExpVgst / (1.0 + ExpVgst);
         dT10_dVb = T3 * dn_dVb - dT10_dVg * (dVth_dVb + Vgst * dn_dVb / n);
@@ -690,7 +690,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         dT9_dVd = dn_dVd * T3;
         dT9_dVb = dn_dVb * T3;
     } else {
-        ExpVgst = exp(T2);
+        ExpVgst = ngb_exp(T2);
         T3 = coxe / cdep0;
         T4 = T3 * ExpVgst;
         T5 = T1 * T4 / T0;
@@ -859,7 +859,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         dDenomi_dVg += T7;
     } else if (mobMod == 2) {
         T0 = (Vgsteff + B4I(vtfbphi1)) / toxe;
-        T1 = exp(B4P(eu) * log(T0));
+        T1 = ngb_exp(B4P(eu) * ngb_log(T0));
         dT1_dVg = T1 * B4P(eu) / T0 / toxe;
         T2 = ua + uc * Vbseff;
         T12 = sqrt(Vth * Vth + 0.0001);
@@ -910,7 +910,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     } else if (mobMod == 6) {
         const double vtfbphi1 = B4I(vtfbphi1);
         T0 = (Vgsteff + vtfbphi1) / toxe;
-        T1 = exp(B4P(eu) * log(T0));
+        T1 = ngb_exp(B4P(eu) * ngb_log(T0));
         dT1_dVg = T1 * B4P(eu) / T0 / toxe;
         T2 = ua + uc * Vbseff;
         T12 = sqrt(vtfbphi1 * vtfbphi1 + 0.0001);
@@ -928,10 +928,10 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         const double VgsteffVth = B4P(VgsteffVth);
         double dT11_dVg;
         T0 = (Vgsteff + B4I(vtfbphi1)) * 1.0e-8 / toxe / 6.0;
-        T1 = exp(B4P(eu) * log(T0));
+        T1 = ngb_exp(B4P(eu) * ngb_log(T0));
         dT1_dVg = T1 * B4P(eu) * 1.0e-8 / T0 / toxe / 6.0;
         T2 = ua + uc * Vbseff;
-        T10 = exp(B4P(ucs) * log(0.5 + 0.5 * Vgsteff / VgsteffVth));
+        T10 = ngb_exp(B4P(ucs) * ngb_log(0.5 + 0.5 * Vgsteff / VgsteffVth));
         T11 = ud / T10;
         dT11_dVg = -0.5 * B4P(ucs) * T11 / (0.5 + 0.5 * Vgsteff / VgsteffVth) / VgsteffVth;
         dDenomi_dVg = T2 * dT1_dVg + dT11_dVg;
@@ -1155,7 +1155,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     dT0_dVg = 1.0 / tmp2;
     T0 = (Vgsteff + tmp1) * dT0_dVg;
 
-    tmp3 = exp(B4M(bdos) * 0.7 * log(T0));
+    tmp3 = ngb_exp(B4M(bdos) * 0.7 * ngb_log(T0));
     T1 = 1.0 + tmp3;
     T2 = B4M(bdos) * 0.7 * tmp3 / T0;
     Tcen = B4M(ados) * 1.9e-9 / T1;
@@ -1316,7 +1316,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     double VADITS, dVADITS_dVg, dVADITS_dVd;
     T0 = B4P(pditsd) * Vds;
     if (T0 > B4_EXP_THRESHOLD) { T1 = B4_MAX_EXP; dT1_dVd = 0; }
-    else { T1 = exp(T0); dT1_dVd = T1 * B4P(pditsd); }
+    else { T1 = ngb_exp(T0); dT1_dVd = T1 * B4P(pditsd); }
     if (B4P(pdits) > B4_MIN_EXP) {
         T2 = 1.0 + B4M(pditsl) * Leff;
         VADITS = (1.0 + T2 * T1) / B4P(pdits);
@@ -1333,7 +1333,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     if ((B4P(pscbe2) > 0.0) && (B4P(pscbe1) >= 0.0)) {
         if (diffVds > B4P(pscbe1) * B4P(litl) / B4_EXP_THRESHOLD) {
             T0 = B4P(pscbe1) * B4P(litl) / diffVds;
-            VASCBE = Leff * exp(T0) / B4P(pscbe2);
+            VASCBE = Leff * ngb_exp(T0) / B4P(pscbe2);
             T1 = T0 * VASCBE / diffVds;
             dVASCBE_dVg = T1 * dVdseff_dVg;
             dVASCBE_dVd = -T1 * (1.0 - dVdseff_dVd);
@@ -1365,7 +1365,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     Idsa *= T0;
 
     /* ---- add CLM to Ids ---- */
-    T0 = log(Va / Vasat);
+    T0 = ngb_log(Va / Vasat);
     dT0_dVg = dVa_dVg / Va - dVasat_dVg / Vasat;
     dT0_dVb = dVa_dVb / Va - dVasat_dVb / Vasat;
     dT0_dVd = dVa_dVd / Va - dVasat_dVd / Vasat;
@@ -1389,7 +1389,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         T2 = tmp / Leff;
         if (diffVds > B4P(beta0) / B4_EXP_THRESHOLD) {
             T0 = -B4P(beta0) / diffVds;
-            T1 = T2 * diffVds * exp(T0);
+            T1 = T2 * diffVds * ngb_exp(T0);
             T3 = T1 / diffVds * (T0 - 1.0);
             dT1_dVg = T3 * dVdseff_dVg;
             dT1_dVd = T3 * (dVdseff_dVd - 1.0);
@@ -1447,9 +1447,9 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         T0 = 2 * 3;                                       /* 2 * MM */
         T1 = vs / (B4P(vtl) * B4P(tfactor));
         if (T1 > 0.0) {
-            T2 = 1.0 + exp(T0 * log(T1));
+            T2 = 1.0 + ngb_exp(T0 * ngb_log(T1));
             T3 = (T2 - 1.0) * T0 / vs;
-            Fsevl = 1.0 / exp(log(T2) / T0);
+            Fsevl = 1.0 / ngb_exp(ngb_log(T2) / T0);
             dT2_dVg = T3 * dvs_dVg;
             dT2_dVd = T3 * dvs_dVd;
             dT2_dVb = T3 * dvs_dVb;
@@ -1501,7 +1501,7 @@ NGB_HD void b4_gidl0(double T1, double dvg_eff, double T0den, double agidl, doub
         double dT1_dVg = -dvg_eff * dT1_dVd;
         double T2 = bgidl / T1, T3, T4, T5, T6, T7, T8, Ig, Ggd, Ggg;
         if (T2 < 100.0) {
-            Ig = agidl * weffCJ * T1 * exp(-T2);
+            Ig = agidl * weffCJ * T1 * ngb_exp(-T2);
             T3 = Ig * (1.0 + T2) / T1;
             Ggd = T3 * dT1_dVd;
             Ggg = T3 * dT1_dVg;
@@ -1535,7 +1535,7 @@ NGB_HD void b4_gidl1(double T1, double dvg_eff, double T0den, double agidl, doub
         double dT1_dVg = -rgidl * dT1_dVd * dvg_eff;
         double T2 = bgidl / T1, T3, T4, T5, T6, Ig, Ggd, Ggg, Ggb;
         if (T2 < B4_EXPL_THRESHOLD) {
-            Ig = weffCJ * agidl * T1 * exp(-T2);
+            Ig = weffCJ * agidl * T1 * ngb_exp(-T2);
             T3 = Ig / T1 * (T2 + 1);
             Ggd = T3 * dT1_dVd;
             Ggg = T3 * dT1_dVg;
@@ -1550,7 +1550,7 @@ NGB_HD void b4_gidl1(double T1, double dvg_eff, double T0den, double agidl, doub
         if (T4 == 0) T5 = B4_EXPL_THRESHOLD;
         else T5 = kgidl / T4;
         if (T5 < B4_EXPL_THRESHOLD) {
-            T6 = exp(T5);
+            T6 = ngb_exp(T5);
             Ggb = -Ig * T6 * T5 / T4;
         } else {
             T6 = B4_MAX_EXPL;
@@ -1578,7 +1578,7 @@ NGB_HD void b4_ig_edge(double vg, double vfbsd_tot, double Aechvb, double Bechvb
     double T6, dT6_dVg;
     if (T5 > B4_EXP_THRESHOLD) { T6 = B4_MAX_EXP; dT6_dVg = 0.0; }
     else if (T5 < -B4_EXP_THRESHOLD) { T6 = B4_MIN_EXP; dT6_dVg = 0.0; }
-    else { T6 = exp(T5); dT6_dVg = T6 * BechvbEdge * (T3 - 2.0 * T4 * vg_eff) * dvg_eff; }
+    else { T6 = ngb_exp(T5); dT6_dVg = T6 * BechvbEdge * (T3 - 2.0 * T4 * vg_eff) * dvg_eff; }
     *Ig = Aechvb * T2 * T6;
     *dIg_dVg = Aechvb * (T2 * dT6_dVg + T6 * dT2_dVg);
 }
@@ -1815,11 +1815,11 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
             }
         }
         if (VxNVt < -B4_EXP_THRESHOLD) {
-            Vaux = T0 * log(1.0 + B4_MIN_EXP);
+            Vaux = T0 * ngb_log(1.0 + B4_MIN_EXP);
             dVaux_dVg = dVaux_dVd = dVaux_dVb = 0.0;
         } else if ((VxNVt >= -B4_EXP_THRESHOLD) && (VxNVt <= B4_EXP_THRESHOLD)) {
-            ExpVxNVt = exp(VxNVt);
-            Vaux = T0 * log(1.0 + ExpVxNVt);
+            ExpVxNVt = ngb_exp(VxNVt);
+            Vaux = T0 * ngb_log(1.0 + ExpVxNVt);
             dVaux_dVg = ExpVxNVt / (1.0 + ExpVxNVt);
             if (igcMod == 1) {
                 dVaux_dVd = 0.0;
@@ -1849,7 +1849,7 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
             T6 = B4_MIN_EXP;
             dT6_dVg = dT6_dVd = dT6_dVb = 0.0;
         } else {
-            T6 = exp(T5);
+            T6 = ngb_exp(T5);
             dT6_dVg = T6 * T12 * (T3 - 2.0 * T4 * Voxdepinv);
             dT6_dVd = dT6_dVg * dVoxdepinv_dVd;
             dT6_dVb = dT6_dVg * dVoxdepinv_dVb;
@@ -1893,7 +1893,7 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
             T9 = B4_MIN_EXP;
             dT9_dVg = dT9_dVd = dT9_dVb = 0.0;
         } else {
-            T9 = exp(T7);
+            T9 = ngb_exp(T7);
             dT9_dVg = T9 * dT7_dVg;
             dT9_dVd = T9 * dT7_dVd;
             dT9_dVb = T9 * dT7_dVb;
@@ -1959,11 +1959,11 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
             dVaux_dVg = -dVgs_eff_dVg;
             dVaux_dVb = 1.0;
         } else if (VxNVt < -B4_EXP_THRESHOLD) {
-            Vaux = T0 * log(1.0 + B4_MIN_EXP);
+            Vaux = T0 * ngb_log(1.0 + B4_MIN_EXP);
             dVaux_dVg = dVaux_dVb = 0.0;
         } else {
-            ExpVxNVt = exp(VxNVt);
-            Vaux = T0 * log(1.0 + ExpVxNVt);
+            ExpVxNVt = ngb_exp(VxNVt);
+            Vaux = T0 * ngb_log(1.0 + ExpVxNVt);
             dVaux_dVb = ExpVxNVt / (1.0 + ExpVxNVt);
             dVaux_dVg = -dVaux_dVb * dVgs_eff_dVg;
         }
@@ -1985,7 +1985,7 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
             T6 = B4_MIN_EXP;
             dT6_dVg = dT6_dVb = 0.0;
         } else {
-            T6 = exp(T5);
+            T6 = ngb_exp(T5);
             dT6_dVg = T6 * T12 * (T3 - 2.0 * T4 * Voxacc);
             dT6_dVb = dT6_dVg * dVoxacc_dVb;
             dT6_dVg *= dVoxacc_dVg;
@@ -2004,11 +2004,11 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
             dVaux_dVd = dVoxdepinv_dVd;
             dVaux_dVb = dVoxdepinv_dVb;
         } else if (VxNVt < -B4_EXP_THRESHOLD) {
-            Vaux = T0 * log(1.0 + B4_MIN_EXP);
+            Vaux = T0 * ngb_log(1.0 + B4_MIN_EXP);
             dVaux_dVg = dVaux_dVd = dVaux_dVb = 0.0;
         } else {
-            ExpVxNVt = exp(VxNVt);
-            Vaux = T0 * log(1.0 + ExpVxNVt);
+            ExpVxNVt = ngb_exp(VxNVt);
+            Vaux = T0 * ngb_log(1.0 + ExpVxNVt);
             dVaux_dVg = ExpVxNVt / (1.0 + ExpVxNVt);
             dVaux_dVd = dVaux_dVg * dVoxdepinv_dVd;
             dVaux_dVb = dVaux_dVg * dVoxdepinv_dVb;
@@ -2033,7 +2033,7 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
             T6 = B4_MIN_EXP;
             dT6_dVg = dT6_dVd = dT6_dVb = 0.0;
         } else {
-            T6 = exp(T5);
+            T6 = ngb_exp(T5);
             dT6_dVg = T6 * T12 * (T3 - 2.0 * T4 * Voxdepinv);
             dT6_dVd = dT6_dVg * dVoxdepinv_dVd;
             dT6_dVb = dT6_dVg * dVoxdepinv_dVb;
@@ -2096,14 +2096,14 @@ NGB_HD void b4_vgsteff_cv(const double *Mrow, const double *Prow, const B4W *w,
             dVgsteff_dVd = -dVth_dVd;
             dVgsteff_dVb = -dVth_dVb;
         } else if (VgstNVt < -B4_EXP_THRESHOLD) {
-            Vgsteff = T0 * log(1.0 + B4_MIN_EXP);
+            Vgsteff = T0 * ngb_log(1.0 + B4_MIN_EXP);
             dVgsteff_dVg = 0.0;
             dVgsteff_dVd = Vgsteff / noff;
             dVgsteff_dVb = dVgsteff_dVd * dnoff_dVb;
             dVgsteff_dVd *= dnoff_dVd;
         } else {
-            ExpVgst = exp(VgstNVt);
-            Vgsteff = T0 * log(1.0 + ExpVgst);
+            ExpVgst = ngb_exp(VgstNVt);
+            Vgsteff = T0 * ngb_log(1.0 + ExpVgst);
             dVgsteff_dVg = ExpVgst / (1.0 + ExpVgst);
             dVgsteff_dVd = -dVgsteff_dVg * (dVth_dVd + (Vgst - voffcv) / noff * dnoff_dVd)
                          + Vgsteff / noff * dnoff_dVd;
@@ -2122,14 +2122,14 @@ NGB_HD void b4_vgsteff_cv(const double *Mrow, const double *Prow, const B4W *w,
             dT10_dVd = -dVth_dVd * mstarcv;
             dT10_dVb = -dVth_dVb * mstarcv;
         } else if (T2 < -B4_EXP_THRESHOLD) {
-            T10 = Vtm * log(1.0 + B4_MIN_EXP);
+            T10 = Vtm * ngb_log(1.0 + B4_MIN_EXP);
             dT10_dVg = 0.0;
             dT10_dVd = T10 * dn_dVd;
             dT10_dVb = T10 * dn_dVb;
             T10 *= n;
         } else {
-            ExpVgst = exp(T2);
-            T3 = Vtm * log(1.0 + ExpVgst);
+            ExpVgst = ngb_exp(T2);
+            T3 = Vtm * ngb_log(1.0 + ExpVgst);
             T10 = n * T3;
             dT10_dVg = mstarcv * ExpVgst / (1.0 + ExpVgst);
             dT10_dVb = T3 * dn_dVb - dT10_dVg * (dVth_dVb + Vgst * dn_dVb / n);
@@ -2152,7 +2152,7 @@ NGB_HD void b4_vgsteff_cv(const double *Mrow, const double *Prow, const B4W *w,
             dT9_dVd = dn_dVd * T3;
             dT9_dVb = dn_dVb * T3;
         } else {
-            ExpVgst = exp(T2);
+            ExpVgst = ngb_exp(T2);
             T3 = coxe / cdep0;
             T4 = T3 * ExpVgst;
             T5 = T1 * T4 / T0;
@@ -2596,7 +2596,7 @@ NGB_HD int b4_charges(const B4Ctx *c, size_t t, const double *Mrow, const double
 
             tmp = T0 * B4P(acde);
             if ((-B4_EXP_THRESHOLD < tmp) && (tmp < B4_EXP_THRESHOLD)) {
-                Tcen = ldeb * exp(tmp);
+                Tcen = ldeb * ngb_exp(tmp);
                 dTcen_dVg = B4P(acde) * Tcen;
                 dTcen_dVb = dTcen_dVg * dT0_dVb;
                 dTcen_dVg *= dT0_dVg;
@@ -2652,7 +2652,7 @@ NGB_HD int b4_charges(const B4Ctx *c, size_t t, const double *Mrow, const double
             }
             T1 = 2.0 * T0 + Vgsteff;
 
-            DeltaPhi = Vtm * log(1.0 + T1 * Vgsteff / Denomi);
+            DeltaPhi = Vtm * ngb_log(1.0 + T1 * Vgsteff / Denomi);
             dDeltaPhi_dVg = 2.0 * Vtm * (T1 - T0) / (Denomi + T1 * Vgsteff);
 
             /* VgDP = Vgsteff - DeltaPhi */
@@ -2664,7 +2664,7 @@ NGB_HD int b4_charges(const B4Ctx *c, size_t t, const double *Mrow, const double
 
             Tox += Tox;
             T0 = (Vgsteff + B4I(vtfbphi2)) / Tox;
-            tmp = exp(B4M(bdos) * 0.7 * log(T0));
+            tmp = ngb_exp(B4M(bdos) * 0.7 * ngb_log(T0));
             T1 = 1.0 + tmp;
             T2 = B4M(bdos) * 0.7 * tmp / (T0 * Tox);
             Tcen = B4M(ados) * 1.9e-9 / T1;
@@ -2834,7 +2834,7 @@ NGB_HD void b4_junction_cv(double vj, double cz, double czsw, double czswg, doub
         if (cz > 0.0) {
             arg = 1.0 - vj / PhiB;
             if (MJ == 0.5) sarg = 1.0 / sqrt(arg);
-            else sarg = exp(-MJ * log(arg));
+            else sarg = ngb_exp(-MJ * ngb_log(arg));
             *q = PhiB * cz * (1.0 - arg * sarg) / (1.0 - MJ);
             *cap = cz * sarg;
         } else {
@@ -2844,14 +2844,14 @@ NGB_HD void b4_junction_cv(double vj, double cz, double czsw, double czswg, doub
         if (czsw > 0.0) {
             arg = 1.0 - vj / PhiBSW;
             if (MJSW == 0.5) sarg = 1.0 / sqrt(arg);
-            else sarg = exp(-MJSW * log(arg));
+            else sarg = ngb_exp(-MJSW * ngb_log(arg));
             *q += PhiBSW * czsw * (1.0 - arg * sarg) / (1.0 - MJSW);
             *cap += czsw * sarg;
         }
         if (czswg > 0.0) {
             arg = 1.0 - vj / PhiBSWG;
             if (MJSWG == 0.5) sarg = 1.0 / sqrt(arg);
-            else sarg = exp(-MJSWG * log(arg));
+            else sarg = ngb_exp(-MJSWG * ngb_log(arg));
             *q += PhiBSWG * czswg * (1.0 - arg * sarg) / (1.0 - MJSWG);
             *cap += czswg * sarg;
         }

@@ -11,6 +11,7 @@
 #define NGB_DEVSUP_CUH
 #include "ngb_common.h"
 #include "ngb_types.h"
+#include "ngb_math.cuh"
 
 NGB_HD double ngb_limvds(double vnew, double vold)
 {
@@ -33,10 +34,10 @@ NGB_HD double ngb_pnjlim(double vnew, double vold, double vt, double vcrit, int 
     if ((vnew > vcrit) && (fabs(vnew - vold) > (vt + vt))) {
         if (vold > 0) {
             double arg = (vnew - vold) / vt;
-            if (arg > 0) vnew = vold + vt * (2 + log(arg - 2));
-            else         vnew = vold - vt * (2 + log(2 - arg));
+            if (arg > 0) vnew = vold + vt * (2 + ngb_log(arg - 2));
+            else         vnew = vold - vt * (2 + ngb_log(2 - arg));
         } else {
-            vnew = vt * log(vnew / vt);
+            vnew = vt * ngb_log(vnew / vt);
         }
         *icheck = 1;
     } else if (vnew < 0) {

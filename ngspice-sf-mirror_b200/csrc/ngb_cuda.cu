@@ -163,6 +163,41 @@ int ngb_dev_sync(void)
 long ngb_dev_launch_count(void) { return g_launches; }
 void *ngb_dev_stream(void) { return (void *)g_stream; }
 
+/* live timing of the dominant kernel: CUDA events around sampled bsim4_load launches */
+#define NGB_PROF_MAX 2048
+static int g_prof_on = 0, g_prof_every = 1, g_prof_n = 0;
+static long g_prof_seen = 0;
+static cudaEvent_t g_prof_ev[2 * NGB_PROF_MAX];
+static int g_prof_created = 0;
+
+void ngb_dev_profile(int enable, int every)
+{
+    if (enable && !g_prof_created) {
+        for (int i = 0; i < 2 * NGB_PROF_MAX; i++) cudaEventCreate(&g_prof_ev[i]);
+        g_prof_created = 1;
+    }
+    g_prof_on = enable; g_prof_every = every > 0 ? every : 1; g_prof_n = 0; g_prof_seen = 0;
+}
+int ngb_dev_profile_read(double *ms_sum, long *count)
+{
+    double sum = 0.0;
+    if (g_stream) cudaStreamSynchronize(g_stream);
+    for (int i = 0; i < g_prof_n; i++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_prof_ev[2 * i], g_prof_ev[2 * i + 1]) == cudaSuccess) sum += ms;
+    }
+    if (ms_sum) *ms_sum = sum;
+    if (count) *count = g_prof_n;
+    g_prof_n = 0; g_prof_seen = 0;
+    return 0;
+}
+int ngb_dev_set_stream(void *stream)
+{
+    if (g_device < 0) return NGB_E_PANIC;
+    g_stream = (cudaStream_t)stream;
+    return 0;
+}
+
 static int post_launch(const char *what)
 {
     cudaError_t e = cudaGetLastError();
@@ -175,7 +210,10 @@ int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag)
 {
     if (c->T <= 0) return 0;
     const unsigned grid = (unsigned)(((size_t)c->T + 127) / 128);
+    const int rec = g_prof_on && (g_prof_seen++ % g_prof_every == 0) && g_prof_n < NGB_PROF_MAX;
+    if (rec) cudaEventRecord(g_prof_ev[2 * g_prof_n], g_stream);
     ngb_k_bsim4_load<<<grid, 128, 0, g_stream>>>(*c, errflag);
+    if (rec) { cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], g_stream); g_prof_n++; }
     return post_launch("bsim4_load");
 }
 int ngb_launch_cap_load(const NgbCapCtx *c, int *errflag)

@@ -22,7 +22,10 @@ int   ngb_dev_d2h(void *dst, const void *src, size_t bytes);
 int   ngb_dev_memset(void *dst, int byte, size_t bytes);
 int   ngb_dev_sync(void);
 long  ngb_dev_launch_count(void);               /* kernels launched so far (bench "gpu_launches") */
-void *ngb_dev_stream(void);                     /* cudaStream_t the kernels are launched on */
+void *ngb_dev_stream(void);
+int   ngb_dev_set_stream(void *stream);         /* adopt a caller-owned cudaStream_t */
+void  ngb_dev_profile(int enable, int every);   /* CUDA-event timing of sampled bsim4_load launches */
+int   ngb_dev_profile_read(double *ms_sum, long *count);                     /* cudaStream_t the kernels are launched on */
 
 int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag);
 int ngb_launch_cap_load(const NgbCapCtx *c, int *errflag);

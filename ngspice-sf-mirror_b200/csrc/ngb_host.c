@@ -26,6 +26,11 @@ void ngb_set_error(const char *fmt, ...)
 const char *ngbLastError(void) { return g_err; }
 const char *ngbBackend(void) { return ngb_dev_backend(); }
 long ngbLaunchCount(void) { return ngb_dev_launch_count(); }
+int ngbInit(int device) { return ngb_dev_init(device); }
+int ngbSetStream(void *cuda_stream) { return ngb_dev_set_stream(cuda_stream); }
+int ngbSync(void) { return ngb_dev_sync(); }
+void ngbProfile(int enable, int every) { ngb_dev_profile(enable, every); }
+int ngbProfileRead(double *ms_sum, long *count) { return ngb_dev_profile_read(ms_sum, count); }
 
 /* ------------------------------------------------------------------ field names */
 #define X(n) #n,
@@ -616,6 +621,12 @@ int ngbCircuitSetLuPattern(ngb_circuit *c, int n, int nblocks, const int *Q, con
     }
     /* NOTE on level correctness: within column k the U entries are visited in topological
      * order, so when pair (L(i,j), U(j,k)) raises level[target] the level of U(j,k) is final. */
+    /* self-check: every operand of an entry must sit on a strictly lower level */
+    for (k = 0; k < nV; k++) {
+        for (p = e_pptr[k]; p < e_pptr[k + 1]; p++)
+            if (level[pl[p]] >= level[k] || level[pu[p]] >= level[k]) { ngb_set_error("LU schedule: operand level violation at entry %d", k); free(pl); free(pu); goto bad; }
+        if (e_div[k] >= 0 && level[e_div[k]] >= level[k]) { ngb_set_error("LU schedule: pivot level violation at entry %d", k); free(pl); free(pu); goto bad; }
+    }
     for (k = 0; k < nV; k++) if (level[k] + 1 > nlev) nlev = level[k] + 1;
     h->lev_ptr = (int *)xcalloc((size_t)nlev + 1, sizeof(int));
     h->lev_ent = (int *)xcalloc((size_t)nV, sizeof(int));
@@ -689,6 +700,11 @@ int ngbCircuitSetLuPattern(ngb_circuit *c, int n, int nblocks, const int *Q, con
         /* The level of x_k must be final before it feeds later rows.  Inside a block the U loop
          * runs k descending and x_k receives pairs only from larger k, and y rows receive L pairs
          * from smaller k before being used: the chronological sweep above is a valid order. */
+        for (k = 0; k < ntask; k++) {
+            for (p = t_pptr[k]; p < t_pptr[k + 1]; p++)
+                if (tl[t_src[p]] >= tl[k]) { ngb_set_error("solve schedule: source level violation at task %d", k); return NGB_E_PANIC; }
+            if (t_kind[k] == 1 && tl[t_init[k]] >= tl[k]) { ngb_set_error("solve schedule: x before y at task %d", k); return NGB_E_PANIC; }
+        }
         for (k = 0; k < ntask; k++) if (tl[k] + 1 > nslev) nslev = tl[k] + 1;
         {
             int *sp = (int *)xcalloc((size_t)nslev + 1, sizeof(int)), *st = (int *)xcalloc((size_t)ntask, sizeof(int)), *fill;

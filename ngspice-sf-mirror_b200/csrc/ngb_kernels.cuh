@@ -152,7 +152,7 @@ NGB_HD double ngb_src_value(const NgbSrcCtx *c, size_t t, int inst, int s, int m
             const double THETA = forder > 4 ? SCO(4) : 0.0;
             time -= TD;
             if (time <= 0) value = VO + VA * sin(phase);
-            else value = VO + VA * sin(FREQ * time * 2.0 * M_PI + phase) * exp(-time * THETA);
+            else value = VO + VA * sin(FREQ * time * 2.0 * M_PI + phase) * ngb_exp(-time * THETA);
         } break;
         }
     }

@@ -78,6 +78,10 @@ def run(name, netlist, calls, save):
     os.makedirs(TMP, exist_ok=True)
     cir = os.path.join(TMP, name + ".cir")
     open(cir, "w").write(netlist)
+    if name in ("ro17", "ro101", "ro17k"):
+        # the netlist itself is kept too: the CPU-baseline arm of bench.py feeds it to oracle/_ref/ngspice
+        os.makedirs(os.path.join(HERE, "netlists"), exist_ok=True)
+        open(os.path.join(HERE, "netlists", name + ".cir"), "w").write(netlist)
     env = dict(os.environ, NGB_DUMP_FLAT=os.path.join(TMP, name + ".flat"),
                NGB_DUMP_TRACE=os.path.join(TMP, name + ".trace"), NGB_DUMP_CALLS=calls,
                NGB_DUMP_STATS=os.path.join(TMP, name + ".stats"))

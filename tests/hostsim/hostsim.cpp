@@ -23,6 +23,9 @@ int ngb_dev_memset(void *d, int v, size_t n) { memset(d, v, n); return 0; }
 int ngb_dev_sync(void) { return 0; }
 long ngb_dev_launch_count(void) { return g_launches; }
 void *ngb_dev_stream(void) { return nullptr; }
+int ngb_dev_set_stream(void *) { return 0; }
+void ngb_dev_profile(int, int) {}
+int ngb_dev_profile_read(double *ms, long *n) { if (ms) *ms = 0; if (n) *n = 0; return 0; }
 
 int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag)
 {
@@ -65,3 +68,7 @@ int ngb_launch_tran_control(const NgbTranCtx *c)
     return 0;
 }
 }
+
+/* test entry points for the libm-compatible exp/log (tests/test_math_replica.py) */
+extern "C" void hostsim_exp(const double *x, double *y, int n) { for (int i = 0; i < n; i++) y[i] = ngb_exp(x[i]); }
+extern "C" void hostsim_log(const double *x, double *y, int n) { for (int i = 0; i < n; i++) y[i] = ngb_log(x[i]); }
