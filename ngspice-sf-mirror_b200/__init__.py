@@ -10,6 +10,7 @@ import os
 import numpy as np
 from . import ngt  # noqa: F401
 from . import mc  # noqa: F401
+from . import parallel  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libngb200.so")
