@@ -204,7 +204,7 @@ def bench_ours(args):
     if args.workload == "ro101":
         inst_host = np.repeat(np.asarray(flat["b4/inst"])[:, :, None], S, axis=2)
     else:
-        dv = pkg.mc.draw_delvto(S, ninst, sigma=0.015, seed=1000 + rank)
+        dv = pkg.mc.delvto_as_parsed(pkg.mc.draw_delvto(S, ninst, sigma=0.015, seed=1000 + rank))
         inst_host = pkg.mc.bsim4_inst_with_delvto(lib, flat, dv)
     pinned = torch.empty(inst_host.shape, dtype=torch.float64).pin_memory()
     pinned.numpy()[...] = inst_host

@@ -13,7 +13,7 @@ from . import mc  # noqa: F401
 from . import parallel  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libngb200.so")
+LIB_PATH = os.environ.get("NGB200_LIB", os.path.join(_HERE, "libngb200.so"))
 
 _c_int_p = ctypes.POINTER(ctypes.c_int)
 _c_dbl_p = ctypes.POINTER(ctypes.c_double)

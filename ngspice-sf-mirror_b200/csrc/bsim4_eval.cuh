@@ -27,6 +27,15 @@
 #include "bsim4_fields.h"
 #include "devsup.cuh"
 
+/* Optional CTA-wide barrier at each phase boundary of the evaluation (keeps the warps of a CTA in
+ * one instruction-cache window).  Measured on B200: no gain (571 vs 572 us per launch), so it is
+ * off unless NGB_B4_PHASE_BARRIERS is defined. */
+#if defined(__CUDA_ARCH__) && defined(NGB_B4_PHASE_BARRIERS)
+#define NGB_CTA_ALIGN() __syncthreads()
+#else
+#define NGB_CTA_ALIGN() ((void)0)
+#endif
+
 #define B4_MAX_EXPL 2.688117142e+43
 #define B4_MIN_EXPL 3.720075976e-44
 #define B4_EXPL_THRESHOLD 100.0
@@ -409,6 +418,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     double dT10_dVg, dT10_dVd, dT10_dVb;
     double tmp, tmp1, tmp2, tmp3, tmp4;
 
+    NGB_CTA_ALIGN();
     /* ---- source/drain junction diodes (DC) ---- */
     {
         const int dioMod = (int)B4M(dioMod);
@@ -453,6 +463,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         }
     }
 
+    NGB_CTA_ALIGN();
     /* ---- orientation ---- */
     double Vds, Vgs, Vbs, Vdb;
     if (w->vds >= 0.0) { w->mode = 1;  Vds = w->vds;  Vgs = w->vgs; Vbs = w->vbs; Vdb = w->vds - w->vbs; }
@@ -464,6 +475,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     else { epsrox = B4M(epsrox); toxe = B4M(toxe); epssub = B4_EPSSI; }
     w->toxe = toxe; w->epsrox = epsrox; w->epssub = epssub;
 
+    NGB_CTA_ALIGN();
     /* ---- effective body bias ---- */
     const double vbsc = B4I(vbsc);
     const double phi = B4P(phi), sqrtPhi = B4P(sqrtPhi);
@@ -497,6 +509,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     const double weff = B4P(weff);
     const double factor1 = B4M(factor1);
 
+    NGB_CTA_ALIGN();
     /* ---- threshold voltage ---- */
     T3 = sqrt(Xdep);
     const double V0 = B4P(vbi) - phi;
@@ -578,6 +591,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
                     + B4P(kt2) * TempRatio;
     double dVth_dVd = -dDIBL_Sft_dVd;
 
+    NGB_CTA_ALIGN();
     /* ---- subthreshold swing factor n ---- */
     double n, dn_dVb, dn_dVd;
     tmp1 = epssub / Xdep;
@@ -633,6 +647,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
 
     w->von = Vth;
 
+    NGB_CTA_ALIGN();
     /* ---- poly-gate depletion ---- */
     {
         const double vfbphi = B4I(vfb) + phi;
@@ -647,6 +662,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
 
     const double Vgst = Vgs_eff - Vth;
 
+    NGB_CTA_ALIGN();
     /* ---- Vgsteff ---- */
     const double mstar = B4P(mstar);
     const double cdep0 = B4P(cdep0);
@@ -706,6 +722,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     const double dVgsteff_dVd = (T9 * dT10_dVd - T10 * dT9_dVd) / T11;
     const double dVgsteff_dVb = (T9 * dT10_dVb - T10 * dT9_dVb) / T11;
 
+    NGB_CTA_ALIGN();
     /* ---- effective channel geometry ---- */
     T9 = sqrtPhis - sqrtPhi;
     double Weff = weff - 2.0 * (B4P(dwg) * Vgsteff + B4P(dwb) * T9);
@@ -740,6 +757,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         /* grdsw (noise/ask only) not kept */
     }
 
+    NGB_CTA_ALIGN();
     /* ---- Abulk ---- */
     double Abulk0, dAbulk0_dVb, Abulk, dAbulk_dVg, dAbulk_dVb, Abulk0_Q, dAbulk0_Q_dVb;
     T9 = 0.5 * k1ox * Lpe_Vb / sqrtPhis;
@@ -813,6 +831,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         Abulk0_Q = Abulk0;
     }
 
+    NGB_CTA_ALIGN();
     /* ---- mobility ---- */
     const int mobMod = (int)B4M(mobMod);
     const double ua = B4P(ua), ub = B4P(ub), uc = B4P(uc), ud = B4P(ud);
@@ -957,6 +976,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     const double dueff_dVd = T9 * dDenomi_dVd;
     const double dueff_dVb = T9 * dDenomi_dVb;
 
+    NGB_CTA_ALIGN();
     /* ---- saturation drain voltage ---- */
     const double vsattemp = B4I(vsattemp);
     const double WVCox = Weff * vsattemp * coxe;
@@ -1048,6 +1068,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     }
     w->vdsat = Vdsat;
 
+    NGB_CTA_ALIGN();
     /* ---- Vdseff ---- */
     const double delta = B4P(delta);
     double Vdseff, dVdseff_dVg, dVdseff_dVd, dVdseff_dVb;
@@ -1086,6 +1107,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     if (Vdseff > Vds) Vdseff = Vds;
     const double diffVds = Vds - Vdseff;
 
+    NGB_CTA_ALIGN();
     /* ---- velocity overshoot ---- */
     if (((int)B4M(lambdaGiven)) && (B4M(lambda) > 0.0)) {
         T1 = Leff * ueff;
@@ -1125,6 +1147,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         Esat = EsatL / Leff;
     }
 
+    NGB_CTA_ALIGN();
     /* ---- Vasat ---- */
     tmp4 = 1.0 - 0.5 * Abulk * Vdsat / Vgst2Vtm;
     T9 = WVCoxRds * Vgsteff;
@@ -1148,6 +1171,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     const double dVasat_dVb = (dT0_dVb - Vasat * dT1_dVb) / T1;
     const double dVasat_dVd = dT0_dVd / T1;
 
+    NGB_CTA_ALIGN();
     /* ---- Idl ---- */
     double Tcen, dTcen_dVg, Coxeff, dCoxeff_dVg;
     tmp1 = B4I(vtfbphi2);
@@ -1202,6 +1226,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     const double dIdl_dVd = T1 * dgche_dVd;
     const double dIdl_dVb = T1 * dgche_dVb - T2 * dRds_dVb;
 
+    NGB_CTA_ALIGN();
     /* ---- degradation factor due to pocket implant ---- */
     double FP, dFP_dVg;
     if (B4P(fprout) <= 0.0) {
@@ -1213,6 +1238,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         dFP_dVg = FP * FP * T9 / Vgst2Vtm;
     }
 
+    NGB_CTA_ALIGN();
     /* ---- VACLM ---- */
     double PvagTerm, dPvagTerm_dVg, dPvagTerm_dVb, dPvagTerm_dVd;
     T8 = B4P(pvag) / EsatL;
@@ -1260,6 +1286,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         dCclm_dVd = dCclm_dVg = dCclm_dVb = 0.0;
     }
 
+    NGB_CTA_ALIGN();
     /* ---- VADIBL ---- */
     double VADIBL, dVADIBL_dVg, dVADIBL_dVd, dVADIBL_dVb;
     if (B4P(thetaRout) > B4_MIN_EXP) {
@@ -1306,12 +1333,14 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         dVADIBL_dVd = dVADIBL_dVg = dVADIBL_dVb = 0.0;
     }
 
+    NGB_CTA_ALIGN();
     /* ---- Va ---- */
     const double Va = Vasat + VACLM;
     const double dVa_dVg = dVasat_dVg + dVACLM_dVg;
     const double dVa_dVb = dVasat_dVb + dVACLM_dVb;
     const double dVa_dVd = dVasat_dVd + dVACLM_dVd;
 
+    NGB_CTA_ALIGN();
     /* ---- VADITS ---- */
     double VADITS, dVADITS_dVg, dVADITS_dVd;
     T0 = B4P(pditsd) * Vds;
@@ -1328,6 +1357,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         dVADITS_dVg = dVADITS_dVd = 0;
     }
 
+    NGB_CTA_ALIGN();
     /* ---- VASCBE ---- */
     double VASCBE, dVASCBE_dVg, dVASCBE_dVd, dVASCBE_dVb;
     if ((B4P(pscbe2) > 0.0) && (B4P(pscbe1) >= 0.0)) {
@@ -1347,6 +1377,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         dVASCBE_dVg = dVASCBE_dVd = dVASCBE_dVb = 0.0;
     }
 
+    NGB_CTA_ALIGN();
     /* ---- add DIBL to Ids ---- */
     double Idsa, dIdsa_dVg, dIdsa_dVd, dIdsa_dVb;
     T9 = diffVds / VADIBL;
@@ -1356,6 +1387,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     dIdsa_dVd = T0 * dIdl_dVd + Idl * (1.0 - dVdseff_dVd - T9 * dVADIBL_dVd) / VADIBL;
     dIdsa_dVb = T0 * dIdl_dVb - Idl * (dVdseff_dVb + T9 * dVADIBL_dVb) / VADIBL;
 
+    NGB_CTA_ALIGN();
     /* ---- add DITS to Ids ---- */
     T9 = diffVds / VADITS;
     T0 = 1.0 + T9;
@@ -1364,6 +1396,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     dIdsa_dVb = T0 * dIdsa_dVb - Idsa * dVdseff_dVb / VADITS;
     Idsa *= T0;
 
+    NGB_CTA_ALIGN();
     /* ---- add CLM to Ids ---- */
     T0 = ngb_log(Va / Vasat);
     dT0_dVg = dVa_dVg / Va - dVasat_dVg / Vasat;
@@ -1380,6 +1413,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     dIdsa_dVd = dIdsa_dVd * T9 + Idsa * dT9_dVd;
     Idsa *= T9;
 
+    NGB_CTA_ALIGN();
     /* ---- substrate current ---- */
     double Isub, Gbd, Gbb, Gbg;
     tmp = B4P(alpha0) + B4P(alpha1) * Leff;
@@ -1414,6 +1448,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     }
     w->csub = Isub; w->gbbs = Gbb; w->gbgs = Gbg; w->gbds = Gbd;
 
+    NGB_CTA_ALIGN();
     /* ---- add SCBE to Ids ---- */
     double Ids, Gm, Gds, Gmb, cdrain;
     T9 = diffVds / VASCBE;
@@ -1434,6 +1469,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
 
     cdrain = Ids * Vdseff;
 
+    NGB_CTA_ALIGN();
     /* ---- source-end velocity limit ---- */
     if (((int)B4M(vtlGiven)) && (B4M(vtl) > 0.0)) {
         double vs, dvs_dVg, dvs_dVd, dvs_dVb, Fsevl, dFsevl_dVg, dFsevl_dVd, dFsevl_dVb;
@@ -1604,6 +1640,7 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
     double dT2_dVg, dT2_dVd, dT2_dVb, dT6_dVg, dT6_dVd, dT6_dVb, dT7_dVg, dT7_dVd, dT7_dVb;
     double dT8_dVg, dT8_dVd, dT8_dVb, dT9_dVg, dT9_dVd, dT9_dVb, dT10_dVg, dT10_dVd, dT10_dVb;
 
+    NGB_CTA_ALIGN();
     /* ---- Rg ---- */
     w->gcrg = w->gcrgd = w->gcrgg = w->gcrgs = w->gcrgb = 0.0;
     if (rgateMod > 1) {      /* trnqsMod/acnqsMod are 0 on this path */
@@ -1634,6 +1671,7 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
         w->gcrgs = -(w->gcrgg + w->gcrgd + w->gcrgb);
     }
 
+    NGB_CTA_ALIGN();
     /* ---- bias-dependent external S/D resistance ---- */
     if ((int)B4M(rdsMod)) {
         double vgs_eff, dvgs_eff_dvg, vgd_eff, dvgd_eff_dvg, dT0_dvg, dT1_dvb, dT3_dvg, dT3_dvb;
@@ -1716,6 +1754,7 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
         w->gdtot = w->gdtotd = w->gdtotg = w->gdtots = w->gdtotb = 0.0;
     }
 
+    NGB_CTA_ALIGN();
     /* ---- GIDL / GISL ---- */
     {
         const double weffCJ = B4P(weffCJ);
@@ -1747,6 +1786,7 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
         }
     }
 
+    NGB_CTA_ALIGN();
     /* ---- gate tunnelling current ---- */
     double Vfb = 0.0, Voxacc = 0.0, dVoxacc_dVg = 0.0, dVoxacc_dVb = 0.0;
     double Voxdepinv = 0.0, dVoxdepinv_dVg = 0.0, dVoxdepinv_dVd = 0.0, dVoxdepinv_dVb = 0.0;
@@ -2053,6 +2093,7 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
         w->Igb = w->gIgbg = w->gIgbd = w->gIgbs = w->gIgbb = 0.0;
     }
 
+    NGB_CTA_ALIGN();
     /* ---- finger multiplication ---- */
     if (nf != 1.0) {
         w->cdrain *= nf; w->gds *= nf; w->gm *= nf; w->gmbs *= nf;
@@ -2914,6 +2955,7 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
     const double vds = w.vds, vgs = w.vgs, vbs = w.vbs, vbd = w.vbd, vgd = w.vgd, vgb = w.vgb;
     const double vgmb = w.vgmb, vbs_jct = w.vbs_jct, vbd_jct = w.vbd_jct;
 
+    NGB_CTA_ALIGN();
     /* ---- junction C-V ---- */
     w.capbs = w.capbd = 0.0;
     w.qbs = B4ST(0, B4ST_qbs);
@@ -2936,6 +2978,7 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
         B4ST(0, B4ST_qbd) = w.qbd;
     }
 
+    NGB_CTA_ALIGN();
     /* ---- convergence flag from limiting (NEWCONV build: only `Check`) ---- */
     if (((flags & B4F_OFF) == 0) || (!(mode_ckt & NGB_MODEINITFIX))) {
         if (w.Check == 1) {
@@ -3210,6 +3253,7 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
         gcdbdb = gcsbsb = 0.0;
     }
 
+    NGB_CTA_ALIGN();
     /* ---- Norton equivalents of the DC currents (line900) ---- */
     double Gm, Gmbs, FwdSum, RevSum, ceqdrn, ceqbd, ceqbs;
     double gbbdp, gbbsp, gbdpg, gbdpdp, gbdpb, gbdpsp, gbspg, gbspdp, gbspb, gbspsp;
@@ -3401,6 +3445,7 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
         if (rgateMod == 3) ceqqgmid = -ceqqgmid;
     }
 
+    NGB_CTA_ALIGN();
     /* ---- right-hand side ---- */
     const double m = B4I(m);
     const double mult_i = B4I(mult_i) * m;
@@ -3427,6 +3472,7 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
         B4_STAMP(B4R_s, (mult_i * ceqgstot));
     }
 
+    NGB_CTA_ALIGN();
     /* ---- matrix ---- */
     double gjbd, gjbs, gdpr, gspr;
     if (!rbodyMod) { gjbd = w.gbd; gjbs = w.gbs; }
@@ -3573,6 +3619,7 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
         B4_STAMP(B4S_Bb, mult_i * (grbsb + grbdb + grbpb));
     }
 
+    NGB_CTA_ALIGN();
     /* ---- operating point ---- */
     c->op[(size_t)B4O_von * c->T + t] = w.von;
     if (c->op_full) {

@@ -17,6 +17,12 @@
 #include "ngb_dev.h"
 #include "ngb_kernels.cuh"
 
+#ifndef NGB_B4_CTA
+#define NGB_B4_CTA 256
+#endif
+#ifndef NGB_B4_MINBLOCKS
+#define NGB_B4_MINBLOCKS 2      /* 128 registers/thread, 16 warps/SM: measured 1.5x faster than 255 registers */
+#endif
 static cudaStream_t g_stream = nullptr;
 static int g_device = -1;
 static long g_launches = 0;
@@ -28,7 +34,7 @@ extern "C" void ngb_set_error(const char *fmt, ...);
     ngb_set_error("%s failed: %s", #call, cudaGetErrorString(e_)); return NGB_E_PANIC; } } while (0)
 
 /* ------------------------------------------------------------------ kernels */
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(NGB_B4_CTA, NGB_B4_MINBLOCKS)
 ngb_k_bsim4_load(const B4Ctx c, int *errflag)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -87,6 +93,29 @@ __global__ void ngb_k_lu_block(const NgbLuCtx c)
     ngb_lu_sample(&c, s, threadIdx.x, blockDim.x, V, Rs, Z);
 }
 
+/* packed schedule in shared memory: `groups` samples per CTA, `tpg` threads per sample */
+__global__ void ngb_k_lu_packed(const NgbLuCtx c, int groups, int tpg, int per_sample_doubles)
+{
+    extern __shared__ double smem[];
+    const NgbLuPacked *h = &c.pk;
+    unsigned short *sb = reinterpret_cast<unsigned short *>(smem);
+    const int blob_doubles = (h->blob_u16 + 3) / 4;
+    {   /* one coalesced copy of the schedule per CTA */
+        const unsigned *src = reinterpret_cast<const unsigned *>(h->blob);
+        unsigned *dst = reinterpret_cast<unsigned *>(smem);
+        for (int i = threadIdx.x; i < h->blob_u16 / 2; i += blockDim.x) dst[i] = __ldg(&src[i]);
+    }
+    __syncthreads();
+    const int g = threadIdx.x / tpg, lane = threadIdx.x - g * tpg;
+    const int s = blockIdx.x * groups + g;
+    if (s >= c.S) return;
+    double *V = smem + blob_doubles + (size_t)g * per_sample_doubles;
+    double *Rs = V + h->nV;
+    double *Z = Rs + h->n;
+    double *As = Z;                 /* the sample's A is dead before the solve starts */
+    ngb_lu_sample_packed(&c, sb, s, lane, tpg, V, Rs, Z, As);
+}
+
 __global__ void __launch_bounds__(128)
 ngb_k_tran_control(const NgbTranCtx c)
 {
@@ -125,6 +154,7 @@ int ngb_dev_init(int device)
     CUDA_OK(cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CUDA_OK(cudaFuncSetAttribute(ngb_k_lu_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
     CUDA_OK(cudaFuncSetAttribute(ngb_k_lu_block, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
+    CUDA_OK(cudaFuncSetAttribute(ngb_k_lu_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
     g_device = device;
     return 0;
 }
@@ -209,10 +239,10 @@ static int post_launch(const char *what)
 int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag)
 {
     if (c->T <= 0) return 0;
-    const unsigned grid = (unsigned)(((size_t)c->T + 127) / 128);
+    const unsigned grid = (unsigned)(((size_t)c->T + NGB_B4_CTA - 1) / NGB_B4_CTA);
     const int rec = g_prof_on && (g_prof_seen++ % g_prof_every == 0) && g_prof_n < NGB_PROF_MAX;
     if (rec) cudaEventRecord(g_prof_ev[2 * g_prof_n], g_stream);
-    ngb_k_bsim4_load<<<grid, 128, 0, g_stream>>>(*c, errflag);
+    ngb_k_bsim4_load<<<grid, NGB_B4_CTA, 0, g_stream>>>(*c, errflag);
     if (rec) { cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], g_stream); g_prof_n++; }
     return post_launch("bsim4_load");
 }
@@ -241,6 +271,25 @@ int ngb_launch_lu(const NgbLuCtx *c)
 {
     const int per = c->sch.nV + c->sch.n + c->sch.ntask;
     const size_t bytes1 = (size_t)per * sizeof(double);
+    if (c->pk.ok) {
+        const int per = c->sch.nV + c->sch.n + (c->sch.ntask > c->sch.nnz ? c->sch.ntask : c->sch.nnz);   /* A aliases the solve vector */
+        const size_t bytes1 = (size_t)per * sizeof(double);
+        /* schedule blob + per-sample values in shared memory.  Many samples: one warp each, as many
+         * per CTA as keeps two CTAs resident; few samples: one CTA of 256 threads per sample. */
+        const size_t blob = (size_t)((c->pk.blob_u16 + 3) / 4) * sizeof(double);
+        const size_t budget = (size_t)g_smem_optin / 2 - 2048;
+        if (c->S >= 64 && blob + bytes1 <= budget) {
+            int groups = (int)((budget - blob) / bytes1);
+            if (groups > 8) groups = 8;
+            const unsigned grid = (unsigned)((c->S + groups - 1) / groups);
+            ngb_k_lu_packed<<<grid, groups * 32, blob + bytes1 * groups, g_stream>>>(*c, groups, 32, per);
+            return post_launch("lu_packed");
+        }
+        if (blob + bytes1 <= (size_t)g_smem_optin) {
+            ngb_k_lu_packed<<<(unsigned)c->S, 256, blob + bytes1, g_stream>>>(*c, 1, 256, per);
+            return post_launch("lu_packed");
+        }
+    }
     /* warp per sample while four samples fit one CTA's shared memory with room for 2+ CTAs/SM */
     if (bytes1 * 4 <= (size_t)g_smem_optin / 2) {
         const int warps = 4;

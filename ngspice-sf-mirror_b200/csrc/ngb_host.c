@@ -155,6 +155,7 @@ ngb_circuit *ngbCircuitCreate(int neq, const int *node_type)
     return c;
 }
 
+static void free_packed(NgbLuPacked *p);
 static void free_sched(NgbLuSched *h)
 {
 #define F(p) free((void *)h->p)
@@ -179,6 +180,7 @@ void ngbCircuitDestroy(ngb_circuit *c)
     free(c->tgt_ptr); free(c->tgt_rows); free(c->const_row); free(c->const_val);
     free(c->klu_Q); free(c->klu_R); free(c->klu_Pnum);
     free_sched(&c->sch);
+    free_packed(&c->pk);
     free(c);
 }
 
@@ -515,6 +517,80 @@ int ngbCircuitGetBsim4Slots(const ngb_circuit *c, int *slots)
 }
 
 /* ------------------------------------------------------------------ LU task schedule */
+static void free_packed(NgbLuPacked *p)
+{
+    free((void *)p->blob); free((void *)p->aslot); free((void *)p->arow); free((void *)p->ext);
+    memset(p, 0, sizeof *p);
+}
+
+/* renumber values and solve tasks level by level and pack the per-level data as 16-bit indices */
+static void build_packed(ngb_circuit *c)
+{
+    const NgbLuSched *h = &c->sch;
+    NgbLuPacked *p = &c->pk;
+    const int nV = h->nV, n = h->n, ntask = h->ntask, np = c->npairs, nsp = c->nsolvepairs;
+    int *vint, *tint, k, q, off = 0;
+    unsigned short *b;
+    int *aslot, *arow, *ext;
+    free_packed(p);
+    if (nV >= 65535 || ntask >= 65535 || np >= 65535 || nsp >= 65535 || n >= 65535 || h->nnz >= 65535) return;   /* generic kernel only */
+    vint = (int *)xcalloc((size_t)nV, sizeof(int)); tint = (int *)xcalloc((size_t)ntask, sizeof(int));
+    for (k = 0; k < nV; k++) vint[h->lev_ent[k]] = k;           /* lev_ent lists entries level by level */
+    for (k = 0; k < ntask; k++) tint[h->slev_task[k]] = k;
+    p->n = n; p->nnz = h->nnz; p->nV = nV; p->nlev = h->nlev; p->ntask = ntask; p->nslev = h->nslev; p->npairs = np; p->nsp = nsp;
+#define SEG(field, cnt) p->field = off; off += (cnt)
+    SEG(o_lev_ptr, h->nlev + 1); SEG(o_div, nV); SEG(o_pptr, nV + 1); SEG(o_pl, np); SEG(o_pu, np); SEG(o_diag, n);
+    SEG(o_slev_ptr, h->nslev + 1); SEG(o_kind, ntask); SEG(o_init, ntask); SEG(o_tdiv, ntask); SEG(o_tpptr, ntask + 1);
+    SEG(o_tval, nsp); SEG(o_tsrc, nsp); SEG(o_out, n);
+    SEG(o_aslot, nV); SEG(o_arow, nV); SEG(o_rowptr, n + 1); SEG(o_rowslot, h->nnz);
+#undef SEG
+    if (off & 1) off++;
+    p->blob_u16 = off;
+    b = (unsigned short *)xcalloc((size_t)off, sizeof(unsigned short));
+    aslot = (int *)xcalloc((size_t)nV, sizeof(int)); arow = (int *)xcalloc((size_t)nV, sizeof(int)); ext = (int *)xcalloc((size_t)nV, sizeof(int));
+    for (k = 0; k <= h->nlev; k++) b[p->o_lev_ptr + k] = (unsigned short)h->lev_ptr[k];
+    q = 0;
+    for (k = 0; k < nV; k++) {
+        const int e = h->lev_ent[k];           /* external id of internal entry k */
+        int pp;
+        ext[k] = e; aslot[k] = h->e_aslot[e]; arow[k] = h->e_arow[e];
+        b[p->o_div + k] = (unsigned short)(h->e_div[e] >= 0 ? vint[h->e_div[e]] : 0xFFFF);
+        b[p->o_pptr + k] = (unsigned short)q;
+        for (pp = h->e_pptr[e]; pp < h->e_pptr[e + 1]; pp++, q++) {
+            b[p->o_pl + q] = (unsigned short)vint[h->pair_l[pp]];
+            b[p->o_pu + q] = (unsigned short)vint[h->pair_u[pp]];
+        }
+    }
+    b[p->o_pptr + nV] = (unsigned short)q;
+    for (k = 0; k < n; k++) b[p->o_diag + k] = (unsigned short)vint[h->diag_v[k]];
+    for (k = 0; k <= h->nslev; k++) b[p->o_slev_ptr + k] = (unsigned short)h->slev_ptr[k];
+    q = 0;
+    for (k = 0; k < ntask; k++) {
+        const int t = h->slev_task[k];
+        int pp;
+        b[p->o_kind + k] = (unsigned short)h->t_kind[t];
+        b[p->o_init + k] = (unsigned short)(h->t_kind[t] == 0 ? h->t_init[t] : tint[h->t_init[t]]);
+        b[p->o_tdiv + k] = (unsigned short)(h->t_div[t] >= 0 ? vint[h->t_div[t]] : 0xFFFF);
+        b[p->o_tpptr + k] = (unsigned short)q;
+        for (pp = h->t_pptr[t]; pp < h->t_pptr[t + 1]; pp++, q++) {
+            b[p->o_tval + q] = (unsigned short)vint[h->t_val[pp]];
+            b[p->o_tsrc + q] = (unsigned short)tint[h->t_src[pp]];
+        }
+    }
+    b[p->o_tpptr + ntask] = (unsigned short)q;
+    for (k = 0; k < n; k++) b[p->o_out + k] = (unsigned short)tint[h->out_task[k]];
+    for (k = 0; k < nV; k++) {
+        b[p->o_aslot + k] = (unsigned short)(aslot[k] >= 0 ? aslot[k] : 0xFFFF);
+        b[p->o_arow + k] = (unsigned short)(aslot[k] >= 0 ? arow[k] : 0);
+    }
+    for (k = 0; k <= n; k++) b[p->o_rowptr + k] = (unsigned short)h->row_ptr[k];
+    for (k = 0; k < h->nnz; k++) b[p->o_rowslot + k] = (unsigned short)h->row_slot[k];
+    p->blob = b; p->aslot = aslot; p->arow = arow; p->ext = ext;
+    p->row_ptr = h->row_ptr; p->row_slot = h->row_slot; p->b_eq = h->b_eq; p->out_eq = h->out_eq;
+    p->ok = 1;
+    free(vint); free(tint);
+}
+
 int ngbCircuitSetLuPattern(ngb_circuit *c, int n, int nblocks, const int *Q, const int *R, const int *Pnum,
                            const int *Lp, const int *Li, const int *Up, const int *Ui,
                            const int *Offp, const int *Offi)
@@ -726,6 +802,7 @@ int ngbCircuitSetLuPattern(ngb_circuit *c, int n, int nblocks, const int *Q, con
         h->b_eq = b_eq; h->out_task = ot; h->out_eq = oe;
     }
     free(Pinv); free(pos); free(level);
+    build_packed(c);
     c->have_lu = 1;
     return NGB_OK;
 bad:
@@ -783,6 +860,17 @@ static void sched_to_dev(ngb_batch *b, const ngb_circuit *c)
     D(t_kind, h->ntask); D(t_init, h->ntask); D(t_div, h->ntask); D(t_pptr, h->ntask + 1);
     D(t_val, c->nsolvepairs); D(t_src, c->nsolvepairs); D(b_eq, h->n); D(out_task, h->n); D(out_eq, h->n);
 #undef D
+}
+static void packed_to_dev(ngb_batch *b, const ngb_circuit *c)
+{
+    const NgbLuPacked *p = &c->pk; NgbLuPacked *d = &b->dpk;
+    *d = *p;
+    if (!p->ok) return;
+    d->blob = (const unsigned short *)dev_dup(p->blob, sizeof(unsigned short) * (size_t)p->blob_u16);
+    d->aslot = (const int *)dev_dup(p->aslot, sizeof(int) * (size_t)p->nV);
+    d->arow = (const int *)dev_dup(p->arow, sizeof(int) * (size_t)p->nV);
+    d->ext = (const int *)dev_dup(p->ext, sizeof(int) * (size_t)p->nV);
+    d->row_ptr = b->dsch.row_ptr; d->row_slot = b->dsch.row_slot; d->b_eq = b->dsch.b_eq; d->out_eq = b->dsch.out_eq;
 }
 static void sched_dev_free(NgbLuSched *d)
 {
@@ -889,6 +977,7 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
     }
     if (c->have_lu) {
         sched_to_dev(b, c);
+        packed_to_dev(b, c);
         b->V = (double *)dalloc(b, "lu.V", sizeof(double) * (size_t)c->sch.nV * S);
         b->Rs = (double *)dalloc(b, "lu.Rs", sizeof(double) * (size_t)c->sch.n * S);
         b->nodeconv = (int *)dalloc(b, "lu.nodeconv", sizeof(int) * (size_t)S);
@@ -911,7 +1000,10 @@ void ngbBatchDestroy(ngb_batch *b)
     ngb_dev_free(b->b4_nodes); ngb_dev_free(b->b4_spos); ngb_dev_free(b->b4_prow_t);
     ngb_dev_free(b->cap_nodes); ngb_dev_free(b->cap_spos);
     ngb_dev_free(b->vs_fn); ngb_dev_free(b->vs_spos); ngb_dev_free(b->is_fn); ngb_dev_free(b->is_spos);
-    if (b->have_lu) sched_dev_free(&b->dsch);
+    if (b->have_lu) {
+        if (b->dpk.ok) { ngb_dev_free((void *)b->dpk.blob); ngb_dev_free((void *)b->dpk.aslot); ngb_dev_free((void *)b->dpk.arow); ngb_dev_free((void *)b->dpk.ext); }
+        sched_dev_free(&b->dsch);
+    }
     ngb_tran_free(b);
     free(b);
 }
@@ -992,7 +1084,7 @@ void ngb_fill_luctx(ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve)
 {
     const ngb_circuit *c = b->c;
     memset(x, 0, sizeof *x);
-    x->sch = b->dsch; x->S = b->S; x->neq1 = b->neq1; x->Ax = b->Ax; x->V = b->V; x->Rs = b->Rs; x->x = b->x;
+    x->sch = b->dsch; x->pk = b->dpk; x->S = b->S; x->neq1 = b->neq1; x->Ax = b->Ax; x->V = b->V; x->Rs = b->Rs; x->x = b->x;
     x->do_factor = do_factor; x->do_solve = do_solve; x->node_type = b->d_node_type;
     x->reltol = c->opt.reltol; x->abstol = c->opt.abstol; x->vntol = c->opt.vntol;
     x->nodeconv = b->nodeconv; x->singular_col = b->singular; x->ctl = b->ctl;

@@ -29,6 +29,7 @@ struct ngb_circuit {
     int klu_nblocks; int *klu_Q, *klu_R, *klu_Pnum;
     int lnz, unz, nzoff, npairs, nsolvepairs;
     NgbLuSched sch;                /* host arrays */
+    NgbLuPacked pk;                /* host arrays, level-contiguous 16-bit form */
 };
 
 #define NGB_MAX_ARR 64
@@ -45,6 +46,7 @@ struct ngb_batch {
     double *vs_par; int *vs_fn, *vs_spos;
     double *is_par; int *is_fn, *is_spos;
     NgbLuSched dsch;               /* device arrays */
+    NgbLuPacked dpk;
     double *V, *Rs; int *nodeconv, *singular;
     struct { const char *name; void *ptr; size_t bytes; } arr[NGB_MAX_ARR];
     int narr;

@@ -341,4 +341,128 @@ NGB_HD void ngb_lu_sample(const NgbLuCtx *c, int s, int lane, int nl, double *V,
     }
 }
 
+
+/* Packed variant: `sb` is the schedule blob (shared memory on the device), V/Rs/Z group-private.
+ * Same arithmetic, same order; only the bookkeeping differs:
+ *   1. row scale factors, 2. every value initialised to A/Rs in one parallel pass,
+ *   3. levels (contiguous ranges) touch shared memory only. */
+NGB_HD void ngb_lu_sample_packed(const NgbLuCtx *c, const unsigned short *sb, int s, int lane, int nl,
+                                 double *V, double *Rs, double *Z, double *As)
+{
+    const NgbLuPacked *h = &c->pk;
+    const int S = c->S, n = h->n, nV = h->nV;
+    if (!NGB_LDG(&c->ctl.active[s])) return;
+
+    if (c->do_factor) {
+        /* the sample's matrix into shared memory: one coalesced sweep */
+        const double *Ax = c->Ax + (size_t)s * h->nnz;
+        for (int p = lane; p < h->nnz; p += nl) As[p] = Ax[p];
+        if (lane == 0) c->singular_col[s] = -1;
+        NGB_GROUP_SYNC();
+        for (int i = lane; i < n; i += nl) {
+            double r = 0.0;
+            const int lo = sb[h->o_rowptr + i], hi = sb[h->o_rowptr + i + 1];
+            for (int p = lo; p < hi; p++) {
+                double a = fabs(As[sb[h->o_rowslot + p]]);
+                r = (r > a) ? r : a;
+            }
+            if (r == 0.0) r = 1.0;
+            Rs[i] = r;
+        }
+        NGB_GROUP_SYNC();
+        for (int e = lane; e < nV; e += nl) {
+            const int as = sb[h->o_aslot + e];
+            V[e] = (as != 0xFFFF) ? As[as] / Rs[sb[h->o_arow + e]] : 0.0;
+        }
+        NGB_GROUP_SYNC();
+        for (int lev = 0; lev < h->nlev; lev++) {
+            const int lo = sb[h->o_lev_ptr + lev], hi = sb[h->o_lev_ptr + lev + 1];
+            for (int e = lo + lane; e < hi; e += nl) {
+                double v = V[e];
+                const int p0 = sb[h->o_pptr + e], p1 = sb[h->o_pptr + e + 1];
+                for (int p = p0; p < p1; p++) {
+#ifdef __CUDA_ARCH__
+                    v = __dsub_rn(v, __dmul_rn(V[sb[h->o_pl + p]], V[sb[h->o_pu + p]]));
+#else
+                    { volatile double pr = V[sb[h->o_pl + p]] * V[sb[h->o_pu + p]]; v = v - pr; }
+#endif
+                }
+                const int dv = sb[h->o_div + e];
+                if (dv != 0xFFFF) v = v / V[dv];
+                V[e] = v;
+            }
+            NGB_GROUP_SYNC();
+        }
+        for (int k = lane; k < n; k += nl)
+            if (V[sb[h->o_diag + k]] == 0.0) { c->singular_col[s] = k; c->ctl.err[s] = NGB_E_SINGULAR; }
+        if (c->V) {
+            double *Vg = c->V + (size_t)s * nV;
+            for (int e = lane; e < nV; e += nl) Vg[NGB_LDG(&h->ext[e])] = V[e];
+            double *Rg = c->Rs + (size_t)s * n;
+            for (int i = lane; i < n; i += nl) Rg[i] = Rs[i];
+        }
+    } else {
+        const double *Vg = c->V + (size_t)s * nV;
+        for (int e = lane; e < nV; e += nl) V[e] = Vg[NGB_LDG(&h->ext[e])];
+        const double *Rg = c->Rs + (size_t)s * n;
+        for (int i = lane; i < n; i += nl) Rs[i] = Rg[i];
+        NGB_GROUP_SYNC();
+    }
+
+    if (c->do_solve) {
+        const int xs = NGB_LDG(&c->ctl.xsel[s]);
+        double *rhs = c->x + (size_t)(1 - xs) * c->neq1 * S;
+        const double *old = c->x + (size_t)xs * c->neq1 * S;
+        /* y tasks start from b/Rs: fetch all right-hand sides in one parallel pass */
+        for (int tk = lane; tk < h->ntask; tk += nl) {
+            if (sb[h->o_kind + tk] == 0) {
+                const int row = sb[h->o_init + tk];
+                Z[tk] = rhs[(size_t)NGB_LDG(&h->b_eq[row]) * S + s] / Rs[row];
+            }
+        }
+        NGB_GROUP_SYNC();
+        for (int lev = 0; lev < h->nslev; lev++) {
+            const int lo = sb[h->o_slev_ptr + lev], hi = sb[h->o_slev_ptr + lev + 1];
+            for (int tk = lo + lane; tk < hi; tk += nl) {
+                const int kind = sb[h->o_kind + tk];
+                double z = (kind == 0) ? Z[tk] : Z[sb[h->o_init + tk]];
+                const int p0 = sb[h->o_tpptr + tk], p1 = sb[h->o_tpptr + tk + 1];
+                for (int p = p0; p < p1; p++) {
+#ifdef __CUDA_ARCH__
+                    z = __dsub_rn(z, __dmul_rn(V[sb[h->o_tval + p]], Z[sb[h->o_tsrc + p]]));
+#else
+                    { volatile double pr = V[sb[h->o_tval + p]] * Z[sb[h->o_tsrc + p]]; z = z - pr; }
+#endif
+                }
+                if (kind == 1) z = z / V[sb[h->o_tdiv + tk]];
+                Z[tk] = z;
+            }
+            NGB_GROUP_SYNC();
+        }
+        for (int i = lane; i < c->neq1; i += nl) rhs[(size_t)i * S + s] = 0.0;
+        NGB_GROUP_SYNC();
+        for (int k = lane; k < n; k += nl) {
+            const int eq = NGB_LDG(&h->out_eq[k]);
+            if (eq != 0) rhs[(size_t)eq * S + s] = Z[sb[h->o_out + k]];
+        }
+        NGB_GROUP_SYNC();
+        if (c->nodeconv) {
+            int bad = 0;
+            for (int i = 1 + lane; i <= n; i += nl) {
+                const double nw = rhs[(size_t)i * S + s], od = old[(size_t)i * S + s];
+                if (nw != nw) { bad = 1; continue; }
+                const double mx = (fabs(od) > fabs(nw)) ? fabs(od) : fabs(nw);
+                const double tol = c->reltol * mx
+                                 + ((NGB_LDG(&c->node_type[i]) == NGB_SP_VOLTAGE) ? c->vntol : c->abstol);
+                if (fabs(nw - od) > tol) bad = 1;
+            }
+#ifdef __CUDA_ARCH__
+            if (bad) atomicOr(&c->nodeconv[s], 1);
+#else
+            if (bad) c->nodeconv[s] = 1;
+#endif
+        }
+    }
+}
+
 #endif

@@ -118,6 +118,7 @@ static int enqueue_tick(ngb_batch *b, int with_lu)
     if (with_lu) {
         NgbLuCtx lx;
         ngb_fill_luctx(b, &lx, 1, 1);
+        lx.V = NULL;                       /* fused factor+solve: the factors never leave shared memory */
         if ((r = ngb_launch_lu(&lx))) return r;
     }
     return ngb_launch_tran_control(&b->tran->x);

@@ -126,8 +126,24 @@ typedef struct NgbLuSched {
     const int *out_eq;      /* [n] equation number receiving it                          */
 } NgbLuSched;
 
+/* the same schedule renumbered so that every level is a contiguous index range, with all
+ * per-level data as 16-bit indices in one blob that a CTA copies to shared memory once */
+typedef struct NgbLuPacked {
+    int ok;                 /* usable: every index fits 16 bits                           */
+    int n, nnz, nV, nlev, ntask, nslev, npairs, nsp;
+    int blob_u16;           /* length of blob in 16-bit words (even)                      */
+    int o_lev_ptr, o_div, o_pptr, o_pl, o_pu, o_diag;              /* factor, offsets in blob */
+    int o_slev_ptr, o_kind, o_init, o_tdiv, o_tpptr, o_tval, o_tsrc, o_out;   /* solve      */
+    int o_aslot, o_arow, o_rowptr, o_rowslot;   /* A -> value map and CSR of A (0xFFFF = none)   */
+    const unsigned short *blob;
+    const int *aslot, *arow, *ext;      /* [nV] internal order: A slot, original row, external id */
+    const int *row_ptr, *row_slot;      /* CSR view of A                                   */
+    const int *b_eq, *out_eq;           /* [n]                                             */
+} NgbLuPacked;
+
 typedef struct NgbLuCtx {
     NgbLuSched sch;
+    NgbLuPacked pk;
     int S, neq1;
     const double *Ax;       /* [S][nnz]                                                  */
     double *V;              /* [S][nV] LU values (kept for a later solve / parity checks) */

@@ -36,6 +36,31 @@ def bsim4_inst_with_delvto(lib, flat, delvto):
     return out
 
 
+def spice_number(text):
+    """the value the reference front end gives a plain decimal token (digits, '.', e+-NN), which
+    is not always the nearest double: INPevaluate accumulates the digits into a double mantissa
+    and multiplies by pow(10, exponent) (src/spicelib/parser/inpeval.c:65-201)"""
+    import math
+    t = text.strip().lower()
+    sign = 1.0
+    if t[0] in "+-":
+        sign = -1.0 if t[0] == "-" else 1.0
+        t = t[1:]
+    mant, _, ex = t.partition("e")
+    ip, _, fp = mant.partition(".")
+    m = 0.0
+    for ch in ip + fp:
+        m = 10.0 * m + (ord(ch) - 48)
+    e = -len(fp) + (int(ex) if ex else 0)
+    return sign * m * math.pow(10.0, float(e))
+
+
+def delvto_as_parsed(delvto, fmt="{:.17g}"):
+    """delvto draws as the reference sees them after a round trip through netlist text"""
+    flat = np.asarray(delvto, dtype=np.float64)
+    return np.array([spice_number(fmt.format(v)) for v in flat.ravel()]).reshape(flat.shape)
+
+
 def draw_delvto(nsamples, ninst, sigma=0.015, seed=1):
     """per-sample, per-instance Vth mismatch ~ N(0, sigma) (seeded, reproducible on any host)"""
     rng = np.random.default_rng(seed)
