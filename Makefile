@@ -12,10 +12,12 @@ HDRS := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh include/*.h)
 
 all: $(PKG)/libngb200.so
 
-$(PKG)/libngb200.so: $(CSRC)/ngb_cuda.cu $(HOSTC) $(HDRS)
+# the device compile goes through tools/nvcc_outline.py: plain nvcc steps, with the f64 div/rcp/sqrt
+# of the BSIM4 kernel turned into calls of one shared subroutine each (instruction-fetch bound code)
+$(PKG)/libngb200.so: $(CSRC)/ngb_cuda.cu $(HOSTC) $(HDRS) tools/nvcc_outline.py
 	gcc -O2 -fPIC -std=gnu99 -Wall -I$(CSRC) -Iinclude -x c -include $(CSRC)/c_compat.h -c $(CSRC)/ngb_host.c -o $(CSRC)/ngb_host.o
 	gcc -O2 -fPIC -std=gnu99 -Wall -I$(CSRC) -Iinclude -x c -include $(CSRC)/c_compat.h -c $(CSRC)/ngb_tran.c -o $(CSRC)/ngb_tran.o
-	$(NVCC) $(NVFLAGS) -c $(CSRC)/ngb_cuda.cu -o $(CSRC)/ngb_cuda.o 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; false)
+	python3 tools/nvcc_outline.py --outline-entries bsim4 -- $(NVCC) $(NVFLAGS) $(NVDEFS) -c $(CSRC)/ngb_cuda.cu -o $(CSRC)/ngb_cuda.o 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; false)
 	$(NVCC) -shared -o $@ $(CSRC)/ngb_cuda.o $(CSRC)/ngb_host.o $(CSRC)/ngb_tran.o -lcudart
 
 hostsim: tests/hostsim/libngb200_hostsim.so

@@ -113,7 +113,8 @@ __global__ void ngb_k_lu_packed(const NgbLuCtx c, int groups, int tpg, int per_s
     double *Rs = V + h->nV;
     double *Z = Rs + h->n;
     double *As = Z;                 /* the sample's A is dead before the solve starts */
-    ngb_lu_sample_packed(&c, sb, s, lane, tpg, V, Rs, Z, As);
+    double *P = Z + (h->ntask > h->nnz ? h->ntask : h->nnz);
+    ngb_lu_sample_packed(&c, sb, s, lane, tpg, V, Rs, Z, As, P);
 }
 
 __global__ void __launch_bounds__(128)
@@ -272,15 +273,16 @@ int ngb_launch_lu(const NgbLuCtx *c)
     const int per = c->sch.nV + c->sch.n + c->sch.ntask;
     const size_t bytes1 = (size_t)per * sizeof(double);
     if (c->pk.ok) {
-        const int per = c->sch.nV + c->sch.n + (c->sch.ntask > c->sch.nnz ? c->sch.ntask : c->sch.nnz);   /* A aliases the solve vector */
+        const int per = c->sch.nV + c->sch.n + (c->sch.ntask > c->sch.nnz ? c->sch.ntask : c->sch.nnz) + c->pk.maxlp;   /* A aliases the solve vector */
         const size_t bytes1 = (size_t)per * sizeof(double);
-        /* schedule blob + per-sample values in shared memory.  Many samples: one warp each, as many
-         * per CTA as keeps two CTAs resident; few samples: one CTA of 256 threads per sample. */
+        /* schedule blob + per-sample values in shared memory.  Many samples: one warp each, one CTA
+         * per SM holding as many samples as its shared memory takes (the blob is paid once per CTA);
+         * few samples: one CTA of 256 threads per sample. */
         const size_t blob = (size_t)((c->pk.blob_u16 + 3) / 4) * sizeof(double);
-        const size_t budget = (size_t)g_smem_optin / 2 - 2048;
-        if (c->S >= 64 && blob + bytes1 <= budget) {
+        const size_t budget = (size_t)g_smem_optin - 1024;
+        if (c->S >= 64 && blob + 4 * bytes1 <= budget) {
             int groups = (int)((budget - blob) / bytes1);
-            if (groups > 8) groups = 8;
+            if (groups > 16) groups = 16;
             const unsigned grid = (unsigned)((c->S + groups - 1) / groups);
             ngb_k_lu_packed<<<grid, groups * 32, blob + bytes1 * groups, g_stream>>>(*c, groups, 32, per);
             return post_launch("lu_packed");

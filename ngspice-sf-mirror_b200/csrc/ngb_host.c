@@ -585,6 +585,15 @@ static void build_packed(ngb_circuit *c)
     }
     for (k = 0; k <= n; k++) b[p->o_rowptr + k] = (unsigned short)h->row_ptr[k];
     for (k = 0; k < h->nnz; k++) b[p->o_rowslot + k] = (unsigned short)h->row_slot[k];
+    p->maxlp = 1;
+    for (k = 0; k < h->nlev; k++) {
+        const int np_lev = b[p->o_pptr + h->lev_ptr[k + 1]] - b[p->o_pptr + h->lev_ptr[k]];
+        if (np_lev > p->maxlp) p->maxlp = np_lev;
+    }
+    for (k = 0; k < h->nslev; k++) {
+        const int np_lev = b[p->o_tpptr + h->slev_ptr[k + 1]] - b[p->o_tpptr + h->slev_ptr[k]];
+        if (np_lev > p->maxlp) p->maxlp = np_lev;
+    }
     p->blob = b; p->aslot = aslot; p->arow = arow; p->ext = ext;
     p->row_ptr = h->row_ptr; p->row_slot = h->row_slot; p->b_eq = h->b_eq; p->out_eq = h->out_eq;
     p->ok = 1;

@@ -346,8 +346,11 @@ NGB_HD void ngb_lu_sample(const NgbLuCtx *c, int s, int lane, int nl, double *V,
  * Same arithmetic, same order; only the bookkeeping differs:
  *   1. row scale factors, 2. every value initialised to A/Rs in one parallel pass,
  *   3. levels (contiguous ranges) touch shared memory only. */
+/* Each level runs in two phases: the products l*u of ALL its pairs, spread evenly over the lanes
+ * (P), then per entry the subtractions in KLU's order.  The long rows (a supply node touches every
+ * stage) would otherwise keep one lane busy with index loads and multiplies while 31 wait. */
 NGB_HD void ngb_lu_sample_packed(const NgbLuCtx *c, const unsigned short *sb, int s, int lane, int nl,
-                                 double *V, double *Rs, double *Z, double *As)
+                                 double *V, double *Rs, double *Z, double *As, double *P)
 {
     const NgbLuPacked *h = &c->pk;
     const int S = c->S, n = h->n, nV = h->nV;
@@ -377,14 +380,25 @@ NGB_HD void ngb_lu_sample_packed(const NgbLuCtx *c, const unsigned short *sb, in
         NGB_GROUP_SYNC();
         for (int lev = 0; lev < h->nlev; lev++) {
             const int lo = sb[h->o_lev_ptr + lev], hi = sb[h->o_lev_ptr + lev + 1];
+            const int pbase = sb[h->o_pptr + lo], pend = sb[h->o_pptr + hi];
+            if (pend > pbase) {
+                for (int p = pbase + lane; p < pend; p += nl) {
+#ifdef __CUDA_ARCH__
+                    P[p - pbase] = __dmul_rn(V[sb[h->o_pl + p]], V[sb[h->o_pu + p]]);
+#else
+                    { volatile double pr = V[sb[h->o_pl + p]] * V[sb[h->o_pu + p]]; P[p - pbase] = pr; }
+#endif
+                }
+                NGB_GROUP_SYNC();
+            }
             for (int e = lo + lane; e < hi; e += nl) {
                 double v = V[e];
                 const int p0 = sb[h->o_pptr + e], p1 = sb[h->o_pptr + e + 1];
                 for (int p = p0; p < p1; p++) {
 #ifdef __CUDA_ARCH__
-                    v = __dsub_rn(v, __dmul_rn(V[sb[h->o_pl + p]], V[sb[h->o_pu + p]]));
+                    v = __dsub_rn(v, P[p - pbase]);
 #else
-                    { volatile double pr = V[sb[h->o_pl + p]] * V[sb[h->o_pu + p]]; v = v - pr; }
+                    v = v - P[p - pbase];
 #endif
                 }
                 const int dv = sb[h->o_div + e];
@@ -423,15 +437,26 @@ NGB_HD void ngb_lu_sample_packed(const NgbLuCtx *c, const unsigned short *sb, in
         NGB_GROUP_SYNC();
         for (int lev = 0; lev < h->nslev; lev++) {
             const int lo = sb[h->o_slev_ptr + lev], hi = sb[h->o_slev_ptr + lev + 1];
+            const int pbase = sb[h->o_tpptr + lo], pend = sb[h->o_tpptr + hi];
+            if (pend > pbase) {
+                for (int p = pbase + lane; p < pend; p += nl) {
+#ifdef __CUDA_ARCH__
+                    P[p - pbase] = __dmul_rn(V[sb[h->o_tval + p]], Z[sb[h->o_tsrc + p]]);
+#else
+                    { volatile double pr = V[sb[h->o_tval + p]] * Z[sb[h->o_tsrc + p]]; P[p - pbase] = pr; }
+#endif
+                }
+                NGB_GROUP_SYNC();
+            }
             for (int tk = lo + lane; tk < hi; tk += nl) {
                 const int kind = sb[h->o_kind + tk];
                 double z = (kind == 0) ? Z[tk] : Z[sb[h->o_init + tk]];
                 const int p0 = sb[h->o_tpptr + tk], p1 = sb[h->o_tpptr + tk + 1];
                 for (int p = p0; p < p1; p++) {
 #ifdef __CUDA_ARCH__
-                    z = __dsub_rn(z, __dmul_rn(V[sb[h->o_tval + p]], Z[sb[h->o_tsrc + p]]));
+                    z = __dsub_rn(z, P[p - pbase]);
 #else
-                    { volatile double pr = V[sb[h->o_tval + p]] * Z[sb[h->o_tsrc + p]]; z = z - pr; }
+                    z = z - P[p - pbase];
 #endif
                 }
                 if (kind == 1) z = z / V[sb[h->o_tdiv + tk]];

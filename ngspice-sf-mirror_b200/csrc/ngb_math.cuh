@@ -24,6 +24,16 @@
 #define NGB_TABLE static const
 #endif
 
+/* On the device exp/log are real (out-of-line) functions: the BSIM4 evaluation is bound by
+ * instruction fetch (18k straight-line instructions per evaluation, far beyond the instruction
+ * caches), and ~70 inlined copies of these bodies would be streamed from L2 by every warp; one
+ * shared copy stays cache-resident. */
+#ifdef __CUDACC__
+#define NGB_MATH_FN __device__ __noinline__
+#else
+#define NGB_MATH_FN static inline
+#endif
+
 /* 2^(i/128) as (tail, scale-bits) pairs */
 NGB_TABLE unsigned long long ngb_exp_tab[256] = {
     0x0000000000000000ULL, 0x3ff0000000000000ULL, 0x3c9b3b4f1a88bf6eULL, 0x3feff63da9fb3335ULL,
@@ -181,7 +191,7 @@ NGB_HD unsigned long long ngb_d2bits(double f)
 #define NGB_TAB(t, i) ((t)[i])
 #endif
 
-NGB_HD double ngb_exp(double x)
+NGB_MATH_FN double ngb_exp(double x)
 {
     const double InvLn2N = 0x1.71547652b82fep+7, Shift = 0x1.8000000000000p+52;
     const double NegLn2hiN = -0x1.62e42fefa0000p-8, NegLn2loN = -0x1.cf79abc9e3b3ap-47;
@@ -206,7 +216,7 @@ NGB_HD double ngb_exp(double x)
     return fma(scale, tmp, scale);
 }
 
-NGB_HD double ngb_log(double x)
+NGB_MATH_FN double ngb_log(double x)
 {
     const double Ln2hi = 0x1.62e42fefa3800p-1, Ln2lo = 0x1.ef35793c76730p-45;
     const double A0 = -0x1.0000000000001p-1, A1 = 0x1.555555551305bp-2, A2 = -0x1.fffffffeb4590p-3, A3 = 0x1.999b324f10111p-3, A4 = -0x1.55575e506c89fp-3;

@@ -134,6 +134,7 @@ typedef struct NgbLuPacked {
     int blob_u16;           /* length of blob in 16-bit words (even)                      */
     int o_lev_ptr, o_div, o_pptr, o_pl, o_pu, o_diag;              /* factor, offsets in blob */
     int o_slev_ptr, o_kind, o_init, o_tdiv, o_tpptr, o_tval, o_tsrc, o_out;   /* solve      */
+    int maxlp;                                  /* most pairs any one factor/solve level has     */
     int o_aslot, o_arow, o_rowptr, o_rowslot;   /* A -> value map and CSR of A (0xFFFF = none)   */
     const unsigned short *blob;
     const int *aslot, *arow, *ext;      /* [nV] internal order: A slot, original row, external id */
