@@ -52,6 +52,25 @@ class ClockSampler:
         self.th = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
+        """NVML in-process (one cheap query per 0.5 s); spawning nvidia-smi every 200 ms was measured to
+        slow the timed region by ~10 %, so the subprocess form is only the fallback, at 2 s intervals"""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.dev)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            bits = [("hw_slowdown", pynvml.nvmlClocksThrottleReasonHwSlowdown),
+                    ("hw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonSwThermalSlowdown),
+                    ("sw_power_cap", pynvml.nvmlClocksThrottleReasonSwPowerCap)]
+            while not self.stop:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if (r & b) else "Not Active" for _, b in bits])
+                time.sleep(0.5)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop:
@@ -62,7 +81,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(2.0)
 
     def __enter__(self):
         self.th.start(); return self
@@ -77,6 +96,16 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons}
+
+
+def traffic_from_profiles(units):
+    """DRAM bytes per ngb_k_bsim4_load launch from the committed `ncu --set full` capture
+    (profiles/r01_traffic.json), scaled to this run's evaluations per launch"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["ngb_k_bsim4_load"]
+        return (d["dram_bytes_read"] + d["dram_bytes_write"]) * units / d["units_per_launch"]
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------ reference CPU arm
@@ -305,7 +334,7 @@ def bench_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak if hbm_peak else None, "traffic": None,
+                         "frac": achieved / hbm_peak if hbm_peak else None, "traffic": traffic_from_profiles(units),
                          "kernel": "ngb_k_bsim4_load", "avg_launch_ms": k_ms, "timed_launches": prof[1],
                          "units_per_launch": units, "bytes_per_unit": B4_BYTES_PER_EVAL, "peak_source": which,
                          "fp64_tflops_algorithmic": units * B4_FLOP_PER_EVAL / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0,
