@@ -30,7 +30,7 @@ void ngb_tran_free(struct ngb_batch *b)
     ngb_dev_free(t->x.npts); ngb_dev_free(t->x.brkflag); ngb_dev_free(t->x.accepted); ngb_dev_free(t->x.rejected);
     ngb_dev_free(t->x.numiter); ngb_dev_free(t->x.timepts); ngb_dev_free(t->x.save_delta); ngb_dev_free(t->x.old_delta);
     ngb_dev_free(t->x.breaks); ngb_dev_free(t->x.out_time); ngb_dev_free(t->x.out_val); ngb_dev_free(t->x.ndone);
-    ngb_dev_free(t->d_save_eq);
+    ngb_dev_free(t->d_save_eq); ngb_dev_free(t->x.isrc_break); ngb_dev_free(t->x.vsrc_break);
     free(t);
     b->tran = NULL;
 }
@@ -58,6 +58,11 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     x->out_time = (double *)dz(sizeof(double) * (size_t)S * max_points);
     x->out_val = (double *)dz(sizeof(double) * (size_t)S * max_points * (nsave ? nsave : 1));
     x->ndone = (int *)dz(sizeof(int) * 2);
+    ngb_fill_srcctx(b, &x->isrc, 1); ngb_fill_srcctx(b, &x->vsrc, 0);
+    x->isrc_break = (double *)dz(sizeof(double) * (size_t)(x->isrc.ninst > 0 ? x->isrc.ninst : 1) * S);
+    x->vsrc_break = (double *)dz(sizeof(double) * (size_t)(x->vsrc.ninst > 0 ? x->vsrc.ninst : 1) * S);
+    ngb_launch_fill_f64(x->isrc_break, -1.0, (x->isrc.ninst > 0 ? x->isrc.ninst : 1) * S);
+    ngb_launch_fill_f64(x->vsrc_break, -1.0, (x->vsrc.ninst > 0 ? x->vsrc.ninst : 1) * S);
     t->d_save_eq = (int *)dz(sizeof(int) * (nsave ? nsave : 1));
     if (!x->out_val || !x->out_time || !x->breaks) { ngb_set_error("transient buffers: out of device memory"); return NGB_E_PANIC; }
     if (nsave) ngb_dev_h2d(t->d_save_eq, save_eq, sizeof(int) * (size_t)nsave);

@@ -43,6 +43,10 @@ typedef struct NgbTranCtx {
     double *out_time;          /* [S][max_points] */
     double *out_val;           /* [S][max_points][nsave] */
     int *ndone;                /* [1] samples in DONE or FAIL */
+    /* breakpoint-generating sources (VSRCaccept / ISRCaccept): tables of the load kernels plus the
+     * per-sample VSRCbreak_time / ISRCbreak_time, [ninst][S], -1 at setup (vsrcset.c:34) */
+    NgbSrcCtx isrc, vsrc;
+    double *isrc_break, *vsrc_break;
     /* circuit scalars */
     double tstep, tstop, tmax, tstart, delmin, minbreak, xmu;
     int maxorder, uic, max_iter_tran, max_iter_dc;
@@ -142,6 +146,46 @@ NGB_HD void ngb_finish(const NgbTranCtx *c, int s, int phase, int err)
 #endif
 }
 
+/* VSRCaccept / ISRCaccept (vsrc/vsrcacct.c:22-152, isrc/isrcacct.c): PULSE sources ask for a
+ * breakpoint at their next corner; DC, SIN, EXP, SFFM, AM never do */
+NGB_HD int ngb_src_accept(const NgbTranCtx *c, const NgbSrcCtx *sc, double *brk, int poff, int s, double now)
+{
+    const int S = c->S;
+    for (int inst = 0; inst < sc->ninst; inst++) {
+        const int ftype = NGB_LDG(&sc->fn[inst]);
+        const int forder = NGB_LDG(&sc->fn[sc->ninst + inst]);
+        const size_t t = (size_t)inst * S + s;
+#define SCO(k) NGB_LDG(&sc->par[(size_t)(poff + (k)) * sc->T + t])
+        if (ftype == NGB_FN_PULSE) {
+            const double TD = forder > 2 ? SCO(2) : 0.0;
+            const double TR = (forder > 3 && SCO(3) > 0.0) ? SCO(3) : c->tstep;
+            const double TF = (forder > 4 && SCO(4) > 0.0) ? SCO(4) : c->tstep;
+            const double PW = (forder > 5 && SCO(5) >= 0.0) ? SCO(5) : 0.0;
+            const double PER = (forder > 6 && SCO(6) > 0.0) ? SCO(6) : TR + TF + PW;
+            const double PHASE = forder > 7 ? SCO(7) : 0.0;
+            double time = now - TD;
+            if (PHASE > 0.0 && time > PHASE * PER) continue;
+            if (now >= brk[t]) {
+                double wait, atime;
+                if (time >= PER) time -= PER * floor(time / PER);
+                atime = time + c->minbreak;
+                if (atime < 0.0) wait = -time;
+                else if (atime < TR) wait = TR - time;
+                else if (atime < TR + PW) wait = TR + PW - time;
+                else if (atime < TR + PW + TF) wait = TR + PW + TF - time;
+                else wait = PER - time;
+                brk[t] = now + wait;
+                { const int e = ngb_set_break(c, s, brk[t], now); if (e) return e; }
+                brk[t] -= c->minbreak;
+            }
+        } else if (ftype != 0 && ftype != NGB_FN_SINE) {
+            return NGB_E_UNSUPP;
+        }
+#undef SCO
+    }
+    return NGB_OK;
+}
+
 /* the nextTime: label of dctran.c:355-665 -- accept the point, output, breakpoints, rotate */
 NGB_HD void ngb_next_time(const NgbTranCtx *c, int s)
 {
@@ -149,7 +193,12 @@ NGB_HD void ngb_next_time(const NgbTranCtx *c, int s)
     const double time = c->ctl.time[s];
     const int mode = c->ctl.mode[s];
     double delta;
-    /* CKTaccept: no breakpoint-generating sources on this path (DC / SIN) */
+    /* CKTaccept: device types in DEVices order, isrc before vsrc (dev.c:142-209) */
+    {
+        int e = ngb_src_accept(c, &c->isrc, c->isrc_break, 2, s, time);
+        if (!e) e = ngb_src_accept(c, &c->vsrc, c->vsrc_break, 1, s, time);
+        if (e) { ngb_finish(c, s, NGB_PH_FAIL, e); return; }
+    }
     if (time > TBRK(0)) ngb_clr_break(c, s);
     c->accepted[s] += 1;
     c->brkflag[s] = 0;

@@ -58,6 +58,28 @@ def ro_netlist(stages, tran=".tran .1ns 150ns uic", extra_opts="", kick=False, d
     return "\n".join(lines) + "\n" + ro_cards() + "\n.end\n"
 
 
+def qa_card(kind):
+    """model card of the reference's BSIM4 QA suite (tests/bsim4/<kind>/parameters), selected the way
+    its qaSpec does for ngspice: level=14 version=4.8.1"""
+    body = open(os.path.join(REF, f"tests/bsim4/{kind}/parameters/{kind}Parameters")).read()
+    return f".model {kind[0]}inv {kind} level=14 version=4.8.1\n" + body
+
+
+def inv_netlist():
+    """BASELINE config 1: CMOS inverter, QA-suite cards, PULSE input, 10 fF load, DC operating
+    point followed by `.tran 10p 10n`"""
+    return "\n".join([
+        "* CMOS inverter on the tests/bsim4 QA model cards",
+        "vdd vdd 0 1.2",
+        "vin in 0 pulse(0 1.2 0 50p 50p 1n 2n)",
+        "mp out in vdd vdd pinv w=10e-6 l=0.06e-6",
+        "mn out in 0 0 ninv w=10e-6 l=0.06e-6",
+        "cl out 0 10f",
+        ".option klu",
+        ".tran 10p 10n",
+        qa_card("nmos"), qa_card("pmos"), ".end", ""])
+
+
 def read_raw(path):
     data = open(path, "rb").read()
     i = data.index(b"Binary:\n")
@@ -78,7 +100,7 @@ def run(name, netlist, calls, save):
     os.makedirs(TMP, exist_ok=True)
     cir = os.path.join(TMP, name + ".cir")
     open(cir, "w").write(netlist)
-    if name in ("ro17", "ro101", "ro17k"):
+    if name in ("ro17", "ro101", "ro17k", "inv"):
         # the netlist itself is kept too: the CPU-baseline arm of bench.py feeds it to oracle/_ref/ngspice
         os.makedirs(os.path.join(HERE, "netlists"), exist_ok=True)
         open(os.path.join(HERE, "netlists", name + ".cir"), "w").write(netlist)
@@ -131,5 +153,7 @@ if __name__ == "__main__":
         np.save(os.path.join(HERE, "ro17mc.delvto.npy"), dv)
         for i in range(4):
             run(f"ro17mc{i}", ro_netlist(17, tran=".tran .1ns 20ns uic", kick=True, delvto=dv[i]), "1", ["18", "2", "9", "vdd#branch"])
+    if "inv" in which:
+        run("inv", inv_netlist(), "0-40,100,101,300,301", ["out", "in", "vdd#branch", "vin#branch"])
     if "ro101" in which:
         run("ro101", ro_netlist(101), "1,2,3000", ["102", "2", "50", "vdd#branch"])
