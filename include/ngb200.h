@@ -46,9 +46,11 @@ int ngbProfileRead(double *ms_sum, long *count);
 
 /* field-list sizes, so callers can check they were built against the same lists
  * (bsim4_fields.h): [0]=model [1]=bin [2]=instance [3]=node roles [4]=matrix stamps
- * [5]=matrix+rhs stamps [6]=states [7]=op-point fields */
+ * [5]=matrix+rhs stamps [6]=states [7]=op-point fields; list 8 of ngbBsim4FieldName is the diode
+ * parameter list of dio_fields.h (ngbDioLayout: [0]=parameters [1]=states [2]=stamp rows) */
 void ngbBsim4Layout(int out[8]);
 const char *ngbBsim4FieldName(int list, int index);
+void ngbDioLayout(int out[3]);
 
 /* ---- circuit description: what DEVsetup/DEVtemperature/DEVbindCSC leave behind ---- */
 ngb_circuit *ngbCircuitCreate(int neq, const int *node_type /* [neq+1], 3=voltage 4=current */);
@@ -70,6 +72,12 @@ int ngbCircuitSetExactOrder(ngb_circuit *c, int on);
 int ngbCircuitAddResistors(ngb_circuit *c, int n, const int *nodes /* [2][n] */, const double *g);
 int ngbCircuitAddCapacitors(ngb_circuit *c, int n, const int *nodes /* [2][n] */,
                             const double *par /* [3][n] C, m, ic */);
+/* junction diodes after DIOsetup/DIOtemp (dio/diosetup.c, diotemp.c): nodes [3][n] pos neg posPrime
+ * (posPrime == pos without series resistance), flags [n] DIOF_* and par [DIOP_COUNT][n] as listed
+ * in csrc/dio_fields.h -- replaces the DIOinstance/DIOmodel walk of DIOload (dio/dioload.c:75-80).
+ * Options outside this path (separate sidewall diode, self-heating, soft reverse recovery,
+ * recombination current) return E_UNSUPP */
+int ngbCircuitAddDiodes(ngb_circuit *c, int n, const int *nodes, const int *flags, const double *par);
 int ngbCircuitAddVsources(ngb_circuit *c, int n, const int *nodes /* [3][n] pos neg branch */,
                           const int *fn /* [3][n] type order dcGiven */, const double *par /* [9][n] */);
 int ngbCircuitAddIsources(ngb_circuit *c, int n, const int *nodes /* [2][n] */,
@@ -105,6 +113,7 @@ void ngbBatchDestroy(ngb_batch *b);
  *   x            f64 [2][neq+1][S]      Ax  f64 [S][nnz]      stamp f64 [rows][S]
  *   b4.inst      f64 [NI][ninst*S]      b4.state f64 [4][29][ninst*S]   b4.op f64 [NO][ninst*S]
  *   b4.prow      int [ninst*S]          cap.state f64 [4][2][ncap*S]    cap.par f64 [3][ncap*S]
+ *   dio.par      f64 [NP][nd*S]         dio.state f64 [4][22][nd*S]
  *   vsrc.par     f64 [9][nv*S]          lu.V f64 [S][nV]    lu.Rs f64 [S][n]
  *   lu.nodeconv  int [S]                lu.singular int [S] */
 long ngbBatchArrayBytes(ngb_batch *b, const char *name);

@@ -68,6 +68,10 @@ class Library:
         for li, key in ((0, "model"), (1, "bin"), (2, "inst"), (3, "node"), (5, "stamp"), (7, "op")):
             n = self.layout[li]
             self.fields[key] = [L.ngbBsim4FieldName(li, i).decode() for i in range(n)]
+        dl = (ctypes.c_int * 3)()
+        L.ngbDioLayout(dl)
+        self.dio_layout = list(dl)                       # parameters, states, stamp rows
+        self.fields["dio"] = [L.ngbBsim4FieldName(8, i).decode() for i in range(dl[0])]
 
     @property
     def backend(self):
@@ -147,6 +151,12 @@ class Circuit:
         if n:
             lib.check(lib.L.ngbCircuitAddCapacitors(c.h, int(n), _ip(_i32(flat["cap/nodes"])), _dp(_f64(flat["cap/par"]))),
                       "ngbCircuitAddCapacitors")
+        n = sc(flat, "dio/n", 0)
+        if n:
+            par = _f64(flat["dio/par"])
+            assert par.shape[0] == lib.dio_layout[0], "fixture built against a different diode field list"
+            lib.check(lib.L.ngbCircuitAddDiodes(c.h, int(n), _ip(_i32(flat["dio/nodes"][[0, 1, 3]])), _ip(_i32(flat["dio/flags"])),
+                                                _dp(par)), "ngbCircuitAddDiodes")
         n = sc(flat, "vsrc/n", 0)
         if n:
             lib.check(lib.L.ngbCircuitAddVsources(c.h, int(n), _ip(_i32(flat["vsrc/nodes"])), _ip(_i32(flat["vsrc/fn"])),

@@ -1,0 +1,319 @@
+/* dio_eval.cuh -- junction diode load, one thread per (instance, sample).
+ *
+ * Follows DIOload (src/spicelib/devices/dio/dioload.c:17-865) for the configuration without a
+ * separate sidewall diode, self-heating, soft reverse recovery and recombination current (those
+ * are refused at upload, dio_fields.h): initial-voltage selection :139-221, pnjlim with the
+ * breakdown mirror :296-329, bottom / sidewall / tunnel currents with high-injection knees
+ * :360-522, depletion + diffusion + overlap charge :530-604, NIintegrate :667-680, convergence
+ * flag :713-726, state stores :727-742 and the stamps :757-790.  DIOtrunc (diotrunc.c:22-29) is
+ * folded in: the LTE bound of the junction charge is reduced into ctl.lte.
+ */
+#ifndef NGB_DIO_EVAL_CUH
+#define NGB_DIO_EVAL_CUH
+#include "ngb_types.h"
+#include "dio_fields.h"
+#include "devsup.cuh"
+
+typedef struct NgbDioCtx {
+    int ninst, S, T;
+    const int *nodes;       /* [3][ninst] pos, neg, posPrime                          */
+    const int *flags;       /* [ninst] DIOF_*                                          */
+    const double *par;      /* [DIOP_COUNT][T]                                         */
+    const int *spos;        /* [DIOS_COUNT][ninst] stamp rows, -1 = ground             */
+    double *state;          /* [nhist][DIOST_COUNT][T]                                 */
+    double *stamp;
+    const double *x; int neq1;
+    double reltol, abstol, vntol, chgtol, trtol;
+    NgbCtl ctl;
+} NgbDioCtx;
+
+#define NGB_CONSTKoverQ (1.38064852e-23 / 1.6021766208e-19)   /* CONSTboltz / CHARGE (const.h:32,37; main.c:492) */
+#define NGB_CONSTe 2.7182818284590452354                      /* CONSTnap (const.h) */
+
+NGB_HD int ngb_dio_thread(const NgbDioCtx *c, size_t t)
+{
+    const int S = c->S;
+    const int inst = (int)(t / (size_t)S);
+    const int s = (int)(t - (size_t)inst * S);
+    if (!NGB_LDG(&c->ctl.active[s])) return NGB_OK;
+    const int mode = NGB_LDG(&c->ctl.mode[s]);
+    const int head = NGB_LDG(&c->ctl.head[s]);
+    const int fl = NGB_LDG(&c->flags[inst]);
+    const int nh = c->ctl.nhist;
+#define P(n) NGB_LDG(&c->par[(size_t)DIOP_##n * c->T + t])
+#define ST(h, k) c->state[((size_t)(((head) + (h)) % nh) * DIOST_COUNT + (k)) * c->T + t]
+    {   /* deferred whole-vector state copies of DCtran (dctran.c:319-322, 711-716) */
+        const int sop = NGB_LDG(&c->ctl.stateop[s]);
+        if (sop) {
+            for (int k = 0; k < DIOST_COUNT; k++) {
+                if (sop & NGB_OP_COPY01) ST(1, k) = ST(0, k);
+                if (sop & NGB_OP_COPY1_23) { const double v = ST(1, k); ST(2, k) = v; if (nh > 3) ST(3, k) = v; }
+                if ((sop & NGB_OP_COPY23) && nh > 3) ST(3, k) = ST(2, k);
+            }
+        }
+    }
+    const double gmin = NGB_LDG(&c->ctl.gmin[s]);
+    const double Temp = P(temp);
+    const double vt = NGB_CONSTKoverQ * Temp;
+    const double vte = P(emissionCoeff) * vt;
+    const double vtesw = P(swEmissionCoeff) * vt;
+    const double vtebrk = P(brkdEmissionCoeff) * vt;
+    const double gspr = P(tConductance);
+    const double tBV = P(tBrkdwnV);
+    double vd, cd, gd, cdb, gdb, cdb_dT, cdsw = 0.0, gdsw = 0.0, cdsw_dT = 0.0, dIdio_dT;
+    double cdres, gdres;
+    int Check = 1;
+
+    if (mode & NGB_MODEINITSMSIG) {
+        vd = ST(0, DIOST_voltage);
+    } else if (mode & NGB_MODEINITTRAN) {
+        vd = ST(1, DIOST_voltage);
+    } else if ((mode & NGB_MODEINITJCT) && (mode & NGB_MODETRANOP) && (mode & NGB_MODEUIC)) {
+        vd = P(initCond);
+    } else if ((mode & NGB_MODEINITJCT) && (fl & DIOF_OFF)) {
+        vd = 0.0;
+    } else if (mode & NGB_MODEINITJCT) {
+        vd = P(tVcrit);
+    } else if ((mode & NGB_MODEINITFIX) && (fl & DIOF_OFF)) {
+        vd = 0.0;
+    } else {
+        if (mode & NGB_MODEINITPRED) {
+            /* DEVpred (devsup.c): extrapolation from the two previous points */
+            const double d0 = NGB_LDG(&c->ctl.delta[s]), d1 = NGB_LDG(&c->ctl.delta_old[(size_t)1 * S + s]);
+            const double xfact = d0 / d1;
+            ST(0, DIOST_voltage) = ST(1, DIOST_voltage);
+            vd = (1 + xfact) * ST(1, DIOST_voltage) - xfact * ST(2, DIOST_voltage);
+            ST(0, DIOST_current) = ST(1, DIOST_current);
+            ST(0, DIOST_conduct) = ST(1, DIOST_conduct);
+            ST(0, DIOST_deltemp) = ST(1, DIOST_deltemp);
+            ST(0, DIOST_dIdio_dT) = ST(1, DIOST_dIdio_dT);
+            ST(0, DIOST_qth) = ST(1, DIOST_qth);
+            ST(0, DIOST_resCurrent) = ST(1, DIOST_resCurrent);
+            ST(0, DIOST_resConduct) = ST(1, DIOST_resConduct);
+            ST(0, DIOST_cqcsr) = ST(1, DIOST_cqcsr);
+            ST(0, DIOST_gqcsr) = ST(1, DIOST_gqcsr);
+        } else {
+            const double *xo = c->x + (size_t)NGB_LDG(&c->ctl.xsel[s]) * c->neq1 * S;
+            vd = NGB_LDG(&xo[(size_t)NGB_LDG(&c->nodes[2 * c->ninst + inst]) * S + s])
+               - NGB_LDG(&xo[(size_t)NGB_LDG(&c->nodes[c->ninst + inst]) * S + s]);
+            ST(0, DIOST_qth) = 0.0;                        /* cth0 * delTemp, no self-heating */
+            if (mode & NGB_MODEINITTRAN) ST(1, DIOST_qth) = 0.0;
+        }
+        /* limit the new junction voltage */
+        {
+            const double lim = -tBV + 10 * vtebrk;
+            if ((fl & DIOF_BV) && vd < NGB_MIN(0.0, lim)) {
+                double vdtemp = -(vd + tBV);
+                vdtemp = ngb_pnjlim(vdtemp, -(ST(0, DIOST_voltage) + tBV), vtebrk, P(tVcrit), &Check);
+                vd = -(vdtemp + tBV);
+            } else {
+                vd = ngb_pnjlim(vd, ST(0, DIOST_voltage), vte, P(tVcrit), &Check);
+            }
+        }
+    }
+
+    /* dc current and derivatives */
+    {
+        const double csat = P(tSatCur), csat_dT = P(tSatCur_dT);
+        const double csatsw = P(tSatSWCur), csatsw_dT = P(tSatSWCur_dT);
+        if ((fl & DIOF_SATSW) && (fl & DIOF_NSW)) {           /* sidewall with its own characteristic */
+            const double vds = vd;
+            if (vds >= -3 * vtesw) {
+                const double evd = ngb_exp(vds / vtesw);
+                cdsw = csatsw * (evd - 1);
+                gdsw = csatsw * evd / vtesw;
+                cdsw_dT = csatsw_dT * (evd - 1) - csatsw * vds * evd / (vtesw * Temp);
+            } else if (!(fl & DIOF_BV) || vds >= -tBV) {
+                double argsw = 3 * vtesw / (vds * NGB_CONSTe), argsw_dT;
+                argsw = argsw * argsw * argsw;
+                argsw_dT = 3 * argsw / Temp;
+                cdsw = -csatsw * (1 + argsw);
+                gdsw = csatsw * 3 * argsw / vds;
+                cdsw_dT = -csatsw_dT - (csatsw_dT * argsw + csatsw * argsw_dT);
+            } else {
+                const double evrev = ngb_exp(-(tBV + vds) / vtebrk);
+                const double evrev_dT = (tBV + vds) * evrev / (vtebrk * Temp);
+                cdsw = -csatsw * evrev;
+                gdsw = csatsw * evrev / vtebrk;
+                cdsw_dT = -(csatsw_dT * evrev + csatsw * evrev_dT);
+            }
+        }
+        if (vd >= -3 * vte) {
+            const double evd = ngb_exp(vd / vte);
+            cdb = csat * (evd - 1);
+            gdb = csat * evd / vte;
+            cdb_dT = csat_dT * (evd - 1) - csat * vd * evd / (vte * Temp);
+            if ((fl & DIOF_SATSW) && !(fl & DIOF_NSW)) {
+                cdsw = csatsw * (evd - 1);
+                gdsw = csatsw * evd / vte;
+                cdsw_dT = csatsw_dT * (evd - 1) - csatsw * vd * evd / (vte * Temp);
+            }
+        } else if (!(fl & DIOF_BV) || vd >= -tBV) {
+            double arg = 3 * vte / (vd * NGB_CONSTe), darg_dT;
+            arg = arg * arg * arg;
+            darg_dT = 3 * arg / Temp;
+            cdb = -csat * (1 + arg);
+            gdb = csat * 3 * arg / vd;
+            cdb_dT = -csat_dT - (csat_dT * arg + csat * darg_dT);
+            if ((fl & DIOF_SATSW) && !(fl & DIOF_NSW)) {
+                cdsw = -csatsw * (1 + arg);
+                gdsw = csatsw * 3 * arg / vd;
+                cdsw_dT = -csatsw_dT - (csatsw_dT * arg + csatsw * darg_dT);
+            }
+        } else {
+            double evrev = ngb_exp(-(tBV + vd) / vtebrk);
+            double evrev_dT = (tBV + vd) * evrev / (vtebrk * Temp);
+            cdb = -csat * evrev;
+            gdb = csat * evrev / vtebrk;
+            cdb_dT = -(csat_dT * evrev + csat * evrev_dT);
+            if ((fl & DIOF_SATSW) && !(fl & DIOF_NSW)) {
+                /* vdsw is 0 without a separate sidewall diode (dioload.c:56, 459) */
+                evrev = ngb_exp(-(tBV + 0.0) / vtebrk);
+                evrev_dT = (tBV + 0.0) * evrev / (vtebrk * Temp);
+                cdsw = -csatsw * evrev;
+                gdsw = csatsw * evrev / vtebrk;
+                cdsw_dT = -(csatsw_dT * evrev + csatsw * evrev_dT);
+            }
+        }
+        if (fl & DIOF_TUNSW) {
+            const double vtetun = P(tunEmissionCoeff) * vt;
+            const double evd = ngb_exp(-vd / vtetun);
+            const double is = P(tTunSatSWCur);
+            cdsw = cdsw - is * (evd - 1);
+            gdsw = gdsw + is * evd / vtetun;
+            cdsw_dT = cdsw_dT - P(tTunSatSWCur_dT) * (evd - 1) - is * vd * evd / (vtetun * Temp);
+        }
+        if (fl & DIOF_TUN) {
+            const double vtetun = P(tunEmissionCoeff) * vt;
+            const double evd = ngb_exp(-vd / vtetun);
+            const double is = P(tTunSatCur);
+            cdb = cdb - is * (evd - 1);
+            gdb = gdb + is * evd / vtetun;
+            cdb_dT = cdb_dT - P(tTunSatCur_dT) * (evd - 1) - is * vd * evd / (vtetun * Temp);
+        }
+        if (vd >= -3 * vte) {
+            if ((fl & DIOF_IKF) && cdb > 1.0e-18) {
+                const double ik = P(forwardKneeCurrent);
+                const double sq = sqrt(cdb / ik);
+                gdb = ((1 + sq) * gdb - cdb * gdb / (2 * sq * ik)) / (1 + 2 * sq + cdb / ik);
+                cdb = cdb / (1 + sq);
+            }
+        } else {
+            if ((fl & DIOF_IKR) && cdb < -1.0e-18) {
+                const double ik = P(reverseKneeCurrent);
+                const double sq = sqrt(cdb / (-ik));
+                gdb = ((1 + sq) * gdb + cdb * gdb / (2 * sq * ik)) / (1 + 2 * sq - cdb / ik);
+                cdb = cdb / (1 + sq);
+            }
+        }
+        if ((fl & DIOF_IKP) && cdsw > 1.0e-18) {
+            const double ik = P(forwardSWKneeCurrent);
+            const double sq = sqrt(cdsw / ik);
+            gdsw = ((1 + sq) * gdsw - cdsw * gdsw / (2 * sq * ik)) / (1 + 2 * sq + cdsw / ik);
+            cdsw = cdsw / (1 + sq);
+        }
+        cd = cdb + cdsw + gmin * vd;
+        gd = gdb + gdsw + gmin;
+        dIdio_dT = cdb_dT + cdsw_dT;
+    }
+    cdres = cd; gdres = gd;
+
+    if ((mode & (NGB_MODEDCTRANCURVE | NGB_MODETRAN | NGB_MODEAC | NGB_MODEINITSMSIG)) ||
+        ((mode & NGB_MODETRANOP) && (mode & NGB_MODEUIC))) {
+        /* charge storage */
+        const double czero = P(tJctCap), mj = P(tGradingCoeff), pb = P(tJctPot), fcpb = P(tDepCap);
+        const double czeroSW = P(tJctSWCap), mjsw = P(gradingSWCoeff), pbsw = P(tJctSWPot), fcpbsw = P(tDepSWCap);
+        const double cov = P(cmetal) + P(cpoly);
+        const double tt = P(tTransitTime);
+        double deplcharge, deplcap, deplchargeSW, deplcapSW, capd;
+        if (vd < fcpb) {
+            const double arg = 1 - vd / pb;
+            const double sarg = ngb_exp(-mj * ngb_log(arg));
+            deplcharge = pb * czero * (1 - arg * sarg) / (1 - mj);
+            deplcap = czero * sarg;
+        } else {
+            const double czof2 = czero / P(tF2);
+            deplcharge = czero * P(tF1) + czof2 * (P(tF3) * (vd - fcpb) + (mj / (pb + pb)) * (vd * vd - fcpb * fcpb));
+            deplcap = czof2 * (P(tF3) + mj * vd / pb);
+        }
+        if (vd < fcpbsw) {
+            const double argSW = 1 - vd / pbsw;
+            const double sargSW = ngb_exp(-mjsw * ngb_log(argSW));
+            deplchargeSW = pbsw * czeroSW * (1 - argSW * sargSW) / (1 - mjsw);
+            deplcapSW = czeroSW * sargSW;
+        } else {
+            const double czof2SW = czeroSW / P(tF2SW);
+            deplchargeSW = czeroSW * P(tF1) + czof2SW * (P(tF3SW) * (vd - fcpbsw) + (mjsw / (pbsw + pbsw)) * (vd * vd - fcpbsw * fcpbsw));
+            deplcapSW = czof2SW * (P(tF3SW) + mjsw * vd / pbsw);
+        }
+        {
+            const double diffcharge = tt * cd, diffcap = tt * gd;
+            ST(0, DIOST_capCharge) = diffcharge + deplcharge + deplchargeSW + cov * vd;
+            capd = diffcap + deplcap + deplcapSW + P(cmetal) + P(cpoly);
+            ST(0, DIOST_srcapCharge) = 0.0;
+        }
+        if (!(mode & NGB_MODETRANOP) || !(mode & NGB_MODEUIC)) {
+            if (mode & NGB_MODEINITSMSIG) {
+                ST(0, DIOST_capCurrent) = capd;
+                return NGB_OK;                             /* `continue` of dioload.c:628 */
+            }
+            {
+                const int order = NGB_LDG(&c->ctl.order[s]);
+                const double ag0 = NGB_LDG(&c->ctl.ag0[s]), ag1 = NGB_LDG(&c->ctl.ag1[s]);
+                double q0, q1, cc, geq;
+                if (order != 1 && order != 2) return NGB_E_ORDER;
+                if (mode & NGB_MODEINITTRAN) ST(1, DIOST_capCharge) = ST(0, DIOST_capCharge);
+                q0 = ST(0, DIOST_capCharge); q1 = ST(1, DIOST_capCharge);
+                cc = ngb_integrate_trap(order, ag0, ag1, q0, q1, (order == 2) ? ST(1, DIOST_capCurrent) : 0.0);
+                ST(0, DIOST_capCurrent) = cc;
+                geq = ag0 * capd;
+                gd = gd + geq;
+                cd = cd + cc;
+                if (mode & NGB_MODEINITTRAN) ST(1, DIOST_capCurrent) = cc;
+                if (c->ctl.lte)                            /* DIOtrunc -> CKTterr on the junction charge */
+                    ngb_lte_state(&c->ctl, s, c->state, DIOST_COUNT, (size_t)c->T, t, head, DIOST_capCharge, order);
+            }
+        }
+    }
+
+    /* convergence flag */
+    if (!(mode & NGB_MODEINITFIX) || !(fl & DIOF_OFF)) {
+        if (Check == 1) {
+#ifdef __CUDA_ARCH__
+            atomicAdd(&c->ctl.noncon[s], 1);
+#else
+            c->ctl.noncon[s] += 1;
+#endif
+        }
+    }
+    ST(0, DIOST_voltage) = vd;
+    ST(0, DIOST_current) = cd;
+    ST(0, DIOST_conduct) = gd;
+    ST(0, DIOST_deltemp) = 0.0;
+    ST(0, DIOST_dIdio_dT) = dIdio_dT;
+    ST(0, DIOST_qp) = 0.0;                                 /* rhsOld[qpNode = 0] */
+    ST(0, DIOST_resCurrent) = cdres;
+    ST(0, DIOST_resConduct) = gdres;
+    ST(0, DIOST_cqcsr) = 0.0;
+    ST(0, DIOST_gqcsr) = 0.0;
+
+    /* stamps, in the statement order of dioload.c:757-790 */
+    {
+        const double cdeq = cd - gd * vd;
+#define STAMP(k, v) do { const int r_ = NGB_LDG(&c->spos[(k) * c->ninst + inst]); if (r_ >= 0) c->stamp[(size_t)r_ * S + s] = (v); } while (0)
+        STAMP(DIOS_rhsNeg, cdeq);
+        STAMP(DIOS_rhsPosPrime, -cdeq);
+        STAMP(DIOS_posPos, gspr);
+        STAMP(DIOS_negNeg, gd);
+        STAMP(DIOS_ppPp, gd + gspr);
+        STAMP(DIOS_posPp, -gspr);
+        STAMP(DIOS_negPp, -gd);
+        STAMP(DIOS_ppPos, -gspr);
+        STAMP(DIOS_ppNeg, -gd);
+#undef STAMP
+    }
+#undef P
+#undef ST
+    return NGB_OK;
+}
+#endif

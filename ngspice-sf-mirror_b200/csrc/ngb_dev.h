@@ -7,6 +7,7 @@
 #include <stddef.h>
 #include "ngb_types.h"
 #include "bsim4_eval.cuh"
+#include "dio_eval.cuh"
 #include "ngb_tran.cuh"
 
 #ifdef __cplusplus
@@ -35,6 +36,7 @@ int ngb_launch_lu(const NgbLuCtx *c);
 int ngb_launch_clear_i32(int *p, int value, int n);
 int ngb_launch_tran_control(const NgbTranCtx *c);
 int ngb_launch_fill_f64(double *p, double value, int n);
+int ngb_launch_dio_load(const NgbDioCtx *c, int *errflag);
 
 #ifdef __cplusplus
 }

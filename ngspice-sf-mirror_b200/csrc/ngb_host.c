@@ -47,6 +47,13 @@ void ngbBsim4Layout(int out[8])
     out[0] = B4M_COUNT; out[1] = B4P_COUNT; out[2] = B4I_COUNT; out[3] = B4N_COUNT;
     out[4] = B4S_MAT_COUNT; out[5] = B4S_COUNT; out[6] = B4ST_COUNT; out[7] = B4O_COUNT;
 }
+static const char *dio_par_names[] = {
+#define X(n) #n,
+    NGB_DIO_INST_FIELDS(X)
+    NGB_DIO_MODEL_FIELDS(X)
+#undef X
+};
+void ngbDioLayout(int out[3]) { out[0] = DIOP_COUNT; out[1] = DIOST_COUNT; out[2] = DIOS_COUNT; }
 const char *ngbBsim4FieldName(int list, int index)
 {
     const char **t; int n;
@@ -57,6 +64,7 @@ const char *ngbBsim4FieldName(int list, int index)
     case 3: t = b4_node_names; n = B4N_COUNT; break;
     case 4: case 5: t = b4_stamp_names; n = B4S_COUNT; break;
     case 7: t = b4_op_names; n = B4O_COUNT; break;
+    case 8: t = dio_par_names; n = DIOP_COUNT; break;
     default: return NULL;
     }
     return (index >= 0 && index < n) ? t[index] : NULL;
@@ -174,6 +182,7 @@ void ngbCircuitDestroy(ngb_circuit *c)
     free(c->b4_spos); free(c->b4_slots);
     free(c->res_nodes); free(c->res_g); free(c->res_spos);
     free(c->cap_nodes); free(c->cap_par); free(c->cap_spos);
+    free(c->dio_nodes); free(c->dio_flags); free(c->dio_par); free(c->dio_spos);
     free(c->vs_nodes); free(c->vs_fn); free(c->vs_par); free(c->vs_spos); free(c->vs_cspos);
     free(c->is_nodes); free(c->is_fn); free(c->is_par); free(c->is_spos);
     free(c->Ap); free(c->Ai); free(c->eq2col); free(c->col2eq); free(c->slot_diag); free(c->diag_slot);
@@ -236,6 +245,21 @@ int ngbCircuitAddCapacitors(ngb_circuit *c, int n, const int *nodes, const doubl
     if (c->finalized || c->cap_n) return NGB_E_PANIC;
     c->cap_n = n; c->cap_nodes = (int *)xdup(nodes, sizeof(int) * 2 * (size_t)n);
     c->cap_par = (double *)xdup(par, sizeof(double) * 3 * (size_t)n);
+    return NGB_OK;
+}
+int ngbCircuitAddDiodes(ngb_circuit *c, int n, const int *nodes, const int *flags, const double *par)
+{
+    int i;
+    if (c->finalized || c->dio_n) return NGB_E_PANIC;
+    for (i = 0; i < n; i++)
+        if (flags[i] & DIOF_UNSUPPORTED) {
+            ngb_set_error("diode %d: model option not on this path (flags 0x%x: recombination current 0x200, "
+                          "separate sidewall diode 0x400, self-heating 0x800, soft reverse recovery 0x1000)", i, flags[i] & DIOF_UNSUPPORTED);
+            return NGB_E_UNSUPP;
+        }
+    c->dio_n = n; c->dio_nodes = (int *)xdup(nodes, sizeof(int) * 3 * (size_t)n);
+    c->dio_flags = (int *)xdup(flags, sizeof(int) * (size_t)n);
+    c->dio_par = (double *)xdup(par, sizeof(double) * DIOP_COUNT * (size_t)n);
     return NGB_OK;
 }
 int ngbCircuitAddVsources(ngb_circuit *c, int n, const int *nodes, const int *fn, const double *par)
@@ -330,6 +354,11 @@ int ngbCircuitFinalize(ngb_circuit *c)
         int p = c->cap_nodes[i], q = c->cap_nodes[c->cap_n + i];
         coo_push(&coo, p, p); coo_push(&coo, q, q); coo_push(&coo, p, q); coo_push(&coo, q, p);
     }
+    for (i = 0; i < c->dio_n; i++) {                 /* diosetup.c:438-444 */
+        int p = c->dio_nodes[i], q = c->dio_nodes[c->dio_n + i], pp = c->dio_nodes[2 * c->dio_n + i];
+        coo_push(&coo, p, pp); coo_push(&coo, q, pp); coo_push(&coo, pp, p); coo_push(&coo, pp, q);
+        coo_push(&coo, p, p); coo_push(&coo, q, q); coo_push(&coo, pp, pp);
+    }
     for (i = 0; i < c->res_n; i++) {
         int p = c->res_nodes[i], q = c->res_nodes[c->res_n + i];
         coo_push(&coo, p, p); coo_push(&coo, q, q); coo_push(&coo, p, q); coo_push(&coo, q, p);
@@ -378,7 +407,7 @@ int ngbCircuitFinalize(ngb_circuit *c)
     }
 
     /* 3. stamp rows and contribution lists, in CKTload order: device types by their rank in
-     *    the reference device table (bsim4 < cap < isrc < res < vsrc, dev.c:142-209), instances
+     *    the reference device table (bsim4 < cap < dio < isrc < res < vsrc, dev.c:142-209), instances
      *    in list order, positions in load order */
     c->nstamp_rows = 0;
     c->b4_spos = (int *)xcalloc((size_t)c->b4_n * B4S_TOTAL, sizeof(int));
@@ -449,6 +478,20 @@ int ngbCircuitFinalize(ngb_circuit *c)
         c->cap_spos[3 * nn + i] = new_row(c, &cb, slot_lookup(c, q, p));
         c->cap_spos[4 * nn + i] = new_row(c, &cb, p > 0 ? c->nnz + p : -1);
         c->cap_spos[5 * nn + i] = new_row(c, &cb, q > 0 ? c->nnz + q : -1);
+    }
+    c->dio_spos = (int *)xcalloc((size_t)c->dio_n * DIOS_COUNT + 1, sizeof(int));
+    for (i = 0; i < c->dio_n; i++) {
+        const int nn = c->dio_n;
+        int p = c->dio_nodes[i], q = c->dio_nodes[nn + i], pp = c->dio_nodes[2 * nn + i];
+        c->dio_spos[DIOS_rhsNeg * nn + i] = new_row(c, &cb, q > 0 ? c->nnz + q : -1);
+        c->dio_spos[DIOS_rhsPosPrime * nn + i] = new_row(c, &cb, pp > 0 ? c->nnz + pp : -1);
+        c->dio_spos[DIOS_posPos * nn + i] = new_row(c, &cb, slot_lookup(c, p, p));
+        c->dio_spos[DIOS_negNeg * nn + i] = new_row(c, &cb, slot_lookup(c, q, q));
+        c->dio_spos[DIOS_ppPp * nn + i] = new_row(c, &cb, slot_lookup(c, pp, pp));
+        c->dio_spos[DIOS_posPp * nn + i] = new_row(c, &cb, slot_lookup(c, p, pp));
+        c->dio_spos[DIOS_negPp * nn + i] = new_row(c, &cb, slot_lookup(c, q, pp));
+        c->dio_spos[DIOS_ppPos * nn + i] = new_row(c, &cb, slot_lookup(c, pp, p));
+        c->dio_spos[DIOS_ppNeg * nn + i] = new_row(c, &cb, slot_lookup(c, pp, q));
     }
     c->is_spos = (int *)xcalloc((size_t)c->is_n * 2 + 1, sizeof(int));
     for (i = 0; i < c->is_n; i++) {
@@ -974,6 +1017,14 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
         b->cap_nodes = (int *)dev_dup(c->cap_nodes, sizeof(int) * 2 * (size_t)c->cap_n);
         b->cap_spos = (int *)dev_dup(c->cap_spos, sizeof(int) * 6 * (size_t)c->cap_n);
     }
+    if (c->dio_n) {
+        const size_t T = (size_t)c->dio_n * S;
+        b->dio_par = (double *)dalloc_rep(b, "dio.par", c->dio_par, DIOP_COUNT, c->dio_n, S);
+        b->dio_state = (double *)dalloc(b, "dio.state", sizeof(double) * NGB_NHIST * DIOST_COUNT * T);
+        b->dio_nodes = (int *)dev_dup(c->dio_nodes, sizeof(int) * 3 * (size_t)c->dio_n);
+        b->dio_flags = (int *)dev_dup(c->dio_flags, sizeof(int) * (size_t)c->dio_n);
+        b->dio_spos = (int *)dev_dup(c->dio_spos, sizeof(int) * DIOS_COUNT * (size_t)c->dio_n);
+    }
     if (c->vs_n) {
         b->vs_par = (double *)dalloc_rep(b, "vsrc.par", c->vs_par, 9, c->vs_n, S);
         b->vs_fn = (int *)dev_dup(c->vs_fn, sizeof(int) * 3 * (size_t)c->vs_n);
@@ -1008,6 +1059,7 @@ void ngbBatchDestroy(ngb_batch *b)
     ngb_dev_free(b->b4_mtab); ngb_dev_free(b->b4_ptab); ngb_dev_free(b->b4_prow); ngb_dev_free(b->b4_flags);
     ngb_dev_free(b->b4_nodes); ngb_dev_free(b->b4_spos); ngb_dev_free(b->b4_prow_t);
     ngb_dev_free(b->cap_nodes); ngb_dev_free(b->cap_spos);
+    ngb_dev_free(b->dio_nodes); ngb_dev_free(b->dio_flags); ngb_dev_free(b->dio_spos);
     ngb_dev_free(b->vs_fn); ngb_dev_free(b->vs_spos); ngb_dev_free(b->is_fn); ngb_dev_free(b->is_spos);
     if (b->have_lu) {
         if (b->dpk.ok) { ngb_dev_free((void *)b->dpk.blob); ngb_dev_free((void *)b->dpk.aslot); ngb_dev_free((void *)b->dpk.arow); ngb_dev_free((void *)b->dpk.ext); }
@@ -1073,6 +1125,14 @@ void ngb_fill_capctx(ngb_batch *b, NgbCapCtx *x)
     x->ninst = c->cap_n; x->S = b->S; x->T = c->cap_n * b->S; x->nodes = b->cap_nodes; x->par = b->cap_par;
     x->spos = b->cap_spos; x->state = b->cap_state; x->stamp = b->stamp; x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl;
 }
+void ngb_fill_dioctx(ngb_batch *b, NgbDioCtx *x)
+{
+    const ngb_circuit *c = b->c;
+    memset(x, 0, sizeof *x);
+    x->ninst = c->dio_n; x->S = b->S; x->T = c->dio_n * b->S; x->nodes = b->dio_nodes; x->flags = b->dio_flags; x->par = b->dio_par;
+    x->spos = b->dio_spos; x->state = b->dio_state; x->stamp = b->stamp; x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl;
+    x->reltol = c->opt.reltol; x->abstol = c->opt.abstol; x->vntol = c->opt.vntol; x->chgtol = c->opt.chgtol; x->trtol = c->opt.trtol;
+}
 void ngb_fill_srcctx(ngb_batch *b, NgbSrcCtx *x, int is_current)
 {
     const ngb_circuit *c = b->c;
@@ -1113,6 +1173,7 @@ int ngb_enqueue_load(ngb_batch *b)
     int r;
     if (c->b4_n) { B4Ctx x; ngb_fill_b4ctx(b, &x); if ((r = ngb_launch_bsim4_load(&x, b->errflag))) return r; }
     if (c->cap_n) { NgbCapCtx x; ngb_fill_capctx(b, &x); if ((r = ngb_launch_cap_load(&x, b->errflag))) return r; }
+    if (c->dio_n) { NgbDioCtx x; ngb_fill_dioctx(b, &x); if ((r = ngb_launch_dio_load(&x, b->errflag))) return r; }
     if (c->is_n) { NgbSrcCtx x; ngb_fill_srcctx(b, &x, 1); if ((r = ngb_launch_src_load(&x))) return r; }
     if (c->vs_n) { NgbSrcCtx x; ngb_fill_srcctx(b, &x, 0); if ((r = ngb_launch_src_load(&x))) return r; }
     { NgbAsmCtx x; ngb_fill_asmctx(b, &x); if ((r = ngb_launch_assemble(&x))) return r; }

@@ -3,6 +3,7 @@
 #define NGB_HOST_H
 #include "ngb_types.h"
 #include "bsim4_eval.cuh"
+#include "dio_eval.cuh"
 
 #ifdef __cplusplus
 extern "C" {
@@ -18,6 +19,7 @@ struct ngb_circuit {
     int *b4_spos, *b4_slots;
     int res_n; int *res_nodes; double *res_g; int *res_spos;
     int cap_n; int *cap_nodes; double *cap_par; int *cap_spos;
+    int dio_n; int *dio_nodes, *dio_flags; double *dio_par; int *dio_spos;
     int vs_n; int *vs_nodes, *vs_fn; double *vs_par; int *vs_spos, *vs_cspos;
     int is_n; int *is_nodes, *is_fn; double *is_par; int *is_spos;
     /* CSC pattern (SMPconvertCOOtoCSC) */
@@ -43,6 +45,7 @@ struct ngb_batch {
     int *d_node_type, *d_tgt_ptr, *d_tgt_rows, *d_slot_diag;
     double *b4_inst, *b4_state, *b4_op, *b4_mtab, *b4_ptab; int *b4_prow, *b4_prow_t, *b4_flags, *b4_nodes, *b4_spos;
     double *cap_par, *cap_state; int *cap_nodes, *cap_spos;
+    double *dio_par, *dio_state; int *dio_nodes, *dio_flags, *dio_spos;
     double *vs_par; int *vs_fn, *vs_spos;
     double *is_par; int *is_fn, *is_spos;
     NgbLuSched dsch;               /* device arrays */
@@ -56,6 +59,7 @@ struct ngb_batch {
 void ngb_set_error(const char *fmt, ...);
 void ngb_fill_b4ctx(struct ngb_batch *b, B4Ctx *x);
 void ngb_fill_capctx(struct ngb_batch *b, NgbCapCtx *x);
+void ngb_fill_dioctx(struct ngb_batch *b, NgbDioCtx *x);
 void ngb_fill_srcctx(struct ngb_batch *b, NgbSrcCtx *x, int is_current);
 void ngb_fill_asmctx(struct ngb_batch *b, NgbAsmCtx *x);
 void ngb_fill_luctx(struct ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve);

@@ -111,6 +111,7 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     ngb_launch_fill_f64(b->ctl.lte2, 1e300, S);
     ngb_dev_memset(b->x, 0, sizeof(double) * 2 * (size_t)b->neq1 * S);
     if (b->b4_state) ngb_dev_memset(b->b4_state, 0, sizeof(double) * NGB_NHIST * B4ST_COUNT * (size_t)c->b4_n * S);
+    if (b->dio_state) ngb_dev_memset(b->dio_state, 0, sizeof(double) * NGB_NHIST * DIOST_COUNT * (size_t)c->dio_n * S);
     if (b->cap_state) ngb_dev_memset(b->cap_state, 0, sizeof(double) * NGB_NHIST * 2 * (size_t)c->cap_n * S);
     if (b->b4_op) ngb_dev_memset(b->b4_op, 0, sizeof(double) * B4O_COUNT * (size_t)c->b4_n * S);
     return ngb_dev_sync();

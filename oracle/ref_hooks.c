@@ -33,12 +33,14 @@
 #include "cap/capdefs.h"
 #include "vsrc/vsrcdefs.h"
 #include "isrc/isrcdefs.h"
+#include "dio/diodefs.h"
 #include "klu_internal.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "../ngspice-sf-mirror_b200/csrc/bsim4_fields.h"
+#include "../ngspice-sf-mirror_b200/csrc/dio_fields.h"
 
 extern SPICEdev **DEVices;
 extern int DEVmaxnum;
@@ -93,7 +95,7 @@ static int slot_of(KLUmatrix *K, double *p)
     return -1;     /* trash cell (ground row/column) */
 }
 
-static int b4_type = -2, res_type, cap_type, vsrc_type, isrc_type;
+static int b4_type = -2, res_type, cap_type, vsrc_type, isrc_type, dio_type;
 static void lookup_types(void)
 {
     if (b4_type != -2) return;
@@ -102,6 +104,7 @@ static void lookup_types(void)
     cap_type = CKTtypelook("Capacitor");
     vsrc_type = CKTtypelook("Vsource");
     isrc_type = CKTtypelook("Isource");
+    dio_type = CKTtypelook("Diode");
 }
 
 /* ---------------------------------------------------------------- flat circuit dump */
@@ -292,6 +295,62 @@ static void dump_linear(FILE *f, CKTcircuit *ckt, KLUmatrix *K)
     put_is(f, "isrc/n", n);
 }
 
+/* diodes: node numbers, flags and the DIOtemp results DIOload reads (dio_fields.h) */
+static void dump_dio(FILE *f, CKTcircuit *ckt, KLUmatrix *K)
+{
+    int n = 0, i;
+    if (dio_type >= 0) {
+        DIOmodel *m; DIOinstance *h;
+        for (m = (DIOmodel *)ckt->CKThead[dio_type]; m; m = DIOnextModel(m))
+            for (h = DIOinstances(m); h; h = DIOnextInstance(h)) n++;
+        if (n) {
+            int *nodes = (int *)calloc((size_t)n * 6, sizeof(int)), *slots = (int *)calloc((size_t)n * 7, sizeof(int));
+            int *flags = (int *)calloc((size_t)n, sizeof(int)), *sb = (int *)calloc((size_t)n, sizeof(int));
+            double *par = (double *)calloc((size_t)n * DIOP_COUNT, sizeof(double));
+            size_t nb = 0; char *names = (char *)calloc((size_t)n * 64 + 1, 1);
+            i = 0;
+            for (m = (DIOmodel *)ckt->CKThead[dio_type]; m; m = DIOnextModel(m))
+                for (h = DIOinstances(m); h; h = DIOnextInstance(h), i++) {
+                    int fl = 0, k = 0;
+                    nodes[i] = h->DIOposNode; nodes[n + i] = h->DIOnegNode; nodes[2 * n + i] = h->DIOtempNode;
+                    nodes[3 * n + i] = h->DIOposPrimeNode; nodes[4 * n + i] = h->DIOposSwPrimeNode; nodes[5 * n + i] = h->DIOqpNode;
+                    slots[i] = slot_of(K, h->DIOposPosPtr); slots[n + i] = slot_of(K, h->DIOnegNegPtr);
+                    slots[2 * n + i] = slot_of(K, h->DIOposPrimePosPrimePtr); slots[3 * n + i] = slot_of(K, h->DIOposPosPrimePtr);
+                    slots[4 * n + i] = slot_of(K, h->DIOnegPosPrimePtr); slots[5 * n + i] = slot_of(K, h->DIOposPrimePosPtr);
+                    slots[6 * n + i] = slot_of(K, h->DIOposPrimeNegPtr);
+                    if (h->DIOoff) fl |= DIOF_OFF;
+                    if (m->DIObreakdownVoltageGiven) fl |= DIOF_BV;
+                    if (m->DIOsatSWCurGiven) fl |= DIOF_SATSW;
+                    if (m->DIOswEmissionCoeffGiven) fl |= DIOF_NSW;
+                    if (m->DIOtunSatSWCurGiven) fl |= DIOF_TUNSW;
+                    if (m->DIOtunSatCurGiven) fl |= DIOF_TUN;
+                    if (m->DIOforwardKneeCurrentGiven) fl |= DIOF_IKF;
+                    if (m->DIOreverseKneeCurrentGiven) fl |= DIOF_IKR;
+                    if (m->DIOforwardSWKneeCurrentGiven) fl |= DIOF_IKP;
+                    if (m->DIOrecSatCurGiven) fl |= DIOF_RECSAT;
+                    if (m->DIOresistSWGiven) fl |= DIOF_RESISTSW;
+                    if ((h->DIOtempNode > 0) && h->DIOthermal && m->DIOrth0Given) fl |= DIOF_SELFHEAT;
+                    if ((h->DIOqpNode > 0) && (m->DIOsoftRevRecParam != 0) && (h->DIOtTransitTime != 0)) fl |= DIOF_REVREC;
+                    flags[i] = fl; sb[i] = h->DIOstate;
+#define X(nm) par[(size_t)(k++) * n + i] = h->DIO##nm;
+                    NGB_DIO_INST_FIELDS(X)
+#undef X
+#define X(nm) par[(size_t)(k++) * n + i] = m->DIO##nm;
+                    NGB_DIO_MODEL_FIELDS(X)
+#undef X
+                    nb += (size_t)snprintf(names + nb, 64, "%s\n", h->DIOname);
+                }
+            put_i2(f, "dio/nodes", nodes, 6, n); put_i2(f, "dio/slots", slots, 7, n);
+            put_i1(f, "dio/flags", flags, n); put_i1(f, "dio/state_base", sb, n);
+            put_d2(f, "dio/par", par, DIOP_COUNT, n);
+            { int *nb_i = (int *)calloc(nb + 1, sizeof(int)); size_t q; for (q = 0; q < nb; q++) nb_i[q] = (unsigned char)names[q];
+              put_i1(f, "dio/names_bytes", nb_i, (long long)nb); free(nb_i); }
+            free(nodes); free(slots); free(flags); free(sb); free(par); free(names);
+        }
+    }
+    put_is(f, "dio/n", n);
+}
+
 static void dump_flat(CKTcircuit *ckt, const char *path)
 {
     FILE *f = ngt_open(path);
@@ -353,6 +412,7 @@ static void dump_flat(CKTcircuit *ckt, const char *path)
     }
     dump_bsim4(f, ckt, K);
     dump_linear(f, ckt, K);
+    dump_dio(f, ckt, K);
     fclose(f);
     free(ntype); free(nic); free(nicg); free(names);
 }
@@ -534,6 +594,7 @@ int __wrap_CKTload(CKTcircuit *ckt)
         if (K) { tname(nm, "Ax"); put_d1(trace_f, nm, K->KLUmatrixAx, K->KLUmatrixNZ); }
         tname(nm, "rhs"); put_d1(trace_f, nm, ckt->CKTrhs, ckt->CKTmaxEqNum + 1);
         tname(nm, "state0_out"); put_d1(trace_f, nm, ckt->CKTstate0, ckt->CKTnumStates);
+        tname(nm, "state1_out"); put_d1(trace_f, nm, ckt->CKTstate1, ckt->CKTnumStates);
         tname(nm, "noncon"); put_is(trace_f, nm, ckt->CKTnoncon);
         fflush(trace_f);
     }

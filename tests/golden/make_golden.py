@@ -8,6 +8,7 @@ and test files.  Needs /root/reference; the fixtures it writes do not.
          that runs (4.5.0 would select the separate bsim4v5 device), `.option xmu=0.49 klu`.
   ro101  same cards, 101 stages (BASELINE config 2).
   inv    tests/bsim4/{nmos,pmos}/parameters cards, CMOS inverter with PULSE input (config 1).
+  dio    junction diodes (rectifier, zener clamp, sidewall/tunnel/knee parameters) with R, C, SIN source.
 
 Outputs (tests/golden/): <name>.flat.ngt  flattened circuit after CKTsetup/CKTtemp
                          <name>.trace.ngt.gz recorded CKTload / KLU calls (subset)
@@ -80,6 +81,30 @@ def inv_netlist():
         qa_card("nmos"), qa_card("pmos"), ".end", ""])
 
 
+def dio_netlist():
+    """rectifier + zener clamp + a diode with sidewall, tunnel and knee parameters: exercises DIOload's
+    forward / reverse / breakdown branches, series resistance (internal node) and none, charge storage"""
+    return "\n".join([
+        "* diode rectifier, zener clamp, sidewall/tunnel diode",
+        "vin in 0 sin(0 5 1meg)",
+        "d1 in out dmod",
+        "c1 out 0 1n",
+        "r1 out 0 1k",
+        "r2 in z 100",
+        "d2 0 z dz",
+        "d3 z 0 dsw area=1.5 pj=2",
+        "r3 in w 2k",
+        "d4 w 0 dnors",
+        "d5 0 w dnors off",
+        ".model dmod d is=1e-14 rs=10 n=1.05 cjo=2p vj=0.7 m=0.45 tt=5n bv=50 ibv=1e-6",
+        ".model dz d is=1e-12 rs=5 bv=3.3 ibv=1e-3 cjo=10p nbv=1.2",
+        ".model dsw d is=2e-14 rs=2 n=1.1 cjo=1p jsw=1e-13 ns=1.2 cjp=1p php=0.8 mjsw=0.3 ikf=0.05 ikr=0.01 jtun=1e-9 ntun=30 tt=1n",
+        ".model dnors d is=5e-15 cjo=0.5p tt=2n",
+        ".option klu",
+        ".tran 5n 3u",
+        ".end", ""])
+
+
 def read_raw(path):
     data = open(path, "rb").read()
     i = data.index(b"Binary:\n")
@@ -100,7 +125,7 @@ def run(name, netlist, calls, save):
     os.makedirs(TMP, exist_ok=True)
     cir = os.path.join(TMP, name + ".cir")
     open(cir, "w").write(netlist)
-    if name in ("ro17", "ro101", "ro17k", "inv"):
+    if name in ("ro17", "ro101", "ro17k", "inv", "dio"):
         # the netlist itself is kept too: the CPU-baseline arm of bench.py feeds it to oracle/_ref/ngspice
         os.makedirs(os.path.join(HERE, "netlists"), exist_ok=True)
         open(os.path.join(HERE, "netlists", name + ".cir"), "w").write(netlist)
@@ -155,5 +180,7 @@ if __name__ == "__main__":
             run(f"ro17mc{i}", ro_netlist(17, tran=".tran .1ns 20ns uic", kick=True, delvto=dv[i]), "1", ["18", "2", "9", "vdd#branch"])
     if "inv" in which:
         run("inv", inv_netlist(), "0-40,100,101,300,301", ["out", "in", "vdd#branch", "vin#branch"])
+    if "dio" in which:
+        run("dio", dio_netlist(), "0-30,200,201,1000,1001,2000", ["out", "z", "w", "vin#branch"])
     if "ro101" in which:
         run("ro101", ro_netlist(101), "1,2,3000", ["102", "2", "50", "vdd#branch"])

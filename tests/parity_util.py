@@ -43,6 +43,9 @@ def state_maps(flat, lib):
     n = ngt.scalar(flat, "cap/n", 0)
     if n:
         out["cap"] = flat["cap/state_base"][None, :] + np.arange(2)[:, None]
+    n = ngt.scalar(flat, "dio/n", 0)
+    if n:
+        out["dio"] = flat["dio/state_base"][None, :] + np.arange(lib.dio_layout[1])[:, None]
     return out
 
 
@@ -73,7 +76,7 @@ def replay_load(lib, circ, flat, trace, call, S=1, batch=None):
     b.put("x", x)
     maps = state_maps(flat, lib)
     hist = [trace[c + "state0_in"], trace[c + "state1_in"], trace.get(c + "state2_in")]
-    for dev, key in (("b4", "b4.state"), ("cap", "cap.state")):
+    for dev, key in (("b4", "b4.state"), ("cap", "cap.state"), ("dio", "dio.state")):
         if dev not in maps:
             continue
         m = maps[dev]                                  # [k][n]
@@ -97,8 +100,10 @@ def replay_load(lib, circ, flat, trace, call, S=1, batch=None):
         ours["b4_op"] = b.get("b4.op", (lib.layout[7], maps["b4"].shape[1], S))
     if "cap" in maps:
         ours["cap_state"] = b.get("cap.state", (4,) + maps["cap"].shape + (S,))
+    if "dio" in maps:
+        ours["dio_state"] = b.get("dio.state", (4,) + maps["dio"].shape + (S,))
     ref = dict(Ax=trace[c + "Ax"], rhs=trace[c + "rhs"][:neq1], noncon=int(trace[c + "noncon"][0]),
-               state0=trace[c + "state0_out"], mode=mode)
+               state0=trace[c + "state0_out"], state1=trace.get(c + "state1_out"), mode=mode)
     if c + "b4_op_out" in trace:
         ref["b4_op"] = trace[c + "b4_op_out"]
         ref["b4_state1"] = trace[c + "b4_state1"]
