@@ -47,7 +47,7 @@ int ngbProfileRead(double *ms_sum, long *count);
 /* field-list sizes, so callers can check they were built against the same lists
  * (bsim4_fields.h): [0]=model [1]=bin [2]=instance [3]=node roles [4]=matrix stamps
  * [5]=matrix+rhs stamps [6]=states [7]=op-point fields; list 8 of ngbBsim4FieldName is the diode
- * parameter list of dio_fields.h (ngbDioLayout: [0]=parameters [1]=states [2]=stamp rows) */
+ * parameter list of dio_fields.h, lists 9-11 the BSIM3 model / bin / instance lists (ngbDioLayout: [0]=parameters [1]=states [2]=stamp rows) */
 void ngbBsim4Layout(int out[8]);
 const char *ngbBsim4FieldName(int list, int index);
 void ngbDioLayout(int out[3]);
@@ -72,6 +72,13 @@ int ngbCircuitSetExactOrder(ngb_circuit *c, int on);
 int ngbCircuitAddResistors(ngb_circuit *c, int n, const int *nodes /* [2][n] */, const double *g);
 int ngbCircuitAddCapacitors(ngb_circuit *c, int n, const int *nodes /* [2][n] */,
                             const double *par /* [3][n] C, m, ic */);
+/* BSIM3v3.3.0 instances in reference list order, same three-table form as BSIM4 with the lists of
+ * csrc/bsim3_fields.h: nodes [6][ninst] d g s b d' s', flags [ninst] (B3F_*), prow, inst [NI][ninst],
+ * mtab [nrows][NM], ptab [nrows][NP] -- replaces the BSIM3instance/BSIM3model walk of BSIM3load
+ * (bsim3/b3ld.c:182-186).  nqsMod, acmMod != 0 and capMod 0/1 return E_UNSUPP */
+int ngbCircuitAddBsim3(ngb_circuit *c, int ninst, const int *nodes, const int *flags, const int *prow,
+                       const double *inst, int nrows, const double *mtab, const double *ptab);
+void ngbBsim3Layout(int out[6]);               /* model, bin, instance, node roles, stamp rows, states */
 /* junction diodes after DIOsetup/DIOtemp (dio/diosetup.c, diotemp.c): nodes [3][n] pos neg posPrime
  * (posPrime == pos without series resistance), flags [n] DIOF_* and par [DIOP_COUNT][n] as listed
  * in csrc/dio_fields.h -- replaces the DIOinstance/DIOmodel walk of DIOload (dio/dioload.c:75-80).
@@ -96,6 +103,11 @@ int ngbCircuitGetBsim4Slots(const ngb_circuit *c, int *slots /* [70][ninst], -1 
 int ngbCircuitSetLuPattern(ngb_circuit *c, int n, int nblocks, const int *Q, const int *R,
                            const int *Pnum, const int *Lp, const int *Li, const int *Up, const int *Ui,
                            const int *Offp, const int *Offi);
+/* NIiter runs the pivoting factor twice in a run with a DC operating point: at MODEINITJCT and in the
+ * first iteration under MODEINITTRAN (niiter.c:107-111), and the pivot order may change.  Set 0
+ * (default) holds the first result, set 1 the second; ngbCircuitSelectLuSet chooses which one the
+ * next ngbCircuitSetLuPattern / ngbCircuitLuInfo refers to.  With only set 0 present it serves both */
+int ngbCircuitSelectLuSet(ngb_circuit *c, int which);
 /* own BTF + fill-reducing ordering + pivoting factor on one sample's matrix values
  * (host; the role klu_analyze/klu_factor play) */
 int ngbCircuitAnalyze(ngb_circuit *c, const double *Ax);
@@ -107,12 +119,13 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int nsamples, int device);
 void ngbBatchDestroy(ngb_batch *b);
 
 /* named device arrays (tests, the reference-side shim, result download):
- *   ctl.mode ctl.active ctl.head ctl.order ctl.noncon ctl.xsel ctl.err          int   [S]
+ *   ctl.mode ctl.active ctl.head ctl.order ctl.noncon ctl.xsel ctl.err ctl.lusel int  [S]
  *   ctl.ag0 ctl.ag1 ctl.delta ctl.time ctl.gmin ctl.diag_gmin ctl.srcfact        f64   [S]
  *   ctl.delta_old                                                                f64   [7][S]
  *   x            f64 [2][neq+1][S]      Ax  f64 [S][nnz]      stamp f64 [rows][S]
  *   b4.inst      f64 [NI][ninst*S]      b4.state f64 [4][29][ninst*S]   b4.op f64 [NO][ninst*S]
  *   b4.prow      int [ninst*S]          cap.state f64 [4][2][ncap*S]    cap.par f64 [3][ncap*S]
+ *   b3.inst      f64 [NI][n3*S]         b3.state f64 [4][17][n3*S]      b3.von f64 [n3*S]
  *   dio.par      f64 [NP][nd*S]         dio.state f64 [4][22][nd*S]
  *   vsrc.par     f64 [9][nv*S]          lu.V f64 [S][nV]    lu.Rs f64 [S][n]
  *   lu.nodeconv  int [S]                lu.singular int [S] */

@@ -72,6 +72,11 @@ class Library:
         L.ngbDioLayout(dl)
         self.dio_layout = list(dl)                       # parameters, states, stamp rows
         self.fields["dio"] = [L.ngbBsim4FieldName(8, i).decode() for i in range(dl[0])]
+        bl = (ctypes.c_int * 6)()
+        L.ngbBsim3Layout(bl)
+        self.b3_layout = list(bl)                        # model, bin, instance, node roles, stamp rows, states
+        for li, key, n in ((9, "b3model", bl[0]), (10, "b3bin", bl[1]), (11, "b3inst", bl[2])):
+            self.fields[key] = [L.ngbBsim4FieldName(li, i).decode() for i in range(n)]
 
     @property
     def backend(self):
@@ -143,6 +148,14 @@ class Circuit:
                 "fixture built against different BSIM4 field lists"
             lib.check(lib.L.ngbCircuitAddBsim4(c.h, int(n), _ip(nodes), _ip(flags), _ip(prow), _dp(inst),
                                                int(mtab.shape[0]), _dp(mtab), _dp(ptab)), "ngbCircuitAddBsim4")
+        n = sc(flat, "b3/ninst", 0)
+        if n:
+            inst, mtab, ptab = _f64(flat["b3/inst"]), _f64(flat["b3/mtab"]), _f64(flat["b3/ptab"])
+            assert inst.shape[0] == lib.b3_layout[2] and mtab.shape[1] == lib.b3_layout[0] and ptab.shape[1] == lib.b3_layout[1], \
+                "fixture built against different BSIM3 field lists"
+            lib.check(lib.L.ngbCircuitAddBsim3(c.h, int(n), _ip(_i32(flat["b3/nodes"])), _ip(_i32(flat["b3/flags"])),
+                                               _ip(_i32(flat["b3/prow"])), _dp(inst), int(mtab.shape[0]), _dp(mtab), _dp(ptab)),
+                      "ngbCircuitAddBsim3")
         n = sc(flat, "res/n", 0)
         if n:
             lib.check(lib.L.ngbCircuitAddResistors(c.h, int(n), _ip(_i32(flat["res/nodes"])), _dp(_f64(flat["res/g"]))),
@@ -182,8 +195,16 @@ class Circuit:
         self.lib.check(self.lib.L.ngbCircuitGetBsim4Slots(self.h, _ip(s)))
         return s
 
-    def set_lu_pattern(self, pat, prefix=""):
-        """pat: dict with n nblocks Q R Pnum Lp Li Up Ui Offp Offi (KLU symbolic + numeric pattern)."""
+    def set_lu_pattern(self, pat, prefix="", which=0):
+        """pat: dict with n nblocks Q R Pnum Lp Li Up Ui Offp Offi (KLU symbolic + numeric pattern);
+        a list/tuple gives the pattern of the first pivoting factor and of the re-pivoting in the
+        first transient iteration (sets 0 and 1)."""
+        if isinstance(pat, (list, tuple)):
+            for w, p1 in enumerate(pat[:2]):
+                self.set_lu_pattern(p1, prefix, which=w)
+            self.lib.check(self.lib.L.ngbCircuitSelectLuSet(self.h, 0))
+            return
+        self.lib.check(self.lib.L.ngbCircuitSelectLuSet(self.h, int(which)))
         g = lambda k: _i32(pat[prefix + k])
         self._keep = [g(k) for k in ("Q", "R", "Pnum", "Lp", "Li", "Up", "Ui", "Offp", "Offi")]
         n = int(np.asarray(pat[prefix + "n"]).reshape(-1)[0]); nb = int(np.asarray(pat[prefix + "nblocks"]).reshape(-1)[0])
@@ -196,7 +217,7 @@ class Circuit:
         return dict(zip(["nV", "nlev", "npairs", "ntask", "nslev", "nsolvepairs", "lnz", "unz", "nzoff"], list(info)))
 
 
-_INT_ARRAYS = {"ctl.mode", "ctl.active", "ctl.head", "ctl.order", "ctl.noncon", "ctl.xsel", "ctl.err",
+_INT_ARRAYS = {"ctl.lusel", "ctl.mode", "ctl.active", "ctl.head", "ctl.order", "ctl.noncon", "ctl.xsel", "ctl.err",
                "b4.prow", "lu.nodeconv", "lu.singular", "errflag"}
 
 

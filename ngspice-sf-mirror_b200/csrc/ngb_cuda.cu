@@ -52,6 +52,15 @@ ngb_k_cap_load(const NgbCapCtx c, int *errflag)
     if (e) atomicMax(errflag, e);
 }
 
+__global__ void __launch_bounds__(256, 2)
+ngb_k_bsim3_load(const B3Ctx c, int *errflag)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)c.T) return;
+    const int e = b3_load_thread(&c, t);
+    if (e) atomicMax(errflag, e);
+}
+
 __global__ void __launch_bounds__(256)
 ngb_k_dio_load(const NgbDioCtx c, int *errflag)
 {
@@ -262,6 +271,13 @@ int ngb_launch_cap_load(const NgbCapCtx *c, int *errflag)
     const unsigned grid = (unsigned)(((size_t)c->T + 255) / 256);
     ngb_k_cap_load<<<grid, 256, 0, g_stream>>>(*c, errflag);
     return post_launch("cap_load");
+}
+int ngb_launch_bsim3_load(const B3Ctx *c, int *errflag)
+{
+    if (c->T <= 0) return 0;
+    const unsigned grid = (unsigned)(((size_t)c->T + 255) / 256);
+    ngb_k_bsim3_load<<<grid, 256, 0, g_stream>>>(*c, errflag);
+    return post_launch("bsim3_load");
 }
 int ngb_launch_dio_load(const NgbDioCtx *c, int *errflag)
 {

@@ -8,6 +8,7 @@
 #include "ngb_types.h"
 #include "bsim4_eval.cuh"
 #include "dio_eval.cuh"
+#include "bsim3_eval.cuh"
 #include "ngb_tran.cuh"
 
 #ifdef __cplusplus
@@ -37,6 +38,7 @@ int ngb_launch_clear_i32(int *p, int value, int n);
 int ngb_launch_tran_control(const NgbTranCtx *c);
 int ngb_launch_fill_f64(double *p, double value, int n);
 int ngb_launch_dio_load(const NgbDioCtx *c, int *errflag);
+int ngb_launch_bsim3_load(const B3Ctx *c, int *errflag);
 
 #ifdef __cplusplus
 }

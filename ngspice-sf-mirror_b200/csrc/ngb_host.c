@@ -47,6 +47,7 @@ void ngbBsim4Layout(int out[8])
     out[0] = B4M_COUNT; out[1] = B4P_COUNT; out[2] = B4I_COUNT; out[3] = B4N_COUNT;
     out[4] = B4S_MAT_COUNT; out[5] = B4S_COUNT; out[6] = B4ST_COUNT; out[7] = B4O_COUNT;
 }
+static const char *b3_model_names[B3M_COUNT], *b3_bin_names[B3P_COUNT], *b3_inst_names[B3I_COUNT];
 static const char *dio_par_names[] = {
 #define X(n) #n,
     NGB_DIO_INST_FIELDS(X)
@@ -65,6 +66,9 @@ const char *ngbBsim4FieldName(int list, int index)
     case 4: case 5: t = b4_stamp_names; n = B4S_COUNT; break;
     case 7: t = b4_op_names; n = B4O_COUNT; break;
     case 8: t = dio_par_names; n = DIOP_COUNT; break;
+    case 9: t = b3_model_names; n = B3M_COUNT; break;
+    case 10: t = b3_bin_names; n = B3P_COUNT; break;
+    case 11: t = b3_inst_names; n = B3I_COUNT; break;
     default: return NULL;
     }
     return (index >= 0 && index < n) ? t[index] : NULL;
@@ -182,6 +186,7 @@ void ngbCircuitDestroy(ngb_circuit *c)
     free(c->b4_spos); free(c->b4_slots);
     free(c->res_nodes); free(c->res_g); free(c->res_spos);
     free(c->cap_nodes); free(c->cap_par); free(c->cap_spos);
+    free(c->b3_nodes); free(c->b3_flags); free(c->b3_prow); free(c->b3_inst); free(c->b3_mtab); free(c->b3_ptab); free(c->b3_spos);
     free(c->dio_nodes); free(c->dio_flags); free(c->dio_par); free(c->dio_spos);
     free(c->vs_nodes); free(c->vs_fn); free(c->vs_par); free(c->vs_spos); free(c->vs_cspos);
     free(c->is_nodes); free(c->is_fn); free(c->is_par); free(c->is_spos);
@@ -190,6 +195,7 @@ void ngbCircuitDestroy(ngb_circuit *c)
     free(c->klu_Q); free(c->klu_R); free(c->klu_Pnum);
     free_sched(&c->sch);
     free_packed(&c->pk);
+    { int w; for (w = 0; w < 2; w++) if (c->lu[w].valid) { free_sched(&c->lu[w].sch); free_packed(&c->lu[w].pk); } }
     free(c);
 }
 
@@ -245,6 +251,70 @@ int ngbCircuitAddCapacitors(ngb_circuit *c, int n, const int *nodes, const doubl
     if (c->finalized || c->cap_n) return NGB_E_PANIC;
     c->cap_n = n; c->cap_nodes = (int *)xdup(nodes, sizeof(int) * 2 * (size_t)n);
     c->cap_par = (double *)xdup(par, sizeof(double) * 3 * (size_t)n);
+    return NGB_OK;
+}
+/* (row role, column role) of every BSIM3 stamp: the TSTALLOC table of b3set.c:1090-1111 */
+static const int b3_stamp_r[B3S_COUNT] = {
+#define d B3N_d
+#define g B3N_g
+#define s B3N_s
+#define b B3N_b
+#define dp B3N_dp
+#define sp B3N_sp
+#define X(n, r, cc) r,
+    NGB_B3_STAMPS(X)
+#undef X
+};
+static const int b3_stamp_c[B3S_COUNT] = {
+#define X(n, r, cc) cc,
+    NGB_B3_STAMPS(X)
+#undef X
+#undef d
+#undef g
+#undef s
+#undef b
+#undef dp
+#undef sp
+};
+static const char *b3_model_names[] = {
+#define X(n) #n,
+    NGB_B3_MODEL_FIELDS(X)
+#undef X
+};
+static const char *b3_bin_names[] = {
+#define X(n) #n,
+    NGB_B3_BIN_FIELDS(X)
+#undef X
+};
+static const char *b3_inst_names[] = {
+#define X(n) #n,
+    NGB_B3_INST_FIELDS(X)
+#undef X
+};
+void ngbBsim3Layout(int out[6])
+{ out[0] = B3M_COUNT; out[1] = B3P_COUNT; out[2] = B3I_COUNT; out[3] = B3N_COUNT; out[4] = B3S_COUNT; out[5] = B3ST_COUNT; }
+
+int ngbCircuitAddBsim3(ngb_circuit *c, int ninst, const int *nodes, const int *flags, const int *prow,
+                       const double *inst, int nrows, const double *mtab, const double *ptab)
+{
+    int i;
+    if (c->finalized || c->b3_n) return NGB_E_PANIC;
+    for (i = 0; i < ninst; i++) {
+        const double *mr;
+        if (prow[i] < 0 || prow[i] >= nrows) { ngb_set_error("BSIM3 instance %d: parameter row %d out of range", i, prow[i]); return NGB_E_PANIC; }
+        mr = mtab + (size_t)prow[i] * B3M_COUNT;
+        if (flags[i] & B3F_NQS) { ngb_set_error("BSIM3 instance %d: nqsMod/acnqsMod not supported", i); return NGB_E_UNSUPP; }
+        if ((int)mr[B3M_acmMod] != 0) { ngb_set_error("BSIM3 instance %d: acmMod=%d not supported (0 only)", i, (int)mr[B3M_acmMod]); return NGB_E_UNSUPP; }
+        if ((int)mr[B3M_capMod] != 2 && (int)mr[B3M_capMod] != 3) {
+            ngb_set_error("BSIM3 instance %d: capMod=%d not supported (2 and 3)", i, (int)mr[B3M_capMod]); return NGB_E_UNSUPP; }
+    }
+    c->b3_n = ninst; c->b3_nrows = nrows;
+    c->b3_nodes = (int *)xdup(nodes, sizeof(int) * B3N_COUNT * (size_t)ninst);
+    c->b3_flags = (int *)xdup(flags, sizeof(int) * (size_t)ninst);
+    c->b3_prow = (int *)xdup(prow, sizeof(int) * (size_t)ninst);
+    c->b3_inst = (double *)xdup(inst, sizeof(double) * B3I_COUNT * (size_t)ninst);
+    c->b3_mtab = (double *)xdup(mtab, sizeof(double) * B3M_COUNT * (size_t)nrows);
+    c->b3_ptab = (double *)xdup(ptab, sizeof(double) * B3P_COUNT * (size_t)nrows);
     return NGB_OK;
 }
 int ngbCircuitAddDiodes(ngb_circuit *c, int n, const int *nodes, const int *flags, const double *par)
@@ -350,6 +420,9 @@ int ngbCircuitFinalize(ngb_circuit *c)
             coo_push(&coo, c->b4_nodes[rr * c->b4_n + i], c->b4_nodes[rc * c->b4_n + i]);
         }
     }
+    for (i = 0; i < c->b3_n; i++)
+        for (k = B3S_RHS_COUNT; k < B3S_COUNT; k++)
+            coo_push(&coo, c->b3_nodes[b3_stamp_r[k] * c->b3_n + i], c->b3_nodes[b3_stamp_c[k] * c->b3_n + i]);
     for (i = 0; i < c->cap_n; i++) {
         int p = c->cap_nodes[i], q = c->cap_nodes[c->cap_n + i];
         coo_push(&coo, p, p); coo_push(&coo, q, q); coo_push(&coo, p, q); coo_push(&coo, q, p);
@@ -407,9 +480,16 @@ int ngbCircuitFinalize(ngb_circuit *c)
     }
 
     /* 3. stamp rows and contribution lists, in CKTload order: device types by their rank in
-     *    the reference device table (bsim4 < cap < dio < isrc < res < vsrc, dev.c:142-209), instances
+     *    the reference device table (bsim3 < bsim4 < cap < dio < isrc < res < vsrc, dev.c:142-209), instances
      *    in list order, positions in load order */
     c->nstamp_rows = 0;
+    c->b3_spos = (int *)xcalloc((size_t)c->b3_n * B3S_COUNT + 1, sizeof(int));
+    for (i = 0; i < c->b3_n; i++)
+        for (k = 0; k < B3S_COUNT; k++) {
+            const int rr = c->b3_nodes[b3_stamp_r[k] * c->b3_n + i], rc = c->b3_nodes[b3_stamp_c[k] * c->b3_n + i];
+            if (k < B3S_RHS_COUNT) c->b3_spos[k * c->b3_n + i] = new_row(c, &cb, (rr > 0 && c->eq2col[rr] >= 0) ? c->nnz + rr : -1);
+            else c->b3_spos[k * c->b3_n + i] = new_row(c, &cb, slot_lookup(c, rr, rc));
+        }
     c->b4_spos = (int *)xcalloc((size_t)c->b4_n * B4S_TOTAL, sizeof(int));
     c->b4_slots = (int *)xcalloc((size_t)c->b4_n * B4S_MAT_COUNT, sizeof(int));
     for (i = 0; i < c->b4_n; i++) {
@@ -855,6 +935,13 @@ int ngbCircuitSetLuPattern(ngb_circuit *c, int n, int nblocks, const int *Q, con
     }
     free(Pinv); free(pos); free(level);
     build_packed(c);
+    {   /* move the finished set into its slot */
+        struct ngb_luset *L = &c->lu[c->lu_target];
+        if (L->valid) { free_sched(&L->sch); free_packed(&L->pk); }
+        L->sch = c->sch; L->pk = c->pk; L->npairs = c->npairs; L->nsolvepairs = c->nsolvepairs;
+        L->lnz = c->lnz; L->unz = c->unz; L->nzoff = c->nzoff; L->valid = 1;
+        memset(&c->sch, 0, sizeof c->sch); memset(&c->pk, 0, sizeof c->pk);
+    }
     c->have_lu = 1;
     return NGB_OK;
 bad:
@@ -862,11 +949,18 @@ bad:
     return NGB_E_PANIC;
 }
 
+int ngbCircuitSelectLuSet(ngb_circuit *c, int which)
+{
+    if (which < 0 || which > 1) return NGB_E_PANIC;
+    c->lu_target = which;
+    return NGB_OK;
+}
 int ngbCircuitLuInfo(const ngb_circuit *c, int info[9])
 {
-    if (!c->have_lu) return NGB_E_PANIC;
-    info[0] = c->sch.nV; info[1] = c->sch.nlev; info[2] = c->npairs; info[3] = c->sch.ntask;
-    info[4] = c->sch.nslev; info[5] = c->nsolvepairs; info[6] = c->lnz; info[7] = c->unz; info[8] = c->nzoff;
+    const struct ngb_luset *L = &c->lu[c->lu_target];
+    if (!L->valid) return NGB_E_PANIC;
+    info[0] = L->sch.nV; info[1] = L->sch.nlev; info[2] = L->npairs; info[3] = L->sch.ntask;
+    info[4] = L->sch.nslev; info[5] = L->nsolvepairs; info[6] = L->lnz; info[7] = L->unz; info[8] = L->nzoff;
     return NGB_OK;
 }
 
@@ -901,9 +995,10 @@ static void *dalloc_rep(ngb_batch *b, const char *name, const double *host, int 
     return d;
 }
 
-static void sched_to_dev(ngb_batch *b, const ngb_circuit *c)
+static void sched_to_dev(ngb_batch *b, const ngb_circuit *cc, int w)
 {
-    const NgbLuSched *h = &c->sch; NgbLuSched *d = &b->dsch;
+    const struct ngb_luset *c = &cc->lu[w];
+    const NgbLuSched *h = &c->sch; NgbLuSched *d = &b->dlu[w].dsch;
     *d = *h;
 #define D(f, cnt) d->f = (const int *)dev_dup(h->f, sizeof(int) * (size_t)(cnt))
     D(lev_ptr, h->nlev + 1); D(lev_ent, h->nV); D(e_aslot, h->nV); D(e_arow, h->nV); D(e_div, h->nV);
@@ -913,16 +1008,16 @@ static void sched_to_dev(ngb_batch *b, const ngb_circuit *c)
     D(t_val, c->nsolvepairs); D(t_src, c->nsolvepairs); D(b_eq, h->n); D(out_task, h->n); D(out_eq, h->n);
 #undef D
 }
-static void packed_to_dev(ngb_batch *b, const ngb_circuit *c)
+static void packed_to_dev(ngb_batch *b, const ngb_circuit *c, int w)
 {
-    const NgbLuPacked *p = &c->pk; NgbLuPacked *d = &b->dpk;
+    const NgbLuPacked *p = &c->lu[w].pk; NgbLuPacked *d = &b->dlu[w].dpk;
     *d = *p;
     if (!p->ok) return;
     d->blob = (const unsigned short *)dev_dup(p->blob, sizeof(unsigned short) * (size_t)p->blob_u16);
     d->aslot = (const int *)dev_dup(p->aslot, sizeof(int) * (size_t)p->nV);
     d->arow = (const int *)dev_dup(p->arow, sizeof(int) * (size_t)p->nV);
     d->ext = (const int *)dev_dup(p->ext, sizeof(int) * (size_t)p->nV);
-    d->row_ptr = b->dsch.row_ptr; d->row_slot = b->dsch.row_slot; d->b_eq = b->dsch.b_eq; d->out_eq = b->dsch.out_eq;
+    d->row_ptr = b->dlu[w].dsch.row_ptr; d->row_slot = b->dlu[w].dsch.row_slot; d->b_eq = b->dlu[w].dsch.b_eq; d->out_eq = b->dlu[w].dsch.out_eq;
 }
 static void sched_dev_free(NgbLuSched *d)
 {
@@ -962,6 +1057,8 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
     k->lte = (double *)dalloc(b, "ctl.lte", sizeof(double) * (size_t)S);
     k->lte2 = (double *)dalloc(b, "ctl.lte2", sizeof(double) * (size_t)S);
     k->stateop = (int *)dalloc(b, "ctl.stateop", sizeof(int) * (size_t)S);
+    k->lusel = (int *)dalloc(b, "ctl.lusel", sizeof(int) * (size_t)S);
+    if (k->lusel) ngb_dev_memset(k->lusel, 0, sizeof(int) * (size_t)S);
     k->nhist = c->opt.maxorder + 2;
     if (k->nhist > NGB_NHIST) k->nhist = NGB_NHIST;
     k->reltol = c->opt.reltol; k->abstol = c->opt.abstol; k->chgtol = c->opt.chgtol; k->trtol = c->opt.trtol;
@@ -1010,6 +1107,18 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
         b->b4_nodes = (int *)dev_dup(c->b4_nodes, sizeof(int) * (size_t)c->b4_n * B4N_COUNT);
         b->b4_spos = (int *)dev_dup(c->b4_spos, sizeof(int) * (size_t)c->b4_n * B4S_TOTAL);
     }
+    if (c->b3_n) {
+        const size_t T = (size_t)c->b3_n * S;
+        b->b3_inst = (double *)dalloc_rep(b, "b3.inst", c->b3_inst, B3I_COUNT, c->b3_n, S);
+        b->b3_state = (double *)dalloc(b, "b3.state", sizeof(double) * NGB_NHIST * B3ST_COUNT * T);
+        b->b3_von = (double *)dalloc(b, "b3.von", sizeof(double) * T);
+        b->b3_mtab = (double *)dev_dup(c->b3_mtab, sizeof(double) * (size_t)c->b3_nrows * B3M_COUNT);
+        b->b3_ptab = (double *)dev_dup(c->b3_ptab, sizeof(double) * (size_t)c->b3_nrows * B3P_COUNT);
+        b->b3_prow = (int *)dev_dup(c->b3_prow, sizeof(int) * (size_t)c->b3_n);
+        b->b3_flags = (int *)dev_dup(c->b3_flags, sizeof(int) * (size_t)c->b3_n);
+        b->b3_nodes = (int *)dev_dup(c->b3_nodes, sizeof(int) * (size_t)c->b3_n * B3N_COUNT);
+        b->b3_spos = (int *)dev_dup(c->b3_spos, sizeof(int) * (size_t)c->b3_n * B3S_COUNT);
+    }
     if (c->cap_n) {
         const size_t T = (size_t)c->cap_n * S;
         b->cap_par = (double *)dalloc_rep(b, "cap.par", c->cap_par, 3, c->cap_n, S);
@@ -1036,10 +1145,15 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
         b->is_spos = (int *)dev_dup(c->is_spos, sizeof(int) * 2 * (size_t)c->is_n);
     }
     if (c->have_lu) {
-        sched_to_dev(b, c);
-        packed_to_dev(b, c);
-        b->V = (double *)dalloc(b, "lu.V", sizeof(double) * (size_t)c->sch.nV * S);
-        b->Rs = (double *)dalloc(b, "lu.Rs", sizeof(double) * (size_t)c->sch.n * S);
+        int w, nVmax = 0;
+        for (w = 0; w < 2; w++)
+            if (c->lu[w].valid) {
+                sched_to_dev(b, c, w); packed_to_dev(b, c, w); b->dlu[w].valid = 1;
+                if (c->lu[w].sch.nV > nVmax) nVmax = c->lu[w].sch.nV;
+            }
+        b->lu_which = c->lu[0].valid ? 0 : 1;
+        b->V = (double *)dalloc(b, "lu.V", sizeof(double) * (size_t)nVmax * S);
+        b->Rs = (double *)dalloc(b, "lu.Rs", sizeof(double) * (size_t)c->n * S);
         b->nodeconv = (int *)dalloc(b, "lu.nodeconv", sizeof(int) * (size_t)S);
         b->singular = (int *)dalloc(b, "lu.singular", sizeof(int) * (size_t)S);
         b->have_lu = 1;
@@ -1060,10 +1174,16 @@ void ngbBatchDestroy(ngb_batch *b)
     ngb_dev_free(b->b4_nodes); ngb_dev_free(b->b4_spos); ngb_dev_free(b->b4_prow_t);
     ngb_dev_free(b->cap_nodes); ngb_dev_free(b->cap_spos);
     ngb_dev_free(b->dio_nodes); ngb_dev_free(b->dio_flags); ngb_dev_free(b->dio_spos);
+    ngb_dev_free(b->b3_mtab); ngb_dev_free(b->b3_ptab); ngb_dev_free(b->b3_prow); ngb_dev_free(b->b3_flags); ngb_dev_free(b->b3_nodes); ngb_dev_free(b->b3_spos);
     ngb_dev_free(b->vs_fn); ngb_dev_free(b->vs_spos); ngb_dev_free(b->is_fn); ngb_dev_free(b->is_spos);
     if (b->have_lu) {
-        if (b->dpk.ok) { ngb_dev_free((void *)b->dpk.blob); ngb_dev_free((void *)b->dpk.aslot); ngb_dev_free((void *)b->dpk.arow); ngb_dev_free((void *)b->dpk.ext); }
-        sched_dev_free(&b->dsch);
+        int w;
+        for (w = 0; w < 2; w++)
+            if (b->dlu[w].valid) {
+                if (b->dlu[w].dpk.ok) { ngb_dev_free((void *)b->dlu[w].dpk.blob); ngb_dev_free((void *)b->dlu[w].dpk.aslot);
+                                        ngb_dev_free((void *)b->dlu[w].dpk.arow); ngb_dev_free((void *)b->dlu[w].dpk.ext); }
+                sched_dev_free(&b->dlu[w].dsch);
+            }
     }
     ngb_tran_free(b);
     free(b);
@@ -1125,6 +1245,15 @@ void ngb_fill_capctx(ngb_batch *b, NgbCapCtx *x)
     x->ninst = c->cap_n; x->S = b->S; x->T = c->cap_n * b->S; x->nodes = b->cap_nodes; x->par = b->cap_par;
     x->spos = b->cap_spos; x->state = b->cap_state; x->stamp = b->stamp; x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl;
 }
+void ngb_fill_b3ctx(ngb_batch *b, B3Ctx *x)
+{
+    const ngb_circuit *c = b->c;
+    memset(x, 0, sizeof *x);
+    x->ninst = c->b3_n; x->S = b->S; x->T = c->b3_n * b->S; x->mtab = b->b3_mtab; x->ptab = b->b3_ptab; x->prow = b->b3_prow;
+    x->inst = b->b3_inst; x->flags = b->b3_flags; x->nodes = b->b3_nodes; x->spos = b->b3_spos; x->stamp = b->stamp;
+    x->state = b->b3_state; x->von = b->b3_von; x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl;
+    x->temp = c->opt.temp; x->vt0 = c->opt.vt0;
+}
 void ngb_fill_dioctx(ngb_batch *b, NgbDioCtx *x)
 {
     const ngb_circuit *c = b->c;
@@ -1149,11 +1278,11 @@ void ngb_fill_asmctx(ngb_batch *b, NgbAsmCtx *x)
     x->S = b->S; x->nnz = c->nnz; x->neq1 = b->neq1; x->tgt_ptr = b->d_tgt_ptr; x->tgt_rows = b->d_tgt_rows;
     x->slot_diag = b->d_slot_diag; x->stamp = b->stamp; x->Ax = b->Ax; x->x = b->x; x->add_diag_gmin = 1; x->ctl = b->ctl;
 }
-void ngb_fill_luctx(ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve)
+void ngb_fill_luctx(ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve, int which)
 {
     const ngb_circuit *c = b->c;
     memset(x, 0, sizeof *x);
-    x->sch = b->dsch; x->pk = b->dpk; x->S = b->S; x->neq1 = b->neq1; x->Ax = b->Ax; x->V = b->V; x->Rs = b->Rs; x->x = b->x;
+    x->sch = b->dlu[which].dsch; x->pk = b->dlu[which].dpk; x->which = which; x->S = b->S; x->neq1 = b->neq1; x->Ax = b->Ax; x->V = b->V; x->Rs = b->Rs; x->x = b->x;
     x->do_factor = do_factor; x->do_solve = do_solve; x->node_type = b->d_node_type;
     x->reltol = c->opt.reltol; x->abstol = c->opt.abstol; x->vntol = c->opt.vntol;
     x->nodeconv = b->nodeconv; x->singular_col = b->singular; x->ctl = b->ctl;
@@ -1171,6 +1300,7 @@ int ngb_enqueue_load(ngb_batch *b)
 {
     const ngb_circuit *c = b->c;
     int r;
+    if (c->b3_n) { B3Ctx x; ngb_fill_b3ctx(b, &x); if ((r = ngb_launch_bsim3_load(&x, b->errflag))) return r; }
     if (c->b4_n) { B4Ctx x; ngb_fill_b4ctx(b, &x); if ((r = ngb_launch_bsim4_load(&x, b->errflag))) return r; }
     if (c->cap_n) { NgbCapCtx x; ngb_fill_capctx(b, &x); if ((r = ngb_launch_cap_load(&x, b->errflag))) return r; }
     if (c->dio_n) { NgbDioCtx x; ngb_fill_dioctx(b, &x); if ((r = ngb_launch_dio_load(&x, b->errflag))) return r; }
@@ -1193,7 +1323,8 @@ static int lu_call(ngb_batch *b, int f, int s)
 {
     NgbLuCtx x; int r;
     if (!b->have_lu) { ngb_set_error("no LU pattern: call ngbCircuitSetLuPattern or ngbCircuitAnalyze before ngbBatchCreate"); return NGB_E_PANIC; }
-    ngb_fill_luctx(b, &x, f, s);
+    ngb_fill_luctx(b, &x, f, s, b->lu_which);
+    x.ctl.lusel = NULL;                                   /* direct calls: every active sample, on the selected set */
     if (s) ngb_launch_clear_i32(b->nodeconv, 0, b->S);
     if ((r = ngb_launch_lu(&x))) return r;
     return ngb_dev_sync();

@@ -4,6 +4,7 @@
 #include "ngb_types.h"
 #include "bsim4_eval.cuh"
 #include "dio_eval.cuh"
+#include "bsim3_eval.cuh"
 
 #ifdef __cplusplus
 extern "C" {
@@ -19,6 +20,7 @@ struct ngb_circuit {
     int *b4_spos, *b4_slots;
     int res_n; int *res_nodes; double *res_g; int *res_spos;
     int cap_n; int *cap_nodes; double *cap_par; int *cap_spos;
+    int b3_n, b3_nrows; int *b3_nodes, *b3_flags, *b3_prow; double *b3_inst, *b3_mtab, *b3_ptab; int *b3_spos;
     int dio_n; int *dio_nodes, *dio_flags; double *dio_par; int *dio_spos;
     int vs_n; int *vs_nodes, *vs_fn; double *vs_par; int *vs_spos, *vs_cspos;
     int is_n; int *is_nodes, *is_fn; double *is_par; int *is_spos;
@@ -30,8 +32,12 @@ struct ngb_circuit {
     /* LU: imported or own symbolic objects + task schedule */
     int klu_nblocks; int *klu_Q, *klu_R, *klu_Pnum;
     int lnz, unz, nzoff, npairs, nsolvepairs;
-    NgbLuSched sch;                /* host arrays */
+    NgbLuSched sch;                /* host arrays (set being built) */
     NgbLuPacked pk;                /* host arrays, level-contiguous 16-bit form */
+    /* finished pattern sets: [0] from the first pivoting factor, [1] (optional) from the re-pivoting of
+     * the first transient iteration; lu_target selects which one ngbCircuitSetLuPattern fills */
+    struct ngb_luset { NgbLuSched sch; NgbLuPacked pk; int npairs, nsolvepairs, lnz, unz, nzoff, valid; } lu[2];
+    int lu_target;
 };
 
 #define NGB_MAX_ARR 64
@@ -45,11 +51,12 @@ struct ngb_batch {
     int *d_node_type, *d_tgt_ptr, *d_tgt_rows, *d_slot_diag;
     double *b4_inst, *b4_state, *b4_op, *b4_mtab, *b4_ptab; int *b4_prow, *b4_prow_t, *b4_flags, *b4_nodes, *b4_spos;
     double *cap_par, *cap_state; int *cap_nodes, *cap_spos;
+    double *b3_inst, *b3_state, *b3_von, *b3_mtab, *b3_ptab; int *b3_prow, *b3_flags, *b3_nodes, *b3_spos;
     double *dio_par, *dio_state; int *dio_nodes, *dio_flags, *dio_spos;
     double *vs_par; int *vs_fn, *vs_spos;
     double *is_par; int *is_fn, *is_spos;
-    NgbLuSched dsch;               /* device arrays */
-    NgbLuPacked dpk;
+    struct { NgbLuSched dsch; NgbLuPacked dpk; int valid; } dlu[2];   /* device arrays per pattern set */
+    int lu_which;                  /* set used by the direct ngbLuFac/ngbSolve calls */
     double *V, *Rs; int *nodeconv, *singular;
     struct { const char *name; void *ptr; size_t bytes; } arr[NGB_MAX_ARR];
     int narr;
@@ -60,9 +67,10 @@ void ngb_set_error(const char *fmt, ...);
 void ngb_fill_b4ctx(struct ngb_batch *b, B4Ctx *x);
 void ngb_fill_capctx(struct ngb_batch *b, NgbCapCtx *x);
 void ngb_fill_dioctx(struct ngb_batch *b, NgbDioCtx *x);
+void ngb_fill_b3ctx(struct ngb_batch *b, B3Ctx *x);
 void ngb_fill_srcctx(struct ngb_batch *b, NgbSrcCtx *x, int is_current);
 void ngb_fill_asmctx(struct ngb_batch *b, NgbAsmCtx *x);
-void ngb_fill_luctx(struct ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve);
+void ngb_fill_luctx(struct ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve, int which);
 int ngb_enqueue_load(struct ngb_batch *b);
 void ngb_tran_free(struct ngb_batch *b);
 int ngbBatchSetBsim4Rows(struct ngb_batch *b, const int *prow_t, int nrows, const double *mtab, const double *ptab);

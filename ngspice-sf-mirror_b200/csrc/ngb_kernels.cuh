@@ -223,6 +223,7 @@ NGB_HD void ngb_lu_sample(const NgbLuCtx *c, int s, int lane, int nl, double *V,
     const int S = c->S, n = h->n, nV = h->nV;
     const int active = NGB_LDG(&c->ctl.active[s]);
     if (!active) return;
+    if (c->ctl.lusel && NGB_LDG(&c->ctl.lusel[s]) != c->which) return;
     const double *Ax = c->Ax + (size_t)s * h->nnz;
 
     if (c->do_factor) {
@@ -355,6 +356,7 @@ NGB_HD void ngb_lu_sample_packed(const NgbLuCtx *c, const unsigned short *sb, in
     const NgbLuPacked *h = &c->pk;
     const int S = c->S, n = h->n, nV = h->nV;
     if (!NGB_LDG(&c->ctl.active[s])) return;
+    if (c->ctl.lusel && NGB_LDG(&c->ctl.lusel[s]) != c->which) return;
 
     if (c->do_factor) {
         /* the sample's matrix into shared memory: one coalesced sweep */

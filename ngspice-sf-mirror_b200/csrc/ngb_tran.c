@@ -18,6 +18,7 @@ struct ngb_tran {
     int max_points, nsave;
     int *d_save_eq;
     long ticks;
+    int dc_over;               /* every sample has left the DC operating point (pattern set 0 idle) */
 };
 
 static void *dz(size_t bytes) { return ngb_dev_malloc(bytes ? bytes : 8); }
@@ -70,6 +71,7 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     t->max_points = max_points; t->nsave = nsave;
     x->tstep = c->opt.tstep; x->tstop = c->opt.tstop; x->tmax = c->opt.tmax; x->tstart = c->opt.tstart;
     x->delmin = c->opt.delmin; x->minbreak = c->opt.minbreak; x->xmu = c->opt.xmu;
+    x->nluset = b->dlu[1].valid ? 2 : 1;
     x->maxorder = c->opt.maxorder; x->uic = c->opt.uic; x->max_iter_tran = c->opt.itl4; x->max_iter_dc = c->opt.itl1;
     if (x->minbreak == 0) x->minbreak = x->tmax * 5e-5;            /* dctran.c:163-164 */
 
@@ -96,6 +98,7 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
         ngb_dev_h2d(b->ctl.noncon, iv, sizeof(int) * S);
         ngb_dev_h2d(b->ctl.err, iv, sizeof(int) * S);
         ngb_dev_h2d(b->ctl.stateop, iv, sizeof(int) * S);
+        ngb_dev_h2d(b->ctl.lusel, iv, sizeof(int) * S);
         ngb_dev_h2d(b->nodeconv, iv, sizeof(int) * S);
         for (i = 0; i < NGB_MAXBRK; i++) for (s = 0; s < S; s++) dv[(size_t)i * S + s] = (i == 0) ? 0.0 : c->opt.tstop;
         ngb_dev_h2d(x->breaks, dv, sizeof(double) * NGB_MAXBRK * S);
@@ -111,6 +114,8 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     ngb_launch_fill_f64(b->ctl.lte2, 1e300, S);
     ngb_dev_memset(b->x, 0, sizeof(double) * 2 * (size_t)b->neq1 * S);
     if (b->b4_state) ngb_dev_memset(b->b4_state, 0, sizeof(double) * NGB_NHIST * B4ST_COUNT * (size_t)c->b4_n * S);
+    if (b->b3_state) { ngb_dev_memset(b->b3_state, 0, sizeof(double) * NGB_NHIST * B3ST_COUNT * (size_t)c->b3_n * S);
+                       ngb_dev_memset(b->b3_von, 0, sizeof(double) * (size_t)c->b3_n * S); }
     if (b->dio_state) ngb_dev_memset(b->dio_state, 0, sizeof(double) * NGB_NHIST * DIOST_COUNT * (size_t)c->dio_n * S);
     if (b->cap_state) ngb_dev_memset(b->cap_state, 0, sizeof(double) * NGB_NHIST * 2 * (size_t)c->cap_n * S);
     if (b->b4_op) ngb_dev_memset(b->b4_op, 0, sizeof(double) * B4O_COUNT * (size_t)c->b4_n * S);
@@ -122,10 +127,16 @@ static int enqueue_tick(ngb_batch *b, int with_lu)
     int r;
     if ((r = ngb_enqueue_load(b))) return r;
     if (with_lu) {
-        NgbLuCtx lx;
-        ngb_fill_luctx(b, &lx, 1, 1);
-        lx.V = NULL;                       /* fused factor+solve: the factors never leave shared memory */
-        if ((r = ngb_launch_lu(&lx))) return r;
+        int w;
+        for (w = 0; w < 2; w++) {
+            NgbLuCtx lx;
+            if (!b->dlu[w].valid) continue;
+            if (w == 0 && b->dlu[1].valid && b->tran->dc_over) continue;   /* every sample has re-pivoted: set 0 is idle */
+            ngb_fill_luctx(b, &lx, 1, 1, w);
+            if (!b->dlu[1].valid) lx.ctl.lusel = NULL;                     /* one set: no per-sample selection */
+            lx.V = NULL;                       /* fused factor+solve: the factors never leave shared memory */
+            if ((r = ngb_launch_lu(&lx))) return r;
+        }
     }
     return ngb_launch_tran_control(&b->tran->x);
 }
@@ -151,6 +162,7 @@ int ngbTranRun(ngb_batch *b, int max_points, const int *save_eq, int nsave)
         for (i = 0; i < check_every; i++, tick++)
             if ((r = enqueue_tick(b, 1))) return r;
         ngb_dev_d2h(done, b->tran->x.ndone, sizeof(int) * 2);
+        if (done[1] >= S) b->tran->dc_over = 1;
         ngb_dev_d2h(e, b->errflag, sizeof e);
         if (e[0]) { ngb_set_error("device load reported error %d", e[0]); return e[0]; }
         if (done[0] >= S) break;

@@ -50,6 +50,7 @@ typedef struct NgbTranCtx {
     /* circuit scalars */
     double tstep, tstop, tmax, tstart, delmin, minbreak, xmu;
     int maxorder, uic, max_iter_tran, max_iter_dc;
+    int nluset;                /* 2: the first transient iteration re-pivots onto pattern set 1 */
 } NgbTranCtx;
 
 NGB_HD int ngb_almost_equal_ulps(double A, double B, int maxUlps)
@@ -325,6 +326,13 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
         c->ctl.mode[s] = (mode & NGB_MODEUIC) | NGB_MODETRAN | NGB_MODEINITTRAN;
         c->ctl.ag0[s] = 0; c->ctl.ag1[s] = 0;
         c->ctl.stateop[s] = NGB_OP_COPY01;
+        /* NIiter re-pivots in the first iteration under MODEINITTRAN (niiter.c:107-111) */
+        if (c->nluset > 1) c->ctl.lusel[s] = 1;
+#ifdef __CUDA_ARCH__
+        atomicAdd(c->ndone + 1, 1);
+#else
+        c->ndone[1] += 1;
+#endif
         ngb_next_time(c, s);
         return;
     }

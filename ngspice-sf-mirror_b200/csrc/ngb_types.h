@@ -39,6 +39,8 @@ typedef struct NgbCtl {
      * lte for the current CKTorder, lte2 for a trial with order 2 (dctran.c:794, 823) */
     double *lte, *lte2;
     int *stateop;         /* pending whole-state copies, applied by the next load (NGB_OP_*) */
+    int *lusel;           /* which LU pattern set the sample is on: 0 = first pivoting factor (DC op),
+                             1 = the re-pivoting of the first transient iteration (niiter.c:107-111)   */
     /* shared scalars */
     int nhist;            /* state vectors in the ring: CKTmaxOrder + 2 (cktsetup.c:192)  */
     double reltol, abstol, chgtol, trtol;
@@ -151,6 +153,7 @@ typedef struct NgbLuCtx {
     double *Rs;             /* [S][n]                                                    */
     double *x;              /* rhs in x[1 - xsel], overwritten by the solution           */
     int do_factor, do_solve;
+    int which;              /* pattern set of this launch: samples with ctl.lusel != which are skipped */
     /* node convergence test of NIconvTest fused after the solve */
     const int *node_type;   /* [neq1] SP_VOLTAGE(3) / SP_CURRENT(4)                      */
     double reltol, abstol, vntol;

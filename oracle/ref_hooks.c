@@ -34,6 +34,7 @@
 #include "vsrc/vsrcdefs.h"
 #include "isrc/isrcdefs.h"
 #include "dio/diodefs.h"
+#include "bsim3/bsim3def.h"
 #include "klu_internal.h"
 #include <stdio.h>
 #include <stdlib.h>
@@ -41,6 +42,7 @@
 
 #include "../ngspice-sf-mirror_b200/csrc/bsim4_fields.h"
 #include "../ngspice-sf-mirror_b200/csrc/dio_fields.h"
+#include "../ngspice-sf-mirror_b200/csrc/bsim3_fields.h"
 
 extern SPICEdev **DEVices;
 extern int DEVmaxnum;
@@ -95,7 +97,7 @@ static int slot_of(KLUmatrix *K, double *p)
     return -1;     /* trash cell (ground row/column) */
 }
 
-static int b4_type = -2, res_type, cap_type, vsrc_type, isrc_type, dio_type;
+static int b4_type = -2, res_type, cap_type, vsrc_type, isrc_type, dio_type, b3_type;
 static void lookup_types(void)
 {
     if (b4_type != -2) return;
@@ -105,6 +107,7 @@ static void lookup_types(void)
     vsrc_type = CKTtypelook("Vsource");
     isrc_type = CKTtypelook("Isource");
     dio_type = CKTtypelook("Diode");
+    b3_type = CKTtypelook("BSIM3");
 }
 
 /* ---------------------------------------------------------------- flat circuit dump */
@@ -295,6 +298,69 @@ static void dump_linear(FILE *f, CKTcircuit *ckt, KLUmatrix *K)
     put_is(f, "isrc/n", n);
 }
 
+/* BSIM3v3.3.0 instances: the same three-table form as BSIM4 (bsim3_fields.h) */
+typedef struct { BSIM3model *m; struct bsim3SizeDependParam *p; } b3row_t;
+static void dump_bsim3(FILE *f, CKTcircuit *ckt, KLUmatrix *K)
+{
+    BSIM3model *model; BSIM3instance *here;
+    int n = 0, nrows = 0, i, r;
+    b3row_t *rows; int *nodes, *slots, *flags, *sbase, *prow; double *inst, *mtab, *ptab;
+    char *names; size_t nb = 0;
+    if (b3_type < 0 || !ckt->CKThead[b3_type]) { put_is(f, "b3/ninst", 0); return; }
+    for (model = (BSIM3model *)ckt->CKThead[b3_type]; model; model = BSIM3nextModel(model))
+        for (here = BSIM3instances(model); here; here = BSIM3nextInstance(here)) n++;
+    rows = (b3row_t *)calloc((size_t)n + 1, sizeof(b3row_t));
+    nodes = (int *)calloc((size_t)n * B3N_COUNT + 1, sizeof(int));
+    slots = (int *)calloc((size_t)n * (B3S_COUNT - B3S_RHS_COUNT) + 1, sizeof(int));
+    flags = (int *)calloc((size_t)n + 1, sizeof(int)); sbase = (int *)calloc((size_t)n + 1, sizeof(int));
+    prow = (int *)calloc((size_t)n + 1, sizeof(int));
+    inst = (double *)calloc((size_t)n * B3I_COUNT + 1, sizeof(double));
+    names = (char *)calloc((size_t)n * 64 + 1, 1);
+    i = 0;
+    for (model = (BSIM3model *)ckt->CKThead[b3_type]; model; model = BSIM3nextModel(model))
+        for (here = BSIM3instances(model); here; here = BSIM3nextInstance(here), i++) {
+            int k = 0;
+            nodes[0 * n + i] = here->BSIM3dNode; nodes[1 * n + i] = here->BSIM3gNode; nodes[2 * n + i] = here->BSIM3sNode;
+            nodes[3 * n + i] = here->BSIM3bNode; nodes[4 * n + i] = here->BSIM3dNodePrime; nodes[5 * n + i] = here->BSIM3sNodePrime;
+#define X(nm, rr, cc) if (k >= B3S_RHS_COUNT) slots[(k - B3S_RHS_COUNT) * n + i] = slot_of(K, here->BSIM3##nm##Ptr); k++;
+#define BSIM3rGPtr BSIM3GgPtr
+#define BSIM3rBPtr BSIM3GgPtr
+#define BSIM3rDPPtr BSIM3GgPtr
+#define BSIM3rSPPtr BSIM3GgPtr
+            NGB_B3_STAMPS(X)
+#undef X
+            k = 0;
+#define X(nm) inst[(size_t)(k++) * n + i] = (double)here->BSIM3##nm;
+            NGB_B3_INST_FIELDS(X)
+#undef X
+            flags[i] = (here->BSIM3off ? B3F_OFF : 0) | ((here->BSIM3nqsMod || here->BSIM3acnqsMod) ? B3F_NQS : 0);
+            sbase[i] = here->BSIM3states;
+            for (r = 0; r < nrows; r++) if (rows[r].m == model && rows[r].p == here->pParam) break;
+            if (r == nrows) { rows[nrows].m = model; rows[nrows].p = here->pParam; nrows++; }
+            prow[i] = r;
+            nb += (size_t)snprintf(names + nb, 64, "%s\n", here->BSIM3name);
+        }
+    mtab = (double *)calloc((size_t)nrows * B3M_COUNT + 1, sizeof(double));
+    ptab = (double *)calloc((size_t)nrows * B3P_COUNT + 1, sizeof(double));
+    for (r = 0; r < nrows; r++) {
+        int k = 0; BSIM3model *m = rows[r].m; struct bsim3SizeDependParam *pParam = rows[r].p;
+#define X(nm) mtab[(size_t)r * B3M_COUNT + (k++)] = (double)m->BSIM3##nm;
+        NGB_B3_MODEL_FIELDS(X)
+#undef X
+        k = 0;
+#define X(nm) ptab[(size_t)r * B3P_COUNT + (k++)] = (double)pParam->BSIM3##nm;
+        NGB_B3_BIN_FIELDS(X)
+#undef X
+    }
+    put_is(f, "b3/ninst", n);
+    put_i2(f, "b3/nodes", nodes, B3N_COUNT, n); put_i2(f, "b3/slots", slots, B3S_COUNT - B3S_RHS_COUNT, n);
+    put_d2(f, "b3/inst", inst, B3I_COUNT, n); put_i1(f, "b3/flags", flags, n); put_i1(f, "b3/state_base", sbase, n);
+    put_i1(f, "b3/prow", prow, n); put_d2(f, "b3/mtab", mtab, nrows, B3M_COUNT); put_d2(f, "b3/ptab", ptab, nrows, B3P_COUNT);
+    { int *nb_i = (int *)calloc(nb + 1, sizeof(int)); size_t q; for (q = 0; q < nb; q++) nb_i[q] = (unsigned char)names[q];
+      put_i1(f, "b3/names_bytes", nb_i, (long long)nb); free(nb_i); }
+    free(rows); free(nodes); free(slots); free(flags); free(sbase); free(prow); free(inst); free(mtab); free(ptab); free(names);
+}
+
 /* diodes: node numbers, flags and the DIOtemp results DIOload reads (dio_fields.h) */
 static void dump_dio(FILE *f, CKTcircuit *ckt, KLUmatrix *K)
 {
@@ -413,6 +479,7 @@ static void dump_flat(CKTcircuit *ckt, const char *path)
     dump_bsim4(f, ckt, K);
     dump_linear(f, ckt, K);
     dump_dio(f, ckt, K);
+    dump_bsim3(f, ckt, K);
     fclose(f);
     free(ntype); free(nic); free(nicg); free(names);
 }
@@ -587,6 +654,15 @@ int __wrap_CKTload(CKTcircuit *ckt)
         tname(nm, "state0_in"); put_d1(trace_f, nm, ckt->CKTstate0, ckt->CKTnumStates);
         tname(nm, "state1_in"); put_d1(trace_f, nm, ckt->CKTstate1, ckt->CKTnumStates);
         if (ckt->CKTstate2) { tname(nm, "state2_in"); put_d1(trace_f, nm, ckt->CKTstate2, ckt->CKTnumStates); }
+        if (b3_type >= 0 && ckt->CKThead[b3_type]) {       /* previous-iterate von: input of DEVfetlim */
+            BSIM3model *m; BSIM3instance *hh; int n3 = 0, q = 0; double *v;
+            for (m = (BSIM3model *)ckt->CKThead[b3_type]; m; m = BSIM3nextModel(m))
+                for (hh = BSIM3instances(m); hh; hh = BSIM3nextInstance(hh)) n3++;
+            v = (double *)calloc((size_t)n3 + 1, sizeof(double));
+            for (m = (BSIM3model *)ckt->CKThead[b3_type]; m; m = BSIM3nextModel(m))
+                for (hh = BSIM3instances(m); hh; hh = BSIM3nextInstance(hh)) v[q++] = hh->BSIM3von;
+            tname(nm, "b3_von_in"); put_d1(trace_f, nm, v, n3); free(v);
+        }
     }
     err = __real_CKTload(ckt);
     if (call_selected) {

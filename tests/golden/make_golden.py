@@ -8,6 +8,7 @@ and test files.  Needs /root/reference; the fixtures it writes do not.
          that runs (4.5.0 would select the separate bsim4v5 device), `.option xmu=0.49 klu`.
   ro101  same cards, 101 stages (BASELINE config 2).
   inv    tests/bsim4/{nmos,pmos}/parameters cards, CMOS inverter with PULSE input (config 1).
+  b3ring BSIM3v3.3.0 ring of five inverters + buffer on the MC_ring.sp level-8 cards.
   dio    junction diodes (rectifier, zener clamp, sidewall/tunnel/knee parameters) with R, C, SIN source.
 
 Outputs (tests/golden/): <name>.flat.ngt  flattened circuit after CKTsetup/CKTtemp
@@ -105,6 +106,32 @@ def dio_netlist():
         ".end", ""])
 
 
+def b3_cards():
+    """the level-8 (BSIM3v3.3.0) n1/p1 cards of examples/Monte_Carlo/MC_ring.sp"""
+    src = open(os.path.join(REF, "examples/Monte_Carlo/MC_ring.sp")).read()
+    i = src.index(".model n1 nmos")
+    j = src.index(".end", i)
+    return src[i:j]
+
+
+def b3_netlist(stages=5):
+    """BSIM3 ring of inverters (cells of MC_ring.sp: w/l/as/ad/ps/pd as there) kicked by the same
+    PULSE source MC_ring.sp uses between input and output, plus an output buffer and load"""
+    lines = ["* BSIM3v3.3.0 ring of inverters (MC_ring.sp cells)",
+             "vin in out dc 0.5 pulse 0.5 0 0.1n 5n 1 1 1",
+             "vdd dd 0 dc 3.3", "vss ss 0 dc 0", "ve sub 0 dc 0", "vpe well 0 dc 3.3"]
+    prev = "in"
+    for k in range(1, stages + 1):
+        nxt = "out" if k == stages else f"n{k}"
+        lines.append(f"mn{k} {nxt} {prev} ss sub n1 w=2u l=0.35u as=3p ad=3p ps=4u pd=4u")
+        lines.append(f"mp{k} {nxt} {prev} dd well p1 w=4u l=0.35u as=7p ad=7p ps=6u pd=6u")
+        prev = nxt
+    lines += ["mnb buf out 0 sub n1 w=2u l=0.35u as=3p ad=3p ps=4u pd=4u",
+              "mpb buf out dd well p1 w=4u l=0.35u as=7p ad=7p ps=6u pd=6u",
+              "cout buf ss 0.2pF", ".option klu", ".tran 0.05n 20n"]
+    return "\n".join(lines) + "\n" + b3_cards() + "\n.end\n"
+
+
 def read_raw(path):
     data = open(path, "rb").read()
     i = data.index(b"Binary:\n")
@@ -125,7 +152,7 @@ def run(name, netlist, calls, save):
     os.makedirs(TMP, exist_ok=True)
     cir = os.path.join(TMP, name + ".cir")
     open(cir, "w").write(netlist)
-    if name in ("ro17", "ro101", "ro17k", "inv", "dio"):
+    if name in ("ro17", "ro101", "ro17k", "inv", "dio", "b3ring"):
         # the netlist itself is kept too: the CPU-baseline arm of bench.py feeds it to oracle/_ref/ngspice
         os.makedirs(os.path.join(HERE, "netlists"), exist_ok=True)
         open(os.path.join(HERE, "netlists", name + ".cir"), "w").write(netlist)
@@ -182,5 +209,7 @@ if __name__ == "__main__":
         run("inv", inv_netlist(), "0-40,100,101,300,301", ["out", "in", "vdd#branch", "vin#branch"])
     if "dio" in which:
         run("dio", dio_netlist(), "0-30,200,201,1000,1001,2000", ["out", "z", "w", "vin#branch"])
+    if "b3ring" in which:
+        run("b3ring", b3_netlist(5), "0-40,300,301,1000,1001", ["out", "buf", "n2", "vdd#branch"])
     if "ro101" in which:
         run("ro101", ro_netlist(101), "1,2,3000", ["102", "2", "50", "vdd#branch"])

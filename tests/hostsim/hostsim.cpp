@@ -39,6 +39,12 @@ int ngb_launch_cap_load(const NgbCapCtx *c, int *errflag)
     for (size_t t = 0; t < (size_t)c->T; t++) { int e = ngb_cap_thread(c, t); if (e && errflag && !errflag[0]) errflag[0] = e; }
     return 0;
 }
+int ngb_launch_bsim3_load(const B3Ctx *c, int *errflag)
+{
+    g_launches++;
+    for (size_t t = 0; t < (size_t)c->T; t++) { int e = b3_load_thread(c, t); if (e && errflag && !errflag[0]) errflag[0] = e; }
+    return 0;
+}
 int ngb_launch_dio_load(const NgbDioCtx *c, int *errflag)
 {
     g_launches++;

@@ -27,6 +27,19 @@ def first_pattern(trace):
     return {kk[len(pre):]: v for kk, v in trace.items() if kk.startswith(pre)}
 
 
+def run_patterns(trace):
+    """the pivoting factors a complete run needs: the first one, plus the one of the first iteration
+    under MODEINITTRAN when the run started with a DC operating point and the pivots changed"""
+    ks = sorted({int(k.split("/")[0][1:]) for k in trace if k.endswith("/pat/n")})
+    first = pattern_at(trace, ks[0])
+    for k in ks[1:]:
+        if int(trace[f"c{k}/mode"][0]) & 0x1000:            # MODEINITTRAN
+            p = pattern_at(trace, k)
+            same = all(np.array_equal(first[q], p[q]) for q in ("Pnum", "Q", "Lp", "Li", "Up", "Ui", "Offp", "Offi"))
+            return [first] if same else [first, p]
+    return [first]
+
+
 def pattern_at(trace, call):
     pre = f"c{call}/pat/"
     d = {kk[len(pre):]: v for kk, v in trace.items() if kk.startswith(pre)}
@@ -43,6 +56,9 @@ def state_maps(flat, lib):
     n = ngt.scalar(flat, "cap/n", 0)
     if n:
         out["cap"] = flat["cap/state_base"][None, :] + np.arange(2)[:, None]
+    n = ngt.scalar(flat, "b3/ninst", 0)
+    if n:
+        out["b3"] = flat["b3/state_base"][None, :] + np.arange(lib.b3_layout[5])[:, None]
     n = ngt.scalar(flat, "dio/n", 0)
     if n:
         out["dio"] = flat["dio/state_base"][None, :] + np.arange(lib.dio_layout[1])[:, None]
@@ -76,7 +92,7 @@ def replay_load(lib, circ, flat, trace, call, S=1, batch=None):
     b.put("x", x)
     maps = state_maps(flat, lib)
     hist = [trace[c + "state0_in"], trace[c + "state1_in"], trace.get(c + "state2_in")]
-    for dev, key in (("b4", "b4.state"), ("cap", "cap.state"), ("dio", "dio.state")):
+    for dev, key in (("b4", "b4.state"), ("cap", "cap.state"), ("dio", "dio.state"), ("b3", "b3.state")):
         if dev not in maps:
             continue
         m = maps[dev]                                  # [k][n]
@@ -93,6 +109,8 @@ def replay_load(lib, circ, flat, trace, call, S=1, batch=None):
         op[0] = op_in[0][:, None]                      # von is the only field the load reads back
         b.put("b4.op", op)
         b.set_op_full(True)
+    if "b3" in maps:
+        b.put("b3.von", np.repeat(trace[c + "b3_von_in"][:, None], S, axis=1))
     b.load()
     ours = dict(Ax=b.get("Ax", (S, -1)), x=b.get("x", (2, neq1, S)), noncon=b.get("ctl.noncon"))
     if "b4" in maps:
@@ -100,6 +118,8 @@ def replay_load(lib, circ, flat, trace, call, S=1, batch=None):
         ours["b4_op"] = b.get("b4.op", (lib.layout[7], maps["b4"].shape[1], S))
     if "cap" in maps:
         ours["cap_state"] = b.get("cap.state", (4,) + maps["cap"].shape + (S,))
+    if "b3" in maps:
+        ours["b3_state"] = b.get("b3.state", (4,) + maps["b3"].shape + (S,))
     if "dio" in maps:
         ours["dio_state"] = b.get("dio.state", (4,) + maps["dio"].shape + (S,))
     ref = dict(Ax=trace[c + "Ax"], rhs=trace[c + "rhs"][:neq1], noncon=int(trace[c + "noncon"][0]),

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 from parity_util import GOLDEN, ngt, pkg, relerr, replay_load, trace_calls, first_pattern
 
-CASES = ["ro17", "ro101", "inv", "dio"]      # inv: DC operating point (INITJCT/INITFIX/INITFLOAT) + PULSE transient
+CASES = ["ro17", "ro101", "inv", "dio", "b3ring"]      # inv: DC operating point (INITJCT/INITFIX/INITFLOAT) + PULSE transient
 
 
 def _load_case(name):
@@ -55,6 +55,12 @@ def _check(lib, name, tol_state, tol_mat, S=1, tol_scaled=None):
             assert relerr(ours["x"][1, 1:, s], ref["rhs"][1:], 1e-300).max() <= tol_mat, (name, call, "rhs")
             if "cap" in maps:
                 assert relerr(ours["cap_state"][0, :, :, s], ref["state0"][maps["cap"]], 1e-300).max() <= tol_state
+            if "b3" in maps:
+                used = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 16]        # the NQS states 12-15 stay untouched
+                assert relerr(ours["b3_state"][0, :, :, s][used], ref["state0"][maps["b3"]][used], 1e-300).max() <= tol_state, (name, call, "b3 state0")
+                if ref["mode"] & 0x1000 and ref["state1"] is not None:
+                    qrows = [4, 5, 6, 7, 8, 9]
+                    assert relerr(ours["b3_state"][1, :, :, s][qrows], ref["state1"][maps["b3"]][qrows], 1e-300).max() <= tol_state
             if "dio" in maps:
                 assert relerr(ours["dio_state"][0, :, :, s], ref["state0"][maps["dio"]], 1e-300).max() <= tol_state, (name, call, "dio state0")
                 if ref["mode"] & 0x1000 and ref["state1"] is not None:

@@ -8,14 +8,14 @@ be compared point by point; the deterministic-start variants (ro17k, Monte-Carlo
 agree within 1e-9 of the waveform range with identical accepted/rejected/iteration counts."""
 import numpy as np
 import pytest
-from parity_util import GOLDEN, ngt, pkg, first_pattern
+from parity_util import run_patterns, GOLDEN, ngt, pkg, first_pattern
 
 
 def _run(lib, name, S=1, inst=None, max_points=8192):
     flat = ngt.read(f"{GOLDEN}/{name}.flat.ngt")
     trace = ngt.read(f"{GOLDEN}/{name}.trace.ngt.gz")
     wave = ngt.read(f"{GOLDEN}/{name}.wave.ngt")
-    circ = pkg.Circuit.from_flat(lib, flat, lu_pattern=first_pattern(trace))
+    circ = pkg.Circuit.from_flat(lib, flat, lu_pattern=run_patterns(trace))
     b = pkg.Batch(circ, S)
     if inst is not None:
         b.put("b4.inst", inst)
@@ -39,7 +39,7 @@ def _compare(res, t, v, wave, s, exact, tol=1e-9):
         assert (err <= tol).all(), err
 
 
-@pytest.mark.parametrize("name", ["ro17", "ro17k", "inv", "dio"])
+@pytest.mark.parametrize("name", ["ro17", "ro17k", "inv", "dio", "b3ring"])
 def test_tran_hostsim_bit_identical(hostsim_lib, name):
     res, t, v, wave = _run(hostsim_lib, name)
     _compare(res, t, v, wave, 0, exact=True)
@@ -82,7 +82,7 @@ def test_tran_hostsim_mc_batch(hostsim_lib):
 # device follows the reference bit for bit; the assertions below allow 1e-9 (the north_star
 # tolerance) but identical accepted / rejected / iteration counts are required.
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,exact", [("ro17k", True), ("ro17", True), ("inv", True), ("dio", False)])
+@pytest.mark.parametrize("name,exact", [("ro17k", True), ("ro17", True), ("inv", True), ("dio", False), ("b3ring", True)])
 def test_tran_gpu_matches_reference(cuda_lib, name, exact):
     """north_star bar: 1e-9 relative and identical accepted-step count; the device arithmetic
     (no FMA contraction, glibc-compatible exp/log) in fact reproduces the reference bit for bit.
