@@ -164,6 +164,19 @@ def bench_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    if args.workload == "array":
+        r = array_cpu_baseline(cores)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ngspice not built"}))
+            return
+        print(json.dumps({
+            "impl": "reference", "metric": "BSIM4 instance-evals/s", "value": r[0], "unit": "evals/s", "n_gpus": args.gpus,
+            "steps": 1, "warmup": 0, "ms_per_step": r[1] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "flat BSIM4 inverter array with RC links (config 4), CKTload only"},
+            "cpu_baseline": {"value": r[0], "unit": "evals/s", "cores": cores, "kind": "reference", "sample": r[2]},
+            "e2e": {"value": r[0], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
     vals = []
     steps = max(1, min(args.steps, 3))
     t_all = []
@@ -350,17 +363,161 @@ def bench_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------ config 4: one large flat circuit
+def array_cpu_baseline(nproc, nx=32, ny=32):
+    """reference ngspice on an nx-by-ny instance of the same generator, one process per core; evals/s
+    from its own STATloadTime ("Matrix load time" of `.option acct`): load only, like the GPU figure"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ngspice")
+    if not os.path.exists(exe):
+        return None
+    synth = importlib.import_module("ngspice-sf-mirror_b200.synth")
+    src = open(os.path.join(GOLDEN, "netlists", "ro17.cir")).read()
+    cards = src[src.index(".model"):src.rindex(".end")]
+    tmp = tempfile.mkdtemp(prefix="ngb_cpu_arr_")
+    cir = os.path.join(tmp, "arr.cir")
+    open(cir, "w").write(synth.inverter_array_netlist(nx, ny, cards).replace(".option klu", ".option klu acct"))
+    t0 = time.time()
+    procs = [subprocess.Popen(["bash", "-c", f"{exe} -b -r /dev/null {cir} > {tmp}/log{p} 2>&1"]) for p in range(nproc)]
+    for pr in procs:
+        pr.wait()
+    wall = time.time() - t0
+    rate = 0.0
+    for p in range(nproc):
+        it, lt = 0, 0.0
+        for ln in open(f"{tmp}/log{p}", errors="replace"):
+            if ln.startswith("Total iterations"):
+                it = int(ln.split("=")[-1].split()[0])
+            if ln.startswith("Matrix load time"):
+                lt = float(ln.split("=")[-1].split()[0])
+        if it and lt:
+            rate += 2 * nx * ny * it / lt
+    return rate, wall, f"{nproc} processes x one {nx}x{ny} array transient each ({2 * nx * ny} BSIM4 instances); evals / STATloadTime, summed"
+
+
+def bench_array(args):
+    """BASELINE config 4: flat array of 2*cells BSIM4 transistors, one circuit (S = 1), instance-parallel
+    CKTload (device loads + assembly).  LU of the ~10*cells unknowns is not part of this figure."""
+    import torch
+    synth = importlib.import_module("ngspice-sf-mirror_b200.synth")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = pkg.library()
+    lib.check(lib.L.ngbInit(local), "ngbInit")
+    stream = torch.cuda.Stream(device=local)
+    lib.check(lib.L.ngbSetStream(ctypes.c_void_p(stream.cuda_stream)), "ngbSetStream")
+    nx = int(round(args.cells ** 0.5)); ny = (args.cells + nx - 1) // nx
+    base = ngt.read(f"{GOLDEN}/ro17k.flat.ngt")
+    flat = synth.inverter_array(base, nx, ny)
+    flat.pop("node/names", None)
+    ninst = int(flat["b4/ninst"][0])
+    circ = pkg.Circuit.from_flat(lib, flat)
+    pat = circ.pattern()
+    batch = pkg.Batch(circ, 1, device=local)
+    neq1 = circ.neq + 1
+    # a transient Newton iteration (MODETRAN | MODEINITFLOAT, order 1, h = 10 ps) on a plausible bias pattern
+    rng = np.random.default_rng(rank)
+    xhost = torch.empty((2, neq1, 1), dtype=torch.float64).pin_memory()
+    xhost.numpy()[...] = 0.0
+    xhost.numpy()[0, 1:, 0] = rng.uniform(0.0, 2.0, size=neq1 - 1)
+    out_A = torch.empty(pat["nnz"], dtype=torch.float64).pin_memory()
+    out_x = torch.empty((2, neq1, 1), dtype=torch.float64).pin_memory()
+    one = lambda v, dt: np.array([v], dtype=dt)
+    batch.put("ctl.mode", one(0x1 | 0x100, np.int32)); batch.put("ctl.active", one(1, np.int32)); batch.put("ctl.order", one(1, np.int32))
+    batch.put("ctl.ag0", one(1e11, np.float64)); batch.put("ctl.ag1", one(-1e11, np.float64)); batch.put("ctl.delta", one(1e-11, np.float64))
+    batch.put("ctl.delta_old", np.full(7, 1e-11)); batch.put("ctl.time", one(1e-10, np.float64))
+    batch.put("ctl.gmin", one(1e-12, np.float64)); batch.put("ctl.srcfact", one(1.0, np.float64))
+    batch.put("x", xhost.numpy())
+
+    def step(e2e):
+        if e2e:
+            batch.put("x", xhost.numpy())
+        lib.check(lib.L.ngbLoad(batch.h), "ngbLoad")
+        if e2e:
+            lib.check(lib.L.ngbBatchDownload(batch.h, b"Ax", ctypes.c_void_p(out_A.data_ptr()), ctypes.c_long(out_A.numel() * 8), ctypes.c_long(0)), "download Ax")
+            lib.check(lib.L.ngbBatchDownload(batch.h, b"x", ctypes.c_void_p(out_x.data_ptr()), ctypes.c_long(out_x.numel() * 8), ctypes.c_long(0)), "download rhs")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+
+    def timed(e2e, profile):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if profile:
+            lib.L.ngbProfile(1, 1)
+        barrier(); n0 = lib.launch_count()
+        a.record(stream)
+        for _ in range(args.steps):
+            step(e2e)
+        b.record(stream)
+        barrier()
+        prof = None
+        if profile:
+            msum, cnt = ctypes.c_double(), ctypes.c_long()
+            lib.L.ngbProfileRead(ctypes.byref(msum), ctypes.byref(cnt)); lib.L.ngbProfile(0, 1)
+            prof = (msum.value, cnt.value)
+        return a.elapsed_time(b), lib.launch_count() - n0, prof
+
+    with ClockSampler(local) as clk:
+        ms, launches, prof = timed(False, True)
+    clocks = clk.summary()
+    ms_e2e, _, _ = timed(True, False)
+    tt = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = tt.tolist()
+    if rank == 0:
+        hbm_peak, which = peaks()
+        k_ms = prof[0] / max(prof[1], 1)
+        achieved = ninst * B4_BYTES_PER_EVAL / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        cpu = array_cpu_baseline(os.cpu_count() or 1)
+        line = {
+            "metric": "BSIM4 instance-evals/s", "value": world * ninst * args.steps / (ms * 1e-3), "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"flat {nx}x{ny} BSIM4 inverter array with RC links (config 4), one circuit per GPU (replicas), "
+                                   "one CKTload (device loads + assembly) per step, LU not included",
+                       "bsim4_instances": ninst, "unknowns": pat["n"], "nnz": pat["nnz"],
+                       "l2": f"inputs larger than L2: {ninst * 2000 / 1e6:.0f} MB touched per load"},
+            "e2e": {"value": world * ninst * args.steps / (ms_e2e * 1e-3), "unit": "evals/s",
+                    "h2d_bytes_per_step": int(xhost.numel() * 8), "d2h_bytes_per_step": int((out_A.numel() + out_x.numel()) * 8)},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak if hbm_peak else None, "traffic": traffic_from_profiles(ninst),
+                         "kernel": "ngb_k_bsim4_load", "avg_launch_ms": k_ms, "timed_launches": prof[1],
+                         "units_per_launch": ninst, "bytes_per_unit": B4_BYTES_PER_EVAL, "peak_source": which,
+                         "kernel_share_of_step": k_ms / (ms / args.steps) if ms else None},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {"value": cpu[0], "unit": "evals/s", "cores": os.cpu_count() or 1, "kind": "reference", "sample": cpu[2]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mc_ro17", choices=["mc_ro17", "ro101"])
+    ap.add_argument("--workload", default="mc_ro17", choices=["mc_ro17", "ro101", "array"])
+    ap.add_argument("--cells", type=int, default=500000, help="inverters of the array workload (2 transistors each)")
     ap.add_argument("--samples", type=int, default=4096, help="Monte-Carlo samples per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)
+    elif args.workload == "array":
+        bench_array(args)
     else:
         bench_ours(args)
 

@@ -9,6 +9,7 @@ and test files.  Needs /root/reference; the fixtures it writes do not.
   ro101  same cards, 101 stages (BASELINE config 2).
   inv    tests/bsim4/{nmos,pmos}/parameters cards, CMOS inverter with PULSE input (config 1).
   b3ring BSIM3v3.3.0 ring of five inverters + buffer on the MC_ring.sp level-8 cards.
+  arr    4x4 BSIM4 inverter array with RC links (small instance of config 4's generator).
   dio    junction diodes (rectifier, zener clamp, sidewall/tunnel/knee parameters) with R, C, SIN source.
 
 Outputs (tests/golden/): <name>.flat.ngt  flattened circuit after CKTsetup/CKTtemp
@@ -152,7 +153,7 @@ def run(name, netlist, calls, save):
     os.makedirs(TMP, exist_ok=True)
     cir = os.path.join(TMP, name + ".cir")
     open(cir, "w").write(netlist)
-    if name in ("ro17", "ro101", "ro17k", "inv", "dio", "b3ring"):
+    if name in ("ro17", "ro101", "ro17k", "inv", "dio", "b3ring", "arr"):
         # the netlist itself is kept too: the CPU-baseline arm of bench.py feeds it to oracle/_ref/ngspice
         os.makedirs(os.path.join(HERE, "netlists"), exist_ok=True)
         open(os.path.join(HERE, "netlists", name + ".cir"), "w").write(netlist)
@@ -211,5 +212,11 @@ if __name__ == "__main__":
         run("dio", dio_netlist(), "0-30,200,201,1000,1001,2000", ["out", "z", "w", "vin#branch"])
     if "b3ring" in which:
         run("b3ring", b3_netlist(5), "0-40,300,301,1000,1001", ["out", "buf", "n2", "vdd#branch"])
+    if "arr" in which:
+        # 4x4 inverter array of BASELINE config 4 (generator: ngspice-sf-mirror_b200/synth.py)
+        import importlib
+        synth = importlib.import_module("ngspice-sf-mirror_b200.synth")
+        run("arr", synth.inverter_array_netlist(4, 4, ro_cards()), "0-30,100,101,400,401",
+            ["out_0_0", "out_3_3", "in_2_1", "vdd#branch"])
     if "ro101" in which:
         run("ro101", ro_netlist(101), "1,2,3000", ["102", "2", "50", "vdd#branch"])

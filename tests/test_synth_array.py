@@ -1,0 +1,63 @@
+"""The synthetic inverter-array generator (BASELINE config 4, ngspice-sf-mirror_b200/synth.py) against
+the reference's own CKTsetup of the same netlist: node numbering differs, so Ax and rhs of one load
+are compared entry by entry through the node NAMES."""
+import importlib
+import numpy as np
+import pytest
+from parity_util import GOLDEN, ngt, pkg
+
+synth = importlib.import_module("ngspice-sf-mirror_b200.synth")
+MODE_TRANOP_FLOAT = 0x20 | 0x100          # MODETRANOP | MODEINITFLOAT
+
+
+def _load_by_name(lib, flat, names, xval, seed_state=None):
+    circ = pkg.Circuit.from_flat(lib, flat)
+    b = pkg.Batch(circ, 1)
+    neq1 = circ.neq + 1
+    b.put("ctl.mode", np.array([MODE_TRANOP_FLOAT], np.int32))
+    b.put("ctl.active", np.array([1], np.int32))
+    b.put("ctl.order", np.array([1], np.int32))
+    b.put("ctl.gmin", np.array([1e-12]))
+    b.put("ctl.srcfact", np.array([1.0]))
+    x = np.zeros((2, neq1, 1))
+    for k in range(1, len(names)):
+        x[0, k, 0] = xval[names[k]]
+    b.put("x", x)
+    b.load()
+    pat = circ.pattern()
+    assert pat["n"] == len(names) - 1                # no structurally empty column: column k is equation k+1
+    Ax = b.get("Ax", (1, -1))[0]
+    rhs = b.get("x", (2, neq1, 1))[1, :, 0]
+    A = {}
+    for col in range(pat["n"]):
+        for p in range(pat["Ap"][col], pat["Ap"][col + 1]):
+            A[(names[pat["Ai"][p] + 1], names[col + 1])] = Ax[p]
+    return A, {names[k]: rhs[k] for k in range(1, len(names))}
+
+
+def test_synthetic_array_matches_reference_setup(hostsim_lib):
+    ref = ngt.read(f"{GOLDEN}/arr.flat.ngt")
+    base = ngt.read(f"{GOLDEN}/ro17k.flat.ngt")
+    ours = synth.inverter_array(base, 4, 4)
+    ref_names = bytes(ref["node/names_bytes"].astype(np.uint8)).decode().split("\n")
+    ref_names = [ln.split(" ", 1)[1].lower() if " " in ln else "" for ln in ref_names if ln.strip()]
+    our_names = ours.pop("node/names")
+    assert sorted(ref_names[1:]) == sorted(our_names[1:])
+    rng = np.random.default_rng(3)
+    xval = {n: float(rng.uniform(0.0, 2.0)) for n in our_names[1:]}
+    A1, r1 = _load_by_name(hostsim_lib, ref, ref_names, xval)
+    A2, r2 = _load_by_name(hostsim_lib, ours, our_names, xval)
+    assert A1.keys() == A2.keys()
+    # instance order differs between the two flattenings, so sums may round differently in the last place
+    for k in A1:
+        assert abs(A1[k] - A2[k]) <= 1e-12 * max(abs(A1[k]), 1e-30), k
+    for k in r1:
+        assert abs(r1[k] - r2[k]) <= 1e-12 * max(abs(r1[k]), 1e-18), k
+
+
+def test_synthetic_array_scales(hostsim_lib):
+    base = ngt.read(f"{GOLDEN}/ro17k.flat.ngt")
+    fl = synth.inverter_array(base, 30, 20)
+    circ = pkg.Circuit.from_flat(hostsim_lib, fl)
+    pat = circ.pattern()
+    assert pat["n"] == 10 * 600 + 4 and int(fl["b4/ninst"][0]) == 1200
