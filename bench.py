@@ -398,6 +398,8 @@ def bench_array(args):
     """BASELINE config 4: flat array of 2*cells BSIM4 transistors, one circuit (S = 1), instance-parallel
     CKTload (device loads + assembly).  LU of the ~10*cells unknowns is not part of this figure."""
     import torch
+    pkg = importlib.import_module("ngspice-sf-mirror_b200")
+    ngt = pkg.ngt
     synth = importlib.import_module("ngspice-sf-mirror_b200.synth")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
