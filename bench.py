@@ -138,7 +138,8 @@ def cpu_reference_run(workload, nproc, samples_per_proc, seed0=1000):
     t0 = time.time()
     procs = []
     for files in jobs:
-        cmd = " ; ".join(f"{exe} -b -r /dev/null {f} > {f}.log 2>&1" for f in files)
+        # the rawfile goes to a scratch file: ngspice unlinks and recreates its -r target, so it must never be /dev/null
+        cmd = " ; ".join(f"{exe} -b -r {f}.raw {f} > {f}.log 2>&1 ; rm -f {f}.raw" for f in files)
         procs.append(subprocess.Popen(["bash", "-c", cmd]))
     for pr in procs:
         pr.wait()
@@ -377,7 +378,7 @@ def array_cpu_baseline(nproc, nx=32, ny=32):
     cir = os.path.join(tmp, "arr.cir")
     open(cir, "w").write(synth.inverter_array_netlist(nx, ny, cards).replace(".option klu", ".option klu acct"))
     t0 = time.time()
-    procs = [subprocess.Popen(["bash", "-c", f"{exe} -b -r /dev/null {cir} > {tmp}/log{p} 2>&1"]) for p in range(nproc)]
+    procs = [subprocess.Popen(["bash", "-c", f"{exe} -b -r {tmp}/raw{p} {cir} > {tmp}/log{p} 2>&1 ; rm -f {tmp}/raw{p}"]) for p in range(nproc)]
     for pr in procs:
         pr.wait()
     wall = time.time() - t0

@@ -86,6 +86,28 @@ ngb_k_assemble(const NgbAsmCtx c, size_t total)
     ngb_asm_thread(&c, u);
 }
 
+/* long contribution lists: one CTA per (long target, sample) */
+__global__ void __launch_bounds__(256)
+ngb_k_assemble_long(const NgbAsmCtx c)
+{
+    __shared__ double part[256];
+    const int li = blockIdx.x / c.S, s = blockIdx.x - li * c.S;
+    if (!c.ctl.active[s]) return;
+    const int tg = c.long_tgt[li];
+    const int lo = c.tgt_ptr[tg], hi = c.tgt_ptr[tg + 1];
+    const int chunk = (hi - lo + 255) / 256;
+    const int a = lo + threadIdx.x * chunk, b = min(a + chunk, hi);
+    double acc = 0.0;
+    for (int p = a; p < b; p++) acc += c.stamp[(size_t)c.tgt_rows[p] * c.S + s];
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int k = 0; k < 256; k++) tot += part[k];
+        ngb_asm_store(&c, tg, s, tot);
+    }
+}
+
 /* one warp per sample: warp w of the CTA owns sample blockIdx.x * warps + w */
 __global__ void ngb_k_lu_warp(const NgbLuCtx c, int per_sample_doubles)
 {
@@ -298,6 +320,12 @@ int ngb_launch_assemble(const NgbAsmCtx *c)
     const size_t total = (size_t)(c->nnz + c->neq1) * c->S;
     const unsigned grid = (unsigned)((total + 255) / 256);
     ngb_k_assemble<<<grid, 256, 0, g_stream>>>(*c, total);
+    if (c->nlong > 0) {
+        const int e = post_launch("assemble");
+        if (e) return e;
+        ngb_k_assemble_long<<<(unsigned)(c->nlong * c->S), 256, 0, g_stream>>>(*c);
+        return post_launch("assemble_long");
+    }
     return post_launch("assemble");
 }
 int ngb_launch_lu(const NgbLuCtx *c)

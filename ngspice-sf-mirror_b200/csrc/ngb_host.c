@@ -191,7 +191,7 @@ void ngbCircuitDestroy(ngb_circuit *c)
     free(c->vs_nodes); free(c->vs_fn); free(c->vs_par); free(c->vs_spos); free(c->vs_cspos);
     free(c->is_nodes); free(c->is_fn); free(c->is_par); free(c->is_spos);
     free(c->Ap); free(c->Ai); free(c->eq2col); free(c->col2eq); free(c->slot_diag); free(c->diag_slot);
-    free(c->tgt_ptr); free(c->tgt_rows); free(c->const_row); free(c->const_val);
+    free(c->long_tgt); free(c->tgt_ptr); free(c->tgt_rows); free(c->const_row); free(c->const_val);
     free(c->klu_Q); free(c->klu_R); free(c->klu_Pnum);
     free_sched(&c->sch);
     free_packed(&c->pk);
@@ -612,6 +612,10 @@ int ngbCircuitFinalize(ngb_circuit *c)
         free(fill);
     }
     free(cb.tgt.v); free(cb.row.v);
+    c->nlong = 0;
+    for (i = 0; i < c->ntgt; i++) if (c->tgt_ptr[i + 1] - c->tgt_ptr[i] > NGB_ASM_LONG) c->nlong++;
+    c->long_tgt = (int *)xcalloc((size_t)c->nlong + 1, sizeof(int));
+    for (i = 0, k = 0; i < c->ntgt; i++) if (c->tgt_ptr[i + 1] - c->tgt_ptr[i] > NGB_ASM_LONG) c->long_tgt[k++] = i;
     c->finalized = 1;
     return NGB_OK;
 }
@@ -1084,6 +1088,7 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
     b->d_tgt_ptr = (int *)dev_dup(c->tgt_ptr, sizeof(int) * ((size_t)c->ntgt + 1));
     b->d_tgt_rows = (int *)dev_dup(c->tgt_rows, sizeof(int) * (size_t)c->tgt_ptr[c->ntgt]);
     b->d_slot_diag = (int *)dev_dup(c->slot_diag, sizeof(int) * (size_t)c->nnz);
+    b->d_long_tgt = (int *)dev_dup(c->long_tgt, sizeof(int) * (size_t)c->nlong);
     /* constant stamp rows (resistors, source incidence): written once */
     if (c->nconst) {
         double *row = (double *)xcalloc((size_t)S, sizeof(double));
@@ -1169,7 +1174,7 @@ void ngbBatchDestroy(ngb_batch *b)
     if (!b) return;
     for (i = 0; i < b->narr; i++)
         if (strcmp(b->arr[i].name, "b4.mtab") && strcmp(b->arr[i].name, "b4.ptab")) ngb_dev_free(b->arr[i].ptr);
-    ngb_dev_free(b->d_node_type); ngb_dev_free(b->d_tgt_ptr); ngb_dev_free(b->d_tgt_rows); ngb_dev_free(b->d_slot_diag);
+    ngb_dev_free(b->d_node_type); ngb_dev_free(b->d_tgt_ptr); ngb_dev_free(b->d_tgt_rows); ngb_dev_free(b->d_slot_diag); ngb_dev_free(b->d_long_tgt);
     ngb_dev_free(b->b4_mtab); ngb_dev_free(b->b4_ptab); ngb_dev_free(b->b4_prow); ngb_dev_free(b->b4_flags);
     ngb_dev_free(b->b4_nodes); ngb_dev_free(b->b4_spos); ngb_dev_free(b->b4_prow_t);
     ngb_dev_free(b->cap_nodes); ngb_dev_free(b->cap_spos);
@@ -1276,7 +1281,7 @@ void ngb_fill_asmctx(ngb_batch *b, NgbAsmCtx *x)
     const ngb_circuit *c = b->c;
     memset(x, 0, sizeof *x);
     x->S = b->S; x->nnz = c->nnz; x->neq1 = b->neq1; x->tgt_ptr = b->d_tgt_ptr; x->tgt_rows = b->d_tgt_rows;
-    x->slot_diag = b->d_slot_diag; x->stamp = b->stamp; x->Ax = b->Ax; x->x = b->x; x->add_diag_gmin = 1; x->ctl = b->ctl;
+    x->slot_diag = b->d_slot_diag; x->long_tgt = b->d_long_tgt; x->nlong = c->nlong; x->stamp = b->stamp; x->Ax = b->Ax; x->x = b->x; x->add_diag_gmin = 1; x->ctl = b->ctl;
 }
 void ngb_fill_luctx(ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve, int which)
 {

@@ -28,6 +28,7 @@ struct ngb_circuit {
     int n, nnz; int *Ap, *Ai, *eq2col, *col2eq, *slot_diag, *diag_slot;
     /* stamp rows and per-target contribution lists */
     int nstamp_rows, ntgt; int *tgt_ptr, *tgt_rows;
+    int nlong; int *long_tgt;     /* targets with more than NGB_ASM_LONG contributions */
     int nconst; int *const_row; double *const_val;
     /* LU: imported or own symbolic objects + task schedule */
     int klu_nblocks; int *klu_Q, *klu_R, *klu_Pnum;
@@ -48,7 +49,7 @@ struct ngb_batch {
     NgbCtl ctl;
     double *x, *Ax, *stamp;
     int *errflag;
-    int *d_node_type, *d_tgt_ptr, *d_tgt_rows, *d_slot_diag;
+    int *d_node_type, *d_tgt_ptr, *d_tgt_rows, *d_slot_diag, *d_long_tgt;
     double *b4_inst, *b4_state, *b4_op, *b4_mtab, *b4_ptab; int *b4_prow, *b4_prow_t, *b4_flags, *b4_nodes, *b4_spos;
     double *cap_par, *cap_state; int *cap_nodes, *cap_spos;
     double *b3_inst, *b3_state, *b3_von, *b3_mtab, *b3_ptab; int *b3_prow, *b3_flags, *b3_nodes, *b3_spos;

@@ -185,6 +185,7 @@ NGB_HD int ngb_src_thread(const NgbSrcCtx *c, size_t t)
 
 /* ------------------------------------------------------------------ assembly */
 /* one thread per (target, sample): u = target * S + s */
+NGB_HD void ngb_asm_store(const NgbAsmCtx *c, int tg, int s, double acc);
 NGB_HD void ngb_asm_thread(const NgbAsmCtx *c, size_t u)
 {
     const int S = c->S;
@@ -193,8 +194,17 @@ NGB_HD void ngb_asm_thread(const NgbAsmCtx *c, size_t u)
     if (!NGB_LDG(&c->ctl.active[s])) return;
     double acc = 0.0;
     const int lo = NGB_LDG(&c->tgt_ptr[tg]), hi = NGB_LDG(&c->tgt_ptr[tg + 1]);
+#ifdef __CUDA_ARCH__
+    if (hi - lo > NGB_ASM_LONG && c->nlong) return;       /* ngb_asm_long_group's job */
+#endif
     for (int p = lo; p < hi; p++)
         acc += NGB_LDG(&c->stamp[(size_t)NGB_LDG(&c->tgt_rows[p]) * S + s]);
+    ngb_asm_store(c, tg, s, acc);
+}
+
+NGB_HD void ngb_asm_store(const NgbAsmCtx *c, int tg, int s, double acc)
+{
+    const int S = c->S;
     if (tg < c->nnz) {
         /* LoadGmin_CSC: CKTdiagGmin on every present diagonal, applied with the factor call */
         if (c->add_diag_gmin && NGB_LDG(&c->slot_diag[tg])) {

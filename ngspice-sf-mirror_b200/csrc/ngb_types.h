@@ -87,10 +87,14 @@ typedef struct NgbSrcCtx {
 
 /* assembly of Ax / rhs from the stamp buffer: target t sums rows tgt_rows[tgt_ptr[t]..tgt_ptr[t+1])
  * in that (reference load) order; targets [0,nnz) are CSC slots, [nnz, nnz+neq+1) are rhs rows */
+#define NGB_ASM_LONG 4096
 typedef struct NgbAsmCtx {
     int S, nnz, neq1;
     const int *tgt_ptr, *tgt_rows;
     const int *slot_diag;   /* [nnz] 1 if the slot is a diagonal entry (LoadGmin_CSC)    */
+    /* targets with more than NGB_ASM_LONG contributions (supply rails of a large flat circuit) are left
+     * to a second launch that sums them as 256 in-order chunks, then the chunk totals in order */
+    const int *long_tgt; int nlong;
     const double *stamp;
     double *Ax;             /* [S][nnz]                                                  */
     double *x;              /* rhs is assembled into x[1 - xsel]                         */
