@@ -398,6 +398,17 @@ static int new_row(ngb_circuit *c, contribs *cb, int target)
     return r;
 }
 
+/* same, with a caller-chosen row: the big device tables number their rows position-major
+ * (row = base + position * ninst + instance) so that neighbouring threads -- neighbouring samples of
+ * one instance, or neighbouring instances when S = 1 -- write neighbouring words */
+static int new_row_at(ngb_circuit *c, contribs *cb, int target, int row)
+{
+    (void)c;
+    if (target < 0) return -1;
+    iv_push(&cb->tgt, target); iv_push(&cb->row, row);
+    return row;
+}
+
 int ngbCircuitFinalize(ngb_circuit *c)
 {
     coovec coo = { 0, 0, 0 };
@@ -487,9 +498,14 @@ int ngbCircuitFinalize(ngb_circuit *c)
     for (i = 0; i < c->b3_n; i++)
         for (k = 0; k < B3S_COUNT; k++) {
             const int rr = c->b3_nodes[b3_stamp_r[k] * c->b3_n + i], rc = c->b3_nodes[b3_stamp_c[k] * c->b3_n + i];
-            if (k < B3S_RHS_COUNT) c->b3_spos[k * c->b3_n + i] = new_row(c, &cb, (rr > 0 && c->eq2col[rr] >= 0) ? c->nnz + rr : -1);
-            else c->b3_spos[k * c->b3_n + i] = new_row(c, &cb, slot_lookup(c, rr, rc));
+            const int row = k * c->b3_n + i;
+            if (k < B3S_RHS_COUNT) c->b3_spos[k * c->b3_n + i] = new_row_at(c, &cb, (rr > 0 && c->eq2col[rr] >= 0) ? c->nnz + rr : -1, row);
+            else c->b3_spos[k * c->b3_n + i] = new_row_at(c, &cb, slot_lookup(c, rr, rc), row);
         }
+    c->nstamp_rows += B3S_COUNT * c->b3_n;
+    {
+        const int b4_base = c->nstamp_rows;
+#define B4ROW(k_) (b4_base + (k_) * c->b4_n + i)
     c->b4_spos = (int *)xcalloc((size_t)c->b4_n * B4S_TOTAL, sizeof(int));
     c->b4_slots = (int *)xcalloc((size_t)c->b4_n * B4S_MAT_COUNT, sizeof(int));
     for (i = 0; i < c->b4_n; i++) {
@@ -535,7 +551,7 @@ int ngbCircuitFinalize(ngb_circuit *c)
             if (k >= B4S_MAT_COUNT && k < B4S_COUNT) {
                 int eq = c->b4_nodes[b4_rhs_role(k) * c->b4_n + i];
                 if (b4_pos_written(k, rg, rb, rds) && eq > 0 && c->eq2col[eq] >= 0)
-                    c->b4_spos[k * c->b4_n + i] = new_row(c, &cb, c->nnz + eq);
+                    c->b4_spos[k * c->b4_n + i] = new_row_at(c, &cb, c->nnz + eq, B4ROW(k));
             } else {
                 int base = k, slot;
                 if (k >= B4S_COUNT) {                 /* extra addend: same slot as its base position */
@@ -545,9 +561,12 @@ int ngbCircuitFinalize(ngb_circuit *c)
                 }
                 slot = c->b4_slots[base * c->b4_n + i];
                 if (slot >= 0 && b4_pos_written(base, rg, rb, rds))
-                    c->b4_spos[k * c->b4_n + i] = new_row(c, &cb, slot);
+                    c->b4_spos[k * c->b4_n + i] = new_row_at(c, &cb, slot, B4ROW(k));
             }
         }
+    }
+#undef B4ROW
+    c->nstamp_rows += B4S_TOTAL * c->b4_n;
     }
     c->cap_spos = (int *)xcalloc((size_t)c->cap_n * 6 + 1, sizeof(int));
     for (i = 0; i < c->cap_n; i++) {
