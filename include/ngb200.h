@@ -117,6 +117,9 @@ int ngbCircuitLuInfo(const ngb_circuit *c, int info[9]);
 /* ---- batch ---- */
 ngb_batch *ngbBatchCreate(ngb_circuit *c, int nsamples, int device);
 void ngbBatchDestroy(ngb_batch *b);
+/* after ngbCircuitSetLuPattern on a circuit that already has batches (a later SMPreorder): upload the
+ * new pattern sets */
+int ngbBatchRefreshLu(ngb_batch *b);
 
 /* named device arrays (tests, the reference-side shim, result download):
  *   ctl.mode ctl.active ctl.head ctl.order ctl.noncon ctl.xsel ctl.err ctl.lusel int  [S]

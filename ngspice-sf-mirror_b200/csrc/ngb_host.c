@@ -1187,6 +1187,48 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
     return b;
 }
 
+static void batch_free_lu(ngb_batch *b)
+{
+    int w;
+    for (w = 0; w < 2; w++)
+        if (b->dlu[w].valid) {
+            if (b->dlu[w].dpk.ok) { ngb_dev_free((void *)b->dlu[w].dpk.blob); ngb_dev_free((void *)b->dlu[w].dpk.aslot);
+                                    ngb_dev_free((void *)b->dlu[w].dpk.arow); ngb_dev_free((void *)b->dlu[w].dpk.ext); }
+            sched_dev_free(&b->dlu[w].dsch);
+            b->dlu[w].valid = 0;
+        }
+}
+
+/* the circuit's LU pattern sets changed after the batch was created (a later SMPreorder in the
+ * reference-side shim): upload them again */
+int ngbBatchRefreshLu(ngb_batch *b)
+{
+    const ngb_circuit *c = b->c;
+    const int S = b->S;
+    int w, nVmax = 0;
+    if (!c->have_lu) { ngb_set_error("no LU pattern on the circuit"); return NGB_E_PANIC; }
+    ngb_dev_sync();
+    batch_free_lu(b);
+    for (w = 0; w < 2; w++)
+        if (c->lu[w].valid) {
+            sched_to_dev(b, c, w); packed_to_dev(b, c, w); b->dlu[w].valid = 1;
+            if (c->lu[w].sch.nV > nVmax) nVmax = c->lu[w].sch.nV;
+        }
+    b->lu_which = c->lu[0].valid ? 0 : 1;
+    if (!b->have_lu || (size_t)nVmax * S * sizeof(double) > (size_t)ngbBatchArrayBytes(b, "lu.V")) {
+        int i;
+        for (i = 0; i < b->narr; i++)                       /* drop the old, smaller work arrays from the registry */
+            if (!strcmp(b->arr[i].name, "lu.V") || !strcmp(b->arr[i].name, "lu.Rs") || !strcmp(b->arr[i].name, "lu.nodeconv") ||
+                !strcmp(b->arr[i].name, "lu.singular")) { ngb_dev_free(b->arr[i].ptr); b->arr[i] = b->arr[--b->narr]; i--; }
+        b->V = (double *)dalloc(b, "lu.V", sizeof(double) * (size_t)nVmax * S);
+        b->Rs = (double *)dalloc(b, "lu.Rs", sizeof(double) * (size_t)c->n * S);
+        b->nodeconv = (int *)dalloc(b, "lu.nodeconv", sizeof(int) * (size_t)S);
+        b->singular = (int *)dalloc(b, "lu.singular", sizeof(int) * (size_t)S);
+    }
+    b->have_lu = 1;
+    return b->failed ? NGB_E_PANIC : NGB_OK;
+}
+
 void ngbBatchDestroy(ngb_batch *b)
 {
     int i;
@@ -1201,13 +1243,7 @@ void ngbBatchDestroy(ngb_batch *b)
     ngb_dev_free(b->b3_mtab); ngb_dev_free(b->b3_ptab); ngb_dev_free(b->b3_prow); ngb_dev_free(b->b3_flags); ngb_dev_free(b->b3_nodes); ngb_dev_free(b->b3_spos);
     ngb_dev_free(b->vs_fn); ngb_dev_free(b->vs_spos); ngb_dev_free(b->is_fn); ngb_dev_free(b->is_spos);
     if (b->have_lu) {
-        int w;
-        for (w = 0; w < 2; w++)
-            if (b->dlu[w].valid) {
-                if (b->dlu[w].dpk.ok) { ngb_dev_free((void *)b->dlu[w].dpk.blob); ngb_dev_free((void *)b->dlu[w].dpk.aslot);
-                                        ngb_dev_free((void *)b->dlu[w].dpk.arow); ngb_dev_free((void *)b->dlu[w].dpk.ext); }
-                sched_dev_free(&b->dlu[w].dsch);
-            }
+        batch_free_lu(b);
     }
     ngb_tran_free(b);
     free(b);

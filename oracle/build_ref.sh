@@ -69,4 +69,21 @@ if [ "$FLAV" = serial ]; then
       -Wl,--wrap=CKTload,--wrap=SMPsolve,--wrap=SMPluFac,--wrap=SMPreorder,--wrap=DCtran \
       -Wl,--start-group "$OUT/libngref.a" -Wl,--end-group -lm -ldl
   echo "built $OUT/ngspice_dump"
+  # drop-in flavour: the same objects with integration/ngb_shim.c interposed in front of CKTload and
+  # the SMP entry points, linked against the product library (INTEGRATION.md level 1); a second copy is
+  # linked against the host build of the kernels so the binding can be exercised without a GPU
+  REPO="$(cd "$HERE/.." && pwd)"
+  gcc -c $CFLAGS $INC -I"$R/spicelib/devices" -I"$R/maths/KLU" "$REPO/integration/ngb_shim.c" -o "$OUT/ngb_shim.o"
+  if [ -f "$REPO/ngspice-sf-mirror_b200/libngb200.so" ]; then
+    gcc -o "$OUT/ngspice_ngb" "$MAINOBJ" "$OUT/ngb_shim.o" \
+        -Wl,--wrap=CKTload,--wrap=SMPsolve,--wrap=SMPluFac,--wrap=SMPreorder \
+        -Wl,--start-group "$OUT/libngref.a" -Wl,--end-group -L"$REPO/ngspice-sf-mirror_b200" -lngb200 \
+        -Wl,-rpath,'$ORIGIN/../../ngspice-sf-mirror_b200' -Wl,-rpath,/usr/local/cuda/lib64 -lm -ldl && echo "built $OUT/ngspice_ngb"
+  fi
+  if [ -f "$REPO/tests/hostsim/libngb200_hostsim.so" ]; then
+    gcc -o "$OUT/ngspice_ngb_hostsim" "$MAINOBJ" "$OUT/ngb_shim.o" \
+        -Wl,--wrap=CKTload,--wrap=SMPsolve,--wrap=SMPluFac,--wrap=SMPreorder \
+        -Wl,--start-group "$OUT/libngref.a" -Wl,--end-group -L"$REPO/tests/hostsim" -lngb200_hostsim \
+        -Wl,-rpath,'$ORIGIN/../../tests/hostsim' -lm -ldl -lstdc++ && echo "built $OUT/ngspice_ngb_hostsim"
+  fi
 fi

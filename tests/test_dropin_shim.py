@@ -1,0 +1,66 @@
+"""Drop-in boundary (INTEGRATION.md level 1): the UNMODIFIED reference objects, linked with
+integration/ngb_shim.c in front of CKTload / SMPreorder / SMPluFac / SMPsolve, must write the same
+rawfile as the stock reference binary -- every node and branch at every accepted time point.
+
+CPU: oracle/_ref/ngspice_ngb_hostsim (the shim bound to the host build of the kernels).
+GPU: oracle/_ref/ngspice_ngb (the shim bound to libngb200.so).
+Both binaries are produced by oracle/build_ref.sh; the tests skip when they are absent."""
+import os
+import subprocess
+import tempfile
+import numpy as np
+import pytest
+from parity_util import GOLDEN, ROOT
+
+REF = os.path.join(ROOT, "oracle", "_ref", "ngspice")
+NETLISTS = ["ro17k", "inv", "dio", "b3ring", "arr"]
+
+
+def _payload(path):
+    data = open(path, "rb").read()
+    i = data.index(b"Binary:\n")
+    head = data[:i].decode(errors="replace")
+    keep = "\n".join(ln for ln in head.splitlines() if not ln.startswith("Date:"))
+    return keep, np.frombuffer(data[i + 8:], dtype=np.float64)
+
+
+def _run(exe, name, tmp, env=None):
+    raw = os.path.join(tmp, f"{os.path.basename(exe)}_{name}.raw")       # never /dev/null: ngspice unlinks its -r target
+    cir = os.path.join(GOLDEN, "netlists", name + ".cir")
+    p = subprocess.run([exe, "-b", "-r", raw, cir], capture_output=True, text=True, env=dict(os.environ, **(env or {})), timeout=600)
+    assert os.path.exists(raw), p.stdout[-2000:] + p.stderr[-2000:]
+    return _payload(raw), p.stdout + p.stderr
+
+
+def _check(exe, name, expect_backend, env=None):
+    if not (os.path.exists(REF) and os.path.exists(exe)):
+        pytest.skip("oracle/_ref binaries not built (oracle/build_ref.sh needs /root/reference)")
+    with tempfile.TemporaryDirectory(prefix="ngb_shim_") as tmp:
+        (h0, v0), _ = _run(REF, name, tmp)
+        (h1, v1), log = _run(exe, name, tmp, env)
+    assert f"ngb_shim: CKTload" in log and expect_backend in log, log[-1500:]     # the shim really took the hot path
+    assert h0 == h1
+    assert v0.shape == v1.shape
+    return v0, v1
+
+
+@pytest.mark.parametrize("name", NETLISTS)
+def test_dropin_hostsim_rawfile_identical(name):
+    v0, v1 = _check(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb_hostsim"), name, "hostsim")
+    assert np.array_equal(v0, v1)
+
+
+def test_dropin_hostsim_load_only_identical():
+    """NGB_SHIM_LU=0: device load, host KLU"""
+    v0, v1 = _check(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb_hostsim"), "inv", "hostsim", env={"NGB_SHIM_LU": "0"})
+    assert np.array_equal(v0, v1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NETLISTS)
+def test_dropin_gpu_rawfile(name):
+    v0, v1 = _check(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb"), name, "cuda-sm_100a")
+    if name == "dio":           # SIN source: CUDA's sin() is not glibc's; the north_star tolerance applies
+        assert np.max(np.abs(v0 - v1) / np.maximum(np.abs(v0), 1e-6)) <= 1e-9
+    else:
+        assert np.array_equal(v0, v1)
