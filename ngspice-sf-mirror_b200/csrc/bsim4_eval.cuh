@@ -143,7 +143,7 @@ NGB_HD void b4_poly_depletion(double phi, double ngate, double epsgate, double c
 }
 
 /* one S/D junction diode, DC part (b4ld.c:701-800 source side, :802-901 drain side) */
-NGB_HD void b4_junction_dc(int dioMod, double Isat, double Nvtm, double vj, double gmin,
+NGB_HD_SHARED void b4_junction_dc(int dioMod, double Isat, double Nvtm, double vj, double gmin,
                            double bv, double xjbv, double XExpBV, double vjmFwd, double vjmRev,
                            double IVjmFwd, double IVjmRev, double slpFwd, double slpRev,
                            double *g, double *cur)
@@ -207,7 +207,7 @@ NGB_HD void b4_junction_dc(int dioMod, double Isat, double Nvtm, double vj, doub
 }
 
 /* trap-assisted tunnelling factor and its bias derivative (b4ld.c:911-987, six copies) */
-NGB_HD void b4_tat(double vts, double vj, double Nvtmr, double *Tn, double *dTn_dVb)
+NGB_HD_SHARED void b4_tat(double vts, double vj, double Nvtmr, double *Tn, double *dTn_dVb)
 {
     double T0, T9, T10, dT0_dVb;
     if ((vts - vj) < (vts * 1e-3)) {
@@ -1527,7 +1527,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
 }
 
 /* one GIDL/GISL branch, gidlMod == 0 (b4ld.c:2324-2358 GIDL, :2365-2399 GISL) */
-NGB_HD void b4_gidl0(double T1, double dvg_eff, double T0den, double agidl, double bgidl, double cgidl,
+NGB_HD_SHARED void b4_gidl0(double T1, double dvg_eff, double T0den, double agidl, double bgidl, double cgidl,
                      double weffCJ, double vb, double *I, double *Gd, double *Gg, double *Gb)
 {
     if ((agidl <= 0.0) || (bgidl <= 0.0) || (T1 <= 0.0) || (cgidl <= 0.0) || (vb > 0.0)) {
@@ -1560,7 +1560,7 @@ NGB_HD void b4_gidl0(double T1, double dvg_eff, double T0den, double agidl, doub
 }
 
 /* one GIDL/GISL branch, gidlMod != 0 (b4ld.c:2409-2459 GISL, :2467-2516 GIDL) */
-NGB_HD void b4_gidl1(double T1, double dvg_eff, double T0den, double agidl, double bgidl, double cgidl,
+NGB_HD_SHARED void b4_gidl1(double T1, double dvg_eff, double T0den, double agidl, double bgidl, double cgidl,
                      double rgidl, double kgidl, double fgidl, double gidlclamp, double weffCJ,
                      double vb, double *I, double *Gd, double *Gg, double *Gb)
 {
@@ -1600,7 +1600,7 @@ NGB_HD void b4_gidl1(double T1, double dvg_eff, double T0den, double agidl, doub
 }
 
 /* edge (gate-to-S/D overlap) tunnelling current (b4ld.c:2727-2755 source, :2758-2785 drain) */
-NGB_HD void b4_ig_edge(double vg, double vfbsd_tot, double Aechvb, double BechvbEdge,
+NGB_HD_SHARED void b4_ig_edge(double vg, double vfbsd_tot, double Aechvb, double BechvbEdge,
                        double aig, double big, double cig, double *Ig, double *dIg_dVg)
 {
     double T0 = vg - vfbsd_tot;
@@ -2863,7 +2863,7 @@ NGB_HD int b4_charges(const B4Ctx *c, size_t t, const double *Mrow, const double
 }
 
 /* one junction's depletion charge and capacitance (b4ld.c:3966-4013 source, :4016-4062 drain) */
-NGB_HD void b4_junction_cv(double vj, double cz, double czsw, double czswg, double MJ, double MJSW,
+NGB_HD_SHARED void b4_junction_cv(double vj, double cz, double czsw, double czswg, double MJ, double MJSW,
                            double MJSWG, double PhiB, double PhiBSW, double PhiBSWG,
                            double *q, double *cap)
 {

@@ -19,10 +19,19 @@
 #ifdef __CUDACC__
 #define NGB_HD __device__ __forceinline__
 #define NGB_D __device__ __forceinline__
+/* helpers that the BSIM4 evaluation calls twice or more (source and drain junctions, the two gate-edge
+ * tunnelling currents, GIDL / GISL): one out-of-line copy each when NGB_OUTLINE_HELPERS is set -- the
+ * evaluation is bound by instruction fetch, see DESIGN.md */
+#ifdef NGB_OUTLINE_HELPERS
+#define NGB_HD_SHARED __device__ __noinline__
+#else
+#define NGB_HD_SHARED __device__ __forceinline__
+#endif
 #define NGB_LDG(p) __ldg(p)
 #else
 #define NGB_HD static inline
 #define NGB_D static inline
+#define NGB_HD_SHARED static inline
 #define NGB_LDG(p) (*(p))
 #endif
 

@@ -27,7 +27,15 @@ long  ngb_dev_launch_count(void);               /* kernels launched so far (benc
 void *ngb_dev_stream(void);
 int   ngb_dev_set_stream(void *stream);         /* adopt a caller-owned cudaStream_t */
 void  ngb_dev_profile(int enable, int every);   /* CUDA-event timing of sampled bsim4_load launches */
-int   ngb_dev_profile_read(double *ms_sum, long *count);                     /* cudaStream_t the kernels are launched on */
+int   ngb_dev_profile_read(double *ms_sum, long *count);
+/* returns 1 when the sampled-launch timing wants THIS Newton step (the caller then launches it kernel by
+ * kernel instead of replaying a graph) */
+int   ngb_dev_profile_due(void);
+/* CUDA graph of one Newton step: begin capture on the launch stream, end + instantiate, replay */
+int   ngb_dev_graph_begin(void);
+int   ngb_dev_graph_end(void **exec, int *nodes);
+int   ngb_dev_graph_launch(void *exec, int nodes);
+void  ngb_dev_graph_destroy(void *exec);                     /* cudaStream_t the kernels are launched on */
 
 int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag);
 int ngb_launch_cap_load(const NgbCapCtx *c, int *errflag);

@@ -19,6 +19,9 @@ struct ngb_tran {
     int *d_save_eq;
     long ticks;
     int dc_over;               /* every sample has left the DC operating point (pattern set 0 idle) */
+    /* CUDA graph of one Newton step, one per launch sequence: [0] while pattern set 0 is still in use,
+     * [1] afterwards; graph_state 0 = not tried, 1 = ready, -1 = unavailable */
+    void *graph[2]; int graph_nodes[2], graph_state[2];
 };
 
 static void *dz(size_t bytes) { return ngb_dev_malloc(bytes ? bytes : 8); }
@@ -32,6 +35,7 @@ void ngb_tran_free(struct ngb_batch *b)
     ngb_dev_free(t->x.numiter); ngb_dev_free(t->x.timepts); ngb_dev_free(t->x.save_delta); ngb_dev_free(t->x.old_delta);
     ngb_dev_free(t->x.breaks); ngb_dev_free(t->x.out_time); ngb_dev_free(t->x.out_val); ngb_dev_free(t->x.ndone);
     ngb_dev_free(t->d_save_eq); ngb_dev_free(t->x.isrc_break); ngb_dev_free(t->x.vsrc_break);
+    ngb_dev_graph_destroy(t->graph[0]); ngb_dev_graph_destroy(t->graph[1]);
     free(t);
     b->tran = NULL;
 }
@@ -122,7 +126,7 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     return ngb_dev_sync();
 }
 
-static int enqueue_tick(ngb_batch *b, int with_lu)
+static int enqueue_tick_direct(ngb_batch *b, int with_lu)
 {
     int r;
     if ((r = ngb_enqueue_load(b))) return r;
@@ -139,6 +143,29 @@ static int enqueue_tick(ngb_batch *b, int with_lu)
         }
     }
     return ngb_launch_tran_control(&b->tran->x);
+}
+
+
+/* one Newton step for the whole batch.  The launch sequence is the same every step, so it is captured
+ * once into a CUDA graph and replayed (six to eight launches become one); steps sampled by the
+ * kernel-timing facility, and the host build, go kernel by kernel. */
+static int enqueue_tick(ngb_batch *b, int with_lu)
+{
+    struct ngb_tran *t = b->tran;
+    const int g = t->dc_over ? 1 : 0;
+    int r;
+    if (!with_lu || ngb_dev_profile_due()) return enqueue_tick_direct(b, with_lu);
+    if (t->graph_state[g] == 0) {
+        if (getenv("NGB_NO_GRAPH") || ngb_dev_graph_begin()) {
+            t->graph_state[g] = -1;
+        } else {
+            r = enqueue_tick_direct(b, with_lu);
+            if (ngb_dev_graph_end(&t->graph[g], &t->graph_nodes[g]) || r) { t->graph_state[g] = -1; if (r) return r; }
+            else t->graph_state[g] = 1;
+        }
+    }
+    if (t->graph_state[g] == 1) return ngb_dev_graph_launch(t->graph[g], t->graph_nodes[g]);
+    return enqueue_tick_direct(b, with_lu);
 }
 
 int ngbTranRun(ngb_batch *b, int max_points, const int *save_eq, int nsave)

@@ -26,6 +26,11 @@ void *ngb_dev_stream(void) { return nullptr; }
 int ngb_dev_set_stream(void *) { return 0; }
 void ngb_dev_profile(int, int) {}
 int ngb_dev_profile_read(double *ms, long *n) { if (ms) *ms = 0; if (n) *n = 0; return 0; }
+int ngb_dev_profile_due(void) { return 0; }
+int ngb_dev_graph_begin(void) { return -1; }           /* no graphs on the host build: every step is launched directly */
+int ngb_dev_graph_end(void **, int *) { return -1; }
+int ngb_dev_graph_launch(void *, int) { return -1; }
+void ngb_dev_graph_destroy(void *) {}
 
 int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag)
 {
