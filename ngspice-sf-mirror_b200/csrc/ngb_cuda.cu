@@ -26,7 +26,7 @@
 static cudaStream_t g_stream = nullptr;
 static int g_device = -1;
 static long g_launches = 0;
-static int g_smem_optin = 0;
+static int g_smem_optin = 0, g_sm_count = 148;
 
 extern "C" void ngb_set_error(const char *fmt, ...);
 
@@ -152,8 +152,8 @@ __global__ void ngb_k_lu_packed(const NgbLuCtx c, int groups, int tpg, int per_s
     double *V = smem + blob_doubles + (size_t)g * per_sample_doubles;
     double *Rs = V + h->nV;
     double *Z = Rs + h->n;
-    double *As = Z;                 /* the sample's A is dead before the solve starts */
-    double *P = Z + (h->ntask > h->nnz ? h->ntask : h->nnz);
+    double *As = Z;                 /* unused: A is read from global memory */
+    double *P = Z + h->ntask;
     ngb_lu_sample_packed(&c, sb, s, lane, tpg, V, Rs, Z, As, P);
 }
 
@@ -193,6 +193,7 @@ int ngb_dev_init(int device)
     if (g_stream) cudaStreamDestroy(g_stream);
     CUDA_OK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     CUDA_OK(cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CUDA_OK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_OK(cudaFuncSetAttribute(ngb_k_lu_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
     CUDA_OK(cudaFuncSetAttribute(ngb_k_lu_block, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
     CUDA_OK(cudaFuncSetAttribute(ngb_k_lu_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
@@ -368,7 +369,7 @@ int ngb_launch_lu(const NgbLuCtx *c)
     const int per = c->sch.nV + c->sch.n + c->sch.ntask;
     const size_t bytes1 = (size_t)per * sizeof(double);
     if (c->pk.ok) {
-        const int per = c->sch.nV + c->sch.n + (c->sch.ntask > c->sch.nnz ? c->sch.ntask : c->sch.nnz) + c->pk.maxlp;   /* A aliases the solve vector */
+        const int per = c->sch.nV + c->sch.n + c->sch.ntask + c->pk.maxlp;
         const size_t bytes1 = (size_t)per * sizeof(double);
         /* schedule blob + per-sample values in shared memory.  Many samples: one warp each, one CTA
          * per SM holding as many samples as its shared memory takes (the blob is paid once per CTA);
@@ -377,7 +378,13 @@ int ngb_launch_lu(const NgbLuCtx *c)
         const size_t budget = (size_t)g_smem_optin - 1024;
         if (c->S >= 64 && blob + 4 * bytes1 <= budget) {
             int groups = (int)((budget - blob) / bytes1);
-            if (groups > 16) groups = 16;
+            if (groups > 32) groups = 32;
+            {   /* one CTA per SM and wave: the fewest waves the shared memory allows, then the smallest group
+                 * count that still needs only that many, so that the last wave is as full as the first */
+                const int waves = (c->S + groups * g_sm_count - 1) / (groups * g_sm_count);
+                const int even = (c->S + waves * g_sm_count - 1) / (waves * g_sm_count);
+                if (even >= 4 && even < groups) groups = even;
+            }
             const unsigned grid = (unsigned)((c->S + groups - 1) / groups);
             ngb_k_lu_packed<<<grid, groups * 32, blob + bytes1 * groups, g_stream>>>(*c, groups, 32, per);
             return post_launch("lu_packed");

@@ -369,16 +369,15 @@ NGB_HD void ngb_lu_sample_packed(const NgbLuCtx *c, const unsigned short *sb, in
     if (c->ctl.lusel && NGB_LDG(&c->ctl.lusel[s]) != c->which) return;
 
     if (c->do_factor) {
-        /* the sample's matrix into shared memory: one coalesced sweep */
+        /* the sample's matrix is read where it lies (L2: the assembly kernel has just written it); keeping
+         * a copy in shared memory cost a third of the samples an SM can hold */
         const double *Ax = c->Ax + (size_t)s * h->nnz;
-        for (int p = lane; p < h->nnz; p += nl) As[p] = Ax[p];
         if (lane == 0) c->singular_col[s] = -1;
-        NGB_GROUP_SYNC();
         for (int i = lane; i < n; i += nl) {
             double r = 0.0;
             const int lo = sb[h->o_rowptr + i], hi = sb[h->o_rowptr + i + 1];
             for (int p = lo; p < hi; p++) {
-                double a = fabs(As[sb[h->o_rowslot + p]]);
+                double a = fabs(NGB_LDG(&Ax[sb[h->o_rowslot + p]]));
                 r = (r > a) ? r : a;
             }
             if (r == 0.0) r = 1.0;
@@ -387,7 +386,7 @@ NGB_HD void ngb_lu_sample_packed(const NgbLuCtx *c, const unsigned short *sb, in
         NGB_GROUP_SYNC();
         for (int e = lane; e < nV; e += nl) {
             const int as = sb[h->o_aslot + e];
-            V[e] = (as != 0xFFFF) ? As[as] / Rs[sb[h->o_arow + e]] : 0.0;
+            V[e] = (as != 0xFFFF) ? NGB_LDG(&Ax[as]) / Rs[sb[h->o_arow + e]] : 0.0;
         }
         NGB_GROUP_SYNC();
         for (int lev = 0; lev < h->nlev; lev++) {
