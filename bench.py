@@ -22,6 +22,7 @@ import ctypes
 import importlib
 import json
 import os
+import re
 import subprocess
 import sys
 import tempfile
@@ -36,7 +37,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 B4_BYTES_PER_EVAL = 2000.0          # algorithmic bytes per BSIM4 instance-eval
-B4_FLOP_PER_EVAL = 3100.0           # provisional source-level FP op count per eval
+B4_FLOP_PER_EVAL = 3100.0
+# oxide-thickness levels of the Monte-Carlo workload: 8 equal-probability bins of N(1.4 nm, 3 %)
+# (tests/golden/make_golden.py: tox_levels; the BSIM4temp results per level are in ro17tox.tables.ngt)
+TOX_Z = [-1.5341205443525463, -0.8871465590188759, -0.4887764111146695, -0.15731068461017067,
+         0.15731068461017067, 0.4887764111146695, 0.8871465590188759, 1.5341205443525463]
+TOX_LEVELS = [1.4e-9 * (1.0 + 0.03 * z) for z in TOX_Z]           # provisional source-level FP op count per eval
 
 
 def peaks():
@@ -125,6 +131,7 @@ def cpu_reference_run(workload, nproc, samples_per_proc, seed0=1000):
         for k in range(samples_per_proc):
             rng = np.random.default_rng(seed0 + p * samples_per_proc + k)
             dv = rng.normal(0.0, 0.015, size=ninst) if workload != "ro101" else np.zeros(ninst)
+            tox = TOX_LEVELS[int(rng.integers(0, len(TOX_LEVELS)))] if workload != "ro101" else None
             lines, i = [], 0
             for ln in base.splitlines():
                 if ln[:2].lower() in ("mp", "mn") and " l=" in ln:
@@ -132,6 +139,8 @@ def cpu_reference_run(workload, nproc, samples_per_proc, seed0=1000):
                 lines.append(ln)
             f = os.path.join(tmp, f"s{p}_{k}.cir")
             text = "\n".join(lines).replace(".option xmu=0.49 klu", ".option xmu=0.49 klu acct")
+            if tox is not None:
+                text = re.sub(r"toxe\s*=\s*1\.4e-0*9", f"toxe    = {tox:.17g}", text)
             open(f, "w").write(text + "\n")
             files.append(f)
         jobs.append(files)
@@ -205,7 +214,7 @@ def workload_config(args):
                 "samples_per_gpu": 1, "bsim4_instances": 202, "unknowns": 911,
                 "l2": "working set smaller than L2 by nature (single circuit); no flush"}
     return {"workload": "Monte Carlo transient, 17-stage BSIM4 ring oscillator (ro_17_4.cir cards, version 4.8.3), "
-                        ".tran .1ns 150ns uic, per-instance delvto mismatch sigma 15 mV",
+                        ".tran .1ns 150ns uic, per-instance delvto mismatch sigma 15 mV and per-sample toxe from 8 levels of N(1.4 nm, 3 %)",
             "samples_per_gpu": args.samples, "bsim4_instances": 34, "unknowns": 155,
             "l2": "inputs larger than L2: per-step working set (parameters+states+stamps+matrices) ~%.0f MB" %
                   (args.samples * 34 * (51 + 4 * 29 + 38 + 52) * 8 / 1e6 + args.samples * 904 * 8 / 1e6)}
@@ -248,17 +257,24 @@ def bench_ours(args):
         inst_host = np.repeat(np.asarray(flat["b4/inst"])[:, :, None], S, axis=2)
     else:
         dv = pkg.mc.delvto_as_parsed(pkg.mc.draw_delvto(S, ninst, sigma=0.015, seed=1000 + rank))
-        inst_host = pkg.mc.bsim4_inst_with_delvto(lib, flat, dv)
+        tox_tables = ngt.read(f"{GOLDEN}/ro17tox.tables.ngt")
+        level = np.random.default_rng(5000 + rank).integers(0, len(tox_tables["levels"]), size=S)
+        inst_host, prow_t, mtab_all, ptab_all = pkg.mc.bsim4_with_tox_levels(lib, flat, tox_tables, level, dv)
+        batch.set_bsim4_rows(prow_t, mtab_all, ptab_all)
     pinned = torch.empty(inst_host.shape, dtype=torch.float64).pin_memory()
     pinned.numpy()[...] = inst_host
     out_t = torch.empty((S, max_points), dtype=torch.float64).pin_memory()
     out_v = torch.empty((S, max_points, 1), dtype=torch.float64).pin_memory()
     h2d_bytes = pinned.numel() * 8
+    if args.workload != "ro101":
+        h2d_bytes += prow_t.nbytes + mtab_all.nbytes + ptab_all.nbytes
     d2h_bytes = (out_t.numel() + out_v.numel()) * 8
 
     def step(e2e):
         if e2e:
             batch.put("b4.inst", pinned.numpy())
+            if args.workload != "ro101":
+                batch.set_bsim4_rows(prow_t, mtab_all, ptab_all)
         res = batch.tran(max_points, save_eq)
         if e2e:
             lib.check(lib.L.ngbTranWaves(batch.h, ctypes.cast(out_t.data_ptr(), ctypes.POINTER(ctypes.c_double)),

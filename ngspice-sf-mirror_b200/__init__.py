@@ -267,6 +267,12 @@ class Batch:
     def load(self):
         self.lib.check(self.lib.L.ngbLoad(self.h), "ngbLoad (CKTload)")
 
+    def set_bsim4_rows(self, prow_t, mtab, ptab):
+        """per-(instance, sample) model/bin parameter rows: Monte-Carlo with model-parameter mismatch"""
+        pr, mt, pt = _i32(prow_t), _f64(mtab), _f64(ptab)
+        assert mt.shape[1] == self.lib.layout[0] and pt.shape[1] == self.lib.layout[1] and mt.shape[0] == pt.shape[0]
+        self.lib.check(self.lib.L.ngbBatchSetBsim4Rows(self.h, _ip(pr), int(mt.shape[0]), _dp(mt), _dp(pt)), "ngbBatchSetBsim4Rows")
+
     def lufac(self):
         self.lib.check(self.lib.L.ngbLuFac(self.h), "ngbLuFac (SMPluFac)")
 

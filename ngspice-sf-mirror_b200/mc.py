@@ -10,17 +10,19 @@ SURVEY.md section 8(f) rank 1)."""
 import numpy as np
 
 
-def bsim4_inst_with_delvto(lib, flat, delvto):
-    """flat: base circuit (delvto = 0); delvto [S][ninst] -> inst table [NI][ninst][S]"""
+def bsim4_inst_with_delvto(lib, flat, delvto, tables=None):
+    """flat: base circuit (delvto = 0); delvto [S][ninst] -> inst table [NI][ninst][S].
+    tables = (inst, mtab, ptab) replaces the base circuit's BSIM4temp results (another toxe level)."""
     names = lib.fields["inst"]
     ix = {n: i for i, n in enumerate(names)}
-    base = np.asarray(flat["b4/inst"], dtype=np.float64)            # [NI][ninst]
+    inst0, mtab0, ptab0 = tables if tables is not None else (flat["b4/inst"], flat["b4/mtab"], flat["b4/ptab"])
+    base = np.asarray(inst0, dtype=np.float64)                      # [NI][ninst]
     S, ninst = delvto.shape
     assert ninst == base.shape[1]
     mnames = lib.fields["model"]; pnames = lib.fields["bin"]
     prow = flat["b4/prow"]
-    typ = flat["b4/mtab"][prow, mnames.index("type")]                # [ninst]
-    phi = flat["b4/ptab"][prow, pnames.index("phi")]
+    typ = mtab0[prow, mnames.index("type")]                          # [ninst]
+    phi = ptab0[prow, pnames.index("phi")]
     out = np.repeat(base[:, :, None], S, axis=2)
     dv = delvto.T                                                    # [ninst][S]
     vth0_b = base[ix["vth0"]][:, None]; vfb_b = base[ix["vfb"]][:, None]
@@ -34,6 +36,27 @@ def bsim4_inst_with_delvto(lib, flat, delvto):
     out[ix["vtfbphi2"]] = np.maximum(4.0 * T3, 0.0)
     out[ix["vfbzb"]] = vfbzbfactor + typ[:, None] * vth0
     return out
+
+
+def bsim4_with_tox_levels(lib, flat, tables, level, delvto):
+    """Model-parameter mismatch on top of delvto: every sample s uses the BSIM4temp results of
+    oxide-thickness level `level[s]` (tables: tests/golden/ro17tox.tables.ngt -- what `altermod toxe=`
+    followed by CKTtemp produces, recorded from the reference for 8 levels).
+    Returns (inst [NI][ninst][S], prow_t [ninst*S], mtab [L*rows][NM], ptab [L*rows][NP])."""
+    level = np.asarray(level, dtype=np.int64)
+    S, ninst = delvto.shape
+    L = len(tables["levels"])
+    nrows = tables["mtab0"].shape[0]
+    prow = np.asarray(flat["b4/prow"], dtype=np.int64)
+    inst = np.empty((len(lib.fields["inst"]), ninst, S))
+    for k in range(L):
+        sel = np.nonzero(level == k)[0]
+        if len(sel):
+            inst[:, :, sel] = bsim4_inst_with_delvto(lib, flat, delvto[sel], (tables[f"inst{k}"], tables[f"mtab{k}"], tables[f"ptab{k}"]))
+    prow_t = (level[None, :] * nrows + prow[:, None]).astype(np.int32).reshape(-1)       # [ninst][S], sample fastest
+    mtab = np.concatenate([tables[f"mtab{k}"] for k in range(L)], axis=0)
+    ptab = np.concatenate([tables[f"ptab{k}"] for k in range(L)], axis=0)
+    return inst, prow_t, mtab, ptab
 
 
 def spice_number(text):

@@ -10,6 +10,7 @@ and test files.  Needs /root/reference; the fixtures it writes do not.
   inv    tests/bsim4/{nmos,pmos}/parameters cards, CMOS inverter with PULSE input (config 1).
   b3ring BSIM3v3.3.0 ring of five inverters + buffer on the MC_ring.sp level-8 cards.
   arr    4x4 BSIM4 inverter array with RC links (small instance of config 4's generator).
+  ro17tox BSIM4temp tables for 8 oxide-thickness levels + two reference transients with toxe and delvto mismatch.
   dio    junction diodes (rectifier, zener clamp, sidewall/tunnel/knee parameters) with R, C, SIN source.
 
 Outputs (tests/golden/): <name>.flat.ngt  flattened circuit after CKTsetup/CKTtemp
@@ -133,6 +134,21 @@ def b3_netlist(stages=5):
     return "\n".join(lines) + "\n" + b3_cards() + "\n.end\n"
 
 
+TOX_Z = [-1.5341205443525463, -0.8871465590188759, -0.4887764111146695, -0.15731068461017067,
+         0.15731068461017067, 0.4887764111146695, 0.8871465590188759, 1.5341205443525463]   # 8 equal-probability Gaussian bins
+
+
+def tox_levels(nominal=1.4e-9, sigma=0.03):
+    return [nominal * (1.0 + sigma * z) for z in TOX_Z]
+
+
+def with_toxe(netlist, toxe):
+    """both model cards get the same oxide thickness (a per-sample, die-level variation)"""
+    out = re.sub(r"toxe\s*=\s*1\.4e-0*9", f"toxe    = {toxe:.17g}", netlist)
+    assert out != netlist
+    return out
+
+
 def read_raw(path):
     data = open(path, "rb").read()
     i = data.index(b"Binary:\n")
@@ -218,5 +234,24 @@ if __name__ == "__main__":
         synth = importlib.import_module("ngspice-sf-mirror_b200.synth")
         run("arr", synth.inverter_array_netlist(4, 4, ro_cards()), "0-30,100,101,400,401",
             ["out_0_0", "out_3_3", "in_2_1", "vdd#branch"])
+    if "ro17tox" in which:
+        # model-parameter mismatch: BSIM4temp results for 8 discrete oxide-thickness levels (what `altermod
+        # toxe=...` + CKTtemp produce), plus two complete reference transients with toxe AND delvto mismatch
+        levels = tox_levels()
+        tabs = {"levels": np.array(levels)}
+        for k, tox in enumerate(levels):
+            run(f"_tox{k}", with_toxe(ro_netlist(17, tran=".tran .1ns 0.2ns uic", kick=True), tox), "0", ["18"])
+            fl = ngt.read(os.path.join(HERE, f"_tox{k}.flat.ngt"))
+            tabs[f"mtab{k}"] = fl["b4/mtab"]; tabs[f"ptab{k}"] = fl["b4/ptab"]; tabs[f"inst{k}"] = fl["b4/inst"]
+            tabs["prow"] = fl["b4/prow"]
+            for ext in (".flat.ngt", ".trace.ngt.gz", ".wave.ngt"):
+                os.remove(os.path.join(HERE, f"_tox{k}" + ext))
+        ngt.write(os.path.join(HERE, "ro17tox.tables.ngt"), tabs)
+        rng = np.random.default_rng(11)
+        dv = rng.normal(0.0, 0.015, size=(2, 34)); lev = np.array([1, 6])
+        np.save(os.path.join(HERE, "ro17tox.delvto.npy"), dv); np.save(os.path.join(HERE, "ro17tox.level.npy"), lev)
+        for i in range(2):
+            run(f"ro17tox{i}", with_toxe(ro_netlist(17, tran=".tran .1ns 20ns uic", kick=True, delvto=dv[i]), levels[lev[i]]),
+                "1", ["18", "2", "9", "vdd#branch"])
     if "ro101" in which:
         run("ro101", ro_netlist(101), "1,2,3000", ["102", "2", "50", "vdd#branch"])

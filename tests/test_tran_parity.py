@@ -124,3 +124,44 @@ def test_tran_gpu_mc_host_side_mismatch(cuda_lib):
     for s in range(dv.shape[0]):
         wave = ngt.read(f"{GOLDEN}/ro17mc{s}.wave.ngt")
         _compare(res, t, v, wave, s, exact=True)
+
+
+def _tox_batch(lib):
+    """two samples with different oxide-thickness levels AND per-instance delvto, in one batch"""
+    base = ngt.read(f"{GOLDEN}/ro17k.flat.ngt")
+    trace = ngt.read(f"{GOLDEN}/ro17k.trace.ngt.gz")
+    tables = ngt.read(f"{GOLDEN}/ro17tox.tables.ngt")
+    dv_netlist = np.load(f"{GOLDEN}/ro17tox.delvto.npy"); level = np.load(f"{GOLDEN}/ro17tox.level.npy")
+    col = {}
+    for k in range(1, 18):
+        col[f"mp{k}"] = 2 * (k - 1); col[f"mn{k}"] = 2 * (k - 1) + 1
+    order = [col[n.lower()] for n in pkg.mc.instance_names(base)]
+    dv = pkg.mc.delvto_as_parsed(dv_netlist[:, order])
+    inst, prow_t, mtab, ptab = pkg.mc.bsim4_with_tox_levels(lib, base, tables, level, dv)
+    for i in range(2):                       # the assembled tables equal what BSIM4temp wrote for each sample
+        ref = ngt.read(f"{GOLDEN}/ro17tox{i}.flat.ngt")
+        assert np.array_equal(inst[:, :, i], ref["b4/inst"])
+        assert np.array_equal(mtab[prow_t.reshape(34, 2)[:, i]], ref["b4/mtab"][ref["b4/prow"]])
+        assert np.array_equal(ptab[prow_t.reshape(34, 2)[:, i]], ref["b4/ptab"][ref["b4/prow"]])
+    circ = pkg.Circuit.from_flat(lib, base, lu_pattern=run_patterns(trace))
+    b = pkg.Batch(circ, 2)
+    b.put("b4.inst", inst)
+    b.set_bsim4_rows(prow_t, mtab, ptab)
+    wave0 = ngt.read(f"{GOLDEN}/ro17tox0.wave.ngt")
+    res = b.tran(1024, wave0["save_eq"])
+    t, v = res.waves()
+    return res, t, v
+
+
+def test_tran_hostsim_tox_and_vth_mismatch(hostsim_lib):
+    """model-parameter (toxe) plus instance (delvto) mismatch: each sample equals its own reference run"""
+    res, t, v = _tox_batch(hostsim_lib)
+    for s in range(2):
+        _compare(res, t, v, ngt.read(f"{GOLDEN}/ro17tox{s}.wave.ngt"), s, exact=True)
+
+
+@pytest.mark.gpu
+def test_tran_gpu_tox_and_vth_mismatch(cuda_lib):
+    res, t, v = _tox_batch(cuda_lib)
+    for s in range(2):
+        _compare(res, t, v, ngt.read(f"{GOLDEN}/ro17tox{s}.wave.ngt"), s, exact=True)
