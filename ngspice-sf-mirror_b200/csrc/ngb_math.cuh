@@ -254,4 +254,161 @@ NGB_MATH_FN double ngb_log(double x)
     const double p = fma(r2, fma(r, A4, A3), fma(r, A2, A1));
     return fma(r * r2, p, fma(r2, A0, lo)) + hi;
 }
+/* pow(): log_inline with the 128-entry table of glibc's __pow_log_data (invc, logc, logctail per
+ * entry), then exp with the low part of y*log(x) carried along (e_pow.c of glibc 2.39, FMA variant,
+ * operation order as executed by __pow_fma).  Main path: x positive and normal, 2^-65 <= |y| < 2^63,
+ * 2^-54 <= |y*log x| < 512; everything else takes the platform's pow(). */
+NGB_TABLE unsigned long long ngb_pow_tab[384] = {
+    0x3ff6a00000000000ULL, 0xbfd62c82f2b9c800ULL, 0x3cfab42428375680ULL, 0x3ff6800000000000ULL,
+    0xbfd5d1bdbf580800ULL, 0xbd1ca508d8e0f720ULL, 0x3ff6600000000000ULL, 0xbfd5767717455800ULL,
+    0xbd2362a4d5b6506dULL, 0x3ff6400000000000ULL, 0xbfd51aad872df800ULL, 0xbce684e49eb067d5ULL,
+    0x3ff6200000000000ULL, 0xbfd4be5f95777800ULL, 0xbd041b6993293ee0ULL, 0x3ff6000000000000ULL,
+    0xbfd4618bc21c6000ULL, 0x3d13d82f484c84ccULL, 0x3ff5e00000000000ULL, 0xbfd404308686a800ULL,
+    0x3cdc42f3ed820b3aULL, 0x3ff5c00000000000ULL, 0xbfd3a64c55694800ULL, 0x3d20b1c686519460ULL,
+    0x3ff5a00000000000ULL, 0xbfd347dd9a988000ULL, 0x3d25594dd4c58092ULL, 0x3ff5800000000000ULL,
+    0xbfd2e8e2bae12000ULL, 0x3d267b1e99b72bd8ULL, 0x3ff5600000000000ULL, 0xbfd2895a13de8800ULL,
+    0x3d15ca14b6cfb03fULL, 0x3ff5600000000000ULL, 0xbfd2895a13de8800ULL, 0x3d15ca14b6cfb03fULL,
+    0x3ff5400000000000ULL, 0xbfd22941fbcf7800ULL, 0xbd165a242853da76ULL, 0x3ff5200000000000ULL,
+    0xbfd1c898c1699800ULL, 0xbd1fafbc68e75404ULL, 0x3ff5000000000000ULL, 0xbfd1675cababa800ULL,
+    0x3d1f1fc63382a8f0ULL, 0x3ff4e00000000000ULL, 0xbfd1058bf9ae4800ULL, 0xbd26a8c4fd055a66ULL,
+    0x3ff4c00000000000ULL, 0xbfd0a324e2739000ULL, 0xbd0c6bee7ef4030eULL, 0x3ff4a00000000000ULL,
+    0xbfd0402594b4d000ULL, 0xbcf036b89ef42d7fULL, 0x3ff4a00000000000ULL, 0xbfd0402594b4d000ULL,
+    0xbcf036b89ef42d7fULL, 0x3ff4800000000000ULL, 0xbfcfb9186d5e4000ULL, 0x3d0d572aab993c87ULL,
+    0x3ff4600000000000ULL, 0xbfcef0adcbdc6000ULL, 0x3d2b26b79c86af24ULL, 0x3ff4400000000000ULL,
+    0xbfce27076e2af000ULL, 0xbd172f4f543fff10ULL, 0x3ff4200000000000ULL, 0xbfcd5c216b4fc000ULL,
+    0x3d21ba91bbca681bULL, 0x3ff4000000000000ULL, 0xbfcc8ff7c79aa000ULL, 0x3d27794f689f8434ULL,
+    0x3ff4000000000000ULL, 0xbfcc8ff7c79aa000ULL, 0x3d27794f689f8434ULL, 0x3ff3e00000000000ULL,
+    0xbfcbc286742d9000ULL, 0x3d194eb0318bb78fULL, 0x3ff3c00000000000ULL, 0xbfcaf3c94e80c000ULL,
+    0x3cba4e633fcd9066ULL, 0x3ff3a00000000000ULL, 0xbfca23bc1fe2b000ULL, 0xbd258c64dc46c1eaULL,
+    0x3ff3a00000000000ULL, 0xbfca23bc1fe2b000ULL, 0xbd258c64dc46c1eaULL, 0x3ff3800000000000ULL,
+    0xbfc9525a9cf45000ULL, 0xbd2ad1d904c1d4e3ULL, 0x3ff3600000000000ULL, 0xbfc87fa06520d000ULL,
+    0x3d2bbdbf7fdbfa09ULL, 0x3ff3400000000000ULL, 0xbfc7ab890210e000ULL, 0x3d2bdb9072534a58ULL,
+    0x3ff3400000000000ULL, 0xbfc7ab890210e000ULL, 0x3d2bdb9072534a58ULL, 0x3ff3200000000000ULL,
+    0xbfc6d60fe719d000ULL, 0xbd10e46aa3b2e266ULL, 0x3ff3000000000000ULL, 0xbfc5ff3070a79000ULL,
+    0xbd1e9e439f105039ULL, 0x3ff3000000000000ULL, 0xbfc5ff3070a79000ULL, 0xbd1e9e439f105039ULL,
+    0x3ff2e00000000000ULL, 0xbfc526e5e3a1b000ULL, 0xbd20de8b90075b8fULL, 0x3ff2c00000000000ULL,
+    0xbfc44d2b6ccb8000ULL, 0x3d170cc16135783cULL, 0x3ff2c00000000000ULL, 0xbfc44d2b6ccb8000ULL,
+    0x3d170cc16135783cULL, 0x3ff2a00000000000ULL, 0xbfc371fc201e9000ULL, 0x3cf178864d27543aULL,
+    0x3ff2800000000000ULL, 0xbfc29552f81ff000ULL, 0xbd248d301771c408ULL, 0x3ff2600000000000ULL,
+    0xbfc1b72ad52f6000ULL, 0xbd2e80a41811a396ULL, 0x3ff2600000000000ULL, 0xbfc1b72ad52f6000ULL,
+    0xbd2e80a41811a396ULL, 0x3ff2400000000000ULL, 0xbfc0d77e7cd09000ULL, 0x3d0a699688e85bf4ULL,
+    0x3ff2400000000000ULL, 0xbfc0d77e7cd09000ULL, 0x3d0a699688e85bf4ULL, 0x3ff2200000000000ULL,
+    0xbfbfec9131dbe000ULL, 0xbd2575545ca333f2ULL, 0x3ff2000000000000ULL, 0xbfbe27076e2b0000ULL,
+    0x3d2a342c2af0003cULL, 0x3ff2000000000000ULL, 0xbfbe27076e2b0000ULL, 0x3d2a342c2af0003cULL,
+    0x3ff1e00000000000ULL, 0xbfbc5e548f5bc000ULL, 0xbd1d0c57585fbe06ULL, 0x3ff1c00000000000ULL,
+    0xbfba926d3a4ae000ULL, 0x3d253935e85baac8ULL, 0x3ff1c00000000000ULL, 0xbfba926d3a4ae000ULL,
+    0x3d253935e85baac8ULL, 0x3ff1a00000000000ULL, 0xbfb8c345d631a000ULL, 0x3d137c294d2f5668ULL,
+    0x3ff1a00000000000ULL, 0xbfb8c345d631a000ULL, 0x3d137c294d2f5668ULL, 0x3ff1800000000000ULL,
+    0xbfb6f0d28ae56000ULL, 0xbd269737c93373daULL, 0x3ff1600000000000ULL, 0xbfb51b073f062000ULL,
+    0x3d1f025b61c65e57ULL, 0x3ff1600000000000ULL, 0xbfb51b073f062000ULL, 0x3d1f025b61c65e57ULL,
+    0x3ff1400000000000ULL, 0xbfb341d7961be000ULL, 0x3d2c5edaccf913dfULL, 0x3ff1400000000000ULL,
+    0xbfb341d7961be000ULL, 0x3d2c5edaccf913dfULL, 0x3ff1200000000000ULL, 0xbfb16536eea38000ULL,
+    0x3d147c5e768fa309ULL, 0x3ff1000000000000ULL, 0xbfaf0a30c0118000ULL, 0x3d2d599e83368e91ULL,
+    0x3ff1000000000000ULL, 0xbfaf0a30c0118000ULL, 0x3d2d599e83368e91ULL, 0x3ff0e00000000000ULL,
+    0xbfab42dd71198000ULL, 0x3d1c827ae5d6704cULL, 0x3ff0e00000000000ULL, 0xbfab42dd71198000ULL,
+    0x3d1c827ae5d6704cULL, 0x3ff0c00000000000ULL, 0xbfa77458f632c000ULL, 0xbd2cfc4634f2a1eeULL,
+    0x3ff0c00000000000ULL, 0xbfa77458f632c000ULL, 0xbd2cfc4634f2a1eeULL, 0x3ff0a00000000000ULL,
+    0xbfa39e87b9fec000ULL, 0x3cf502b7f526feaaULL, 0x3ff0a00000000000ULL, 0xbfa39e87b9fec000ULL,
+    0x3cf502b7f526feaaULL, 0x3ff0800000000000ULL, 0xbf9f829b0e780000ULL, 0xbd2980267c7e09e4ULL,
+    0x3ff0800000000000ULL, 0xbf9f829b0e780000ULL, 0xbd2980267c7e09e4ULL, 0x3ff0600000000000ULL,
+    0xbf97b91b07d58000ULL, 0xbd288d5493faa639ULL, 0x3ff0400000000000ULL, 0xbf8fc0a8b0fc0000ULL,
+    0xbcdf1e7cf6d3a69cULL, 0x3ff0400000000000ULL, 0xbf8fc0a8b0fc0000ULL, 0xbcdf1e7cf6d3a69cULL,
+    0x3ff0200000000000ULL, 0xbf7fe02a6b100000ULL, 0xbd19e23f0dda40e4ULL, 0x3ff0200000000000ULL,
+    0xbf7fe02a6b100000ULL, 0xbd19e23f0dda40e4ULL, 0x3ff0000000000000ULL, 0x0000000000000000ULL,
+    0x0000000000000000ULL, 0x3ff0000000000000ULL, 0x0000000000000000ULL, 0x0000000000000000ULL,
+    0x3fefc00000000000ULL, 0x3f80101575890000ULL, 0xbd10c76b999d2be8ULL, 0x3fef800000000000ULL,
+    0x3f90205658938000ULL, 0xbd23dc5b06e2f7d2ULL, 0x3fef400000000000ULL, 0x3f98492528c90000ULL,
+    0xbd2aa0ba325a0c34ULL, 0x3fef000000000000ULL, 0x3fa0415d89e74000ULL, 0x3d0111c05cf1d753ULL,
+    0x3feec00000000000ULL, 0x3fa466aed42e0000ULL, 0xbd2c167375bdfd28ULL, 0x3fee800000000000ULL,
+    0x3fa894aa149fc000ULL, 0xbd197995d05a267dULL, 0x3fee400000000000ULL, 0x3faccb73cdddc000ULL,
+    0xbd1a68f247d82807ULL, 0x3fee200000000000ULL, 0x3faeea31c006c000ULL, 0xbd0e113e4fc93b7bULL,
+    0x3fede00000000000ULL, 0x3fb1973bd1466000ULL, 0xbd25325d560d9e9bULL, 0x3feda00000000000ULL,
+    0x3fb3bdf5a7d1e000ULL, 0x3d2cc85ea5db4ed7ULL, 0x3fed600000000000ULL, 0x3fb5e95a4d97a000ULL,
+    0xbd2c69063c5d1d1eULL, 0x3fed400000000000ULL, 0x3fb700d30aeac000ULL, 0x3cec1e8da99ded32ULL,
+    0x3fed000000000000ULL, 0x3fb9335e5d594000ULL, 0x3d23115c3abd47daULL, 0x3fecc00000000000ULL,
+    0x3fbb6ac88dad6000ULL, 0xbd1390802bf768e5ULL, 0x3feca00000000000ULL, 0x3fbc885801bc4000ULL,
+    0x3d2646d1c65aacd3ULL, 0x3fec600000000000ULL, 0x3fbec739830a2000ULL, 0xbd2dc068afe645e0ULL,
+    0x3fec400000000000ULL, 0x3fbfe89139dbe000ULL, 0xbd2534d64fa10afdULL, 0x3fec000000000000ULL,
+    0x3fc1178e8227e000ULL, 0x3d21ef78ce2d07f2ULL, 0x3febe00000000000ULL, 0x3fc1aa2b7e23f000ULL,
+    0x3d2ca78e44389934ULL, 0x3feba00000000000ULL, 0x3fc2d1610c868000ULL, 0x3d039d6ccb81b4a1ULL,
+    0x3feb800000000000ULL, 0x3fc365fcb0159000ULL, 0x3cc62fa8234b7289ULL, 0x3feb400000000000ULL,
+    0x3fc4913d8333b000ULL, 0x3d25837954fdb678ULL, 0x3feb200000000000ULL, 0x3fc527e5e4a1b000ULL,
+    0x3d2633e8e5697dc7ULL, 0x3feae00000000000ULL, 0x3fc6574ebe8c1000ULL, 0x3d19cf8b2c3c2e78ULL,
+    0x3feac00000000000ULL, 0x3fc6f0128b757000ULL, 0xbd25118de59c21e1ULL, 0x3feaa00000000000ULL,
+    0x3fc7898d85445000ULL, 0xbd1c661070914305ULL, 0x3fea600000000000ULL, 0x3fc8beafeb390000ULL,
+    0xbd073d54aae92cd1ULL, 0x3fea400000000000ULL, 0x3fc95a5adcf70000ULL, 0x3d07f22858a0ff6fULL,
+    0x3fea000000000000ULL, 0x3fca93ed3c8ae000ULL, 0xbd28724350562169ULL, 0x3fe9e00000000000ULL,
+    0x3fcb31d8575bd000ULL, 0xbd0c358d4eace1aaULL, 0x3fe9c00000000000ULL, 0x3fcbd087383be000ULL,
+    0xbd2d4bc4595412b6ULL, 0x3fe9a00000000000ULL, 0x3fcc6ffbc6f01000ULL, 0xbcf1ec72c5962bd2ULL,
+    0x3fe9600000000000ULL, 0x3fcdb13db0d49000ULL, 0xbd2aff2af715b035ULL, 0x3fe9400000000000ULL,
+    0x3fce530effe71000ULL, 0x3cc212276041f430ULL, 0x3fe9200000000000ULL, 0x3fcef5ade4dd0000ULL,
+    0xbcca211565bb8e11ULL, 0x3fe9000000000000ULL, 0x3fcf991c6cb3b000ULL, 0x3d1bcbecca0cdf30ULL,
+    0x3fe8c00000000000ULL, 0x3fd07138604d5800ULL, 0x3cf89cdb16ed4e91ULL, 0x3fe8a00000000000ULL,
+    0x3fd0c42d67616000ULL, 0x3d27188b163ceae9ULL, 0x3fe8800000000000ULL, 0x3fd1178e8227e800ULL,
+    0xbd2c210e63a5f01cULL, 0x3fe8600000000000ULL, 0x3fd16b5ccbacf800ULL, 0x3d2b9acdf7a51681ULL,
+    0x3fe8400000000000ULL, 0x3fd1bf99635a6800ULL, 0x3d2ca6ed5147bdb7ULL, 0x3fe8200000000000ULL,
+    0x3fd214456d0eb800ULL, 0x3d0a87deba46baeaULL, 0x3fe7e00000000000ULL, 0x3fd2bef07cdc9000ULL,
+    0x3d2a9cfa4a5004f4ULL, 0x3fe7c00000000000ULL, 0x3fd314f1e1d36000ULL, 0xbd28e27ad3213cb8ULL,
+    0x3fe7a00000000000ULL, 0x3fd36b6776be1000ULL, 0x3d116ecdb0f177c8ULL, 0x3fe7800000000000ULL,
+    0x3fd3c25277333000ULL, 0x3d183b54b606bd5cULL, 0x3fe7600000000000ULL, 0x3fd419b423d5e800ULL,
+    0x3d08e436ec90e09dULL, 0x3fe7400000000000ULL, 0x3fd4718dc271c800ULL, 0xbd2f27ce0967d675ULL,
+    0x3fe7200000000000ULL, 0x3fd4c9e09e173000ULL, 0xbd2e20891b0ad8a4ULL, 0x3fe7000000000000ULL,
+    0x3fd522ae0738a000ULL, 0x3d2ebe708164c759ULL, 0x3fe6e00000000000ULL, 0x3fd57bf753c8d000ULL,
+    0x3d1fadedee5d40efULL, 0x3fe6c00000000000ULL, 0x3fd5d5bddf596000ULL, 0xbd0a0b2a08a465dcULL,
+};
+
+NGB_MATH_FN double ngb_pow(double x, double y)
+{
+    const double Ln2hi = 0x1.62e42fefa3800p-1, Ln2lo = 0x1.ef35793c76730p-45;
+    const double A0 = -0x1.0000000000000p-1, A1 = -0x1.5555555555560p-1, A2 = 0x1.0000000000006p-1, A3 = 0x1.999999959554ep-1,
+                 A4 = -0x1.555555529a47ap-1, A5 = -0x1.2495b9b4845e9p+0, A6 = 0x1.0002b8b263fc3p+0;
+    const double InvLn2N = 0x1.71547652b82fep+7, Shift = 0x1.8000000000000p+52;
+    const double NegLn2hiN = -0x1.62e42fefa0000p-8, NegLn2loN = -0x1.cf79abc9e3b3ap-47;
+    const double C2 = 0x1.ffffffffffdbdp-2, C3 = 0x1.555555555543cp-3, C4 = 0x1.55555cf172b91p-5, C5 = 0x1.1111167a4d017p-7;
+    const unsigned long long ix = ngb_d2bits(x), iy = ngb_d2bits(y);
+    const unsigned topx = (unsigned)(ix >> 52), topy = (unsigned)(iy >> 52);
+    if (topx - 0x001u >= 0x7ffu - 0x001u || (topy & 0x7ffu) - 0x3beu >= 0x43eu - 0x3beu) return pow(x, y);
+    /* log_inline */
+    const unsigned long long tmp = ix - 0x3fe6955500000000ULL;
+    const unsigned i = (unsigned)(tmp >> 45) & 127u;
+    const int k = (int)((long long)tmp >> 52);
+    const unsigned long long iz = ix - (tmp & 0xfff0000000000000ULL);
+    const double z = ngb_bits2d(iz), kd = (double)k;
+    const double invc = ngb_bits2d(NGB_TAB(ngb_pow_tab, 3 * i)), logc = ngb_bits2d(NGB_TAB(ngb_pow_tab, 3 * i + 1)),
+                 logctail = ngb_bits2d(NGB_TAB(ngb_pow_tab, 3 * i + 2));
+    const double r = fma(z, invc, -1.0);
+    const double t1 = fma(kd, Ln2hi, logc);
+    const double t2 = t1 + r;
+    const double lo1 = fma(kd, Ln2lo, logctail);
+    const double lo2 = (t1 - t2) + r;
+    const double ar = A0 * r, ar2 = r * ar, ar3 = r * ar2;
+    const double hi = t2 + ar2;
+    const double lo3 = fma(ar, r, -ar2);
+    const double lo4 = (t2 - hi) + ar2;
+    const double pp = fma(ar2, fma(fma(r, A6, A5), ar2, fma(r, A4, A3)), fma(r, A2, A1));
+    const double lo = fma(ar3, pp, ((lo1 + lo2) + lo3) + lo4);
+    const double lhi = hi + lo;
+    const double ltail = (hi - lhi) + lo;
+    /* y * log(x) as ehi + elo */
+    const double ehi = y * lhi;
+    const double elo = fma(y, ltail, fma(lhi, y, -ehi));
+    /* exp_inline(ehi, elo) */
+    const unsigned abstop = (unsigned)(ngb_d2bits(ehi) >> 52) & 0x7ffu;
+    if (abstop - 0x3c9u >= 0x3fu) return pow(x, y);
+    double kq = fma(ehi, InvLn2N, Shift);
+    const unsigned long long ki = ngb_d2bits(kq);
+    kq -= Shift;
+    double rr = fma(kq, NegLn2loN, fma(kq, NegLn2hiN, ehi));
+    rr = elo + rr;
+    const unsigned idx = 2u * (unsigned)(ki & 127u);
+    const unsigned long long top = ki << 45;
+    const double tail = ngb_bits2d(NGB_TAB(ngb_exp_tab, idx));
+    const unsigned long long sbits = NGB_TAB(ngb_exp_tab, idx + 1) + top;
+    const double r2 = rr * rr;
+    const double p1 = fma(rr, C3, C2), p2 = fma(rr, C5, C4);
+    const double tm = fma(r2 * r2, p2, fma(r2, p1, tail + rr));
+    const double scale = ngb_bits2d(sbits);
+    return fma(scale, tm, scale);
+}
+
 #endif

@@ -91,4 +91,5 @@ int ngb_launch_tran_control(const NgbTranCtx *c)
 
 /* test entry points for the libm-compatible exp/log (tests/test_math_replica.py) */
 extern "C" void hostsim_exp(const double *x, double *y, int n) { for (int i = 0; i < n; i++) y[i] = ngb_exp(x[i]); }
+extern "C" void hostsim_pow(const double *x, const double *y, double *z, int n) { for (int i = 0; i < n; i++) z[i] = ngb_pow(x[i], y[i]); }
 extern "C" void hostsim_log(const double *x, double *y, int n) { for (int i = 0; i < n; i++) y[i] = ngb_log(x[i]); }

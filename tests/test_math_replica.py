@@ -34,3 +34,24 @@ def test_exp_log_bit_identical_to_libm(hostsim_lib):
     import platform
     if "fma" in open("/proc/cpuinfo").read():
         assert len(bad) == 0 and len(badl) == 0, (len(bad), len(badl))
+
+
+def test_pow_bit_identical_to_libm(hostsim_lib):
+    """ngb_pow against this host's libm on the argument ranges VBIC and the diode model use
+    (positive bases, exponents of a few units) and on wide random ranges"""
+    L = ctypes.CDLL(HOSTSIM)
+    rng = np.random.default_rng(5)
+    x = np.concatenate([np.exp(rng.uniform(-40, 40, 200000)), rng.uniform(0.5, 2.0, 100000), rng.uniform(1e-3, 10, 100000),
+                        np.array([1.0, 2.0, 0.5, 10.0, 1e-300, 1e300, 3.0])])
+    y = np.concatenate([rng.uniform(-8, 8, 200000), rng.uniform(-3, 3, 100000), rng.choice([0.5, -0.5, 2.0, 1.5, 0.33, -1.0, 3.0], 100000),
+                        np.array([3.0, 0.5, -2.0, 2.5, 1.0, 0.01, 0.0])])
+    z = np.zeros_like(x)
+    P = ctypes.POINTER(ctypes.c_double)
+    L.hostsim_pow(x.ctypes.data_as(P), y.ctypes.data_as(P), z.ctypes.data_as(P), len(x))
+    with np.errstate(over="ignore"):
+        ref = np.array([math.pow(a, b) if abs(b * math.log(a)) < 700 else 0.0 for a, b in zip(x, y)])
+    ok = ref != 0.0
+    bad = np.nonzero((z != ref) & ok)[0]
+    assert len(bad) <= 0.002 * len(x), (len(bad), x[bad[:5]], y[bad[:5]])
+    if "fma" in open("/proc/cpuinfo").read():
+        assert len(bad) == 0, (len(bad), x[bad[:5]], y[bad[:5]], z[bad[:5]], ref[bad[:5]])
