@@ -79,11 +79,11 @@ int ngbCircuitAddCapacitors(ngb_circuit *c, int n, const int *nodes /* [2][n] */
 int ngbCircuitAddBsim3(ngb_circuit *c, int ninst, const int *nodes, const int *flags, const int *prow,
                        const double *inst, int nrows, const double *mtab, const double *ptab);
 void ngbBsim3Layout(int out[6]);               /* model, bin, instance, node roles, stamp rows, states */
-/* junction diodes after DIOsetup/DIOtemp (dio/diosetup.c, diotemp.c): nodes [3][n] pos neg posPrime
- * (posPrime == pos without series resistance), flags [n] DIOF_* and par [DIOP_COUNT][n] as listed
- * in csrc/dio_fields.h -- replaces the DIOinstance/DIOmodel walk of DIOload (dio/dioload.c:75-80).
- * Options outside this path (separate sidewall diode, self-heating, soft reverse recovery,
- * recombination current) return E_UNSUPP */
+/* junction diodes after DIOsetup/DIOtemp (dio/diosetup.c, diotemp.c): nodes [4][n] pos neg posPrime
+ * posSwPrime (posPrime == pos without series resistance; posSwPrime only with a separate sidewall diode),
+ * flags [n] DIOF_* and par [DIOP_COUNT][n] as listed in csrc/dio_fields.h -- replaces the
+ * DIOinstance/DIOmodel walk of DIOload (dio/dioload.c:75-80).  Self-heating and soft reverse recovery
+ * return E_UNSUPP */
 int ngbCircuitAddDiodes(ngb_circuit *c, int n, const int *nodes, const int *flags, const double *par);
 int ngbCircuitAddVsources(ngb_circuit *c, int n, const int *nodes /* [3][n] pos neg branch */,
                           const int *fn /* [3][n] type order dcGiven */, const double *par /* [9][n] */);

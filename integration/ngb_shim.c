@@ -160,12 +160,13 @@ static int flatten_dio(CKTcircuit *ckt)
     DIOmodel *m; DIOinstance *h;
     int n = G.nd, i = 0, rc; int *nodes, *flags; double *par;
     if (!n) return 0;
-    nodes = (int *)xc((size_t)n * 3, sizeof(int)); flags = (int *)xc((size_t)n, sizeof(int)); G.sbd = (int *)xc((size_t)n, sizeof(int));
+    nodes = (int *)xc((size_t)n * 4, sizeof(int)); flags = (int *)xc((size_t)n, sizeof(int)); G.sbd = (int *)xc((size_t)n, sizeof(int));
     par = (double *)xc((size_t)n * DIOP_COUNT, sizeof(double));
     for (m = (DIOmodel *)ckt->CKThead[G.tDIO]; m; m = DIOnextModel(m))
         for (h = DIOinstances(m); h; h = DIOnextInstance(h), i++) {
             int fl = 0, k = 0;
             nodes[i] = h->DIOposNode; nodes[n + i] = h->DIOnegNode; nodes[2 * n + i] = h->DIOposPrimeNode;
+            nodes[3 * n + i] = h->DIOposSwPrimeNode;
             if (h->DIOoff) fl |= DIOF_OFF;
             if (m->DIObreakdownVoltageGiven) fl |= DIOF_BV;
             if (m->DIOsatSWCurGiven) fl |= DIOF_SATSW;

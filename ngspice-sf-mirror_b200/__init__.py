@@ -168,7 +168,7 @@ class Circuit:
         if n:
             par = _f64(flat["dio/par"])
             assert par.shape[0] == lib.dio_layout[0], "fixture built against a different diode field list"
-            lib.check(lib.L.ngbCircuitAddDiodes(c.h, int(n), _ip(_i32(flat["dio/nodes"][[0, 1, 3]])), _ip(_i32(flat["dio/flags"])),
+            lib.check(lib.L.ngbCircuitAddDiodes(c.h, int(n), _ip(_i32(flat["dio/nodes"][[0, 1, 3, 4]])), _ip(_i32(flat["dio/flags"])),
                                                 _dp(par)), "ngbCircuitAddDiodes")
         n = sc(flat, "vsrc/n", 0)
         if n:

@@ -10,9 +10,10 @@
   X(tConductance) X(tJctCap) X(tJctPot) X(tDepCap) X(tGradingCoeff) X(tF1) X(tF2) X(tF3) \
   X(tJctSWCap) X(tJctSWPot) X(tDepSWCap) X(tF2SW) X(tF3SW) X(tTransitTime) \
   X(tTunSatCur) X(tTunSatCur_dT) X(tTunSatSWCur) X(tTunSatSWCur_dT) \
-  X(forwardKneeCurrent) X(reverseKneeCurrent) X(forwardSWKneeCurrent) X(cmetal) X(cpoly)
+  X(forwardKneeCurrent) X(reverseKneeCurrent) X(forwardSWKneeCurrent) X(cmetal) X(cpoly) \
+  X(tRecSatCur) X(tRecSatCur_dT) X(tVcritSW) X(tConductanceSW)
 #define NGB_DIO_MODEL_FIELDS(X) \
-  X(emissionCoeff) X(swEmissionCoeff) X(brkdEmissionCoeff) X(tunEmissionCoeff) X(gradingSWCoeff)
+  X(emissionCoeff) X(swEmissionCoeff) X(brkdEmissionCoeff) X(tunEmissionCoeff) X(gradingSWCoeff) X(recEmissionCoeff)
 
 enum {
 #define X(n) DIOP_##n,
@@ -32,12 +33,12 @@ enum {
 #define DIOF_IKF        0x0040   /* forwardKneeCurrentGiven    */
 #define DIOF_IKR        0x0080   /* reverseKneeCurrentGiven    */
 #define DIOF_IKP        0x0100   /* forwardSWKneeCurrentGiven  */
+#define DIOF_RECSAT     0x0200   /* recSatCurGiven: recombination current with pow-based generation factor */
+#define DIOF_RESISTSW   0x0400   /* resistSWGiven: separate sidewall diode behind its own series resistance */
 /* options this path does not implement: reported as E_UNSUPP when the table is added */
-#define DIOF_RECSAT     0x0200   /* recSatCurGiven (pow-based generation factor)             */
-#define DIOF_RESISTSW   0x0400   /* resistSWGiven: separate sidewall diode                  */
 #define DIOF_SELFHEAT   0x0800   /* temperature node + rth0                                 */
 #define DIOF_REVREC     0x1000   /* soft reverse recovery (qp node)                         */
-#define DIOF_UNSUPPORTED (DIOF_RECSAT | DIOF_RESISTSW | DIOF_SELFHEAT | DIOF_REVREC)
+#define DIOF_UNSUPPORTED (DIOF_SELFHEAT | DIOF_REVREC)
 
 /* states, diodefs.h:263-289 */
 enum { DIOST_voltage, DIOST_current, DIOST_conduct, DIOST_voltageSW, DIOST_currentSW, DIOST_conductSW,
@@ -45,7 +46,9 @@ enum { DIOST_voltage, DIOST_current, DIOST_conduct, DIOST_voltageSW, DIOST_curre
        DIOST_deltemp, DIOST_dIdio_dT, DIOST_dIdioSW_dT, DIOST_srcapCharge, DIOST_srcapCurrent, DIOST_qp,
        DIOST_resCurrent, DIOST_resConduct, DIOST_cqcsr, DIOST_gqcsr, DIOST_COUNT };
 
-/* stamp rows in the statement order of dioload.c:757-790: two rhs adds, seven matrix adds */
-enum { DIOS_rhsNeg, DIOS_rhsPosPrime, DIOS_posPos, DIOS_negNeg, DIOS_ppPp, DIOS_posPp, DIOS_negPp, DIOS_ppPos, DIOS_ppNeg,
+/* stamp rows in the statement order of dioload.c:757-810: rhs adds (main, sidewall), matrix adds (main, sidewall) */
+enum { DIOS_rhsNeg, DIOS_rhsPosPrime, DIOS_rhsNegSw, DIOS_rhsPosSwPrime,
+       DIOS_posPos, DIOS_negNeg, DIOS_ppPp, DIOS_posPp, DIOS_negPp, DIOS_ppPos, DIOS_ppNeg,
+       DIOS_posPosSw, DIOS_negNegSw, DIOS_pspPsp, DIOS_posPsp, DIOS_negPsp, DIOS_pspPos, DIOS_pspNeg,      /* separate sidewall diode */
        DIOS_COUNT };
 #endif

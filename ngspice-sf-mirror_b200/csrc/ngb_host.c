@@ -323,11 +323,10 @@ int ngbCircuitAddDiodes(ngb_circuit *c, int n, const int *nodes, const int *flag
     if (c->finalized || c->dio_n) return NGB_E_PANIC;
     for (i = 0; i < n; i++)
         if (flags[i] & DIOF_UNSUPPORTED) {
-            ngb_set_error("diode %d: model option not on this path (flags 0x%x: recombination current 0x200, "
-                          "separate sidewall diode 0x400, self-heating 0x800, soft reverse recovery 0x1000)", i, flags[i] & DIOF_UNSUPPORTED);
+            ngb_set_error("diode %d: model option not on this path (flags 0x%x: self-heating 0x800, soft reverse recovery 0x1000)", i, flags[i] & DIOF_UNSUPPORTED);
             return NGB_E_UNSUPP;
         }
-    c->dio_n = n; c->dio_nodes = (int *)xdup(nodes, sizeof(int) * 3 * (size_t)n);
+    c->dio_n = n; c->dio_nodes = (int *)xdup(nodes, sizeof(int) * 4 * (size_t)n);
     c->dio_flags = (int *)xdup(flags, sizeof(int) * (size_t)n);
     c->dio_par = (double *)xdup(par, sizeof(double) * DIOP_COUNT * (size_t)n);
     return NGB_OK;
@@ -442,6 +441,10 @@ int ngbCircuitFinalize(ngb_circuit *c)
         int p = c->dio_nodes[i], q = c->dio_nodes[c->dio_n + i], pp = c->dio_nodes[2 * c->dio_n + i];
         coo_push(&coo, p, pp); coo_push(&coo, q, pp); coo_push(&coo, pp, p); coo_push(&coo, pp, q);
         coo_push(&coo, p, p); coo_push(&coo, q, q); coo_push(&coo, pp, pp);
+        if (c->dio_flags[i] & DIOF_RESISTSW) {       /* diosetup.c:447-451 */
+            int ps = c->dio_nodes[3 * c->dio_n + i];
+            coo_push(&coo, p, ps); coo_push(&coo, q, ps); coo_push(&coo, ps, p); coo_push(&coo, ps, q); coo_push(&coo, ps, ps);
+        }
     }
     for (i = 0; i < c->res_n; i++) {
         int p = c->res_nodes[i], q = c->res_nodes[c->res_n + i];
@@ -581,9 +584,15 @@ int ngbCircuitFinalize(ngb_circuit *c)
     c->dio_spos = (int *)xcalloc((size_t)c->dio_n * DIOS_COUNT + 1, sizeof(int));
     for (i = 0; i < c->dio_n; i++) {
         const int nn = c->dio_n;
-        int p = c->dio_nodes[i], q = c->dio_nodes[nn + i], pp = c->dio_nodes[2 * nn + i];
+        int p = c->dio_nodes[i], q = c->dio_nodes[nn + i], pp = c->dio_nodes[2 * nn + i], ps = c->dio_nodes[3 * nn + i], k2;
+        const int sw = (c->dio_flags[i] & DIOF_RESISTSW) != 0;
+        for (k2 = 0; k2 < DIOS_COUNT; k2++) c->dio_spos[k2 * nn + i] = -1;
         c->dio_spos[DIOS_rhsNeg * nn + i] = new_row(c, &cb, q > 0 ? c->nnz + q : -1);
         c->dio_spos[DIOS_rhsPosPrime * nn + i] = new_row(c, &cb, pp > 0 ? c->nnz + pp : -1);
+        if (sw) {
+            c->dio_spos[DIOS_rhsNegSw * nn + i] = new_row(c, &cb, q > 0 ? c->nnz + q : -1);
+            c->dio_spos[DIOS_rhsPosSwPrime * nn + i] = new_row(c, &cb, ps > 0 ? c->nnz + ps : -1);
+        }
         c->dio_spos[DIOS_posPos * nn + i] = new_row(c, &cb, slot_lookup(c, p, p));
         c->dio_spos[DIOS_negNeg * nn + i] = new_row(c, &cb, slot_lookup(c, q, q));
         c->dio_spos[DIOS_ppPp * nn + i] = new_row(c, &cb, slot_lookup(c, pp, pp));
@@ -591,6 +600,15 @@ int ngbCircuitFinalize(ngb_circuit *c)
         c->dio_spos[DIOS_negPp * nn + i] = new_row(c, &cb, slot_lookup(c, q, pp));
         c->dio_spos[DIOS_ppPos * nn + i] = new_row(c, &cb, slot_lookup(c, pp, p));
         c->dio_spos[DIOS_ppNeg * nn + i] = new_row(c, &cb, slot_lookup(c, pp, q));
+        if (sw) {
+            c->dio_spos[DIOS_posPosSw * nn + i] = new_row(c, &cb, slot_lookup(c, p, p));
+            c->dio_spos[DIOS_negNegSw * nn + i] = new_row(c, &cb, slot_lookup(c, q, q));
+            c->dio_spos[DIOS_pspPsp * nn + i] = new_row(c, &cb, slot_lookup(c, ps, ps));
+            c->dio_spos[DIOS_posPsp * nn + i] = new_row(c, &cb, slot_lookup(c, p, ps));
+            c->dio_spos[DIOS_negPsp * nn + i] = new_row(c, &cb, slot_lookup(c, q, ps));
+            c->dio_spos[DIOS_pspPos * nn + i] = new_row(c, &cb, slot_lookup(c, ps, p));
+            c->dio_spos[DIOS_pspNeg * nn + i] = new_row(c, &cb, slot_lookup(c, ps, q));
+        }
     }
     c->is_spos = (int *)xcalloc((size_t)c->is_n * 2 + 1, sizeof(int));
     for (i = 0; i < c->is_n; i++) {
@@ -1154,7 +1172,7 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
         const size_t T = (size_t)c->dio_n * S;
         b->dio_par = (double *)dalloc_rep(b, "dio.par", c->dio_par, DIOP_COUNT, c->dio_n, S);
         b->dio_state = (double *)dalloc(b, "dio.state", sizeof(double) * NGB_NHIST * DIOST_COUNT * T);
-        b->dio_nodes = (int *)dev_dup(c->dio_nodes, sizeof(int) * 3 * (size_t)c->dio_n);
+        b->dio_nodes = (int *)dev_dup(c->dio_nodes, sizeof(int) * 4 * (size_t)c->dio_n);
         b->dio_flags = (int *)dev_dup(c->dio_flags, sizeof(int) * (size_t)c->dio_n);
         b->dio_spos = (int *)dev_dup(c->dio_spos, sizeof(int) * DIOS_COUNT * (size_t)c->dio_n);
     }

@@ -365,9 +365,28 @@ NGB_MATH_FN double ngb_pow(double x, double y)
     const double InvLn2N = 0x1.71547652b82fep+7, Shift = 0x1.8000000000000p+52;
     const double NegLn2hiN = -0x1.62e42fefa0000p-8, NegLn2loN = -0x1.cf79abc9e3b3ap-47;
     const double C2 = 0x1.ffffffffffdbdp-2, C3 = 0x1.555555555543cp-3, C4 = 0x1.55555cf172b91p-5, C5 = 0x1.1111167a4d017p-7;
-    const unsigned long long ix = ngb_d2bits(x), iy = ngb_d2bits(y);
-    const unsigned topx = (unsigned)(ix >> 52), topy = (unsigned)(iy >> 52);
-    if (topx - 0x001u >= 0x7ffu - 0x001u || (topy & 0x7ffu) - 0x3beu >= 0x43eu - 0x3beu) return pow(x, y);
+    unsigned long long ix = ngb_d2bits(x);
+    const unsigned long long iy = ngb_d2bits(y);
+    unsigned topx = (unsigned)(ix >> 52);
+    const unsigned topy = (unsigned)(iy >> 52);
+    unsigned long long sign_bias = 0;
+    if ((topy & 0x7ffu) - 0x3beu >= 0x43eu - 0x3beu) return pow(x, y);
+    if (topx >= 0x800u) {
+        /* negative base (e_pow.c:305-318): an integer exponent continues on |x|, odd ones flip the sign */
+        const int e = (int)(topy & 0x7ffu);
+        int yint;
+        if ((topx & 0x7ffu) - 0x001u >= 0x7ffu - 0x001u) return pow(x, y);
+        if (e < 0x3ff) yint = 0;
+        else if (e > 0x3ff + 52) yint = 2;
+        else if (iy & ((1ULL << (0x3ff + 52 - e)) - 1)) yint = 0;
+        else if (iy & (1ULL << (0x3ff + 52 - e))) yint = 1;
+        else yint = 2;
+        if (yint == 0) return pow(x, y);                     /* NaN */
+        if (yint == 1) sign_bias = 0x800ULL << 7;
+        ix &= 0x7fffffffffffffffULL;
+        topx &= 0x7ffu;
+    }
+    if (topx - 0x001u >= 0x7ffu - 0x001u) return pow(x, y);
     /* log_inline */
     const unsigned long long tmp = ix - 0x3fe6955500000000ULL;
     const unsigned i = (unsigned)(tmp >> 45) & 127u;
@@ -401,7 +420,7 @@ NGB_MATH_FN double ngb_pow(double x, double y)
     double rr = fma(kq, NegLn2loN, fma(kq, NegLn2hiN, ehi));
     rr = elo + rr;
     const unsigned idx = 2u * (unsigned)(ki & 127u);
-    const unsigned long long top = ki << 45;
+    const unsigned long long top = (ki + sign_bias) << 45;
     const double tail = ngb_bits2d(NGB_TAB(ngb_exp_tab, idx));
     const unsigned long long sbits = NGB_TAB(ngb_exp_tab, idx + 1) + top;
     const double r2 = rr * rr;

@@ -99,10 +99,15 @@ def dio_netlist():
         "r3 in w 2k",
         "d4 w 0 dnors",
         "d5 0 w dnors off",
+        "r4 in u 500",
+        "d6 u 0 drec area=2",
+        "d7 0 u dssw pj=3",
         ".model dmod d is=1e-14 rs=10 n=1.05 cjo=2p vj=0.7 m=0.45 tt=5n bv=50 ibv=1e-6",
         ".model dz d is=1e-12 rs=5 bv=3.3 ibv=1e-3 cjo=10p nbv=1.2",
         ".model dsw d is=2e-14 rs=2 n=1.1 cjo=1p jsw=1e-13 ns=1.2 cjp=1p php=0.8 mjsw=0.3 ikf=0.05 ikr=0.01 jtun=1e-9 ntun=30 tt=1n",
         ".model dnors d is=5e-15 cjo=0.5p tt=2n",
+        ".model drec d is=1e-14 rs=3 n=1.0 isr=1e-11 nr=2 cjo=1p vj=0.8 m=0.4 tt=1n bv=40",
+        ".model dssw d level=3 is=1e-14 rs=4 rsw=6 jsw=2e-13 ns=1.3 cjo=1p cjp=2p php=0.75 mjsw=0.35 tt=1n",
         ".option klu",
         ".tran 5n 3u",
         ".end", ""])
@@ -225,7 +230,7 @@ if __name__ == "__main__":
     if "inv" in which:
         run("inv", inv_netlist(), "0-40,100,101,300,301", ["out", "in", "vdd#branch", "vin#branch"])
     if "dio" in which:
-        run("dio", dio_netlist(), "0-30,200,201,1000,1001,2000", ["out", "z", "w", "vin#branch"])
+        run("dio", dio_netlist(), "0-30,200,201,1000,1001,2000", ["out", "z", "w", "u", "vin#branch"])
     if "b3ring" in which:
         run("b3ring", b3_netlist(5), "0-40,300,301,1000,1001", ["out", "buf", "n2", "vdd#branch"])
     if "arr" in which:
