@@ -75,7 +75,7 @@ int ngbCircuitAddCapacitors(ngb_circuit *c, int n, const int *nodes /* [2][n] */
 /* BSIM3v3.3.0 instances in reference list order, same three-table form as BSIM4 with the lists of
  * csrc/bsim3_fields.h: nodes [6][ninst] d g s b d' s', flags [ninst] (B3F_*), prow, inst [NI][ninst],
  * mtab [nrows][NM], ptab [nrows][NP] -- replaces the BSIM3instance/BSIM3model walk of BSIM3load
- * (bsim3/b3ld.c:182-186).  nqsMod, acmMod != 0 and capMod 0/1 return E_UNSUPP */
+ * (bsim3/b3ld.c:182-186).  nqsMod and acmMod != 0 return E_UNSUPP */
 int ngbCircuitAddBsim3(ngb_circuit *c, int ninst, const int *nodes, const int *flags, const int *prow,
                        const double *inst, int nrows, const double *mtab, const double *ptab);
 void ngbBsim3Layout(int out[6]);               /* model, bin, instance, node roles, stamp rows, states */

@@ -1,10 +1,11 @@
 /* bsim3_eval.cuh -- BSIM3v3.3.0 load, one thread per (instance, sample).
  *
  * Restates BSIM3load (src/spicelib/devices/bsim3/b3ld.c:42-3131, serial flavour) for the
- * configuration without NQS, with acmMod = 0 and capMod 2 or 3 (other settings are refused at
- * upload with E_UNSUPP): initial voltages and limiting :176-378, junction diodes :401-494,
+ * configuration without NQS and with acmMod = 0 (other settings are refused at upload with
+ * E_UNSUPP): initial voltages and limiting :176-378, junction diodes :401-494,
  * threshold / mobility / Vdsat / output resistance / drain and substrate current :497-1229,
- * intrinsic charges capMod 2 :1795-1947 and capMod 3 (charge-thickness model) :1950-2238,
+ * intrinsic charges capMod 0 :1267-1600, capMod 1 :1770-1945, capMod 2 :1795-1947 and capMod 3
+ * (charge-thickness model) :1950-2238,
  * junction charges :2256-2431, overlap charges and capacitance matrix :2475-2790, integration
  * and equivalent currents :2793-2900, stamps :2903-3069.  BSIM3trunc (b3trunc.c:38-40) is folded
  * in: the LTE bounds of qb, qg, qd are reduced into ctl.lte.
@@ -691,6 +692,225 @@ NGB_HD void b3_core_dc(const B3Ctx *c, const double *mrow, const double *prw, si
     w->Vtm = Vtm;
 }
 
+/* intrinsic charges, capMod 0 (b3ld.c:1267-1600): piecewise Meyer-like model on Vfbcv */
+NGB_HD void b3_charges_cm0(const B3Ctx *c, const double *mrow, const double *prw, size_t t, B3W *w)
+{
+    const double Vds = w->Vds, cox = B3M(cox), k1ox = B3P(k1ox), phi = B3P(phi), xpart = B3M(xpart);
+    const double Vgs_eff = w->Vgs_eff, dVgs_eff_dVg = w->dVgs_eff_dVg;
+    double Vbseff, dVbseff_dVb, Vfb, Vth, Vgst, dVth_dVb, CoxWL, Arg1;
+    double qgate, qbulk, qdrn, cggb, cgdb, cgsb, cdgb, cddb, cdsb, cbgb, cbdb, cbsb;
+    double T0, T1, T2, T3, T4, T5, T6, T7, T8, T9, T10, T11, T12, tmp, tmp1;
+    (void)c; (void)t;
+    if (w->Vbseff < 0.0) { Vbseff = w->Vbs; dVbseff_dVb = 1.0; }
+    else { Vbseff = phi - w->Phis; dVbseff_dVb = -w->dPhis_dVb; }
+    Vfb = B3P(vfbcv);
+    Vth = Vfb + phi + k1ox * w->sqrtPhis;
+    Vgst = Vgs_eff - Vth;
+    dVth_dVb = k1ox * w->dsqrtPhis_dVb;
+    CoxWL = cox * B3P(weffCV) * B3P(leffCV);
+    Arg1 = Vgs_eff - Vbseff - Vfb;
+
+    if (Arg1 <= 0.0) {
+        qgate = CoxWL * Arg1;
+        qbulk = -qgate;
+        qdrn = 0.0;
+        cggb = CoxWL * dVgs_eff_dVg;
+        cgdb = 0.0;
+        cgsb = CoxWL * (dVbseff_dVb - dVgs_eff_dVg);
+        cdgb = 0.0; cddb = 0.0; cdsb = 0.0;
+        cbgb = -CoxWL * dVgs_eff_dVg;
+        cbdb = 0.0;
+        cbsb = -cgsb;
+    } else if (Vgst <= 0.0) {
+        T1 = 0.5 * k1ox;
+        T2 = sqrt(T1 * T1 + Arg1);
+        qgate = CoxWL * k1ox * (T2 - T1);
+        qbulk = -qgate;
+        qdrn = 0.0;
+        T0 = CoxWL * T1 / T2;
+        cggb = T0 * dVgs_eff_dVg;
+        cgdb = 0.0;
+        cgsb = T0 * (dVbseff_dVb - dVgs_eff_dVg);
+        cdgb = 0.0; cddb = 0.0; cdsb = 0.0;
+        cbgb = -cggb;
+        cbdb = 0.0;
+        cbsb = -cgsb;
+    } else {
+        const double One_Third_CoxWL = CoxWL / 3.0;
+        const double Two_Third_CoxWL = 2.0 * One_Third_CoxWL;
+        const double AbulkCV = w->Abulk0 * B3P(abulkCVfactor);
+        const double dAbulkCV_dVb = B3P(abulkCVfactor) * w->dAbulk0_dVb;
+        const double Vdsat = Vgst / AbulkCV;
+        const double dVdsat_dVg = dVgs_eff_dVg / AbulkCV;
+        const double dVdsat_dVb = -(Vdsat * dAbulkCV_dVb + dVth_dVb) / AbulkCV;
+        double Alphaz, dAlphaz_dVg, dAlphaz_dVb;
+        if (xpart > 0.5) {
+            if (Vdsat <= Vds) {
+                T1 = Vdsat / 3.0;
+                qgate = CoxWL * (Vgs_eff - Vfb - phi - T1);
+                T2 = -Two_Third_CoxWL * Vgst;
+                qbulk = -(qgate + T2);
+                qdrn = 0.0;
+                cggb = One_Third_CoxWL * (3.0 - dVdsat_dVg) * dVgs_eff_dVg;
+                T2 = -One_Third_CoxWL * dVdsat_dVb;
+                cgsb = -(cggb + T2);
+                cgdb = 0.0;
+                cdgb = 0.0; cddb = 0.0; cdsb = 0.0;
+                cbgb = -(cggb - Two_Third_CoxWL * dVgs_eff_dVg);
+                T3 = -(T2 + Two_Third_CoxWL * dVth_dVb);
+                cbsb = -(cbgb + T3);
+                cbdb = 0.0;
+            } else {
+                Alphaz = Vgst / Vdsat;
+                T1 = 2.0 * Vdsat - Vds;
+                T2 = Vds / (3.0 * T1);
+                T3 = T2 * Vds;
+                T9 = 0.25 * CoxWL;
+                T4 = T9 * Alphaz;
+                T7 = 2.0 * Vds - T1 - 3.0 * T3;
+                T8 = T3 - T1 - 2.0 * Vds;
+                qgate = CoxWL * (Vgs_eff - Vfb - phi - 0.5 * (Vds - T3));
+                T10 = T4 * T8;
+                qdrn = T4 * T7;
+                qbulk = -(qgate + qdrn + T10);
+                T5 = T3 / T1;
+                cggb = CoxWL * (1.0 - T5 * dVdsat_dVg) * dVgs_eff_dVg;
+                T11 = -CoxWL * T5 * dVdsat_dVb;
+                cgdb = CoxWL * (T2 - 0.5 + 0.5 * T5);
+                cgsb = -(cggb + T11 + cgdb);
+                T6 = 1.0 / Vdsat;
+                dAlphaz_dVg = T6 * (1.0 - Alphaz * dVdsat_dVg);
+                dAlphaz_dVb = -T6 * (dVth_dVb + Alphaz * dVdsat_dVb);
+                T7 = T9 * T7;
+                T8 = T9 * T8;
+                T9 = 2.0 * T4 * (1.0 - 3.0 * T5);
+                cdgb = (T7 * dAlphaz_dVg - T9 * dVdsat_dVg) * dVgs_eff_dVg;
+                T12 = T7 * dAlphaz_dVb - T9 * dVdsat_dVb;
+                cddb = T4 * (3.0 - 6.0 * T2 - 3.0 * T5);
+                cdsb = -(cdgb + T12 + cddb);
+                T9 = 2.0 * T4 * (1.0 + T5);
+                T10 = (T8 * dAlphaz_dVg - T9 * dVdsat_dVg) * dVgs_eff_dVg;
+                T11 = T8 * dAlphaz_dVb - T9 * dVdsat_dVb;
+                T12 = T4 * (2.0 * T2 + T5 - 1.0);
+                T0 = -(T10 + T11 + T12);
+                cbgb = -(cggb + cdgb + T10);
+                cbdb = -(cgdb + cddb + T12);
+                cbsb = -(cgsb + cdsb + T0);
+            }
+        } else if (xpart < 0.5) {
+            if (Vds >= Vdsat) {
+                T1 = Vdsat / 3.0;
+                qgate = CoxWL * (Vgs_eff - Vfb - phi - T1);
+                T2 = -Two_Third_CoxWL * Vgst;
+                qbulk = -(qgate + T2);
+                qdrn = 0.4 * T2;
+                cggb = One_Third_CoxWL * (3.0 - dVdsat_dVg) * dVgs_eff_dVg;
+                T2 = -One_Third_CoxWL * dVdsat_dVb;
+                cgsb = -(cggb + T2);
+                cgdb = 0.0;
+                T3 = 0.4 * Two_Third_CoxWL;
+                cdgb = -T3 * dVgs_eff_dVg;
+                cddb = 0.0;
+                T4 = T3 * dVth_dVb;
+                cdsb = -(T4 + cdgb);
+                cbgb = -(cggb - Two_Third_CoxWL * dVgs_eff_dVg);
+                T3 = -(T2 + Two_Third_CoxWL * dVth_dVb);
+                cbsb = -(cbgb + T3);
+                cbdb = 0.0;
+            } else {
+                Alphaz = Vgst / Vdsat;
+                T1 = 2.0 * Vdsat - Vds;
+                T2 = Vds / (3.0 * T1);
+                T3 = T2 * Vds;
+                T9 = 0.25 * CoxWL;
+                T4 = T9 * Alphaz;
+                qgate = CoxWL * (Vgs_eff - Vfb - phi - 0.5 * (Vds - T3));
+                T5 = T3 / T1;
+                cggb = CoxWL * (1.0 - T5 * dVdsat_dVg) * dVgs_eff_dVg;
+                tmp = -CoxWL * T5 * dVdsat_dVb;
+                cgdb = CoxWL * (T2 - 0.5 + 0.5 * T5);
+                cgsb = -(cggb + cgdb + tmp);
+                T6 = 1.0 / Vdsat;
+                dAlphaz_dVg = T6 * (1.0 - Alphaz * dVdsat_dVg);
+                dAlphaz_dVb = -T6 * (dVth_dVb + Alphaz * dVdsat_dVb);
+                T6 = 8.0 * Vdsat * Vdsat - 6.0 * Vdsat * Vds + 1.2 * Vds * Vds;
+                T8 = T2 / T1;
+                T7 = Vds - T1 - T8 * T6;
+                qdrn = T4 * T7;
+                T7 *= T9;
+                tmp = T8 / T1;
+                tmp1 = T4 * (2.0 - 4.0 * tmp * T6 + T8 * (16.0 * Vdsat - 6.0 * Vds));
+                cdgb = (T7 * dAlphaz_dVg - tmp1 * dVdsat_dVg) * dVgs_eff_dVg;
+                T10 = T7 * dAlphaz_dVb - tmp1 * dVdsat_dVb;
+                cddb = T4 * (2.0 - (1.0 / (3.0 * T1 * T1) + 2.0 * tmp) * T6 + T8 * (6.0 * Vdsat - 2.4 * Vds));
+                cdsb = -(cdgb + T10 + cddb);
+                T7 = 2.0 * (T1 + T3);
+                qbulk = -(qgate - T4 * T7);
+                T7 *= T9;
+                T0 = 4.0 * T4 * (1.0 - T5);
+                T12 = (-T7 * dAlphaz_dVg - cdgb - T0 * dVdsat_dVg) * dVgs_eff_dVg;
+                T11 = -T7 * dAlphaz_dVb - T10 - T0 * dVdsat_dVb;
+                T10 = -4.0 * T4 * (T2 - 0.5 + 0.5 * T5) - cddb;
+                tmp = -(T10 + T11 + T12);
+                cbgb = -(cggb + cdgb + T12);
+                cbdb = -(cgdb + cddb + T10);
+                cbsb = -(cgsb + cdsb + tmp);
+            }
+        } else {
+            if (Vds >= Vdsat) {
+                T1 = Vdsat / 3.0;
+                qgate = CoxWL * (Vgs_eff - Vfb - phi - T1);
+                T2 = -Two_Third_CoxWL * Vgst;
+                qbulk = -(qgate + T2);
+                qdrn = 0.5 * T2;
+                cggb = One_Third_CoxWL * (3.0 - dVdsat_dVg) * dVgs_eff_dVg;
+                T2 = -One_Third_CoxWL * dVdsat_dVb;
+                cgsb = -(cggb + T2);
+                cgdb = 0.0;
+                cdgb = -One_Third_CoxWL * dVgs_eff_dVg;
+                cddb = 0.0;
+                T4 = One_Third_CoxWL * dVth_dVb;
+                cdsb = -(T4 + cdgb);
+                cbgb = -(cggb - Two_Third_CoxWL * dVgs_eff_dVg);
+                T3 = -(T2 + Two_Third_CoxWL * dVth_dVb);
+                cbsb = -(cbgb + T3);
+                cbdb = 0.0;
+            } else {
+                Alphaz = Vgst / Vdsat;
+                T1 = 2.0 * Vdsat - Vds;
+                T2 = Vds / (3.0 * T1);
+                T3 = T2 * Vds;
+                T9 = 0.25 * CoxWL;
+                T4 = T9 * Alphaz;
+                qgate = CoxWL * (Vgs_eff - Vfb - phi - 0.5 * (Vds - T3));
+                T5 = T3 / T1;
+                cggb = CoxWL * (1.0 - T5 * dVdsat_dVg) * dVgs_eff_dVg;
+                tmp = -CoxWL * T5 * dVdsat_dVb;
+                cgdb = CoxWL * (T2 - 0.5 + 0.5 * T5);
+                cgsb = -(cggb + cgdb + tmp);
+                T6 = 1.0 / Vdsat;
+                dAlphaz_dVg = T6 * (1.0 - Alphaz * dVdsat_dVg);
+                dAlphaz_dVb = -T6 * (dVth_dVb + Alphaz * dVdsat_dVb);
+                T7 = T1 + T3;
+                qdrn = -T4 * T7;
+                qbulk = -(qgate + qdrn + qdrn);
+                T7 *= T9;
+                T0 = T4 * (2.0 * T5 - 2.0);
+                cdgb = (T0 * dVdsat_dVg - T7 * dAlphaz_dVg) * dVgs_eff_dVg;
+                T12 = T0 * dVdsat_dVb - T7 * dAlphaz_dVb;
+                cddb = T4 * (1.0 - 2.0 * T2 - T5);
+                cdsb = -(cdgb + T12 + cddb);
+                cbgb = -(cggb + 2.0 * cdgb);
+                cbdb = -(cgdb + 2.0 * cddb);
+                cbsb = -(cgsb + 2.0 * cdsb);
+            }
+        }
+    }
+    w->qgate = qgate; w->qbulk = qbulk; w->qdrn = qdrn;
+    w->cggb = cggb; w->cgsb = cgsb; w->cgdb = cgdb; w->cdgb = cdgb; w->cdsb = cdsb; w->cddb = cddb;
+    w->cbgb = cbgb; w->cbsb = cbsb; w->cbdb = cbdb;
+}
+
 /* intrinsic charges and capacitances, capMod 2 (b3ld.c:1730-1947) and capMod 3, the
  * charge-thickness model (:1950-2238); both start from the CV version of Vgsteff (:1735-1768) */
 NGB_HD void b3_charges(const B3Ctx *c, const double *mrow, const double *prw, size_t t, B3W *w)
@@ -737,6 +957,125 @@ NGB_HD void b3_charges(const B3Ctx *c, const double *mrow, const double *prw, si
         dVgsteff_dVd = -dVgsteff_dVg * (dVth_dVd + (Vgst - voffcv) / noff * dnoff_dVd) + Vgsteff / noff * dnoff_dVd;
         dVgsteff_dVb = -dVgsteff_dVg * (dVth_dVb + (Vgst - voffcv) / noff * dnoff_dVb) + Vgsteff / noff * dnoff_dVb;
         dVgsteff_dVg *= dVgs_eff_dVg;
+    }
+
+    if (capMod == 1) {
+        /* b3ld.c:1770-1945 */
+        const double Vfb = vfbzb;
+        const double Arg1 = Vgs_eff - VbseffCV - Vfb - Vgsteff;
+        double One_Third_CoxWL, Two_Third_CoxWL, dVdsatCV_dVg, dVdsatCV_dVb, dT0_dVg, dT0_dVb, dT3_dVg, dT3_dVd, dT3_dVb;
+        if (Arg1 <= 0.0) {
+            qgate = CoxWL * Arg1;
+            Cgg = CoxWL * (dVgs_eff_dVg - dVgsteff_dVg);
+            Cgd = -CoxWL * dVgsteff_dVd;
+            Cgb = -CoxWL * (dVbseffCV_dVb + dVgsteff_dVb);
+        } else {
+            T0 = 0.5 * k1ox;
+            T1 = sqrt(T0 * T0 + Arg1);
+            T2 = CoxWL * T0 / T1;
+            qgate = CoxWL * k1ox * (T1 - T0);
+            Cgg = T2 * (dVgs_eff_dVg - dVgsteff_dVg);
+            Cgd = -T2 * dVgsteff_dVd;
+            Cgb = -T2 * (dVbseffCV_dVb + dVgsteff_dVb);
+        }
+        qbulk = -qgate;
+        Cbg = -Cgg;
+        Cbd = -Cgd;
+        Cbb = -Cgb;
+
+        One_Third_CoxWL = CoxWL / 3.0;
+        Two_Third_CoxWL = 2.0 * One_Third_CoxWL;
+        AbulkCV = w->Abulk0 * B3P(abulkCVfactor);
+        dAbulkCV_dVb = B3P(abulkCVfactor) * w->dAbulk0_dVb;
+        VdsatCV = Vgsteff / AbulkCV;
+        if (VdsatCV < Vds) {
+            dVdsatCV_dVg = 1.0 / AbulkCV;
+            dVdsatCV_dVb = -VdsatCV * dAbulkCV_dVb / AbulkCV;
+            T0 = Vgsteff - VdsatCV / 3.0;
+            dT0_dVg = 1.0 - dVdsatCV_dVg / 3.0;
+            dT0_dVb = -dVdsatCV_dVb / 3.0;
+            qgate += CoxWL * T0;
+            Cgg1 = CoxWL * dT0_dVg;
+            Cgb1 = CoxWL * dT0_dVb + Cgg1 * dVgsteff_dVb;
+            Cgd1 = Cgg1 * dVgsteff_dVd;
+            Cgg1 *= dVgsteff_dVg;
+            Cgg += Cgg1;
+            Cgb += Cgb1;
+            Cgd += Cgd1;
+
+            T0 = VdsatCV - Vgsteff;
+            dT0_dVg = dVdsatCV_dVg - 1.0;
+            dT0_dVb = dVdsatCV_dVb;
+            qbulk += One_Third_CoxWL * T0;
+            Cbg1 = One_Third_CoxWL * dT0_dVg;
+            Cbb1 = One_Third_CoxWL * dT0_dVb + Cbg1 * dVgsteff_dVb;
+            Cbd1 = Cbg1 * dVgsteff_dVd;
+            Cbg1 *= dVgsteff_dVg;
+            Cbg += Cbg1;
+            Cbb += Cbb1;
+            Cbd += Cbd1;
+
+            if (xpart > 0.5) T0 = -Two_Third_CoxWL;
+            else if (xpart < 0.5) T0 = -0.4 * CoxWL;
+            else T0 = -One_Third_CoxWL;
+            qsrc = T0 * Vgsteff;
+            Csg = T0 * dVgsteff_dVg;
+            Csb = T0 * dVgsteff_dVb;
+            Csd = T0 * dVgsteff_dVd;
+        } else {
+            T0 = AbulkCV * Vds;
+            T1 = 12.0 * (Vgsteff - 0.5 * T0 + 1.e-20);
+            T2 = Vds / T1;
+            T3 = T0 * T2;
+            dT3_dVg = -12.0 * T2 * T2 * AbulkCV;
+            dT3_dVd = 6.0 * T0 * (4.0 * Vgsteff - T0) / T1 / T1 - 0.5;
+            dT3_dVb = 12.0 * T2 * T2 * dAbulkCV_dVb * Vgsteff;
+
+            qgate += CoxWL * (Vgsteff - 0.5 * Vds + T3);
+            Cgg1 = CoxWL * (1.0 + dT3_dVg);
+            Cgb1 = CoxWL * dT3_dVb + Cgg1 * dVgsteff_dVb;
+            Cgd1 = CoxWL * dT3_dVd + Cgg1 * dVgsteff_dVd;
+            Cgg1 *= dVgsteff_dVg;
+            Cgg += Cgg1;
+            Cgb += Cgb1;
+            Cgd += Cgd1;
+
+            qbulk += CoxWL * (1.0 - AbulkCV) * (0.5 * Vds - T3);
+            Cbg1 = -CoxWL * ((1.0 - AbulkCV) * dT3_dVg);
+            Cbb1 = -CoxWL * ((1.0 - AbulkCV) * dT3_dVb + (0.5 * Vds - T3) * dAbulkCV_dVb) + Cbg1 * dVgsteff_dVb;
+            Cbd1 = -CoxWL * (1.0 - AbulkCV) * dT3_dVd + Cbg1 * dVgsteff_dVd;
+            Cbg1 *= dVgsteff_dVg;
+            Cbg += Cbg1;
+            Cbb += Cbb1;
+            Cbd += Cbd1;
+
+            if (xpart > 0.5) {
+                T1 = T1 + T1;
+                qsrc = -CoxWL * (0.5 * Vgsteff + 0.25 * T0 - T0 * T0 / T1);
+                Csg = -CoxWL * (0.5 + 24.0 * T0 * Vds / T1 / T1 * AbulkCV);
+                Csb = -CoxWL * (0.25 * Vds * dAbulkCV_dVb - 12.0 * T0 * Vds / T1 / T1 * (4.0 * Vgsteff - T0) * dAbulkCV_dVb)
+                    + Csg * dVgsteff_dVb;
+                Csd = -CoxWL * (0.25 * AbulkCV - 12.0 * AbulkCV * T0 / T1 / T1 * (4.0 * Vgsteff - T0)) + Csg * dVgsteff_dVd;
+                Csg *= dVgsteff_dVg;
+            } else if (xpart < 0.5) {
+                T1 = T1 / 12.0;
+                T2 = 0.5 * CoxWL / (T1 * T1);
+                T3 = Vgsteff * (2.0 * T0 * T0 / 3.0 + Vgsteff * (Vgsteff - 4.0 * T0 / 3.0)) - 2.0 * T0 * T0 * T0 / 15.0;
+                qsrc = -T2 * T3;
+                T4 = 4.0 / 3.0 * Vgsteff * (Vgsteff - T0) + 0.4 * T0 * T0;
+                Csg = -2.0 * qsrc / T1 - T2 * (Vgsteff * (3.0 * Vgsteff - 8.0 * T0 / 3.0) + 2.0 * T0 * T0 / 3.0);
+                Csb = (qsrc / T1 * Vds + T2 * T4 * Vds) * dAbulkCV_dVb + Csg * dVgsteff_dVb;
+                Csd = (qsrc / T1 + T2 * T4) * AbulkCV + Csg * dVgsteff_dVd;
+                Csg *= dVgsteff_dVg;
+            } else {
+                qsrc = -0.5 * (qgate + qbulk);
+                Csg = -0.5 * (Cgg1 + Cbg1);
+                Csb = -0.5 * (Cgb1 + Cbb1);
+                Csd = -0.5 * (Cgd1 + Cbd1);
+            }
+        }
+        qdrn = -(qgate + qbulk + qsrc);
+        goto store;
     }
 
     /* accumulation charge through the smoothed flat-band voltage (common to both models) */
@@ -1047,6 +1386,7 @@ NGB_HD void b3_charges(const B3Ctx *c, const double *mrow, const double *prw, si
         Cgd = Cgd1 - Cbd;
         Cgb = Cgb1 - Cbb;
     }
+store:
     Cgb *= dVbseff_dVb;
     Cbb *= dVbseff_dVb;
     Csb *= dVbseff_dVb;
@@ -1111,6 +1451,19 @@ NGB_HD void b3_overlap(double v, double cgo, double cgl_w, double ckappa, double
     const double T4 = sqrt(1.0 - 4.0 * T2 / ckappa);
     *cap = cgo + T3 - T3 * (1.0 - 1.0 / T4) * (0.5 - 0.5 * T0 / T1);
     *q = (cgo + T3) * v - T3 * (T2 + 0.5 * ckappa * (T4 - 1.0));
+}
+
+/* overlap capacitance and charge of one side, capMod 1: b3ld.c:2505-2532 */
+NGB_HD void b3_overlap_cm1(double v, double cgo, double weffCV, double cgl, double ckappa, double *cap, double *q)
+{
+    if (v < 0.0) {
+        const double T1 = sqrt(1.0 - 4.0 * v / ckappa);
+        *cap = cgo + weffCV * cgl / T1;
+        *q = cgo * v - weffCV * 0.5 * cgl * ckappa * (T1 - 1.0);
+    } else {
+        *cap = cgo + weffCV * cgl;
+        *q = (weffCV * cgl + cgo) * v;
+    }
 }
 
 NGB_HD int b3_load_thread(const B3Ctx *c, size_t t)
@@ -1240,8 +1593,10 @@ NGB_HD int b3_load_thread(const B3Ctx *c, size_t t)
 
     w.qgate = w.qbulk = w.qdrn = 0.0;
     w.cggb = w.cgsb = w.cgdb = w.cdgb = w.cdsb = w.cddb = w.cbgb = w.cbsb = w.cbdb = 0.0;
-    if (!((B3M(xpart) < 0) || !ChargeComputationNeeded))
-        b3_charges(c, mrow, prw, t, &w);
+    if (!((B3M(xpart) < 0) || !ChargeComputationNeeded)) {
+        if ((int)B3M(capMod) == 0) b3_charges_cm0(c, mrow, prw, t, &w);
+        else b3_charges(c, mrow, prw, t, &w);
+    }
 
     if (ChargeComputationNeeded) {
         const double weff = B3P(weff);
@@ -1285,8 +1640,19 @@ NGB_HD int b3_load_thread(const B3Ctx *c, size_t t)
             const double ag0 = NGB_LDG(&c->ctl.ag0[s]);
             const double cgbo = B3P(cgbo);
             double cgdo, qgdo, cgso, qgso, qgate = w.qgate, qbulk = w.qbulk, qdrn = w.qdrn, qgd, qgs, qgb;
-            b3_overlap(vgd, B3P(cgdo), B3P(weffCV) * B3P(cgdl), B3P(ckappa), &cgdo, &qgdo);
-            b3_overlap(vgs, B3P(cgso), B3P(weffCV) * B3P(cgsl), B3P(ckappa), &cgso, &qgso);
+            {
+                const int capMod = (int)B3M(capMod);
+                if (capMod == 0) {                               /* b3ld.c:2497-2503 */
+                    cgdo = B3P(cgdo); qgdo = B3P(cgdo) * vgd;
+                    cgso = B3P(cgso); qgso = B3P(cgso) * vgs;
+                } else if (capMod == 1) {                        /* b3ld.c:2504-2532 */
+                    b3_overlap_cm1(vgd, B3P(cgdo), B3P(weffCV), B3P(cgdl), B3P(ckappa), &cgdo, &qgdo);
+                    b3_overlap_cm1(vgs, B3P(cgso), B3P(weffCV), B3P(cgsl), B3P(ckappa), &cgso, &qgso);
+                } else {
+                    b3_overlap(vgd, B3P(cgdo), B3P(weffCV) * B3P(cgdl), B3P(ckappa), &cgdo, &qgdo);
+                    b3_overlap(vgs, B3P(cgso), B3P(weffCV) * B3P(cgsl), B3P(ckappa), &cgso, &qgso);
+                }
+            }
             if (b3mode > 0) {
                 gcggb = (w.cggb + cgdo + cgso + cgbo) * ag0;
                 gcgdb = (w.cgdb - cgdo) * ag0;

@@ -305,8 +305,8 @@ int ngbCircuitAddBsim3(ngb_circuit *c, int ninst, const int *nodes, const int *f
         mr = mtab + (size_t)prow[i] * B3M_COUNT;
         if (flags[i] & B3F_NQS) { ngb_set_error("BSIM3 instance %d: nqsMod/acnqsMod not supported", i); return NGB_E_UNSUPP; }
         if ((int)mr[B3M_acmMod] != 0) { ngb_set_error("BSIM3 instance %d: acmMod=%d not supported (0 only)", i, (int)mr[B3M_acmMod]); return NGB_E_UNSUPP; }
-        if ((int)mr[B3M_capMod] != 2 && (int)mr[B3M_capMod] != 3) {
-            ngb_set_error("BSIM3 instance %d: capMod=%d not supported (2 and 3)", i, (int)mr[B3M_capMod]); return NGB_E_UNSUPP; }
+        if ((int)mr[B3M_capMod] < 0 || (int)mr[B3M_capMod] > 3) {
+            ngb_set_error("BSIM3 instance %d: capMod=%d out of range", i, (int)mr[B3M_capMod]); return NGB_E_UNSUPP; }
     }
     c->b3_n = ninst; c->b3_nrows = nrows;
     c->b3_nodes = (int *)xdup(nodes, sizeof(int) * B3N_COUNT * (size_t)ninst);

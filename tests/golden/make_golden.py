@@ -11,6 +11,7 @@ and test files.  Needs /root/reference; the fixtures it writes do not.
   b3ring BSIM3v3.3.0 ring of five inverters + buffer on the MC_ring.sp level-8 cards.
   arr    4x4 BSIM4 inverter array with RC links (small instance of config 4's generator).
   ro17tox BSIM4temp tables for 8 oxide-thickness levels + two reference transients with toxe and delvto mismatch.
+  b3cap  b3c<capMod>x<xpart> : the 12 capMod / xpart combinations of BSIM3 on a 3-stage ring, 3 ns.
   dio    junction diodes (rectifier, zener clamp, sidewall/tunnel/knee parameters) with R, C, SIN source.
 
 Outputs (tests/golden/): <name>.flat.ngt  flattened circuit after CKTsetup/CKTtemp
@@ -121,7 +122,7 @@ def b3_cards():
     return src[i:j]
 
 
-def b3_netlist(stages=5):
+def b3_netlist(stages=5, capmod=None, xpart=None, tran=".tran 0.05n 20n"):
     """BSIM3 ring of inverters (cells of MC_ring.sp: w/l/as/ad/ps/pd as there) kicked by the same
     PULSE source MC_ring.sp uses between input and output, plus an output buffer and load"""
     lines = ["* BSIM3v3.3.0 ring of inverters (MC_ring.sp cells)",
@@ -135,8 +136,12 @@ def b3_netlist(stages=5):
         prev = nxt
     lines += ["mnb buf out 0 sub n1 w=2u l=0.35u as=3p ad=3p ps=4u pd=4u",
               "mpb buf out dd well p1 w=4u l=0.35u as=7p ad=7p ps=6u pd=6u",
-              "cout buf ss 0.2pF", ".option klu", ".tran 0.05n 20n"]
-    return "\n".join(lines) + "\n" + b3_cards() + "\n.end\n"
+              "cout buf ss 0.2pF", ".option klu", tran]
+    cards = b3_cards()
+    if capmod is not None:
+        extra = f"+capmod={capmod} xpart={xpart}\n"
+        cards = cards.replace("+level=8\n", "+level=8\n" + extra)
+    return "\n".join(lines) + "\n" + cards + "\n.end\n"
 
 
 TOX_Z = [-1.5341205443525463, -0.8871465590188759, -0.4887764111146695, -0.15731068461017067,
@@ -258,5 +263,10 @@ if __name__ == "__main__":
         for i in range(2):
             run(f"ro17tox{i}", with_toxe(ro_netlist(17, tran=".tran .1ns 20ns uic", kick=True, delvto=dv[i]), levels[lev[i]]),
                 "1", ["18", "2", "9", "vdd#branch"])
+    if "b3cap" in which:
+        # every capMod / xpart combination of BSIM3 on a short 3-stage version of the same ring
+        for cm in (0, 1, 2, 3):
+            for xp, tag in ((0.0, "0"), (0.5, "5"), (1.0, "1")):
+                run(f"b3c{cm}x{tag}", b3_netlist(3, capmod=cm, xpart=xp, tran=".tran 0.05n 3n"), "0-8,40,41,120,121", ["out", "buf"])
     if "ro101" in which:
         run("ro101", ro_netlist(101), "1,2,3000", ["102", "2", "50", "vdd#branch"])

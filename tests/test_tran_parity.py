@@ -165,3 +165,20 @@ def test_tran_gpu_tox_and_vth_mismatch(cuda_lib):
     res, t, v = _tox_batch(cuda_lib)
     for s in range(2):
         _compare(res, t, v, ngt.read(f"{GOLDEN}/ro17tox{s}.wave.ngt"), s, exact=True)
+
+
+B3_CAP_CASES = [f"b3c{cm}x{tag}" for cm in (0, 1, 2, 3) for tag in ("0", "5", "1")]
+
+
+@pytest.mark.parametrize("name", B3_CAP_CASES)
+def test_tran_hostsim_bsim3_capmod_xpart(hostsim_lib, name):
+    """every capMod (0-3) x charge partition (xpart 0, 0.5, 1) of BSIM3v3.3.0"""
+    res, t, v, wave = _run(hostsim_lib, name)
+    _compare(res, t, v, wave, 0, exact=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", B3_CAP_CASES)
+def test_tran_gpu_bsim3_capmod_xpart(cuda_lib, name):
+    res, t, v, wave = _run(cuda_lib, name)
+    _compare(res, t, v, wave, 0, exact=True)
