@@ -85,6 +85,15 @@ void ngbBsim3Layout(int out[6]);               /* model, bin, instance, node rol
  * DIOinstance/DIOmodel walk of DIOload (dio/dioload.c:75-80).  Self-heating and soft reverse recovery
  * return E_UNSUPP */
 int ngbCircuitAddDiodes(ngb_circuit *c, int n, const int *nodes, const int *flags, const double *par);
+/* VBIC bipolar transistors (4-terminal) after VBICsetup/VBICtemp (vbic/vbicsetup.c, vbictemp.c):
+ * nodes [11][n] coll base emit subs collCX collCI baseBX baseBI emitEI baseBP subsSI (an internal node
+ * equals its terminal when the series resistance is absent), flags [n] (0x1 off, 0x2 self-heating,
+ * 0x4 excess phase), par [108][n] the parameter vector exactly as VBICload assembles it per instance
+ * (vbic/vbicload.c:127-166), aux [6][n] type, tVcrit, icVBE, icVCE, area*m, temp -- replaces the
+ * VBICinstance/VBICmodel walk of VBICload (vbicload.c:100-107).  Self-heating and excess phase return
+ * E_UNSUPP.  ngbVbicLayout: [0]=parameters [1]=aux [2]=node roles [3]=states [4]=stamp rows */
+int ngbCircuitAddVbic(ngb_circuit *c, int n, const int *nodes, const int *flags, const double *par, const double *aux);
+void ngbVbicLayout(int out[5]);
 int ngbCircuitAddVsources(ngb_circuit *c, int n, const int *nodes /* [3][n] pos neg branch */,
                           const int *fn /* [3][n] type order dcGiven */, const double *par /* [9][n] */);
 int ngbCircuitAddIsources(ngb_circuit *c, int n, const int *nodes /* [2][n] */,
@@ -130,6 +139,7 @@ int ngbBatchRefreshLu(ngb_batch *b);
  *   b4.prow      int [ninst*S]          cap.state f64 [4][2][ncap*S]    cap.par f64 [3][ncap*S]
  *   b3.inst      f64 [NI][n3*S]         b3.state f64 [4][17][n3*S]      b3.von f64 [n3*S]
  *   dio.par      f64 [NP][nd*S]         dio.state f64 [4][22][nd*S]
+ *   vbic.par     f64 [108][nq*S]        vbic.aux f64 [6][nq*S]          vbic.state f64 [4][86][nq*S]
  *   vsrc.par     f64 [9][nv*S]          lu.V f64 [S][nV]    lu.Rs f64 [S][n]
  *   lu.nodeconv  int [S]                lu.singular int [S] */
 long ngbBatchArrayBytes(ngb_batch *b, const char *name);

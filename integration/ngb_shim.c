@@ -30,6 +30,7 @@
 #include "bsim4/bsim4def.h"
 #include "bsim3/bsim3def.h"
 #include "dio/diodefs.h"
+#include "vbic/vbicdefs.h"
 #include "res/resdefs.h"
 #include "cap/capdefs.h"
 #include "vsrc/vsrcdefs.h"
@@ -42,6 +43,7 @@
 #include "../ngspice-sf-mirror_b200/csrc/bsim4_fields.h"
 #include "../ngspice-sf-mirror_b200/csrc/bsim3_fields.h"
 #include "../ngspice-sf-mirror_b200/csrc/dio_fields.h"
+#include "../ngspice-sf-mirror_b200/csrc/vbic_types.h"
 
 extern SPICEdev **DEVices;
 extern int DEVmaxnum;
@@ -56,9 +58,9 @@ static struct {
     ngb_circuit *C; ngb_batch *B;
     CKTcircuit *ckt;
     int neq, nnz;
-    int tB4, tB3, tDIO, tRES, tCAP, tVSRC, tISRC;
-    int n4, n3, nd, nc;
-    int *sb4, *sb3, *sbd, *sbc;          /* state bases per instance */
+    int tB4, tB3, tDIO, tVBIC, tRES, tCAP, tVSRC, tISRC;
+    int n4, n3, nd, nq, nc;
+    int *sb4, *sb3, *sbd, *sbq, *sbc;          /* state bases per instance */
     double *buf; size_t buf_len;
     long loads, facs, solves;
 } G;
@@ -193,6 +195,47 @@ static int flatten_dio(CKTcircuit *ckt)
     return rc;
 }
 
+/* VBIC: the parameter vector is put together the way VBICload does it per instance (vbicload.c:127-166) */
+static int flatten_vbic(CKTcircuit *ckt)
+{
+    VBICmodel *m; VBICinstance *h;
+    int n = G.nq, i = 0, k, rc; int *nodes, *flags; double *par, *aux;
+    if (!n) return 0;
+    nodes = (int *)xc((size_t)n * VBN_COUNT, sizeof(int)); flags = (int *)xc((size_t)n, sizeof(int)); G.sbq = (int *)xc((size_t)n, sizeof(int));
+    par = (double *)xc((size_t)n * VBIC_NP, sizeof(double)); aux = (double *)xc((size_t)n * VBA_COUNT, sizeof(double));
+    for (m = (VBICmodel *)ckt->CKThead[G.tVBIC]; m; m = VBICnextModel(m))
+        for (h = VBICinstances(m); h; h = VBICnextInstance(h), i++) {
+            double p[VBIC_NP];
+            const int nd[VBN_COUNT] = { h->VBICcollNode, h->VBICbaseNode, h->VBICemitNode, h->VBICsubsNode, h->VBICcollCXNode,
+                h->VBICcollCINode, h->VBICbaseBXNode, h->VBICbaseBINode, h->VBICemitEINode, h->VBICbaseBPNode, h->VBICsubsSINode };
+            static const struct { int k; size_t off; } upd[] = {
+#define U(kk, f) { kk, offsetof(VBICinstance, f) }
+                U(1, VBICtextCollResist), U(2, VBICtintCollResist), U(3, VBICtepiSatVoltage), U(4, VBICtepiDoping), U(6, VBICtextBaseResist),
+                U(7, VBICtintBaseResist), U(8, VBICtemitterResist), U(9, VBICtsubstrateResist), U(10, VBICtparBaseResist), U(11, VBICtsatCur),
+                U(12, VBICtemissionCoeffF), U(13, VBICtemissionCoeffR), U(16, VBICtdepletionCapBE), U(17, VBICtpotentialBE),
+                U(21, VBICtdepletionCapBC), U(23, VBICtextCapBC), U(24, VBICtpotentialBC), U(27, VBICtextCapSC), U(28, VBICtpotentialSC),
+                U(31, VBICtidealSatCurBE), U(34, VBICtnidealSatCurBE), U(36, VBICtidealSatCurBC), U(38, VBICtnidealSatCurBC),
+                U(41, VBICtavalanchePar2BC), U(42, VBICtparasitSatCur), U(45, VBICtidealParasitSatCurBE), U(46, VBICtnidealParasitSatCurBE),
+                U(47, VBICtidealParasitSatCurBC), U(49, VBICtnidealParasitSatCurBC), U(53, VBICtrollOffF), U(94, VBICtsepISRR),
+                U(98, VBICtvbbe), U(99, VBICtnbbe)
+#undef U
+            };
+            for (k = 0; k < VBN_COUNT; k++) nodes[(size_t)k * n + i] = nd[k];
+            memcpy(p, &m->VBICtnom, sizeof p);
+            p[0] = h->VBICtemp - CONSTCtoK + p[105];
+            for (k = 0; k < (int)(sizeof upd / sizeof upd[0]); k++) p[upd[k].k] = *(const double *)((const char *)h + upd[k].off);
+            for (k = 0; k < VBIC_NP; k++) par[(size_t)k * n + i] = p[k];
+            aux[(size_t)VBA_type * n + i] = m->VBICtype; aux[(size_t)VBA_tVcrit * n + i] = h->VBICtVcrit;
+            aux[(size_t)VBA_icVBE * n + i] = h->VBICicVBE; aux[(size_t)VBA_icVCE * n + i] = h->VBICicVCE;
+            aux[(size_t)VBA_scale * n + i] = h->VBICarea * h->VBICm; aux[(size_t)VBA_temp * n + i] = h->VBICtemp;
+            flags[i] = (h->VBICoff ? VBF_OFF : 0) | (h->VBIC_selfheat ? VBF_SELFHEAT : 0) | (h->VBIC_excessPhase ? VBF_EXCESS : 0);
+            G.sbq[i] = h->VBICstate;
+        }
+    rc = ngbCircuitAddVbic(G.C, n, nodes, flags, par, aux);
+    free(nodes); free(flags); free(par); free(aux);
+    return rc;
+}
+
 static int flatten_linear(CKTcircuit *ckt)
 {
     int n, i, rc = 0, k;
@@ -262,11 +305,11 @@ static int shim_attach(CKTcircuit *ckt)
     if (!ckt->CKTmatrix || !ckt->CKTmatrix->CKTkluMODE) return shim_fail("matrix is not in KLU mode (.option klu)");
     if (ckt->CKTbypass) return shim_fail("CKTbypass is on");
     K = ckt->CKTmatrix->SMPkluMatrix;
-    G.tB4 = CKTtypelook("BSIM4"); G.tB3 = CKTtypelook("BSIM3"); G.tDIO = CKTtypelook("Diode"); G.tRES = CKTtypelook("Resistor");
+    G.tB4 = CKTtypelook("BSIM4"); G.tB3 = CKTtypelook("BSIM3"); G.tDIO = CKTtypelook("Diode"); G.tVBIC = CKTtypelook("VBIC"); G.tRES = CKTtypelook("Resistor");
     G.tCAP = CKTtypelook("Capacitor"); G.tVSRC = CKTtypelook("Vsource"); G.tISRC = CKTtypelook("Isource");
     for (t = 0; t < DEVmaxnum; t++)
         if (DEVices[t] && ckt->CKThead[t] && DEVices[t]->DEVload &&
-            t != G.tB4 && t != G.tB3 && t != G.tDIO && t != G.tRES && t != G.tCAP && t != G.tVSRC && t != G.tISRC) {
+            t != G.tB4 && t != G.tB3 && t != G.tDIO && t != G.tVBIC && t != G.tRES && t != G.tCAP && t != G.tVSRC && t != G.tISRC) {
             fprintf(stderr, "ngb_shim: device type %s is not on the GPU path\n", DEVices[t]->DEVpublic.name);
             return shim_fail("unsupported device type in the circuit");
         }
@@ -284,8 +327,8 @@ static int shim_attach(CKTcircuit *ckt)
     iopt[0] = ckt->CKTintegrateMethod; iopt[1] = ckt->CKTmaxOrder; iopt[2] = ckt->CKTtranMaxIter; iopt[3] = ckt->CKTdcMaxIter;
     iopt[4] = (ckt->CKTmode & MODEUIC) ? 1 : 0;
     ngbCircuitSetOptions(G.C, dopt, iopt);
-    COUNT(BSIM4, G.tB4, G.n4); COUNT(BSIM3, G.tB3, G.n3); COUNT(DIO, G.tDIO, G.nd); COUNT(CAP, G.tCAP, G.nc);
-    if ((rc = flatten_bsim3(ckt)) || (rc = flatten_bsim4(ckt)) || (rc = flatten_dio(ckt)) || (rc = flatten_linear(ckt)) ||
+    COUNT(BSIM4, G.tB4, G.n4); COUNT(BSIM3, G.tB3, G.n3); COUNT(DIO, G.tDIO, G.nd); COUNT(VBIC, G.tVBIC, G.nq); COUNT(CAP, G.tCAP, G.nc);
+    if ((rc = flatten_bsim3(ckt)) || (rc = flatten_bsim4(ckt)) || (rc = flatten_dio(ckt)) || (rc = flatten_vbic(ckt)) || (rc = flatten_linear(ckt)) ||
         (rc = ngbCircuitFinalize(G.C))) {
         fprintf(stderr, "ngb_shim: %s\n", ngbLastError());
         return shim_fail("circuit uses an option outside the GPU path");
@@ -306,8 +349,8 @@ static int shim_attach(CKTcircuit *ckt)
     e = getenv("NGB_SHIM_LU");
     G.use_lu = !(e && !strcmp(e, "0"));
     G.active = 1;
-    fprintf(stderr, "ngb_shim: CKTload%s on %s (%d BSIM4, %d BSIM3, %d diodes, %d unknowns, %d nonzeros)\n",
-            G.use_lu ? " + SMPluFac + SMPsolve" : "", ngbBackend(), G.n4, G.n3, G.nd, n, nnz);
+    fprintf(stderr, "ngb_shim: CKTload%s on %s (%d BSIM4, %d BSIM3, %d diodes, %d VBIC, %d unknowns, %d nonzeros)\n",
+            G.use_lu ? " + SMPluFac + SMPsolve" : "", ngbBackend(), G.n4, G.n3, G.nd, G.nq, n, nnz);
     return 1;
 }
 
@@ -359,6 +402,7 @@ int __wrap_CKTload(CKTcircuit *ckt)
     states_down("b4.state", B4ST_COUNT, G.n4, G.sb4);
     states_down("b3.state", B3ST_COUNT, G.n3, G.sb3);
     states_down("dio.state", DIOST_COUNT, G.nd, G.sbd);
+    states_down("vbic.state", VBS_COUNT, G.nq, G.sbq);
     states_down("cap.state", 2, G.nc, G.sbc);
     rc = ngbLoad(G.B);
     if (rc) { fprintf(stderr, "ngb_shim: ngbLoad failed (%d): %s\n", rc, ngbLastError()); return rc; }
@@ -368,6 +412,7 @@ int __wrap_CKTload(CKTcircuit *ckt)
     states_up("b4.state", B4ST_COUNT, G.n4, G.sb4);
     states_up("b3.state", B3ST_COUNT, G.n3, G.sb3);
     states_up("dio.state", DIOST_COUNT, G.nd, G.sbd);
+    states_up("vbic.state", VBS_COUNT, G.nq, G.sbq);
     states_up("cap.state", 2, G.nc, G.sbc);
     ngbBatchDownload(G.B, "ctl.noncon", &iv, sizeof(int), 0);
     ckt->CKTnoncon += iv;

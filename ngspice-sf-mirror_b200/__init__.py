@@ -72,6 +72,9 @@ class Library:
         L.ngbDioLayout(dl)
         self.dio_layout = list(dl)                       # parameters, states, stamp rows
         self.fields["dio"] = [L.ngbBsim4FieldName(8, i).decode() for i in range(dl[0])]
+        vl = (ctypes.c_int * 5)()
+        L.ngbVbicLayout(vl)
+        self.vbic_layout = list(vl)                      # parameters, aux, node roles, states, stamp rows
         bl = (ctypes.c_int * 6)()
         L.ngbBsim3Layout(bl)
         self.b3_layout = list(bl)                        # model, bin, instance, node roles, stamp rows, states
@@ -170,6 +173,12 @@ class Circuit:
             assert par.shape[0] == lib.dio_layout[0], "fixture built against a different diode field list"
             lib.check(lib.L.ngbCircuitAddDiodes(c.h, int(n), _ip(_i32(flat["dio/nodes"][[0, 1, 3, 4]])), _ip(_i32(flat["dio/flags"])),
                                                 _dp(par)), "ngbCircuitAddDiodes")
+        n = sc(flat, "vbic/n", 0)
+        if n:
+            par = _f64(flat["vbic/par"]); aux = _f64(flat["vbic/aux"])
+            assert par.shape[0] == lib.vbic_layout[0] and aux.shape[0] == lib.vbic_layout[1]
+            lib.check(lib.L.ngbCircuitAddVbic(c.h, int(n), _ip(_i32(flat["vbic/nodes"])), _ip(_i32(flat["vbic/flags"])),
+                                              _dp(par), _dp(aux)), "ngbCircuitAddVbic")
         n = sc(flat, "vsrc/n", 0)
         if n:
             lib.check(lib.L.ngbCircuitAddVsources(c.h, int(n), _ip(_i32(flat["vsrc/nodes"])), _ip(_i32(flat["vsrc/fn"])),

@@ -16,6 +16,7 @@
 #define NGB_GROUP_SYNC() do { if (nl <= 32) __syncwarp(); else __syncthreads(); } while (0)
 #include "ngb_dev.h"
 #include "ngb_kernels.cuh"
+#include "vbic_eval.cuh"
 
 #ifndef NGB_B4_CTA
 #define NGB_B4_CTA 256
@@ -58,6 +59,15 @@ ngb_k_bsim3_load(const B3Ctx c, int *errflag)
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)c.T) return;
     const int e = b3_load_thread(&c, t);
+    if (e) atomicMax(errflag, e);
+}
+
+__global__ void __launch_bounds__(128)
+ngb_k_vbic_load(const NgbVbicCtx c, int *errflag)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)c.T) return;
+    const int e = vbic_load_thread(&c, t);
     if (e) atomicMax(errflag, e);
 }
 
@@ -336,6 +346,13 @@ int ngb_launch_bsim3_load(const B3Ctx *c, int *errflag)
     const unsigned grid = (unsigned)(((size_t)c->T + 255) / 256);
     ngb_k_bsim3_load<<<grid, 256, 0, g_stream>>>(*c, errflag);
     return post_launch("bsim3_load");
+}
+int ngb_launch_vbic_load(const NgbVbicCtx *c, int *errflag)
+{
+    if (c->T <= 0) return 0;
+    const unsigned grid = (unsigned)(((size_t)c->T + 127) / 128);
+    ngb_k_vbic_load<<<grid, 128, 0, g_stream>>>(*c, errflag);
+    return post_launch("vbic_load");
 }
 int ngb_launch_dio_load(const NgbDioCtx *c, int *errflag)
 {

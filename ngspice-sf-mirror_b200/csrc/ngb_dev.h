@@ -9,6 +9,7 @@
 #include "bsim4_eval.cuh"
 #include "dio_eval.cuh"
 #include "bsim3_eval.cuh"
+#include "vbic_types.h"
 #include "ngb_tran.cuh"
 
 #ifdef __cplusplus
@@ -47,6 +48,7 @@ int ngb_launch_tran_control(const NgbTranCtx *c);
 int ngb_launch_fill_f64(double *p, double value, int n);
 int ngb_launch_dio_load(const NgbDioCtx *c, int *errflag);
 int ngb_launch_bsim3_load(const B3Ctx *c, int *errflag);
+int ngb_launch_vbic_load(const NgbVbicCtx *c, int *errflag);
 
 #ifdef __cplusplus
 }

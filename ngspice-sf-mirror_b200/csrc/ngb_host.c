@@ -187,6 +187,7 @@ void ngbCircuitDestroy(ngb_circuit *c)
     free(c->res_nodes); free(c->res_g); free(c->res_spos);
     free(c->cap_nodes); free(c->cap_par); free(c->cap_spos);
     free(c->b3_nodes); free(c->b3_flags); free(c->b3_prow); free(c->b3_inst); free(c->b3_mtab); free(c->b3_ptab); free(c->b3_spos);
+    free(c->vb_nodes); free(c->vb_flags); free(c->vb_par); free(c->vb_aux); free(c->vb_spos);
     free(c->dio_nodes); free(c->dio_flags); free(c->dio_par); free(c->dio_spos);
     free(c->vs_nodes); free(c->vs_fn); free(c->vs_par); free(c->vs_spos); free(c->vs_cspos);
     free(c->is_nodes); free(c->is_fn); free(c->is_par); free(c->is_spos);
@@ -315,6 +316,71 @@ int ngbCircuitAddBsim3(ngb_circuit *c, int ninst, const int *nodes, const int *f
     c->b3_inst = (double *)xdup(inst, sizeof(double) * B3I_COUNT * (size_t)ninst);
     c->b3_mtab = (double *)xdup(mtab, sizeof(double) * B3M_COUNT * (size_t)nrows);
     c->b3_ptab = (double *)xdup(ptab, sizeof(double) * B3P_COUNT * (size_t)nrows);
+    return NGB_OK;
+}
+/* VBIC: structural entries and stamp statements as (row role, column role) tables */
+#define coll VBN_coll
+#define base VBN_base
+#define emit VBN_emit
+#define subs VBN_subs
+#define cx VBN_cx
+#define ci VBN_ci
+#define bx VBN_bx
+#define bi VBN_bi
+#define ei VBN_ei
+#define bp VBN_bp
+#define si VBN_si
+static const int vb_struct_r[] = {
+#define T(r, cc) r,
+    NGB_VBIC_STRUCT(T)
+#undef T
+};
+static const int vb_struct_c[] = {
+#define T(r, cc) cc,
+    NGB_VBIC_STRUCT(T)
+#undef T
+};
+static const int vb_stamp_r[] = {
+#define SR(n, v) n,
+#define SM(r, cc, v) r,
+    NGB_VBIC_STAMPS(SR, SM)
+#undef SR
+#undef SM
+};
+static const int vb_stamp_c[] = {           /* -1: right-hand side */
+#define SR(n, v) -1,
+#define SM(r, cc, v) cc,
+    NGB_VBIC_STAMPS(SR, SM)
+#undef SR
+#undef SM
+};
+#undef coll
+#undef base
+#undef emit
+#undef subs
+#undef cx
+#undef ci
+#undef bx
+#undef bi
+#undef ei
+#undef bp
+#undef si
+void ngbVbicLayout(int out[5]) { out[0] = VBIC_NP; out[1] = VBA_COUNT; out[2] = VBN_COUNT; out[3] = VBS_COUNT; out[4] = VBIC_NSTAMPS; }
+
+int ngbCircuitAddVbic(ngb_circuit *c, int n, const int *nodes, const int *flags, const double *par, const double *aux)
+{
+    int i;
+    if (c->finalized || c->vb_n) return NGB_E_PANIC;
+    for (i = 0; i < n; i++)
+        if (flags[i] & VBF_UNSUPPORTED) {
+            ngb_set_error("VBIC instance %d: self-heating (0x2) / excess phase (0x4) not on this path (flags 0x%x)", i, flags[i]);
+            return NGB_E_UNSUPP;
+        }
+    c->vb_n = n;
+    c->vb_nodes = (int *)xdup(nodes, sizeof(int) * VBN_COUNT * (size_t)n);
+    c->vb_flags = (int *)xdup(flags, sizeof(int) * (size_t)n);
+    c->vb_par = (double *)xdup(par, sizeof(double) * VBIC_NP * (size_t)n);
+    c->vb_aux = (double *)xdup(aux, sizeof(double) * VBA_COUNT * (size_t)n);
     return NGB_OK;
 }
 int ngbCircuitAddDiodes(ngb_circuit *c, int n, const int *nodes, const int *flags, const double *par)
@@ -450,6 +516,9 @@ int ngbCircuitFinalize(ngb_circuit *c)
         int p = c->res_nodes[i], q = c->res_nodes[c->res_n + i];
         coo_push(&coo, p, p); coo_push(&coo, q, q); coo_push(&coo, p, q); coo_push(&coo, q, p);
     }
+    for (i = 0; i < c->vb_n; i++)
+        for (k = 0; k < (int)(sizeof vb_struct_r / sizeof vb_struct_r[0]); k++)
+            coo_push(&coo, c->vb_nodes[vb_struct_r[k] * c->vb_n + i], c->vb_nodes[vb_struct_c[k] * c->vb_n + i]);
     for (i = 0; i < c->vs_n; i++) {
         int p = c->vs_nodes[i], q = c->vs_nodes[c->vs_n + i], br = c->vs_nodes[2 * c->vs_n + i];
         coo_push(&coo, p, br); coo_push(&coo, q, br); coo_push(&coo, br, q); coo_push(&coo, br, p);
@@ -494,7 +563,7 @@ int ngbCircuitFinalize(ngb_circuit *c)
     }
 
     /* 3. stamp rows and contribution lists, in CKTload order: device types by their rank in
-     *    the reference device table (bsim3 < bsim4 < cap < dio < isrc < res < vsrc, dev.c:142-209), instances
+     *    the reference device table (bsim3 < bsim4 < cap < dio < isrc < res < vbic < vsrc, dev.c:142-209), instances
      *    in list order, positions in load order */
     c->nstamp_rows = 0;
     c->b3_spos = (int *)xcalloc((size_t)c->b3_n * B3S_COUNT + 1, sizeof(int));
@@ -626,6 +695,13 @@ int ngbCircuitFinalize(ngb_circuit *c)
         CONST_ROW(slot_lookup(c, p, p), g); CONST_ROW(slot_lookup(c, q, q), g);
         CONST_ROW(slot_lookup(c, p, q), -g); CONST_ROW(slot_lookup(c, q, p), -g);
     }
+    c->vb_spos = (int *)xcalloc((size_t)c->vb_n * VBIC_NSTAMPS + 1, sizeof(int));
+    for (i = 0; i < c->vb_n; i++)
+        for (k = 0; k < VBIC_NSTAMPS; k++) {
+            const int rr = c->vb_nodes[vb_stamp_r[k] * c->vb_n + i];
+            if (vb_stamp_c[k] < 0) c->vb_spos[k * c->vb_n + i] = new_row(c, &cb, (rr > 0 && c->eq2col[rr] >= 0) ? c->nnz + rr : -1);
+            else c->vb_spos[k * c->vb_n + i] = new_row(c, &cb, slot_lookup(c, rr, c->vb_nodes[vb_stamp_c[k] * c->vb_n + i]));
+        }
     c->vs_spos = (int *)xcalloc((size_t)c->vs_n + 1, sizeof(int));
     c->vs_cspos = (int *)xcalloc((size_t)c->vs_n * 4 + 1, sizeof(int));
     for (i = 0; i < c->vs_n; i++) {
@@ -1176,6 +1252,15 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
         b->dio_flags = (int *)dev_dup(c->dio_flags, sizeof(int) * (size_t)c->dio_n);
         b->dio_spos = (int *)dev_dup(c->dio_spos, sizeof(int) * DIOS_COUNT * (size_t)c->dio_n);
     }
+    if (c->vb_n) {
+        const size_t T = (size_t)c->vb_n * S;
+        b->vb_par = (double *)dalloc_rep(b, "vbic.par", c->vb_par, VBIC_NP, c->vb_n, S);
+        b->vb_aux = (double *)dalloc_rep(b, "vbic.aux", c->vb_aux, VBA_COUNT, c->vb_n, S);
+        b->vb_state = (double *)dalloc(b, "vbic.state", sizeof(double) * NGB_NHIST * VBS_COUNT * T);
+        b->vb_nodes = (int *)dev_dup(c->vb_nodes, sizeof(int) * VBN_COUNT * (size_t)c->vb_n);
+        b->vb_flags = (int *)dev_dup(c->vb_flags, sizeof(int) * (size_t)c->vb_n);
+        b->vb_spos = (int *)dev_dup(c->vb_spos, sizeof(int) * VBIC_NSTAMPS * (size_t)c->vb_n);
+    }
     if (c->vs_n) {
         b->vs_par = (double *)dalloc_rep(b, "vsrc.par", c->vs_par, 9, c->vs_n, S);
         b->vs_fn = (int *)dev_dup(c->vs_fn, sizeof(int) * 3 * (size_t)c->vs_n);
@@ -1258,6 +1343,7 @@ void ngbBatchDestroy(ngb_batch *b)
     ngb_dev_free(b->b4_nodes); ngb_dev_free(b->b4_spos); ngb_dev_free(b->b4_prow_t);
     ngb_dev_free(b->cap_nodes); ngb_dev_free(b->cap_spos);
     ngb_dev_free(b->dio_nodes); ngb_dev_free(b->dio_flags); ngb_dev_free(b->dio_spos);
+    ngb_dev_free(b->vb_nodes); ngb_dev_free(b->vb_flags); ngb_dev_free(b->vb_spos);
     ngb_dev_free(b->b3_mtab); ngb_dev_free(b->b3_ptab); ngb_dev_free(b->b3_prow); ngb_dev_free(b->b3_flags); ngb_dev_free(b->b3_nodes); ngb_dev_free(b->b3_spos);
     ngb_dev_free(b->vs_fn); ngb_dev_free(b->vs_spos); ngb_dev_free(b->is_fn); ngb_dev_free(b->is_spos);
     if (b->have_lu) {
@@ -1332,6 +1418,14 @@ void ngb_fill_b3ctx(ngb_batch *b, B3Ctx *x)
     x->state = b->b3_state; x->von = b->b3_von; x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl;
     x->temp = c->opt.temp; x->vt0 = c->opt.vt0;
 }
+void ngb_fill_vbctx(ngb_batch *b, NgbVbicCtx *x)
+{
+    const ngb_circuit *c = b->c;
+    memset(x, 0, sizeof *x);
+    x->ninst = c->vb_n; x->S = b->S; x->T = c->vb_n * b->S; x->nstamps = VBIC_NSTAMPS; x->nodes = b->vb_nodes; x->flags = b->vb_flags;
+    x->par = b->vb_par; x->aux = b->vb_aux; x->spos = b->vb_spos; x->state = b->vb_state; x->stamp = b->stamp;
+    x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl;
+}
 void ngb_fill_dioctx(ngb_batch *b, NgbDioCtx *x)
 {
     const ngb_circuit *c = b->c;
@@ -1383,6 +1477,7 @@ int ngb_enqueue_load(ngb_batch *b)
     if (c->cap_n) { NgbCapCtx x; ngb_fill_capctx(b, &x); if ((r = ngb_launch_cap_load(&x, b->errflag))) return r; }
     if (c->dio_n) { NgbDioCtx x; ngb_fill_dioctx(b, &x); if ((r = ngb_launch_dio_load(&x, b->errflag))) return r; }
     if (c->is_n) { NgbSrcCtx x; ngb_fill_srcctx(b, &x, 1); if ((r = ngb_launch_src_load(&x))) return r; }
+    if (c->vb_n) { NgbVbicCtx x; ngb_fill_vbctx(b, &x); if ((r = ngb_launch_vbic_load(&x, b->errflag))) return r; }
     if (c->vs_n) { NgbSrcCtx x; ngb_fill_srcctx(b, &x, 0); if ((r = ngb_launch_src_load(&x))) return r; }
     { NgbAsmCtx x; ngb_fill_asmctx(b, &x); if ((r = ngb_launch_assemble(&x))) return r; }
     return NGB_OK;

@@ -5,6 +5,7 @@
 #include "bsim4_eval.cuh"
 #include "dio_eval.cuh"
 #include "bsim3_eval.cuh"
+#include "vbic_types.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -21,6 +22,7 @@ struct ngb_circuit {
     int res_n; int *res_nodes; double *res_g; int *res_spos;
     int cap_n; int *cap_nodes; double *cap_par; int *cap_spos;
     int b3_n, b3_nrows; int *b3_nodes, *b3_flags, *b3_prow; double *b3_inst, *b3_mtab, *b3_ptab; int *b3_spos;
+    int vb_n; int *vb_nodes, *vb_flags; double *vb_par, *vb_aux; int *vb_spos;
     int dio_n; int *dio_nodes, *dio_flags; double *dio_par; int *dio_spos;
     int vs_n; int *vs_nodes, *vs_fn; double *vs_par; int *vs_spos, *vs_cspos;
     int is_n; int *is_nodes, *is_fn; double *is_par; int *is_spos;
@@ -53,6 +55,7 @@ struct ngb_batch {
     double *b4_inst, *b4_state, *b4_op, *b4_mtab, *b4_ptab; int *b4_prow, *b4_prow_t, *b4_flags, *b4_nodes, *b4_spos;
     double *cap_par, *cap_state; int *cap_nodes, *cap_spos;
     double *b3_inst, *b3_state, *b3_von, *b3_mtab, *b3_ptab; int *b3_prow, *b3_flags, *b3_nodes, *b3_spos;
+    double *vb_par, *vb_aux, *vb_state; int *vb_nodes, *vb_flags, *vb_spos;
     double *dio_par, *dio_state; int *dio_nodes, *dio_flags, *dio_spos;
     double *vs_par; int *vs_fn, *vs_spos;
     double *is_par; int *is_fn, *is_spos;
@@ -69,6 +72,7 @@ void ngb_fill_b4ctx(struct ngb_batch *b, B4Ctx *x);
 void ngb_fill_capctx(struct ngb_batch *b, NgbCapCtx *x);
 void ngb_fill_dioctx(struct ngb_batch *b, NgbDioCtx *x);
 void ngb_fill_b3ctx(struct ngb_batch *b, B3Ctx *x);
+void ngb_fill_vbctx(struct ngb_batch *b, NgbVbicCtx *x);
 void ngb_fill_srcctx(struct ngb_batch *b, NgbSrcCtx *x, int is_current);
 void ngb_fill_asmctx(struct ngb_batch *b, NgbAsmCtx *x);
 void ngb_fill_luctx(struct ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve, int which);

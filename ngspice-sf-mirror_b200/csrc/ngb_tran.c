@@ -120,6 +120,7 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     if (b->b4_state) ngb_dev_memset(b->b4_state, 0, sizeof(double) * NGB_NHIST * B4ST_COUNT * (size_t)c->b4_n * S);
     if (b->b3_state) { ngb_dev_memset(b->b3_state, 0, sizeof(double) * NGB_NHIST * B3ST_COUNT * (size_t)c->b3_n * S);
                        ngb_dev_memset(b->b3_von, 0, sizeof(double) * (size_t)c->b3_n * S); }
+    if (b->vb_state) ngb_dev_memset(b->vb_state, 0, sizeof(double) * NGB_NHIST * VBS_COUNT * (size_t)c->vb_n * S);
     if (b->dio_state) ngb_dev_memset(b->dio_state, 0, sizeof(double) * NGB_NHIST * DIOST_COUNT * (size_t)c->dio_n * S);
     if (b->cap_state) ngb_dev_memset(b->cap_state, 0, sizeof(double) * NGB_NHIST * 2 * (size_t)c->cap_n * S);
     if (b->b4_op) ngb_dev_memset(b->b4_op, 0, sizeof(double) * B4O_COUNT * (size_t)c->b4_n * S);

@@ -34,6 +34,7 @@
 #include "vsrc/vsrcdefs.h"
 #include "isrc/isrcdefs.h"
 #include "dio/diodefs.h"
+#include "vbic/vbicdefs.h"
 #include "bsim3/bsim3def.h"
 #include "klu_internal.h"
 #include <stdio.h>
@@ -42,6 +43,7 @@
 
 #include "../ngspice-sf-mirror_b200/csrc/bsim4_fields.h"
 #include "../ngspice-sf-mirror_b200/csrc/dio_fields.h"
+#include "../ngspice-sf-mirror_b200/csrc/vbic_types.h"
 #include "../ngspice-sf-mirror_b200/csrc/bsim3_fields.h"
 
 extern SPICEdev **DEVices;
@@ -97,7 +99,7 @@ static int slot_of(KLUmatrix *K, double *p)
     return -1;     /* trash cell (ground row/column) */
 }
 
-static int b4_type = -2, res_type, cap_type, vsrc_type, isrc_type, dio_type, b3_type;
+static int b4_type = -2, res_type, cap_type, vsrc_type, isrc_type, dio_type, b3_type, vbic_type;
 static void lookup_types(void)
 {
     if (b4_type != -2) return;
@@ -107,6 +109,7 @@ static void lookup_types(void)
     vsrc_type = CKTtypelook("Vsource");
     isrc_type = CKTtypelook("Isource");
     dio_type = CKTtypelook("Diode");
+    vbic_type = CKTtypelook("VBIC");
     b3_type = CKTtypelook("BSIM3");
 }
 
@@ -417,6 +420,55 @@ static void dump_dio(FILE *f, CKTcircuit *ckt, KLUmatrix *K)
     put_is(f, "dio/n", n);
 }
 
+/* VBIC: the parameter vector as VBICload assembles it (vbicload.c:127-166), node numbers, flags */
+static void dump_vbic(FILE *f, CKTcircuit *ckt)
+{
+    int n = 0, i, k;
+    if (vbic_type >= 0) {
+        VBICmodel *m; VBICinstance *h;
+        for (m = (VBICmodel *)ckt->CKThead[vbic_type]; m; m = VBICnextModel(m))
+            for (h = VBICinstances(m); h; h = VBICnextInstance(h)) n++;
+        if (n) {
+            int *nodes = (int *)calloc((size_t)n * VBN_COUNT, sizeof(int));
+            int *flags = (int *)calloc((size_t)n, sizeof(int)), *sb = (int *)calloc((size_t)n, sizeof(int));
+            double *par = (double *)calloc((size_t)n * VBIC_NP, sizeof(double)), *aux = (double *)calloc((size_t)n * VBA_COUNT, sizeof(double));
+            size_t nb = 0; char *names = (char *)calloc((size_t)n * 64 + 1, 1);
+            i = 0;
+            for (m = (VBICmodel *)ckt->CKThead[vbic_type]; m; m = VBICnextModel(m))
+                for (h = VBICinstances(m); h; h = VBICnextInstance(h), i++) {
+                    double p[VBIC_NP];
+                    const int nd[VBN_COUNT] = { h->VBICcollNode, h->VBICbaseNode, h->VBICemitNode, h->VBICsubsNode, h->VBICcollCXNode,
+                        h->VBICcollCINode, h->VBICbaseBXNode, h->VBICbaseBINode, h->VBICemitEINode, h->VBICbaseBPNode, h->VBICsubsSINode };
+                    for (k = 0; k < VBN_COUNT; k++) nodes[(size_t)k * n + i] = nd[k];
+                    memcpy(p, &m->VBICtnom, sizeof p);
+                    p[0] = h->VBICtemp - CONSTCtoK + p[105];
+                    p[1] = h->VBICtextCollResist; p[2] = h->VBICtintCollResist; p[3] = h->VBICtepiSatVoltage; p[4] = h->VBICtepiDoping;
+                    p[6] = h->VBICtextBaseResist; p[7] = h->VBICtintBaseResist; p[8] = h->VBICtemitterResist; p[9] = h->VBICtsubstrateResist;
+                    p[10] = h->VBICtparBaseResist; p[11] = h->VBICtsatCur; p[12] = h->VBICtemissionCoeffF; p[13] = h->VBICtemissionCoeffR;
+                    p[16] = h->VBICtdepletionCapBE; p[17] = h->VBICtpotentialBE; p[21] = h->VBICtdepletionCapBC; p[23] = h->VBICtextCapBC;
+                    p[24] = h->VBICtpotentialBC; p[27] = h->VBICtextCapSC; p[28] = h->VBICtpotentialSC; p[31] = h->VBICtidealSatCurBE;
+                    p[34] = h->VBICtnidealSatCurBE; p[36] = h->VBICtidealSatCurBC; p[38] = h->VBICtnidealSatCurBC; p[41] = h->VBICtavalanchePar2BC;
+                    p[42] = h->VBICtparasitSatCur; p[45] = h->VBICtidealParasitSatCurBE; p[46] = h->VBICtnidealParasitSatCurBE;
+                    p[47] = h->VBICtidealParasitSatCurBC; p[49] = h->VBICtnidealParasitSatCurBC; p[53] = h->VBICtrollOffF;
+                    p[94] = h->VBICtsepISRR; p[98] = h->VBICtvbbe; p[99] = h->VBICtnbbe;
+                    for (k = 0; k < VBIC_NP; k++) par[(size_t)k * n + i] = p[k];
+                    aux[(size_t)VBA_type * n + i] = m->VBICtype; aux[(size_t)VBA_tVcrit * n + i] = h->VBICtVcrit;
+                    aux[(size_t)VBA_icVBE * n + i] = h->VBICicVBE; aux[(size_t)VBA_icVCE * n + i] = h->VBICicVCE;
+                    aux[(size_t)VBA_scale * n + i] = h->VBICarea * h->VBICm; aux[(size_t)VBA_temp * n + i] = h->VBICtemp;
+                    flags[i] = (h->VBICoff ? VBF_OFF : 0) | (h->VBIC_selfheat ? VBF_SELFHEAT : 0) | (h->VBIC_excessPhase ? VBF_EXCESS : 0);
+                    sb[i] = h->VBICstate;
+                    nb += (size_t)snprintf(names + nb, 64, "%s\n", h->VBICname);
+                }
+            put_i2(f, "vbic/nodes", nodes, VBN_COUNT, n); put_i1(f, "vbic/flags", flags, n); put_i1(f, "vbic/state_base", sb, n);
+            put_d2(f, "vbic/par", par, VBIC_NP, n); put_d2(f, "vbic/aux", aux, VBA_COUNT, n);
+            { int *nb_i = (int *)calloc(nb + 1, sizeof(int)); size_t q; for (q = 0; q < nb; q++) nb_i[q] = (unsigned char)names[q];
+              put_i1(f, "vbic/names_bytes", nb_i, (long long)nb); free(nb_i); }
+            free(nodes); free(flags); free(sb); free(par); free(aux); free(names);
+        }
+    }
+    put_is(f, "vbic/n", n);
+}
+
 static void dump_flat(CKTcircuit *ckt, const char *path)
 {
     FILE *f = ngt_open(path);
@@ -479,6 +531,7 @@ static void dump_flat(CKTcircuit *ckt, const char *path)
     dump_bsim4(f, ckt, K);
     dump_linear(f, ckt, K);
     dump_dio(f, ckt, K);
+    dump_vbic(f, ckt);
     dump_bsim3(f, ckt, K);
     fclose(f);
     free(ntype); free(nic); free(nicg); free(names);

@@ -114,6 +114,42 @@ def dio_netlist():
         ".end", ""])
 
 
+def vbic_netlist():
+    """VBIC (level 4): common-emitter stage with the full-featured card of tests/vbic/CEamp.cir (quasi-
+    saturation, avalanche, parasitic transistor, knee currents; TD and RTH removed -- excess phase and
+    self-heating are outside this path), a pnp follower with a lean card (no series resistances except
+    RE: collapsed internal nodes), an emitter-coupled pair with area/m factors; DC operating point and
+    PULSE transient"""
+    return "\n".join([
+        "* VBIC stages: CE amplifier, pnp follower, emitter-coupled pair",
+        "vcc vp 0 dc 5",
+        "vin in 0 dc 0.7 pulse(0.7 1.1 1n 0.5n 0.5n 6n 14n)",
+        "rb in b 1k",
+        "rc vp c 1k",
+        "q1 c b 0 0 n1",
+        "cl c 0 0.2p",
+        "q2 0 c e2 vp p1",
+        "re2 vp e2 2k",
+        "vref r 0 dc 0.9",
+        "q3 o1 in t 0 n1 area=2",
+        "q4 o2 r t 0 n1 area=2 m=1.5",
+        "r5 vp o1 1.5k", "r6 vp o2 1.5k",
+        "it t 0 dc 1.2m",
+        "c2 o2 0 0.1p",
+        ".model n1 npn level=4",
+        "+ is=1e-16 ibei=1e-18 iben=5e-15 ibci=2e-17 ibcn=5e-15 isp=1e-15 rcx=10",
+        "+ rci=60 rbx=10 rbi=40 re=2 rs=20 rbp=40 vef=10 ver=4 ikf=2e-3 itf=8e-2",
+        "+ xtf=20 ikr=2e-4 ikp=2e-4 cje=1e-13 cjc=2e-14 cjep=1e-13 cjcp=4e-13 vo=2",
+        "+ gamm=2e-11 hrcf=2 qco=1e-12 avc1=2 avc2=15 tf=10e-12 tr=100e-12",
+        "+ cbeo=5e-15 cbco=3e-15 wbe=0.8 ibeip=1e-19 ibenp=1e-16 ibcip=1e-17 ibcnp=1e-15 aje=-0.5 ajc=-0.5 ajs=-0.5",
+        ".model p1 pnp level=4",
+        "+ is=2e-16 ibei=2e-18 iben=1e-15 ibci=1e-17 ibcn=1e-15 re=3 vef=20 ver=6 ikf=1e-3",
+        "+ cje=5e-14 cjc=1e-14 tf=20e-12 tr=200e-12 fc=0.9 qbm=1 nkf=0.6",
+        ".option klu",
+        ".tran 0.05n 30n",
+        ".end", ""])
+
+
 def b3_cards():
     """the level-8 (BSIM3v3.3.0) n1/p1 cards of examples/Monte_Carlo/MC_ring.sp"""
     src = open(os.path.join(REF, "examples/Monte_Carlo/MC_ring.sp")).read()
@@ -179,7 +215,7 @@ def run(name, netlist, calls, save):
     os.makedirs(TMP, exist_ok=True)
     cir = os.path.join(TMP, name + ".cir")
     open(cir, "w").write(netlist)
-    if name in ("ro17", "ro101", "ro17k", "inv", "dio", "b3ring", "arr"):
+    if name in ("ro17", "ro101", "ro17k", "inv", "dio", "b3ring", "arr", "vbic"):
         # the netlist itself is kept too: the CPU-baseline arm of bench.py feeds it to oracle/_ref/ngspice
         os.makedirs(os.path.join(HERE, "netlists"), exist_ok=True)
         open(os.path.join(HERE, "netlists", name + ".cir"), "w").write(netlist)
@@ -236,6 +272,8 @@ if __name__ == "__main__":
         run("inv", inv_netlist(), "0-40,100,101,300,301", ["out", "in", "vdd#branch", "vin#branch"])
     if "dio" in which:
         run("dio", dio_netlist(), "0-30,200,201,1000,1001,2000", ["out", "z", "w", "u", "vin#branch"])
+    if "vbic" in which:
+        run("vbic", vbic_netlist(), "0-40,100,101,300,301,800", ["c", "e2", "o1", "o2", "b", "vcc#branch"])
     if "b3ring" in which:
         run("b3ring", b3_netlist(5), "0-40,300,301,1000,1001", ["out", "buf", "n2", "vdd#branch"])
     if "arr" in which:

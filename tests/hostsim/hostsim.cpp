@@ -10,6 +10,7 @@
 #include <vector>
 #include "ngb_dev.h"
 #include "ngb_kernels.cuh"
+#include "vbic_eval.cuh"
 
 static long g_launches = 0;
 extern "C" {
@@ -48,6 +49,12 @@ int ngb_launch_bsim3_load(const B3Ctx *c, int *errflag)
 {
     g_launches++;
     for (size_t t = 0; t < (size_t)c->T; t++) { int e = b3_load_thread(c, t); if (e && errflag && !errflag[0]) errflag[0] = e; }
+    return 0;
+}
+int ngb_launch_vbic_load(const NgbVbicCtx *c, int *errflag)
+{
+    g_launches++;
+    for (size_t t = 0; t < (size_t)c->T; t++) { int e = vbic_load_thread(c, t); if (e && errflag && !errflag[0]) errflag[0] = e; }
     return 0;
 }
 int ngb_launch_dio_load(const NgbDioCtx *c, int *errflag)

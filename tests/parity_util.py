@@ -62,6 +62,9 @@ def state_maps(flat, lib):
     n = ngt.scalar(flat, "dio/n", 0)
     if n:
         out["dio"] = flat["dio/state_base"][None, :] + np.arange(lib.dio_layout[1])[:, None]
+    n = ngt.scalar(flat, "vbic/n", 0)
+    if n:
+        out["vbic"] = flat["vbic/state_base"][None, :] + np.arange(lib.vbic_layout[3])[:, None]
     return out
 
 
@@ -92,7 +95,7 @@ def replay_load(lib, circ, flat, trace, call, S=1, batch=None):
     b.put("x", x)
     maps = state_maps(flat, lib)
     hist = [trace[c + "state0_in"], trace[c + "state1_in"], trace.get(c + "state2_in")]
-    for dev, key in (("b4", "b4.state"), ("cap", "cap.state"), ("dio", "dio.state"), ("b3", "b3.state")):
+    for dev, key in (("b4", "b4.state"), ("cap", "cap.state"), ("dio", "dio.state"), ("b3", "b3.state"), ("vbic", "vbic.state")):
         if dev not in maps:
             continue
         m = maps[dev]                                  # [k][n]
@@ -122,6 +125,8 @@ def replay_load(lib, circ, flat, trace, call, S=1, batch=None):
         ours["b3_state"] = b.get("b3.state", (4,) + maps["b3"].shape + (S,))
     if "dio" in maps:
         ours["dio_state"] = b.get("dio.state", (4,) + maps["dio"].shape + (S,))
+    if "vbic" in maps:
+        ours["vbic_state"] = b.get("vbic.state", (4,) + maps["vbic"].shape + (S,))
     ref = dict(Ax=trace[c + "Ax"], rhs=trace[c + "rhs"][:neq1], noncon=int(trace[c + "noncon"][0]),
                state0=trace[c + "state0_out"], state1=trace.get(c + "state1_out"), mode=mode)
     if c + "b4_op_out" in trace:

@@ -41,6 +41,7 @@ def _check(exe, name, expect_backend, env=None):
     assert f"ngb_shim: CKTload" in log and expect_backend in log, log[-1500:]     # the shim really took the hot path
     assert h0 == h1
     assert v0.shape == v1.shape
+    _check.nvars = int([ln for ln in h0.splitlines() if ln.startswith("No. Variables")][0].split(":")[1])
     return v0, v1
 
 
@@ -50,10 +51,28 @@ def test_dropin_hostsim_rawfile_identical(name):
     assert np.array_equal(v0, v1)
 
 
+def _vbic_close(v0, v1):
+    """VBIC Jacobians come from dual numbers (rounding-level differences from the generated code):
+    same number of points (v*.shape checked by _check), 1e-9 relative to each vector's range"""
+    a = v0.reshape(-1, _check.nvars); b = v1.reshape(-1, _check.nvars)
+    return float(np.max(np.max(np.abs(a - b), axis=0) / np.maximum(np.max(np.abs(a), axis=0), 1e-300)))
+
+
+def test_dropin_hostsim_vbic_rawfile():
+    v0, v1 = _check(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb_hostsim"), "vbic", "hostsim")
+    assert _vbic_close(v0, v1) <= 1e-9
+
+
 def test_dropin_hostsim_load_only_identical():
     """NGB_SHIM_LU=0: device load, host KLU"""
     v0, v1 = _check(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb_hostsim"), "inv", "hostsim", env={"NGB_SHIM_LU": "0"})
     assert np.array_equal(v0, v1)
+
+
+@pytest.mark.gpu
+def test_dropin_gpu_vbic_rawfile():
+    v0, v1 = _check(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb"), "vbic", "cuda-sm_100a")
+    assert _vbic_close(v0, v1) <= 1e-9
 
 
 @pytest.mark.gpu

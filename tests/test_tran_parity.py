@@ -45,6 +45,14 @@ def test_tran_hostsim_bit_identical(hostsim_lib, name):
     _compare(res, t, v, wave, 0, exact=True)
 
 
+def test_tran_hostsim_vbic(hostsim_lib):
+    """VBIC stages (DC operating point + PULSE transient): identical accepted / rejected / iteration
+    counts and 1e-9 on the waveforms.  Not bit-identical by construction: the Jacobian entries come from
+    forward-mode dual numbers, equal to the reference's generated derivative code up to rounding."""
+    res, t, v, wave = _run(hostsim_lib, "vbic")
+    _compare(res, t, v, wave, 0, exact=False)
+
+
 def _mc_inst(lib):
     base = ngt.read(f"{GOLDEN}/ro17k.flat.ngt")
     dv_netlist = np.load(f"{GOLDEN}/ro17mc.delvto.npy")       # columns: mp1 mn1 mp2 mn2 ... (netlist order)
@@ -82,7 +90,7 @@ def test_tran_hostsim_mc_batch(hostsim_lib):
 # device follows the reference bit for bit; the assertions below allow 1e-9 (the north_star
 # tolerance) but identical accepted / rejected / iteration counts are required.
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,exact", [("ro17k", True), ("ro17", True), ("inv", True), ("dio", False), ("b3ring", True)])
+@pytest.mark.parametrize("name,exact", [("ro17k", True), ("ro17", True), ("inv", True), ("dio", False), ("b3ring", True), ("vbic", False)])
 def test_tran_gpu_matches_reference(cuda_lib, name, exact):
     """north_star bar: 1e-9 relative and identical accepted-step count; the device arithmetic
     (no FMA contraction, glibc-compatible exp/log) in fact reproduces the reference bit for bit.
