@@ -523,17 +523,199 @@ def bench_array(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------ config 5: mixed-model parameter sweep
+SWEEP_GRID = 256                      # 256 x 256 = 65 536 points of (vdd, r1); 8 192 points per GPU on 8 GPUs
+SWEEP_COUNTS = {"bsim4": 16, "bsim3": 8, "vbic": 2, "diode": 3}
+
+
+def sweep_points(rank, world, n):
+    """the (vdd, r1) netlist tokens of this rank's share of the grid: consecutive rows of the 256 x 256 grid"""
+    from parity_util import pkg
+    vt = pkg.sweep.grid_tokens(1.6, 2.4, SWEEP_GRID)
+    rt = pkg.sweep.grid_tokens(200.0, 5000.0, SWEEP_GRID, fmt="{:.5g}")
+    first = (rank * n) % (SWEEP_GRID * SWEEP_GRID)
+    idx = (first + np.arange(n)) % (SWEEP_GRID * SWEEP_GRID)
+    return [vt[i // SWEEP_GRID] for i in idx], [rt[i % SWEEP_GRID] for i in idx]
+
+
+def sweep_cpu_baseline(nproc, per_proc=128):
+    """the reference on the same sweep: `nproc` processes, each running `per_proc` grid points one after the other"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ngspice")
+    if not os.path.exists(exe):
+        return None
+    base = open(os.path.join(GOLDEN, "netlists", "mix.cir")).read()
+    n = nproc * per_proc
+    stride = (SWEEP_GRID * SWEEP_GRID) // n
+    from parity_util import pkg
+    vt = pkg.sweep.grid_tokens(1.6, 2.4, SWEEP_GRID)
+    rt = pkg.sweep.grid_tokens(200.0, 5000.0, SWEEP_GRID, fmt="{:.5g}")
+    tmp = tempfile.mkdtemp(prefix="ngb_sweep_")
+    procs = []
+    t0 = time.time()
+    for p in range(nproc):
+        files = []
+        for k in range(per_proc):
+            i = (p * per_proc + k) * stride + (p * 37 + k * 11) % SWEEP_GRID      # spread over the grid
+            text = base.replace("vdd dd 0 dc 2.0", f"vdd dd 0 dc {vt[(i // SWEEP_GRID) % SWEEP_GRID]}").replace("r1 a8 x 1k", f"r1 a8 x {rt[i % SWEEP_GRID]}")
+            text = text.replace(".option klu", ".option klu acct")
+            f = os.path.join(tmp, f"p{p}_{k}.cir")
+            open(f, "w").write(text)
+            files.append(f)
+        cmd = " ; ".join(f"{exe} -b -r {f}.raw {f} > {f}.log 2>&1 ; rm -f {f}.raw" for f in files)
+        procs.append((subprocess.Popen(["bash", "-c", cmd]), files))
+    iters = 0
+    for pr, files in procs:
+        pr.wait()
+    wall = time.time() - t0
+    for _, files in procs:
+        for f in files:
+            for ln in open(f + ".log", errors="replace"):
+                if ln.startswith("Total iterations"):
+                    iters += int(ln.split("=")[-1].strip().split()[0])
+    return n / wall, iters, wall, f"{n} grid points ({per_proc} per process x {nproc} processes), DC op + 200-step transient each"
+
+
+def bench_sweep(args):
+    import torch
+    import torch.distributed as dist
+    from parity_util import ngt, pkg, run_patterns
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            cores = os.cpu_count() or 1
+            r = sweep_cpu_baseline(cores)
+            if r is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ngspice not built"}))
+            else:
+                print(json.dumps({"impl": "reference", "metric": "sweep points/s", "value": r[0], "unit": "points/s", "n_gpus": args.gpus,
+                                  "steps": 1, "warmup": 0, "ms_per_step": r[2] * 1e3, "higher_is_better": True, "scaling": "weak",
+                                  "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": sweep_config(args),
+                                  "cpu_baseline": {"value": r[0], "unit": "points/s", "cores": cores, "kind": "reference", "sample": r[3]},
+                                  "e2e": {"value": r[0], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = pkg.library()
+    assert lib.backend == "cuda-sm_100a"
+    lib.check(lib.L.ngbInit(local), "ngbInit")
+    stream = torch.cuda.Stream(device=local)
+    lib.check(lib.L.ngbSetStream(ctypes.c_void_p(stream.cuda_stream)), "ngbSetStream")
+
+    flat = ngt.read(f"{GOLDEN}/mix.flat.ngt")
+    trace = ngt.read(f"{GOLDEN}/mix.trace.ngt.gz")
+    wave = ngt.read(f"{GOLDEN}/mix.wave.ngt")
+    S = args.samples
+    circ = pkg.Circuit.from_flat(lib, flat, lu_pattern=run_patterns(trace))
+    batch = pkg.Batch(circ, S, device=local)
+    save_eq = wave["save_eq"][:5]                     # a8, x, y4, cq, e2
+    max_points = 320
+    vdd_tok, r_tok = sweep_points(rank, world, S)
+    vpar = pkg.sweep.vsource_table(flat, S, {"vdd": vdd_tok})
+    gtab = pkg.sweep.resistor_table(flat, S, {"r1": r_tok})
+    out_t = torch.empty((S, max_points), dtype=torch.float64).pin_memory()
+    out_v = torch.empty((S, max_points, len(save_eq)), dtype=torch.float64).pin_memory()
+    h2d_bytes = vpar.nbytes + gtab.nbytes
+    d2h_bytes = (out_t.numel() + out_v.numel()) * 8
+
+    def step(e2e):
+        if e2e:
+            batch.put("vsrc.par", vpar)
+            batch.set_resistors(gtab)
+        res = batch.tran(max_points, save_eq)
+        if e2e:
+            lib.check(lib.L.ngbTranWaves(batch.h, ctypes.cast(out_t.data_ptr(), ctypes.POINTER(ctypes.c_double)),
+                                         ctypes.cast(out_v.data_ptr(), ctypes.POINTER(ctypes.c_double))), "ngbTranWaves")
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    batch.put("vsrc.par", vpar)
+    batch.set_resistors(gtab)
+    for _ in range(args.warmup):
+        res = step(False)
+    bad = int((res.accepted.astype(np.int64) < 100).sum())       # points whose transient did not run through
+
+    def timed(e2e):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        iters = 0; ticks = 0
+        barrier()
+        n0 = lib.launch_count()
+        for k in range(args.steps):
+            evs[k][0].record(stream)
+            r = step(e2e)
+            evs[k][1].record(stream)
+            iters += int(r.numiter.astype(np.int64).sum()); ticks += r.ticks
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in evs), iters, ticks, lib.launch_count() - n0
+
+    with ClockSampler(local) as clk:
+        ms, iters, ticks, launches = timed(False)
+    clocks = clk.summary()
+    ms_e2e, iters_e2e, _, _ = timed(True)
+    tt = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    ww = torch.tensor([float(iters), float(S * args.steps), float(bad)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ww, op=dist.ReduceOp.SUM)
+    ms_max, ms_e2e_max = tt.tolist()
+    iters_tot, points_tot, bad_tot = ww.tolist()
+    if rank == 0:
+        hbm_peak, which = peaks()
+        ndev = sum(SWEEP_COUNTS.values())
+        # algorithmic bytes of one Newton step of one point: the four load kernels' tables, states and stamps
+        # (DESIGN.md section 7: BSIM4 2 000 B, BSIM3 1 400 B, VBIC 3 400 B, diode 700 B per evaluation)
+        bytes_step = SWEEP_COUNTS["bsim4"] * 2000 + SWEEP_COUNTS["bsim3"] * 1400 + SWEEP_COUNTS["vbic"] * 3400 + SWEEP_COUNTS["diode"] * 700
+        achieved = iters_tot * bytes_step / (ms_max * 1e-3) / 1e9
+        cpu = sweep_cpu_baseline(os.cpu_count() or 1)
+        line = {
+            "metric": "sweep points/s", "value": points_tot / (ms_max * 1e-3), "unit": "points/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": sweep_config(args),
+            "device_evals_per_s": ndev * iters_tot / (ms_max * 1e-3), "newton_iterations_per_point": iters_tot / points_tot,
+            "newton_steps_per_sweep": ticks / args.steps, "points_not_completed": int(bad_tot),
+            "e2e": {"value": points_tot / (ms_e2e_max * 1e-3), "unit": "points/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if hbm_peak else None,
+                         "traffic": None, "kernel": "whole Newton step (all load kernels + assembly + LU), algorithmic device-load bytes only",
+                         "bytes_per_unit": bytes_step, "peak_source": which},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {"value": cpu[0], "unit": "points/s", "cores": os.cpu_count() or 1, "kind": "reference", "sample": cpu[3]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def sweep_config(args):
+    return {"workload": "mixed-model sweep cell (16 BSIM4 + 8 BSIM3 + 2 VBIC + 3 diodes + R/C, 104 unknowns), 256 x 256 grid of "
+                        "(vdd 1.6-2.4 V, r1 200-5000 ohm), DC operating point + .tran 25p 5n per point (config 5)",
+            "points_per_gpu": args.samples, "l2": "per-step working set larger than L2 at 8 192 points"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mc_ro17", choices=["mc_ro17", "ro101", "array"])
+    ap.add_argument("--workload", default="mc_ro17", choices=["mc_ro17", "ro101", "array", "sweep"])
     ap.add_argument("--cells", type=int, default=500000, help="inverters of the array workload (2 transistors each)")
-    ap.add_argument("--samples", type=int, default=4096, help="Monte-Carlo samples per GPU")
+    ap.add_argument("--samples", type=int, default=None, help="Monte-Carlo samples (default 4096) or sweep points (default 8192) per GPU")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.samples is None:
+        args.samples = 8192 if args.workload == "sweep" else 4096
+    if args.workload == "sweep":
+        bench_sweep(args)
+    elif args.impl == "reference":
         bench_reference(args)
     elif args.workload == "array":
         bench_array(args)

@@ -146,6 +146,9 @@ long ngbBatchArrayBytes(ngb_batch *b, const char *name);
 int ngbBatchUpload(ngb_batch *b, const char *name, const void *host, long bytes, long offset);
 int ngbBatchDownload(ngb_batch *b, const char *name, void *host, long bytes, long offset);
 void *ngbBatchDevPtr(ngb_batch *b, const char *name);
+/* per-sample resistor values for parameter sweeps: g [nres][S] = RESconduct as REStemp computes it
+ * (res/restemp.c), replaces `alter r = value` between runs */
+int ngbBatchSetResistors(ngb_batch *b, const double *g);
 int ngbBatchSetOpFull(ngb_batch *b, int on);   /* export every B4O_* field (parity runs) */
 
 /* hot path, one call = one step of NIiter for every active sample */

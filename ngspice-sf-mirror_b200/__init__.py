@@ -11,6 +11,7 @@ import numpy as np
 from . import ngt  # noqa: F401
 from . import mc  # noqa: F401
 from . import parallel  # noqa: F401
+from . import sweep  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NGB200_LIB", os.path.join(_HERE, "libngb200.so"))
@@ -268,6 +269,12 @@ class Batch:
         self.lib.check(self.lib.L.ngbBatchDownload(self.h, name.encode(), a.ctypes.data_as(ctypes.c_void_p),
                                                    ctypes.c_long(a.nbytes), ctypes.c_long(0)), f"download {name}")
         return a.reshape(shape) if shape is not None else a
+
+    def set_resistors(self, g):
+        """per-sample conductances g [nres][S] (parameter sweeps)"""
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        assert g.shape[1] == self.S
+        self.lib.check(self.lib.L.ngbBatchSetResistors(self.h, _dp(g)), "ngbBatchSetResistors")
 
     def set_op_full(self, on=True):
         self.lib.L.ngbBatchSetOpFull(self.h, 1 if on else 0)

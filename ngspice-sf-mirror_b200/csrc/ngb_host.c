@@ -692,8 +692,11 @@ int ngbCircuitFinalize(ngb_circuit *c)
     for (i = 0; i < c->res_n; i++) {
         int p = c->res_nodes[i], q = c->res_nodes[c->res_n + i];
         double g = c->res_g[i];
-        CONST_ROW(slot_lookup(c, p, p), g); CONST_ROW(slot_lookup(c, q, q), g);
-        CONST_ROW(slot_lookup(c, p, q), -g); CONST_ROW(slot_lookup(c, q, p), -g);
+        const int tg[4] = { slot_lookup(c, p, p), slot_lookup(c, q, q), slot_lookup(c, p, q), slot_lookup(c, q, p) };
+        for (k = 0; k < 4; k++) {
+            c->res_spos[k * c->res_n + i] = (tg[k] >= 0) ? c->nstamp_rows : -1;      /* the row CONST_ROW is about to create */
+            CONST_ROW(tg[k], k < 2 ? g : -g);
+        }
     }
     c->vb_spos = (int *)xcalloc((size_t)c->vb_n * VBIC_NSTAMPS + 1, sizeof(int));
     for (i = 0; i < c->vb_n; i++)
@@ -1377,6 +1380,24 @@ int ngbBatchDownload(ngb_batch *b, const char *name, void *host, long bytes, lon
     return ngb_dev_d2h(host, (char *)b->arr[i].ptr + offset, (size_t)bytes);
 }
 int ngbBatchSetOpFull(ngb_batch *b, int on) { b->op_full = on; return NGB_OK; }
+
+/* per-sample resistor conductances (parameter sweeps): g [nres][S], what REStemp leaves in RESconduct */
+int ngbBatchSetResistors(ngb_batch *b, const double *g)
+{
+    const ngb_circuit *c = b->c;
+    const int S = b->S;
+    double *neg = (double *)xcalloc((size_t)S, sizeof(double));
+    int i, k, s, rc = NGB_OK;
+    for (i = 0; i < c->res_n && !rc; i++) {
+        for (s = 0; s < S; s++) neg[s] = -g[(size_t)i * S + s];
+        for (k = 0; k < 4 && !rc; k++) {
+            const int r = c->res_spos[k * c->res_n + i];
+            if (r >= 0) rc = ngb_dev_h2d(b->stamp + (size_t)r * S, k < 2 ? g + (size_t)i * S : neg, sizeof(double) * (size_t)S);
+        }
+    }
+    free(neg);
+    return rc;
+}
 
 /* per-thread parameter rows (Monte-Carlo with model-parameter mismatch): prow [ninst*S] */
 int ngbBatchSetBsim4Rows(ngb_batch *b, const int *prow_t, int nrows, const double *mtab, const double *ptab)

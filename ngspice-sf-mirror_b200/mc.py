@@ -60,21 +60,31 @@ def bsim4_with_tox_levels(lib, flat, tables, level, delvto):
 
 
 def spice_number(text):
-    """the value the reference front end gives a plain decimal token (digits, '.', e+-NN), which
+    """the value the reference front end gives a numeric token (digits, '.', e+-NN, scale suffix), which
     is not always the nearest double: INPevaluate accumulates the digits into a double mantissa
-    and multiplies by pow(10, exponent) (src/spicelib/parser/inpeval.c:65-201)"""
+    and multiplies by pow(10, exponent) (src/spicelib/parser/inpeval.c:65-201); an integer token
+    without suffix is returned as the mantissa itself (:73-81)"""
     import math
+    import re
     t = text.strip().lower()
-    sign = 1.0
-    if t[0] in "+-":
-        sign = -1.0 if t[0] == "-" else 1.0
-        t = t[1:]
-    mant, _, ex = t.partition("e")
-    ip, _, fp = mant.partition(".")
+    m_ = re.fullmatch(r"([+-]?)(\d*)(?:\.(\d*))?(?:[ed]([+-]?\d+))?([a-z]*)", t)
+    if not m_ or not (m_.group(2) or m_.group(3)):
+        raise ValueError(f"not a SPICE number: {text!r}")
+    sign = -1.0 if m_.group(1) == "-" else 1.0
+    ip, fp, ex, suf = m_.group(2), m_.group(3) or "", m_.group(4), m_.group(5)
     m = 0.0
     for ch in ip + fp:
         m = 10.0 * m + (ord(ch) - 48)
+    if m_.group(3) is None and ex is None and not suf:
+        return m * sign
     e = -len(fp) + (int(ex) if ex else 0)
+    if suf.startswith("meg"):
+        e += 6
+    elif suf.startswith("mil"):
+        e -= 6
+        m *= 25.4
+    elif suf:
+        e += {"t": 12, "g": 9, "k": 3, "m": -3, "u": -6, "n": -9, "p": -12, "f": -15, "a": -18}.get(suf[0], 0)
     return sign * m * math.pow(10.0, float(e))
 
 

@@ -196,6 +196,7 @@ static void dump_bsim4(FILE *f, CKTcircuit *ckt, KLUmatrix *K)
     free(inst); free(mtab); free(ptab); free(names);
 }
 
+static void put_names(FILE *f, const char *key, GENmodel *head);
 static void dump_linear(FILE *f, CKTcircuit *ckt, KLUmatrix *K)
 {
     int n, i;
@@ -221,6 +222,7 @@ static void dump_linear(FILE *f, CKTcircuit *ckt, KLUmatrix *K)
         }
     }
     put_is(f, "res/n", n);
+    if (n) put_names(f, "res/names_bytes", ckt->CKThead[res_type]);
     /* capacitors */
     n = 0;
     if (cap_type >= 0) {
@@ -274,6 +276,7 @@ static void dump_linear(FILE *f, CKTcircuit *ckt, KLUmatrix *K)
         }
     }
     put_is(f, "vsrc/n", n);
+    if (n) put_names(f, "vsrc/names_bytes", ckt->CKThead[vsrc_type]);
     /* current sources */
     n = 0;
     if (isrc_type >= 0) {
@@ -418,6 +421,20 @@ static void dump_dio(FILE *f, CKTcircuit *ckt, KLUmatrix *K)
         }
     }
     put_is(f, "dio/n", n);
+}
+
+static void put_names(FILE *f, const char *key, GENmodel *head)
+{
+    GENmodel *m; GENinstance *h; size_t nb = 0, cap = 64; int *out = (int *)calloc(cap, sizeof(int));
+    for (m = head; m; m = m->GENnextModel)
+        for (h = m->GENinstances; h; h = h->GENnextInstance) {
+            const char *s = h->GENname; size_t L = strlen(s), q;
+            if (nb + L + 2 > cap) { cap = 2 * (nb + L + 2); out = (int *)realloc(out, cap * sizeof(int)); }
+            for (q = 0; q < L; q++) out[nb++] = (unsigned char)s[q];
+            out[nb++] = '\n';
+        }
+    put_i1(f, key, out, (long long)nb);
+    free(out);
 }
 
 /* VBIC: the parameter vector as VBICload assembles it (vbicload.c:127-166), node numbers, flags */

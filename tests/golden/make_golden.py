@@ -150,6 +150,44 @@ def vbic_netlist():
         ".end", ""])
 
 
+def mix_netlist(vdd="2.0", r="1k"):
+    """BASELINE config 5: one cell with every model family of the path -- an 8-stage BSIM4 inverter chain on
+    the swept supply, an RC interconnect with the swept resistor and clamp diodes, a 4-stage BSIM3 level
+    shifter and a two-transistor VBIC output stage on 3.3 V; DC operating point + 200-step transient.
+    The two swept values are passed as netlist text, exactly what `alter vdd` / `alter r1` would set."""
+    lines = ["* mixed-model sweep cell: BSIM4 + BSIM3 + VBIC + diode + R/C",
+             f"vdd dd 0 dc {vdd}", "v33 d3 0 dc 3.3",
+             "vin in 0 dc 0 pulse(0 2.0 0.2n 0.1n 0.1n 1.2n 3n)"]
+    prev = "in"
+    for k in range(1, 9):
+        lines.append(f"mp{k} a{k} {prev} dd dd p1 l=0.1u w=10u ad=5p pd=6u as=5p ps=6u")
+        lines.append(f"mn{k} a{k} {prev} 0 0 n1 l=0.1u w=5u ad=5p pd=6u as=5p ps=6u")
+        prev = f"a{k}"
+    lines += [f"r1 a8 x {r}", "c1 x 0 30f", "d1 x d3 dcl", "d2 0 x dcl"]
+    prev = "x"
+    for k in range(1, 5):
+        lines.append(f"mnl{k} y{k} {prev} 0 0 nb3 w=2u l=0.35u as=3p ad=3p ps=4u pd=4u")
+        lines.append(f"mpl{k} y{k} {prev} d3 d3 pb3 w=4u l=0.35u as=7p ad=7p ps=6u pd=6u")
+        prev = f"y{k}"
+    lines += ["c2 y4 0 50f",
+              "rb1 y4 b1 20k", "q1 cq b1 0 0 nv", "rc1 d3 cq 2k", "q2 d3 cq e2 0 nv area=2", "re2 e2 0 3k", "c3 e2 0 0.1p",
+              "r5 d3 m 10k", "d3 m 0 dref", "r6 m b1 200k",
+              ".model dcl d is=1e-14 rs=20 n=1.05 cjo=5f vj=0.7 m=0.4 tt=50p bv=12",
+              ".model dref d is=5e-15 rs=5 cjo=10f tt=0.1n",
+              ".model nv npn level=4",
+              "+ is=1e-16 ibei=1e-18 iben=5e-15 ibci=2e-17 ibcn=5e-15 isp=1e-15 rcx=10",
+              "+ rci=60 rbx=10 rbi=40 re=2 rs=20 rbp=40 vef=10 ver=4 ikf=2e-3 itf=8e-2",
+              "+ xtf=20 ikr=2e-4 ikp=2e-4 cje=1e-13 cjc=2e-14 cjep=1e-13 cjcp=4e-13 vo=2",
+              "+ gamm=2e-11 hrcf=2 qco=1e-12 avc1=2 avc2=15 tf=10e-12 tr=100e-12",
+              ".option klu", ".tran 25p 5n"]
+    b3 = b3_cards().replace(".model n1 nmos", ".model nb3 nmos").replace(".model p1 pmos", ".model pb3 pmos")
+    return "\n".join(lines) + "\n" + b3 + "\n" + ro_cards() + "\n.end\n"
+
+
+# sweep points recorded for parity (value text exactly as it appears in the netlist): centre + 4 corners
+MIX_POINTS = [("2.0", "1k"), ("1.6", "200"), ("1.6", "5k"), ("2.4", "200"), ("2.4", "5k")]
+
+
 def b3_cards():
     """the level-8 (BSIM3v3.3.0) n1/p1 cards of examples/Monte_Carlo/MC_ring.sp"""
     src = open(os.path.join(REF, "examples/Monte_Carlo/MC_ring.sp")).read()
@@ -215,7 +253,7 @@ def run(name, netlist, calls, save):
     os.makedirs(TMP, exist_ok=True)
     cir = os.path.join(TMP, name + ".cir")
     open(cir, "w").write(netlist)
-    if name in ("ro17", "ro101", "ro17k", "inv", "dio", "b3ring", "arr", "vbic"):
+    if name in ("ro17", "ro101", "ro17k", "inv", "dio", "b3ring", "arr", "vbic", "mix"):
         # the netlist itself is kept too: the CPU-baseline arm of bench.py feeds it to oracle/_ref/ngspice
         os.makedirs(os.path.join(HERE, "netlists"), exist_ok=True)
         open(os.path.join(HERE, "netlists", name + ".cir"), "w").write(netlist)
@@ -274,6 +312,13 @@ if __name__ == "__main__":
         run("dio", dio_netlist(), "0-30,200,201,1000,1001,2000", ["out", "z", "w", "u", "vin#branch"])
     if "vbic" in which:
         run("vbic", vbic_netlist(), "0-40,100,101,300,301,800", ["c", "e2", "o1", "o2", "b", "vcc#branch"])
+    if "mix" in which:
+        save = ["a8", "x", "y4", "cq", "e2", "vdd#branch", "v33#branch"]
+        run("mix", mix_netlist(*MIX_POINTS[0]), "0-40,100,101,300", save)
+        for k, (vdd, r) in enumerate(MIX_POINTS[1:], 1):       # corners: waveforms only
+            run(f"mix{k}", mix_netlist(vdd, r), "0", save)
+            for ext in (".flat.ngt", ".trace.ngt.gz"):
+                os.remove(os.path.join(HERE, f"mix{k}" + ext))
     if "b3ring" in which:
         run("b3ring", b3_netlist(5), "0-40,300,301,1000,1001", ["out", "buf", "n2", "vdd#branch"])
     if "arr" in which:

@@ -58,8 +58,9 @@ def _vbic_close(v0, v1):
     return float(np.max(np.max(np.abs(a - b), axis=0) / np.maximum(np.max(np.abs(a), axis=0), 1e-300)))
 
 
-def test_dropin_hostsim_vbic_rawfile():
-    v0, v1 = _check(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb_hostsim"), "vbic", "hostsim")
+@pytest.mark.parametrize("name", ["vbic", "mix"])
+def test_dropin_hostsim_vbic_rawfile(name):
+    v0, v1 = _check(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb_hostsim"), name, "hostsim")
     assert _vbic_close(v0, v1) <= 1e-9
 
 
@@ -70,8 +71,9 @@ def test_dropin_hostsim_load_only_identical():
 
 
 @pytest.mark.gpu
-def test_dropin_gpu_vbic_rawfile():
-    v0, v1 = _check(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb"), "vbic", "cuda-sm_100a")
+@pytest.mark.parametrize("name", ["vbic", "mix"])
+def test_dropin_gpu_vbic_rawfile(name):
+    v0, v1 = _check(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb"), name, "cuda-sm_100a")
     assert _vbic_close(v0, v1) <= 1e-9
 
 

@@ -53,6 +53,42 @@ def test_tran_hostsim_vbic(hostsim_lib):
     _compare(res, t, v, wave, 0, exact=False)
 
 
+MIX_POINTS = [("2.0", "1k"), ("1.6", "200"), ("1.6", "5k"), ("2.4", "200"), ("2.4", "5k")]     # make_golden.py
+
+
+def _mix_sweep(lib, reps=1):
+    """BASELINE config 5: the mixed BSIM4 + BSIM3 + VBIC + diode + R/C cell, every sample with its own supply
+    voltage and interconnect resistor (centre + four corners of the sweep grid), in ONE batch"""
+    flat = ngt.read(f"{GOLDEN}/mix.flat.ngt")
+    trace = ngt.read(f"{GOLDEN}/mix.trace.ngt.gz")
+    wave = ngt.read(f"{GOLDEN}/mix.wave.ngt")
+    circ = pkg.Circuit.from_flat(lib, flat, lu_pattern=run_patterns(trace))
+    pts = MIX_POINTS * reps
+    b = pkg.Batch(circ, len(pts))
+    pkg.sweep.apply(b, flat, dc={"vdd": [p[0] for p in pts]}, res={"r1": [p[1] for p in pts]})
+    res = b.tran(8192, wave["save_eq"])
+    t, v = res.waves()
+    for s in range(len(pts)):
+        k = s % len(MIX_POINTS)
+        _compare(res, t, v, ngt.read(f"{GOLDEN}/mix{k if k else ''}.wave.ngt"), s, exact=False)
+
+
+def test_tran_hostsim_mix_cell(hostsim_lib):
+    """all model families of the path in one circuit (1e-9, identical step / iteration counts; not
+    bit-identical because of the VBIC Jacobian, see test_tran_hostsim_vbic)"""
+    res, t, v, wave = _run(hostsim_lib, "mix")
+    _compare(res, t, v, wave, 0, exact=False)
+
+
+def test_tran_hostsim_mix_sweep(hostsim_lib):
+    _mix_sweep(hostsim_lib)
+
+
+@pytest.mark.gpu
+def test_tran_gpu_mix_sweep(cuda_lib):
+    _mix_sweep(cuda_lib, reps=13)       # 65 samples: more than two warps, every point on its own time axis
+
+
 def _mc_inst(lib):
     base = ngt.read(f"{GOLDEN}/ro17k.flat.ngt")
     dv_netlist = np.load(f"{GOLDEN}/ro17mc.delvto.npy")       # columns: mp1 mn1 mp2 mn2 ... (netlist order)
