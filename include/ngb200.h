@@ -117,6 +117,13 @@ int ngbCircuitSetLuPattern(ngb_circuit *c, int n, int nblocks, const int *Q, con
  * (default) holds the first result, set 1 the second; ngbCircuitSelectLuSet chooses which one the
  * next ngbCircuitSetLuPattern / ngbCircuitLuInfo refers to.  With only set 0 present it serves both */
 int ngbCircuitSelectLuSet(ngb_circuit *c, int which);
+/* NIiter re-pivots (SMPreorder) at up to four moments of a run: [0] the MODEINITJCT iteration, [1] the
+ * iteration after it (NISHOULDREORDER, niiter.c:335) whose order serves the rest of the operating point,
+ * [2] the first iteration under MODEINITTRAN (niiter.c:107-111), [3] the iteration after it (:343-344),
+ * whose order serves the rest of the transient.  set_of_event[4] names the pattern set (0..3, filled
+ * through ngbCircuitSelectLuSet + ngbCircuitSetLuPattern) each of these factors produced; a UIC run
+ * starts at [2].  Default without this call: set 0 for [0],[1]; set 1 (if filled, else 0) for [2],[3] */
+int ngbCircuitSetLuEvents(ngb_circuit *c, const int *set_of_event);
 /* own BTF + fill-reducing ordering + pivoting factor on one sample's matrix values
  * (host; the role klu_analyze/klu_factor play) */
 int ngbCircuitAnalyze(ngb_circuit *c, const double *Ax);

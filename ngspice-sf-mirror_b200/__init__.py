@@ -134,6 +134,7 @@ class Circuit:
         sc = ngt.scalar
         c = cls(lib, sc(flat, "meta/neq"), flat["node/type"])
         c.flat = flat
+        c.uic = int(sc(flat, "tran/uic", 0))
         d = np.array([sc(flat, "opt/reltol"), sc(flat, "opt/abstol"), sc(flat, "opt/vntol"),
                       sc(flat, "opt/chgtol"), sc(flat, "opt/trtol"), sc(flat, "opt/temp"), sc(flat, "opt/vt0"),
                       sc(flat, "opt/xmu"), sc(flat, "tran/tstep", 0.0), sc(flat, "tran/tstop", 0.0),
@@ -205,13 +206,35 @@ class Circuit:
         self.lib.check(self.lib.L.ngbCircuitGetBsim4Slots(self.h, _ip(s)))
         return s
 
-    def set_lu_pattern(self, pat, prefix="", which=0):
-        """pat: dict with n nblocks Q R Pnum Lp Li Up Ui Offp Offi (KLU symbolic + numeric pattern);
-        a list/tuple gives the pattern of the first pivoting factor and of the re-pivoting in the
-        first transient iteration (sets 0 and 1)."""
+    def set_lu_pattern(self, pat, prefix="", which=0, uic=None):
+        """pat: dict with n nblocks Q R Pnum Lp Li Up Ui Offp Offi (KLU symbolic + numeric pattern).
+        A list/tuple gives the pivoting factors of a run in the order the reference computed them
+        (NIiter re-pivots in the INITJCT iteration, in the one after it, and in the first two
+        iterations of the first time point; a UIC run has only the last two): identical factors share
+        a pattern set, and every pivoting event is mapped onto its set (ngbCircuitSetLuEvents)."""
         if isinstance(pat, (list, tuple)):
-            for w, p1 in enumerate(pat[:2]):
+            if uic is None:
+                uic = bool(getattr(self, "uic", 0))
+            pats = list(pat)
+            keys = ("Pnum", "Q", "Lp", "Li", "Up", "Ui", "Offp", "Offi")
+            sets, set_of = [], []
+            for p1 in pats:
+                for k, q in enumerate(sets):
+                    if all(np.array_equal(np.asarray(q[prefix + kk]), np.asarray(p1[prefix + kk])) for kk in keys):
+                        set_of.append(k)
+                        break
+                else:
+                    sets.append(p1)
+                    set_of.append(len(sets) - 1)
+            assert len(sets) <= 4
+            for w, p1 in enumerate(sets):
                 self.set_lu_pattern(p1, prefix, which=w)
+            # events 0..3; a run with fewer factors than events keeps the last one (e.g. recorded runs of one factor)
+            if uic:
+                ev = [set_of[0], set_of[0]] + [set_of[min(k, len(set_of) - 1)] for k in (0, 1)]
+            else:
+                ev = [set_of[min(k, len(set_of) - 1)] for k in range(4)]
+            self.lib.check(self.lib.L.ngbCircuitSetLuEvents(self.h, _ip(np.array(ev, np.int32))), "ngbCircuitSetLuEvents")
             self.lib.check(self.lib.L.ngbCircuitSelectLuSet(self.h, 0))
             return
         self.lib.check(self.lib.L.ngbCircuitSelectLuSet(self.h, int(which)))

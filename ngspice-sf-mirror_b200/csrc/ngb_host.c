@@ -196,7 +196,7 @@ void ngbCircuitDestroy(ngb_circuit *c)
     free(c->klu_Q); free(c->klu_R); free(c->klu_Pnum);
     free_sched(&c->sch);
     free_packed(&c->pk);
-    { int w; for (w = 0; w < 2; w++) if (c->lu[w].valid) { free_sched(&c->lu[w].sch); free_packed(&c->lu[w].pk); } }
+    { int w; for (w = 0; w < NGB_LU_SETS; w++) if (c->lu[w].valid) { free_sched(&c->lu[w].sch); free_packed(&c->lu[w].pk); } }
     free(c);
 }
 
@@ -1071,9 +1071,29 @@ bad:
 
 int ngbCircuitSelectLuSet(ngb_circuit *c, int which)
 {
-    if (which < 0 || which > 1) return NGB_E_PANIC;
+    if (which < 0 || which >= NGB_LU_SETS) return NGB_E_PANIC;
     c->lu_target = which;
     return NGB_OK;
+}
+int ngbCircuitSetLuEvents(ngb_circuit *c, const int *set_of_event)
+{
+    int e;
+    for (e = 0; e < NGB_LU_EVENTS; e++) {
+        if (set_of_event[e] < 0 || set_of_event[e] >= NGB_LU_SETS || !c->lu[set_of_event[e]].valid) {
+            ngb_set_error("pivoting event %d refers to pattern set %d, which is not filled", e, set_of_event[e]);
+            return NGB_E_PANIC;
+        }
+        c->lu_event[e] = set_of_event[e];
+    }
+    c->lu_event_set = 1;
+    return NGB_OK;
+}
+/* without ngbCircuitSetLuEvents: set 0 serves the operating point, set 1 (when filled) the transient */
+void ngb_lu_events(const ngb_circuit *c, int ev[NGB_LU_EVENTS])
+{
+    int e;
+    for (e = 0; e < NGB_LU_EVENTS; e++)
+        ev[e] = c->lu_event_set ? c->lu_event[e] : ((e >= 2 && c->lu[1].valid) ? 1 : (c->lu[0].valid ? 0 : 1));
 }
 int ngbCircuitLuInfo(const ngb_circuit *c, int info[9])
 {
@@ -1276,7 +1296,7 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
     }
     if (c->have_lu) {
         int w, nVmax = 0;
-        for (w = 0; w < 2; w++)
+        for (w = 0; w < NGB_LU_SETS; w++)
             if (c->lu[w].valid) {
                 sched_to_dev(b, c, w); packed_to_dev(b, c, w); b->dlu[w].valid = 1;
                 if (c->lu[w].sch.nV > nVmax) nVmax = c->lu[w].sch.nV;
@@ -1296,7 +1316,7 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
 static void batch_free_lu(ngb_batch *b)
 {
     int w;
-    for (w = 0; w < 2; w++)
+    for (w = 0; w < NGB_LU_SETS; w++)
         if (b->dlu[w].valid) {
             if (b->dlu[w].dpk.ok) { ngb_dev_free((void *)b->dlu[w].dpk.blob); ngb_dev_free((void *)b->dlu[w].dpk.aslot);
                                     ngb_dev_free((void *)b->dlu[w].dpk.arow); ngb_dev_free((void *)b->dlu[w].dpk.ext); }
@@ -1315,7 +1335,7 @@ int ngbBatchRefreshLu(ngb_batch *b)
     if (!c->have_lu) { ngb_set_error("no LU pattern on the circuit"); return NGB_E_PANIC; }
     ngb_dev_sync();
     batch_free_lu(b);
-    for (w = 0; w < 2; w++)
+    for (w = 0; w < NGB_LU_SETS; w++)
         if (c->lu[w].valid) {
             sched_to_dev(b, c, w); packed_to_dev(b, c, w); b->dlu[w].valid = 1;
             if (c->lu[w].sch.nV > nVmax) nVmax = c->lu[w].sch.nV;

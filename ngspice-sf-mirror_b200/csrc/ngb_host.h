@@ -37,10 +37,11 @@ struct ngb_circuit {
     int lnz, unz, nzoff, npairs, nsolvepairs;
     NgbLuSched sch;                /* host arrays (set being built) */
     NgbLuPacked pk;                /* host arrays, level-contiguous 16-bit form */
-    /* finished pattern sets: [0] from the first pivoting factor, [1] (optional) from the re-pivoting of
-     * the first transient iteration; lu_target selects which one ngbCircuitSetLuPattern fills */
-    struct ngb_luset { NgbLuSched sch; NgbLuPacked pk; int npairs, nsolvepairs, lnz, unz, nzoff, valid; } lu[2];
+    /* finished pattern sets, one per distinct pivoting factor of a run (NIiter re-pivots in the INITJCT
+     * iteration, in the iteration after it, and in the first two iterations of the first time point); lu_target selects which one ngbCircuitSetLuPattern fills */
+    struct ngb_luset { NgbLuSched sch; NgbLuPacked pk; int npairs, nsolvepairs, lnz, unz, nzoff, valid; } lu[NGB_LU_SETS];
     int lu_target;
+    int lu_event[NGB_LU_EVENTS], lu_event_set;   /* pivoting event -> pattern set (ngbCircuitSetLuEvents) */
 };
 
 #define NGB_MAX_ARR 64
@@ -59,7 +60,7 @@ struct ngb_batch {
     double *dio_par, *dio_state; int *dio_nodes, *dio_flags, *dio_spos;
     double *vs_par; int *vs_fn, *vs_spos;
     double *is_par; int *is_fn, *is_spos;
-    struct { NgbLuSched dsch; NgbLuPacked dpk; int valid; } dlu[2];   /* device arrays per pattern set */
+    struct { NgbLuSched dsch; NgbLuPacked dpk; int valid; } dlu[NGB_LU_SETS];   /* device arrays per pattern set */
     int lu_which;                  /* set used by the direct ngbLuFac/ngbSolve calls */
     double *V, *Rs; int *nodeconv, *singular;
     struct { const char *name; void *ptr; size_t bytes; } arr[NGB_MAX_ARR];
@@ -73,6 +74,7 @@ void ngb_fill_capctx(struct ngb_batch *b, NgbCapCtx *x);
 void ngb_fill_dioctx(struct ngb_batch *b, NgbDioCtx *x);
 void ngb_fill_b3ctx(struct ngb_batch *b, B3Ctx *x);
 void ngb_fill_vbctx(struct ngb_batch *b, NgbVbicCtx *x);
+void ngb_lu_events(const struct ngb_circuit *c, int ev[NGB_LU_EVENTS]);
 void ngb_fill_srcctx(struct ngb_batch *b, NgbSrcCtx *x, int is_current);
 void ngb_fill_asmctx(struct ngb_batch *b, NgbAsmCtx *x);
 void ngb_fill_luctx(struct ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve, int which);

@@ -18,10 +18,11 @@ struct ngb_tran {
     int max_points, nsave;
     int *d_save_eq;
     long ticks;
-    int dc_over;               /* every sample has left the DC operating point (pattern set 0 idle) */
-    /* CUDA graph of one Newton step, one per launch sequence: [0] while pattern set 0 is still in use,
-     * [1] afterwards; graph_state 0 = not tried, 1 = ready, -1 = unavailable */
-    void *graph[2]; int graph_nodes[2], graph_state[2];
+    int stage;                 /* 0: some sample is still in the operating point; 1: all in the transient;
+                                * 2: all past the last pivoting event (only the final pattern set is in use) */
+    /* CUDA graph of one Newton step, one per launch sequence (= per stage);
+     * graph_state 0 = not tried, 1 = ready, -1 = unavailable */
+    void *graph[3]; int graph_nodes[3], graph_state[3];
 };
 
 static void *dz(size_t bytes) { return ngb_dev_malloc(bytes ? bytes : 8); }
@@ -33,9 +34,9 @@ void ngb_tran_free(struct ngb_batch *b)
     ngb_dev_free(t->x.phase); ngb_dev_free(t->x.iterno); ngb_dev_free(t->x.firsttime); ngb_dev_free(t->x.nbreak);
     ngb_dev_free(t->x.npts); ngb_dev_free(t->x.brkflag); ngb_dev_free(t->x.accepted); ngb_dev_free(t->x.rejected);
     ngb_dev_free(t->x.numiter); ngb_dev_free(t->x.timepts); ngb_dev_free(t->x.save_delta); ngb_dev_free(t->x.old_delta);
-    ngb_dev_free(t->x.breaks); ngb_dev_free(t->x.out_time); ngb_dev_free(t->x.out_val); ngb_dev_free(t->x.ndone);
+    ngb_dev_free(t->x.breaks); ngb_dev_free(t->x.out_time); ngb_dev_free(t->x.out_val); ngb_dev_free(t->x.ndone); ngb_dev_free(t->x.evstage);
     ngb_dev_free(t->d_save_eq); ngb_dev_free(t->x.isrc_break); ngb_dev_free(t->x.vsrc_break);
-    ngb_dev_graph_destroy(t->graph[0]); ngb_dev_graph_destroy(t->graph[1]);
+    ngb_dev_graph_destroy(t->graph[0]); ngb_dev_graph_destroy(t->graph[1]); ngb_dev_graph_destroy(t->graph[2]);
     free(t);
     b->tran = NULL;
 }
@@ -62,7 +63,7 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     x->breaks = (double *)dz(sizeof(double) * NGB_MAXBRK * S);
     x->out_time = (double *)dz(sizeof(double) * (size_t)S * max_points);
     x->out_val = (double *)dz(sizeof(double) * (size_t)S * max_points * (nsave ? nsave : 1));
-    x->ndone = (int *)dz(sizeof(int) * 2);
+    x->ndone = (int *)dz(sizeof(int) * 4); x->evstage = (int *)dz(sizeof(int) * S);
     ngb_fill_srcctx(b, &x->isrc, 1); ngb_fill_srcctx(b, &x->vsrc, 0);
     x->isrc_break = (double *)dz(sizeof(double) * (size_t)(x->isrc.ninst > 0 ? x->isrc.ninst : 1) * S);
     x->vsrc_break = (double *)dz(sizeof(double) * (size_t)(x->vsrc.ninst > 0 ? x->vsrc.ninst : 1) * S);
@@ -75,7 +76,8 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     t->max_points = max_points; t->nsave = nsave;
     x->tstep = c->opt.tstep; x->tstop = c->opt.tstop; x->tmax = c->opt.tmax; x->tstart = c->opt.tstart;
     x->delmin = c->opt.delmin; x->minbreak = c->opt.minbreak; x->xmu = c->opt.xmu;
-    x->nluset = b->dlu[1].valid ? 2 : 1;
+    ngb_lu_events(c, x->lu_event);
+    x->nluset = (x->lu_event[0] != x->lu_event[1] || x->lu_event[1] != x->lu_event[2] || x->lu_event[2] != x->lu_event[3]) ? 2 : 1;
     x->maxorder = c->opt.maxorder; x->uic = c->opt.uic; x->max_iter_tran = c->opt.itl4; x->max_iter_dc = c->opt.itl1;
     if (x->minbreak == 0) x->minbreak = x->tmax * 5e-5;            /* dctran.c:163-164 */
 
@@ -97,12 +99,13 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
         /* NIiter under MODETRANOP|MODEUIC swaps rhs/rhsOld before its single CKTload */
         for (s = 0; s < S; s++) iv[s] = c->opt.uic ? 1 : 0;
         ngb_dev_h2d(b->ctl.xsel, iv, sizeof(int) * S);
+        for (s = 0; s < S; s++) iv[s] = x->lu_event[c->opt.uic ? 2 : 0];
+        ngb_dev_h2d(b->ctl.lusel, iv, sizeof(int) * S);
         memset(iv, 0, sizeof(int) * S);
         ngb_dev_h2d(b->ctl.head, iv, sizeof(int) * S);
         ngb_dev_h2d(b->ctl.noncon, iv, sizeof(int) * S);
         ngb_dev_h2d(b->ctl.err, iv, sizeof(int) * S);
         ngb_dev_h2d(b->ctl.stateop, iv, sizeof(int) * S);
-        ngb_dev_h2d(b->ctl.lusel, iv, sizeof(int) * S);
         ngb_dev_h2d(b->nodeconv, iv, sizeof(int) * S);
         for (i = 0; i < NGB_MAXBRK; i++) for (s = 0; s < S; s++) dv[(size_t)i * S + s] = (i == 0) ? 0.0 : c->opt.tstop;
         ngb_dev_h2d(x->breaks, dv, sizeof(double) * NGB_MAXBRK * S);
@@ -132,13 +135,17 @@ static int enqueue_tick_direct(ngb_batch *b, int with_lu)
     int r;
     if ((r = ngb_enqueue_load(b))) return r;
     if (with_lu) {
-        int w;
-        for (w = 0; w < 2; w++) {
+        const int *ev = b->tran->x.lu_event;
+        const int first = b->tran->stage == 0 ? 0 : (b->tran->stage == 1 ? 2 : 3);      /* events still ahead of some sample */
+        int w, e;
+        for (w = 0; w < NGB_LU_SETS; w++) {
             NgbLuCtx lx;
+            int used = 0;
             if (!b->dlu[w].valid) continue;
-            if (w == 0 && b->dlu[1].valid && b->tran->dc_over) continue;   /* every sample has re-pivoted: set 0 is idle */
+            for (e = first; e < NGB_LU_EVENTS; e++) if (ev[e] == w) used = 1;
+            if (!used) continue;                                            /* no sample can be on this set any more */
             ngb_fill_luctx(b, &lx, 1, 1, w);
-            if (!b->dlu[1].valid) lx.ctl.lusel = NULL;                     /* one set: no per-sample selection */
+            if (b->tran->x.nluset == 1) lx.ctl.lusel = NULL;               /* one set: no per-sample selection */
             lx.V = NULL;                       /* fused factor+solve: the factors never leave shared memory */
             if ((r = ngb_launch_lu(&lx))) return r;
         }
@@ -153,7 +160,7 @@ static int enqueue_tick_direct(ngb_batch *b, int with_lu)
 static int enqueue_tick(ngb_batch *b, int with_lu)
 {
     struct ngb_tran *t = b->tran;
-    const int g = t->dc_over ? 1 : 0;
+    const int g = t->stage;
     int r;
     if (!with_lu || ngb_dev_profile_due()) return enqueue_tick_direct(b, with_lu);
     if (t->graph_state[g] == 0) {
@@ -172,7 +179,7 @@ static int enqueue_tick(ngb_batch *b, int with_lu)
 int ngbTranRun(ngb_batch *b, int max_points, const int *save_eq, int nsave)
 {
     const int S = b->S;
-    int r, done[2] = { 0, 0 }, e[4] = { 0, 0, 0, 0 };
+    int r, done[4] = { 0, 0, 0, 0 }, e[4] = { 0, 0, 0, 0 };
     long tick = 0, max_ticks;
     int check_every = 64;
     if (!b->have_lu) { ngb_set_error("no LU pattern set for this circuit"); return NGB_E_PANIC; }
@@ -189,8 +196,8 @@ int ngbTranRun(ngb_batch *b, int max_points, const int *save_eq, int nsave)
         int i;
         for (i = 0; i < check_every; i++, tick++)
             if ((r = enqueue_tick(b, 1))) return r;
-        ngb_dev_d2h(done, b->tran->x.ndone, sizeof(int) * 2);
-        if (done[1] >= S) b->tran->dc_over = 1;
+        ngb_dev_d2h(done, b->tran->x.ndone, sizeof(int) * 4);
+        b->tran->stage = (done[2] >= S) ? 2 : ((done[1] >= S) ? 1 : 0);
         ngb_dev_d2h(e, b->errflag, sizeof e);
         if (e[0]) { ngb_set_error("device load reported error %d", e[0]); return e[0]; }
         if (done[0] >= S) break;

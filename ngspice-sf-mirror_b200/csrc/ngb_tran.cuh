@@ -42,7 +42,8 @@ typedef struct NgbTranCtx {
     const int *save_eq;        /* [nsave] */
     double *out_time;          /* [S][max_points] */
     double *out_val;           /* [S][max_points][nsave] */
-    int *ndone;                /* [1] samples in DONE or FAIL */
+    int *evstage;              /* [S] see ngb_ev_advance */
+    int *ndone;                /* [0] samples in DONE or FAIL, [1] past the operating point, [2] past the last pivoting event */
     /* breakpoint-generating sources (VSRCaccept / ISRCaccept): tables of the load kernels plus the
      * per-sample VSRCbreak_time / ISRCbreak_time, [ninst][S], -1 at setup (vsrcset.c:34) */
     NgbSrcCtx isrc, vsrc;
@@ -50,7 +51,8 @@ typedef struct NgbTranCtx {
     /* circuit scalars */
     double tstep, tstop, tmax, tstart, delmin, minbreak, xmu;
     int maxorder, uic, max_iter_tran, max_iter_dc;
-    int nluset;                /* 2: the first transient iteration re-pivots onto pattern set 1 */
+    int nluset;                /* > 1: samples move between pattern sets at the pivoting events */
+    int lu_event[NGB_LU_EVENTS];   /* pattern set of each pivoting event (ngb_types.h) */
 } NgbTranCtx;
 
 NGB_HD int ngb_almost_equal_ulps(double A, double B, int maxUlps)
@@ -135,8 +137,24 @@ NGB_HD void ngb_begin_point(const NgbTranCtx *c, int s)
     c->phase[s] = NGB_PH_TRAN;
 }
 
+/* pivoting-event bookkeeping: evstage[s] = 1 once the sample has left the operating point, 2 once it is
+ * past the last re-pivoting of its run; ndone[1], ndone[2] count the samples at or beyond each stage so
+ * that the host can stop launching pattern sets nobody is on */
+NGB_HD void ngb_ev_advance(const NgbTranCtx *c, int s, int to)
+{
+    while (c->evstage[s] < to) {
+        const int st = ++c->evstage[s];
+#ifdef __CUDA_ARCH__
+        atomicAdd(c->ndone + st, 1);
+#else
+        c->ndone[st] += 1;
+#endif
+    }
+}
+
 NGB_HD void ngb_finish(const NgbTranCtx *c, int s, int phase, int err)
 {
+    ngb_ev_advance(c, s, 2);
     c->phase[s] = phase;
     c->ctl.active[s] = 0;
     if (err) c->ctl.err[s] = err;
@@ -277,6 +295,7 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
         c->ctl.ag0[s] = 0; c->ctl.ag1[s] = 0;
         c->ctl.stateop[s] = NGB_OP_COPY01;
         c->ctl.noncon[s] = 0; c->nodeconv_w[s] = 0; c->ctl.lte[s] = 1e300; c->ctl.lte2[s] = 1e300;
+        ngb_ev_advance(c, s, 1);
         ngb_next_time(c, s);
         return;
     }
@@ -297,9 +316,14 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
             if (noncon == 0) niret = NGB_OK;
         } else if (mode & NGB_MODEINITJCT) {
             mode = (mode & ~NGB_INITF) | NGB_MODEINITFIX;
+            if (c->nluset > 1) c->ctl.lusel[s] = c->lu_event[1];           /* NISHOULDREORDER, niiter.c:335 */
         } else if (mode & NGB_MODEINITFIX) {
             if (noncon == 0) mode = (mode & ~NGB_INITF) | NGB_MODEINITFLOAT;
         } else if (mode & (NGB_MODEINITTRAN | NGB_MODEINITPRED | NGB_MODEINITSMSIG)) {
+            if ((mode & NGB_MODEINITTRAN) && iterno <= 1) {
+                if (c->nluset > 1) c->ctl.lusel[s] = c->lu_event[3];       /* NISHOULDREORDER, niiter.c:343-344 */
+                ngb_ev_advance(c, s, 2);
+            }
             mode = (mode & ~NGB_INITF) | NGB_MODEINITFLOAT;
         } else {
             niret = NGB_E_PANIC;
@@ -327,12 +351,8 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
         c->ctl.ag0[s] = 0; c->ctl.ag1[s] = 0;
         c->ctl.stateop[s] = NGB_OP_COPY01;
         /* NIiter re-pivots in the first iteration under MODEINITTRAN (niiter.c:107-111) */
-        if (c->nluset > 1) c->ctl.lusel[s] = 1;
-#ifdef __CUDA_ARCH__
-        atomicAdd(c->ndone + 1, 1);
-#else
-        c->ndone[1] += 1;
-#endif
+        if (c->nluset > 1) c->ctl.lusel[s] = c->lu_event[2];
+        ngb_ev_advance(c, s, 1);
         ngb_next_time(c, s);
         return;
     }

@@ -87,6 +87,10 @@ typedef struct NgbSrcCtx {
 
 /* assembly of Ax / rhs from the stamp buffer: target t sums rows tgt_rows[tgt_ptr[t]..tgt_ptr[t+1])
  * in that (reference load) order; targets [0,nnz) are CSC slots, [nnz, nnz+neq+1) are rhs rows */
+/* pivoting events of one run (niiter.c:107-111, 333-349): 0 the MODEINITJCT iteration, 1 the iteration after it (rest of the
+ * operating point), 2 the first iteration under MODEINITTRAN, 3 the iteration after it (rest of the transient) */
+#define NGB_LU_EVENTS 4
+#define NGB_LU_SETS 4
 #define NGB_ASM_LONG 4096
 typedef struct NgbAsmCtx {
     int S, nnz, neq1;

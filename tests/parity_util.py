@@ -28,16 +28,14 @@ def first_pattern(trace):
 
 
 def run_patterns(trace):
-    """the pivoting factors a complete run needs: the first one, plus the one of the first iteration
-    under MODEINITTRAN when the run started with a DC operating point and the pivots changed"""
+    """the pivoting factors of a complete run, in the order the reference computed them (recorded by
+    oracle/ref_hooks.c at every SMPreorder): the INITJCT iteration and the one after it, then the first two
+    iterations of the first time point -- two factors for a UIC run.  Circuit.set_lu_pattern maps them onto
+    pattern sets (identical factors share one)."""
     ks = sorted({int(k.split("/")[0][1:]) for k in trace if k.endswith("/pat/n")})
-    first = pattern_at(trace, ks[0])
-    for k in ks[1:]:
-        if int(trace[f"c{k}/mode"][0]) & 0x1000:            # MODEINITTRAN
-            p = pattern_at(trace, k)
-            same = all(np.array_equal(first[q], p[q]) for q in ("Pnum", "Q", "Lp", "Li", "Up", "Ui", "Offp", "Offi"))
-            return [first] if same else [first, p]
-    return [first]
+    uic = bool(int(trace[f"c{ks[0]}/mode"][0]) & 0x1000) or not (int(trace[f"c{ks[0]}/mode"][0]) & 0x200)
+    want = 2 if uic else 4
+    return [pattern_at(trace, k) for k in ks[:want]]
 
 
 def pattern_at(trace, call):
