@@ -35,6 +35,8 @@ void ngb_tran_free(struct ngb_batch *b)
     ngb_dev_free(t->x.npts); ngb_dev_free(t->x.brkflag); ngb_dev_free(t->x.accepted); ngb_dev_free(t->x.rejected);
     ngb_dev_free(t->x.numiter); ngb_dev_free(t->x.timepts); ngb_dev_free(t->x.save_delta); ngb_dev_free(t->x.old_delta);
     ngb_dev_free(t->x.breaks); ngb_dev_free(t->x.out_time); ngb_dev_free(t->x.out_val); ngb_dev_free(t->x.ndone); ngb_dev_free(t->x.evstage);
+    ngb_dev_free(t->x.gm_stage); ngb_dev_free(t->x.gm_factor); ngb_dev_free(t->x.gm_oldgmin); ngb_dev_free(t->x.gm_xold);
+    { int a; for (a = 0; a < t->x.gm_narr; a++) ngb_dev_free(t->x.gm_arr[a].old); }
     ngb_dev_free(t->d_save_eq); ngb_dev_free(t->x.isrc_break); ngb_dev_free(t->x.vsrc_break);
     ngb_dev_graph_destroy(t->graph[0]); ngb_dev_graph_destroy(t->graph[1]); ngb_dev_graph_destroy(t->graph[2]);
     free(t);
@@ -76,6 +78,23 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     t->max_points = max_points; t->nsave = nsave;
     x->tstep = c->opt.tstep; x->tstop = c->opt.tstop; x->tmax = c->opt.tmax; x->tstart = c->opt.tstart;
     x->delmin = c->opt.delmin; x->minbreak = c->opt.minbreak; x->xmu = c->opt.xmu;
+    if (!c->opt.uic) {
+        /* dynamic gmin stepping needs a copy of the solution and of every device's CKTstate0 per sample */
+        struct { double *st; int K, n; } tab[5] = {
+            { b->b4_state, B4ST_COUNT, c->b4_n }, { b->b3_state, B3ST_COUNT, c->b3_n }, { b->vb_state, VBS_COUNT, c->vb_n },
+            { b->dio_state, DIOST_COUNT, c->dio_n }, { b->cap_state, 2, c->cap_n } };
+        x->gm_stage = (int *)dz(sizeof(int) * S);
+        x->gm_factor = (double *)dz(sizeof(double) * S); x->gm_oldgmin = (double *)dz(sizeof(double) * S);
+        x->gm_xold = (double *)dz(sizeof(double) * (size_t)b->neq1 * S);
+        for (i = 0; i < 5; i++)
+            if (tab[i].st && tab[i].n > 0) {
+                x->gm_arr[x->gm_narr].state = tab[i].st; x->gm_arr[x->gm_narr].K = tab[i].K; x->gm_arr[x->gm_narr].ninst = tab[i].n;
+                x->gm_arr[x->gm_narr].old = (double *)dz(sizeof(double) * (size_t)tab[i].K * tab[i].n * S);
+                if (!x->gm_arr[x->gm_narr].old) { ngb_set_error("gmin-stepping buffers: out of device memory"); return NGB_E_PANIC; }
+                x->gm_narr++;
+            }
+        x->gm_enable = 1;
+    }
     ngb_lu_events(c, x->lu_event);
     x->nluset = (x->lu_event[0] != x->lu_event[1] || x->lu_event[1] != x->lu_event[2] || x->lu_event[2] != x->lu_event[3]) ? 2 : 1;
     x->maxorder = c->opt.maxorder; x->uic = c->opt.uic; x->max_iter_tran = c->opt.itl4; x->max_iter_dc = c->opt.itl1;

@@ -51,6 +51,13 @@ typedef struct NgbTranCtx {
     /* circuit scalars */
     double tstep, tstop, tmax, tstart, delmin, minbreak, xmu;
     int maxorder, uic, max_iter_tran, max_iter_dc;
+    /* dynamic gmin stepping (cktop.c:162-274), the operating-point fallback when plain Newton fails:
+     * gm_stage 0 = plain NIiter, 1 = inside the stepping loop, 2 = final NIiter with CKTdiagGmin = gshunt */
+    int *gm_stage;             /* [S] */
+    double *gm_factor, *gm_oldgmin;   /* [S] */
+    double *gm_xold;           /* [neq1][S] OldRhsOld */
+    struct { double *state, *old; int K, ninst; } gm_arr[5];   /* device state tables and their OldCKTstate0 copies [K][ninst*S] */
+    int gm_narr, gm_enable;
     int nluset;                /* > 1: samples move between pattern sets at the pivoting events */
     int lu_event[NGB_LU_EVENTS];   /* pattern set of each pivoting event (ngb_types.h) */
 } NgbTranCtx;
@@ -271,6 +278,36 @@ NGB_HD void ngb_next_time(const NgbTranCtx *c, int s)
     ngb_begin_point(c, s);
 }
 
+/* CKTstate0 and CKTrhsOld of sample s: op 0 zero them, 1 save to the Old copies, 2 restore from them (cktop.c:182-186, 210-214, 244-248) */
+NGB_HD void ngb_gm_states(const NgbTranCtx *c, int s, int op)
+{
+    const int S = c->S, nh = c->ctl.nhist, head = c->ctl.head[s];
+    double *xo = c->x + (size_t)c->ctl.xsel[s] * c->neq1 * S;
+    for (int i = 1; i < c->neq1; i++) {
+        const size_t k = (size_t)i * S + s;
+        if (op == 0) xo[k] = 0.0; else if (op == 1) c->gm_xold[k] = xo[k]; else xo[k] = c->gm_xold[k];
+    }
+    for (int a = 0; a < c->gm_narr; a++) {
+        const size_t T = (size_t)c->gm_arr[a].ninst * S;
+        const int K = c->gm_arr[a].K;
+        double *st = c->gm_arr[a].state + (size_t)(head % nh) * K * T;
+        double *old = c->gm_arr[a].old;
+        for (int k = 0; k < K; k++)
+            for (int inst = 0; inst < c->gm_arr[a].ninst; inst++) {
+                const size_t j = (size_t)k * T + (size_t)inst * S + s;
+                if (op == 0) st[j] = 0.0; else if (op == 1) old[j] = st[j]; else st[j] = old[j];
+            }
+    }
+}
+
+/* start the next NIiter call of the operating point for sample s */
+NGB_HD void ngb_gm_next_niiter(const NgbTranCtx *c, int s, int mode)
+{
+    c->ctl.mode[s] = mode;
+    c->iterno[s] = 0;
+    if ((mode & NGB_MODEINITJCT) && c->nluset > 1) c->ctl.lusel[s] = c->lu_event[0];
+}
+
 /* One controller step for sample s, after the load (+ LU + solve) of this tick. */
 NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
 {
@@ -304,7 +341,9 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
     int iterno = c->iterno[s] + 1;
     int mode = c->ctl.mode[s];
     int noncon = c->ctl.noncon[s];
-    const int maxiter = (phase == NGB_PH_DCOP) ? NGB_MAX(c->max_iter_dc, 100) : NGB_MAX(c->max_iter_tran, 100);
+    /* NIiter raises maxIter to 100 (niiter.c:37); the gmin steps run with CKTdcTrcvMaxIter (itl2, default 50) */
+    const int maxiter = (phase == NGB_PH_DCOP) ? ((c->gm_stage && c->gm_stage[s] == 1) ? 100 : NGB_MAX(c->max_iter_dc, 100))
+                                               : NGB_MAX(c->max_iter_tran, 100);
     int niret = -1;                          /* -1: keep iterating, 0: converged, >0: error */
     c->iterno[s] = iterno;
     if (iterno > maxiter) {
@@ -340,8 +379,54 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
     }
     c->numiter[s] += iterno;
 
+    if (phase == NGB_PH_DCOP && c->gm_enable) {
+        /* CKTop (cktop.c:27-112): plain NIiter, then dynamic_gmin (:162-274).  new_gmin, source stepping and
+         * OPtran are not built: a sample that dynamic gmin stepping cannot bring home fails with NIiter's code */
+        const int firstmode = (mode & NGB_MODEUIC) | NGB_MODETRANOP | NGB_MODEINITJCT;
+        const int contmode = (mode & NGB_MODEUIC) | NGB_MODETRANOP | NGB_MODEINITFLOAT;
+        const int stage = c->gm_stage[s];
+        const int itl2 = 50;                                   /* CKTdcTrcvMaxIter */
+        const double gmin_factor = 10.0;                        /* CKTgminFactor */
+        const double gtarget = c->ctl.gmin[s];                  /* MAX(CKTgmin, CKTgshunt), gshunt = 0 */
+        if (stage == 0 && niret != NGB_OK) {
+            c->gm_stage[s] = 1;
+            ngb_gm_states(c, s, 0);
+            c->gm_factor[s] = gmin_factor;
+            c->gm_oldgmin[s] = 1e-2;
+            c->ctl.diag_gmin[s] = 1e-2 / gmin_factor;
+            ngb_gm_next_niiter(c, s, firstmode);
+            return;
+        }
+        if (stage == 1) {
+            double factor = c->gm_factor[s];
+            int leave = 0;
+            if (niret == NGB_OK) {
+                mode = contmode;
+                if (c->ctl.diag_gmin[s] <= gtarget) {
+                    leave = 1;
+                } else {
+                    ngb_gm_states(c, s, 1);
+                    if (iterno <= itl2 / 4) { factor *= sqrt(factor); if (factor > gmin_factor) factor = gmin_factor; }
+                    if (iterno > 3 * itl2 / 4) factor = NGB_MAX(sqrt(factor), 1.00005);
+                    c->gm_oldgmin[s] = c->ctl.diag_gmin[s];
+                    if (c->ctl.diag_gmin[s] < factor * gtarget) { factor = c->ctl.diag_gmin[s] / gtarget; c->ctl.diag_gmin[s] = gtarget; }
+                    else c->ctl.diag_gmin[s] /= factor;
+                }
+            } else if (factor < 1.00005) {
+                leave = 1;                                       /* "Last gmin step failed" */
+            } else {
+                factor = sqrt(sqrt(factor));
+                c->ctl.diag_gmin[s] = c->gm_oldgmin[s] / factor;
+                ngb_gm_states(c, s, 2);
+            }
+            c->gm_factor[s] = factor;
+            if (leave) { c->ctl.diag_gmin[s] = 0.0; c->gm_stage[s] = 2; }      /* CKTdiagGmin = CKTgshunt, final NIiter */
+            ngb_gm_next_niiter(c, s, mode);
+            return;
+        }
+    }
     if (phase == NGB_PH_DCOP) {
-        if (niret != NGB_OK) { ngb_finish(c, s, NGB_PH_FAIL, niret); return; }   /* no gmin/source stepping yet */
+        if (niret != NGB_OK) { ngb_finish(c, s, NGB_PH_FAIL, niret); return; }
         c->timepts[s] += 1;
         c->ctl.order[s] = 1;
         for (int i = 0; i < 7; i++) c->ctl.delta_old[(size_t)i * S + s] = c->tmax;

@@ -185,7 +185,12 @@ def mix_netlist(vdd="2.0", r="1k"):
 
 
 # sweep points recorded for parity (value text exactly as it appears in the netlist): centre + 4 corners
-MIX_POINTS = [("2.0", "1k"), ("1.6", "200"), ("1.6", "5k"), ("2.4", "200"), ("2.4", "5k")]
+MIX_POINTS = [("2.0", "1k"), ("1.6", "200"), ("1.6", "5k"), ("2.4", "200"), ("2.4", "5k"),
+              # operating points plain Newton does not reach: the reference goes through dynamic gmin stepping (cktop.c:162)
+              ("1.69098", "1348.2"),
+              # marginal operating points (66 and 43 Newton iterations in the reference) whose own pivot order differs from
+              # the centre's: the batch, bound to the centre's pivot orders, reaches them through gmin stepping instead
+              ("1.69412", "2364.7"), ("1.69412", "2383.5")]
 
 
 def b3_cards():

@@ -24,9 +24,10 @@ def _run(lib, name, S=1, inst=None, max_points=8192):
     return res, t, v, wave
 
 
-def _compare(res, t, v, wave, s, exact, tol=1e-9):
+def _compare(res, t, v, wave, s, exact, tol=1e-9, same_route=True):
     acc, rej, nit = (int(x) for x in wave["stats"][:3])
-    assert int(res.accepted[s]) == acc and int(res.rejected[s]) == rej and int(res.numiter[s]) == nit
+    assert int(res.accepted[s]) == acc and int(res.rejected[s]) == rej
+    assert int(res.numiter[s]) == nit or not same_route
     n = int(res.npoints[s])
     assert n == len(wave["time"])
     if exact:
@@ -53,12 +54,16 @@ def test_tran_hostsim_vbic(hostsim_lib):
     _compare(res, t, v, wave, 0, exact=False)
 
 
-MIX_POINTS = [("2.0", "1k"), ("1.6", "200"), ("1.6", "5k"), ("2.4", "200"), ("2.4", "5k")]     # make_golden.py
+MIX_POINTS = [("2.0", "1k"), ("1.6", "200"), ("1.6", "5k"), ("2.4", "200"), ("2.4", "5k"),     # make_golden.py
+              ("1.69098", "1348.2"),                          # the reference needs dynamic gmin stepping here (cktop.c:162)
+              ("1.69412", "2364.7"), ("1.69412", "2383.5")]   # marginal: bound to the centre's pivot orders the batch needs it too
+MIX_SAME_ROUTE = 6          # the first six points take the reference's route: identical iteration counts
 
 
 def _mix_sweep(lib, reps=1):
     """BASELINE config 5: the mixed BSIM4 + BSIM3 + VBIC + diode + R/C cell, every sample with its own supply
-    voltage and interconnect resistor (centre + four corners of the sweep grid), in ONE batch"""
+    voltage and interconnect resistor (centre + four corners of the sweep grid, plus three points whose
+    operating point needs gmin stepping), in ONE batch"""
     flat = ngt.read(f"{GOLDEN}/mix.flat.ngt")
     trace = ngt.read(f"{GOLDEN}/mix.trace.ngt.gz")
     wave = ngt.read(f"{GOLDEN}/mix.wave.ngt")
@@ -70,7 +75,7 @@ def _mix_sweep(lib, reps=1):
     t, v = res.waves()
     for s in range(len(pts)):
         k = s % len(MIX_POINTS)
-        _compare(res, t, v, ngt.read(f"{GOLDEN}/mix{k if k else ''}.wave.ngt"), s, exact=False)
+        _compare(res, t, v, ngt.read(f"{GOLDEN}/mix{k if k else ''}.wave.ngt"), s, exact=False, same_route=k < MIX_SAME_ROUTE)
 
 
 def test_tran_hostsim_mix_cell(hostsim_lib):
@@ -86,7 +91,7 @@ def test_tran_hostsim_mix_sweep(hostsim_lib):
 
 @pytest.mark.gpu
 def test_tran_gpu_mix_sweep(cuda_lib):
-    _mix_sweep(cuda_lib, reps=13)       # 65 samples: more than two warps, every point on its own time axis
+    _mix_sweep(cuda_lib, reps=9)        # 72 samples: more than two warps, every point on its own time axis
 
 
 def _mc_inst(lib):
