@@ -116,6 +116,11 @@ int ngbCircuitSetLuPattern(ngb_circuit *c, int n, int nblocks, const int *Q, con
  * first iteration under MODEINITTRAN (niiter.c:107-111), and the pivot order may change.  Set 0
  * (default) holds the first result, set 1 the second; ngbCircuitSelectLuSet chooses which one the
  * next ngbCircuitSetLuPattern / ngbCircuitLuInfo refers to.  With only set 0 present it serves both */
+/* .nodeset (kind 0) / .ic (kind 1) rows: eq [n] equation numbers, value [n] volts -- what CKTic (cktic.c) leaves in
+ * CKTnode.nsGiven/nodeset, icGiven/ic.  Applied at the end of every load while the operating point is computed,
+ * exactly as cktload.c:118-172 (ZeroNoncurRow :182-201).  Per-sample values: array "node.override" [n][S].
+ * Call after ngbCircuitFinalize and before ngbBatchCreate */
+int ngbCircuitSetNodeOverrides(ngb_circuit *c, int n, const int *eq, const int *kind, const double *value);
 int ngbCircuitSelectLuSet(ngb_circuit *c, int which);
 /* NIiter re-pivots (SMPreorder) at up to four moments of a run: [0] the MODEINITJCT iteration, [1] the
  * iteration after it (NISHOULDREORDER, niiter.c:335) whose order serves the rest of the operating point,

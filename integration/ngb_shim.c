@@ -313,9 +313,6 @@ static int shim_attach(CKTcircuit *ckt)
             fprintf(stderr, "ngb_shim: device type %s is not on the GPU path\n", DEVices[t]->DEVpublic.name);
             return shim_fail("unsupported device type in the circuit");
         }
-    for (node = ckt->CKTnodes; node; node = node->next)
-        if (node->nsGiven || (node->icGiven && !(ckt->CKTmode & MODEUIC)))
-            return shim_fail(".nodeset / .ic row overrides of CKTload are not implemented");
     ntype = (int *)xc((size_t)neq + 1, sizeof(int));
     for (node = ckt->CKTnodes; node; node = node->next) if (node->number >= 0 && node->number <= neq) ntype[node->number] = node->type;
     G.C = ngbCircuitCreate(neq, ntype);
@@ -332,6 +329,19 @@ static int shim_attach(CKTcircuit *ckt)
         (rc = ngbCircuitFinalize(G.C))) {
         fprintf(stderr, "ngb_shim: %s\n", ngbLastError());
         return shim_fail("circuit uses an option outside the GPU path");
+    }
+    {   /* .nodeset / .ic rows (cktload.c:118-172): nodesets first, then initial conditions, each in node order */
+        int nov = 0, pass, i = 0, *oeq, *okind; double *oval;
+        for (node = ckt->CKTnodes; node; node = node->next) nov += (node->nsGiven ? 1 : 0) + (node->icGiven ? 1 : 0);
+        if (nov) {
+            oeq = (int *)xc((size_t)nov, sizeof(int)); okind = (int *)xc((size_t)nov, sizeof(int)); oval = (double *)xc((size_t)nov, sizeof(double));
+            for (pass = 0; pass < 2; pass++)
+                for (node = ckt->CKTnodes; node; node = node->next)
+                    if (pass ? node->icGiven : node->nsGiven) { oeq[i] = node->number; okind[i] = pass; oval[i] = pass ? node->ic : node->nodeset; i++; }
+            rc = ngbCircuitSetNodeOverrides(G.C, nov, oeq, okind, oval);
+            free(oeq); free(okind); free(oval);
+            if (rc) { fprintf(stderr, "ngb_shim: %s\n", ngbLastError()); return shim_fail("node overrides rejected"); }
+        }
     }
     ngbCircuitPatternSize(G.C, &n, &nnz, &nrows);
     if (n != (int)K->KLUmatrixN || nnz != (int)K->KLUmatrixNZ) return shim_fail("CSC pattern differs from SMPconvertCOOtoCSC's");

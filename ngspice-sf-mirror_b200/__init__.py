@@ -190,6 +190,10 @@ class Circuit:
             lib.check(lib.L.ngbCircuitAddIsources(c.h, int(n), _ip(_i32(flat["isrc/nodes"])), _ip(_i32(flat["isrc/fn"])),
                                                   _dp(_f64(flat["isrc/par"]))), "ngbCircuitAddIsources")
         lib.check(lib.L.ngbCircuitFinalize(c.h), "ngbCircuitFinalize")
+        n = sc(flat, "node/nov", 0)
+        if n:
+            lib.check(lib.L.ngbCircuitSetNodeOverrides(c.h, int(n), _ip(_i32(flat["node/ov_eq"])), _ip(_i32(flat["node/ov_kind"])),
+                                                       _dp(_f64(flat["node/ov_val"]))), "ngbCircuitSetNodeOverrides")
         if lu_pattern is not None:
             c.set_lu_pattern(lu_pattern)
         return c

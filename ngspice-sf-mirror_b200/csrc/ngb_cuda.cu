@@ -368,6 +368,13 @@ int ngb_launch_src_load(const NgbSrcCtx *c)
     ngb_k_src_load<<<grid, 256, 0, g_stream>>>(*c);
     return post_launch("src_load");
 }
+__global__ void __launch_bounds__(128)
+ngb_k_node_override(const NgbAsmCtx c)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < c.S) ngb_override_thread(&c, s);
+}
+
 int ngb_launch_assemble(const NgbAsmCtx *c)
 {
     const size_t total = (size_t)(c->nnz + c->neq1) * c->S;
@@ -377,7 +384,12 @@ int ngb_launch_assemble(const NgbAsmCtx *c)
         const int e = post_launch("assemble");
         if (e) return e;
         ngb_k_assemble_long<<<(unsigned)(c->nlong * c->S), 256, 0, g_stream>>>(*c);
-        return post_launch("assemble_long");
+    }
+    if (c->nov > 0) {
+        const int e = post_launch("assemble");
+        if (e) return e;
+        ngb_k_node_override<<<(unsigned)((c->S + 127) / 128), 128, 0, g_stream>>>(*c);
+        return post_launch("node_override");
     }
     return post_launch("assemble");
 }

@@ -192,6 +192,7 @@ void ngbCircuitDestroy(ngb_circuit *c)
     free(c->vs_nodes); free(c->vs_fn); free(c->vs_par); free(c->vs_spos); free(c->vs_cspos);
     free(c->is_nodes); free(c->is_fn); free(c->is_par); free(c->is_spos);
     free(c->Ap); free(c->Ai); free(c->eq2col); free(c->col2eq); free(c->slot_diag); free(c->diag_slot);
+    free(c->ov_eq); free(c->ov_kind); free(c->ov_cur); free(c->ov_diag); free(c->ov_zptr); free(c->ov_zslot); free(c->ov_val);
     free(c->long_tgt); free(c->tgt_ptr); free(c->tgt_rows); free(c->const_row); free(c->const_val);
     free(c->klu_Q); free(c->klu_R); free(c->klu_Pnum);
     free_sched(&c->sch);
@@ -1069,6 +1070,41 @@ bad:
     return NGB_E_PANIC;
 }
 
+/* .nodeset (kind 0) and .ic (kind 1) nodes, what CKTic left in CKTnode.nsGiven/nodeset/icGiven/ic: CKTload
+ * overrides these rows while the operating point is computed (cktload.c:118-172).  Rows are applied in
+ * the order given within each kind, nodesets first, like the two node loops of the reference. */
+int ngbCircuitSetNodeOverrides(ngb_circuit *c, int n, const int *eq, const int *kind, const double *value)
+{
+    int i, k, pass, nz = 0, m = 0;
+    if (!c->finalized) { ngb_set_error("ngbCircuitSetNodeOverrides: call ngbCircuitFinalize first"); return NGB_E_PANIC; }
+    free(c->ov_eq); free(c->ov_kind); free(c->ov_cur); free(c->ov_diag); free(c->ov_zptr); free(c->ov_zslot); free(c->ov_val);
+    c->ov_eq = (int *)xcalloc((size_t)n + 1, sizeof(int)); c->ov_kind = (int *)xcalloc((size_t)n + 1, sizeof(int));
+    c->ov_cur = (int *)xcalloc((size_t)n + 1, sizeof(int)); c->ov_diag = (int *)xcalloc((size_t)n + 1, sizeof(int));
+    c->ov_zptr = (int *)xcalloc((size_t)n + 2, sizeof(int)); c->ov_val = (double *)xcalloc((size_t)n + 1, sizeof(double));
+    c->ov_zslot = (int *)xcalloc((size_t)c->nnz + 1, sizeof(int));
+    for (pass = 0; pass < 2; pass++)
+        for (i = 0; i < n; i++) {
+            int row, col;
+            if ((kind[i] ? 1 : 0) != pass) continue;
+            if (eq[i] <= 0 || eq[i] > c->neq || c->eq2col[eq[i]] < 0) { ngb_set_error("node override %d: equation %d is not in the matrix", i, eq[i]); return NGB_E_PANIC; }
+            row = c->eq2col[eq[i]];
+            c->ov_eq[m] = eq[i]; c->ov_kind[m] = pass; c->ov_val[m] = value[i]; c->ov_diag[m] = slot_lookup(c, eq[i], eq[i]);
+            /* ZeroNoncurRow: every entry of the row; current-type columns stay (and flag the row) */
+            for (col = 0; col < c->n; col++)
+                for (k = c->Ap[col]; k < c->Ap[col + 1]; k++)
+                    if (c->Ai[k] == row) {
+                        if (c->node_type[c->col2eq[col]] == 4 /* SP_CURRENT */) c->ov_cur[m] = 1;
+                        else {
+                            if (nz >= c->nnz) { int *z = (int *)realloc(c->ov_zslot, sizeof(int) * (size_t)(nz + c->nnz + 1)); if (!z) return NGB_E_PANIC; c->ov_zslot = z; }
+                            c->ov_zslot[nz++] = k;
+                        }
+                    }
+            c->ov_zptr[++m] = nz;
+        }
+    c->ov_n = m;
+    return NGB_OK;
+}
+
 int ngbCircuitSelectLuSet(ngb_circuit *c, int which)
 {
     if (which < 0 || which >= NGB_LU_SETS) return NGB_E_PANIC;
@@ -1275,6 +1311,13 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
         b->dio_flags = (int *)dev_dup(c->dio_flags, sizeof(int) * (size_t)c->dio_n);
         b->dio_spos = (int *)dev_dup(c->dio_spos, sizeof(int) * DIOS_COUNT * (size_t)c->dio_n);
     }
+    if (c->ov_n) {
+        b->ov_val = (double *)dalloc_rep(b, "node.override", c->ov_val, 1, c->ov_n, S);
+        b->ov_eq = (int *)dev_dup(c->ov_eq, sizeof(int) * (size_t)c->ov_n); b->ov_kind = (int *)dev_dup(c->ov_kind, sizeof(int) * (size_t)c->ov_n);
+        b->ov_cur = (int *)dev_dup(c->ov_cur, sizeof(int) * (size_t)c->ov_n); b->ov_diag = (int *)dev_dup(c->ov_diag, sizeof(int) * (size_t)c->ov_n);
+        b->ov_zptr = (int *)dev_dup(c->ov_zptr, sizeof(int) * ((size_t)c->ov_n + 1));
+        b->ov_zslot = (int *)dev_dup(c->ov_zslot, sizeof(int) * ((size_t)c->ov_zptr[c->ov_n] + 1));
+    }
     if (c->vb_n) {
         const size_t T = (size_t)c->vb_n * S;
         b->vb_par = (double *)dalloc_rep(b, "vbic.par", c->vb_par, VBIC_NP, c->vb_n, S);
@@ -1367,6 +1410,7 @@ void ngbBatchDestroy(ngb_batch *b)
     ngb_dev_free(b->cap_nodes); ngb_dev_free(b->cap_spos);
     ngb_dev_free(b->dio_nodes); ngb_dev_free(b->dio_flags); ngb_dev_free(b->dio_spos);
     ngb_dev_free(b->vb_nodes); ngb_dev_free(b->vb_flags); ngb_dev_free(b->vb_spos);
+    ngb_dev_free(b->ov_eq); ngb_dev_free(b->ov_kind); ngb_dev_free(b->ov_cur); ngb_dev_free(b->ov_diag); ngb_dev_free(b->ov_zptr); ngb_dev_free(b->ov_zslot);
     ngb_dev_free(b->b3_mtab); ngb_dev_free(b->b3_ptab); ngb_dev_free(b->b3_prow); ngb_dev_free(b->b3_flags); ngb_dev_free(b->b3_nodes); ngb_dev_free(b->b3_spos);
     ngb_dev_free(b->vs_fn); ngb_dev_free(b->vs_spos); ngb_dev_free(b->is_fn); ngb_dev_free(b->is_spos);
     if (b->have_lu) {
@@ -1490,6 +1534,8 @@ void ngb_fill_asmctx(ngb_batch *b, NgbAsmCtx *x)
     memset(x, 0, sizeof *x);
     x->S = b->S; x->nnz = c->nnz; x->neq1 = b->neq1; x->tgt_ptr = b->d_tgt_ptr; x->tgt_rows = b->d_tgt_rows;
     x->slot_diag = b->d_slot_diag; x->long_tgt = b->d_long_tgt; x->nlong = c->nlong; x->stamp = b->stamp; x->Ax = b->Ax; x->x = b->x; x->add_diag_gmin = 1; x->ctl = b->ctl;
+    x->nov = c->ov_n; x->ov_eq = b->ov_eq; x->ov_kind = b->ov_kind; x->ov_cur = b->ov_cur; x->ov_diag = b->ov_diag;
+    x->ov_zptr = b->ov_zptr; x->ov_zslot = b->ov_zslot; x->ov_val = b->ov_val;
 }
 void ngb_fill_luctx(ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve, int which)
 {

@@ -32,6 +32,8 @@ struct ngb_circuit {
     int nstamp_rows, ntgt; int *tgt_ptr, *tgt_rows;
     int nlong; int *long_tgt;     /* targets with more than NGB_ASM_LONG contributions */
     int nconst; int *const_row; double *const_val;
+    /* .nodeset / .ic rows (ngbCircuitSetNodeOverrides) */
+    int ov_n; int *ov_eq, *ov_kind, *ov_cur, *ov_diag, *ov_zptr, *ov_zslot; double *ov_val;
     /* LU: imported or own symbolic objects + task schedule */
     int klu_nblocks; int *klu_Q, *klu_R, *klu_Pnum;
     int lnz, unz, nzoff, npairs, nsolvepairs;
@@ -57,6 +59,7 @@ struct ngb_batch {
     double *cap_par, *cap_state; int *cap_nodes, *cap_spos;
     double *b3_inst, *b3_state, *b3_von, *b3_mtab, *b3_ptab; int *b3_prow, *b3_flags, *b3_nodes, *b3_spos;
     double *vb_par, *vb_aux, *vb_state; int *vb_nodes, *vb_flags, *vb_spos;
+    int *ov_eq, *ov_kind, *ov_cur, *ov_diag, *ov_zptr, *ov_zslot; double *ov_val;
     double *dio_par, *dio_state; int *dio_nodes, *dio_flags, *dio_spos;
     double *vs_par; int *vs_fn, *vs_spos;
     double *is_par; int *is_fn, *is_spos;

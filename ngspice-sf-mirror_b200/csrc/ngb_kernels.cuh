@@ -219,6 +219,36 @@ NGB_HD void ngb_asm_store(const NgbAsmCtx *c, int tg, int s, double acc)
     }
 }
 
+/* nodeset / ic assignments at the end of CKTload (cktload.c:118-172), one thread per sample, rows in
+ * reference order.  LoadGmin_CSC runs after CKTload in the reference; the assembly has already added
+ * CKTdiagGmin to the diagonals, so a rewritten diagonal gets it again here. */
+NGB_HD void ngb_override_thread(const NgbAsmCtx *c, int s)
+{
+    const int S = c->S;
+    if (!NGB_LDG(&c->ctl.active[s])) return;
+    const int mode = NGB_LDG(&c->ctl.mode[s]);
+    if (!(mode & NGB_MODEDC)) return;
+    const double srcfact = NGB_LDG(&c->ctl.srcfact[s]);
+    const double dg = c->add_diag_gmin ? NGB_LDG(&c->ctl.diag_gmin[s]) : 0.0;
+    double *Ax = c->Ax + (size_t)s * c->nnz;
+    double *rhs = c->x + (size_t)(1 - NGB_LDG(&c->ctl.xsel[s])) * c->neq1 * S;
+    for (int i = 0; i < c->nov; i++) {
+        const int kind = NGB_LDG(&c->ov_kind[i]);
+        if (kind == 0 ? !(mode & (NGB_MODEINITJCT | NGB_MODEINITFIX)) : (!(mode & NGB_MODETRANOP) || (mode & NGB_MODEUIC))) continue;
+        const int eq = NGB_LDG(&c->ov_eq[i]), d = NGB_LDG(&c->ov_diag[i]);
+        const double v = NGB_LDG(&c->ov_val[(size_t)i * S + s]);
+        for (int p = NGB_LDG(&c->ov_zptr[i]); p < NGB_LDG(&c->ov_zptr[i + 1]); p++) Ax[NGB_LDG(&c->ov_zslot[p])] = 0.0;
+        if (NGB_LDG(&c->ov_cur[i])) {
+            rhs[(size_t)eq * S + s] = 1.0e10 * v * srcfact;
+            if (d >= 0) { if (kind == 0) Ax[d] = 1e10; else Ax[d] += 1.0e10; }
+        } else {
+            rhs[(size_t)eq * S + s] = v * srcfact;
+            if (d >= 0) Ax[d] = 1;
+        }
+        if (d >= 0 && dg != 0.0) Ax[d] += dg;
+    }
+}
+
 /* ------------------------------------------------------------------ LU */
 #ifndef NGB_GROUP_SYNC
 #define NGB_GROUP_SYNC() ((void)0)     /* hostsim: one "thread" per group */

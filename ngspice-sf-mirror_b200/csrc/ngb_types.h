@@ -103,6 +103,12 @@ typedef struct NgbAsmCtx {
     double *Ax;             /* [S][nnz]                                                  */
     double *x;              /* rhs is assembled into x[1 - xsel]                         */
     int add_diag_gmin;
+    /* .nodeset / .ic row overrides of CKTload (cktload.c:118-172): nov rows in reference order (nodesets, then
+     * initial conditions); ov_zptr/ov_zslot list the voltage-column entries ZeroNoncurRow clears, ov_cur says
+     * whether the row keeps an entry in a current column, ov_val [nov][S] is the forced voltage */
+    int nov;
+    const int *ov_eq, *ov_kind, *ov_cur, *ov_diag, *ov_zptr, *ov_zslot;
+    const double *ov_val;
     NgbCtl ctl;
 } NgbAsmCtx;
 

@@ -549,6 +549,17 @@ static void dump_flat(CKTcircuit *ckt, const char *path)
     dump_linear(f, ckt, K);
     dump_dio(f, ckt, K);
     dump_vbic(f, ckt);
+    {   /* .nodeset / .ic nodes as CKTic left them: nodesets first, then initial conditions, each in node order */
+        CKTnode *nd; int n = 0, pass, i = 0; int *eq, *kind; double *val;
+        for (nd = ckt->CKTnodes; nd; nd = nd->next) n += (nd->nsGiven ? 1 : 0) + (nd->icGiven ? 1 : 0);
+        eq = (int *)calloc((size_t)n + 1, sizeof(int)); kind = (int *)calloc((size_t)n + 1, sizeof(int)); val = (double *)calloc((size_t)n + 1, sizeof(double));
+        for (pass = 0; pass < 2; pass++)
+            for (nd = ckt->CKTnodes; nd; nd = nd->next)
+                if (pass ? nd->icGiven : nd->nsGiven) { eq[i] = nd->number; kind[i] = pass; val[i] = pass ? nd->ic : nd->nodeset; i++; }
+        put_is(f, "node/nov", n);
+        if (n) { put_i1(f, "node/ov_eq", eq, n); put_i1(f, "node/ov_kind", kind, n); put_d1(f, "node/ov_val", val, n); }
+        free(eq); free(kind); free(val);
+    }
     dump_bsim3(f, ckt, K);
     fclose(f);
     free(ntype); free(nic); free(nicg); free(names);

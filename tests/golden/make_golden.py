@@ -193,6 +193,27 @@ MIX_POINTS = [("2.0", "1k"), ("1.6", "200"), ("1.6", "5k"), ("2.4", "200"), ("2.
               ("1.69412", "2364.7"), ("1.69412", "2383.5")]
 
 
+def latch_netlist():
+    """.nodeset and .ic without UIC: CKTload's row overrides (cktload.c:118-172).  A BSIM4 latch whose state
+    is picked by .nodeset (forced during the INITJCT / INITFIX iterations only), an RC ladder whose nodes
+    are held by .ic through the whole operating point, one of them next to a source branch; a set pulse
+    flips the latch in the transient"""
+    mos = "l=0.1u w={w} ad=5p pd=6u as=5p ps=6u"
+    return "\n".join([
+        "* BSIM4 latch with .nodeset, RC ladder with .ic",
+        "vdd dd 0 dc 2.0",
+        "vset s 0 dc 0 pulse(0 2 1n 0.1n 0.1n 1n 10n)",
+        "mp1 q qb dd dd p1 " + mos.format(w="10u"), "mn1 q qb 0 0 n1 " + mos.format(w="5u"),
+        "mp2 qb q dd dd p1 " + mos.format(w="10u"), "mn2 qb q 0 0 n1 " + mos.format(w="5u"),
+        "mn3 q s 0 0 n1 " + mos.format(w="20u"),
+        "c1 q 0 10f", "c2 qb 0 10f",
+        "r1 dd a 10k", "c3 a 0 50f", "r2 a b 5k", "c4 b 0 20f",
+        "vm b bm dc 0", "r3 bm 0 100k",
+        ".nodeset v(q)=2 v(qb)=0",
+        ".ic v(a)=0.5 v(b)=1.2",
+        ".option klu", ".tran 20p 4n"]) + "\n" + ro_cards() + "\n.end\n"
+
+
 def b3_cards():
     """the level-8 (BSIM3v3.3.0) n1/p1 cards of examples/Monte_Carlo/MC_ring.sp"""
     src = open(os.path.join(REF, "examples/Monte_Carlo/MC_ring.sp")).read()
@@ -258,7 +279,7 @@ def run(name, netlist, calls, save):
     os.makedirs(TMP, exist_ok=True)
     cir = os.path.join(TMP, name + ".cir")
     open(cir, "w").write(netlist)
-    if name in ("ro17", "ro101", "ro17k", "inv", "dio", "b3ring", "arr", "vbic", "mix"):
+    if name in ("ro17", "ro101", "ro17k", "inv", "dio", "b3ring", "arr", "vbic", "mix", "latch"):
         # the netlist itself is kept too: the CPU-baseline arm of bench.py feeds it to oracle/_ref/ngspice
         os.makedirs(os.path.join(HERE, "netlists"), exist_ok=True)
         open(os.path.join(HERE, "netlists", name + ".cir"), "w").write(netlist)
@@ -324,6 +345,8 @@ if __name__ == "__main__":
             run(f"mix{k}", mix_netlist(vdd, r), "0", save)
             for ext in (".flat.ngt", ".trace.ngt.gz"):
                 os.remove(os.path.join(HERE, f"mix{k}" + ext))
+    if "latch" in which:
+        run("latch", latch_netlist(), "0-40,100,101,200", ["q", "qb", "a", "b", "vdd#branch", "vm#branch"])
     if "b3ring" in which:
         run("b3ring", b3_netlist(5), "0-40,300,301,1000,1001", ["out", "buf", "n2", "vdd#branch"])
     if "arr" in which:

@@ -74,6 +74,7 @@ int ngb_launch_assemble(const NgbAsmCtx *c)
     g_launches++;
     const size_t n = (size_t)(c->nnz + c->neq1) * c->S;
     for (size_t u = 0; u < n; u++) ngb_asm_thread(c, u);
+    if (c->nov > 0) { g_launches++; for (int s = 0; s < c->S; s++) ngb_override_thread(c, s); }
     return 0;
 }
 int ngb_launch_lu(const NgbLuCtx *c)

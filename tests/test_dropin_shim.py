@@ -13,7 +13,7 @@ import pytest
 from parity_util import GOLDEN, ROOT
 
 REF = os.path.join(ROOT, "oracle", "_ref", "ngspice")
-NETLISTS = ["ro17k", "inv", "dio", "b3ring", "arr"]
+NETLISTS = ["ro17k", "inv", "dio", "b3ring", "arr", "latch"]
 
 
 def _payload(path):
