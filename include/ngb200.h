@@ -96,6 +96,10 @@ int ngbCircuitAddVbic(ngb_circuit *c, int n, const int *nodes, const int *flags,
 void ngbVbicLayout(int out[5]);
 int ngbCircuitAddVsources(ngb_circuit *c, int n, const int *nodes /* [3][n] pos neg branch */,
                           const int *fn /* [3][n] type order dcGiven */, const double *par /* [9][n] */);
+/* PWL voltage source `inst` (of the ngbCircuitAddVsources table, type 5): the corner list VSRCcoeffs
+ * (ncoef = VSRCfunctionOrder values t0 v0 t1 v1 ...), VSRCrdelay, and VSRCrBreakpt when `r=` makes the list
+ * repeat (-1 otherwise) -- vsrc/vsrcload.c:324-367, breakpoints vsrcacct.c:174-226 */
+int ngbCircuitSetVsourcePwl(ngb_circuit *c, int inst, int ncoef, const double *coef, double rdelay, int rbreakpt);
 int ngbCircuitAddIsources(ngb_circuit *c, int n, const int *nodes /* [2][n] */,
                           const int *fn /* [3][n] */, const double *par /* [10][n] */);
 

@@ -274,6 +274,12 @@ static int flatten_linear(CKTcircuit *ckt)
             }
         rc = ngbCircuitAddVsources(G.C, n, nodes, fn, par); free(nodes); free(fn); free(par);
         if (rc) return rc;
+        i = 0;
+        for (m = (VSRCmodel *)ckt->CKThead[G.tVSRC]; m; m = VSRCnextModel(m))
+            for (h = VSRCinstances(m); h; h = VSRCnextInstance(h), i++)
+                if (h->VSRCfunctionType == PWL &&
+                    (rc = ngbCircuitSetVsourcePwl(G.C, i, h->VSRCfunctionOrder, h->VSRCcoeffs, h->VSRCrdelay, h->VSRCrGiven ? h->VSRCrBreakpt : -1)))
+                    return rc;
     }
     COUNT(ISRC, G.tISRC, n);
     if (n) {

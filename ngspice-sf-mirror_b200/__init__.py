@@ -185,6 +185,13 @@ class Circuit:
         if n:
             lib.check(lib.L.ngbCircuitAddVsources(c.h, int(n), _ip(_i32(flat["vsrc/nodes"])), _ip(_i32(flat["vsrc/fn"])),
                                                   _dp(_f64(flat["vsrc/par"]))), "ngbCircuitAddVsources")
+            if "vsrc/pwl_ptr" in flat:
+                ptr = _i32(flat["vsrc/pwl_ptr"]); co = _f64(flat["vsrc/pwl"])
+                for k in range(int(n)):
+                    if ptr[k + 1] > ptr[k]:
+                        seg = np.ascontiguousarray(co[ptr[k]:ptr[k + 1]])
+                        lib.check(lib.L.ngbCircuitSetVsourcePwl(c.h, k, len(seg), _dp(seg), ctypes.c_double(float(flat["vsrc/pwl_rdelay"][k])),
+                                                                int(flat["vsrc/pwl_rep"][k])), "ngbCircuitSetVsourcePwl")
         n = sc(flat, "isrc/n", 0)
         if n:
             lib.check(lib.L.ngbCircuitAddIsources(c.h, int(n), _ip(_i32(flat["isrc/nodes"])), _ip(_i32(flat["isrc/fn"])),

@@ -13,7 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 
-#define NGB_GROUP_SYNC() do { if (nl <= 32) __syncwarp(); else __syncthreads(); } while (0)
+#define NGB_GROUP_SYNC() do { if (nl <= 32) __syncwarp(ngb_gsync_mask); else __syncthreads(); } while (0)
 #include "ngb_dev.h"
 #include "ngb_kernels.cuh"
 #include "vbic_eval.cuh"
@@ -158,13 +158,17 @@ __global__ void ngb_k_lu_packed(const NgbLuCtx c, int groups, int tpg, int per_s
     __syncthreads();
     const int g = threadIdx.x / tpg, lane = threadIdx.x - g * tpg;
     const int s = blockIdx.x * groups + g;
-    if (s >= c.S) return;
+    /* groups narrower than a warp share it: the lanes of samples that sit this launch out (finished, or on
+     * another pattern set) leave, the others synchronise among themselves */
+    const bool live = g < groups && s < c.S && c.ctl.active[s] && !(c.ctl.lusel && c.ctl.lusel[s] != c.which);
+    const unsigned mask = (tpg <= 32) ? __ballot_sync(0xffffffffu, live) : 0xffffffffu;
+    if (!live) return;
     double *V = smem + blob_doubles + (size_t)g * per_sample_doubles;
     double *Rs = V + h->nV;
     double *Z = Rs + h->n;
     double *As = Z;                 /* unused: A is read from global memory */
     double *P = Z + h->ntask;
-    ngb_lu_sample_packed(&c, sb, s, lane, tpg, V, Rs, Z, As, P);
+    ngb_lu_sample_packed(&c, sb, s, lane, tpg, V, Rs, Z, As, P, mask);
 }
 
 __global__ void __launch_bounds__(128)
@@ -415,7 +419,9 @@ int ngb_launch_lu(const NgbLuCtx *c)
                 if (even >= 4 && even < groups) groups = even;
             }
             const unsigned grid = (unsigned)((c->S + groups - 1) / groups);
-            ngb_k_lu_packed<<<grid, groups * 32, blob + bytes1 * groups, g_stream>>>(*c, groups, 32, per);
+            static int tpg = 0;
+            if (!tpg) { const char *e = getenv("NGB_LU_TPG"); tpg = e ? atoi(e) : 32; if (tpg != 4 && tpg != 8 && tpg != 16) tpg = 32; }
+            ngb_k_lu_packed<<<grid, (groups * tpg + 31) / 32 * 32, blob + bytes1 * groups, g_stream>>>(*c, groups, tpg, per);
             return post_launch("lu_packed");
         }
         if (blob + bytes1 <= (size_t)g_smem_optin) {

@@ -190,6 +190,7 @@ void ngbCircuitDestroy(ngb_circuit *c)
     free(c->vb_nodes); free(c->vb_flags); free(c->vb_par); free(c->vb_aux); free(c->vb_spos);
     free(c->dio_nodes); free(c->dio_flags); free(c->dio_par); free(c->dio_spos);
     free(c->vs_nodes); free(c->vs_fn); free(c->vs_par); free(c->vs_spos); free(c->vs_cspos);
+    free(c->vs_pwl_ptr); free(c->vs_pwl_rep); free(c->vs_pwl_rdelay); free(c->vs_pwl_len); free(c->vs_pwl);
     free(c->is_nodes); free(c->is_fn); free(c->is_par); free(c->is_spos);
     free(c->Ap); free(c->Ai); free(c->eq2col); free(c->col2eq); free(c->slot_diag); free(c->diag_slot);
     free(c->ov_eq); free(c->ov_kind); free(c->ov_cur); free(c->ov_diag); free(c->ov_zptr); free(c->ov_zslot); free(c->ov_val);
@@ -403,8 +404,8 @@ int ngbCircuitAddVsources(ngb_circuit *c, int n, const int *nodes, const int *fn
     int i;
     if (c->finalized || c->vs_n) return NGB_E_PANIC;
     for (i = 0; i < n; i++)
-        if (fn[i] != 0 && fn[i] != NGB_FN_PULSE && fn[i] != NGB_FN_SINE) {
-            ngb_set_error("voltage source %d: waveform type %d not supported (DC, PULSE, SIN)", i, fn[i]);
+        if (fn[i] < 0 || fn[i] > NGB_FN_AM) {
+            ngb_set_error("voltage source %d: waveform type %d not supported (DC, PULSE, SIN, EXP, SFFM, PWL, AM)", i, fn[i]);
             return NGB_E_UNSUPP;
         }
     c->vs_n = n; c->vs_nodes = (int *)xdup(nodes, sizeof(int) * 3 * (size_t)n);
@@ -412,12 +413,34 @@ int ngbCircuitAddVsources(ngb_circuit *c, int n, const int *nodes, const int *fn
     c->vs_par = (double *)xdup(par, sizeof(double) * 9 * (size_t)n);
     return NGB_OK;
 }
+/* corner list of a PWL voltage source (VSRCcoeffs, VSRCfunctionOrder entries: t0 v0 t1 v1 ...), its delay
+ * VSRCrdelay and, for a repeating list, the index VSRCrBreakpt of the corner the repetition restarts from (-1: none) */
+int ngbCircuitSetVsourcePwl(ngb_circuit *c, int inst, int ncoef, const double *coef, double rdelay, int rbreakpt)
+{
+    int i, at;
+    if (c->finalized || inst < 0 || inst >= c->vs_n || ncoef < 2 || (ncoef & 1)) return NGB_E_PANIC;
+    if (!c->vs_pwl_ptr) {
+        c->vs_pwl_ptr = (int *)xcalloc((size_t)c->vs_n + 1, sizeof(int));
+        c->vs_pwl_rep = (int *)xcalloc((size_t)c->vs_n, sizeof(int));
+        c->vs_pwl_rdelay = (double *)xcalloc((size_t)c->vs_n, sizeof(double));
+        c->vs_pwl_len = (int *)xcalloc((size_t)c->vs_n, sizeof(int));
+        for (i = 0; i < c->vs_n; i++) c->vs_pwl_rep[i] = -1;
+    }
+    if (c->vs_pwl_len[inst]) return NGB_E_PANIC;                  /* once per instance */
+    at = c->vs_pwl_n;
+    c->vs_pwl = (double *)realloc(c->vs_pwl, sizeof(double) * (size_t)(at + ncoef));
+    memcpy(c->vs_pwl + at, coef, sizeof(double) * (size_t)ncoef);
+    c->vs_pwl_n = at + ncoef;
+    c->vs_pwl_ptr[inst] = at; c->vs_pwl_len[inst] = ncoef; c->vs_pwl_rdelay[inst] = rdelay; c->vs_pwl_rep[inst] = rbreakpt;
+    c->vs_fn[c->vs_n + inst] = ncoef;                              /* VSRCfunctionOrder */
+    return NGB_OK;
+}
 int ngbCircuitAddIsources(ngb_circuit *c, int n, const int *nodes, const int *fn, const double *par)
 {
     int i;
     if (c->finalized || c->is_n) return NGB_E_PANIC;
     for (i = 0; i < n; i++)
-        if (fn[i] != 0 && fn[i] != NGB_FN_PULSE && fn[i] != NGB_FN_SINE) {
+        if (fn[i] != 0 && fn[i] != NGB_FN_PULSE && fn[i] != NGB_FN_SINE && fn[i] != NGB_FN_EXP) {
             ngb_set_error("current source %d: waveform type %d not supported (DC, PULSE, SIN)", i, fn[i]);
             return NGB_E_UNSUPP;
         }
@@ -1330,6 +1353,12 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
     if (c->vs_n) {
         b->vs_par = (double *)dalloc_rep(b, "vsrc.par", c->vs_par, 9, c->vs_n, S);
         b->vs_fn = (int *)dev_dup(c->vs_fn, sizeof(int) * 3 * (size_t)c->vs_n);
+        if (c->vs_pwl_ptr) {
+            b->vs_pwl_ptr = (int *)dev_dup(c->vs_pwl_ptr, sizeof(int) * ((size_t)c->vs_n + 1));
+            b->vs_pwl_rep = (int *)dev_dup(c->vs_pwl_rep, sizeof(int) * (size_t)c->vs_n);
+            b->vs_pwl_rdelay = (double *)dev_dup(c->vs_pwl_rdelay, sizeof(double) * (size_t)c->vs_n);
+            b->vs_pwl = (double *)dev_dup(c->vs_pwl, sizeof(double) * (size_t)c->vs_pwl_n);
+        }
         b->vs_spos = (int *)dev_dup(c->vs_spos, sizeof(int) * (size_t)c->vs_n);
     }
     if (c->is_n) {
@@ -1412,6 +1441,7 @@ void ngbBatchDestroy(ngb_batch *b)
     ngb_dev_free(b->vb_nodes); ngb_dev_free(b->vb_flags); ngb_dev_free(b->vb_spos);
     ngb_dev_free(b->ov_eq); ngb_dev_free(b->ov_kind); ngb_dev_free(b->ov_cur); ngb_dev_free(b->ov_diag); ngb_dev_free(b->ov_zptr); ngb_dev_free(b->ov_zslot);
     ngb_dev_free(b->b3_mtab); ngb_dev_free(b->b3_ptab); ngb_dev_free(b->b3_prow); ngb_dev_free(b->b3_flags); ngb_dev_free(b->b3_nodes); ngb_dev_free(b->b3_spos);
+    ngb_dev_free(b->vs_pwl_ptr); ngb_dev_free(b->vs_pwl_rep); ngb_dev_free(b->vs_pwl_rdelay); ngb_dev_free(b->vs_pwl);
     ngb_dev_free(b->vs_fn); ngb_dev_free(b->vs_spos); ngb_dev_free(b->is_fn); ngb_dev_free(b->is_spos);
     if (b->have_lu) {
         batch_free_lu(b);
@@ -1525,7 +1555,8 @@ void ngb_fill_srcctx(ngb_batch *b, NgbSrcCtx *x, int is_current)
     memset(x, 0, sizeof *x);
     x->S = b->S; x->is_current = is_current; x->stamp = b->stamp; x->tstep = c->opt.tstep; x->tstop = c->opt.tstop; x->ctl = b->ctl;
     if (is_current) { x->ninst = c->is_n; x->fn = b->is_fn; x->par = b->is_par; x->spos = b->is_spos; }
-    else { x->ninst = c->vs_n; x->fn = b->vs_fn; x->par = b->vs_par; x->spos = b->vs_spos; }
+    else { x->ninst = c->vs_n; x->fn = b->vs_fn; x->par = b->vs_par; x->spos = b->vs_spos;
+           x->pwl_ptr = b->vs_pwl_ptr; x->pwl_rep = b->vs_pwl_rep; x->pwl_rdelay = b->vs_pwl_rdelay; x->pwl = b->vs_pwl; }
     x->T = x->ninst * b->S;
 }
 void ngb_fill_asmctx(ngb_batch *b, NgbAsmCtx *x)

@@ -154,6 +154,67 @@ NGB_HD double ngb_src_value(const NgbSrcCtx *c, size_t t, int inst, int s, int m
             if (time <= 0) value = VO + VA * sin(phase);
             else value = VO + VA * sin(FREQ * time * 2.0 * M_PI + phase) * ngb_exp(-time * THETA);
         } break;
+        case NGB_FN_EXP: {          /* vsrcload.c:203-231 */
+            const double V1 = SCO(0), V2 = SCO(1);
+            const double TD1 = (forder > 2 && SCO(2) != 0.0) ? SCO(2) : c->tstep;
+            const double TAU1 = (forder > 3 && SCO(3) != 0.0) ? SCO(3) : c->tstep;
+            const double TD2 = (forder > 4 && SCO(4) != 0.0) ? SCO(4) : TD1 + c->tstep;
+            const double TAU2 = (forder > 5 && SCO(5) != 0.0) ? SCO(5) : c->tstep;
+            if (time <= TD1) value = V1;
+            else if (time <= TD2) value = V1 + (V2 - V1) * (1 - ngb_exp(-(time - TD1) / TAU1));
+            else value = V1 + (V2 - V1) * (1 - ngb_exp(-(time - TD1) / TAU1)) + (V1 - V2) * (1 - ngb_exp(-(time - TD2) / TAU2));
+        } break;
+        case NGB_FN_SFFM: {         /* vsrcload.c:233-287 */
+            const double VO = SCO(0), VA = SCO(1);
+            const double FC = forder > 2 ? SCO(2) : (5. / c->tstop);
+            double MDI = forder > 3 ? SCO(3) : 90.0;
+            const double FM = (forder > 4 && SCO(4) != 0.0) ? SCO(4) : (500. / c->tstop);
+            const double TD = forder > 5 ? SCO(5) : 0;
+            const double phasem = (forder > 6 ? SCO(6) : 0.0) * M_PI / 180.0;
+            const double phasec = (forder > 7 ? SCO(7) : 0.0) * M_PI / 180.0;
+            if (MDI > FC / FM) MDI = FC / FM; else if (MDI < 0) MDI = 0;
+            time -= TD;
+            if (time <= 0) value = 0;
+            else value = VO + VA * sin((2.0 * M_PI * FC * time + phasec) + MDI * sin(2.0 * M_PI * FM * time + phasem));
+        } break;
+        case NGB_FN_AM: {           /* vsrcload.c:288-322 */
+            const double VO = SCO(0), VMO = SCO(1);
+            const double VMA = forder > 2 ? SCO(2) : 1.;
+            const double FM = forder > 3 ? SCO(3) : (5. / c->tstop);
+            const double FC = forder > 4 ? SCO(4) : (500. / c->tstop);
+            const double TD = forder > 5 ? SCO(5) : 0.0;
+            const double phasem = (forder > 6 ? SCO(6) : 0.0) * M_PI / 180.0;
+            const double phasec = (forder > 7 ? SCO(7) : 0.0) * M_PI / 180.0;
+            time -= TD;
+            if (time <= 0) value = 0;
+            else value = VO + (VMO + VMA * sin(2.0 * M_PI * FM * time + phasem)) * sin(2.0 * M_PI * FC * time + phasec);
+        } break;
+        case NGB_FN_PWL: {          /* vsrcload.c:324-367; forder = number of list entries */
+            const double *co = c->pwl + NGB_LDG(&c->pwl_ptr[inst]);
+            const int rep = NGB_LDG(&c->pwl_rep[inst]);
+            time -= NGB_LDG(&c->pwl_rdelay[inst]);
+            if (time <= NGB_LDG(&co[0])) { value = NGB_LDG(&co[1]); break; }
+            const double end_time = NGB_LDG(&co[forder - 2]);
+            if (time > end_time) {
+                if (rep >= 0) {
+                    const double period = end_time - NGB_LDG(&co[rep]);
+                    time -= NGB_LDG(&co[rep]);
+                    time -= period * floor(time / period);
+                    time += NGB_LDG(&co[rep]);
+                } else { value = NGB_LDG(&co[forder - 1]); break; }
+            }
+            value = dc;
+            for (int i = 2; i < forder; i += 2) {
+                const double itime = NGB_LDG(&co[i]);
+                if (itime >= time) {
+                    time -= NGB_LDG(&co[i - 2]);
+                    time /= NGB_LDG(&co[i]) - NGB_LDG(&co[i - 2]);
+                    value = NGB_LDG(&co[i - 1]);
+                    value += time * (NGB_LDG(&co[i + 1]) - NGB_LDG(&co[i - 1]));
+                    break;
+                }
+            }
+        } break;
         }
     }
 #undef SCO
@@ -259,6 +320,7 @@ NGB_HD void ngb_override_thread(const NgbAsmCtx *c, int s)
  * on the device): V[nV], Rs[n], Z[ntask]. */
 NGB_HD void ngb_lu_sample(const NgbLuCtx *c, int s, int lane, int nl, double *V, double *Rs, double *Z)
 {
+    const unsigned ngb_gsync_mask = 0xffffffffu; (void)ngb_gsync_mask;
     const NgbLuSched *h = &c->sch;
     const int S = c->S, n = h->n, nV = h->nV;
     const int active = NGB_LDG(&c->ctl.active[s]);
@@ -391,8 +453,9 @@ NGB_HD void ngb_lu_sample(const NgbLuCtx *c, int s, int lane, int nl, double *V,
  * (P), then per entry the subtractions in KLU's order.  The long rows (a supply node touches every
  * stage) would otherwise keep one lane busy with index loads and multiplies while 31 wait. */
 NGB_HD void ngb_lu_sample_packed(const NgbLuCtx *c, const unsigned short *sb, int s, int lane, int nl,
-                                 double *V, double *Rs, double *Z, double *As, double *P)
+                                 double *V, double *Rs, double *Z, double *As, double *P, unsigned ngb_gsync_mask)
 {
+    (void)ngb_gsync_mask;
     const NgbLuPacked *h = &c->pk;
     const int S = c->S, n = h->n, nV = h->nV;
     if (!NGB_LDG(&c->ctl.active[s])) return;

@@ -204,7 +204,30 @@ NGB_HD int ngb_src_accept(const NgbTranCtx *c, const NgbSrcCtx *sc, double *brk,
                 { const int e = ngb_set_break(c, s, brk[t], now); if (e) return e; }
                 brk[t] -= c->minbreak;
             }
-        } else if (ftype != 0 && ftype != NGB_FN_SINE) {
+        } else if (ftype == NGB_FN_PWL) {       /* vsrcacct.c:174-226 */
+            if (now >= brk[t]) {
+                const double *co = sc->pwl + NGB_LDG(&sc->pwl_ptr[inst]);
+                const int rep = NGB_LDG(&sc->pwl_rep[inst]);
+                double time = now - NGB_LDG(&sc->pwl_rdelay[inst]);
+                const double end = NGB_LDG(&co[forder - 2]);
+                if (time > end) {
+                    if (rep >= 0) {
+                        const double period = end - NGB_LDG(&co[rep]);
+                        time -= NGB_LDG(&co[rep]);
+                        time -= period * floor(time / period);
+                        time += NGB_LDG(&co[rep]);
+                    } else { brk[t] = c->tstop; continue; }
+                }
+                const double atime = time + c->minbreak;
+                for (int i = 0; i < forder; i += 2)
+                    if (NGB_LDG(&co[i]) > atime) {
+                        brk[t] = now + NGB_LDG(&co[i]) - time;
+                        { const int e = ngb_set_break(c, s, brk[t], now); if (e) return e; }
+                        brk[t] -= c->minbreak;
+                        break;
+                    }
+            }
+        } else if (ftype != 0 && ftype != NGB_FN_SINE && ftype != NGB_FN_EXP && ftype != NGB_FN_SFFM && ftype != NGB_FN_AM) {
             return NGB_E_UNSUPP;
         }
 #undef SCO

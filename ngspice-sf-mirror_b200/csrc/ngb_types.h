@@ -54,6 +54,10 @@ typedef struct NgbCtl {
 /* source waveform codes (vsrcdefs.h:146-160) */
 #define NGB_FN_PULSE 1
 #define NGB_FN_SINE  2
+#define NGB_FN_EXP   3
+#define NGB_FN_SFFM  4
+#define NGB_FN_PWL   5
+#define NGB_FN_AM    6
 
 /* circuit-wide scalars */
 typedef struct NgbOpts {
@@ -82,6 +86,10 @@ typedef struct NgbSrcCtx {
     const int *spos;        /* VSRC [1][ninst] rhs_branch ; ISRC [2][ninst] rhs_pos rhs_neg */
     double *stamp;
     double tstep, tstop;    /* CKTstep, CKTfinalTime (PULSE/SINE defaults)               */
+    /* PWL sources: corner lists t0 v0 t1 v1 ... (shared by the samples), pwl_ptr [ninst+1] into pwl;
+     * pwl_rdelay [ninst] = VSRCrdelay, pwl_rep [ninst] = VSRCrBreakpt when the list repeats, else -1 */
+    const int *pwl_ptr, *pwl_rep;
+    const double *pwl, *pwl_rdelay;
     NgbCtl ctl;
 } NgbSrcCtx;
 

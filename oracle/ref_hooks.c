@@ -272,6 +272,27 @@ static void dump_linear(FILE *f, CKTcircuit *ckt, KLUmatrix *K)
                 }
             put_i2(f, "vsrc/nodes", nodes, 3, n); put_i2(f, "vsrc/slots", slots, 4, n);
             put_i2(f, "vsrc/fn", fn, 3, n); put_d2(f, "vsrc/par", par, 9, n);
+            {   /* PWL corner lists */
+                int *ptr = (int *)calloc((size_t)n + 1, sizeof(int)), *rep = (int *)calloc((size_t)n, sizeof(int)), tot = 0, any = 0;
+                double *rd = (double *)calloc((size_t)n, sizeof(double)), *co;
+                i = 0;
+                for (m = (VSRCmodel *)ckt->CKThead[vsrc_type]; m; m = VSRCnextModel(m))
+                    for (h = VSRCinstances(m); h; h = VSRCnextInstance(h), i++) {
+                        ptr[i] = tot; rep[i] = -1;
+                        if (h->VSRCfunctionType == PWL) { tot += h->VSRCfunctionOrder; any = 1; rd[i] = h->VSRCrdelay; if (h->VSRCrGiven) rep[i] = h->VSRCrBreakpt; }
+                    }
+                ptr[n] = tot;
+                if (any) {
+                    co = (double *)calloc((size_t)tot + 1, sizeof(double)); i = 0;
+                    for (m = (VSRCmodel *)ckt->CKThead[vsrc_type]; m; m = VSRCnextModel(m))
+                        for (h = VSRCinstances(m); h; h = VSRCnextInstance(h), i++)
+                            if (h->VSRCfunctionType == PWL) memcpy(co + ptr[i], h->VSRCcoeffs, sizeof(double) * (size_t)h->VSRCfunctionOrder);
+                    put_i1(f, "vsrc/pwl_ptr", ptr, (long long)n + 1); put_i1(f, "vsrc/pwl_rep", rep, n);
+                    put_d1(f, "vsrc/pwl_rdelay", rd, n); put_d1(f, "vsrc/pwl", co, tot);
+                    free(co);
+                }
+                free(ptr); free(rep); free(rd);
+            }
             free(nodes); free(slots); free(fn); free(par);
         }
     }

@@ -214,6 +214,28 @@ def latch_netlist():
         ".option klu", ".tran 20p 4n"]) + "\n" + ro_cards() + "\n.end\n"
 
 
+def srcs_netlist():
+    """every independent-source waveform of the path: PWL (plain, delayed, repeating), EXP, SFFM and AM voltage
+    sources and an EXP current source, each into an RC section; a BSIM4 inverter on the PWL input"""
+    mos = "l=0.1u w={w} ad=5p pd=6u as=5p ps=6u"
+    return "\n".join([
+        "* source waveforms: PWL / EXP / SFFM / AM",
+        "vdd dd 0 dc 2.0",
+        "v1 a 0 pwl(0 0 0.5n 0 0.7n 2 1.5n 2 1.6n 0.4 3n 1.2)",
+        "mp1 y a dd dd p1 " + mos.format(w="10u"), "mn1 y a 0 0 n1 " + mos.format(w="5u"), "c1 y 0 20f",
+        "v2 b 0 pwl(0 0 0.2n 1 0.5n 1 0.6n 0) r=0.2n td=0.3n",
+        "r2 b b2 1k", "c2 b2 0 0.1p",
+        "v3 c 0 exp(0 1.5 0.2n 0.3n 1.5n 0.4n)",
+        "r3 c c2 2k", "c3 c2 0 50f",
+        "v4 d 0 sffm(0.5 0.4 2g 3 0.4g)",
+        "r4 d d2 500", "c4 d2 0 20f",
+        "v5 e 0 am(0.2 1 0.8 0.5g 3g 0.1n)",
+        "r5 e e2 500", "c5 e2 0 20f",
+        "i6 0 f exp(0 1m 0.5n 0.2n 2n 0.3n)",
+        "r6 f 0 1k", "c6 f 0 0.2p",
+        ".option klu", ".tran 10p 4n"]) + "\n" + ro_cards() + "\n.end\n"
+
+
 def b3_cards():
     """the level-8 (BSIM3v3.3.0) n1/p1 cards of examples/Monte_Carlo/MC_ring.sp"""
     src = open(os.path.join(REF, "examples/Monte_Carlo/MC_ring.sp")).read()
@@ -279,7 +301,7 @@ def run(name, netlist, calls, save):
     os.makedirs(TMP, exist_ok=True)
     cir = os.path.join(TMP, name + ".cir")
     open(cir, "w").write(netlist)
-    if name in ("ro17", "ro101", "ro17k", "inv", "dio", "b3ring", "arr", "vbic", "mix", "latch"):
+    if name in ("ro17", "ro101", "ro17k", "inv", "dio", "b3ring", "arr", "vbic", "mix", "latch", "srcs"):
         # the netlist itself is kept too: the CPU-baseline arm of bench.py feeds it to oracle/_ref/ngspice
         os.makedirs(os.path.join(HERE, "netlists"), exist_ok=True)
         open(os.path.join(HERE, "netlists", name + ".cir"), "w").write(netlist)
@@ -347,6 +369,8 @@ if __name__ == "__main__":
                 os.remove(os.path.join(HERE, f"mix{k}" + ext))
     if "latch" in which:
         run("latch", latch_netlist(), "0-40,100,101,200", ["q", "qb", "a", "b", "vdd#branch", "vm#branch"])
+    if "srcs" in which:
+        run("srcs", srcs_netlist(), "0-20,100,101,300", ["y", "b2", "c2", "d2", "e2", "f", "v1#branch"])
     if "b3ring" in which:
         run("b3ring", b3_netlist(5), "0-40,300,301,1000,1001", ["out", "buf", "n2", "vdd#branch"])
     if "arr" in which:

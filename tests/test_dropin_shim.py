@@ -13,7 +13,7 @@ import pytest
 from parity_util import GOLDEN, ROOT
 
 REF = os.path.join(ROOT, "oracle", "_ref", "ngspice")
-NETLISTS = ["ro17k", "inv", "dio", "b3ring", "arr", "latch"]
+NETLISTS = ["ro17k", "inv", "dio", "b3ring", "arr", "latch", "srcs"]
 
 
 def _payload(path):
@@ -81,7 +81,7 @@ def test_dropin_gpu_vbic_rawfile(name):
 @pytest.mark.parametrize("name", NETLISTS)
 def test_dropin_gpu_rawfile(name):
     v0, v1 = _check(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb"), name, "cuda-sm_100a")
-    if name == "dio":           # SIN source: CUDA's sin() is not glibc's; the north_star tolerance applies
+    if name in ("dio", "srcs"):   # SIN / SFFM / AM sources: CUDA's sin() is not glibc's; the north_star tolerance applies
         assert np.max(np.abs(v0 - v1) / np.maximum(np.abs(v0), 1e-6)) <= 1e-9
     else:
         assert np.array_equal(v0, v1)

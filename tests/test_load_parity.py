@@ -11,7 +11,7 @@ import pytest
 from parity_util import GOLDEN, ngt, pkg, relerr, replay_load, trace_calls, first_pattern
 
 DUAL = ("vbic", "mix")      # fixtures holding VBIC devices: derivatives by dual numbers, see vbic_eval.cuh
-CASES = ["ro17", "ro101", "inv", "dio", "b3ring", "vbic", "mix", "latch"]   # latch: .nodeset / .ic row overrides      # inv: DC operating point (INITJCT/INITFIX/INITFLOAT) + PULSE transient
+CASES = ["ro17", "ro101", "inv", "dio", "b3ring", "vbic", "mix", "latch", "srcs"]   # latch: .nodeset / .ic row overrides; srcs: PWL / EXP / SFFM / AM sources      # inv: DC operating point (INITJCT/INITFIX/INITFLOAT) + PULSE transient
 
 
 def _load_case(name):

@@ -40,7 +40,7 @@ def _compare(res, t, v, wave, s, exact, tol=1e-9, same_route=True):
         assert (err <= tol).all(), err
 
 
-@pytest.mark.parametrize("name", ["ro17", "ro17k", "inv", "dio", "b3ring", "latch"])
+@pytest.mark.parametrize("name", ["ro17", "ro17k", "inv", "dio", "b3ring", "latch", "srcs"])
 def test_tran_hostsim_bit_identical(hostsim_lib, name):
     res, t, v, wave = _run(hostsim_lib, name)
     _compare(res, t, v, wave, 0, exact=True)
@@ -131,7 +131,7 @@ def test_tran_hostsim_mc_batch(hostsim_lib):
 # device follows the reference bit for bit; the assertions below allow 1e-9 (the north_star
 # tolerance) but identical accepted / rejected / iteration counts are required.
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,exact", [("ro17k", True), ("ro17", True), ("inv", True), ("dio", False), ("b3ring", True), ("vbic", False), ("latch", True)])
+@pytest.mark.parametrize("name,exact", [("ro17k", True), ("ro17", True), ("inv", True), ("dio", False), ("b3ring", True), ("vbic", False), ("latch", True), ("srcs", False)])
 def test_tran_gpu_matches_reference(cuda_lib, name, exact):
     """north_star bar: 1e-9 relative and identical accepted-step count; the device arithmetic
     (no FMA contraction, glibc-compatible exp/log) in fact reproduces the reference bit for bit.
