@@ -674,7 +674,7 @@ def bench_sweep(args):
         # algorithmic bytes of one Newton step of one point: the four load kernels' tables, states and stamps
         # (BSIM4 2 000 B, BSIM3 1 400 B, VBIC 3 400 B, diode 700 B per evaluation)
         bytes_step = SWEEP_COUNTS["bsim4"] * 2000 + SWEEP_COUNTS["bsim3"] * 1400 + SWEEP_COUNTS["vbic"] * 3400 + SWEEP_COUNTS["diode"] * 700
-        achieved = iters_tot * bytes_step / (ms_max * 1e-3) / 1e9
+        achieved = iters_tot * bytes_step / (ms_max * 1e-3) / 1e9 / world          # per GPU
         cpu = sweep_cpu_baseline(os.cpu_count() or 1)
         line = {
             "metric": "sweep points/s", "value": points_tot / (ms_max * 1e-3), "unit": "points/s", "n_gpus": world,
