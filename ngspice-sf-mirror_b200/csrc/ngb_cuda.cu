@@ -143,17 +143,20 @@ __global__ void ngb_k_lu_block(const NgbLuCtx c)
     ngb_lu_sample(&c, s, threadIdx.x, blockDim.x, V, Rs, Z);
 }
 
-/* packed schedule in shared memory: `groups` samples per CTA, `tpg` threads per sample */
+/* packed schedule in shared memory: `groups` samples per CTA, `tpg` threads per sample;
+ * v2 selects the record packing (ngb_lu_sample_pk2) */
+template <int V2>
 __global__ void ngb_k_lu_packed(const NgbLuCtx c, int groups, int tpg, int per_sample_doubles)
 {
     extern __shared__ double smem[];
     const NgbLuPacked *h = &c.pk;
     unsigned short *sb = reinterpret_cast<unsigned short *>(smem);
-    const int blob_doubles = (h->blob_u16 + 3) / 4;
+    const int blob_u16 = V2 ? h->blob2_u16 : h->blob_u16;
+    const int blob_doubles = (blob_u16 + 3) / 4;
     {   /* one coalesced copy of the schedule per CTA */
-        const unsigned *src = reinterpret_cast<const unsigned *>(h->blob);
+        const unsigned *src = reinterpret_cast<const unsigned *>(V2 ? h->blob2 : h->blob);
         unsigned *dst = reinterpret_cast<unsigned *>(smem);
-        for (int i = threadIdx.x; i < h->blob_u16 / 2; i += blockDim.x) dst[i] = __ldg(&src[i]);
+        for (int i = threadIdx.x; i < blob_u16 / 2; i += blockDim.x) dst[i] = __ldg(&src[i]);
     }
     __syncthreads();
     const int g = threadIdx.x / tpg, lane = threadIdx.x - g * tpg;
@@ -166,9 +169,12 @@ __global__ void ngb_k_lu_packed(const NgbLuCtx c, int groups, int tpg, int per_s
     double *V = smem + blob_doubles + (size_t)g * per_sample_doubles;
     double *Rs = V + h->nV;
     double *Z = Rs + h->n;
-    double *As = Z;                 /* unused: A is read from global memory */
     double *P = Z + h->ntask;
-    ngb_lu_sample_packed(&c, sb, s, lane, tpg, V, Rs, Z, As, P, mask);
+    if (V2) {
+        if (tpg == 32) ngb_lu_sample_pk2(&c, sb, s, lane, 32, V, Rs, Z, P, mask);     /* the common case with a constant stride */
+        else ngb_lu_sample_pk2(&c, sb, s, lane, tpg, V, Rs, Z, P, mask);
+    }
+    else ngb_lu_sample_packed(&c, sb, s, lane, tpg, V, Rs, Z, Z /* unused: A is read from global memory */, P, mask);
 }
 
 __global__ void __launch_bounds__(128)
@@ -210,7 +216,8 @@ int ngb_dev_init(int device)
     CUDA_OK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_OK(cudaFuncSetAttribute(ngb_k_lu_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
     CUDA_OK(cudaFuncSetAttribute(ngb_k_lu_block, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
-    CUDA_OK(cudaFuncSetAttribute(ngb_k_lu_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
+    CUDA_OK(cudaFuncSetAttribute(ngb_k_lu_packed<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
+    CUDA_OK(cudaFuncSetAttribute(ngb_k_lu_packed<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
     g_device = device;
     return 0;
 }
@@ -407,7 +414,10 @@ int ngb_launch_lu(const NgbLuCtx *c)
         /* schedule blob + per-sample values in shared memory.  Many samples: one warp each, one CTA
          * per SM holding as many samples as its shared memory takes (the blob is paid once per CTA);
          * few samples: one CTA of 256 threads per sample. */
-        const size_t blob = (size_t)((c->pk.blob_u16 + 3) / 4) * sizeof(double);
+        static int v1 = -1;
+        if (v1 < 0) { const char *e = getenv("NGB_LU_V1"); v1 = (e && atoi(e)) ? 1 : 0; }   /* first packing, for comparison */
+        const int v2 = c->pk.ok2 && !v1;
+        const size_t blob = (size_t)(((v2 ? c->pk.blob2_u16 : c->pk.blob_u16) + 3) / 4) * sizeof(double);
         const size_t budget = (size_t)g_smem_optin - 1024;
         if (c->S >= 64 && blob + 4 * bytes1 <= budget) {
             int groups = (int)((budget - blob) / bytes1);
@@ -421,11 +431,13 @@ int ngb_launch_lu(const NgbLuCtx *c)
             const unsigned grid = (unsigned)((c->S + groups - 1) / groups);
             static int tpg = 0;
             if (!tpg) { const char *e = getenv("NGB_LU_TPG"); tpg = e ? atoi(e) : 32; if (tpg != 4 && tpg != 8 && tpg != 16) tpg = 32; }
-            ngb_k_lu_packed<<<grid, (groups * tpg + 31) / 32 * 32, blob + bytes1 * groups, g_stream>>>(*c, groups, tpg, per);
+            if (v2) ngb_k_lu_packed<1><<<grid, (groups * tpg + 31) / 32 * 32, blob + bytes1 * groups, g_stream>>>(*c, groups, tpg, per);
+            else ngb_k_lu_packed<0><<<grid, (groups * tpg + 31) / 32 * 32, blob + bytes1 * groups, g_stream>>>(*c, groups, tpg, per);
             return post_launch("lu_packed");
         }
         if (blob + bytes1 <= (size_t)g_smem_optin) {
-            ngb_k_lu_packed<<<(unsigned)c->S, 256, blob + bytes1, g_stream>>>(*c, 1, 256, per);
+            if (v2) ngb_k_lu_packed<1><<<(unsigned)c->S, 256, blob + bytes1, g_stream>>>(*c, 1, 256, per);
+            else ngb_k_lu_packed<0><<<(unsigned)c->S, 256, blob + bytes1, g_stream>>>(*c, 1, 256, per);
             return post_launch("lu_packed");
         }
     }

@@ -786,7 +786,7 @@ int ngbCircuitGetBsim4Slots(const ngb_circuit *c, int *slots)
 /* ------------------------------------------------------------------ LU task schedule */
 static void free_packed(NgbLuPacked *p)
 {
-    free((void *)p->blob); free((void *)p->aslot); free((void *)p->arow); free((void *)p->ext);
+    free((void *)p->blob); free((void *)p->blob2); free((void *)p->aslot); free((void *)p->arow); free((void *)p->ext);
     memset(p, 0, sizeof *p);
 }
 
@@ -861,9 +861,119 @@ static void build_packed(ngb_circuit *c)
         const int np_lev = b[p->o_tpptr + h->slev_ptr[k + 1]] - b[p->o_tpptr + h->slev_ptr[k]];
         if (np_lev > p->maxlp) p->maxlp = np_lev;
     }
+    if (getenv("NGB_LU_STATS")) {          /* development aid: shape of the level schedule */
+        int sum_max = 0, sum_prod = 0, e2;
+        for (k = 0; k < h->nlev; k++) {
+            int mx = 0;
+            for (e2 = h->lev_ptr[k]; e2 < h->lev_ptr[k + 1]; e2++) { int cnt = b[p->o_pptr + e2 + 1] - b[p->o_pptr + e2]; if (cnt > mx) mx = cnt; }
+            fprintf(stderr, "lu level %d: %d values, %d products, longest row %d\n", k, h->lev_ptr[k + 1] - h->lev_ptr[k],
+                    b[p->o_pptr + h->lev_ptr[k + 1]] - b[p->o_pptr + h->lev_ptr[k]], mx);
+            sum_max += mx; sum_prod += b[p->o_pptr + h->lev_ptr[k + 1]] - b[p->o_pptr + h->lev_ptr[k]];
+        }
+        fprintf(stderr, "lu factor: %d levels, %d values, %d products, sum of longest rows %d\n", h->nlev, nV, sum_prod, sum_max);
+        sum_max = 0; sum_prod = 0;
+        for (k = 0; k < h->nslev; k++) {
+            int mx = 0;
+            for (e2 = h->slev_ptr[k]; e2 < h->slev_ptr[k + 1]; e2++) { int cnt = b[p->o_tpptr + e2 + 1] - b[p->o_tpptr + e2]; if (cnt > mx) mx = cnt; }
+            fprintf(stderr, "solve level %d: %d tasks, %d products, longest row %d\n", k, h->slev_ptr[k + 1] - h->slev_ptr[k],
+                    b[p->o_tpptr + h->slev_ptr[k + 1]] - b[p->o_tpptr + h->slev_ptr[k]], mx);
+            sum_max += mx; sum_prod += b[p->o_tpptr + h->slev_ptr[k + 1]] - b[p->o_tpptr + h->slev_ptr[k]];
+        }
+        fprintf(stderr, "lu solve: %d levels, %d tasks, %d products, sum of longest rows %d, blob %d u16\n", h->nslev, ntask, sum_prod, sum_max, off);
+    }
     p->blob = b; p->aslot = aslot; p->arow = arow; p->ext = ext;
     p->row_ptr = h->row_ptr; p->row_slot = h->row_slot; p->b_eq = h->b_eq; p->out_eq = h->out_eq;
     p->ok = 1;
+    /* ---- second packing: records instead of parallel index arrays (ngb_lu_sample_pk2) ---- */
+    do {
+        const int neq1 = c->neq + 1;
+        int off2 = 0, lev0 = 0, slev0 = 0, e0, e2, *eqtask;
+        unsigned short *b2;
+        if (neq1 >= 65535) break;
+        /* leading levels whose entries have neither products nor a pivot division stay as initialised */
+        while (lev0 < h->nlev) {
+            int work = 0;
+            for (e2 = h->lev_ptr[lev0]; e2 < h->lev_ptr[lev0 + 1]; e2++)
+                if (b[p->o_pptr + e2 + 1] != b[p->o_pptr + e2] || b[p->o_div + e2] != 0xFFFF) work = 1;
+            if (work) break;
+            lev0++;
+        }
+        while (slev0 < h->nslev) {
+            int work = 0;
+            for (e2 = h->slev_ptr[slev0]; e2 < h->slev_ptr[slev0 + 1]; e2++)
+                if (b[p->o_tpptr + e2 + 1] != b[p->o_tpptr + e2] || b[p->o_kind + e2] != 0) work = 1;
+            if (work) break;
+            slev0++;
+        }
+        e0 = h->lev_ptr[lev0];
+        eqtask = (int *)xcalloc((size_t)neq1, sizeof(int));
+        for (k = 0; k < neq1; k++) eqtask[k] = 0xFFFF;
+        for (k = 0; k < n; k++) {
+            const int eq = h->out_eq[k];
+            if (eq <= 0) continue;
+            if (eq >= neq1 || eqtask[eq] != 0xFFFF) { eqtask[0] = -1; break; }     /* not a one-to-one map: first packing only */
+            eqtask[eq] = tint[h->out_task[k]];
+        }
+        if (eqtask[0] == -1) { free(eqtask); break; }
+#define SEG2(field, cnt, width) off2 = (off2 + 3) & ~3; p->field = off2; off2 += (cnt) * (width)
+        SEG2(o2_levd, h->nlev, 4); SEG2(o2_emeta, nV - e0, 4); SEG2(o2_pair, np, 2); SEG2(o2_diag, n, 1);
+        SEG2(o2_slotmap, h->nnz, 2); SEG2(o2_rowptr, n + 1, 1); SEG2(o2_rowv, h->nnz, 1);
+        SEG2(o2_slevd, h->nslev, 4); SEG2(o2_tmeta, ntask, 4); SEG2(o2_tpair, nsp, 2);
+        SEG2(o2_yinit, n, 4); SEG2(o2_eqtask, neq1, 1);
+#undef SEG2
+        off2 = (off2 + 3) & ~3;
+        b2 = (unsigned short *)xcalloc((size_t)off2 + 4, sizeof(unsigned short));
+        for (k = 0; k < h->nlev; k++) {
+            unsigned short *r = b2 + p->o2_levd + 4 * k;
+            r[0] = (unsigned short)h->lev_ptr[k]; r[1] = (unsigned short)h->lev_ptr[k + 1];
+            r[2] = b[p->o_pptr + h->lev_ptr[k]]; r[3] = b[p->o_pptr + h->lev_ptr[k + 1]];
+        }
+        for (k = e0; k < nV; k++) {
+            unsigned short *r = b2 + p->o2_emeta + 4 * (k - e0);
+            r[0] = b[p->o_pptr + k]; r[1] = b[p->o_pptr + k + 1]; r[2] = b[p->o_div + k]; r[3] = 0;
+        }
+        for (k = 0; k < np; k++) { b2[p->o2_pair + 2 * k] = b[p->o_pl + k]; b2[p->o2_pair + 2 * k + 1] = b[p->o_pu + k]; }
+        for (k = 0; k < n; k++) b2[p->o2_diag + k] = b[p->o_diag + k];
+        for (k = 0; k < h->nnz; k++) { b2[p->o2_slotmap + 2 * k] = 0xFFFF; b2[p->o2_slotmap + 2 * k + 1] = 0; }
+        for (k = 0; k < nV; k++)
+            if (aslot[k] >= 0) { b2[p->o2_slotmap + 2 * aslot[k]] = (unsigned short)k; b2[p->o2_slotmap + 2 * aslot[k] + 1] = (unsigned short)arow[k]; }
+        for (k = 0; k <= n; k++) b2[p->o2_rowptr + k] = (unsigned short)h->row_ptr[k];
+        {
+            int bad = 0;
+            for (k = 0; k < h->nnz; k++) {
+                const int v = b2[p->o2_slotmap + 2 * h->row_slot[k]];
+                if (v == 0xFFFF) bad = 1;               /* an entry of A outside the factors: first packing only */
+                b2[p->o2_rowv + k] = (unsigned short)v;
+            }
+            if (bad) { free(b2); free(eqtask); break; }
+        }
+        for (k = 0; k < h->nslev; k++) {
+            unsigned short *r = b2 + p->o2_slevd + 4 * k;
+            r[0] = (unsigned short)h->slev_ptr[k]; r[1] = (unsigned short)h->slev_ptr[k + 1];
+            r[2] = b[p->o_tpptr + h->slev_ptr[k]]; r[3] = b[p->o_tpptr + h->slev_ptr[k + 1]];
+        }
+        q = 0;
+        for (k = 0; k < ntask; k++) {
+            unsigned short *r = b2 + p->o2_tmeta + 4 * k;
+            const int kind = b[p->o_kind + k];
+            r[0] = b[p->o_tpptr + k]; r[1] = b[p->o_tpptr + k + 1];
+            r[2] = (unsigned short)(kind == 0 ? k : b[p->o_init + k]);
+            r[3] = (unsigned short)(kind == 1 ? b[p->o_tdiv + k] : 0xFFFF);
+            if (kind == 0) {
+                unsigned short *y = b2 + p->o2_yinit + 4 * q;
+                const int row = b[p->o_init + k];
+                if (q >= n) { q = n + 1; break; }
+                y[0] = (unsigned short)k; y[1] = (unsigned short)row; y[2] = (unsigned short)h->b_eq[row]; y[3] = 0;
+                q++;
+            }
+        }
+        if (q != n) { free(b2); free(eqtask); break; }
+        for (k = 0; k < nsp; k++) { b2[p->o2_tpair + 2 * k] = b[p->o_tval + k]; b2[p->o2_tpair + 2 * k + 1] = b[p->o_tsrc + k]; }
+        for (k = 0; k < neq1; k++) b2[p->o2_eqtask + k] = (unsigned short)eqtask[k];
+        free(eqtask);
+        p->lev0 = lev0; p->e0 = e0; p->slev0 = slev0; p->blob2 = b2; p->blob2_u16 = off2; p->ok2 = 1;
+        if (getenv("NGB_LU_STATS")) fprintf(stderr, "lu second packing: %d u16, first factor level %d (value %d), first solve level %d\n", off2, lev0, e0, slev0);
+    } while (0);
     free(vint); free(tint);
 }
 
@@ -1216,6 +1326,7 @@ static void packed_to_dev(ngb_batch *b, const ngb_circuit *c, int w)
     d->aslot = (const int *)dev_dup(p->aslot, sizeof(int) * (size_t)p->nV);
     d->arow = (const int *)dev_dup(p->arow, sizeof(int) * (size_t)p->nV);
     d->ext = (const int *)dev_dup(p->ext, sizeof(int) * (size_t)p->nV);
+    if (p->ok2) d->blob2 = (const unsigned short *)dev_dup(p->blob2, sizeof(unsigned short) * (size_t)p->blob2_u16);
     d->row_ptr = b->dlu[w].dsch.row_ptr; d->row_slot = b->dlu[w].dsch.row_slot; d->b_eq = b->dlu[w].dsch.b_eq; d->out_eq = b->dlu[w].dsch.out_eq;
 }
 static void sched_dev_free(NgbLuSched *d)
@@ -1390,6 +1501,7 @@ static void batch_free_lu(ngb_batch *b)
     int w;
     for (w = 0; w < NGB_LU_SETS; w++)
         if (b->dlu[w].valid) {
+            if (b->dlu[w].dpk.ok2) ngb_dev_free((void *)b->dlu[w].dpk.blob2);
             if (b->dlu[w].dpk.ok) { ngb_dev_free((void *)b->dlu[w].dpk.blob); ngb_dev_free((void *)b->dlu[w].dpk.aslot);
                                     ngb_dev_free((void *)b->dlu[w].dpk.arow); ngb_dev_free((void *)b->dlu[w].dpk.ext); }
             sched_dev_free(&b->dlu[w].dsch);

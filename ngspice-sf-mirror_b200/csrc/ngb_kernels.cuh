@@ -594,4 +594,212 @@ NGB_HD void ngb_lu_sample_packed(const NgbLuCtx *c, const unsigned short *sb, in
     }
 }
 
+/* ---- second packing: records (NgbLuPacked o2_*) ------------------------------------------------
+ * Same arithmetic, same order of operations per value as ngb_lu_sample_packed (and therefore as
+ * klu_refactor / klu_solve); what changes is how a warp gets to its operands:
+ *   - the sample's matrix is read once, slot-parallel and coalesced, straight into the value array;
+ *     row maxima and the division by them then work on shared memory only (the first packing walked
+ *     the CSR rows with one dependent global load per entry);
+ *   - a level, a value and a solve task are one 8-byte record each and a product is one 4-byte word,
+ *     so every step of a level costs one index load instead of two to four dependent ones;
+ *   - levels whose entries need no arithmetic (level 0 of the factorisation and of the solve) are
+ *     not visited;
+ *   - the solution is written, zero-filled and tested for convergence in one pass over the equations. */
+#ifdef __CUDACC__
+#define NGB_UNROLL _Pragma("unroll")
+#define NGB_UNROLL4 _Pragma("unroll 4")
+#else
+#define NGB_UNROLL
+#define NGB_UNROLL4
+#endif
+#ifdef __CUDA_ARCH__
+#define NGB_DMUL(a, b) __dmul_rn((a), (b))
+#define NGB_DSUB(a, b) __dsub_rn((a), (b))
+#else
+static inline double ngb_host_dmul(double a, double b) { volatile double r = a * b; return r; }
+#define NGB_DMUL(a, b) ngb_host_dmul((a), (b))
+#define NGB_DSUB(a, b) ((a) - (b))
+#endif
+typedef struct { unsigned x, y; } NgbRec;     /* four 16-bit fields */
+
+NGB_HD void ngb_lu_sample_pk2(const NgbLuCtx *c, const unsigned short *sb, int s, int lane, int nl,
+                              double *V, double *Rs, double *Z, double *P, unsigned ngb_gsync_mask)
+{
+    (void)ngb_gsync_mask;
+    const NgbLuPacked *h = &c->pk;
+    const int S = c->S, n = h->n, nV = h->nV;
+    const NgbRec *levd = (const NgbRec *)(sb + h->o2_levd);
+    const NgbRec *emeta = (const NgbRec *)(sb + h->o2_emeta) - h->e0;
+    const unsigned *pair = (const unsigned *)(sb + h->o2_pair);
+    const unsigned short *diag = sb + h->o2_diag;
+    if (!NGB_LDG(&c->ctl.active[s])) return;
+    if (c->ctl.lusel && NGB_LDG(&c->ctl.lusel[s]) != c->which) return;
+
+    if (c->do_factor) {
+        const double *Ax = c->Ax + (size_t)s * h->nnz;
+        const unsigned *slotmap = (const unsigned *)(sb + h->o2_slotmap);
+        const unsigned short *rowptr = sb + h->o2_rowptr, *rowv = sb + h->o2_rowv;
+        const int nnz = h->nnz;
+        if (lane == 0) c->singular_col[s] = -1;
+        for (int e = lane; e < nV; e += nl) V[e] = 0.0;
+        NGB_GROUP_SYNC();
+        /* A -> V, four independent coalesced loads in flight per lane */
+        for (int j0 = lane; j0 < nnz; j0 += 4 * nl) {
+            double a[4];
+NGB_UNROLL
+            for (int u = 0; u < 4; u++) { const int j = j0 + u * nl; a[u] = (j < nnz) ? NGB_LDG(&Ax[j]) : 0.0; }
+NGB_UNROLL
+            for (int u = 0; u < 4; u++) { const int j = j0 + u * nl; if (j < nnz) V[slotmap[j] & 0xFFFFu] = a[u]; }
+        }
+        NGB_GROUP_SYNC();
+        /* KLU_scale: largest magnitude of every row (1 for an empty row) */
+        for (int i = lane; i < n; i += nl) {
+            double r = 0.0;
+            const int lo = rowptr[i], hi = rowptr[i + 1];
+            for (int q = lo; q < hi; q++) {
+                const double a = fabs(V[rowv[q]]);
+                r = (r > a) ? r : a;
+            }
+            if (r == 0.0) r = 1.0;
+            Rs[i] = r;
+        }
+        NGB_GROUP_SYNC();
+        for (int j = lane; j < nnz; j += nl) {
+            const unsigned w = slotmap[j];
+            const int e = (int)(w & 0xFFFFu);
+            V[e] = V[e] / Rs[w >> 16];
+        }
+        NGB_GROUP_SYNC();
+        {
+            NgbRec d = levd[h->lev0 < h->nlev ? h->lev0 : 0];
+            for (int lev = h->lev0; lev < h->nlev; lev++) {
+                const int lo = (int)(d.x & 0xFFFFu), hi = (int)(d.x >> 16);
+                const int pbase = (int)(d.y & 0xFFFFu), pend = (int)(d.y >> 16);
+                if (lev + 1 < h->nlev) d = levd[lev + 1];
+                if (pend > pbase) {
+                    for (int q = pbase + lane; q < pend; q += nl) {
+                        const unsigned w = pair[q];
+                        P[q - pbase] = NGB_DMUL(V[w & 0xFFFFu], V[w >> 16]);
+                    }
+                    NGB_GROUP_SYNC();
+                }
+                for (int e = lo + lane; e < hi; e += nl) {
+                    const NgbRec m = emeta[e];
+                    const double *pp = P + ((int)(m.x & 0xFFFFu) - pbase);
+                    const int cnt = (int)(m.x >> 16) - (int)(m.x & 0xFFFFu);
+                    const unsigned dv = m.y & 0xFFFFu;
+                    double v = V[e];
+NGB_UNROLL4
+                    for (int k = 0; k < cnt; k++) v = NGB_DSUB(v, pp[k]);
+                    if (dv != 0xFFFFu) v = v / V[dv];
+                    V[e] = v;
+                }
+                NGB_GROUP_SYNC();
+            }
+        }
+        for (int k = lane; k < n; k += nl)
+            if (V[diag[k]] == 0.0) { c->singular_col[s] = k; c->ctl.err[s] = NGB_E_SINGULAR; }
+        if (c->V) {
+            double *Vg = c->V + (size_t)s * nV;
+            for (int e = lane; e < nV; e += nl) Vg[NGB_LDG(&h->ext[e])] = V[e];
+            double *Rg = c->Rs + (size_t)s * n;
+            for (int i = lane; i < n; i += nl) Rg[i] = Rs[i];
+        }
+    } else {
+        const double *Vg = c->V + (size_t)s * nV;
+        for (int e = lane; e < nV; e += nl) V[e] = Vg[NGB_LDG(&h->ext[e])];
+        const double *Rg = c->Rs + (size_t)s * n;
+        for (int i = lane; i < n; i += nl) Rs[i] = Rg[i];
+        NGB_GROUP_SYNC();
+    }
+
+    if (c->do_solve) {
+        const NgbRec *slevd = (const NgbRec *)(sb + h->o2_slevd);
+        const NgbRec *tmeta = (const NgbRec *)(sb + h->o2_tmeta);
+        const unsigned *tpair = (const unsigned *)(sb + h->o2_tpair);
+        const NgbRec *yinit = (const NgbRec *)(sb + h->o2_yinit);
+        const unsigned short *eqtask = sb + h->o2_eqtask;
+        const int xs = NGB_LDG(&c->ctl.xsel[s]);
+        double *rhs = c->x + (size_t)(1 - xs) * c->neq1 * S;
+        const double *old = c->x + (size_t)xs * c->neq1 * S;
+        /* forward-solve tasks start from b/Rs: all right-hand sides fetched with four loads in flight */
+        for (int q0 = lane; q0 < n; q0 += 4 * nl) {
+            double bq[4];
+NGB_UNROLL
+            for (int u = 0; u < 4; u++) {
+                const int q = q0 + u * nl;
+                bq[u] = (q < n) ? rhs[(size_t)(yinit[q].y & 0xFFFFu) * S + s] : 0.0;
+            }
+NGB_UNROLL
+            for (int u = 0; u < 4; u++) {
+                const int q = q0 + u * nl;
+                if (q < n) { const NgbRec y = yinit[q]; Z[y.x & 0xFFFFu] = bq[u] / Rs[y.x >> 16]; }
+            }
+        }
+        NGB_GROUP_SYNC();
+        {
+            NgbRec d = slevd[h->slev0 < h->nslev ? h->slev0 : 0];
+            for (int lev = h->slev0; lev < h->nslev; lev++) {
+                const int lo = (int)(d.x & 0xFFFFu), hi = (int)(d.x >> 16);
+                const int pbase = (int)(d.y & 0xFFFFu), pend = (int)(d.y >> 16);
+                if (lev + 1 < h->nslev) d = slevd[lev + 1];
+                if (pend > pbase) {
+                    for (int q = pbase + lane; q < pend; q += nl) {
+                        const unsigned w = tpair[q];
+                        P[q - pbase] = NGB_DMUL(V[w & 0xFFFFu], Z[w >> 16]);
+                    }
+                    NGB_GROUP_SYNC();
+                }
+                for (int tk = lo + lane; tk < hi; tk += nl) {
+                    const NgbRec m = tmeta[tk];
+                    const double *pp = P + ((int)(m.x & 0xFFFFu) - pbase);
+                    const int cnt = (int)(m.x >> 16) - (int)(m.x & 0xFFFFu);
+                    const unsigned dv = m.y >> 16;
+                    double z = Z[m.y & 0xFFFFu];
+NGB_UNROLL4
+                    for (int k = 0; k < cnt; k++) z = NGB_DSUB(z, pp[k]);
+                    if (dv != 0xFFFFu) z = z / V[dv];
+                    Z[tk] = z;
+                }
+                NGB_GROUP_SYNC();
+            }
+        }
+        /* solution out (equations without a column get 0, row 0 is ground) + node test of NIconvTest */
+        {
+            int bad = 0;
+            const int neq1 = c->neq1;
+            for (int i0 = lane; i0 < neq1; i0 += 4 * nl) {
+                double od[4];
+                if (c->nodeconv) {
+NGB_UNROLL
+                    for (int u = 0; u < 4; u++) { const int i = i0 + u * nl; od[u] = (i < neq1 && i <= n) ? old[(size_t)i * S + s] : 0.0; }
+                }
+NGB_UNROLL
+                for (int u = 0; u < 4; u++) {
+                    const int i = i0 + u * nl;
+                    if (i < neq1) {
+                        const unsigned tk = eqtask[i];
+                        const double nw = (tk != 0xFFFFu) ? Z[tk] : 0.0;
+                        rhs[(size_t)i * S + s] = nw;
+                        if (c->nodeconv && i >= 1 && i <= n) {
+                            if (nw != nw) { bad = 1; continue; }
+                            const double mx = (fabs(od[u]) > fabs(nw)) ? fabs(od[u]) : fabs(nw);
+                            const double tol = c->reltol * mx
+                                             + ((NGB_LDG(&c->node_type[i]) == NGB_SP_VOLTAGE) ? c->vntol : c->abstol);
+                            if (fabs(nw - od[u]) > tol) bad = 1;
+                        }
+                    }
+                }
+            }
+            if (c->nodeconv) {
+#ifdef __CUDA_ARCH__
+                if (bad) atomicOr(&c->nodeconv[s], 1);
+#else
+                if (bad) c->nodeconv[s] = 1;
+#endif
+            }
+        }
+    }
+}
+
 #endif

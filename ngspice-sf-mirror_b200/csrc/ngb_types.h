@@ -164,6 +164,25 @@ typedef struct NgbLuPacked {
     const int *aslot, *arow, *ext;      /* [nV] internal order: A slot, original row, external id */
     const int *row_ptr, *row_slot;      /* CSR view of A                                   */
     const int *b_eq, *out_eq;           /* [n]                                             */
+    /* second packing (ngb_lu_sample_pk2): one 8-byte record per level / value / task and one 4-byte
+     * word per product, so that the dependent index loads of a level collapse into one load each;
+     * levels whose entries need no arithmetic (level 0) are not visited at all */
+    int ok2;
+    int blob2_u16;          /* length of blob2 in 16-bit words (multiple of 4)            */
+    int lev0, e0;           /* first factor level with work, first value of that level    */
+    int slev0;              /* first solve level with work                                */
+    int o2_levd;            /* [nlev]  {lo, hi, pbase, pend}                              */
+    int o2_emeta;           /* [nV-e0] {p0, p1, div or 0xFFFF, 0}                         */
+    int o2_pair;            /* [np]    {l, u}                                             */
+    int o2_diag;            /* [n]                                                        */
+    int o2_slotmap;         /* [nnz]   {value, row} of A slot j                           */
+    int o2_rowptr, o2_rowv; /* [n+1], [nnz] values of row i (row scale factors)           */
+    int o2_slevd;           /* [nslev] {lo, hi, pbase, pend}                              */
+    int o2_tmeta;           /* [ntask] {p0, p1, start task, div or 0xFFFF}                */
+    int o2_tpair;           /* [nsp]   {value, source task}                               */
+    int o2_yinit;           /* [n]     {task, row, equation, 0} of the forward solve      */
+    int o2_eqtask;          /* [neq1]  task holding the solution of equation i, 0xFFFF none */
+    const unsigned short *blob2;
 } NgbLuPacked;
 
 typedef struct NgbLuCtx {

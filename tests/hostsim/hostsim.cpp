@@ -82,7 +82,8 @@ int ngb_launch_lu(const NgbLuCtx *c)
     g_launches++;
     std::vector<double> V(c->sch.nV + 1), Rs(c->sch.n + 1), Z(c->sch.ntask + 1), As(c->sch.nnz + 1), P(c->pk.maxlp + 1);
     for (int s = 0; s < c->S; s++) {
-        if (c->pk.ok) ngb_lu_sample_packed(c, c->pk.blob, s, 0, 1, V.data(), Rs.data(), Z.data(), As.data(), P.data(), 0xffffffffu);
+        if (c->pk.ok2 && !getenv("NGB_LU_V1")) ngb_lu_sample_pk2(c, c->pk.blob2, s, 0, 1, V.data(), Rs.data(), Z.data(), P.data(), 0xffffffffu);
+        else if (c->pk.ok) ngb_lu_sample_packed(c, c->pk.blob, s, 0, 1, V.data(), Rs.data(), Z.data(), As.data(), P.data(), 0xffffffffu);
         else ngb_lu_sample(c, s, 0, 1, V.data(), Rs.data(), Z.data());
     }
     return 0;
