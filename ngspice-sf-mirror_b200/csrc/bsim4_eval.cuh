@@ -26,6 +26,7 @@
 #include "ngb_types.h"
 #include "bsim4_fields.h"
 #include "devsup.cuh"
+#include "bsim4_split.h"
 
 /* Optional CTA-wide barrier at each phase boundary of the evaluation (keeps the warps of a CTA in
  * one instruction-cache window).  Measured on B200: no gain (571 vs 572 us per launch), so it is
@@ -68,6 +69,7 @@ typedef struct B4Ctx {
     double *op;                /* [B4O_COUNT][T] operating point (von is read back)      */
     int op_full;               /* 0: keep only von ; 1: export every B4O_* (parity runs) */
     int split;                 /* 1: exact-order stamps (B4X_* rows live), 0: merged      */
+    double *wscr;              /* [B4WF_COUNT][T] B4W fields in flight between the kernels of the phase-split load; NULL: one kernel */
     const double *x;           /* [2][neq1][S] solution buffers; xsel[s] picks CKTrhsOld  */
     int neq1;                  /* equations + 1 (row 0 is ground)                         */
     NgbCtl ctl;                /* per-sample control block                                */
@@ -106,7 +108,6 @@ typedef struct B4W {
     /* charges */
     double qgate, qbulk, qdrn, qsrc;
     double cggb, cgsb, cgdb, cdgb, cdsb, cddb, cbgb, cbsb, cbdb;
-    double capbs, capbd, qbs, qbd;
 } B4W;
 
 #define B4M(f) NGB_LDG(&Mrow[B4M_##f])
@@ -2909,26 +2910,34 @@ NGB_HD_SHARED void b4_junction_cv(double vj, double cz, double czsw, double czsw
                             if (r_ >= 0) c->stamp[(size_t)r_ * c->S + s] = (V); } while (0)
 
 /* The whole load for thread t = inst * S + s.  Returns NGB_OK or an NGB_E_* code. */
-NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
+/* what every phase of one evaluation starts from (cheap to recompute, so the split kernels do) */
+typedef struct B4Pro {
+    int inst, s, head, mode_ckt, flags, charge;
+    const double *Mrow, *Prow;
+} B4Pro;
+
+/* returns 1 when the thread has work; 0 with *err set otherwise.  `first` also applies DCtran's deferred
+ * whole-state copies, which must happen exactly once per load */
+NGB_HD int b4_prologue(const B4Ctx *c, size_t t, int first, B4Pro *p, int *err)
 {
     const int S = c->S;
     const int inst = (int)(t / (size_t)S);
     const int s = (int)(t - (size_t)inst * S);
-    if (!NGB_LDG(&c->ctl.active[s])) return NGB_OK;
+    *err = NGB_OK;
+    if (!NGB_LDG(&c->ctl.active[s])) return 0;
 
     const int mode_ckt = NGB_LDG(&c->ctl.mode[s]);
     const int head = NGB_LDG(&c->ctl.head[s]);
-    const int flags = NGB_LDG(&c->flags[inst]);
-    const int rbodyMod = B4F_RBODY(flags), rgateMod = B4F_RGATE(flags);
     const int prow = c->prow_per_thread ? NGB_LDG(&c->prow[t]) : NGB_LDG(&c->prow[inst]);
-    const double *Mrow = c->mtab + (size_t)prow * B4M_COUNT;
-    const double *Prow = c->ptab + (size_t)prow * B4P_COUNT;
-    B4W w;
+    p->inst = inst; p->s = s; p->head = head; p->mode_ckt = mode_ckt;
+    p->flags = NGB_LDG(&c->flags[inst]);
+    p->Mrow = c->mtab + (size_t)prow * B4M_COUNT;
+    p->Prow = c->ptab + (size_t)prow * B4P_COUNT;
 
-    if (mode_ckt & NGB_MODEINITSMSIG) return NGB_E_UNSUPP;
+    if (mode_ckt & NGB_MODEINITSMSIG) { *err = NGB_E_UNSUPP; return 0; }
 
     /* deferred whole-state copies of DCtran: this thread owns its 29 states */
-    {
+    if (first) {
         const int sop = NGB_LDG(&c->ctl.stateop[s]);
         if (sop) {
             for (int k = 0; k < B4ST_COUNT; k++) {
@@ -2939,705 +2948,86 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
         }
     }
 
-    const int ChargeComputationNeeded =
+    p->charge =
         ((mode_ckt & (NGB_MODEDCTRANCURVE | NGB_MODEAC | NGB_MODETRAN | NGB_MODEINITSMSIG)) ||
          ((mode_ckt & NGB_MODETRANOP) && (mode_ckt & NGB_MODEUIC))) ? 1 : 0;
-
-    b4_fetch_limit(c, t, inst, s, head, mode_ckt, Mrow, flags, &w);
-    b4_core_dc(c, t, s, Mrow, Prow, flags, &w);
-    b4_parasitics(c, t, Mrow, Prow, flags, &w);
-    b4_charges(c, t, Mrow, Prow, ChargeComputationNeeded, &w);
-
-    const double nf = B4I(nf);
-    const double type = B4M(type);
-    const int rdsMod = (int)B4M(rdsMod);
-    const int igcMod = (int)B4M(igcMod), igbMod = (int)B4M(igbMod);
-    const double vds = w.vds, vgs = w.vgs, vbs = w.vbs, vbd = w.vbd, vgd = w.vgd, vgb = w.vgb;
-    const double vgmb = w.vgmb, vbs_jct = w.vbs_jct, vbd_jct = w.vbd_jct;
-
-    NGB_CTA_ALIGN();
-    /* ---- junction C-V ---- */
-    w.capbs = w.capbd = 0.0;
-    w.qbs = B4ST(0, B4ST_qbs);
-    w.qbd = B4ST(0, B4ST_qbd);
-    if (ChargeComputationNeeded) {
-        const double weffCJnf = B4P(weffCJ) * nf;
-        const double czbd = B4M(DunitAreaTempJctCap) * B4I(Adeff);
-        const double czbs = B4M(SunitAreaTempJctCap) * B4I(Aseff);
-        const double czbdsw = B4M(DunitLengthSidewallTempJctCap) * B4I(Pdeff);
-        const double czbdswg = B4M(DunitLengthGateSidewallTempJctCap) * weffCJnf;
-        const double czbssw = B4M(SunitLengthSidewallTempJctCap) * B4I(Pseff);
-        const double czbsswg = B4M(SunitLengthGateSidewallTempJctCap) * weffCJnf;
-        b4_junction_cv(vbs_jct, czbs, czbssw, czbsswg, B4M(SbulkJctBotGradingCoeff),
-                       B4M(SbulkJctSideGradingCoeff), B4M(SbulkJctGateSideGradingCoeff),
-                       B4M(PhiBS), B4M(PhiBSWS), B4M(PhiBSWGS), &w.qbs, &w.capbs);
-        b4_junction_cv(vbd_jct, czbd, czbdsw, czbdswg, B4M(DbulkJctBotGradingCoeff),
-                       B4M(DbulkJctSideGradingCoeff), B4M(DbulkJctGateSideGradingCoeff),
-                       B4M(PhiBD), B4M(PhiBSWD), B4M(PhiBSWGD), &w.qbd, &w.capbd);
-        B4ST(0, B4ST_qbs) = w.qbs;
-        B4ST(0, B4ST_qbd) = w.qbd;
-    }
-
-    NGB_CTA_ALIGN();
-    /* ---- convergence flag from limiting (NEWCONV build: only `Check`) ---- */
-    if (((flags & B4F_OFF) == 0) || (!(mode_ckt & NGB_MODEINITFIX))) {
-        if (w.Check == 1) {
-#ifdef __CUDA_ARCH__
-            atomicAdd(&c->ctl.noncon[s], 1);
-#else
-            c->ctl.noncon[s] += 1;
-#endif
-        }
-    }
-
-    B4ST(0, B4ST_vds) = vds;
-    B4ST(0, B4ST_vgs) = vgs;
-    B4ST(0, B4ST_vbs) = vbs;
-    B4ST(0, B4ST_vbd) = vbd;
-    B4ST(0, B4ST_vges) = w.vges;
-    B4ST(0, B4ST_vgms) = w.vgms;
-    B4ST(0, B4ST_vdbs) = w.vdbs;
-    B4ST(0, B4ST_vdbd) = w.vdbd;
-    B4ST(0, B4ST_vsbs) = w.vsbs;
-    B4ST(0, B4ST_vses) = w.vses;
-    B4ST(0, B4ST_vdes) = w.vdes;
-    B4ST(0, B4ST_qdef) = w.qdef;
-
-    /* capacitance-matrix entries times ag0, equivalent charge currents */
-    double gcdgb = 0, gcddb = 0, gcdsb = 0, gcdbb = 0, gcsgb = 0, gcsdb = 0, gcssb = 0, gcsbb = 0;
-    double gcggb = 0, gcgdb = 0, gcgsb = 0, gcgbb = 0, gcbdb = 0, gcbgb = 0, gcbsb = 0, gcbbb = 0;
-    double gcgmgmb = 0, gcgmdb = 0, gcgmsb = 0, gcgmbb = 0, gcdgmb = 0, gcsgmb = 0, gcbgmb = 0;
-    double gcdbdb = 0, gcsbsb = 0;
-    double ceqqg = 0, ceqqb = 0, ceqqd = 0, ceqqjd = 0, ceqqjs = 0, ceqqgmid = 0;
-    double cgdo = 0, cgso = 0, qgdo = 0, qgso = 0;
-
-    int do_charge = ChargeComputationNeeded;
-    if (do_charge) {
-        double qgate = w.qgate, qbulk = w.qbulk, qdrn = w.qdrn, qsrc, qgmid = 0.0, qgmb, qgb;
-        const double cgbo = B4P(cgbo);
-        double vgdx, vgsx, T0, T1, T2, T3, T4;
-        if (rgateMod == 3) { vgdx = w.vgmd; vgsx = w.vgms; }
-        else { vgdx = vgd; vgsx = vgs; }
-
-        if ((int)B4M(capMod) == 0) {
-            cgdo = B4P(cgdo);
-            qgdo = B4P(cgdo) * vgdx;
-            cgso = B4P(cgso);
-            qgso = B4P(cgso) * vgsx;
-        } else {
-            const double weffCV = B4P(weffCV);
-            T0 = vgdx + B4_DELTA_1;
-            T1 = sqrt(T0 * T0 + 4.0 * B4_DELTA_1);
-            T2 = 0.5 * (T0 - T1);
-            T3 = weffCV * B4P(cgdl);
-            T4 = sqrt(1.0 - 4.0 * T2 / B4P(ckappad));
-            cgdo = B4P(cgdo) + T3 - T3 * (1.0 - 1.0 / T4) * (0.5 - 0.5 * T0 / T1);
-            qgdo = (B4P(cgdo) + T3) * vgdx - T3 * (T2 + 0.5 * B4P(ckappad) * (T4 - 1.0));
-
-            T0 = vgsx + B4_DELTA_1;
-            T1 = sqrt(T0 * T0 + 4.0 * B4_DELTA_1);
-            T2 = 0.5 * (T0 - T1);
-            T3 = weffCV * B4P(cgsl);
-            T4 = sqrt(1.0 - 4.0 * T2 / B4P(ckappas));
-            cgso = B4P(cgso) + T3 - T3 * (1.0 - 1.0 / T4) * (0.5 - 0.5 * T0 / T1);
-            qgso = (B4P(cgso) + T3) * vgsx - T3 * (T2 + 0.5 * B4P(ckappas) * (T4 - 1.0));
-        }
-        if (nf != 1.0) { cgdo *= nf; cgso *= nf; qgdo *= nf; qgso *= nf; }
-
-        const double ag0 = NGB_LDG(&c->ctl.ag0[s]);
-        if (w.mode > 0) {
-            qdrn -= qgdo;
-            if (rgateMod == 3) {
-                gcgmgmb = (cgdo + cgso + cgbo) * ag0;
-                gcgmdb = -cgdo * ag0;
-                gcgmsb = -cgso * ag0;
-                gcgmbb = -cgbo * ag0;
-                gcdgmb = gcgmdb; gcsgmb = gcgmsb; gcbgmb = gcgmbb;
-
-                gcggb = w.cggb * ag0;
-                gcgdb = w.cgdb * ag0;
-                gcgsb = w.cgsb * ag0;
-                gcgbb = -(gcggb + gcgdb + gcgsb);
-
-                gcdgb = w.cdgb * ag0;
-                gcsgb = -(w.cggb + w.cbgb + w.cdgb) * ag0;
-                gcbgb = w.cbgb * ag0;
-
-                qgmb = cgbo * vgmb;
-                qgmid = qgdo + qgso + qgmb;
-                qbulk -= qgmb;
-                qsrc = -(qgate + qgmid + qbulk + qdrn);
-            } else {
-                gcggb = (w.cggb + cgdo + cgso + cgbo) * ag0;
-                gcgdb = (w.cgdb - cgdo) * ag0;
-                gcgsb = (w.cgsb - cgso) * ag0;
-                gcgbb = -(gcggb + gcgdb + gcgsb);
-
-                gcdgb = (w.cdgb - cgdo) * ag0;
-                gcsgb = -(w.cggb + w.cbgb + w.cdgb + cgso) * ag0;
-                gcbgb = (w.cbgb - cgbo) * ag0;
-
-                gcdgmb = gcsgmb = gcbgmb = 0.0;
-
-                qgb = cgbo * vgb;
-                qgate += qgdo + qgso + qgb;
-                qbulk -= qgb;
-                qsrc = -(qgate + qbulk + qdrn);
-            }
-            gcddb = (w.cddb + w.capbd + cgdo) * ag0;
-            gcdsb = w.cdsb * ag0;
-
-            gcsdb = -(w.cgdb + w.cbdb + w.cddb) * ag0;
-            gcssb = (w.capbs + cgso - (w.cgsb + w.cbsb + w.cdsb)) * ag0;
-
-            if (!rbodyMod) {
-                gcdbb = -(gcdgb + gcddb + gcdsb + gcdgmb);
-                gcsbb = -(gcsgb + gcsdb + gcssb + gcsgmb);
-                gcbdb = (w.cbdb - w.capbd) * ag0;
-                gcbsb = (w.cbsb - w.capbs) * ag0;
-                gcdbdb = 0.0; gcsbsb = 0.0;
-            } else {
-                gcdbb = -(w.cddb + w.cdgb + w.cdsb) * ag0;
-                gcsbb = -(gcsgb + gcsdb + gcssb + gcsgmb) + w.capbs * ag0;
-                gcbdb = w.cbdb * ag0;
-                gcbsb = w.cbsb * ag0;
-                gcdbdb = -w.capbd * ag0;
-                gcsbsb = -w.capbs * ag0;
-            }
-            gcbbb = -(gcbdb + gcbgb + gcbsb + gcbgmb);
-        } else {
-            qsrc = qdrn - qgso;
-            if (rgateMod == 3) {
-                gcgmgmb = (cgdo + cgso + cgbo) * ag0;
-                gcgmdb = -cgdo * ag0;
-                gcgmsb = -cgso * ag0;
-                gcgmbb = -cgbo * ag0;
-                gcdgmb = gcgmdb; gcsgmb = gcgmsb; gcbgmb = gcgmbb;
-
-                gcggb = w.cggb * ag0;
-                gcgdb = w.cgsb * ag0;
-                gcgsb = w.cgdb * ag0;
-                gcgbb = -(gcggb + gcgdb + gcgsb);
-
-                gcdgb = -(w.cggb + w.cbgb + w.cdgb) * ag0;
-                gcsgb = w.cdgb * ag0;
-                gcbgb = w.cbgb * ag0;
-
-                qgmb = cgbo * vgmb;
-                qgmid = qgdo + qgso + qgmb;
-                qbulk -= qgmb;
-                qdrn = -(qgate + qgmid + qbulk + qsrc);
-            } else {
-                gcggb = (w.cggb + cgdo + cgso + cgbo) * ag0;
-                gcgdb = (w.cgsb - cgdo) * ag0;
-                gcgsb = (w.cgdb - cgso) * ag0;
-                gcgbb = -(gcggb + gcgdb + gcgsb);
-
-                gcdgb = -(w.cggb + w.cbgb + w.cdgb + cgdo) * ag0;
-                gcsgb = (w.cdgb - cgso) * ag0;
-                gcbgb = (w.cbgb - cgbo) * ag0;
-
-                gcdgmb = gcsgmb = gcbgmb = 0.0;
-
-                qgb = cgbo * vgb;
-                qgate += qgdo + qgso + qgb;
-                qbulk -= qgb;
-                qdrn = -(qgate + qbulk + qsrc);
-            }
-            gcddb = (w.capbd + cgdo - (w.cgsb + w.cbsb + w.cdsb)) * ag0;
-            gcdsb = -(w.cgdb + w.cbdb + w.cddb) * ag0;
-
-            gcsdb = w.cdsb * ag0;
-            gcssb = (w.cddb + w.capbs + cgso) * ag0;
-
-            if (!rbodyMod) {
-                gcdbb = -(gcdgb + gcddb + gcdsb + gcdgmb);
-                gcsbb = -(gcsgb + gcsdb + gcssb + gcsgmb);
-                gcbdb = (w.cbsb - w.capbd) * ag0;
-                gcbsb = (w.cbdb - w.capbs) * ag0;
-                gcdbdb = 0.0; gcsbsb = 0.0;
-            } else {
-                gcdbb = -(gcdgb + gcddb + gcdsb + gcdgmb) + w.capbd * ag0;
-                gcsbb = -(w.cddb + w.cdgb + w.cdsb) * ag0;
-                gcbdb = w.cbsb * ag0;
-                gcbsb = w.cbdb * ag0;
-                gcdbdb = -w.capbd * ag0;
-                gcsbsb = -w.capbs * ag0;
-            }
-            gcbbb = -(gcbgb + gcbdb + gcbsb + gcbgmb);
-        }
-
-        /* charges into state0 */
-        B4ST(0, B4ST_qg) = qgate;
-        B4ST(0, B4ST_qd) = qdrn - w.qbd;
-        B4ST(0, B4ST_qs) = qsrc - w.qbs;
-        if (rgateMod == 3) B4ST(0, B4ST_qgmid) = qgmid;
-        if (!rbodyMod) B4ST(0, B4ST_qb) = qbulk + w.qbd + w.qbs;
-        else B4ST(0, B4ST_qb) = qbulk;
-
-        /* no integration in a DC sweep, but the capacitances were still evaluated */
-        if (mode_ckt & NGB_MODEDCTRANCURVE) do_charge = 0;
-    }
-
-    if (do_charge) {
-        const int order = NGB_LDG(&c->ctl.order[s]);
-        const double ag0 = NGB_LDG(&c->ctl.ag0[s]), ag1 = NGB_LDG(&c->ctl.ag1[s]);
-        const int inittran = (mode_ckt & NGB_MODEINITTRAN) != 0;
-        double cqgate, cqbody, cqdrn, cqgmid = 0.0, cqbs = 0.0, cqbd = 0.0;
-        if (order != 1 && order != 2) return NGB_E_ORDER;
-
-        /* NIintegrate on one (q, cq) state pair; INITTRAN first copies q0 -> q1 */
-#define B4_INTEG(KQ, KC, OUT) do { \
-            double q0_ = B4ST(0, KQ), q1_; \
-            if (inittran) { B4ST(1, KQ) = q0_; q1_ = q0_; } else q1_ = B4ST(1, KQ); \
-            OUT = ngb_integrate_trap(order, ag0, ag1, q0_, q1_, (order == 2) ? B4ST(1, KC) : 0.0); \
-            B4ST(0, KC) = OUT; } while (0)
-
-        B4_INTEG(B4ST_qb, B4ST_cqb, cqbody);
-        B4_INTEG(B4ST_qg, B4ST_cqg, cqgate);
-        B4_INTEG(B4ST_qd, B4ST_cqd, cqdrn);
-        if (rgateMod == 3) B4_INTEG(B4ST_qgmid, B4ST_cqgmid, cqgmid);
-        if (rbodyMod) {
-            B4_INTEG(B4ST_qbs, B4ST_cqbs, cqbs);
-            B4_INTEG(B4ST_qbd, B4ST_cqbd, cqbd);
-        }
-#undef B4_INTEG
-
-        /* equivalent charge currents */
-        ceqqg = cqgate - gcggb * vgb + gcgdb * vbd + gcgsb * vbs;
-        ceqqd = cqdrn - gcdgb * vgb - gcdgmb * vgmb + (gcddb + gcdbdb) * vbd
-              - gcdbdb * vbd_jct + gcdsb * vbs;
-        ceqqb = cqbody - gcbgb * vgb - gcbgmb * vgmb + gcbdb * vbd + gcbsb * vbs;
-
-        if (rgateMod == 3)
-            ceqqgmid = cqgmid + gcgmdb * vbd + gcgmsb * vbs - gcgmgmb * vgmb;
-        else
-            ceqqgmid = 0.0;
-
-        if (rbodyMod) {
-            ceqqjs = cqbs + gcsbsb * vbs_jct;
-            ceqqjd = cqbd + gcdbdb * vbd_jct;
-        }
-
-        /* BSIM4trunc (b4trunc.c:33-71): step-size estimates for CKTtrunc */
-        if (c->ctl.lte) {
-            ngb_lte_state(&c->ctl, s, c->state, B4ST_COUNT, (size_t)c->T, t, head, B4ST_qb, order);
-            ngb_lte_state(&c->ctl, s, c->state, B4ST_COUNT, (size_t)c->T, t, head, B4ST_qg, order);
-            ngb_lte_state(&c->ctl, s, c->state, B4ST_COUNT, (size_t)c->T, t, head, B4ST_qd, order);
-            if (rbodyMod) {
-                ngb_lte_state(&c->ctl, s, c->state, B4ST_COUNT, (size_t)c->T, t, head, B4ST_qbs, order);
-                ngb_lte_state(&c->ctl, s, c->state, B4ST_COUNT, (size_t)c->T, t, head, B4ST_qbd, order);
-            }
-            if (rgateMod == 3)
-                ngb_lte_state(&c->ctl, s, c->state, B4ST_COUNT, (size_t)c->T, t, head, B4ST_qgmid, order);
-        }
-
-        if (inittran) {
-            B4ST(1, B4ST_cqb) = B4ST(0, B4ST_cqb);
-            B4ST(1, B4ST_cqg) = B4ST(0, B4ST_cqg);
-            B4ST(1, B4ST_cqd) = B4ST(0, B4ST_cqd);
-            if (rgateMod == 3) B4ST(1, B4ST_cqgmid) = B4ST(0, B4ST_cqgmid);
-            if (rbodyMod) {
-                B4ST(1, B4ST_cqbs) = B4ST(0, B4ST_cqbs);
-                B4ST(1, B4ST_cqbd) = B4ST(0, B4ST_cqbd);
-            }
-        }
-    } else {
-        /* line850: no charge currents; capacitance terms vanish from the stamps */
-        gcdgb = gcddb = gcdsb = gcdbb = 0.0;
-        gcsgb = gcsdb = gcssb = gcsbb = 0.0;
-        gcggb = gcgdb = gcgsb = gcgbb = 0.0;
-        gcbdb = gcbgb = gcbsb = gcbbb = 0.0;
-        gcgmgmb = gcgmdb = gcgmsb = gcgmbb = 0.0;
-        gcdgmb = gcsgmb = gcbgmb = 0.0;
-        gcdbdb = gcsbsb = 0.0;
-    }
-
-    NGB_CTA_ALIGN();
-    /* ---- Norton equivalents of the DC currents (line900) ---- */
-    double Gm, Gmbs, FwdSum, RevSum, ceqdrn, ceqbd, ceqbs;
-    double gbbdp, gbbsp, gbdpg, gbdpdp, gbdpb, gbdpsp, gbspg, gbspdp, gbspb, gbspsp;
-    double gIstotg, gIstotd, gIstots, gIstotb, Istoteq, gIdtotg, gIdtotd, gIdtots, gIdtotb, Idtoteq;
-    double gIbtotg, gIbtotd, gIbtots, gIbtotb, Ibtoteq, gIgtotg, gIgtotd, gIgtots, gIgtotb, Igtoteq;
-    double gcrg, gcrgd, gcrgg, gcrgs, gcrgb, ceqgcrg, Tr = 0.0;
-    const double cdrain = w.cdrain;
-
-    if (w.mode >= 0) {
-        Gm = w.gm;
-        Gmbs = w.gmbs;
-        FwdSum = Gm + Gmbs;
-        RevSum = 0.0;
-
-        ceqdrn = type * (cdrain - w.gds * vds - Gm * vgs - Gmbs * vbs);
-        ceqbd = type * (w.csub + w.Igidl - (w.gbds + w.ggidld) * vds
-                        - (w.gbgs + w.ggidlg) * vgs - (w.gbbs + w.ggidlb) * vbs);
-        ceqbs = type * (w.Igisl + w.ggisls * vds - w.ggislg * vgd - w.ggislb * vbd);
-
-        gbbdp = -(w.gbds);
-        gbbsp = w.gbds + w.gbgs + w.gbbs;
-
-        gbdpg = w.gbgs;
-        gbdpdp = w.gbds;
-        gbdpb = w.gbbs;
-        gbdpsp = -(gbdpg + gbdpdp + gbdpb);
-
-        gbspg = 0.0; gbspdp = 0.0; gbspb = 0.0; gbspsp = 0.0;
-
-        if (igcMod) {
-            gIstotg = w.gIgsg + w.gIgcsg;
-            gIstotd = w.gIgcsd;
-            gIstots = w.gIgss + w.gIgcss;
-            gIstotb = w.gIgcsb;
-            Istoteq = type * (w.Igs + w.Igcs - gIstotg * vgs - w.gIgcsd * vds - w.gIgcsb * vbs);
-
-            gIdtotg = w.gIgdg + w.gIgcdg;
-            gIdtotd = w.gIgdd + w.gIgcdd;
-            gIdtots = w.gIgcds;
-            gIdtotb = w.gIgcdb;
-            Idtoteq = type * (w.Igd + w.Igcd - w.gIgdg * vgd - w.gIgcdg * vgs
-                              - w.gIgcdd * vds - w.gIgcdb * vbs);
-        } else {
-            gIstotg = gIstotd = gIstots = gIstotb = Istoteq = 0.0;
-            gIdtotg = gIdtotd = gIdtots = gIdtotb = Idtoteq = 0.0;
-        }
-
-        if (igbMod) {
-            gIbtotg = w.gIgbg;
-            gIbtotd = w.gIgbd;
-            gIbtots = w.gIgbs;
-            gIbtotb = w.gIgbb;
-            Ibtoteq = type * (w.Igb - w.gIgbg * vgs - w.gIgbd * vds - w.gIgbb * vbs);
-        } else {
-            gIbtotg = gIbtotd = gIbtots = gIbtotb = Ibtoteq = 0.0;
-        }
-
-        if ((igcMod != 0) || (igbMod != 0)) {
-            gIgtotg = gIstotg + gIdtotg + gIbtotg;
-            gIgtotd = gIstotd + gIdtotd + gIbtotd;
-            gIgtots = gIstots + gIdtots + gIbtots;
-            gIgtotb = gIstotb + gIdtotb + gIbtotb;
-            Igtoteq = Istoteq + Idtoteq + Ibtoteq;
-        } else {
-            gIgtotg = gIgtotd = gIgtots = gIgtotb = Igtoteq = 0.0;
-        }
-
-        if (rgateMod == 2) Tr = w.vges - vgs;
-        else if (rgateMod == 3) Tr = w.vgms - vgs;
-        if (rgateMod > 1) {
-            gcrgd = w.gcrgd * Tr;
-            gcrgg = w.gcrgg * Tr;
-            gcrgs = w.gcrgs * Tr;
-            gcrgb = w.gcrgb * Tr;
-            ceqgcrg = -(gcrgd * vds + gcrgg * vgs + gcrgb * vbs);
-            gcrgg -= w.gcrg;
-            gcrg = w.gcrg;
-        } else {
-            ceqgcrg = gcrg = gcrgd = gcrgg = gcrgs = gcrgb = 0.0;
-        }
-    } else {
-        Gm = -w.gm;
-        Gmbs = -w.gmbs;
-        FwdSum = 0.0;
-        RevSum = -(Gm + Gmbs);
-
-        ceqdrn = -type * (cdrain + w.gds * vds + Gm * vgd + Gmbs * vbd);
-
-        ceqbs = type * (w.csub + w.Igisl + (w.gbds + w.ggisls) * vds
-                        - (w.gbgs + w.ggislg) * vgd - (w.gbbs + w.ggislb) * vbd);
-        ceqbd = type * (w.Igidl - w.ggidld * vds - w.ggidlg * vgs - w.ggidlb * vbs);
-
-        gbbsp = -(w.gbds);
-        gbbdp = w.gbds + w.gbgs + w.gbbs;
-
-        gbdpg = 0.0; gbdpsp = 0.0; gbdpb = 0.0; gbdpdp = 0.0;
-
-        gbspg = w.gbgs;
-        gbspsp = w.gbds;
-        gbspb = w.gbbs;
-        gbspdp = -(gbspg + gbspsp + gbspb);
-
-        if (igcMod) {
-            gIstotg = w.gIgsg + w.gIgcdg;
-            gIstotd = w.gIgcds;
-            gIstots = w.gIgss + w.gIgcdd;
-            gIstotb = w.gIgcdb;
-            Istoteq = type * (w.Igs + w.Igcd - w.gIgsg * vgs - w.gIgcdg * vgd
-                              + w.gIgcdd * vds - w.gIgcdb * vbd);
-
-            gIdtotg = w.gIgdg + w.gIgcsg;
-            gIdtotd = w.gIgdd + w.gIgcss;
-            gIdtots = w.gIgcsd;
-            gIdtotb = w.gIgcsb;
-            Idtoteq = type * (w.Igd + w.Igcs - (w.gIgdg + w.gIgcsg) * vgd
-                              + w.gIgcsd * vds - w.gIgcsb * vbd);
-        } else {
-            gIstotg = gIstotd = gIstots = gIstotb = Istoteq = 0.0;
-            gIdtotg = gIdtotd = gIdtots = gIdtotb = Idtoteq = 0.0;
-        }
-
-        if (igbMod) {
-            gIbtotg = w.gIgbg;
-            gIbtotd = w.gIgbs;
-            gIbtots = w.gIgbd;
-            gIbtotb = w.gIgbb;
-            Ibtoteq = type * (w.Igb - w.gIgbg * vgd + w.gIgbd * vds - w.gIgbb * vbd);
-        } else {
-            gIbtotg = gIbtotd = gIbtots = gIbtotb = Ibtoteq = 0.0;
-        }
-
-        if ((igcMod != 0) || (igbMod != 0)) {
-            gIgtotg = gIstotg + gIdtotg + gIbtotg;
-            gIgtotd = gIstotd + gIdtotd + gIbtotd;
-            gIgtots = gIstots + gIdtots + gIbtots;
-            gIgtotb = gIstotb + gIdtotb + gIbtotb;
-            Igtoteq = Istoteq + Idtoteq + Ibtoteq;
-        } else {
-            gIgtotg = gIgtotd = gIgtots = gIgtotb = Igtoteq = 0.0;
-        }
-
-        if (rgateMod == 2) Tr = w.vges - vgs;
-        else if (rgateMod == 3) Tr = w.vgms - vgs;
-        if (rgateMod > 1) {
-            gcrgd = w.gcrgs * Tr;
-            gcrgg = w.gcrgg * Tr;
-            gcrgs = w.gcrgd * Tr;
-            gcrgb = w.gcrgb * Tr;
-            ceqgcrg = -(gcrgg * vgd - gcrgs * vds + gcrgb * vbd);
-            gcrgg -= w.gcrg;
-            gcrg = w.gcrg;
-        } else {
-            ceqgcrg = gcrg = gcrgd = gcrgg = gcrgs = gcrgb = 0.0;
-        }
-    }
-
-    double gstot, gstotd, gstotg, gstots, gstotb, ceqgstot, gdtot, gdtotd, gdtotg, gdtots, gdtotb, ceqgdtot;
-    if (rdsMod == 1) {
-        ceqgstot = type * (w.gstotd * vds + w.gstotg * vgs + w.gstotb * vbs);
-        gstot = w.gstot;
-        gstotd = w.gstotd;
-        gstotg = w.gstotg;
-        gstots = w.gstots - gstot;
-        gstotb = w.gstotb;
-
-        ceqgdtot = -type * (w.gdtotd * vds + w.gdtotg * vgs + w.gdtotb * vbs);
-        gdtot = w.gdtot;
-        gdtotd = w.gdtotd - gdtot;
-        gdtotg = w.gdtotg;
-        gdtots = w.gdtots;
-        gdtotb = w.gdtotb;
-    } else {
-        gstot = gstotd = gstotg = gstots = gstotb = ceqgstot = 0.0;
-        gdtot = gdtotd = gdtotg = gdtots = gdtotb = ceqgdtot = 0.0;
-    }
-
-    double ceqjs, ceqjd;
-    if (type > 0) {
-        ceqjs = (w.cbs - w.gbs * vbs_jct);
-        ceqjd = (w.cbd - w.gbd * vbd_jct);
-    } else {
-        ceqjs = -(w.cbs - w.gbs * vbs_jct);
-        ceqjd = -(w.cbd - w.gbd * vbd_jct);
-        ceqqg = -ceqqg;
-        ceqqd = -ceqqd;
-        ceqqb = -ceqqb;
-        ceqgcrg = -ceqgcrg;
-        if (rbodyMod) { ceqqjs = -ceqqjs; ceqqjd = -ceqqjd; }
-        if (rgateMod == 3) ceqqgmid = -ceqqgmid;
-    }
-
-    NGB_CTA_ALIGN();
-    /* ---- right-hand side ---- */
-    const double m = B4I(m);
-    const double mult_i = B4I(mult_i) * m;
-    const double mult_q = B4I(mult_q) * m;
-
-    B4_STAMP(B4R_dp, (mult_i * (ceqjd - ceqbd + ceqgdtot - ceqdrn + Idtoteq) - mult_q * ceqqd));
-    B4_STAMP(B4R_gp, -(mult_q * ceqqg - mult_i * (ceqgcrg - Igtoteq)));
-    if (rgateMod == 2) B4_STAMP(B4R_ge, -(mult_i * ceqgcrg));
-    else if (rgateMod == 3) B4_STAMP(B4R_gm, -(mult_q * ceqqgmid + mult_i * ceqgcrg));
-
-    if (!rbodyMod) {
-        B4_STAMP(B4R_bp, (mult_i * (ceqbd + ceqbs - ceqjd - ceqjs + Ibtoteq) - mult_q * ceqqb));
-        B4_STAMP(B4R_sp, (mult_i * (ceqdrn - ceqbs + ceqjs - ceqgstot + Istoteq)
-                          + mult_q * (ceqqg + ceqqb + ceqqd + ceqqgmid)));
-    } else {
-        B4_STAMP(B4R_db, -(mult_i * (ceqjd) + mult_q * ceqqjd));
-        B4_STAMP(B4R_bp, (mult_i * (ceqbd + ceqbs + Ibtoteq) - mult_q * ceqqb));
-        B4_STAMP(B4R_sb, -(mult_i * (ceqjs) + mult_q * ceqqjs));
-        B4_STAMP(B4R_sp, (mult_i * (ceqdrn - ceqbs + ceqjs - ceqgstot + Istoteq)
-                          + mult_q * (ceqqd + ceqqg + ceqqb + ceqqjd + ceqqjs + ceqqgmid)));
-    }
-    if (rdsMod) {
-        B4_STAMP(B4R_d, -(mult_i * ceqgdtot));
-        B4_STAMP(B4R_s, (mult_i * ceqgstot));
-    }
-
-    NGB_CTA_ALIGN();
-    /* ---- matrix ---- */
-    double gjbd, gjbs, gdpr, gspr;
-    if (!rbodyMod) { gjbd = w.gbd; gjbs = w.gbs; }
-    else gjbd = gjbs = 0.0;
-    if (!rdsMod) { gdpr = B4I(drainConductance); gspr = B4I(sourceConductance); }
-    else gdpr = gspr = 0.0;
-    const double geltd = B4I(grgeltd);
-
-    /* gate row(s) */
-    if (rgateMod == 1) {
-        B4_STAMP(B4S_GEge, mult_i * geltd);
-        B4_STAMP(B4S_GPge, -(mult_i * geltd));
-        B4_STAMP(B4S_GEgp, -(mult_i * geltd));
-        B4_STAMP(B4S_GPgp, mult_q * (gcggb) + mult_i * (geltd + gIgtotg));
-        B4_STAMP(B4S_GPdp, mult_q * (gcgdb) + mult_i * gIgtotd);
-        B4_STAMP(B4S_GPsp, mult_q * (gcgsb) + mult_i * gIgtots);
-        B4_STAMP(B4S_GPbp, mult_q * (gcgbb) + mult_i * gIgtotb);
-    } else if (rgateMod == 2) {
-        B4_STAMP(B4S_GEge, mult_i * gcrg);
-        B4_STAMP(B4S_GEgp, mult_i * gcrgg);
-        B4_STAMP(B4S_GEdp, mult_i * gcrgd);
-        B4_STAMP(B4S_GEsp, mult_i * gcrgs);
-        B4_STAMP(B4S_GEbp, mult_i * gcrgb);
-        B4_STAMP(B4S_GPge, -(mult_i * gcrg));
-        B4_STAMP(B4S_GPgp, mult_q * (gcggb) + mult_i * (gIgtotg - gcrgg));
-        B4_STAMP(B4S_GPdp, mult_q * (gcgdb) + mult_i * (gIgtotd - gcrgd));
-        B4_STAMP(B4S_GPsp, mult_q * (gcgsb) + mult_i * (gIgtots - gcrgs));
-        B4_STAMP(B4S_GPbp, mult_q * (gcgbb) + mult_i * (gIgtotb - gcrgb));
-    } else if (rgateMod == 3) {
-        B4_STAMP(B4S_GEge, mult_i * geltd);
-        B4_STAMP(B4S_GEgm, -(mult_i * geltd));
-        B4_STAMP(B4S_GMge, -(mult_i * geltd));
-        B4_STAMP(B4S_GMgm, mult_i * (geltd + gcrg) + mult_q * gcgmgmb);
-        B4_STAMP(B4S_GMdp, mult_i * gcrgd + mult_q * gcgmdb);
-        B4_STAMP(B4S_GMgp, mult_i * gcrgg);
-        B4_STAMP(B4S_GMsp, mult_i * gcrgs + mult_q * gcgmsb);
-        B4_STAMP(B4S_GMbp, mult_i * gcrgb + mult_q * gcgmbb);
-        B4_STAMP(B4S_DPgm, mult_q * gcdgmb);
-        B4_STAMP(B4S_GPgm, -(mult_i * gcrg));
-        B4_STAMP(B4S_SPgm, mult_q * gcsgmb);
-        B4_STAMP(B4S_BPgm, mult_q * gcbgmb);
-        B4_STAMP(B4S_GPgp, mult_q * (gcggb) + mult_i * (gIgtotg - gcrgg));
-        B4_STAMP(B4S_GPdp, mult_q * (gcgdb) + mult_i * (gIgtotd - gcrgd));
-        B4_STAMP(B4S_GPsp, mult_q * (gcgsb) + mult_i * (gIgtots - gcrgs));
-        B4_STAMP(B4S_GPbp, mult_q * (gcgbb) + mult_i * (gIgtotb - gcrgb));
-    } else {
-        B4_STAMP(B4S_GPgp, mult_q * (gcggb) + mult_i * gIgtotg);
-        B4_STAMP(B4S_GPdp, mult_q * (gcgdb) + mult_i * gIgtotd);
-        B4_STAMP(B4S_GPsp, mult_q * (gcgsb) + mult_i * gIgtots);
-        B4_STAMP(B4S_GPbp, mult_q * (gcgbb) + mult_i * gIgtotb);
-    }
-
-    if (rdsMod) {
-        B4_STAMP(B4S_Dgp, mult_i * gdtotg);
-        B4_STAMP(B4S_Dsp, mult_i * gdtots);
-        B4_STAMP(B4S_Dbp, mult_i * gdtotb);
-        B4_STAMP(B4S_Sdp, mult_i * gstotd);
-        B4_STAMP(B4S_Sgp, mult_i * gstotg);
-        B4_STAMP(B4S_Sbp, mult_i * gstotb);
-    }
-
-    const double ggidld = w.ggidld, ggidlg = w.ggidlg, ggidlb = w.ggidlb;
-    const double ggislg = w.ggislg, ggisls = w.ggisls, ggislb = w.ggislb;
-
-    /* rows d', s', b': the reference applies the channel/junction term, then the GIDL and
-     * GISL terms, then (rbodyMod) the body-network term, in that order.  B4_STAMP2 emits the
-     * later addend on its own row in exact-order mode and pre-summed otherwise. */
-    const int split = c->split;
-#define B4_STAMP2(K, V, KX, VX) do { if (split) { B4_STAMP(K, V); B4_STAMP(KX, VX); } else B4_STAMP(K, (V) + (VX)); } while (0)
-    B4_STAMP2(B4S_DPdp, (mult_i * (gdpr + w.gds + w.gbd - gdtotd + RevSum + gbdpdp - gIdtotd)
-                         + mult_q * (gcddb)), B4X_DPdp_g, mult_i * ggidld);
-    B4_STAMP(B4S_DPd, -(mult_i * (gdpr + gdtot)));
-    B4_STAMP2(B4S_DPgp, (mult_i * (Gm - gdtotg + gbdpg - gIdtotg) + mult_q * (gcdgb)), B4X_DPgp_g, mult_i * ggidlg);
-    B4_STAMP2(B4S_DPsp, -(mult_i * (w.gds + gdtots + gIdtots + FwdSum - gbdpsp) - mult_q * (gcdsb)),
-              B4X_DPsp_g, -(mult_i * (ggidlg + ggidld + ggidlb)));
-    B4_STAMP2(B4S_DPbp, -(mult_i * (gjbd + gdtotb - Gmbs - gbdpb + gIdtotb) - mult_q * (gcdbb)),
-              B4X_DPbp_g, mult_i * ggidlb);
-
-    B4_STAMP(B4S_Ddp, -(mult_i * (gdpr - gdtotd)));
-    B4_STAMP(B4S_Dd, mult_i * (gdpr + gdtot));
-
-    B4_STAMP2(B4S_SPdp, -(mult_i * (w.gds + gstotd + RevSum - gbspdp + gIstotd) - mult_q * (gcsdb)),
-              B4X_SPdp_s, -(mult_i * (ggisls + ggislg + ggislb)));
-    B4_STAMP2(B4S_SPgp, (mult_q * (gcsgb) + mult_i * (gbspg - Gm - gstotg - gIstotg)), B4X_SPgp_s, mult_i * ggislg);
-    B4_STAMP2(B4S_SPsp, (mult_i * (gspr + w.gds + w.gbs - gIstots - gstots + FwdSum + gbspsp)
-                         + mult_q * (gcssb)), B4X_SPsp_s, mult_i * ggisls);
-    B4_STAMP(B4S_SPs, -(mult_i * (gspr + gstot)));
-    B4_STAMP2(B4S_SPbp, -(mult_i * (gjbs + gstotb + Gmbs - gbspb + gIstotb) - mult_q * (gcsbb)),
-              B4X_SPbp_s, mult_i * ggislb);
-
-    B4_STAMP(B4S_Ssp, -(mult_i * (gspr - gstots)));
-    B4_STAMP(B4S_Ss, mult_i * (gspr + gstot));
-
-    {
-        const double bpdp = (mult_q * gcbdb - mult_i * (gjbd - gbbdp + gIbtotd));
-        const double bpgp = (mult_q * gcbgb - mult_i * (w.gbgs + gIbtotg));
-        const double bpsp = (mult_q * gcbsb - mult_i * (gjbs - gbbsp + gIbtots));
-        const double bpbp = (mult_i * (gjbd + gjbs - w.gbbs - gIbtotb) + mult_q * gcbbb);
-        const double rb = rbodyMod ? mult_i * (B4I(grbpd) + B4I(grbps) + B4I(grbpb)) : 0.0;
-        if (split) {
-            B4_STAMP(B4S_BPdp, bpdp); B4_STAMP(B4S_BPgp, bpgp); B4_STAMP(B4S_BPsp, bpsp); B4_STAMP(B4S_BPbp, bpbp);
-            B4_STAMP(B4X_BPdp_g, -(mult_i * ggidld));
-            B4_STAMP(B4X_BPgp_g, -(mult_i * ggidlg));
-            B4_STAMP(B4X_BPsp_g, mult_i * (ggidlg + ggidld + ggidlb));
-            B4_STAMP(B4X_BPbp_g, -(mult_i * ggidlb));
-            B4_STAMP(B4X_BPdp_s, mult_i * (ggislg + ggisls + ggislb));
-            B4_STAMP(B4X_BPgp_s, -(mult_i * ggislg));
-            B4_STAMP(B4X_BPsp_s, -(mult_i * ggisls));
-            B4_STAMP(B4X_BPbp_s, -(mult_i * ggislb));
-            if (rbodyMod) B4_STAMP(B4X_BPbp_r, rb);
-        } else {
-            double v;
-            v = bpdp; v -= mult_i * ggidld; v += mult_i * (ggislg + ggisls + ggislb); B4_STAMP(B4S_BPdp, v);
-            v = bpgp; v -= mult_i * ggidlg; v -= mult_i * ggislg; B4_STAMP(B4S_BPgp, v);
-            v = bpsp; v += mult_i * (ggidlg + ggidld + ggidlb); v -= mult_i * ggisls; B4_STAMP(B4S_BPsp, v);
-            v = bpbp; v -= mult_i * ggidlb; v -= mult_i * ggislb; if (rbodyMod) v += rb; B4_STAMP(B4S_BPbp, v);
-        }
-    }
-#undef B4_STAMP2
-
-    if (rbodyMod) {
-        const double grbpd = B4I(grbpd), grbdb = B4I(grbdb), grbpb = B4I(grbpb);
-        const double grbps = B4I(grbps), grbsb = B4I(grbsb);
-        B4_STAMP(B4S_DPdb, mult_q * gcdbdb - mult_i * w.gbd);
-        B4_STAMP(B4S_SPsb, -(mult_i * w.gbs - mult_q * gcsbsb));
-
-        B4_STAMP(B4S_DBdp, mult_q * gcdbdb - mult_i * w.gbd);
-        B4_STAMP(B4S_DBdb, mult_i * (w.gbd + grbpd + grbdb) - mult_q * gcdbdb);
-        B4_STAMP(B4S_DBbp, -(mult_i * grbpd));
-        B4_STAMP(B4S_DBb, -(mult_i * grbdb));
-
-        B4_STAMP(B4S_BPdb, -(mult_i * grbpd));
-        B4_STAMP(B4S_BPb, -(mult_i * grbpb));
-        B4_STAMP(B4S_BPsb, -(mult_i * grbps));
-
-        B4_STAMP(B4S_SBsp, mult_q * gcsbsb - mult_i * w.gbs);
-        B4_STAMP(B4S_SBbp, -(mult_i * grbps));
-        B4_STAMP(B4S_SBb, -(mult_i * grbsb));
-        B4_STAMP(B4S_SBsb, mult_i * (w.gbs + grbps + grbsb) - mult_q * gcsbsb);
-
-        B4_STAMP(B4S_Bdb, -(mult_i * grbdb));
-        B4_STAMP(B4S_Bbp, -(mult_i * grbpb));
-        B4_STAMP(B4S_Bsb, -(mult_i * grbsb));
-        B4_STAMP(B4S_Bb, mult_i * (grbsb + grbdb + grbpb));
-    }
-
-    NGB_CTA_ALIGN();
-    /* ---- operating point ---- */
-    c->op[(size_t)B4O_von * c->T + t] = w.von;
-    if (c->op_full) {
-#define B4_OP(f, v) c->op[(size_t)B4O_##f * c->T + t] = (v)
-        B4_OP(mode, (double)w.mode); B4_OP(cd, w.cdrain); B4_OP(gm, w.gm); B4_OP(gds, w.gds);
-        B4_OP(gmbs, w.gmbs); B4_OP(gbd, w.gbd); B4_OP(gbs, w.gbs); B4_OP(cbd, w.cbd); B4_OP(cbs, w.cbs);
-        B4_OP(csub, w.csub); B4_OP(gbbs, w.gbbs); B4_OP(gbgs, w.gbgs); B4_OP(gbds, w.gbds);
-        B4_OP(Igidl, w.Igidl); B4_OP(Igisl, w.Igisl); B4_OP(Igcs, w.Igcs); B4_OP(Igcd, w.Igcd);
-        B4_OP(Igs, w.Igs); B4_OP(Igd, w.Igd); B4_OP(Igb, w.Igb); B4_OP(vdsat, w.vdsat);
-        B4_OP(Vgsteff, w.Vgsteff); B4_OP(Vdseff, w.Vdseff);
-        B4_OP(qgate, w.qgate); B4_OP(qbulk, w.qbulk); B4_OP(qdrn, w.qdrn);
-        B4_OP(capbd, w.capbd); B4_OP(capbs, w.capbs);
-        B4_OP(cggb, w.cggb); B4_OP(cgdb, w.cgdb); B4_OP(cgsb, w.cgsb);
-        B4_OP(cbgb, w.cbgb); B4_OP(cbdb, w.cbdb); B4_OP(cbsb, w.cbsb);
-        B4_OP(cdgb, w.cdgb); B4_OP(cddb, w.cddb); B4_OP(cdsb, w.cdsb);
-#undef B4_OP
-    }
-    (void)qgdo; (void)qgso; (void)Tr; (void)ceqqjd; (void)ceqqjs;
+    return 1;
+}
+
+NGB_HD int b4_finish(const B4Ctx *c, size_t t, const B4Pro *pro, const B4W *wp);
+NGB_HD int b4_finish_lazy(const B4Ctx *c, size_t t, const B4Pro *pro, const B4W *wp);
+
+NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
+{
+    B4Pro p;
+    B4W w;
+    int err;
+    if (!b4_prologue(c, t, 1, &p, &err)) return err;
+    b4_fetch_limit(c, t, p.inst, p.s, p.head, p.mode_ckt, p.Mrow, p.flags, &w);
+    b4_core_dc(c, t, p.s, p.Mrow, p.Prow, p.flags, &w);
+    b4_parasitics(c, t, p.Mrow, p.Prow, p.flags, &w);
+    b4_charges(c, t, p.Mrow, p.Prow, p.charge, &w);
+    return b4_finish(c, t, &p, &w);
+}
+
+#define B4FIN_NAME b4_finish
+#define B4FIN_W const B4W w = *wp;
+#define BW(f) w.f
+#include "bsim4_finish.inc"
+#undef B4FIN_NAME
+#undef B4FIN_W
+#undef BW
+#define B4FIN_NAME b4_finish_lazy
+#define B4FIN_W (void)wp;
+#define BW(f) NGB_LDG((const double *)&c->wscr[(size_t)B4WF_##f * c->T + t])
+#include "bsim4_finish.inc"
+#undef B4FIN_NAME
+#undef B4FIN_W
+#undef BW
+
+/* ---- the same evaluation as four kernels (core / parasitics / charges / finish) -----------------
+ * One evaluation is ~23 k instructions and keeps ~180 doubles alive; as one kernel it runs at 128
+ * registers with ~1 KB of spill per thread and streams 390 KB of code per warp.  Split at the phase
+ * boundaries, every kernel has a third of the code and of the live values; the B4W fields a later phase
+ * needs (bsim4_split.h, generated from this file) travel through c->wscr, thread-fastest, written once
+ * and read once.  The arithmetic is the same code in the same order: results are bit-identical. */
+#define B4W_LD_D(f) w.f = c->wscr[(size_t)B4WF_##f * c->T + t];
+#define B4W_LD_I(f) w.f = (int)c->wscr[(size_t)B4WF_##f * c->T + t];
+#define B4W_ST_D(f) c->wscr[(size_t)B4WF_##f * c->T + t] = w.f;
+#define B4W_ST_I(f) c->wscr[(size_t)B4WF_##f * c->T + t] = (double)w.f;
+
+NGB_HD int b4_phase_core(const B4Ctx *c, size_t t)
+{
+    B4Pro p; B4W w; int err;
+    if (!b4_prologue(c, t, 1, &p, &err)) return err;
+    b4_fetch_limit(c, t, p.inst, p.s, p.head, p.mode_ckt, p.Mrow, p.flags, &w);
+    b4_core_dc(c, t, p.s, p.Mrow, p.Prow, p.flags, &w);
+    B4W_OUT_CORE(B4W_ST_D, B4W_ST_I)
     return NGB_OK;
 }
+NGB_HD int b4_phase_para(const B4Ctx *c, size_t t)
+{
+    B4Pro p; B4W w; int err;
+    if (!b4_prologue(c, t, 0, &p, &err)) return NGB_OK;       /* the first phase has reported it */
+    B4W_IN_PARA(B4W_LD_D, B4W_LD_I)
+    b4_parasitics(c, t, p.Mrow, p.Prow, p.flags, &w);
+    B4W_OUT_PARA(B4W_ST_D, B4W_ST_I)
+    return NGB_OK;
+}
+NGB_HD int b4_phase_chrg(const B4Ctx *c, size_t t)
+{
+    B4Pro p; B4W w; int err;
+    if (!b4_prologue(c, t, 0, &p, &err)) return NGB_OK;
+    B4W_IN_CHRG(B4W_LD_D, B4W_LD_I)
+    b4_charges(c, t, p.Mrow, p.Prow, p.charge, &w);
+    B4W_OUT_CHRG(B4W_ST_D, B4W_ST_I)
+    return NGB_OK;
+}
+NGB_HD int b4_phase_fin(const B4Ctx *c, size_t t)
+{
+    B4Pro p; int err;
+    if (!b4_prologue(c, t, 0, &p, &err)) return NGB_OK;
+    return b4_finish_lazy(c, t, &p, (const B4W *)0);
+}
+
 #endif

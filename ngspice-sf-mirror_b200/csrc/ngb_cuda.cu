@@ -10,6 +10,7 @@
  * All kernels are launched on one non-default stream; nothing here falls back to the host.
  */
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 
@@ -24,9 +25,16 @@
 #ifndef NGB_B4_MINBLOCKS
 #define NGB_B4_MINBLOCKS 2      /* 128 registers/thread, 16 warps/SM: measured 1.5x faster than 255 registers */
 #endif
-static cudaStream_t g_stream = nullptr;
+static thread_local cudaStream_t g_stream = nullptr;   /* per host thread: batches driven from different threads run concurrently */
+/* device-type load kernels of one CKTload are independent of each other: they run on side streams between a
+ * fork and a join event (parallel branches of the captured graph); g_cur is the stream a launch goes to */
+#define NGB_SIDE 4
+static thread_local cudaStream_t g_cur = nullptr, g_side[NGB_SIDE];
+static thread_local cudaEvent_t g_fork, g_join[NGB_SIDE];
+static thread_local int g_side_ready = 0, g_side_used[NGB_SIDE], g_branching = 0;
+static int g_branch_off = -1;
 static int g_device = -1;
-static long g_launches = 0;
+static std::atomic<long> g_launches{0};
 static int g_smem_optin = 0, g_sm_count = 148;
 
 extern "C" void ngb_set_error(const char *fmt, ...);
@@ -43,6 +51,35 @@ ngb_k_bsim4_load(const B4Ctx c, int *errflag)
     const int e = b4_load_thread(&c, t);
     if (e) atomicMax(errflag, e);
 }
+
+/* the four kernels of the phase-split load (bsim4_eval.cuh: b4_phase_*); register budgets per phase */
+#ifndef NGB_B4P_CTA
+#define NGB_B4P_CTA 256
+#endif
+#ifndef NGB_B4P_MB_CORE
+#define NGB_B4P_MB_CORE 2
+#endif
+#ifndef NGB_B4P_MB_PARA
+#define NGB_B4P_MB_PARA 2
+#endif
+#ifndef NGB_B4P_MB_CHRG
+#define NGB_B4P_MB_CHRG 2
+#endif
+#ifndef NGB_B4P_MB_FIN
+#define NGB_B4P_MB_FIN 2
+#endif
+#define NGB_B4_PHASE_KERNEL(name, body, mb) \
+__global__ void __launch_bounds__(NGB_B4P_CTA, mb) name(const B4Ctx c, int *errflag) \
+{ \
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; \
+    if (t >= (size_t)c.T) return; \
+    const int e = body(&c, t); \
+    if (e) atomicMax(errflag, e); \
+}
+NGB_B4_PHASE_KERNEL(ngb_k_b4_core, b4_phase_core, NGB_B4P_MB_CORE)
+NGB_B4_PHASE_KERNEL(ngb_k_b4_para, b4_phase_para, NGB_B4P_MB_PARA)
+NGB_B4_PHASE_KERNEL(ngb_k_b4_chrg, b4_phase_chrg, NGB_B4P_MB_CHRG)
+NGB_B4_PHASE_KERNEL(ngb_k_b4_fin, b4_phase_fin, NGB_B4P_MB_FIN)
 
 __global__ void __launch_bounds__(256)
 ngb_k_cap_load(const NgbCapCtx c, int *errflag)
@@ -212,6 +249,15 @@ int ngb_dev_init(int device)
     CUDA_OK(cudaSetDevice(device));
     if (g_stream) cudaStreamDestroy(g_stream);
     CUDA_OK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    g_cur = g_stream;
+    if (!g_side_ready) {
+        for (int i = 0; i < NGB_SIDE; i++) {
+            CUDA_OK(cudaStreamCreateWithFlags(&g_side[i], cudaStreamNonBlocking));
+            CUDA_OK(cudaEventCreateWithFlags(&g_join[i], cudaEventDisableTiming));
+        }
+        CUDA_OK(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+        g_side_ready = 1;
+    }
     CUDA_OK(cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CUDA_OK(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_OK(cudaFuncSetAttribute(ngb_k_lu_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
@@ -258,10 +304,10 @@ void *ngb_dev_stream(void) { return (void *)g_stream; }
 
 /* live timing of the dominant kernel: CUDA events around sampled bsim4_load launches */
 #define NGB_PROF_MAX 2048
-static int g_prof_on = 0, g_prof_every = 1, g_prof_n = 0;
-static long g_prof_seen = 0;
-static cudaEvent_t g_prof_ev[2 * NGB_PROF_MAX];
-static int g_prof_created = 0;
+static thread_local int g_prof_on = 0, g_prof_every = 1, g_prof_n = 0;
+static thread_local long g_prof_seen = 0;
+static thread_local cudaEvent_t g_prof_ev[2 * NGB_PROF_MAX];
+static thread_local int g_prof_created = 0;
 
 void ngb_dev_profile(int enable, int every)
 {
@@ -287,11 +333,11 @@ int ngb_dev_profile_read(double *ms_sum, long *count)
 int ngb_dev_set_stream(void *stream)
 {
     if (g_device < 0) return NGB_E_PANIC;
-    g_stream = (cudaStream_t)stream;
+    g_stream = (cudaStream_t)stream; g_cur = g_stream;
     return 0;
 }
 
-static int g_capturing = 0, g_prof_force = 0;
+static thread_local int g_capturing = 0, g_prof_force = 0;
 int ngb_dev_profile_due(void)
 {
     if (!g_prof_on || g_prof_n >= NGB_PROF_MAX) return 0;
@@ -324,6 +370,38 @@ int ngb_dev_graph_launch(void *exec, int nodes)
 }
 void ngb_dev_graph_destroy(void *exec) { if (exec) cudaGraphExecDestroy((cudaGraphExec_t)exec); }
 
+/* fork / join around the device-type loads of one CKTload.  A step whose bsim4_load is being timed
+ * (ngb_dev_profile_due) stays on one stream so that the kernel is measured alone. */
+int ngb_dev_branch_begin(void)
+{
+    if (g_branch_off < 0) { const char *e = getenv("NGB_NO_BRANCH"); g_branch_off = (e && atoi(e)) ? 1 : 0; }
+    g_branching = 0;
+    if (g_branch_off || !g_side_ready || g_prof_force) return 0;
+    if (cudaEventRecord(g_fork, g_stream) != cudaSuccess) { cudaGetLastError(); return 0; }
+    for (int i = 0; i < NGB_SIDE; i++) g_side_used[i] = 0;
+    g_branching = 1;
+    return 1;
+}
+void ngb_dev_branch(int i)
+{
+    if (!g_branching || i < 0) { g_cur = g_stream; return; }
+    i %= NGB_SIDE;
+    if (!g_side_used[i]) { cudaStreamWaitEvent(g_side[i], g_fork, 0); g_side_used[i] = 1; }
+    g_cur = g_side[i];
+}
+int ngb_dev_branch_end(void)
+{
+    g_cur = g_stream;
+    if (!g_branching) return 0;
+    g_branching = 0;
+    for (int i = 0; i < NGB_SIDE; i++)
+        if (g_side_used[i]) {
+            CUDA_OK(cudaEventRecord(g_join[i], g_side[i]));
+            CUDA_OK(cudaStreamWaitEvent(g_stream, g_join[i], 0));
+        }
+    return 0;
+}
+
 static int post_launch(const char *what)
 {
     cudaError_t e = cudaGetLastError();
@@ -339,44 +417,52 @@ int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag)
     /* sampled timing: forced by ngb_dev_profile_due (transient driver) or by this launch's own turn */
     const int rec = !g_capturing && g_prof_on && g_prof_n < NGB_PROF_MAX && (g_prof_force || (g_prof_seen++ % g_prof_every == 0));
     g_prof_force = 0;
-    if (rec) cudaEventRecord(g_prof_ev[2 * g_prof_n], g_stream);
-    ngb_k_bsim4_load<<<grid, NGB_B4_CTA, 0, g_stream>>>(*c, errflag);
-    if (rec) { cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], g_stream); g_prof_n++; }
+    if (rec) cudaEventRecord(g_prof_ev[2 * g_prof_n], g_cur);
+    if (c->wscr) {
+        const unsigned gp = (unsigned)(((size_t)c->T + NGB_B4P_CTA - 1) / NGB_B4P_CTA);
+        ngb_k_b4_core<<<gp, NGB_B4P_CTA, 0, g_cur>>>(*c, errflag);
+        ngb_k_b4_para<<<gp, NGB_B4P_CTA, 0, g_cur>>>(*c, errflag);
+        ngb_k_b4_chrg<<<gp, NGB_B4P_CTA, 0, g_cur>>>(*c, errflag);
+        if (!g_capturing) g_launches += 3;
+        ngb_k_b4_fin<<<gp, NGB_B4P_CTA, 0, g_cur>>>(*c, errflag);
+    } else
+    ngb_k_bsim4_load<<<grid, NGB_B4_CTA, 0, g_cur>>>(*c, errflag);
+    if (rec) { cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], g_cur); g_prof_n++; }
     return post_launch("bsim4_load");
 }
 int ngb_launch_cap_load(const NgbCapCtx *c, int *errflag)
 {
     if (c->T <= 0) return 0;
     const unsigned grid = (unsigned)(((size_t)c->T + 255) / 256);
-    ngb_k_cap_load<<<grid, 256, 0, g_stream>>>(*c, errflag);
+    ngb_k_cap_load<<<grid, 256, 0, g_cur>>>(*c, errflag);
     return post_launch("cap_load");
 }
 int ngb_launch_bsim3_load(const B3Ctx *c, int *errflag)
 {
     if (c->T <= 0) return 0;
     const unsigned grid = (unsigned)(((size_t)c->T + 255) / 256);
-    ngb_k_bsim3_load<<<grid, 256, 0, g_stream>>>(*c, errflag);
+    ngb_k_bsim3_load<<<grid, 256, 0, g_cur>>>(*c, errflag);
     return post_launch("bsim3_load");
 }
 int ngb_launch_vbic_load(const NgbVbicCtx *c, int *errflag)
 {
     if (c->T <= 0) return 0;
     const unsigned grid = (unsigned)(((size_t)c->T + 127) / 128);
-    ngb_k_vbic_load<<<grid, 128, 0, g_stream>>>(*c, errflag);
+    ngb_k_vbic_load<<<grid, 128, 0, g_cur>>>(*c, errflag);
     return post_launch("vbic_load");
 }
 int ngb_launch_dio_load(const NgbDioCtx *c, int *errflag)
 {
     if (c->T <= 0) return 0;
     const unsigned grid = (unsigned)(((size_t)c->T + 255) / 256);
-    ngb_k_dio_load<<<grid, 256, 0, g_stream>>>(*c, errflag);
+    ngb_k_dio_load<<<grid, 256, 0, g_cur>>>(*c, errflag);
     return post_launch("dio_load");
 }
 int ngb_launch_src_load(const NgbSrcCtx *c)
 {
     if (c->T <= 0) return 0;
     const unsigned grid = (unsigned)(((size_t)c->T + 255) / 256);
-    ngb_k_src_load<<<grid, 256, 0, g_stream>>>(*c);
+    ngb_k_src_load<<<grid, 256, 0, g_cur>>>(*c);
     return post_launch("src_load");
 }
 __global__ void __launch_bounds__(128)

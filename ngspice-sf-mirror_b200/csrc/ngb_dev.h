@@ -38,6 +38,12 @@ int   ngb_dev_graph_end(void **exec, int *nodes);
 int   ngb_dev_graph_launch(void *exec, int nodes);
 void  ngb_dev_graph_destroy(void *exec);                     /* cudaStream_t the kernels are launched on */
 
+/* the load kernels of the device types are independent: between begin and end, ngb_dev_branch(i) sends the
+ * following launches to side stream i (i < 0: the main stream); end joins them all into the main stream */
+int   ngb_dev_branch_begin(void);
+void  ngb_dev_branch(int i);
+int   ngb_dev_branch_end(void);
+
 int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag);
 int ngb_launch_cap_load(const NgbCapCtx *c, int *errflag);
 int ngb_launch_src_load(const NgbSrcCtx *c);

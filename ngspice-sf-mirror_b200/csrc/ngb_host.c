@@ -18,7 +18,7 @@
 #include "ngb_host.h"
 #include "../../include/ngb200.h"
 
-static char g_err[512] = "";
+static __thread char g_err[512] = "";      /* per host thread, like the launch stream */
 void ngb_set_error(const char *fmt, ...)
 {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
@@ -1409,6 +1409,12 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
         b->b4_inst = (double *)dalloc_rep(b, "b4.inst", c->b4_inst, B4I_COUNT, c->b4_n, S);
         b->b4_state = (double *)dalloc(b, "b4.state", sizeof(double) * NGB_NHIST * B4ST_COUNT * T);
         b->b4_op = (double *)dalloc(b, "b4.op", sizeof(double) * B4O_COUNT * T);
+        {   /* phase-split load (four kernels, B4W fields through a scratch array): NGB_B4_SPLIT=1 forces it,
+             * =0 forbids it; by default batches large enough to fill the chip several times use it */
+            const char *e = getenv("NGB_B4_SPLIT");
+            const int on = e ? atoi(e) : (T >= (size_t)NGB_B4_SPLIT_MIN);
+            b->b4_wscr = on ? (double *)dalloc(b, "b4.wscr", sizeof(double) * B4WF_COUNT * T) : NULL;
+        }
         b->b4_mtab = (double *)dev_dup(c->b4_mtab, sizeof(double) * (size_t)c->b4_nrows * B4M_COUNT);
         b->b4_ptab = (double *)dev_dup(c->b4_ptab, sizeof(double) * (size_t)c->b4_nrows * B4P_COUNT);
         reg(b, "b4.mtab", b->b4_mtab, sizeof(double) * (size_t)c->b4_nrows * B4M_COUNT);
@@ -1627,7 +1633,7 @@ void ngb_fill_b4ctx(ngb_batch *b, B4Ctx *x)
     x->inst = b->b4_inst; x->flags = b->b4_flags; x->nodes = b->b4_nodes; x->spos = b->b4_spos;
     x->stamp = b->stamp; x->state = b->b4_state; x->op = b->b4_op; x->op_full = b->op_full;
     x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl; x->temp = c->opt.temp; x->vt0 = c->opt.vt0;
-    x->split = c->exact_order;
+    x->split = c->exact_order; x->wscr = b->b4_wscr;
 }
 void ngb_fill_capctx(ngb_batch *b, NgbCapCtx *x)
 {
@@ -1702,13 +1708,21 @@ int ngb_enqueue_load(ngb_batch *b)
 {
     const ngb_circuit *c = b->c;
     int r;
-    if (c->b3_n) { B3Ctx x; ngb_fill_b3ctx(b, &x); if ((r = ngb_launch_bsim3_load(&x, b->errflag))) return r; }
-    if (c->b4_n) { B4Ctx x; ngb_fill_b4ctx(b, &x); if ((r = ngb_launch_bsim4_load(&x, b->errflag))) return r; }
-    if (c->cap_n) { NgbCapCtx x; ngb_fill_capctx(b, &x); if ((r = ngb_launch_cap_load(&x, b->errflag))) return r; }
-    if (c->dio_n) { NgbDioCtx x; ngb_fill_dioctx(b, &x); if ((r = ngb_launch_dio_load(&x, b->errflag))) return r; }
-    if (c->is_n) { NgbSrcCtx x; ngb_fill_srcctx(b, &x, 1); if ((r = ngb_launch_src_load(&x))) return r; }
-    if (c->vb_n) { NgbVbicCtx x; ngb_fill_vbctx(b, &x); if ((r = ngb_launch_vbic_load(&x, b->errflag))) return r; }
-    if (c->vs_n) { NgbSrcCtx x; ngb_fill_srcctx(b, &x, 0); if ((r = ngb_launch_src_load(&x))) return r; }
+    /* one branch per device type (they write disjoint stamp rows and states); the reference's order of the
+     * types only matters for the summation order, which the assembly fixes */
+    ngb_dev_branch_begin();
+    r = 0;
+    if (!r && c->b4_n) { B4Ctx x; ngb_dev_branch(-1); ngb_fill_b4ctx(b, &x); r = ngb_launch_bsim4_load(&x, b->errflag); }
+    if (!r && c->b3_n) { B3Ctx x; ngb_dev_branch(0); ngb_fill_b3ctx(b, &x); r = ngb_launch_bsim3_load(&x, b->errflag); }
+    if (!r && c->vb_n) { NgbVbicCtx x; ngb_dev_branch(1); ngb_fill_vbctx(b, &x); r = ngb_launch_vbic_load(&x, b->errflag); }
+    if (!r && c->dio_n) { NgbDioCtx x; ngb_dev_branch(2); ngb_fill_dioctx(b, &x); r = ngb_launch_dio_load(&x, b->errflag); }
+    if (!r && c->cap_n) { NgbCapCtx x; ngb_dev_branch(3); ngb_fill_capctx(b, &x); r = ngb_launch_cap_load(&x, b->errflag); }
+    if (!r && c->is_n) { NgbSrcCtx x; ngb_dev_branch(3); ngb_fill_srcctx(b, &x, 1); r = ngb_launch_src_load(&x); }
+    if (!r && c->vs_n) { NgbSrcCtx x; ngb_dev_branch(3); ngb_fill_srcctx(b, &x, 0); r = ngb_launch_src_load(&x); }
+    {
+        const int rj = ngb_dev_branch_end();
+        if (r || rj) return r ? r : rj;
+    }
     { NgbAsmCtx x; ngb_fill_asmctx(b, &x); if ((r = ngb_launch_assemble(&x))) return r; }
     return NGB_OK;
 }
