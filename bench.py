@@ -216,6 +216,7 @@ def workload_config(args):
     return {"workload": "Monte Carlo transient, 17-stage BSIM4 ring oscillator (ro_17_4.cir cards, version 4.8.3), "
                         ".tran .1ns 150ns uic, per-instance delvto mismatch sigma 15 mV and per-sample toxe from 8 levels of N(1.4 nm, 3 %)",
             "samples_per_gpu": args.samples, "bsim4_instances": 34, "unknowns": 155,
+            "layout": "draws unsorted" if os.environ.get("NGB_BENCH_UNSORTED") else "samples laid out level by level (same draws)",
             "l2": "inputs larger than L2: per-step working set (parameters+states+stamps+matrices) ~%.0f MB" %
                   (args.samples * 34 * (51 + 4 * 29 + 38 + 52) * 8 / 1e6 + args.samples * 904 * 8 / 1e6)}
 
@@ -259,6 +260,10 @@ def bench_ours(args):
         dv = pkg.mc.delvto_as_parsed(pkg.mc.draw_delvto(S, ninst, sigma=0.015, seed=1000 + rank))
         tox_tables = ngt.read(f"{GOLDEN}/ro17tox.tables.ngt")
         level = np.random.default_rng(5000 + rank).integers(0, len(tox_tables["levels"]), size=S)
+        if not os.environ.get("NGB_BENCH_UNSORTED"):
+            # same draws, laid out level by level: a warp's 32 samples then share their parameter rows
+            order = pkg.mc.group_by_level(level)
+            level, dv = level[order], dv[order]
         inst_host, prow_t, mtab_all, ptab_all = pkg.mc.bsim4_with_tox_levels(lib, flat, tox_tables, level, dv)
         batch.set_bsim4_rows(prow_t, mtab_all, ptab_all)
     pinned = torch.empty(inst_host.shape, dtype=torch.float64).pin_memory()

@@ -59,6 +59,14 @@ def bsim4_with_tox_levels(lib, flat, tables, level, delvto):
     return inst, prow_t, mtab, ptab
 
 
+def group_by_level(level):
+    """Batch layout for model-parameter mismatch: positions of the samples ordered by parameter level (stable),
+    so that the 32 consecutive samples a warp evaluates read the SAME model / bin rows (one cache line per
+    parameter instead of up to one per level).  Returns `order` with batch position p holding draw order[p];
+    results come back in batch order, `inverse = np.argsort(order)` puts them in draw order again."""
+    return np.argsort(np.asarray(level), kind="stable")
+
+
 def spice_number(text):
     """the value the reference front end gives a numeric token (digits, '.', e+-NN, scale suffix), which
     is not always the nearest double: INPevaluate accumulates the digits into a double mantissa
