@@ -645,7 +645,8 @@ def bench_sweep(args):
 
     batch.put("vsrc.par", vpar)
     batch.set_resistors(gtab)
-    for _ in range(args.warmup):
+    res = None
+    for _ in range(max(args.warmup, 1)):                         # the completion check below needs one run at least
         res = step(False)
     bad = int((res.accepted.astype(np.int64) < 100).sum())       # points whose transient did not run through
 

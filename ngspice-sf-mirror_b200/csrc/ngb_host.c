@@ -884,10 +884,20 @@ static void build_packed(ngb_circuit *c)
     p->blob = b; p->aslot = aslot; p->arow = arow; p->ext = ext;
     p->row_ptr = h->row_ptr; p->row_slot = h->row_slot; p->b_eq = h->b_eq; p->out_eq = h->out_eq;
     p->ok = 1;
-    /* ---- second packing: records instead of parallel index arrays (ngb_lu_sample_pk2) ---- */
+    /* ---- second packing: records instead of parallel index arrays (ngb_lu_sample_pk2) ----
+     * A level is a list of ITEMS {first product, last product, pivot, target value}.  The subtractions of a value
+     * are ordered, but the leading ones whose operands are two or more levels old do not have to wait for the
+     * value's own level: they become a second item one level earlier (run by an idle lane, off the critical
+     * path), and the value's own item keeps only the late products and the division.  Same operations, same
+     * order per value. */
     do {
         const int neq1 = c->neq + 1;
-        int off2 = 0, lev0 = 0, slev0 = 0, e0, e2, *eqtask;
+        const int hoist = getenv("NGB_LU_NOHOIST") ? 0 : 1;
+        int off2 = 0, lev0 = 0, slev0 = 0, e0, e2, *eqtask, L, nit = 0, nsit = 0, np2 = 0, nsp2 = 0, maxlp2 = 1;
+        int *lv = NULL, *tlv = NULL;
+        /* items: lev, p0 (into the level-ordered pair list), count, div, target, start (solve) */
+        struct item { int lev, src0, cnt, dv, tgt, start, pre; } *fi = NULL, *si = NULL;
+        int *fi_ptr = NULL, *si_ptr = NULL;
         unsigned short *b2;
         if (neq1 >= 65535) break;
         /* leading levels whose entries have neither products nor a pivot division stay as initialised */
@@ -915,64 +925,128 @@ static void build_packed(ngb_circuit *c)
             eqtask[eq] = tint[h->out_task[k]];
         }
         if (eqtask[0] == -1) { free(eqtask); break; }
+
+        /* items of the factorisation */
+        lv = (int *)xcalloc((size_t)nV + 1, sizeof(int)); tlv = (int *)xcalloc((size_t)ntask + 1, sizeof(int));
+        for (L = 0; L < h->nlev; L++) for (k = h->lev_ptr[L]; k < h->lev_ptr[L + 1]; k++) lv[k] = L;
+        for (L = 0; L < h->nslev; L++) for (k = h->slev_ptr[L]; k < h->slev_ptr[L + 1]; k++) tlv[k] = L;
+        fi = (struct item *)xcalloc(2 * (size_t)nV + 2, sizeof *fi);
+        for (k = e0; k < nV; k++) {
+            const int q0 = b[p->o_pptr + k], q1 = b[p->o_pptr + k + 1];
+            int m = 0;
+            L = lv[k];
+            if (hoist && L - 1 >= lev0)
+                while (q0 + m < q1 && lv[b[p->o_pl + q0 + m]] <= L - 2 && lv[b[p->o_pu + q0 + m]] <= L - 2) m++;
+            if (m >= 1) { struct item t = { L - 1, q0, m, 0xFFFF, k, 0, 1 }; fi[nit++] = t; }
+            { struct item t = { L, q0 + m, q1 - q0 - m, b[p->o_div + k], k, 0, 0 }; fi[nit++] = t; }
+        }
+        /* items of the solve: a backward task starts from its forward task's value, which must be old enough too */
+        si = (struct item *)xcalloc(2 * (size_t)ntask + 2, sizeof *si);
+        for (k = h->slev_ptr[slev0]; k < ntask; k++) {
+            const int q0 = b[p->o_tpptr + k], q1 = b[p->o_tpptr + k + 1];
+            const int kind = b[p->o_kind + k];
+            const int start = kind == 0 ? k : b[p->o_init + k];
+            int m = 0;
+            L = tlv[k];
+            if (hoist && L - 1 >= slev0 && (start == k || tlv[start] <= L - 2))
+                while (q0 + m < q1 && tlv[b[p->o_tsrc + q0 + m]] <= L - 2) m++;      /* the LU values are all final by now */
+            if (m >= 1) { struct item t = { L - 1, q0, m, 0xFFFF, k, start, 1 }; si[nsit++] = t; }
+            { struct item t = { L, q0 + m, q1 - q0 - m, kind == 1 ? b[p->o_tdiv + k] : 0xFFFF, k, m >= 1 ? k : start, 0 }; si[nsit++] = t; }
+        }
+        if (nit >= 65535 || nsit >= 65535) { free(eqtask); free(lv); free(tlv); free(fi); free(si); break; }
+        /* level by level: the value's own items first, then the hoisted ones */
+        fi_ptr = (int *)xcalloc((size_t)h->nlev + 2, sizeof(int)); si_ptr = (int *)xcalloc((size_t)h->nslev + 2, sizeof(int));
 #define SEG2(field, cnt, width) off2 = (off2 + 3) & ~3; p->field = off2; off2 += (cnt) * (width)
-        SEG2(o2_levd, h->nlev, 4); SEG2(o2_emeta, nV - e0, 4); SEG2(o2_pair, np, 2); SEG2(o2_diag, n, 1);
+        SEG2(o2_levd, h->nlev, 4); SEG2(o2_emeta, nit, 4); SEG2(o2_pair, np, 2); SEG2(o2_diag, n, 1);
         SEG2(o2_slotmap, h->nnz, 2); SEG2(o2_rowptr, n + 1, 1); SEG2(o2_rowv, h->nnz, 1);
-        SEG2(o2_slevd, h->nslev, 4); SEG2(o2_tmeta, ntask, 4); SEG2(o2_tpair, nsp, 2);
+        SEG2(o2_slevd, h->nslev, 4); SEG2(o2_tmeta, nsit, 4); SEG2(o2_ttgt, nsit, 1); SEG2(o2_tpair, nsp, 2);
         SEG2(o2_yinit, n, 4); SEG2(o2_eqtask, neq1, 1);
 #undef SEG2
         off2 = (off2 + 3) & ~3;
         b2 = (unsigned short *)xcalloc((size_t)off2 + 4, sizeof(unsigned short));
-        for (k = 0; k < h->nlev; k++) {
-            unsigned short *r = b2 + p->o2_levd + 4 * k;
-            r[0] = (unsigned short)h->lev_ptr[k]; r[1] = (unsigned short)h->lev_ptr[k + 1];
-            r[2] = b[p->o_pptr + h->lev_ptr[k]]; r[3] = b[p->o_pptr + h->lev_ptr[k + 1]];
+        {
+            int it = 0, pass, i2;
+            for (L = 0; L < h->nlev; L++) {
+                unsigned short *r = b2 + p->o2_levd + 4 * L;
+                const int it0 = it, pb = np2;
+                for (pass = 0; pass < 2; pass++)
+                    for (i2 = 0; i2 < nit; i2++) {
+                        unsigned short *m;
+                        int q;
+                        if (fi[i2].lev != L || fi[i2].pre != pass) continue;
+                        m = b2 + p->o2_emeta + 4 * it++;
+                        m[0] = (unsigned short)np2; m[1] = (unsigned short)(np2 + fi[i2].cnt); m[2] = (unsigned short)fi[i2].dv; m[3] = (unsigned short)fi[i2].tgt;
+                        for (q = 0; q < fi[i2].cnt; q++, np2++) {
+                            b2[p->o2_pair + 2 * np2] = b[p->o_pl + fi[i2].src0 + q];
+                            b2[p->o2_pair + 2 * np2 + 1] = b[p->o_pu + fi[i2].src0 + q];
+                        }
+                    }
+                r[0] = (unsigned short)it0; r[1] = (unsigned short)it; r[2] = (unsigned short)pb; r[3] = (unsigned short)np2;
+                if (np2 - pb > maxlp2) maxlp2 = np2 - pb;
+                fi_ptr[L + 1] = it;
+            }
+            it = 0;
+            for (L = 0; L < h->nslev; L++) {
+                unsigned short *r = b2 + p->o2_slevd + 4 * L;
+                const int it0 = it, pb = nsp2;
+                for (pass = 0; pass < 2; pass++)
+                    for (i2 = 0; i2 < nsit; i2++) {
+                        unsigned short *m;
+                        int q;
+                        if (si[i2].lev != L || si[i2].pre != pass) continue;
+                        b2[p->o2_ttgt + it] = (unsigned short)si[i2].tgt;
+                        m = b2 + p->o2_tmeta + 4 * it++;
+                        m[0] = (unsigned short)nsp2; m[1] = (unsigned short)(nsp2 + si[i2].cnt); m[2] = (unsigned short)si[i2].start; m[3] = (unsigned short)si[i2].dv;
+                        for (q = 0; q < si[i2].cnt; q++, nsp2++) {
+                            b2[p->o2_tpair + 2 * nsp2] = b[p->o_tval + si[i2].src0 + q];
+                            b2[p->o2_tpair + 2 * nsp2 + 1] = b[p->o_tsrc + si[i2].src0 + q];
+                        }
+                    }
+                r[0] = (unsigned short)it0; r[1] = (unsigned short)it; r[2] = (unsigned short)pb; r[3] = (unsigned short)nsp2;
+                if (nsp2 - pb > maxlp2) maxlp2 = nsp2 - pb;
+                si_ptr[L + 1] = it;
+            }
         }
-        for (k = e0; k < nV; k++) {
-            unsigned short *r = b2 + p->o2_emeta + 4 * (k - e0);
-            r[0] = b[p->o_pptr + k]; r[1] = b[p->o_pptr + k + 1]; r[2] = b[p->o_div + k]; r[3] = 0;
-        }
-        for (k = 0; k < np; k++) { b2[p->o2_pair + 2 * k] = b[p->o_pl + k]; b2[p->o2_pair + 2 * k + 1] = b[p->o_pu + k]; }
         for (k = 0; k < n; k++) b2[p->o2_diag + k] = b[p->o_diag + k];
         for (k = 0; k < h->nnz; k++) { b2[p->o2_slotmap + 2 * k] = 0xFFFF; b2[p->o2_slotmap + 2 * k + 1] = 0; }
         for (k = 0; k < nV; k++)
             if (aslot[k] >= 0) { b2[p->o2_slotmap + 2 * aslot[k]] = (unsigned short)k; b2[p->o2_slotmap + 2 * aslot[k] + 1] = (unsigned short)arow[k]; }
         for (k = 0; k <= n; k++) b2[p->o2_rowptr + k] = (unsigned short)h->row_ptr[k];
         {
-            int bad = 0;
+            int bad = (np2 != np || nsp2 != nsp);           /* every product exactly once */
             for (k = 0; k < h->nnz; k++) {
                 const int v = b2[p->o2_slotmap + 2 * h->row_slot[k]];
                 if (v == 0xFFFF) bad = 1;               /* an entry of A outside the factors: first packing only */
                 b2[p->o2_rowv + k] = (unsigned short)v;
             }
-            if (bad) { free(b2); free(eqtask); break; }
+            q = 0;
+            for (k = 0; k < ntask && !bad; k++)
+                if (b[p->o_kind + k] == 0) {
+                    unsigned short *y = b2 + p->o2_yinit + 4 * q;
+                    const int row = b[p->o_init + k];
+                    if (q >= n) { bad = 1; break; }
+                    y[0] = (unsigned short)k; y[1] = (unsigned short)row; y[2] = (unsigned short)h->b_eq[row]; y[3] = 0;
+                    q++;
+                }
+            if (q != n) bad = 1;
+            if (bad) { free(b2); free(eqtask); free(lv); free(tlv); free(fi); free(si); free(fi_ptr); free(si_ptr); break; }
         }
-        for (k = 0; k < h->nslev; k++) {
-            unsigned short *r = b2 + p->o2_slevd + 4 * k;
-            r[0] = (unsigned short)h->slev_ptr[k]; r[1] = (unsigned short)h->slev_ptr[k + 1];
-            r[2] = b[p->o_tpptr + h->slev_ptr[k]]; r[3] = b[p->o_tpptr + h->slev_ptr[k + 1]];
-        }
-        q = 0;
-        for (k = 0; k < ntask; k++) {
-            unsigned short *r = b2 + p->o2_tmeta + 4 * k;
-            const int kind = b[p->o_kind + k];
-            r[0] = b[p->o_tpptr + k]; r[1] = b[p->o_tpptr + k + 1];
-            r[2] = (unsigned short)(kind == 0 ? k : b[p->o_init + k]);
-            r[3] = (unsigned short)(kind == 1 ? b[p->o_tdiv + k] : 0xFFFF);
-            if (kind == 0) {
-                unsigned short *y = b2 + p->o2_yinit + 4 * q;
-                const int row = b[p->o_init + k];
-                if (q >= n) { q = n + 1; break; }
-                y[0] = (unsigned short)k; y[1] = (unsigned short)row; y[2] = (unsigned short)h->b_eq[row]; y[3] = 0;
-                q++;
+        for (k = 0; k < neq1; k++) b2[p->o2_eqtask + k] = (unsigned short)eqtask[k];
+        if (maxlp2 > p->maxlp) p->maxlp = maxlp2;
+        p->lev0 = lev0; p->e0 = e0; p->slev0 = slev0; p->blob2 = b2; p->blob2_u16 = off2; p->ok2 = 1;
+        if (getenv("NGB_LU_STATS")) {
+            int npre = 0, nspre = 0, i2;
+            for (i2 = 0; i2 < nit; i2++) npre += fi[i2].pre;
+            for (i2 = 0; i2 < nsit; i2++) nspre += si[i2].pre;
+            fprintf(stderr, "lu second packing: %d u16, first factor level %d, first solve level %d, %d + %d hoisted prefixes, most products per level %d\n",
+                    off2, lev0, slev0, npre, nspre, p->maxlp);
+            for (L = lev0; L < h->nlev; L++) {
+                int mx = 0;
+                for (i2 = 0; i2 < nit; i2++) if (fi[i2].lev == L && !fi[i2].pre && fi[i2].cnt > mx) mx = fi[i2].cnt;
+                fprintf(stderr, "  factor level %d: %d items, longest own row %d\n", L, fi_ptr[L + 1] - fi_ptr[L], mx);
             }
         }
-        if (q != n) { free(b2); free(eqtask); break; }
-        for (k = 0; k < nsp; k++) { b2[p->o2_tpair + 2 * k] = b[p->o_tval + k]; b2[p->o2_tpair + 2 * k + 1] = b[p->o_tsrc + k]; }
-        for (k = 0; k < neq1; k++) b2[p->o2_eqtask + k] = (unsigned short)eqtask[k];
-        free(eqtask);
-        p->lev0 = lev0; p->e0 = e0; p->slev0 = slev0; p->blob2 = b2; p->blob2_u16 = off2; p->ok2 = 1;
-        if (getenv("NGB_LU_STATS")) fprintf(stderr, "lu second packing: %d u16, first factor level %d (value %d), first solve level %d\n", off2, lev0, e0, slev0);
+        free(eqtask); free(lv); free(tlv); free(fi); free(si); free(fi_ptr); free(si_ptr);
     } while (0);
     free(vint); free(tint);
 }
@@ -1712,13 +1786,14 @@ int ngb_enqueue_load(ngb_batch *b)
      * types only matters for the summation order, which the assembly fixes */
     ngb_dev_branch_begin();
     r = 0;
-    if (!r && c->b4_n) { B4Ctx x; ngb_dev_branch(-1); ngb_fill_b4ctx(b, &x); r = ngb_launch_bsim4_load(&x, b->errflag); }
-    if (!r && c->b3_n) { B3Ctx x; ngb_dev_branch(0); ngb_fill_b3ctx(b, &x); r = ngb_launch_bsim3_load(&x, b->errflag); }
+    /* the small, latency-bound kernels first: their few CTAs are resident when the BSIM4 load fills the rest */
     if (!r && c->vb_n) { NgbVbicCtx x; ngb_dev_branch(1); ngb_fill_vbctx(b, &x); r = ngb_launch_vbic_load(&x, b->errflag); }
+    if (!r && c->b3_n) { B3Ctx x; ngb_dev_branch(0); ngb_fill_b3ctx(b, &x); r = ngb_launch_bsim3_load(&x, b->errflag); }
     if (!r && c->dio_n) { NgbDioCtx x; ngb_dev_branch(2); ngb_fill_dioctx(b, &x); r = ngb_launch_dio_load(&x, b->errflag); }
     if (!r && c->cap_n) { NgbCapCtx x; ngb_dev_branch(3); ngb_fill_capctx(b, &x); r = ngb_launch_cap_load(&x, b->errflag); }
     if (!r && c->is_n) { NgbSrcCtx x; ngb_dev_branch(3); ngb_fill_srcctx(b, &x, 1); r = ngb_launch_src_load(&x); }
     if (!r && c->vs_n) { NgbSrcCtx x; ngb_dev_branch(3); ngb_fill_srcctx(b, &x, 0); r = ngb_launch_src_load(&x); }
+    if (!r && c->b4_n) { B4Ctx x; ngb_dev_branch(-1); ngb_fill_b4ctx(b, &x); r = ngb_launch_bsim4_load(&x, b->errflag); }
     {
         const int rj = ngb_dev_branch_end();
         if (r || rj) return r ? r : rj;

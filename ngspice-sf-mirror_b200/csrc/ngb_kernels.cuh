@@ -629,7 +629,7 @@ NGB_HD void ngb_lu_sample_pk2(const NgbLuCtx *c, const unsigned short *sb, int s
     const NgbLuPacked *h = &c->pk;
     const int S = c->S, n = h->n, nV = h->nV;
     const NgbRec *levd = (const NgbRec *)(sb + h->o2_levd);
-    const NgbRec *emeta = (const NgbRec *)(sb + h->o2_emeta) - h->e0;
+    const NgbRec *emeta = (const NgbRec *)(sb + h->o2_emeta);
     const unsigned *pair = (const unsigned *)(sb + h->o2_pair);
     const unsigned short *diag = sb + h->o2_diag;
     if (!NGB_LDG(&c->ctl.active[s])) return;
@@ -683,11 +683,12 @@ NGB_UNROLL
                     }
                     NGB_GROUP_SYNC();
                 }
-                for (int e = lo + lane; e < hi; e += nl) {
-                    const NgbRec m = emeta[e];
+                for (int it = lo + lane; it < hi; it += nl) {           /* items: own rows first, hoisted prefixes after */
+                    const NgbRec m = emeta[it];
                     const double *pp = P + ((int)(m.x & 0xFFFFu) - pbase);
                     const int cnt = (int)(m.x >> 16) - (int)(m.x & 0xFFFFu);
                     const unsigned dv = m.y & 0xFFFFu;
+                    const int e = (int)(m.y >> 16);
                     double v = V[e];
 NGB_UNROLL4
                     for (int k = 0; k < cnt; k++) v = NGB_DSUB(v, pp[k]);
@@ -717,6 +718,7 @@ NGB_UNROLL4
         const NgbRec *slevd = (const NgbRec *)(sb + h->o2_slevd);
         const NgbRec *tmeta = (const NgbRec *)(sb + h->o2_tmeta);
         const unsigned *tpair = (const unsigned *)(sb + h->o2_tpair);
+        const unsigned short *ttgt = sb + h->o2_ttgt;
         const NgbRec *yinit = (const NgbRec *)(sb + h->o2_yinit);
         const unsigned short *eqtask = sb + h->o2_eqtask;
         const int xs = NGB_LDG(&c->ctl.xsel[s]);
@@ -750,8 +752,9 @@ NGB_UNROLL
                     }
                     NGB_GROUP_SYNC();
                 }
-                for (int tk = lo + lane; tk < hi; tk += nl) {
-                    const NgbRec m = tmeta[tk];
+                for (int it = lo + lane; it < hi; it += nl) {
+                    const NgbRec m = tmeta[it];
+                    const int tk = ttgt[it];
                     const double *pp = P + ((int)(m.x & 0xFFFFu) - pbase);
                     const int cnt = (int)(m.x >> 16) - (int)(m.x & 0xFFFFu);
                     const unsigned dv = m.y >> 16;

@@ -171,14 +171,15 @@ typedef struct NgbLuPacked {
     int blob2_u16;          /* length of blob2 in 16-bit words (multiple of 4)            */
     int lev0, e0;           /* first factor level with work, first value of that level    */
     int slev0;              /* first solve level with work                                */
-    int o2_levd;            /* [nlev]  {lo, hi, pbase, pend}                              */
-    int o2_emeta;           /* [nV-e0] {p0, p1, div or 0xFFFF, 0}                         */
+    int o2_levd;            /* [nlev]  {first item, last item, pbase, pend}               */
+    int o2_emeta;           /* [items] {p0, p1, div or 0xFFFF, target value}              */
     int o2_pair;            /* [np]    {l, u}                                             */
     int o2_diag;            /* [n]                                                        */
     int o2_slotmap;         /* [nnz]   {value, row} of A slot j                           */
     int o2_rowptr, o2_rowv; /* [n+1], [nnz] values of row i (row scale factors)           */
     int o2_slevd;           /* [nslev] {lo, hi, pbase, pend}                              */
-    int o2_tmeta;           /* [ntask] {p0, p1, start task, div or 0xFFFF}                */
+    int o2_tmeta;           /* [items] {p0, p1, start task, div or 0xFFFF}                */
+    int o2_ttgt;            /* [items] target task                                        */
     int o2_tpair;           /* [nsp]   {value, source task}                               */
     int o2_yinit;           /* [n]     {task, row, equation, 0} of the forward solve      */
     int o2_eqtask;          /* [neq1]  task holding the solution of equation i, 0xFFFF none */
