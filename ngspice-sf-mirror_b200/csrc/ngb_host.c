@@ -930,28 +930,47 @@ static void build_packed(ngb_circuit *c)
         lv = (int *)xcalloc((size_t)nV + 1, sizeof(int)); tlv = (int *)xcalloc((size_t)ntask + 1, sizeof(int));
         for (L = 0; L < h->nlev; L++) for (k = h->lev_ptr[L]; k < h->lev_ptr[L + 1]; k++) lv[k] = L;
         for (L = 0; L < h->nslev; L++) for (k = h->slev_ptr[L]; k < h->slev_ptr[L + 1]; k++) tlv[k] = L;
-        fi = (struct item *)xcalloc(2 * (size_t)nV + 2, sizeof *fi);
+        /* every product is subtracted in the first level in which (a) both operands are final and (b) the product
+         * before it in the value's order has been subtracted: runs of products per (value, level) */
+        fi = (struct item *)xcalloc((size_t)nV + (size_t)np + 2, sizeof *fi);
         for (k = e0; k < nV; k++) {
             const int q0 = b[p->o_pptr + k], q1 = b[p->o_pptr + k + 1];
-            int m = 0;
+            int q = q0, sprev = lev0;
             L = lv[k];
-            if (hoist && L - 1 >= lev0)
-                while (q0 + m < q1 && lv[b[p->o_pl + q0 + m]] <= L - 2 && lv[b[p->o_pu + q0 + m]] <= L - 2) m++;
-            if (m >= 1) { struct item t = { L - 1, q0, m, 0xFFFF, k, 0, 1 }; fi[nit++] = t; }
-            { struct item t = { L, q0 + m, q1 - q0 - m, b[p->o_div + k], k, 0, 0 }; fi[nit++] = t; }
+            while (q < q1) {
+                int plv = lv[b[p->o_pl + q]] > lv[b[p->o_pu + q]] ? lv[b[p->o_pl + q]] : lv[b[p->o_pu + q]], run = q, sl;
+                sl = plv + 1 > sprev ? plv + 1 : sprev;
+                if (!hoist || sl > L) sl = L;
+                while (run < q1) {
+                    int pl2 = lv[b[p->o_pl + run]] > lv[b[p->o_pu + run]] ? lv[b[p->o_pl + run]] : lv[b[p->o_pu + run]];
+                    if (hoist && pl2 + 1 > sl && sl < L) break;
+                    run++;
+                }
+                if (sl < L) { struct item t = { sl, q, run - q, 0xFFFF, k, 0, 1 }; fi[nit++] = t; q = run; sprev = sl; }
+                else break;                                  /* the rest belongs to the value's own level */
+            }
+            { struct item t = { L, q, q1 - q, b[p->o_div + k], k, 0, 0 }; fi[nit++] = t; }
         }
-        /* items of the solve: a backward task starts from its forward task's value, which must be old enough too */
-        si = (struct item *)xcalloc(2 * (size_t)ntask + 2, sizeof *si);
+        /* items of the solve: a backward task starts from its forward task's value, which must be final first */
+        si = (struct item *)xcalloc((size_t)ntask + (size_t)nsp + 2, sizeof *si);
         for (k = h->slev_ptr[slev0]; k < ntask; k++) {
             const int q0 = b[p->o_tpptr + k], q1 = b[p->o_tpptr + k + 1];
             const int kind = b[p->o_kind + k];
-            const int start = kind == 0 ? k : b[p->o_init + k];
-            int m = 0;
+            int start = kind == 0 ? k : b[p->o_init + k];
+            int q = q0, sprev = slev0;
             L = tlv[k];
-            if (hoist && L - 1 >= slev0 && (start == k || tlv[start] <= L - 2))
-                while (q0 + m < q1 && tlv[b[p->o_tsrc + q0 + m]] <= L - 2) m++;      /* the LU values are all final by now */
-            if (m >= 1) { struct item t = { L - 1, q0, m, 0xFFFF, k, start, 1 }; si[nsit++] = t; }
-            { struct item t = { L, q0 + m, q1 - q0 - m, kind == 1 ? b[p->o_tdiv + k] : 0xFFFF, k, m >= 1 ? k : start, 0 }; si[nsit++] = t; }
+            if (start != k && tlv[start] + 1 > sprev) sprev = tlv[start] + 1;
+            while (q < q1) {
+                int run = q, sl = tlv[b[p->o_tsrc + q]] + 1 > sprev ? tlv[b[p->o_tsrc + q]] + 1 : sprev;
+                if (!hoist || sl > L) sl = L;
+                while (run < q1) {
+                    if (hoist && tlv[b[p->o_tsrc + run]] + 1 > sl && sl < L) break;
+                    run++;
+                }
+                if (sl < L) { struct item t = { sl, q, run - q, 0xFFFF, k, start, 1 }; si[nsit++] = t; q = run; sprev = sl; start = k; }
+                else break;
+            }
+            { struct item t = { L, q, q1 - q, kind == 1 ? b[p->o_tdiv + k] : 0xFFFF, k, start, 0 }; si[nsit++] = t; }
         }
         if (nit >= 65535 || nsit >= 65535) { free(eqtask); free(lv); free(tlv); free(fi); free(si); break; }
         /* level by level: the value's own items first, then the hoisted ones */
@@ -1038,12 +1057,17 @@ static void build_packed(ngb_circuit *c)
             int npre = 0, nspre = 0, i2;
             for (i2 = 0; i2 < nit; i2++) npre += fi[i2].pre;
             for (i2 = 0; i2 < nsit; i2++) nspre += si[i2].pre;
-            fprintf(stderr, "lu second packing: %d u16, first factor level %d, first solve level %d, %d + %d hoisted prefixes, most products per level %d\n",
+            fprintf(stderr, "lu second packing: %d u16, first factor level %d, first solve level %d, %d + %d early runs, most products per level %d\n",
                     off2, lev0, slev0, npre, nspre, p->maxlp);
             for (L = lev0; L < h->nlev; L++) {
                 int mx = 0;
-                for (i2 = 0; i2 < nit; i2++) if (fi[i2].lev == L && !fi[i2].pre && fi[i2].cnt > mx) mx = fi[i2].cnt;
-                fprintf(stderr, "  factor level %d: %d items, longest own row %d\n", L, fi_ptr[L + 1] - fi_ptr[L], mx);
+                for (i2 = 0; i2 < nit; i2++) if (fi[i2].lev == L && fi[i2].cnt > mx) mx = fi[i2].cnt;
+                fprintf(stderr, "  factor level %d: %d items, longest run %d\n", L, fi_ptr[L + 1] - fi_ptr[L], mx);
+            }
+            for (L = slev0; L < h->nslev; L++) {
+                int mx = 0;
+                for (i2 = 0; i2 < nsit; i2++) if (si[i2].lev == L && si[i2].cnt > mx) mx = si[i2].cnt;
+                fprintf(stderr, "  solve level %d: %d items, longest run %d\n", L, si_ptr[L + 1] - si_ptr[L], mx);
             }
         }
         free(eqtask); free(lv); free(tlv); free(fi); free(si); free(fi_ptr); free(si_ptr);

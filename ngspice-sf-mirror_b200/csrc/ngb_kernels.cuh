@@ -664,7 +664,8 @@ NGB_UNROLL
             Rs[i] = r;
         }
         NGB_GROUP_SYNC();
-        for (int j = lane; j < nnz; j += nl) {
+        NGB_UNROLL4
+        for (int j = lane; j < nnz; j += nl) {           /* independent divisions: four in flight per lane */
             const unsigned w = slotmap[j];
             const int e = (int)(w & 0xFFFFu);
             V[e] = V[e] / Rs[w >> 16];
