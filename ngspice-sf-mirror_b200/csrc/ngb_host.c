@@ -1001,7 +1001,12 @@ static void build_packed(ngb_circuit *c)
                         }
                     }
                 r[0] = (unsigned short)it0; r[1] = (unsigned short)it; r[2] = (unsigned short)pb; r[3] = (unsigned short)np2;
-                if (np2 - pb > maxlp2) maxlp2 = np2 - pb;
+                {   /* no run longer than one product: the items multiply for themselves (empty product range = no first phase) */
+                    int direct = 1;
+                    for (i2 = 0; i2 < nit; i2++) if (fi[i2].lev == L && fi[i2].cnt > 1) direct = 0;
+                    if (direct) r[3] = r[2];
+                    else if (np2 - pb > maxlp2) maxlp2 = np2 - pb;
+                }
                 fi_ptr[L + 1] = it;
             }
             it = 0;
@@ -1022,7 +1027,12 @@ static void build_packed(ngb_circuit *c)
                         }
                     }
                 r[0] = (unsigned short)it0; r[1] = (unsigned short)it; r[2] = (unsigned short)pb; r[3] = (unsigned short)nsp2;
-                if (nsp2 - pb > maxlp2) maxlp2 = nsp2 - pb;
+                {
+                    int direct = 1;
+                    for (i2 = 0; i2 < nsit; i2++) if (si[i2].lev == L && si[i2].cnt > 1) direct = 0;
+                    if (direct) r[3] = r[2];
+                    else if (nsp2 - pb > maxlp2) maxlp2 = nsp2 - pb;
+                }
                 si_ptr[L + 1] = it;
             }
         }

@@ -691,8 +691,13 @@ NGB_UNROLL
                     const unsigned dv = m.y & 0xFFFFu;
                     const int e = (int)(m.y >> 16);
                     double v = V[e];
+                    if (pend > pbase) {
 NGB_UNROLL4
-                    for (int k = 0; k < cnt; k++) v = NGB_DSUB(v, pp[k]);
+                        for (int k = 0; k < cnt; k++) v = NGB_DSUB(v, pp[k]);
+                    } else if (cnt) {                 /* level of single products: no first phase, multiply here */
+                        const unsigned w = pair[m.x & 0xFFFFu];
+                        v = NGB_DSUB(v, NGB_DMUL(V[w & 0xFFFFu], V[w >> 16]));
+                    }
                     if (dv != 0xFFFFu) v = v / V[dv];
                     V[e] = v;
                 }
@@ -760,8 +765,13 @@ NGB_UNROLL
                     const int cnt = (int)(m.x >> 16) - (int)(m.x & 0xFFFFu);
                     const unsigned dv = m.y >> 16;
                     double z = Z[m.y & 0xFFFFu];
+                    if (pend > pbase) {
 NGB_UNROLL4
-                    for (int k = 0; k < cnt; k++) z = NGB_DSUB(z, pp[k]);
+                        for (int k = 0; k < cnt; k++) z = NGB_DSUB(z, pp[k]);
+                    } else if (cnt) {
+                        const unsigned w = tpair[m.x & 0xFFFFu];
+                        z = NGB_DSUB(z, NGB_DMUL(V[w & 0xFFFFu], Z[w >> 16]));
+                    }
                     if (dv != 0xFFFFu) z = z / V[dv];
                     Z[tk] = z;
                 }
