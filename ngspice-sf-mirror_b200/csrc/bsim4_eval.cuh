@@ -70,6 +70,8 @@ typedef struct B4Ctx {
     int op_full;               /* 0: keep only von ; 1: export every B4O_* (parity runs) */
     int split;                 /* 1: exact-order stamps (B4X_* rows live), 0: merged      */
     double *wscr;              /* [B4WF_COUNT][T] B4W fields in flight between the kernels of the phase-split load; NULL: one kernel */
+    int lte_deferred;          /* 1: BSIM4trunc runs in its own launch after the solve, for converged samples only (b4_lte_thread) */
+    const int *nodeconv;       /* [S] node part of NIconvTest (LU kernel), read by b4_lte_thread            */
     const double *x;           /* [2][neq1][S] solution buffers; xsel[s] picks CKTrhsOld  */
     int neq1;                  /* equations + 1 (row 0 is ground)                         */
     NgbCtl ctl;                /* per-sample control block                                */
@@ -3028,6 +3030,44 @@ NGB_HD int b4_phase_fin(const B4Ctx *c, size_t t)
     B4Pro p; int err;
     if (!b4_prologue(c, t, 0, &p, &err)) return NGB_OK;
     return b4_finish_lazy(c, t, &p, (const B4W *)0);
+}
+
+/* ---- BSIM4trunc out of the load ------------------------------------------------------------------
+ * The reference calls DEVtrunc once per converged time point (CKTtrunc, dctran.c:794); evaluated inside every
+ * load it was a fifth of the kernel's instructions (10 copies of CKTterr, 70 of the 313 divisions).  With
+ * lte_deferred the load skips it and this thread runs after SMPsolve + NIconvTest, only for samples whose
+ * iteration can be the converged one (transient, MODEINITFLOAT, CKTnoncon == 0, node test passed -- a superset
+ * of NIiter's own decision, which the controller takes afterwards).  It reads the same states the load has just
+ * written, so the bounds are the same bits.  On the device a warp takes ONE sample (lanes = instances): samples
+ * converge at different steps, and with the load's sample-fastest threads nearly every warp would hold a
+ * converged lane and walk the whole evaluation. */
+/* can this sample's iteration be the converged one?  (uniform over the instances of a sample) */
+NGB_HD int b4_lte_wanted(const B4Ctx *c, int s)
+{
+    if (!c->ctl.lte || !NGB_LDG(&c->ctl.active[s])) return 0;
+    const int mode_ckt = NGB_LDG(&c->ctl.mode[s]);
+    if (!(mode_ckt & NGB_MODETRAN) || !(mode_ckt & NGB_MODEINITFLOAT)) return 0;
+    if (NGB_LDG(&c->ctl.noncon[s]) != 0 || NGB_LDG(&c->nodeconv[s]) != 0) return 0;
+    return 1;
+}
+/* bounds of one instance, folded into *m1 / *m2 (the caller reduces over its instances and writes once) */
+NGB_HD void b4_lte_inst(const B4Ctx *c, int inst, int s, double *m1, double *m2)
+{
+    const size_t t = (size_t)inst * c->S + s;
+    const int head = NGB_LDG(&c->ctl.head[s]);
+    const int order = NGB_LDG(&c->ctl.order[s]);
+    const int flags = NGB_LDG(&c->flags[inst]);
+    const int rbodyMod = B4F_RBODY(flags), rgateMod = B4F_RGATE(flags);
+    double d1, d2;
+    if (order != 1 && order != 2) return;
+#define B4_LTE1(KQ) do { ngb_lte_values(&c->ctl, s, c->state, B4ST_COUNT, (size_t)c->T, t, head, KQ, order, &d1, &d2); \
+                         if (d1 < *m1) { *m1 = d1; } if (d2 < *m2) { *m2 = d2; } } while (0)
+    B4_LTE1(B4ST_qb);
+    B4_LTE1(B4ST_qg);
+    B4_LTE1(B4ST_qd);
+    if (rbodyMod) { B4_LTE1(B4ST_qbs); B4_LTE1(B4ST_qbd); }
+    if (rgateMod == 3) B4_LTE1(B4ST_qgmid);
+#undef B4_LTE1
 }
 
 #endif

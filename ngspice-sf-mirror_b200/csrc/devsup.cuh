@@ -133,7 +133,33 @@ NGB_HD void ngb_atomic_min_pos(double *addr, double v)
 }
 
 /* LTE contribution of one charge state of thread t: state array [hist][nstate][T] */
-NGB_HD void ngb_lte_state(const NgbCtl *k, int s, const double *state, int nstate, size_t T, size_t t,
+/* the two bounds of one charge state (order as is, and order 2 while the order is still 1), not yet reduced */
+NGB_HD void ngb_lte_values(const NgbCtl *k, int s, const double *state, int nstate, size_t T, size_t t,
+                           int head, int kq, int order, double *d1, double *d2)
+{
+    const int nh = k->nhist, S = k->S;
+    double q[4], dold[3];
+    const double delta = NGB_LDG(&k->delta[s]);
+    int i;
+#define LST(h, kk) state[((size_t)(((head) + (h)) % nh) * nstate + (kk)) * T + t]
+    const double cc0 = LST(0, kq + 1), cc1 = LST(1, kq + 1);
+    for (i = 0; i < 3; i++) dold[i] = NGB_LDG(&k->delta_old[(size_t)i * S + s]);
+    for (i = 0; i < 4; i++) q[i] = (i <= order + 1 || (order == 1 && nh >= 4)) && i < nh ? LST(i, kq) : 0.0;
+    /* literal orders: the difference tables unroll into registers */
+    *d1 = (order == 1) ? ngb_terr(1, q, cc0, cc1, dold, delta, k->reltol, k->abstol, k->chgtol, k->trtol)
+                       : ngb_terr(2, q, cc0, cc1, dold, delta, k->reltol, k->abstol, k->chgtol, k->trtol);
+    *d2 = (order == 1 && nh >= 4) ? ngb_terr(2, q, cc0, cc1, dold, delta, k->reltol, k->abstol, k->chgtol, k->trtol) : 1e300;
+#undef LST
+}
+
+/* one out-of-line copy per kernel: the BSIM4 load carried ten inlined CKTterr bodies (4 k instructions, a sixth of
+ * its code) that the transient driver no longer executes there */
+#ifdef __CUDACC__
+__device__ __noinline__
+#else
+static inline
+#endif
+void ngb_lte_state(const NgbCtl *k, int s, const double *state, int nstate, size_t T, size_t t,
                           int head, int kq, int order)
 {
     const int nh = k->nhist, S = k->S;

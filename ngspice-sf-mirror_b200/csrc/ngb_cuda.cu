@@ -81,6 +81,20 @@ NGB_B4_PHASE_KERNEL(ngb_k_b4_para, b4_phase_para, NGB_B4P_MB_PARA)
 NGB_B4_PHASE_KERNEL(ngb_k_b4_chrg, b4_phase_chrg, NGB_B4P_MB_CHRG)
 NGB_B4_PHASE_KERNEL(ngb_k_b4_fin, b4_phase_fin, NGB_B4P_MB_FIN)
 
+__global__ void __launch_bounds__(128)
+ngb_k_bsim4_lte(const B4Ctx c)
+{
+    const int s = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (s >= c.S || !b4_lte_wanted(&c, s)) return;
+    double m1 = 1e300, m2 = 1e300;
+    for (int inst = lane; inst < c.ninst; inst += 32) b4_lte_inst(&c, inst, s, &m1, &m2);
+    for (int o = 16; o > 0; o >>= 1) {          /* min is exact in any order */
+        m1 = fmin(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+        m2 = fmin(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    }
+    if (lane == 0) { ngb_atomic_min_pos(&c.ctl.lte[s], m1); ngb_atomic_min_pos(&c.ctl.lte2[s], m2); }
+}
+
 __global__ void __launch_bounds__(256)
 ngb_k_cap_load(const NgbCapCtx c, int *errflag)
 {
@@ -429,6 +443,12 @@ int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag)
     ngb_k_bsim4_load<<<grid, NGB_B4_CTA, 0, g_cur>>>(*c, errflag);
     if (rec) { cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], g_cur); g_prof_n++; }
     return post_launch("bsim4_load");
+}
+int ngb_launch_bsim4_lte(const B4Ctx *c)
+{
+    if (c->T <= 0) return 0;
+    ngb_k_bsim4_lte<<<(unsigned)(((size_t)c->S * 32 + 127) / 128), 128, 0, g_stream>>>(*c);
+    return post_launch("bsim4_lte");
 }
 int ngb_launch_cap_load(const NgbCapCtx *c, int *errflag)
 {

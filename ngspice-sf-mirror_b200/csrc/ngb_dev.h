@@ -45,6 +45,7 @@ void  ngb_dev_branch(int i);
 int   ngb_dev_branch_end(void);
 
 int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag);
+int ngb_launch_bsim4_lte(const B4Ctx *c);          /* BSIM4trunc for the samples that can have converged */
 int ngb_launch_cap_load(const NgbCapCtx *c, int *errflag);
 int ngb_launch_src_load(const NgbSrcCtx *c);
 int ngb_launch_assemble(const NgbAsmCtx *c);

@@ -1741,7 +1741,7 @@ void ngb_fill_b4ctx(ngb_batch *b, B4Ctx *x)
     x->inst = b->b4_inst; x->flags = b->b4_flags; x->nodes = b->b4_nodes; x->spos = b->b4_spos;
     x->stamp = b->stamp; x->state = b->b4_state; x->op = b->b4_op; x->op_full = b->op_full;
     x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl; x->temp = c->opt.temp; x->vt0 = c->opt.vt0;
-    x->split = c->exact_order; x->wscr = b->b4_wscr;
+    x->split = c->exact_order; x->wscr = b->b4_wscr; x->lte_deferred = b->lte_deferred; x->nodeconv = b->nodeconv;
 }
 void ngb_fill_capctx(ngb_batch *b, NgbCapCtx *x)
 {

@@ -61,6 +61,7 @@ struct ngb_batch {
     int *errflag;
     int *d_node_type, *d_tgt_ptr, *d_tgt_rows, *d_slot_diag, *d_long_tgt;
     double *b4_wscr;                  /* scratch of the phase-split BSIM4 load or NULL */
+    int lte_deferred;                 /* transient driver: BSIM4trunc in its own launch after the solve */
     double *b4_inst, *b4_state, *b4_op, *b4_mtab, *b4_ptab; int *b4_prow, *b4_prow_t, *b4_flags, *b4_nodes, *b4_spos;
     double *cap_par, *cap_state; int *cap_nodes, *cap_spos;
     double *b3_inst, *b3_state, *b3_von, *b3_mtab, *b3_ptab; int *b3_prow, *b3_flags, *b3_nodes, *b3_spos;

@@ -53,6 +53,7 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     ngb_tran_free(b);
     t = (struct ngb_tran *)calloc(1, sizeof *t);
     b->tran = t;
+    b->lte_deferred = getenv("NGB_LTE_INLOAD") ? 0 : 1;       /* BSIM4trunc after the solve, converged samples only */
     x = &t->x;
     x->ctl = b->ctl; x->S = S; x->neq1 = b->neq1; x->x = b->x;
     x->nodeconv = b->nodeconv; x->nodeconv_w = b->nodeconv;
@@ -169,6 +170,11 @@ static int enqueue_tick_direct(ngb_batch *b, int with_lu)
             if ((r = ngb_launch_lu(&lx))) return r;
         }
     }
+    if (with_lu && b->lte_deferred && b->c->b4_n) {     /* BSIM4trunc for the samples whose iteration can have converged */
+        B4Ctx x;
+        ngb_fill_b4ctx(b, &x);
+        if ((r = ngb_launch_bsim4_lte(&x))) return r;
+    }
     return ngb_launch_tran_control(&b->tran->x);
 }
 
@@ -222,6 +228,7 @@ int ngbTranRun(ngb_batch *b, int max_points, const int *save_eq, int nsave)
         if (done[0] >= S) break;
     }
     b->tran->ticks = tick;
+    b->lte_deferred = 0;                 /* direct ngbLoad calls keep the bound inside the load */
     if (done[0] < S) { ngb_set_error("transient did not finish within %ld Newton steps", max_ticks); return NGB_E_ITERLIM; }
     return NGB_OK;
 }

@@ -49,6 +49,17 @@ int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag)
     for (size_t t = 0; t < (size_t)c->T; t++) { int e = b4_load_thread(c, t); if (e && errflag && !errflag[0]) errflag[0] = e; }
     return 0;
 }
+int ngb_launch_bsim4_lte(const B4Ctx *c)
+{
+    g_launches++;
+    for (int s = 0; s < c->S; s++)
+        if (b4_lte_wanted(c, s)) {
+            double m1 = 1e300, m2 = 1e300;
+            for (int inst = 0; inst < c->ninst; inst++) b4_lte_inst(c, inst, s, &m1, &m2);
+            ngb_atomic_min_pos(&c->ctl.lte[s], m1); ngb_atomic_min_pos(&c->ctl.lte2[s], m2);
+        }
+    return 0;
+}
 int ngb_launch_cap_load(const NgbCapCtx *c, int *errflag)
 {
     g_launches++;
