@@ -64,6 +64,7 @@ typedef struct B4Ctx {
     const int *flags;          /* [ninst] packed B4F_*                                   */
     const int *nodes;          /* [B4N_COUNT][ninst] equation numbers (0 = ground)       */
     const int *spos;           /* [B4S_COUNT][ninst] stamp row or -1                     */
+    int srow0;                 /* rows are position-major: position k of instance i is row srow0 + k * ninst + i, live or not */
     double *stamp;             /* [nrows_stamp][S]                                       */
     double *state;             /* [NGB_NHIST][B4ST_COUNT][T]                             */
     double *op;                /* [B4O_COUNT][T] operating point (von is read back)      */
@@ -2908,8 +2909,15 @@ NGB_HD_SHARED void b4_junction_cv(double vj, double cz, double czsw, double czsw
 }
 
 /* store one stamp value if the position is live for this instance */
+/* every (position, instance) owns a row whether the assembly reads it or not (ground nodes, absent internal
+ * nodes), so a stamp is one store at a computed address: no row lookup, no branch.  NGB_B4_STAMP_LOOKUP restores
+ * the lookup (dead rows are then not written). */
+#ifdef NGB_B4_STAMP_LOOKUP
 #define B4_STAMP(K, V) do { int r_ = NGB_LDG(&c->spos[(K) * c->ninst + inst]); \
                             if (r_ >= 0) c->stamp[(size_t)r_ * c->S + s] = (V); } while (0)
+#else
+#define B4_STAMP(K, V) c->stamp[(size_t)(c->srow0 + (K) * c->ninst + inst) * c->S + s] = (V)
+#endif
 
 /* The whole load for thread t = inst * S + s.  Returns NGB_OK or an NGB_E_* code. */
 /* what every phase of one evaluation starts from (cheap to recompute, so the split kernels do) */

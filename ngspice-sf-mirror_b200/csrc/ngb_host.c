@@ -601,6 +601,7 @@ int ngbCircuitFinalize(ngb_circuit *c)
     c->nstamp_rows += B3S_COUNT * c->b3_n;
     {
         const int b4_base = c->nstamp_rows;
+        c->b4_row0 = b4_base;
 #define B4ROW(k_) (b4_base + (k_) * c->b4_n + i)
     c->b4_spos = (int *)xcalloc((size_t)c->b4_n * B4S_TOTAL, sizeof(int));
     c->b4_slots = (int *)xcalloc((size_t)c->b4_n * B4S_MAT_COUNT, sizeof(int));
@@ -1742,6 +1743,7 @@ void ngb_fill_b4ctx(ngb_batch *b, B4Ctx *x)
     x->stamp = b->stamp; x->state = b->b4_state; x->op = b->b4_op; x->op_full = b->op_full;
     x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl; x->temp = c->opt.temp; x->vt0 = c->opt.vt0;
     x->split = c->exact_order; x->wscr = b->b4_wscr; x->lte_deferred = b->lte_deferred; x->nodeconv = b->nodeconv;
+    x->srow0 = c->b4_row0;
 }
 void ngb_fill_capctx(ngb_batch *b, NgbCapCtx *x)
 {

@@ -23,6 +23,7 @@ struct ngb_circuit {
     /* device tables (host copies, instance order = reference list order) */
     int b4_n, b4_nrows; int *b4_nodes, *b4_flags, *b4_prow; double *b4_inst, *b4_mtab, *b4_ptab;
     int *b4_spos, *b4_slots;
+    int b4_row0;                   /* first stamp row of the BSIM4 block: position k of instance i is row b4_row0 + k * b4_n + i */
     int res_n; int *res_nodes; double *res_g; int *res_spos;
     int cap_n; int *cap_nodes; double *cap_par; int *cap_spos;
     int b3_n, b3_nrows; int *b3_nodes, *b3_flags, *b3_prow; double *b3_inst, *b3_mtab, *b3_ptab; int *b3_spos;
