@@ -102,6 +102,11 @@ int ngbCircuitAddVsources(ngb_circuit *c, int n, const int *nodes /* [3][n] pos 
 int ngbCircuitSetVsourcePwl(ngb_circuit *c, int inst, int ncoef, const double *coef, double rdelay, int rbreakpt);
 int ngbCircuitAddIsources(ngb_circuit *c, int n, const int *nodes /* [2][n] */,
                           const int *fn /* [3][n] */, const double *par /* [10][n] */);
+/* PWL current source `inst` (of the ngbCircuitAddIsources table, type 5): the corner list ISRCcoeffs (ncoef =
+ * ISRCfunctionOrder values t0 i0 t1 i1 ...).  ISRCload's PWL knows no delay and no repetition (isrc/isrcload.c:291-314)
+ * and ISRCaccept sets the next corner only on a breakpoint (isrcacct.c:181-197); SFFM of a current source reads its
+ * phases from coefficients 5 and 6 and applies no delay (isrcload.c:206-254).  All mirrored as they are */
+int ngbCircuitSetIsourcePwl(ngb_circuit *c, int inst, int ncoef, const double *coef);
 
 /* SMPmakeElt + SMPconvertCOOtoCSC + DEVbindCSC (klusmp.c:137-323, 417-440): builds the CSC
  * pattern, the slot map and the per-target contribution lists */

@@ -294,6 +294,12 @@ static int flatten_linear(CKTcircuit *ckt)
                 for (k = 0; k < 8; k++) par[(size_t)(2 + k) * n + i] = (h->ISRCcoeffs && k < h->ISRCfunctionOrder) ? h->ISRCcoeffs[k] : 0.0;
             }
         rc = ngbCircuitAddIsources(G.C, n, nodes, fn, par); free(nodes); free(fn); free(par);
+        if (rc) return rc;
+        i = 0;
+        for (m = (ISRCmodel *)ckt->CKThead[G.tISRC]; m; m = ISRCnextModel(m))
+            for (h = ISRCinstances(m); h; h = ISRCnextInstance(h), i++)
+                if (h->ISRCfunctionType == PWL && (rc = ngbCircuitSetIsourcePwl(G.C, i, h->ISRCfunctionOrder, h->ISRCcoeffs)))
+                    return rc;
     }
     return rc;
 }

@@ -196,6 +196,12 @@ class Circuit:
         if n:
             lib.check(lib.L.ngbCircuitAddIsources(c.h, int(n), _ip(_i32(flat["isrc/nodes"])), _ip(_i32(flat["isrc/fn"])),
                                                   _dp(_f64(flat["isrc/par"]))), "ngbCircuitAddIsources")
+            if "isrc/pwl_ptr" in flat:
+                ptr = _i32(flat["isrc/pwl_ptr"]); co = _f64(flat["isrc/pwl"])
+                for k in range(int(n)):
+                    if ptr[k + 1] > ptr[k]:
+                        seg = np.ascontiguousarray(co[ptr[k]:ptr[k + 1]])
+                        lib.check(lib.L.ngbCircuitSetIsourcePwl(c.h, k, len(seg), _dp(seg)), "ngbCircuitSetIsourcePwl")
         lib.check(lib.L.ngbCircuitFinalize(c.h), "ngbCircuitFinalize")
         n = sc(flat, "node/nov", 0)
         if n:

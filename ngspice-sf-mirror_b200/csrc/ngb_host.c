@@ -191,6 +191,7 @@ void ngbCircuitDestroy(ngb_circuit *c)
     free(c->dio_nodes); free(c->dio_flags); free(c->dio_par); free(c->dio_spos);
     free(c->vs_nodes); free(c->vs_fn); free(c->vs_par); free(c->vs_spos); free(c->vs_cspos);
     free(c->vs_pwl_ptr); free(c->vs_pwl_rep); free(c->vs_pwl_rdelay); free(c->vs_pwl_len); free(c->vs_pwl);
+    free(c->is_pwl_ptr); free(c->is_pwl_len); free(c->is_pwl);
     free(c->is_nodes); free(c->is_fn); free(c->is_par); free(c->is_spos);
     free(c->Ap); free(c->Ai); free(c->eq2col); free(c->col2eq); free(c->slot_diag); free(c->diag_slot);
     free(c->ov_eq); free(c->ov_kind); free(c->ov_cur); free(c->ov_diag); free(c->ov_zptr); free(c->ov_zslot); free(c->ov_val);
@@ -440,13 +441,33 @@ int ngbCircuitAddIsources(ngb_circuit *c, int n, const int *nodes, const int *fn
     int i;
     if (c->finalized || c->is_n) return NGB_E_PANIC;
     for (i = 0; i < n; i++)
-        if (fn[i] != 0 && fn[i] != NGB_FN_PULSE && fn[i] != NGB_FN_SINE && fn[i] != NGB_FN_EXP) {
-            ngb_set_error("current source %d: waveform type %d not supported (DC, PULSE, SIN)", i, fn[i]);
+        if (fn[i] < 0 || fn[i] > NGB_FN_AM) {
+            ngb_set_error("current source %d: waveform type %d not supported (DC, PULSE, SIN, EXP, SFFM, PWL, AM)", i, fn[i]);
             return NGB_E_UNSUPP;
         }
     c->is_n = n; c->is_nodes = (int *)xdup(nodes, sizeof(int) * 2 * (size_t)n);
     c->is_fn = (int *)xdup(fn, sizeof(int) * 3 * (size_t)n);
     c->is_par = (double *)xdup(par, sizeof(double) * 10 * (size_t)n);
+    return NGB_OK;
+}
+
+/* corner list of a PWL current source (ISRCcoeffs, ISRCfunctionOrder entries); ISRCload / ISRCaccept know neither a
+ * delay nor a repetition (isrcload.c:291-314, isrcacct.c:181-197) */
+int ngbCircuitSetIsourcePwl(ngb_circuit *c, int inst, int ncoef, const double *coef)
+{
+    int at;
+    if (c->finalized || inst < 0 || inst >= c->is_n || ncoef < 2 || (ncoef & 1)) return NGB_E_PANIC;
+    if (!c->is_pwl_ptr) {
+        c->is_pwl_ptr = (int *)xcalloc((size_t)c->is_n + 1, sizeof(int));
+        c->is_pwl_len = (int *)xcalloc((size_t)c->is_n, sizeof(int));
+    }
+    if (c->is_pwl_len[inst]) return NGB_E_PANIC;                  /* once per instance */
+    at = c->is_pwl_n;
+    c->is_pwl = (double *)realloc(c->is_pwl, sizeof(double) * (size_t)(at + ncoef));
+    memcpy(c->is_pwl + at, coef, sizeof(double) * (size_t)ncoef);
+    c->is_pwl_n = at + ncoef;
+    c->is_pwl_ptr[inst] = at; c->is_pwl_len[inst] = ncoef;
+    c->is_fn[c->is_n + inst] = ncoef;                              /* ISRCfunctionOrder */
     return NGB_OK;
 }
 
@@ -507,6 +528,12 @@ int ngbCircuitFinalize(ngb_circuit *c)
     int i, k, n, ncol;
     int *used;
     if (c->finalized) return NGB_OK;
+    for (i = 0; i < c->vs_n; i++)
+        if (c->vs_fn[i] == NGB_FN_PWL && !(c->vs_pwl_len && c->vs_pwl_len[i])) {
+            ngb_set_error("voltage source %d is PWL and has no corner list (ngbCircuitSetVsourcePwl)", i); return NGB_E_PANIC; }
+    for (i = 0; i < c->is_n; i++)
+        if (c->is_fn[i] == NGB_FN_PWL && !(c->is_pwl_len && c->is_pwl_len[i])) {
+            ngb_set_error("current source %d is PWL and has no corner list (ngbCircuitSetIsourcePwl)", i); return NGB_E_PANIC; }
 
     /* 1. structural entries, as the DEVsetup routines would request them */
     for (i = 0; i < c->b4_n; i++) {
@@ -1591,6 +1618,10 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
         b->is_par = (double *)dalloc_rep(b, "isrc.par", c->is_par, 10, c->is_n, S);
         b->is_fn = (int *)dev_dup(c->is_fn, sizeof(int) * 3 * (size_t)c->is_n);
         b->is_spos = (int *)dev_dup(c->is_spos, sizeof(int) * 2 * (size_t)c->is_n);
+        if (c->is_pwl_ptr) {
+            b->is_pwl_ptr = (int *)dev_dup(c->is_pwl_ptr, sizeof(int) * ((size_t)c->is_n + 1));
+            b->is_pwl = (double *)dev_dup(c->is_pwl, sizeof(double) * (size_t)c->is_pwl_n);
+        }
     }
     if (c->have_lu) {
         int w, nVmax = 0;
@@ -1669,6 +1700,7 @@ void ngbBatchDestroy(ngb_batch *b)
     ngb_dev_free(b->ov_eq); ngb_dev_free(b->ov_kind); ngb_dev_free(b->ov_cur); ngb_dev_free(b->ov_diag); ngb_dev_free(b->ov_zptr); ngb_dev_free(b->ov_zslot);
     ngb_dev_free(b->b3_mtab); ngb_dev_free(b->b3_ptab); ngb_dev_free(b->b3_prow); ngb_dev_free(b->b3_flags); ngb_dev_free(b->b3_nodes); ngb_dev_free(b->b3_spos);
     ngb_dev_free(b->vs_pwl_ptr); ngb_dev_free(b->vs_pwl_rep); ngb_dev_free(b->vs_pwl_rdelay); ngb_dev_free(b->vs_pwl);
+    ngb_dev_free(b->is_pwl_ptr); ngb_dev_free(b->is_pwl);
     ngb_dev_free(b->vs_fn); ngb_dev_free(b->vs_spos); ngb_dev_free(b->is_fn); ngb_dev_free(b->is_spos);
     if (b->have_lu) {
         batch_free_lu(b);
@@ -1782,7 +1814,8 @@ void ngb_fill_srcctx(ngb_batch *b, NgbSrcCtx *x, int is_current)
     const ngb_circuit *c = b->c;
     memset(x, 0, sizeof *x);
     x->S = b->S; x->is_current = is_current; x->stamp = b->stamp; x->tstep = c->opt.tstep; x->tstop = c->opt.tstop; x->ctl = b->ctl;
-    if (is_current) { x->ninst = c->is_n; x->fn = b->is_fn; x->par = b->is_par; x->spos = b->is_spos; }
+    if (is_current) { x->ninst = c->is_n; x->fn = b->is_fn; x->par = b->is_par; x->spos = b->is_spos;
+                      x->pwl_ptr = b->is_pwl_ptr; x->pwl = b->is_pwl; }
     else { x->ninst = c->vs_n; x->fn = b->vs_fn; x->par = b->vs_par; x->spos = b->vs_spos;
            x->pwl_ptr = b->vs_pwl_ptr; x->pwl_rep = b->vs_pwl_rep; x->pwl_rdelay = b->vs_pwl_rdelay; x->pwl = b->vs_pwl; }
     x->T = x->ninst * b->S;

@@ -31,6 +31,7 @@ struct ngb_circuit {
     int dio_n; int *dio_nodes, *dio_flags; double *dio_par; int *dio_spos;
     int vs_n; int *vs_nodes, *vs_fn; double *vs_par; int *vs_spos, *vs_cspos;
     int *vs_pwl_ptr, *vs_pwl_rep, *vs_pwl_len, vs_pwl_n; double *vs_pwl, *vs_pwl_rdelay;
+    int *is_pwl_ptr, *is_pwl_len, is_pwl_n; double *is_pwl;      /* PWL current sources: corner lists only (isrcload.c has no delay / repetition) */
     int is_n; int *is_nodes, *is_fn; double *is_par; int *is_spos;
     /* CSC pattern (SMPconvertCOOtoCSC) */
     int n, nnz; int *Ap, *Ai, *eq2col, *col2eq, *slot_diag, *diag_slot;
@@ -69,7 +70,7 @@ struct ngb_batch {
     double *vb_par, *vb_aux, *vb_state; int *vb_nodes, *vb_flags, *vb_spos;
     int *ov_eq, *ov_kind, *ov_cur, *ov_diag, *ov_zptr, *ov_zslot; double *ov_val;
     double *dio_par, *dio_state; int *dio_nodes, *dio_flags, *dio_spos;
-    double *vs_par; int *vs_fn, *vs_spos; int *vs_pwl_ptr, *vs_pwl_rep; double *vs_pwl, *vs_pwl_rdelay;
+    double *vs_par; int *vs_fn, *vs_spos; int *vs_pwl_ptr, *vs_pwl_rep; double *vs_pwl, *vs_pwl_rdelay; int *is_pwl_ptr; double *is_pwl;
     double *is_par; int *is_fn, *is_spos;
     struct { NgbLuSched dsch; NgbLuPacked dpk; int valid; } dlu[NGB_LU_SETS];   /* device arrays per pattern set */
     int lu_which;                  /* set used by the direct ngbLuFac/ngbSolve calls */

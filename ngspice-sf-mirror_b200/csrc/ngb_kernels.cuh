@@ -165,6 +165,18 @@ NGB_HD double ngb_src_value(const NgbSrcCtx *c, size_t t, int inst, int s, int m
             else value = V1 + (V2 - V1) * (1 - ngb_exp(-(time - TD1) / TAU1)) + (V1 - V2) * (1 - ngb_exp(-(time - TD2) / TAU2));
         } break;
         case NGB_FN_SFFM: {         /* vsrcload.c:233-287 */
+            if (c->is_current) {    /* isrcload.c:206-254 differs: no delay is applied (TD is read and not used), the
+                                     * modulation phase is coefficient 5 and the carrier phase coefficient 6 */
+                const double VO = SCO(0), VA = SCO(1);
+                const double FC = forder > 2 ? SCO(2) : (5. / c->tstop);
+                double MDI = forder > 3 ? SCO(3) : 90.0;
+                const double FM = (forder > 4 && SCO(4) != 0.0) ? SCO(4) : (500. / c->tstop);
+                const double phasem = (forder > 5 ? SCO(5) : 0.0) * M_PI / 180.0;
+                const double phasec = (forder > 6 ? SCO(6) : 0.0) * M_PI / 180.0;
+                if (MDI > FC / FM) MDI = FC / FM; else if (MDI < 0) MDI = 0;
+                value = VO + VA * sin((2.0 * M_PI * FC * time + phasec) + MDI * sin(2.0 * M_PI * FM * time + phasem));
+                break;
+            }
             const double VO = SCO(0), VA = SCO(1);
             const double FC = forder > 2 ? SCO(2) : (5. / c->tstop);
             double MDI = forder > 3 ? SCO(3) : 90.0;
@@ -191,6 +203,19 @@ NGB_HD double ngb_src_value(const NgbSrcCtx *c, size_t t, int inst, int s, int m
         } break;
         case NGB_FN_PWL: {          /* vsrcload.c:324-367; forder = number of list entries */
             const double *co = c->pwl + NGB_LDG(&c->pwl_ptr[inst]);
+            if (c->is_current) {    /* isrcload.c:291-314: the older search, no delay, no repetition */
+                if (time < NGB_LDG(&co[0])) { value = NGB_LDG(&co[1]); break; }
+                value = NGB_LDG(&co[forder - 1]);
+                for (int i = 0; i < forder / 2 - 1; i++) {
+                    const double t0 = NGB_LDG(&co[2 * i]), t1 = NGB_LDG(&co[2 * (i + 1)]);
+                    if (t0 == time) { value = NGB_LDG(&co[2 * i + 1]); break; }
+                    if (t0 < time && t1 > time) {
+                        value = NGB_LDG(&co[2 * i + 1]) + (((time - t0) / (t1 - t0)) * (NGB_LDG(&co[2 * i + 3]) - NGB_LDG(&co[2 * i + 1])));
+                        break;
+                    }
+                }
+                break;
+            }
             const int rep = NGB_LDG(&c->pwl_rep[inst]);
             time -= NGB_LDG(&c->pwl_rdelay[inst]);
             if (time <= NGB_LDG(&co[0])) { value = NGB_LDG(&co[1]); break; }

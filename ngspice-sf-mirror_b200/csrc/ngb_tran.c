@@ -112,6 +112,7 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
         ngb_dev_h2d(x->phase, iv, sizeof(int) * S);
         for (s = 0; s < S; s++) iv[s] = 1;
         ngb_dev_h2d(x->firsttime, iv, sizeof(int) * S);
+        ngb_dev_h2d(x->brkflag, iv, sizeof(int) * S);              /* CKTbreak = 1 (dctran.c:195): ISRCaccept's PWL reads it */
         ngb_dev_h2d(b->ctl.active, iv, sizeof(int) * S);
         ngb_dev_h2d(b->ctl.order, iv, sizeof(int) * S);
         for (s = 0; s < S; s++) iv[s] = 2;

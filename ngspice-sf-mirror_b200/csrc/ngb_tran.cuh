@@ -204,6 +204,20 @@ NGB_HD int ngb_src_accept(const NgbTranCtx *c, const NgbSrcCtx *sc, double *brk,
                 { const int e = ngb_set_break(c, s, brk[t], now); if (e) return e; }
                 brk[t] -= c->minbreak;
             }
+        } else if (ftype == NGB_FN_PWL && sc->is_current) {     /* isrcacct.c:181-197: only on a breakpoint (CKTbreak) */
+            const double *co = sc->pwl + NGB_LDG(&sc->pwl_ptr[inst]);
+            if (!c->brkflag[s]) continue;
+            if (now < NGB_LDG(&co[0])) {
+                const int e = ngb_set_break(c, s, NGB_LDG(&co[0]), now);       /* the reference drops this error code */
+                (void)e;
+                continue;
+            }
+            for (int i = 0; i < forder / 2 - 1; i++)
+                if (ngb_almost_equal_ulps(NGB_LDG(&co[2 * i]), now, 3)) {
+                    const int e = ngb_set_break(c, s, NGB_LDG(&co[2 * i + 2]), now);
+                    if (e) return e;
+                    break;
+                }
         } else if (ftype == NGB_FN_PWL) {       /* vsrcacct.c:174-226 */
             if (now >= brk[t]) {
                 const double *co = sc->pwl + NGB_LDG(&sc->pwl_ptr[inst]);

@@ -319,6 +319,26 @@ static void dump_linear(FILE *f, CKTcircuit *ckt, KLUmatrix *K)
                         par[(size_t)(2 + k) * n + i] = (h->ISRCcoeffs && k < h->ISRCfunctionOrder) ? h->ISRCcoeffs[k] : 0.0;
                 }
             put_i2(f, "isrc/nodes", nodes, 2, n); put_i2(f, "isrc/fn", fn, 3, n); put_d2(f, "isrc/par", par, 10, n);
+            {   /* PWL corner lists */
+                int *ptr = (int *)calloc((size_t)n + 1, sizeof(int)), tot = 0;
+                double *co;
+                i = 0;
+                for (m = (ISRCmodel *)ckt->CKThead[isrc_type]; m; m = ISRCnextModel(m))
+                    for (h = ISRCinstances(m); h; h = ISRCnextInstance(h), i++) {
+                        ptr[i] = tot;
+                        if (h->ISRCfunctionType == PWL) tot += h->ISRCfunctionOrder;
+                    }
+                ptr[n] = tot;
+                if (tot) {
+                    co = (double *)calloc((size_t)tot + 1, sizeof(double)); i = 0;
+                    for (m = (ISRCmodel *)ckt->CKThead[isrc_type]; m; m = ISRCnextModel(m))
+                        for (h = ISRCinstances(m); h; h = ISRCnextInstance(h), i++)
+                            if (h->ISRCfunctionType == PWL) memcpy(co + ptr[i], h->ISRCcoeffs, sizeof(double) * (size_t)h->ISRCfunctionOrder);
+                    put_i1(f, "isrc/pwl_ptr", ptr, (long long)n + 1); put_d1(f, "isrc/pwl", co, tot);
+                    free(co);
+                }
+                free(ptr);
+            }
             free(nodes); free(fn); free(par);
         }
     }

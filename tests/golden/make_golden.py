@@ -216,7 +216,7 @@ def latch_netlist():
 
 def srcs_netlist():
     """every independent-source waveform of the path: PWL (plain, delayed, repeating), EXP, SFFM and AM voltage
-    sources and an EXP current source, each into an RC section; a BSIM4 inverter on the PWL input"""
+    sources and EXP, SFFM, AM and PWL current sources, each into an RC section; a BSIM4 inverter on the PWL input"""
     mos = "l=0.1u w={w} ad=5p pd=6u as=5p ps=6u"
     return "\n".join([
         "* source waveforms: PWL / EXP / SFFM / AM",
@@ -233,6 +233,14 @@ def srcs_netlist():
         "r5 e e2 500", "c5 e2 0 20f",
         "i6 0 f exp(0 1m 0.5n 0.2n 2n 0.3n)",
         "r6 f 0 1k", "c6 f 0 0.2p",
+        # ISRCload's own SFFM (phases in coefficients 5 and 6, no delay), AM and PWL (no delay / repetition; ISRCaccept
+        # sets the next corner only on a breakpoint); the list starts after t = 0
+        "i7 0 g sffm(0.2m 1m 2g 3 0.4g 20 30)",
+        "r7 g 0 1k", "c7 g 0 50f",
+        "i8 0 h am(0.2m 1m 0.8 0.5g 3g 0.1n 10 20)",
+        "r8 h 0 1k", "c8 h 0 50f",
+        "i9 0 k pwl(0.2n 0 0.6n 1m 1n 1m 1.4n 0.2m 2.5n 0.8m)",
+        "r9 k 0 1k", "c9 k 0 0.1p",
         ".option klu", ".tran 10p 4n"]) + "\n" + ro_cards() + "\n.end\n"
 
 
@@ -370,7 +378,7 @@ if __name__ == "__main__":
     if "latch" in which:
         run("latch", latch_netlist(), "0-40,100,101,200", ["q", "qb", "a", "b", "vdd#branch", "vm#branch"])
     if "srcs" in which:
-        run("srcs", srcs_netlist(), "0-20,100,101,300", ["y", "b2", "c2", "d2", "e2", "f", "v1#branch"])
+        run("srcs", srcs_netlist(), "0-20,100,101,300", ["y", "b2", "c2", "d2", "e2", "f", "g", "h", "k", "v1#branch"])
     if "b3ring" in which:
         run("b3ring", b3_netlist(5), "0-40,300,301,1000,1001", ["out", "buf", "n2", "vdd#branch"])
     if "arr" in which:
