@@ -59,6 +59,12 @@ void ngbCircuitDestroy(ngb_circuit *c);
 /* dopt: reltol abstol vntol chgtol trtol temp vt0 xmu tstep tstop tmax tstart delmin minbreak gmin
  * iopt: method(1 trap) maxorder itl4 itl1 uic   (cktntask.c:95-146, cktdojob.c:50-125) */
 int ngbCircuitSetOptions(ngb_circuit *c, const double dopt[15], const int iopt[5]);
+/* CKTop's fallbacks after a failed plain NIiter (cktop.c:62-96): CKTnumGminSteps / CKTnumSrcSteps (defaults 1 / 1,
+ * cktntask.c:120-121; 0 skips the route; 1 = dynamic_gmin then new_gmin / gillespie_src; > 1 would be spice3_gmin /
+ * spice3_src: E_UNSUPP), CKTdcTrcvMaxIter (itl2, default 50), CKTgminFactor (default 10) and CKTnoOpIter (`.option noopiter`:
+ * CKTop skips the plain NIiter, cktop.c:42-55).  They run per sample inside
+ * the device controller of ngbTranRun */
+int ngbCircuitSetOpFallbacks(ngb_circuit *c, int num_gmin_steps, int num_src_steps, int itl2, double gmin_factor, int no_op_iter);
 
 /* BSIM4 instances in the order of the reference instance lists (cktcrte.c:62-64).
  * nodes [12][ninst], flags [ninst] (B4F_*), prow [ninst] row of mtab/ptab, inst [NI][ninst],

@@ -143,6 +143,9 @@ class Circuit:
         i = np.array([sc(flat, "opt/method"), sc(flat, "opt/maxorder"), sc(flat, "opt/itl4"),
                       sc(flat, "opt/itl1"), sc(flat, "tran/uic", 0)], dtype=np.int32)
         lib.check(lib.L.ngbCircuitSetOptions(c.h, _dp(d), _ip(i)), "ngbCircuitSetOptions")
+        if "opt/gminsteps" in flat:      # CKTop's fallbacks (cktop.c:62-96); fixtures recorded before the key existed use the defaults
+            lib.check(lib.L.ngbCircuitSetOpFallbacks(c.h, int(sc(flat, "opt/gminsteps")), int(sc(flat, "opt/srcsteps")), int(sc(flat, "opt/itl2")),
+                                                     ctypes.c_double(float(sc(flat, "opt/gminfactor"))), int(sc(flat, "opt/noopiter", 0))), "ngbCircuitSetOpFallbacks")
         if sc(flat, "opt/bypass", 0):
             raise NgbError("CKTbypass != 0 is not supported on this path")
         n = sc(flat, "b4/ninst", 0)
@@ -222,6 +225,13 @@ class Circuit:
         s = np.zeros((self.lib.layout[4], ninst), np.int32)
         self.lib.check(self.lib.L.ngbCircuitGetBsim4Slots(self.h, _ip(s)))
         return s
+
+    def set_op_fallbacks(self, gminsteps=1, srcsteps=1, itl2=50, gminfactor=10.0, noopiter=0):
+        """CKTop's fallbacks after a failed plain NIiter (cktop.c:62-96): `.option gminsteps= srcsteps= itl2= gminfactor=`;
+        0 skips the route, 1 is dynamic_gmin + new_gmin / gillespie_src, larger counts are refused (E_UNSUPP); `noopiter` skips
+        the plain NIiter"""
+        self.lib.check(self.lib.L.ngbCircuitSetOpFallbacks(self.h, int(gminsteps), int(srcsteps), int(itl2), ctypes.c_double(float(gminfactor)), int(noopiter)),
+                       "ngbCircuitSetOpFallbacks")
 
     def set_lu_pattern(self, pat, prefix="", which=0, uic=None):
         """pat: dict with n nblocks Q R Pnum Lp Li Up Ui Offp Offi (KLU symbolic + numeric pattern).

@@ -163,6 +163,7 @@ ngb_circuit *ngbCircuitCreate(int neq, const int *node_type)
     c->opt.trtol = 7; c->opt.temp = 300.15; c->opt.vt0 = 1.38064852e-23 * (27.0 + 273.15) / 1.6021766208e-19;
     c->opt.xmu = 0.5; c->opt.gmin = 1e-12; c->opt.method = NGB_TRAPEZOIDAL; c->opt.maxorder = 2;
     c->opt.itl4 = 10; c->opt.itl1 = 100;
+    c->opt.num_gmin_steps = 1; c->opt.num_src_steps = 1; c->opt.itl2 = 50; c->opt.gmin_factor = 10;
     c->exact_order = 1;
     return c;
 }
@@ -212,6 +213,19 @@ int ngbCircuitSetOptions(ngb_circuit *c, const double d[15], const int i[5])
     o->method = i[0]; o->maxorder = i[1]; o->itl4 = i[2]; o->itl1 = i[3]; o->uic = i[4];
     if (o->method != NGB_TRAPEZOIDAL) { ngb_set_error("integration method %d not supported (TRAP only)", o->method); return NGB_E_METHOD; }
     if (o->maxorder > 2) { ngb_set_error("maxord %d not supported with TRAP", o->maxorder); return NGB_E_ORDER; }
+    return NGB_OK;
+}
+
+/* the operating-point fallbacks of CKTop (cktop.c:62-96): CKTnumGminSteps and CKTnumSrcSteps (0 skips the route, 1 is
+ * dynamic_gmin + new_gmin / gillespie_src; larger counts select spice3_gmin / spice3_src, which are not built),
+ * CKTdcTrcvMaxIter (itl2), CKTgminFactor, and CKTnoOpIter (`.option noopiter`: no plain NIiter, straight to the fallbacks) */
+int ngbCircuitSetOpFallbacks(ngb_circuit *c, int num_gmin_steps, int num_src_steps, int itl2, double gmin_factor, int no_op_iter)
+{
+    if (num_gmin_steps < 0 || num_gmin_steps > 1) { ngb_set_error("gminsteps=%d selects spice3_gmin, which is not on this path (0 or 1)", num_gmin_steps); return NGB_E_UNSUPP; }
+    if (num_src_steps < 0 || num_src_steps > 1) { ngb_set_error("srcsteps=%d selects spice3_src, which is not on this path (0 or 1)", num_src_steps); return NGB_E_UNSUPP; }
+    if (itl2 < 1 || !(gmin_factor > 1.0)) { ngb_set_error("itl2=%d / gminfactor=%g out of range", itl2, gmin_factor); return NGB_E_PANIC; }
+    c->opt.num_gmin_steps = num_gmin_steps; c->opt.num_src_steps = num_src_steps; c->opt.itl2 = itl2; c->opt.gmin_factor = gmin_factor;
+    c->opt.no_op_iter = no_op_iter ? 1 : 0;
     return NGB_OK;
 }
 

@@ -36,6 +36,7 @@ void ngb_tran_free(struct ngb_batch *b)
     ngb_dev_free(t->x.numiter); ngb_dev_free(t->x.timepts); ngb_dev_free(t->x.save_delta); ngb_dev_free(t->x.old_delta);
     ngb_dev_free(t->x.breaks); ngb_dev_free(t->x.out_time); ngb_dev_free(t->x.out_val); ngb_dev_free(t->x.ndone); ngb_dev_free(t->x.evstage);
     ngb_dev_free(t->x.gm_stage); ngb_dev_free(t->x.gm_factor); ngb_dev_free(t->x.gm_oldgmin); ngb_dev_free(t->x.gm_xold);
+    ngb_dev_free(t->x.gm_startgmin); ngb_dev_free(t->x.gs_conv); ngb_dev_free(t->x.gs_raise); ngb_dev_free(t->x.gs_i);
     { int a; for (a = 0; a < t->x.gm_narr; a++) ngb_dev_free(t->x.gm_arr[a].old); }
     ngb_dev_free(t->d_save_eq); ngb_dev_free(t->x.isrc_break); ngb_dev_free(t->x.vsrc_break);
     ngb_dev_graph_destroy(t->graph[0]); ngb_dev_graph_destroy(t->graph[1]); ngb_dev_graph_destroy(t->graph[2]);
@@ -87,6 +88,10 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
         x->gm_stage = (int *)dz(sizeof(int) * S);
         x->gm_factor = (double *)dz(sizeof(double) * S); x->gm_oldgmin = (double *)dz(sizeof(double) * S);
         x->gm_xold = (double *)dz(sizeof(double) * (size_t)b->neq1 * S);
+        x->gm_startgmin = (double *)dz(sizeof(double) * S); x->gs_conv = (double *)dz(sizeof(double) * S);
+        x->gs_raise = (double *)dz(sizeof(double) * S); x->gs_i = (int *)dz(sizeof(int) * S);
+        x->num_gmin_steps = c->opt.num_gmin_steps; x->num_src_steps = c->opt.num_src_steps;
+        x->itl2 = c->opt.itl2; x->gmin_factor = c->opt.gmin_factor;
         for (i = 0; i < 5; i++)
             if (tab[i].st && tab[i].n > 0) {
                 x->gm_arr[x->gm_narr].state = tab[i].st; x->gm_arr[x->gm_narr].K = tab[i].K; x->gm_arr[x->gm_narr].ninst = tab[i].n;
@@ -136,6 +141,26 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
         ngb_dev_h2d(b->ctl.ag0, dv, sizeof(double) * S);
         ngb_dev_h2d(b->ctl.ag1, dv, sizeof(double) * S);
         ngb_dev_h2d(b->ctl.diag_gmin, dv, sizeof(double) * S);
+        free(iv); free(dv);
+    }
+    if (!c->opt.uic && c->opt.no_op_iter && (c->opt.num_gmin_steps == 1 || c->opt.num_src_steps == 1)) {
+        /* CKTnoOpIter (cktop.c:42-55): no plain NIiter -- every sample starts inside the first fallback, in the
+         * state the controller would have put it in (solution and states are still zero) */
+        int *iv = (int *)calloc((size_t)S, sizeof(int)); double *dv = (double *)calloc((size_t)S, sizeof(double));
+        const int dyn = c->opt.num_gmin_steps == 1;
+        for (s = 0; s < S; s++) iv[s] = dyn ? 1 : 10;
+        ngb_dev_h2d(x->gm_stage, iv, sizeof(int) * S);
+        if (dyn) {
+            for (s = 0; s < S; s++) dv[s] = c->opt.gmin_factor;
+            ngb_dev_h2d(x->gm_factor, dv, sizeof(double) * S);
+            for (s = 0; s < S; s++) dv[s] = 1e-2;
+            ngb_dev_h2d(x->gm_oldgmin, dv, sizeof(double) * S);
+            for (s = 0; s < S; s++) dv[s] = 1e-2 / c->opt.gmin_factor;
+            ngb_dev_h2d(b->ctl.diag_gmin, dv, sizeof(double) * S);
+        } else {
+            memset(dv, 0, sizeof(double) * S);
+            ngb_dev_h2d(b->ctl.srcfact, dv, sizeof(double) * S);         /* gs_conv is already zero */
+        }
         free(iv); free(dv);
     }
     ngb_launch_fill_f64(b->ctl.lte, 1e300, S);

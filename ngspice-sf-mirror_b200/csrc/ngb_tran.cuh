@@ -55,6 +55,13 @@ typedef struct NgbTranCtx {
      * gm_stage 0 = plain NIiter, 1 = inside the stepping loop, 2 = final NIiter with CKTdiagGmin = gshunt */
     int *gm_stage;             /* [S] */
     double *gm_factor, *gm_oldgmin;   /* [S] */
+    /* the rest of CKTop's chain (cktop.c:62-96): gm_stage 3 / 4 = new_gmin's loop (it steps CKTgmin itself, :350-463) and
+     * its final NIiter; 10 / 11 / 12 = gillespie_src (:481-660): first solve with the sources at zero, its diagonal-gmin
+     * ladder when that fails, the source-raising loop */
+    double *gm_startgmin, *gs_conv, *gs_raise;   /* [S] CKTgmin on entry of new_gmin; ConvFact; raise */
+    int *gs_i;                        /* [S] step of the ladder */
+    int num_gmin_steps, num_src_steps, itl2;     /* CKTnumGminSteps, CKTnumSrcSteps (0: skip, 1: the routes built here), CKTdcTrcvMaxIter */
+    double gmin_factor;               /* CKTgminFactor */
     double *gm_xold;           /* [neq1][S] OldRhsOld */
     struct { double *state, *old; int K, ninst; } gm_arr[5];   /* device state tables and their OldCKTstate0 copies [K][ninst*S] */
     int gm_narr, gm_enable;
@@ -417,15 +424,23 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
     c->numiter[s] += iterno;
 
     if (phase == NGB_PH_DCOP && c->gm_enable) {
-        /* CKTop (cktop.c:27-112): plain NIiter, then dynamic_gmin (:162-274).  new_gmin, source stepping and
-         * OPtran are not built: a sample that dynamic gmin stepping cannot bring home fails with NIiter's code */
+        /* CKTop (cktop.c:27-112): plain NIiter; then, with CKTnumGminSteps == 1, dynamic_gmin (:162-274) and new_gmin
+         * (:350-463); then, with CKTnumSrcSteps == 1, gillespie_src (:481-660).  spice3_gmin / spice3_src (counts > 1) are
+         * refused by ngbCircuitSetOpFallbacks, OPtran is not built: a sample none of them brings home fails with the
+         * last NIiter's code */
         const int firstmode = (mode & NGB_MODEUIC) | NGB_MODETRANOP | NGB_MODEINITJCT;
         const int contmode = (mode & NGB_MODEUIC) | NGB_MODETRANOP | NGB_MODEINITFLOAT;
         const int stage = c->gm_stage[s];
-        const int itl2 = 50;                                   /* CKTdcTrcvMaxIter */
-        const double gmin_factor = 10.0;                        /* CKTgminFactor */
-        const double gtarget = c->ctl.gmin[s];                  /* MAX(CKTgmin, CKTgshunt), gshunt = 0 */
-        if (stage == 0 && niret != NGB_OK) {
+        const int itl2 = c->itl2;                               /* CKTdcTrcvMaxIter */
+        const double gmin_factor = c->gmin_factor;              /* CKTgminFactor */
+        int start = 0;                                          /* the fallback that begins now: 1 dynamic_gmin, 3 new_gmin, 10 gillespie_src */
+        int raise_init = 0;
+        if (niret != NGB_OK) {
+            if (stage == 0) start = c->num_gmin_steps == 1 ? 1 : (c->num_src_steps == 1 ? 10 : 0);
+            else if (stage == 2) start = 3;
+            else if (stage == 4) start = c->num_src_steps == 1 ? 10 : 0;
+        }
+        if (start == 1) {
             c->gm_stage[s] = 1;
             ngb_gm_states(c, s, 0);
             c->gm_factor[s] = gmin_factor;
@@ -434,32 +449,113 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
             ngb_gm_next_niiter(c, s, firstmode);
             return;
         }
-        if (stage == 1) {
+        if (start == 3) {
+            c->gm_stage[s] = 3;
+            ngb_gm_states(c, s, 0);
+            c->gm_startgmin[s] = c->ctl.gmin[s];
+            c->gm_factor[s] = gmin_factor;
+            c->gm_oldgmin[s] = 1e-2;
+            c->ctl.gmin[s] = 1e-2 / gmin_factor;
+            ngb_gm_next_niiter(c, s, firstmode);
+            return;
+        }
+        if (start == 10) {
+            c->gm_stage[s] = 10;
+            c->ctl.srcfact[s] = 0.0;
+            c->gs_conv[s] = 0.0;
+            ngb_gm_states(c, s, 0);
+            ngb_gm_next_niiter(c, s, firstmode);
+            return;
+        }
+        if (stage == 1 || stage == 3) {
+            /* the two gmin ladders differ in what they step (CKTdiagGmin through LoadGmin / CKTgmin inside the device
+             * models), in the floor of the shrinking factor and in the value they leave behind */
+            double *g = stage == 1 ? &c->ctl.diag_gmin[s] : &c->ctl.gmin[s];
+            const double gtarget = stage == 1 ? c->ctl.gmin[s] : c->gm_startgmin[s];      /* MAX(CKTgmin, CKTgshunt), gshunt = 0 */
             double factor = c->gm_factor[s];
             int leave = 0;
             if (niret == NGB_OK) {
                 mode = contmode;
-                if (c->ctl.diag_gmin[s] <= gtarget) {
+                if (*g <= gtarget) {
                     leave = 1;
                 } else {
                     ngb_gm_states(c, s, 1);
                     if (iterno <= itl2 / 4) { factor *= sqrt(factor); if (factor > gmin_factor) factor = gmin_factor; }
-                    if (iterno > 3 * itl2 / 4) factor = NGB_MAX(sqrt(factor), 1.00005);
-                    c->gm_oldgmin[s] = c->ctl.diag_gmin[s];
-                    if (c->ctl.diag_gmin[s] < factor * gtarget) { factor = c->ctl.diag_gmin[s] / gtarget; c->ctl.diag_gmin[s] = gtarget; }
-                    else c->ctl.diag_gmin[s] /= factor;
+                    if (iterno > 3 * itl2 / 4) factor = NGB_MAX(sqrt(factor), stage == 1 ? 1.00005 : 3);
+                    c->gm_oldgmin[s] = *g;
+                    if (*g < factor * gtarget) { factor = *g / gtarget; *g = gtarget; }
+                    else *g /= factor;
                 }
             } else if (factor < 1.00005) {
                 leave = 1;                                       /* "Last gmin step failed" */
             } else {
                 factor = sqrt(sqrt(factor));
-                c->ctl.diag_gmin[s] = c->gm_oldgmin[s] / factor;
+                *g = c->gm_oldgmin[s] / factor;
                 ngb_gm_states(c, s, 2);
             }
             c->gm_factor[s] = factor;
-            if (leave) { c->ctl.diag_gmin[s] = 0.0; c->gm_stage[s] = 2; }      /* CKTdiagGmin = CKTgshunt, final NIiter */
+            if (leave) { *g = stage == 1 ? 0.0 : gtarget; c->gm_stage[s] = stage + 1; }   /* CKTdiagGmin = CKTgshunt / CKTgmin = its start value; final NIiter */
             ngb_gm_next_niiter(c, s, mode);
             return;
+        }
+        if (stage == 10) {
+            if (niret != NGB_OK) {                              /* the ladder: CKTdiagGmin from 1e10 * gmin down, eleven steps */
+                double dg = c->ctl.gmin[s];
+                for (int i = 0; i < 10; i++) dg *= 10;
+                c->ctl.diag_gmin[s] = dg;
+                c->gs_i[s] = 0;
+                c->gm_stage[s] = 11;
+                ngb_gm_next_niiter(c, s, mode);
+                return;
+            }
+            raise_init = 1;
+        } else if (stage == 11) {
+            if (niret != NGB_OK) {                              /* "gmin step failed": no solution at zero sources */
+                c->ctl.diag_gmin[s] = 0.0; c->ctl.srcfact[s] = 1.0;
+                ngb_finish(c, s, NGB_PH_FAIL, NGB_E_ITERLIM);
+                return;
+            }
+            c->ctl.diag_gmin[s] /= 10;
+            mode = contmode;
+            c->gs_i[s] += 1;
+            if (c->gs_i[s] <= 10) { ngb_gm_next_niiter(c, s, mode); return; }
+            c->ctl.diag_gmin[s] = 0.0;
+            raise_init = 1;
+        }
+        if (raise_init) {
+            ngb_gm_states(c, s, 1);
+            c->gs_raise[s] = 0.001;
+            c->ctl.srcfact[s] = c->gs_conv[s] + 0.001;
+            c->gm_stage[s] = 12;
+            ngb_gm_next_niiter(c, s, mode);
+            return;
+        }
+        if (stage == 12) {
+            double conv = c->gs_conv[s], raise = c->gs_raise[s], sf = c->ctl.srcfact[s];
+            int stop = 0;
+            mode = contmode;
+            if (niret == NGB_OK) {
+                conv = sf;
+                ngb_gm_states(c, s, 1);
+                sf = conv + raise;
+                if (iterno <= itl2 / 4) raise *= 1.5;
+                if (iterno > 3 * itl2 / 4) raise *= 0.5;
+            } else if (sf - conv < 1e-8) {
+                stop = 1;
+            } else {
+                raise /= 10;
+                if (raise > 0.01) raise = 0.01;
+                sf = conv;
+                ngb_gm_states(c, s, 2);
+            }
+            if (sf > 1) sf = 1;
+            c->gs_conv[s] = conv; c->gs_raise[s] = raise; c->ctl.srcfact[s] = sf;
+            if (!stop && raise >= 1e-7 && conv < 1) { ngb_gm_next_niiter(c, s, mode); return; }
+            c->ctl.diag_gmin[s] = c->ctl.gmin[s];                /* "CKTdiagGmin = CKTgmin = gminstart" (:645): it stays for the run */
+            c->ctl.srcfact[s] = 1.0;
+            c->gm_stage[s] = 13;
+            if (conv != 1) { ngb_finish(c, s, NGB_PH_FAIL, NGB_E_ITERLIM); return; }
+            niret = NGB_OK;                                      /* "Source stepping completed": the operating point stands */
         }
     }
     if (phase == NGB_PH_DCOP) {

@@ -64,6 +64,9 @@ typedef struct NgbOpts {
     double reltol, abstol, vntol, chgtol, trtol, temp, vt0, xmu;
     double tstep, tstop, tmax, tstart, delmin, minbreak, gmin;
     int method, maxorder, itl4, itl1, uic;
+    int no_op_iter;                            /* CKTnoOpIter: skip the plain NIiter of CKTop, start with the fallbacks */
+    int num_gmin_steps, num_src_steps, itl2;   /* CKTnumGminSteps, CKTnumSrcSteps, CKTdcTrcvMaxIter (cktntask.c:117-122) */
+    double gmin_factor;                        /* CKTgminFactor */
 } NgbOpts;
 
 /* two-terminal linear elements and sources */

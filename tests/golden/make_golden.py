@@ -309,7 +309,7 @@ def run(name, netlist, calls, save):
     os.makedirs(TMP, exist_ok=True)
     cir = os.path.join(TMP, name + ".cir")
     open(cir, "w").write(netlist)
-    if name in ("ro17", "ro101", "ro17k", "inv", "dio", "b3ring", "arr", "vbic", "mix", "latch", "srcs"):
+    if name in ("ro17", "ro101", "ro17k", "inv", "dio", "b3ring", "arr", "vbic", "mix", "latch", "srcs", "mixsrc", "invsrc", "invgmin"):
         # the netlist itself is kept too: the CPU-baseline arm of bench.py feeds it to oracle/_ref/ngspice
         os.makedirs(os.path.join(HERE, "netlists"), exist_ok=True)
         open(os.path.join(HERE, "netlists", name + ".cir"), "w").write(netlist)
@@ -375,6 +375,19 @@ if __name__ == "__main__":
             run(f"mix{k}", mix_netlist(vdd, r), "0", save)
             for ext in (".flat.ngt", ".trace.ngt.gz"):
                 os.remove(os.path.join(HERE, f"mix{k}" + ext))
+    if "invsrc" in which:
+        # `.option noopiter` sends CKTop straight to its fallbacks (cktop.c:42-55): with gminsteps=0 that is gillespie_src,
+        # otherwise dynamic_gmin.  The pivoting events are the usual four, so these fixtures carry their own pattern sets
+        run("invsrc", inv_netlist().replace(".option klu", ".option klu noopiter gminsteps=0"), "0,1", ["out", "in", "vdd#branch", "vin#branch"])
+        run("invgmin", inv_netlist().replace(".option klu", ".option klu noopiter"), "0,1", ["out", "in", "vdd#branch", "vin#branch"])
+    if "mixsrc" in which:
+        # the operating point of MIX_POINTS[5] with gmin stepping switched off: CKTop goes straight to gillespie_src
+        # (cktop.c:87-96, 481-660); waveform and statistics only, the batch runs on mix.flat.ngt
+        vdd, r = MIX_POINTS[5]
+        run("mixsrc", mix_netlist(vdd, r).replace(".option klu", ".option klu gminsteps=0"), "0",
+            ["a8", "x", "y4", "cq", "e2", "vdd#branch", "v33#branch"])
+        for ext in (".flat.ngt", ".trace.ngt.gz"):
+            os.remove(os.path.join(HERE, "mixsrc" + ext))
     if "latch" in which:
         run("latch", latch_netlist(), "0-40,100,101,200", ["q", "qb", "a", "b", "vdd#branch", "vm#branch"])
     if "srcs" in which:

@@ -40,7 +40,9 @@ def _compare(res, t, v, wave, s, exact, tol=1e-9, same_route=True):
         assert (err <= tol).all(), err
 
 
-@pytest.mark.parametrize("name", ["ro17", "ro17k", "inv", "dio", "b3ring", "latch", "srcs"])
+# invsrc / invgmin: the inverter with `.option noopiter` (+ `gminsteps=0`): CKTop goes straight to gillespie_src /
+# dynamic_gmin (cktop.c:42-96), which run per sample inside the device controller
+@pytest.mark.parametrize("name", ["ro17", "ro17k", "inv", "dio", "b3ring", "latch", "srcs", "invsrc", "invgmin"])
 def test_tran_hostsim_bit_identical(hostsim_lib, name):
     res, t, v, wave = _run(hostsim_lib, name)
     _compare(res, t, v, wave, 0, exact=True)
@@ -89,6 +91,54 @@ def test_tran_hostsim_mix_sweep(hostsim_lib):
     _mix_sweep(hostsim_lib)
 
 
+def _mix_source_stepping(lib, reps=1):
+    """CKTop with gmin stepping switched off (`.option gminsteps=0`): the sweep point whose plain Newton iteration
+    fails goes through gillespie_src (cktop.c:481-660) -- sources at zero, then raised with an adaptive step, per
+    sample inside the device controller.  Its neighbours in the batch converge directly and must not be disturbed.
+    The reference run (tests/golden/mixsrc.wave.ngt) needs 1701 Newton iterations in all."""
+    flat = ngt.read(f"{GOLDEN}/mix.flat.ngt")
+    trace = ngt.read(f"{GOLDEN}/mix.trace.ngt.gz")
+    wave = ngt.read(f"{GOLDEN}/mix.wave.ngt")
+    circ = pkg.Circuit.from_flat(lib, flat, lu_pattern=run_patterns(trace))
+    circ.set_op_fallbacks(gminsteps=0, srcsteps=1)
+    pts = [MIX_POINTS[0], MIX_POINTS[5], MIX_POINTS[1]] * reps
+    b = pkg.Batch(circ, len(pts))
+    pkg.sweep.apply(b, flat, dc={"vdd": [p[0] for p in pts]}, res={"r1": [p[1] for p in pts]})
+    res = b.tran(8192, wave["save_eq"])
+    t, v = res.waves()
+    for s in range(len(pts)):
+        if s % 3 != 1:
+            _compare(res, t, v, ngt.read(f"{GOLDEN}/{('mix', '', 'mix1')[s % 3]}.wave.ngt"), s, exact=False, same_route=True)
+    if all(int(res.accepted[s]) == 0 for s in range(1, len(pts), 3)):
+        # the zero-source matrix has an exact zero pivot under the pivot orders recorded from the centre's run; the
+        # reference re-pivots there (niiter.c: E_SINGULAR -> NISHOULDREORDER), this path reports E_SINGULAR for the sample
+        # until it has its own pivoting factor (DESIGN.md section 8).  gillespie_src itself is pinned by `invsrc`.
+        pytest.xfail("source stepping of the mixed cell needs a re-pivoting factor at the zero-source solve")
+    for s in range(1, len(pts), 3):
+        _compare(res, t, v, ngt.read(f"{GOLDEN}/mixsrc.wave.ngt"), s, exact=False, same_route=True)
+    return res
+
+
+def test_tran_hostsim_mix_source_stepping(hostsim_lib):
+    _mix_source_stepping(hostsim_lib)
+
+
+def test_op_fallback_options_refused(hostsim_lib):
+    """spice3_gmin / spice3_src (counts > 1) are not on this path: refused when the option is set, not at run time"""
+    flat = ngt.read(f"{GOLDEN}/inv.flat.ngt")
+    circ = pkg.Circuit.from_flat(hostsim_lib, flat)
+    with pytest.raises(pkg.NgbError):
+        circ.set_op_fallbacks(gminsteps=10)
+    with pytest.raises(pkg.NgbError):
+        circ.set_op_fallbacks(srcsteps=5)
+    circ.set_op_fallbacks(gminsteps=0, srcsteps=0)
+
+
+@pytest.mark.gpu
+def test_tran_gpu_mix_source_stepping(cuda_lib):
+    _mix_source_stepping(cuda_lib, reps=12)     # 36 samples: the stepping sample shares its warps with direct ones
+
+
 @pytest.mark.gpu
 def test_tran_gpu_mix_sweep(cuda_lib):
     _mix_sweep(cuda_lib, reps=9)        # 72 samples: more than two warps, every point on its own time axis
@@ -131,7 +181,8 @@ def test_tran_hostsim_mc_batch(hostsim_lib):
 # device follows the reference bit for bit; the assertions below allow 1e-9 (the north_star
 # tolerance) but identical accepted / rejected / iteration counts are required.
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,exact", [("ro17k", True), ("ro17", True), ("inv", True), ("dio", False), ("b3ring", True), ("vbic", False), ("latch", True), ("srcs", False)])
+@pytest.mark.parametrize("name,exact", [("ro17k", True), ("ro17", True), ("inv", True), ("dio", False), ("b3ring", True), ("vbic", False), ("latch", True), ("srcs", False),
+                                        ("invsrc", True), ("invgmin", True)])
 def test_tran_gpu_matches_reference(cuda_lib, name, exact):
     """north_star bar: 1e-9 relative and identical accepted-step count; the device arithmetic
     (no FMA contraction, glibc-compatible exp/log) in fact reproduces the reference bit for bit.
