@@ -745,6 +745,7 @@ static void dump_klu_values(KLUmatrix *K, const char *prefix)
     free(Lx); free(Ux);
 }
 
+static int op_loads = 0;
 int __wrap_CKTload(CKTcircuit *ckt)
 {
     static int flat_done = 0;
@@ -752,6 +753,7 @@ int __wrap_CKTload(CKTcircuit *ckt)
     int err;
     char nm[64];
     cur_ckt = ckt;
+    if (ckt->CKTmode & MODETRANOP) op_loads++;          /* loads of CKTop: plain NIiter + its fallbacks (OPtran loads under MODETRAN) */
     lookup_types();
     if (flat && !flat_done) { flat_done = 1; dump_flat(ckt, flat); }
     if (trace && !trace_f) {
@@ -859,9 +861,9 @@ int __wrap_DCtran(CKTcircuit *ckt, int restart)
             STATistics *s = ckt->CKTstat;
             fprintf(f, "{\"ret\": %d, \"accepted\": %d, \"rejected\": %d, \"numiter\": %d, \"timepts\": %d, "
                        "\"load_calls\": %d, \"load_time\": %.9g, \"decomp_time\": %.9g, \"reorder_time\": %.9g, "
-                       "\"solve_time\": %.9g, \"tran_time\": %.9g}\n",
+                       "\"solve_time\": %.9g, \"tran_time\": %.9g, \"op_loads\": %d}\n",
                     r, s->STATaccepted, s->STATrejected, s->STATnumIter, s->STATtimePts, call_no + 1,
-                    s->STATloadTime, s->STATdecompTime, s->STATreorderTime, s->STATsolveTime, s->STATtranTime);
+                    s->STATloadTime, s->STATdecompTime, s->STATreorderTime, s->STATsolveTime, s->STATtranTime, op_loads);
             fclose(f);
         }
     }

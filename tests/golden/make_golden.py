@@ -349,6 +349,26 @@ def run(name, netlist, calls, save):
     print(name, "points", arr.shape[0], "stats", stats)
 
 
+def run_op_only(name, netlist):
+    """a run whose operating point FAILS in the reference: circuit, pattern sets and the statistics only -- `op_loads` is
+    the number of CKTload calls under MODETRANOP, i.e. the Newton iterations of CKTop's plain NIiter and all its fallbacks"""
+    os.makedirs(TMP, exist_ok=True)
+    cir = os.path.join(TMP, name + ".cir")
+    open(cir, "w").write(netlist)
+    open(os.path.join(HERE, "netlists", name + ".cir"), "w").write(netlist)
+    env = dict(os.environ, NGB_DUMP_FLAT=os.path.join(TMP, name + ".flat"), NGB_DUMP_TRACE=os.path.join(TMP, name + ".trace"),
+               NGB_DUMP_CALLS="0", NGB_DUMP_STATS=os.path.join(TMP, name + ".stats"))
+    p = subprocess.run([DUMP, "-b", "-r", os.path.join(TMP, name + ".raw"), cir], env=env, capture_output=True, text=True)
+    stats = json.load(open(env["NGB_DUMP_STATS"]))
+    log = [ln for ln in (p.stdout + p.stderr).splitlines() if "stepping" in ln]
+    ngt.write(os.path.join(HERE, name + ".flat.ngt"), ngt.read(env["NGB_DUMP_FLAT"]))
+    ngt.write(os.path.join(HERE, name + ".trace.ngt.gz"), ngt.read(env["NGB_DUMP_TRACE"]))
+    ngt.write(os.path.join(HERE, name + ".wave.ngt"),
+              {"stats": np.array([stats["accepted"], stats["rejected"], stats["numiter"], stats["timepts"], stats["load_calls"],
+                                  stats["op_loads"], stats["ret"]], np.int32)})
+    print(name, stats, log)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["ro17", "ro101", "ro17k", "ro17mc"]
     if "ro17" in which:
@@ -380,6 +400,11 @@ if __name__ == "__main__":
         # otherwise dynamic_gmin.  The pivoting events are the usual four, so these fixtures carry their own pattern sets
         run("invsrc", inv_netlist().replace(".option klu", ".option klu noopiter gminsteps=0"), "0,1", ["out", "in", "vdd#branch", "vin#branch"])
         run("invgmin", inv_netlist().replace(".option klu", ".option klu noopiter"), "0,1", ["out", "in", "vdd#branch", "vin#branch"])
+    if "invfail" in which:
+        # tolerances no iteration can meet: the plain NIiter, dynamic_gmin, new_gmin and gillespie_src all fail in turn
+        # (cktop.c:62-96) -- the lengths of their ladders are what this pins (the zero-source solve of gillespie_src is the
+        # one NIiter that converges: its iterates are exactly zero)
+        run_op_only("invfail", inv_netlist().replace(".option klu", ".option klu reltol=1e-15 vntol=1e-20 abstol=1e-22"))
     if "mixsrc" in which:
         # the operating point of MIX_POINTS[5] with gmin stepping switched off: CKTop goes straight to gillespie_src
         # (cktop.c:87-96, 481-660); waveform and statistics only, the batch runs on mix.flat.ngt
