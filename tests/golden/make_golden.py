@@ -405,6 +405,10 @@ if __name__ == "__main__":
         # (cktop.c:62-96) -- the lengths of their ladders are what this pins (the zero-source solve of gillespie_src is the
         # one NIiter that converges: its iterates are exactly zero)
         run_op_only("invfail", inv_netlist().replace(".option klu", ".option klu reltol=1e-15 vntol=1e-20 abstol=1e-22"))
+    if "invtstep" in which:
+        # tolerances the transient cannot hold: the run is abandoned with "timestep too small" (dctran.c:901-913) after
+        # 1044 accepted points; accepted / rejected / iteration counts up to the failure are what this pins
+        run_op_only("invtstep", inv_netlist().replace(".option klu", ".option klu reltol=9e-13 vntol=1e-14 abstol=1e-18"))
     if "mixsrc" in which:
         # the operating point of MIX_POINTS[5] with gmin stepping switched off: CKTop goes straight to gillespie_src
         # (cktop.c:87-96, 481-660); waveform and statistics only, the batch runs on mix.flat.ngt

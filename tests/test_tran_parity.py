@@ -153,6 +153,31 @@ def test_op_fallback_chain_fails_like_reference_gpu(cuda_lib):
     _op_chain_fails(cuda_lib, S=33)
 
 
+def _timestep_too_small(lib, S=1):
+    """tolerances the transient cannot hold (reltol 9e-13): the reference abandons the run with E_TIMESTEP ("timestep too
+    small", dctran.c:901-913) after 1044 accepted and 284 rejected points and 43 314 iterations; every sample of the batch
+    must stop at the same point with the same code"""
+    flat = ngt.read(f"{GOLDEN}/invtstep.flat.ngt")
+    trace = ngt.read(f"{GOLDEN}/invtstep.trace.ngt.gz")
+    acc, rej, nit, _, _, _, ret = (int(x) for x in ngt.read(f"{GOLDEN}/invtstep.wave.ngt")["stats"])
+    assert ret == 106
+    circ = pkg.Circuit.from_flat(lib, flat, lu_pattern=run_patterns(trace))
+    b = pkg.Batch(circ, S)
+    res = b.tran(8192, np.array([1], np.int32))
+    err = b.get("ctl.err")
+    for s in range(S):
+        assert (int(res.accepted[s]), int(res.rejected[s]), int(res.numiter[s]), int(err[s])) == (acc, rej, nit, 106)
+
+
+def test_tran_hostsim_timestep_too_small(hostsim_lib):
+    _timestep_too_small(hostsim_lib)
+
+
+@pytest.mark.gpu
+def test_tran_gpu_timestep_too_small(cuda_lib):
+    _timestep_too_small(cuda_lib, S=3)
+
+
 def test_op_fallback_options_refused(hostsim_lib):
     """spice3_gmin / spice3_src (counts > 1) are not on this path: refused when the option is set, not at run time"""
     flat = ngt.read(f"{GOLDEN}/inv.flat.ngt")
