@@ -48,6 +48,14 @@ def test_tran_hostsim_bit_identical(hostsim_lib, name):
     _compare(res, t, v, wave, 0, exact=True)
 
 
+@pytest.mark.parametrize("name", ["invsrc", "invgmin"])
+def test_tran_hostsim_fallback_batch(hostsim_lib, name):
+    """the `.option noopiter` start state is set up for every sample of a batch, not only the first"""
+    res, t, v, wave = _run(hostsim_lib, name, S=3)
+    for s in range(3):
+        _compare(res, t, v, wave, s, exact=True)
+
+
 def test_tran_hostsim_vbic(hostsim_lib):
     """VBIC stages (DC operating point + PULSE transient): identical accepted / rejected / iteration
     counts and 1e-9 on the waveforms.  Not bit-identical by construction: the Jacobian entries come from
