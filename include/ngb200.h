@@ -64,7 +64,8 @@ int ngbCircuitSetOptions(ngb_circuit *c, const double dopt[15], const int iopt[5
  * spice3_src: E_UNSUPP), CKTdcTrcvMaxIter (itl2, default 50), CKTgminFactor (default 10) and CKTnoOpIter (`.option noopiter`:
  * CKTop skips the plain NIiter, cktop.c:42-55).  They run per sample inside
  * the device controller of ngbTranRun */
-int ngbCircuitSetOpFallbacks(ngb_circuit *c, int num_gmin_steps, int num_src_steps, int itl2, double gmin_factor, int no_op_iter);
+int ngbCircuitSetOpFallbacks(ngb_circuit *c, int num_gmin_steps, int num_src_steps, int itl2, double gmin_factor, int no_op_iter,
+                             double gshunt /* CKTgshunt: the ladders end on MAX(CKTgmin, CKTgshunt) and leave CKTdiagGmin = CKTgshunt */);
 
 /* BSIM4 instances in the order of the reference instance lists (cktcrte.c:62-64).
  * nodes [12][ninst], flags [ninst] (B4F_*), prow [ninst] row of mtab/ptab, inst [NI][ninst],

@@ -336,7 +336,7 @@ static int shim_attach(CKTcircuit *ckt)
     iopt[0] = ckt->CKTintegrateMethod; iopt[1] = ckt->CKTmaxOrder; iopt[2] = ckt->CKTtranMaxIter; iopt[3] = ckt->CKTdcMaxIter;
     iopt[4] = (ckt->CKTmode & MODEUIC) ? 1 : 0;
     ngbCircuitSetOptions(G.C, dopt, iopt);
-    if ((rc = ngbCircuitSetOpFallbacks(G.C, ckt->CKTnumGminSteps, ckt->CKTnumSrcSteps, ckt->CKTdcTrcvMaxIter, ckt->CKTgminFactor, ckt->CKTnoOpIter))) return shim_fail(ngbLastError());
+    if ((rc = ngbCircuitSetOpFallbacks(G.C, ckt->CKTnumGminSteps, ckt->CKTnumSrcSteps, ckt->CKTdcTrcvMaxIter, ckt->CKTgminFactor, ckt->CKTnoOpIter, ckt->CKTgshunt))) return shim_fail(ngbLastError());
     COUNT(BSIM4, G.tB4, G.n4); COUNT(BSIM3, G.tB3, G.n3); COUNT(DIO, G.tDIO, G.nd); COUNT(VBIC, G.tVBIC, G.nq); COUNT(CAP, G.tCAP, G.nc);
     if ((rc = flatten_bsim3(ckt)) || (rc = flatten_bsim4(ckt)) || (rc = flatten_dio(ckt)) || (rc = flatten_vbic(ckt)) || (rc = flatten_linear(ckt)) ||
         (rc = ngbCircuitFinalize(G.C))) {

@@ -145,7 +145,8 @@ class Circuit:
         lib.check(lib.L.ngbCircuitSetOptions(c.h, _dp(d), _ip(i)), "ngbCircuitSetOptions")
         if "opt/gminsteps" in flat:      # CKTop's fallbacks (cktop.c:62-96); fixtures recorded before the key existed use the defaults
             lib.check(lib.L.ngbCircuitSetOpFallbacks(c.h, int(sc(flat, "opt/gminsteps")), int(sc(flat, "opt/srcsteps")), int(sc(flat, "opt/itl2")),
-                                                     ctypes.c_double(float(sc(flat, "opt/gminfactor"))), int(sc(flat, "opt/noopiter", 0))), "ngbCircuitSetOpFallbacks")
+                                                     ctypes.c_double(float(sc(flat, "opt/gminfactor"))), int(sc(flat, "opt/noopiter", 0)),
+                                                     ctypes.c_double(float(sc(flat, "opt/gshunt", 0.0)))), "ngbCircuitSetOpFallbacks")
         if sc(flat, "opt/bypass", 0):
             raise NgbError("CKTbypass != 0 is not supported on this path")
         n = sc(flat, "b4/ninst", 0)
@@ -226,11 +227,11 @@ class Circuit:
         self.lib.check(self.lib.L.ngbCircuitGetBsim4Slots(self.h, _ip(s)))
         return s
 
-    def set_op_fallbacks(self, gminsteps=1, srcsteps=1, itl2=50, gminfactor=10.0, noopiter=0):
+    def set_op_fallbacks(self, gminsteps=1, srcsteps=1, itl2=50, gminfactor=10.0, noopiter=0, gshunt=0.0):
         """CKTop's fallbacks after a failed plain NIiter (cktop.c:62-96): `.option gminsteps= srcsteps= itl2= gminfactor=`;
         0 skips the route, 1 is dynamic_gmin + new_gmin / gillespie_src, larger counts are refused (E_UNSUPP); `noopiter` skips
         the plain NIiter"""
-        self.lib.check(self.lib.L.ngbCircuitSetOpFallbacks(self.h, int(gminsteps), int(srcsteps), int(itl2), ctypes.c_double(float(gminfactor)), int(noopiter)),
+        self.lib.check(self.lib.L.ngbCircuitSetOpFallbacks(self.h, int(gminsteps), int(srcsteps), int(itl2), ctypes.c_double(float(gminfactor)), int(noopiter), ctypes.c_double(float(gshunt))),
                        "ngbCircuitSetOpFallbacks")
 
     def set_lu_pattern(self, pat, prefix="", which=0, uic=None):

@@ -219,13 +219,14 @@ int ngbCircuitSetOptions(ngb_circuit *c, const double d[15], const int i[5])
 /* the operating-point fallbacks of CKTop (cktop.c:62-96): CKTnumGminSteps and CKTnumSrcSteps (0 skips the route, 1 is
  * dynamic_gmin + new_gmin / gillespie_src; larger counts select spice3_gmin / spice3_src, which are not built),
  * CKTdcTrcvMaxIter (itl2), CKTgminFactor, and CKTnoOpIter (`.option noopiter`: no plain NIiter, straight to the fallbacks) */
-int ngbCircuitSetOpFallbacks(ngb_circuit *c, int num_gmin_steps, int num_src_steps, int itl2, double gmin_factor, int no_op_iter)
+int ngbCircuitSetOpFallbacks(ngb_circuit *c, int num_gmin_steps, int num_src_steps, int itl2, double gmin_factor, int no_op_iter, double gshunt)
 {
     if (num_gmin_steps < 0 || num_gmin_steps > 1) { ngb_set_error("gminsteps=%d selects spice3_gmin, which is not on this path (0 or 1)", num_gmin_steps); return NGB_E_UNSUPP; }
     if (num_src_steps < 0 || num_src_steps > 1) { ngb_set_error("srcsteps=%d selects spice3_src, which is not on this path (0 or 1)", num_src_steps); return NGB_E_UNSUPP; }
     if (itl2 < 1 || !(gmin_factor > 1.0)) { ngb_set_error("itl2=%d / gminfactor=%g out of range", itl2, gmin_factor); return NGB_E_PANIC; }
     c->opt.num_gmin_steps = num_gmin_steps; c->opt.num_src_steps = num_src_steps; c->opt.itl2 = itl2; c->opt.gmin_factor = gmin_factor;
     c->opt.no_op_iter = no_op_iter ? 1 : 0;
+    c->opt.gshunt = gshunt > 0 ? gshunt : 0.0;
     return NGB_OK;
 }
 

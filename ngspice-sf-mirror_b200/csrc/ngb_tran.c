@@ -91,7 +91,7 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
         x->gm_startgmin = (double *)dz(sizeof(double) * S); x->gs_conv = (double *)dz(sizeof(double) * S);
         x->gs_raise = (double *)dz(sizeof(double) * S); x->gs_i = (int *)dz(sizeof(int) * S);
         x->num_gmin_steps = c->opt.num_gmin_steps; x->num_src_steps = c->opt.num_src_steps;
-        x->itl2 = c->opt.itl2; x->gmin_factor = c->opt.gmin_factor;
+        x->itl2 = c->opt.itl2; x->gmin_factor = c->opt.gmin_factor; x->gshunt = c->opt.gshunt;
         for (i = 0; i < 5; i++)
             if (tab[i].st && tab[i].n > 0) {
                 x->gm_arr[x->gm_narr].state = tab[i].st; x->gm_arr[x->gm_narr].K = tab[i].K; x->gm_arr[x->gm_narr].ninst = tab[i].n;

@@ -61,7 +61,7 @@ typedef struct NgbTranCtx {
     double *gm_startgmin, *gs_conv, *gs_raise;   /* [S] CKTgmin on entry of new_gmin; ConvFact; raise */
     int *gs_i;                        /* [S] step of the ladder */
     int num_gmin_steps, num_src_steps, itl2;     /* CKTnumGminSteps, CKTnumSrcSteps (0: skip, 1: the routes built here), CKTdcTrcvMaxIter */
-    double gmin_factor;               /* CKTgminFactor */
+    double gmin_factor, gshunt;       /* CKTgminFactor, CKTgshunt */
     double *gm_xold;           /* [neq1][S] OldRhsOld */
     struct { double *state, *old; int K, ninst; } gm_arr[5];   /* device state tables and their OldCKTstate0 copies [K][ninst*S] */
     int gm_narr, gm_enable;
@@ -471,7 +471,8 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
             /* the two gmin ladders differ in what they step (CKTdiagGmin through LoadGmin / CKTgmin inside the device
              * models), in the floor of the shrinking factor and in the value they leave behind */
             double *g = stage == 1 ? &c->ctl.diag_gmin[s] : &c->ctl.gmin[s];
-            const double gtarget = stage == 1 ? c->ctl.gmin[s] : c->gm_startgmin[s];      /* MAX(CKTgmin, CKTgshunt), gshunt = 0 */
+            const double g0 = stage == 1 ? c->ctl.gmin[s] : c->gm_startgmin[s];
+            const double gtarget = NGB_MAX(g0, c->gshunt);                       /* MAX(CKTgmin, CKTgshunt) */
             double factor = c->gm_factor[s];
             int leave = 0;
             if (niret == NGB_OK) {
@@ -494,13 +495,13 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
                 ngb_gm_states(c, s, 2);
             }
             c->gm_factor[s] = factor;
-            if (leave) { *g = stage == 1 ? 0.0 : gtarget; c->gm_stage[s] = stage + 1; }   /* CKTdiagGmin = CKTgshunt / CKTgmin = its start value; final NIiter */
+            if (leave) { *g = stage == 1 ? c->gshunt : gtarget; c->gm_stage[s] = stage + 1; }   /* CKTdiagGmin = CKTgshunt / CKTgmin = MAX(start value, CKTgshunt); final NIiter */
             ngb_gm_next_niiter(c, s, mode);
             return;
         }
         if (stage == 10) {
             if (niret != NGB_OK) {                              /* the ladder: CKTdiagGmin from 1e10 * gmin down, eleven steps */
-                double dg = c->ctl.gmin[s];
+                double dg = (c->gshunt <= 0) ? c->ctl.gmin[s] : c->gshunt;
                 for (int i = 0; i < 10; i++) dg *= 10;
                 c->ctl.diag_gmin[s] = dg;
                 c->gs_i[s] = 0;
@@ -511,7 +512,7 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
             raise_init = 1;
         } else if (stage == 11) {
             if (niret != NGB_OK) {                              /* "gmin step failed": no solution at zero sources */
-                c->ctl.diag_gmin[s] = 0.0; c->ctl.srcfact[s] = 1.0;
+                c->ctl.diag_gmin[s] = c->gshunt; c->ctl.srcfact[s] = 1.0;
                 ngb_finish(c, s, NGB_PH_FAIL, NGB_E_ITERLIM);
                 return;
             }
@@ -519,7 +520,7 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
             mode = contmode;
             c->gs_i[s] += 1;
             if (c->gs_i[s] <= 10) { ngb_gm_next_niiter(c, s, mode); return; }
-            c->ctl.diag_gmin[s] = 0.0;
+            c->ctl.diag_gmin[s] = c->gshunt;
             raise_init = 1;
         }
         if (raise_init) {

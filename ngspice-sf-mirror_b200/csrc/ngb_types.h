@@ -67,6 +67,7 @@ typedef struct NgbOpts {
     int no_op_iter;                            /* CKTnoOpIter: skip the plain NIiter of CKTop, start with the fallbacks */
     int num_gmin_steps, num_src_steps, itl2;   /* CKTnumGminSteps, CKTnumSrcSteps, CKTdcTrcvMaxIter (cktntask.c:117-122) */
     double gmin_factor;                        /* CKTgminFactor */
+    double gshunt;                             /* CKTgshunt (`.option gshunt`): what the gmin ladders of CKTop end on */
 } NgbOpts;
 
 /* two-terminal linear elements and sources */

@@ -571,7 +571,7 @@ static void dump_flat(CKTcircuit *ckt, const char *path)
     put_ds(f, "opt/vt0", CONSTvt0);
     put_is(f, "opt/gminsteps", ckt->CKTnumGminSteps); put_is(f, "opt/srcsteps", ckt->CKTnumSrcSteps);
     put_is(f, "opt/itl2", ckt->CKTdcTrcvMaxIter); put_ds(f, "opt/gminfactor", ckt->CKTgminFactor);
-    put_is(f, "opt/noopiter", ckt->CKTnoOpIter);
+    put_is(f, "opt/noopiter", ckt->CKTnoOpIter); put_ds(f, "opt/gshunt", ckt->CKTgshunt);
     put_ds(f, "tran/tstep", ckt->CKTstep); put_ds(f, "tran/tstop", ckt->CKTfinalTime);
     put_ds(f, "tran/tmax", ckt->CKTmaxStep); put_ds(f, "tran/tstart", ckt->CKTinitTime);
     put_is(f, "tran/uic", (ckt->CKTmode & MODEUIC) ? 1 : 0);

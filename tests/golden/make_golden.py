@@ -309,7 +309,7 @@ def run(name, netlist, calls, save):
     os.makedirs(TMP, exist_ok=True)
     cir = os.path.join(TMP, name + ".cir")
     open(cir, "w").write(netlist)
-    if name in ("ro17", "ro101", "ro17k", "inv", "dio", "b3ring", "arr", "vbic", "mix", "latch", "srcs", "mixsrc", "invsrc", "invgmin"):
+    if name in ("ro17", "ro101", "ro17k", "inv", "dio", "b3ring", "arr", "vbic", "mix", "latch", "srcs", "mixsrc", "invsrc", "invgmin", "invshunt"):
         # the netlist itself is kept too: the CPU-baseline arm of bench.py feeds it to oracle/_ref/ngspice
         os.makedirs(os.path.join(HERE, "netlists"), exist_ok=True)
         open(os.path.join(HERE, "netlists", name + ".cir"), "w").write(netlist)
@@ -400,6 +400,10 @@ if __name__ == "__main__":
         # otherwise dynamic_gmin.  The pivoting events are the usual four, so these fixtures carry their own pattern sets
         run("invsrc", inv_netlist().replace(".option klu", ".option klu noopiter gminsteps=0"), "0,1", ["out", "in", "vdd#branch", "vin#branch"])
         run("invgmin", inv_netlist().replace(".option klu", ".option klu noopiter"), "0,1", ["out", "in", "vdd#branch", "vin#branch"])
+    if "invshunt" in which:
+        # `.option gshunt` sets CKTgshunt: dynamic_gmin then ends on
+        # MAX(CKTgmin, CKTgshunt) and leaves CKTdiagGmin = CKTgshunt for the whole transient (cktop.c:178, 268)
+        run("invshunt", inv_netlist().replace(".option klu", ".option klu noopiter gshunt=1e-9"), "0,1", ["out", "in", "vdd#branch", "vin#branch"])
     if "invfail" in which:
         # tolerances no iteration can meet: the plain NIiter, dynamic_gmin, new_gmin and gillespie_src all fail in turn
         # (cktop.c:62-96) -- the lengths of their ladders are what this pins (the zero-source solve of gillespie_src is the

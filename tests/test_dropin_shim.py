@@ -13,7 +13,7 @@ import pytest
 from parity_util import GOLDEN, ROOT
 
 REF = os.path.join(ROOT, "oracle", "_ref", "ngspice")
-NETLISTS = ["ro17k", "inv", "dio", "b3ring", "arr", "latch", "srcs", "invsrc", "invgmin"]     # invsrc / invgmin: CKTop's own source / gmin stepping drives CKTsrcFact and CKTdiagGmin through the shim
+NETLISTS = ["ro17k", "inv", "dio", "b3ring", "arr", "latch", "srcs", "invsrc", "invgmin", "invshunt"]     # invsrc / invgmin: CKTop's own source / gmin stepping drives CKTsrcFact and CKTdiagGmin through the shim
 
 
 def _payload(path):

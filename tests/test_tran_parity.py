@@ -42,7 +42,7 @@ def _compare(res, t, v, wave, s, exact, tol=1e-9, same_route=True):
 
 # invsrc / invgmin: the inverter with `.option noopiter` (+ `gminsteps=0`): CKTop goes straight to gillespie_src /
 # dynamic_gmin (cktop.c:42-96), which run per sample inside the device controller
-@pytest.mark.parametrize("name", ["ro17", "ro17k", "inv", "dio", "b3ring", "latch", "srcs", "invsrc", "invgmin"])
+@pytest.mark.parametrize("name", ["ro17", "ro17k", "inv", "dio", "b3ring", "latch", "srcs", "invsrc", "invgmin", "invshunt"])       # invshunt: gshunt=1e-9 ends the ladder and stays on the diagonal
 def test_tran_hostsim_bit_identical(hostsim_lib, name):
     res, t, v, wave = _run(hostsim_lib, name)
     _compare(res, t, v, wave, 0, exact=True)
@@ -245,7 +245,7 @@ def test_tran_hostsim_mc_batch(hostsim_lib):
 # tolerance) but identical accepted / rejected / iteration counts are required.
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,exact", [("ro17k", True), ("ro17", True), ("inv", True), ("dio", False), ("b3ring", True), ("vbic", False), ("latch", True), ("srcs", False),
-                                        ("invsrc", True), ("invgmin", True)])
+                                        ("invsrc", True), ("invgmin", True), ("invshunt", True)])
 def test_tran_gpu_matches_reference(cuda_lib, name, exact):
     """north_star bar: 1e-9 relative and identical accepted-step count; the device arithmetic
     (no FMA contraction, glibc-compatible exp/log) in fact reproduces the reference bit for bit.
