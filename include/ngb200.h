@@ -189,6 +189,9 @@ int ngbNewtonStep(ngb_batch *b);               /* ngbLoad + ngbLuFacSolve       
 /* device-resident transient analysis for the whole batch (DCtran + NIiter, per sample) */
 int ngbTranRun(ngb_batch *b, int max_points, const int *save_eq, int nsave);
 int ngbTranStats(ngb_batch *b, int *accepted, int *rejected, int *numiter, int *npoints /* each [S] */);
+/* DCtran's return value per sample (dctran.c: 0, E_ITERLIM 103 when CKTop and its fallbacks fail, E_TIMESTEP 106 "timestep
+ * too small", E_SINGULAR 102 ...): a failed sample stops, the others run on, ngbTranRun returns 0 */
+int ngbTranErrors(ngb_batch *b, int *err /* [S] */);
 long ngbTranWaveBytes(ngb_batch *b);
 int ngbTranWaves(ngb_batch *b, double *times /* [S][max_points] */, double *values /* [S][max_points][nsave] */);
 long ngbTranTicks(ngb_batch *b);              /* Newton steps the batch needed */

@@ -270,6 +270,14 @@ int ngbTranStats(ngb_batch *b, int *accepted, int *rejected, int *numiter, int *
     if (npoints) ngb_dev_d2h(npoints, t->x.npts, n);
     return NGB_OK;
 }
+/* what DCtran returned for each sample: 0, or the reference's error number (E_SINGULAR 102, E_ITERLIM 103 -- the operating
+ * point could not be found --, E_TIMESTEP 106, ...).  ngbTranRun itself fails only when the batch as a whole cannot go on */
+int ngbTranErrors(ngb_batch *b, int *err)
+{
+    if (!b->tran || !err) return NGB_E_PANIC;
+    ngb_dev_d2h(err, b->ctl.err, sizeof(int) * (size_t)b->S);
+    return NGB_OK;
+}
 long ngbTranWaveBytes(ngb_batch *b)
 {
     struct ngb_tran *t = b->tran;

@@ -29,7 +29,7 @@ def _compare(res, t, v, wave, s, exact, tol=1e-9, same_route=True):
     assert int(res.accepted[s]) == acc and int(res.rejected[s]) == rej
     assert int(res.numiter[s]) == nit or not same_route
     n = int(res.npoints[s])
-    assert n == len(wave["time"])
+    assert n == len(wave["time"]) and int(res.err[s]) == 0
     if exact:
         assert np.array_equal(t[s, :n], wave["time"])
         assert np.array_equal(v[s, :n, :], wave["values"])
@@ -144,7 +144,7 @@ def _op_chain_fails(lib, S=1, count_tol=0.0):
     circ = pkg.Circuit.from_flat(lib, flat, lu_pattern=run_patterns(trace))
     b = pkg.Batch(circ, S)
     res = b.tran(64, np.array([1], np.int32))
-    err = b.get("ctl.err")
+    err = res.err
     for s in range(S):
         assert int(res.accepted[s]) == 0 and int(res.npoints[s]) == 0
         assert int(err[s]) == 103                                  # E_ITERLIM, "source stepping failed"
@@ -175,7 +175,7 @@ def _timestep_too_small(lib, S=1, count_tol=0.0):
     circ = pkg.Circuit.from_flat(lib, flat, lu_pattern=run_patterns(trace))
     b = pkg.Batch(circ, S)
     res = b.tran(8192, np.array([1], np.int32))
-    err = b.get("ctl.err")
+    err = res.err
     for s in range(S):
         assert int(err[s]) == 106
         got = (int(res.accepted[s]), int(res.rejected[s]), int(res.numiter[s]))
