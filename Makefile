@@ -5,6 +5,9 @@
 PKG := ngspice-sf-mirror_b200
 CSRC := $(PKG)/csrc
 NGB_INLINE_DIV ?= none
+# divisions that share a denominator register share its reciprocal (tools/nvcc_outline.py): minimum number of
+# divisions per denominator, 0 = off
+NGB_SHARE_RCP ?= 0
 NVCC ?= nvcc
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -Xcompiler -fPIC -std=c++17 \
            -Xptxas -v -I$(CSRC) -Iinclude
@@ -18,7 +21,7 @@ all: $(PKG)/libngb200.so
 $(PKG)/libngb200.so: $(CSRC)/ngb_cuda.cu $(HOSTC) $(HDRS) $(CSRC)/bsim4_finish.inc tools/nvcc_outline.py
 	gcc -O2 -fPIC -std=gnu99 -Wall -I$(CSRC) -Iinclude -x c -include $(CSRC)/c_compat.h -c $(CSRC)/ngb_host.c -o $(CSRC)/ngb_host.o
 	gcc -O2 -fPIC -std=gnu99 -Wall -I$(CSRC) -Iinclude -x c -include $(CSRC)/c_compat.h -c $(CSRC)/ngb_tran.c -o $(CSRC)/ngb_tran.o
-	python3 tools/nvcc_outline.py --outline-entries bsim4,ngb_k_b4_ --inline-div $(NGB_INLINE_DIV) -- $(NVCC) $(NVFLAGS) $(NVDEFS) -c $(CSRC)/ngb_cuda.cu -o $(CSRC)/ngb_cuda.o 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; false)
+	python3 tools/nvcc_outline.py --outline-entries bsim4,ngb_k_b4_ --inline-div $(NGB_INLINE_DIV) --share-rcp $(NGB_SHARE_RCP) -- $(NVCC) $(NVFLAGS) $(NVDEFS) -c $(CSRC)/ngb_cuda.cu -o $(CSRC)/ngb_cuda.o 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; false)
 	$(NVCC) -shared -o $@ $(CSRC)/ngb_cuda.o $(CSRC)/ngb_host.o $(CSRC)/ngb_tran.o -lcudart
 
 hostsim: tests/hostsim/libngb200_hostsim.so

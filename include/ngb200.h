@@ -43,6 +43,10 @@ int ngbSync(void);
  * events; ngbProfileRead returns the summed milliseconds and the number of timed launches */
 void ngbProfile(int enable, int every);
 int ngbProfileRead(double *ms_sum, long *count);
+/* FP64-pipe peak of the selected GPU, measured by a register-only micro-benchmark (the roofline's FP64 denominator):
+ * out[0] DFMA flop/s (2 per instruction), out[1] DADD/DMUL flop/s (1 per instruction: what -fmad=false code can reach),
+ * out[2] SM clock in kHz as the driver reports it */
+int ngbMeasureFp64Peak(double out[3]);
 
 /* field-list sizes, so callers can check they were built against the same lists
  * (bsim4_fields.h): [0]=model [1]=bin [2]=instance [3]=node roles [4]=matrix stamps

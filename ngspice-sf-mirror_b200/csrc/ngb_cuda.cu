@@ -247,6 +247,29 @@ __global__ void ngb_k_clear_i32(int *p, int value, int n)
     if (i < n) p[i] = value;
 }
 
+
+/* FP64-pipe peak of this GPU, measured: eight independent register chains per thread, no memory.
+ * fused = 1: DFMA (2 flop per instruction); fused = 0: alternating DADD / DMUL, the instruction mix of code compiled
+ * with -fmad=false (1 flop per instruction) -- the denominator of roofline.fp64_frac */
+template <int FUSED>
+__global__ void __launch_bounds__(256)
+ngb_k_fp64_peak(double *out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0 - 1e-9 * seed, c = 1e-7;
+    for (int i = 0; i < iters; i++) {
+        if (FUSED) {
+            a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+            a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+        } else {
+            a0 = __dmul_rn(a0, m); a1 = __dadd_rn(a1, c); a2 = __dmul_rn(a2, m); a3 = __dadd_rn(a3, c);
+            a4 = __dmul_rn(a4, m); a5 = __dadd_rn(a5, c); a6 = __dmul_rn(a6, m); a7 = __dadd_rn(a7, c);
+        }
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678) out[0] = r;      /* keeps the chains alive, never true */
+}
+
 /* ------------------------------------------------------------------ runtime */
 extern "C" {
 
@@ -413,6 +436,38 @@ int ngb_dev_branch_end(void)
             CUDA_OK(cudaEventRecord(g_join[i], g_side[i]));
             CUDA_OK(cudaStreamWaitEvent(g_stream, g_join[i], 0));
         }
+    return 0;
+}
+
+
+/* out[0] = DFMA flop/s (2 per instruction), out[1] = DADD/DMUL flop/s (1 per instruction), out[2] = SM clock (kHz) the
+ * driver reports; best of `reps` launches of 148 x 8 CTAs x 256 threads x 8 chains */
+int ngb_dev_fp64_peak(double out[3])
+{
+    if (!g_stream) { ngb_set_error("ngbInit first"); return NGB_E_PANIC; }
+    double *d = nullptr;
+    CUDA_OK(cudaMalloc(&d, 8));
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    const int iters = 1 << 14, grid = g_sm_count * 8, reps = 5;
+    for (int fused = 1; fused >= 0; fused--) {
+        double best = 0.0;
+        for (int r = 0; r < reps + 1; r++) {
+            cudaEventRecord(e0, g_stream);
+            if (fused) ngb_k_fp64_peak<1><<<grid, 256, 0, g_stream>>>(d, iters, 1.0 + r);
+            else ngb_k_fp64_peak<0><<<grid, 256, 0, g_stream>>>(d, iters, 1.0 + r);
+            cudaEventRecord(e1, g_stream);
+            CUDA_OK(cudaEventSynchronize(e1));
+            float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+            const double rate = (double)grid * 256 * 8 * iters * (fused ? 2.0 : 1.0) / (ms * 1e-3);
+            if (r > 0 && rate > best) best = rate;      /* launch 0 is the warm-up */
+        }
+        out[fused ? 0 : 1] = best;
+    }
+    int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g_device);
+    out[2] = khz;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    g_launches += 2 * (reps + 1);
     return 0;
 }
 

@@ -31,6 +31,7 @@ int ngbSetStream(void *cuda_stream) { return ngb_dev_set_stream(cuda_stream); }
 int ngbSync(void) { return ngb_dev_sync(); }
 void ngbProfile(int enable, int every) { ngb_dev_profile(enable, every); }
 int ngbProfileRead(double *ms_sum, long *count) { return ngb_dev_profile_read(ms_sum, count); }
+int ngbMeasureFp64Peak(double out[3]) { return ngb_dev_fp64_peak(out); }
 
 /* ------------------------------------------------------------------ field names */
 #define X(n) #n,

@@ -28,6 +28,7 @@ int ngb_dev_set_stream(void *) { return 0; }
 void ngb_dev_profile(int, int) {}
 int ngb_dev_profile_read(double *ms, long *n) { if (ms) *ms = 0; if (n) *n = 0; return 0; }
 int ngb_dev_profile_due(void) { return 0; }
+int ngb_dev_fp64_peak(double out[3]) { out[0] = out[1] = out[2] = 0; return NGB_E_PANIC; }
 int ngb_dev_branch_begin(void) { return 0; }
 void ngb_dev_branch(int) {}
 int ngb_dev_branch_end(void) { return 0; }
