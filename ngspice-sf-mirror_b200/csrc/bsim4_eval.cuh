@@ -26,7 +26,6 @@
 #include "ngb_types.h"
 #include "bsim4_fields.h"
 #include "devsup.cuh"
-#include "bsim4_split.h"
 
 /* Optional CTA-wide barrier at each phase boundary of the evaluation (keeps the warps of a CTA in
  * one instruction-cache window).  Measured on B200: no gain (571 vs 572 us per launch), so it is
@@ -70,7 +69,6 @@ typedef struct B4Ctx {
     double *op;                /* [B4O_COUNT][T] operating point (von is read back)      */
     int op_full;               /* 0: keep only von ; 1: export every B4O_* (parity runs) */
     int split;                 /* 1: exact-order stamps (B4X_* rows live), 0: merged      */
-    double *wscr;              /* [B4WF_COUNT][T] B4W fields in flight between the kernels of the phase-split load; NULL: one kernel */
     int lte_deferred;          /* 1: BSIM4trunc runs in its own launch after the solve, for converged samples only (b4_lte_thread) */
     const int *nodeconv;       /* [S] node part of NIconvTest (LU kernel), read by b4_lte_thread            */
     const double *x;           /* [2][neq1][S] solution buffers; xsel[s] picks CKTrhsOld  */
@@ -2965,7 +2963,6 @@ NGB_HD int b4_prologue(const B4Ctx *c, size_t t, int first, B4Pro *p, int *err)
 }
 
 NGB_HD int b4_finish(const B4Ctx *c, size_t t, const B4Pro *pro, const B4W *wp);
-NGB_HD int b4_finish_lazy(const B4Ctx *c, size_t t, const B4Pro *pro, const B4W *wp);
 
 NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
 {
@@ -2987,59 +2984,6 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
 #undef B4FIN_NAME
 #undef B4FIN_W
 #undef BW
-#define B4FIN_NAME b4_finish_lazy
-#define B4FIN_W (void)wp;
-#define BW(f) NGB_LDG((const double *)&c->wscr[(size_t)B4WF_##f * c->T + t])
-#include "bsim4_finish.inc"
-#undef B4FIN_NAME
-#undef B4FIN_W
-#undef BW
-
-/* ---- the same evaluation as four kernels (core / parasitics / charges / finish) -----------------
- * One evaluation is ~23 k instructions and keeps ~180 doubles alive; as one kernel it runs at 128
- * registers with ~1 KB of spill per thread and streams 390 KB of code per warp.  Split at the phase
- * boundaries, every kernel has a third of the code and of the live values; the B4W fields a later phase
- * needs (bsim4_split.h, generated from this file) travel through c->wscr, thread-fastest, written once
- * and read once.  The arithmetic is the same code in the same order: results are bit-identical. */
-#define B4W_LD_D(f) w.f = c->wscr[(size_t)B4WF_##f * c->T + t];
-#define B4W_LD_I(f) w.f = (int)c->wscr[(size_t)B4WF_##f * c->T + t];
-#define B4W_ST_D(f) c->wscr[(size_t)B4WF_##f * c->T + t] = w.f;
-#define B4W_ST_I(f) c->wscr[(size_t)B4WF_##f * c->T + t] = (double)w.f;
-
-NGB_HD int b4_phase_core(const B4Ctx *c, size_t t)
-{
-    B4Pro p; B4W w; int err;
-    if (!b4_prologue(c, t, 1, &p, &err)) return err;
-    b4_fetch_limit(c, t, p.inst, p.s, p.head, p.mode_ckt, p.Mrow, p.flags, &w);
-    b4_core_dc(c, t, p.s, p.Mrow, p.Prow, p.flags, &w);
-    B4W_OUT_CORE(B4W_ST_D, B4W_ST_I)
-    return NGB_OK;
-}
-NGB_HD int b4_phase_para(const B4Ctx *c, size_t t)
-{
-    B4Pro p; B4W w; int err;
-    if (!b4_prologue(c, t, 0, &p, &err)) return NGB_OK;       /* the first phase has reported it */
-    B4W_IN_PARA(B4W_LD_D, B4W_LD_I)
-    b4_parasitics(c, t, p.Mrow, p.Prow, p.flags, &w);
-    B4W_OUT_PARA(B4W_ST_D, B4W_ST_I)
-    return NGB_OK;
-}
-NGB_HD int b4_phase_chrg(const B4Ctx *c, size_t t)
-{
-    B4Pro p; B4W w; int err;
-    if (!b4_prologue(c, t, 0, &p, &err)) return NGB_OK;
-    B4W_IN_CHRG(B4W_LD_D, B4W_LD_I)
-    b4_charges(c, t, p.Mrow, p.Prow, p.charge, &w);
-    B4W_OUT_CHRG(B4W_ST_D, B4W_ST_I)
-    return NGB_OK;
-}
-NGB_HD int b4_phase_fin(const B4Ctx *c, size_t t)
-{
-    B4Pro p; int err;
-    if (!b4_prologue(c, t, 0, &p, &err)) return NGB_OK;
-    return b4_finish_lazy(c, t, &p, (const B4W *)0);
-}
-
 /* ---- BSIM4trunc out of the load ------------------------------------------------------------------
  * The reference calls DEVtrunc once per converged time point (CKTtrunc, dctran.c:794); evaluated inside every
  * load it was a fifth of the kernel's instructions (10 copies of CKTterr, 70 of the 313 divisions).  With

@@ -52,35 +52,6 @@ ngb_k_bsim4_load(const B4Ctx c, int *errflag)
     if (e) atomicMax(errflag, e);
 }
 
-/* the four kernels of the phase-split load (bsim4_eval.cuh: b4_phase_*); register budgets per phase */
-#ifndef NGB_B4P_CTA
-#define NGB_B4P_CTA 256
-#endif
-#ifndef NGB_B4P_MB_CORE
-#define NGB_B4P_MB_CORE 2
-#endif
-#ifndef NGB_B4P_MB_PARA
-#define NGB_B4P_MB_PARA 2
-#endif
-#ifndef NGB_B4P_MB_CHRG
-#define NGB_B4P_MB_CHRG 2
-#endif
-#ifndef NGB_B4P_MB_FIN
-#define NGB_B4P_MB_FIN 2
-#endif
-#define NGB_B4_PHASE_KERNEL(name, body, mb) \
-__global__ void __launch_bounds__(NGB_B4P_CTA, mb) name(const B4Ctx c, int *errflag) \
-{ \
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; \
-    if (t >= (size_t)c.T) return; \
-    const int e = body(&c, t); \
-    if (e) atomicMax(errflag, e); \
-}
-NGB_B4_PHASE_KERNEL(ngb_k_b4_core, b4_phase_core, NGB_B4P_MB_CORE)
-NGB_B4_PHASE_KERNEL(ngb_k_b4_para, b4_phase_para, NGB_B4P_MB_PARA)
-NGB_B4_PHASE_KERNEL(ngb_k_b4_chrg, b4_phase_chrg, NGB_B4P_MB_CHRG)
-NGB_B4_PHASE_KERNEL(ngb_k_b4_fin, b4_phase_fin, NGB_B4P_MB_FIN)
-
 __global__ void __launch_bounds__(128)
 ngb_k_bsim4_lte(const B4Ctx c)
 {
@@ -487,14 +458,6 @@ int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag)
     const int rec = !g_capturing && g_prof_on && g_prof_n < NGB_PROF_MAX && (g_prof_force || (g_prof_seen++ % g_prof_every == 0));
     g_prof_force = 0;
     if (rec) cudaEventRecord(g_prof_ev[2 * g_prof_n], g_cur);
-    if (c->wscr) {
-        const unsigned gp = (unsigned)(((size_t)c->T + NGB_B4P_CTA - 1) / NGB_B4P_CTA);
-        ngb_k_b4_core<<<gp, NGB_B4P_CTA, 0, g_cur>>>(*c, errflag);
-        ngb_k_b4_para<<<gp, NGB_B4P_CTA, 0, g_cur>>>(*c, errflag);
-        ngb_k_b4_chrg<<<gp, NGB_B4P_CTA, 0, g_cur>>>(*c, errflag);
-        if (!g_capturing) g_launches += 3;
-        ngb_k_b4_fin<<<gp, NGB_B4P_CTA, 0, g_cur>>>(*c, errflag);
-    } else
     ngb_k_bsim4_load<<<grid, NGB_B4_CTA, 0, g_cur>>>(*c, errflag);
     if (rec) { cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], g_cur); g_prof_n++; }
     return post_launch("bsim4_load");

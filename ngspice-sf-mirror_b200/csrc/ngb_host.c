@@ -1561,12 +1561,6 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
         b->b4_inst = (double *)dalloc_rep(b, "b4.inst", c->b4_inst, B4I_COUNT, c->b4_n, S);
         b->b4_state = (double *)dalloc(b, "b4.state", sizeof(double) * NGB_NHIST * B4ST_COUNT * T);
         b->b4_op = (double *)dalloc(b, "b4.op", sizeof(double) * B4O_COUNT * T);
-        {   /* phase-split load (four kernels, B4W fields through a scratch array): NGB_B4_SPLIT=1 forces it,
-             * =0 forbids it; by default batches large enough to fill the chip several times use it */
-            const char *e = getenv("NGB_B4_SPLIT");
-            const int on = e ? atoi(e) : (T >= (size_t)NGB_B4_SPLIT_MIN);
-            b->b4_wscr = on ? (double *)dalloc(b, "b4.wscr", sizeof(double) * B4WF_COUNT * T) : NULL;
-        }
         b->b4_mtab = (double *)dev_dup(c->b4_mtab, sizeof(double) * (size_t)c->b4_nrows * B4M_COUNT);
         b->b4_ptab = (double *)dev_dup(c->b4_ptab, sizeof(double) * (size_t)c->b4_nrows * B4P_COUNT);
         reg(b, "b4.mtab", b->b4_mtab, sizeof(double) * (size_t)c->b4_nrows * B4M_COUNT);
@@ -1790,7 +1784,7 @@ void ngb_fill_b4ctx(ngb_batch *b, B4Ctx *x)
     x->inst = b->b4_inst; x->flags = b->b4_flags; x->nodes = b->b4_nodes; x->spos = b->b4_spos;
     x->stamp = b->stamp; x->state = b->b4_state; x->op = b->b4_op; x->op_full = b->op_full;
     x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl; x->temp = c->opt.temp; x->vt0 = c->opt.vt0;
-    x->split = c->exact_order; x->wscr = b->b4_wscr; x->lte_deferred = b->lte_deferred; x->nodeconv = b->nodeconv;
+    x->split = c->exact_order; x->lte_deferred = b->lte_deferred; x->nodeconv = b->nodeconv;
     x->srow0 = c->b4_row0;
 }
 void ngb_fill_capctx(ngb_batch *b, NgbCapCtx *x)

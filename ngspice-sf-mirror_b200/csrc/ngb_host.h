@@ -1,10 +1,6 @@
 /* ngb_host.h -- host-side objects behind the opaque handles of include/ngb200.h */
 #ifndef NGB_HOST_H
 #define NGB_HOST_H
-/* BSIM4 evaluations per launch from which the load runs as four phase kernels (see bsim4_eval.cuh) */
-#ifndef NGB_B4_SPLIT_MIN
-#define NGB_B4_SPLIT_MIN (1 << 30)
-#endif
 #include "ngb_types.h"
 #include "bsim4_eval.cuh"
 #include "dio_eval.cuh"
@@ -62,7 +58,6 @@ struct ngb_batch {
     double *x, *Ax, *stamp;
     int *errflag;
     int *d_node_type, *d_tgt_ptr, *d_tgt_rows, *d_slot_diag, *d_long_tgt;
-    double *b4_wscr;                  /* scratch of the phase-split BSIM4 load or NULL */
     int lte_deferred;                 /* transient driver: BSIM4trunc in its own launch after the solve */
     double *b4_inst, *b4_state, *b4_op, *b4_mtab, *b4_ptab; int *b4_prow, *b4_prow_t, *b4_flags, *b4_nodes, *b4_spos;
     double *cap_par, *cap_state; int *cap_nodes, *cap_spos;

@@ -40,13 +40,6 @@ void ngb_dev_graph_destroy(void *) {}
 int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag)
 {
     g_launches++;
-    if (c->wscr) {        /* phase-split load: the four kernels one after the other, as on the device */
-        int (*const ph[4])(const B4Ctx *, size_t) = { b4_phase_core, b4_phase_para, b4_phase_chrg, b4_phase_fin };
-        for (int k = 0; k < 4; k++)
-            for (size_t t = 0; t < (size_t)c->T; t++) { int e = ph[k](c, t); if (e && errflag && !errflag[0]) errflag[0] = e; }
-        g_launches += 3;
-        return 0;
-    }
     for (size_t t = 0; t < (size_t)c->T; t++) { int e = b4_load_thread(c, t); if (e && errflag && !errflag[0]) errflag[0] = e; }
     return 0;
 }
