@@ -79,7 +79,10 @@ typedef struct B4Ctx {
     double vt0;                /* CONSTvt0                                               */
 } B4Ctx;
 
-/* values shared between the evaluation phases of one thread */
+/* values shared between the evaluation phases of one thread.  ~90 of them are written by an early phase and read once
+ * by the finish phase; keeping the first 16 / 32 / 48 of those in shared memory ([field][thread], one LDS / STS per
+ * access) instead of leaving them to the register allocator was measured on B200 and changes nothing (508 / 507 / 519
+ * against 509 us per Newton step; profiles/README.md, round 2), so they are plain members */
 typedef struct B4W {
     /* limited terminal voltages (NMOS polarity) */
     double vds, vgs, vbs, vbd, vgd, vgb, vges, vgms, vged, vgmd, vgmb;
@@ -227,7 +230,17 @@ NGB_HD_SHARED void b4_tat(double vts, double vj, double Nvtmr, double *Tn, doubl
 }
 
 /* state accessors: ring-rotated history, [hist][state][thread] */
-#define B4ST(h, k) c->state[((size_t)(((head) + (h)) % c->ctl.nhist) * B4ST_COUNT + (k)) * c->T + t]
+/* the ring position of history h is head + h (mod nhist); the four per-thread base pointers are formed once per
+ * function (B4ST_BASES) with a compare instead of an integer remainder per access */
+#define B4ST_BASES(head_) \
+    const int b4nh_ = c->ctl.nhist; \
+    const size_t b4hs_ = (size_t)B4ST_COUNT * c->T; \
+    double *const b4st0 = c->state + (size_t)(head_) * b4hs_ + t; \
+    double *const b4st1 = c->state + (size_t)(((head_) + 1 >= b4nh_) ? (head_) + 1 - b4nh_ : (head_) + 1) * b4hs_ + t; \
+    double *const b4st2 = c->state + (size_t)(((head_) + 2 >= b4nh_) ? (head_) + 2 - b4nh_ : (head_) + 2) * b4hs_ + t; \
+    double *const b4st3 = c->state + (size_t)(((head_) + 3 >= b4nh_) ? (head_) + 3 - b4nh_ : (head_) + 3) * b4hs_ + t; \
+    (void)b4st1; (void)b4st2; (void)b4st3; (void)b4st0
+#define B4ST(h, k) b4st##h[(size_t)(k) * c->T]
 
 /* Phase A: terminal voltages by INITF mode and Newton step limiting (b4ld.c:257-698). */
 NGB_HD void b4_fetch_limit(const B4Ctx *c, size_t t, int inst, int s, int head, int mode_ckt,
@@ -238,6 +251,7 @@ NGB_HD void b4_fetch_limit(const B4Ctx *c, size_t t, int inst, int s, int head, 
     const double type = B4M(type);
     const int rdsMod = (int)B4M(rdsMod);
     const int S = c->S;
+    B4ST_BASES(head);
     double vds, vgs, vbs, vges, vgms, vdbs, vsbs, vses, vdes, qdef;
     double vbd, vgd, vged, vgmd, vdbd;
     int Check = 1, Check1 = 1, Check2 = 1;
@@ -391,15 +405,17 @@ NGB_HD void b4_fetch_limit(const B4Ctx *c, size_t t, int inst, int s, int head, 
 
     w->vds = vds; w->vgs = vgs; w->vbs = vbs; w->vges = vges; w->vgms = vgms;
     w->vdbs = vdbs; w->vsbs = vsbs; w->vses = vses; w->vdes = vdes; w->qdef = qdef;
-    w->vbd = vbs - vds;
+    vbd = vbs - vds;
+    vdbd = vdbs - vds;
+    w->vbd = vbd;
     w->vgd = vgs - vds;
     w->vgb = vgs - vbs;
     w->vged = vges - vds;
     w->vgmd = vgms - vds;
     w->vgmb = vgms - vbs;
-    w->vdbd = vdbs - vds;
-    w->vbs_jct = (!rbodyMod) ? w->vbs : w->vsbs;
-    w->vbd_jct = (!rbodyMod) ? w->vbd : w->vdbd;
+    w->vdbd = vdbd;
+    w->vbs_jct = (!rbodyMod) ? vbs : vsbs;
+    w->vbd_jct = (!rbodyMod) ? vbd : vdbd;
     w->Check = Check;
 }
 
@@ -425,7 +441,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     {
         const int dioMod = (int)B4M(dioMod);
         const double weffCJnf = B4P(weffCJ) * nf;
-        double Isat, Nvtm;
+        double Isat, Nvtm, jg, jc;
 
         Nvtm = vtm * B4M(SjctEmissionCoeff);
         if ((B4I(Aseff) <= 0.0) && (B4I(Pseff) <= 0.0)) Isat = 0.0;
@@ -434,7 +450,8 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
                   + weffCJnf * B4M(SjctGateSidewallTempSatCurDensity);
         b4_junction_dc(dioMod, Isat, Nvtm, w->vbs_jct, gmin, B4M(bvs), B4M(xjbvs), B4I(XExpBVS),
                        B4I(vjsmFwd), B4I(vjsmRev), B4I(IVjsmFwd), B4I(IVjsmRev),
-                       B4I(SslpFwd), B4I(SslpRev), &w->gbs, &w->cbs);
+                       B4I(SslpFwd), B4I(SslpRev), &jg, &jc);
+        double gbs = jg, cbs = jc;
 
         Nvtm = vtm * B4M(DjctEmissionCoeff);
         if ((B4I(Adeff) <= 0.0) && (B4I(Pdeff) <= 0.0)) Isat = 0.0;
@@ -443,7 +460,8 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
                   + weffCJnf * B4M(DjctGateSidewallTempSatCurDensity);
         b4_junction_dc(dioMod, Isat, Nvtm, w->vbd_jct, gmin, B4M(bvd), B4M(xjbvd), B4I(XExpBVD),
                        B4I(vjdmFwd), B4I(vjdmRev), B4I(IVjdmFwd), B4I(IVjdmRev),
-                       B4I(DslpFwd), B4I(DslpRev), &w->gbd, &w->cbd);
+                       B4I(DslpFwd), B4I(DslpRev), &jg, &jc);
+        double gbd = jg, cbd = jc;
 
         /* trap-assisted tunnelling and recombination current for reverse bias */
         {
@@ -454,15 +472,16 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
             b4_tat(B4M(vtsswd),  w->vbd_jct, vtm0 * B4M(njtsswdtemp),  &Td4, &dTd4);
             b4_tat(B4M(vtsswgs), w->vbs_jct, vtm0 * B4M(njtsswgstemp), &Ts5, &dTs5);
             b4_tat(B4M(vtsswgd), w->vbd_jct, vtm0 * B4M(njtsswgdtemp), &Td6, &dTd6);
-            w->gbs += B4I(SjctTempRevSatCur) * dTs1 + B4I(SswTempRevSatCur) * dTs3
+            gbs += B4I(SjctTempRevSatCur) * dTs1 + B4I(SswTempRevSatCur) * dTs3
                     + B4I(SswgTempRevSatCur) * dTs5;
-            w->cbs -= B4I(SjctTempRevSatCur) * (Ts1 - 1.0) + B4I(SswTempRevSatCur) * (Ts3 - 1.0)
+            cbs -= B4I(SjctTempRevSatCur) * (Ts1 - 1.0) + B4I(SswTempRevSatCur) * (Ts3 - 1.0)
                     + B4I(SswgTempRevSatCur) * (Ts5 - 1.0);
-            w->gbd += B4I(DjctTempRevSatCur) * dTd2 + B4I(DswTempRevSatCur) * dTd4
+            gbd += B4I(DjctTempRevSatCur) * dTd2 + B4I(DswTempRevSatCur) * dTd4
                     + B4I(DswgTempRevSatCur) * dTd6;
-            w->cbd -= B4I(DjctTempRevSatCur) * (Td2 - 1.0) + B4I(DswTempRevSatCur) * (Td4 - 1.0)
+            cbd -= B4I(DjctTempRevSatCur) * (Td2 - 1.0) + B4I(DswTempRevSatCur) * (Td4 - 1.0)
                     + B4I(DswgTempRevSatCur) * (Td6 - 1.0);
         }
+        w->gbs = gbs; w->cbs = cbs; w->gbd = gbd; w->cbd = cbd;
     }
 
     NGB_CTA_ALIGN();
@@ -1761,6 +1780,7 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
     {
         const double weffCJ = B4P(weffCJ);
         const double vfbsd_add = (mtrlMod == 0) ? 0.0 : B4P(vfbsd);
+        double gI, gGd, gGg, gGb;
         if (mtrlMod == 0) T0 = 3.0 * toxe;
         else T0 = B4M(epsrsub) * toxe / w->epsrox;
 
@@ -1768,23 +1788,27 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
             if (mtrlMod == 0) T1 = (vds - w->vgs_eff - B4P(egidl)) / T0;
             else T1 = (vds - w->vgs_eff - B4P(egidl) + vfbsd_add) / T0;
             b4_gidl0(T1, w->dvgs_eff_dvg, T0, B4P(agidl), B4P(bgidl), B4P(cgidl), weffCJ, vbd,
-                     &w->Igidl, &w->ggidld, &w->ggidlg, &w->ggidlb);
+                     &gI, &gGd, &gGg, &gGb);
+            w->Igidl = gI; w->ggidld = gGd; w->ggidlg = gGg; w->ggidlb = gGb;
             if (mtrlMod == 0) T1 = (-vds - w->vgd_eff - B4P(egisl)) / T0;
             else T1 = (-vds - w->vgd_eff - B4P(egisl) + vfbsd_add) / T0;
             b4_gidl0(T1, w->dvgd_eff_dvg, T0, B4P(agisl), B4P(bgisl), B4P(cgisl), weffCJ, vbs,
-                     &w->Igisl, &w->ggisls, &w->ggislg, &w->ggislb);
+                     &gI, &gGd, &gGg, &gGb);
+            w->Igisl = gI; w->ggisls = gGd; w->ggislg = gGg; w->ggislb = gGb;
         } else {
             const double gidlclamp = B4M(gidlclamp);
             if (mtrlMod == 0) T1 = (-vds - B4P(rgisl) * w->vgd_eff - B4P(egisl)) / T0;
             else T1 = (-vds - B4P(rgisl) * w->vgd_eff - B4P(egisl) + vfbsd_add) / T0;
             b4_gidl1(T1, w->dvgd_eff_dvg, T0, B4P(agisl), B4P(bgisl), B4P(cgisl), B4P(rgisl),
                      B4P(kgisl), B4P(fgisl), gidlclamp, weffCJ, vbs,
-                     &w->Igisl, &w->ggisls, &w->ggislg, &w->ggislb);
+                     &gI, &gGd, &gGg, &gGb);
+            w->Igisl = gI; w->ggisls = gGd; w->ggislg = gGg; w->ggislb = gGb;
             if (mtrlMod == 0) T1 = (vds - B4P(rgidl) * w->vgs_eff - B4P(egidl)) / T0;
             else T1 = (vds - B4P(rgidl) * w->vgs_eff - B4P(egidl) + vfbsd_add) / T0;
             b4_gidl1(T1, w->dvgs_eff_dvg, T0, B4P(agidl), B4P(bgidl), B4P(cgidl), B4P(rgidl),
                      B4P(kgidl), B4P(fgidl), gidlclamp, weffCJ, vbd,
-                     &w->Igidl, &w->ggidld, &w->ggidlg, &w->ggidlb);
+                     &gI, &gGd, &gGg, &gGb);
+            w->Igidl = gI; w->ggidld = gGd; w->ggidlg = gGg; w->ggidlb = gGb;
         }
     }
 
@@ -1975,12 +1999,15 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
         {
             const double vfbsd_tot = B4P(vfbsd) + B4P(vfbsdoff);
             const double BechvbEdge = B4P(BechvbEdge);
+            double eI, eG;
             b4_ig_edge(vgs, vfbsd_tot, B4P(AechvbEdgeS), BechvbEdge, B4P(aigs), B4P(bigs), B4P(cigs),
-                       &w->Igs, &w->gIgsg);
-            w->gIgss = -w->gIgsg;
+                       &eI, &eG);
+            w->Igs = eI; w->gIgsg = eG;
+            w->gIgss = -eG;
             b4_ig_edge(vgd, vfbsd_tot, B4P(AechvbEdgeD), BechvbEdge, B4P(aigd), B4P(bigd), B4P(cigd),
-                       &w->Igd, &w->gIgdg);
-            w->gIgdd = -w->gIgdg;
+                       &eI, &eG);
+            w->Igd = eI; w->gIgdg = eG;
+            w->gIgdd = -eG;
         }
         (void)T0;
     } else {
@@ -2948,6 +2975,7 @@ NGB_HD int b4_prologue(const B4Ctx *c, size_t t, int first, B4Pro *p, int *err)
     if (first) {
         const int sop = NGB_LDG(&c->ctl.stateop[s]);
         if (sop) {
+            B4ST_BASES(head);
             for (int k = 0; k < B4ST_COUNT; k++) {
                 if (sop & NGB_OP_COPY01) B4ST(1, k) = B4ST(0, k);
                 if (sop & NGB_OP_COPY1_23) { const double v = B4ST(1, k); B4ST(2, k) = v; if (c->ctl.nhist > 3) B4ST(3, k) = v; }
@@ -2972,6 +3000,8 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
     if (!b4_prologue(c, t, 1, &p, &err)) return err;
     b4_fetch_limit(c, t, p.inst, p.s, p.head, p.mode_ckt, p.Mrow, p.flags, &w);
     b4_core_dc(c, t, p.s, p.Mrow, p.Prow, p.flags, &w);
+    /* the parasitics and the intrinsic charges only read what the core phase left; the charges first (12 values for the
+     * finish phase alive across the parasitics instead of 52 across the charges) was measured 6 % SLOWER on B200 */
     b4_parasitics(c, t, p.Mrow, p.Prow, p.flags, &w);
     b4_charges(c, t, p.Mrow, p.Prow, p.charge, &w);
     return b4_finish(c, t, &p, &w);

@@ -15,16 +15,16 @@
 #include <cstdlib>
 
 #define NGB_GROUP_SYNC() do { if (nl <= 32) __syncwarp(ngb_gsync_mask); else __syncthreads(); } while (0)
-#include "ngb_dev.h"
-#include "ngb_kernels.cuh"
-#include "vbic_eval.cuh"
-
 #ifndef NGB_B4_CTA
 #define NGB_B4_CTA 256
 #endif
 #ifndef NGB_B4_MINBLOCKS
 #define NGB_B4_MINBLOCKS 2      /* 128 registers/thread, 16 warps/SM: measured 1.5x faster than 255 registers */
 #endif
+#include "ngb_dev.h"
+#include "ngb_kernels.cuh"
+#include "vbic_eval.cuh"
+
 static thread_local cudaStream_t g_stream = nullptr;   /* per host thread: batches driven from different threads run concurrently */
 /* device-type load kernels of one CKTload are independent of each other: they run on side streams between a
  * fork and a join event (parallel branches of the captured graph); g_cur is the stream a launch goes to */
