@@ -149,9 +149,19 @@ int ngbCircuitSelectLuSet(ngb_circuit *c, int which);
  * through ngbCircuitSelectLuSet + ngbCircuitSetLuPattern) each of these factors produced; a UIC run
  * starts at [2].  Default without this call: set 0 for [0],[1]; set 1 (if filled, else 0) for [2],[3] */
 int ngbCircuitSetLuEvents(ngb_circuit *c, const int *set_of_event);
-/* own BTF + fill-reducing ordering + pivoting factor on one sample's matrix values
- * (host; the role klu_analyze/klu_factor play) */
-int ngbCircuitAnalyze(ngb_circuit *c, const double *Ax);
+/* ---- own pivoting factor (the role klu_factor plays behind SMPreorder, klusmp.c:700-760, klu_factor.c:384,
+ * klu_kernel.c:642; csrc/ngb_pivot.c) ----
+ * ngbCircuitSetSymbolic imports what klu_analyze leaves (klu_symbolic P, Q, R: block triangular form with a
+ * fill-reducing order per block); ngbCircuitAnalyze computes an own one instead (one block, greedy minimum degree on
+ * A + A': results then agree with the reference to rounding, not bit for bit).  ngbCircuitFactor runs the pivoting
+ * left-looking factorization (threshold partial pivoting with diagonal preference, `pivtol` = CKTpivotRelTol, <= 0: 1e-3)
+ * on one sample's matrix values and makes the result the pattern set selected by ngbCircuitSelectLuSet, exactly as if
+ * it had been passed to ngbCircuitSetLuPattern; E_SINGULAR when a pivot is zero.  Inside ngbTranRun the same routine
+ * re-pivots a sample whose refactor met a zero pivot (niiter.c:162-195). */
+int ngbCircuitSetSymbolic(ngb_circuit *c, int n, int nblocks, const int *P, const int *Q, const int *R);
+int ngbCircuitAnalyze(ngb_circuit *c);
+int ngbCircuitFactor(ngb_circuit *c, const double *Ax /* [nnz], CSC slot order */, double pivtol);
+int ngbCircuitGetLuPattern(const ngb_circuit *c, int *Pnum, int *Lp, int *Li, int *Up, int *Ui, int *Offp, int *Offi);
 /* info: nV nlev npairs ntask nslev nsolvepairs lnz unz nzoff */
 int ngbCircuitLuInfo(const ngb_circuit *c, int info[9]);
 

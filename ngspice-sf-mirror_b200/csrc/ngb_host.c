@@ -198,7 +198,8 @@ void ngbCircuitDestroy(ngb_circuit *c)
     free(c->Ap); free(c->Ai); free(c->eq2col); free(c->col2eq); free(c->slot_diag); free(c->diag_slot);
     free(c->ov_eq); free(c->ov_kind); free(c->ov_cur); free(c->ov_diag); free(c->ov_zptr); free(c->ov_zslot); free(c->ov_val);
     free(c->long_tgt); free(c->tgt_ptr); free(c->tgt_rows); free(c->const_row); free(c->const_val);
-    free(c->klu_Q); free(c->klu_R); free(c->klu_Pnum);
+    free(c->klu_Q); free(c->klu_R); free(c->klu_Pnum); free(c->klu_P);
+    free(c->pat_Lp); free(c->pat_Li); free(c->pat_Up); free(c->pat_Ui); free(c->pat_Offp); free(c->pat_Offi);
     free_sched(&c->sch);
     free_packed(&c->pk);
     { int w; for (w = 0; w < NGB_LU_SETS; w++) if (c->lu[w].valid) { free_sched(&c->lu[w].sch); free_packed(&c->lu[w].pk); } }
@@ -1142,9 +1143,18 @@ int ngbCircuitSetLuPattern(ngb_circuit *c, int n, int nblocks, const int *Q, con
     if (!c->finalized) { ngb_set_error("circuit not finalized"); return NGB_E_PANIC; }
     if (n != c->n) { ngb_set_error("LU pattern order %d != matrix order %d", n, c->n); return NGB_E_PANIC; }
     free_sched(h);
-    free(c->klu_Q); free(c->klu_R); free(c->klu_Pnum);
-    c->klu_Q = (int *)xdup(Q, sizeof(int) * (size_t)n); c->klu_R = (int *)xdup(R, sizeof(int) * ((size_t)nblocks + 1));
-    c->klu_Pnum = (int *)xdup(Pnum, sizeof(int) * (size_t)n); c->klu_nblocks = nblocks;
+    {   /* keep the factor as given (ngbCircuitGetLuPattern); the arguments may be these very arrays */
+        int *q = (int *)xdup(Q, sizeof(int) * (size_t)n), *r = (int *)xdup(R, sizeof(int) * ((size_t)nblocks + 1));
+        int *pn = (int *)xdup(Pnum, sizeof(int) * (size_t)n);
+        int *lp = (int *)xdup(Lp, sizeof(int) * ((size_t)n + 1)), *li = (int *)xdup(Li, sizeof(int) * (size_t)(lnz > 0 ? lnz : 1));
+        int *up = (int *)xdup(Up, sizeof(int) * ((size_t)n + 1)), *ui = (int *)xdup(Ui, sizeof(int) * (size_t)(unz > 0 ? unz : 1));
+        int *op = (int *)xdup(Offp, sizeof(int) * ((size_t)n + 1)), *oi = (int *)xdup(Offi, sizeof(int) * (size_t)(nzoff > 0 ? nzoff : 1));
+        free(c->klu_Q); free(c->klu_R); free(c->klu_Pnum);
+        free(c->pat_Lp); free(c->pat_Li); free(c->pat_Up); free(c->pat_Ui); free(c->pat_Offp); free(c->pat_Offi);
+        c->klu_Q = q; c->klu_R = r; c->klu_Pnum = pn; c->klu_nblocks = nblocks;
+        c->pat_Lp = lp; c->pat_Li = li; c->pat_Up = up; c->pat_Ui = ui; c->pat_Offp = op; c->pat_Offi = oi;
+        Q = q; R = r; Pnum = pn; Lp = lp; Li = li; Up = up; Ui = ui; Offp = op; Offi = oi;
+    }
     c->lnz = lnz; c->unz = unz; c->nzoff = nzoff;
 
     Pinv = (int *)xcalloc((size_t)n, sizeof(int));

@@ -39,6 +39,9 @@ struct ngb_circuit {
     int ov_n; int *ov_eq, *ov_kind, *ov_cur, *ov_diag, *ov_zptr, *ov_zslot; double *ov_val;
     /* LU: imported or own symbolic objects + task schedule */
     int klu_nblocks; int *klu_Q, *klu_R, *klu_Pnum;
+    int *klu_P;                    /* symbolic row permutation (ngbCircuitSetSymbolic / ngbCircuitAnalyze), NULL when only finished factors were imported */
+    int *pat_Lp, *pat_Li, *pat_Up, *pat_Ui, *pat_Offp, *pat_Offi;    /* the factor last passed to ngbCircuitSetLuPattern */
+    double pivtol;                 /* threshold of the own pivoting factor (CKTpivotRelTol) */
     int lnz, unz, nzoff, npairs, nsolvepairs;
     NgbLuSched sch;                /* host arrays (set being built) */
     NgbLuPacked pk;                /* host arrays, level-contiguous 16-bit form */
@@ -87,6 +90,9 @@ void ngb_fill_asmctx(struct ngb_batch *b, NgbAsmCtx *x);
 void ngb_fill_luctx(struct ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve, int which);
 int ngb_enqueue_load(struct ngb_batch *b);
 void ngb_tran_free(struct ngb_batch *b);
+int ngb_pivot_factor(int n, const int *Ap, const int *Ai, const double *Ax, int nblocks, const int *P, const int *Q,
+                     const int *R, double tol, int *Pnum, int *Lp, int **Li_out, int *Up, int **Ui_out,
+                     int *Offp, int **Offi_out, int *singular_col);
 int ngbBatchSetBsim4Rows(struct ngb_batch *b, const int *prow_t, int nrows, const double *mtab, const double *ptab);
 
 #ifdef __cplusplus

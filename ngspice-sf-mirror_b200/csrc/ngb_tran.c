@@ -293,4 +293,3 @@ int ngbTranWaves(ngb_batch *b, double *times, double *values)
 }
 long ngbTranTicks(ngb_batch *b) { return b->tran ? b->tran->ticks : 0; }
 void *ngbTranDevWaves(ngb_batch *b, int which) { return b->tran ? (which ? (void *)b->tran->x.out_val : (void *)b->tran->x.out_time) : NULL; }
-int ngbCircuitAnalyze(ngb_circuit *c, const double *Ax) { (void)c; (void)Ax; ngb_set_error("own symbolic analysis not built yet"); return NGB_E_UNSUPP; }
