@@ -269,6 +269,11 @@ class Circuit:
         g = lambda k: _i32(pat[prefix + k])
         self._keep = [g(k) for k in ("Q", "R", "Pnum", "Lp", "Li", "Up", "Ui", "Offp", "Offi")]
         n = int(np.asarray(pat[prefix + "n"]).reshape(-1)[0]); nb = int(np.asarray(pat[prefix + "nblocks"]).reshape(-1)[0])
+        if (prefix + "P") in pat:
+            # klu_analyze's row permutation travels with the recorded factor: the library can then re-pivot a sample
+            # whose refactor meets a zero pivot (ngbCircuitSetSymbolic, csrc/ngb_pivot.c)
+            sym = [_i32(pat[prefix + k]) for k in ("P", "Q", "R")]
+            self.lib.check(self.lib.L.ngbCircuitSetSymbolic(self.h, n, nb, *[_ip(a) for a in sym]), "ngbCircuitSetSymbolic")
         self.lib.check(self.lib.L.ngbCircuitSetLuPattern(self.h, n, nb, *[_ip(a) for a in self._keep]),
                        "ngbCircuitSetLuPattern")
 

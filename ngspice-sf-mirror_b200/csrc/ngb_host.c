@@ -1130,6 +1130,19 @@ static void build_packed(ngb_circuit *c)
     free(vint); free(tint);
 }
 
+static unsigned long long lu_signature(int n, const int *Pnum, const int *Lp, const int *Li, const int *Up, const int *Ui)
+{
+    unsigned long long h = 1469598103934665603ULL;
+    int k;
+#define SIG(v) do { h ^= (unsigned long long)(unsigned)(v); h *= 1099511628211ULL; } while (0)
+    for (k = 0; k < n; k++) SIG(Pnum[k]);
+    for (k = 0; k <= n; k++) { SIG(Lp[k]); SIG(Up[k]); }
+    for (k = 0; k < Lp[n]; k++) SIG(Li[k]);
+    for (k = 0; k < Up[n]; k++) SIG(Ui[k]);
+#undef SIG
+    return h;
+}
+
 int ngbCircuitSetLuPattern(ngb_circuit *c, int n, int nblocks, const int *Q, const int *R, const int *Pnum,
                            const int *Lp, const int *Li, const int *Up, const int *Ui,
                            const int *Offp, const int *Offi)
@@ -1356,6 +1369,7 @@ int ngbCircuitSetLuPattern(ngb_circuit *c, int n, int nblocks, const int *Q, con
         if (L->valid) { free_sched(&L->sch); free_packed(&L->pk); }
         L->sch = c->sch; L->pk = c->pk; L->npairs = c->npairs; L->nsolvepairs = c->nsolvepairs;
         L->lnz = c->lnz; L->unz = c->unz; L->nzoff = c->nzoff; L->valid = 1;
+        L->sig = lu_signature(n, Pnum, Lp, Li, Up, Ui);
         memset(&c->sch, 0, sizeof c->sch); memset(&c->pk, 0, sizeof c->pk);
     }
     c->have_lu = 1;
@@ -1673,6 +1687,46 @@ static void batch_free_lu(ngb_batch *b)
             sched_dev_free(&b->dlu[w].dsch);
             b->dlu[w].valid = 0;
         }
+}
+
+/* The reference's answer to a zero pivot in a refactor (niiter.c:162-195): factor the SAME matrix again with pivoting.
+ * Sample s's matrix is fetched, the own pivoting factor (ngb_pivot.c) runs on the circuit's symbolic analysis, and the
+ * result is matched against the pattern sets already there or becomes a new one (slots NGB_LU_EVENTS .. NGB_LU_SETS-1),
+ * uploaded for this batch.  Returns 0 with *set_out, E_SINGULAR when the matrix really is singular, E_UNSUPP when
+ * there is no symbolic analysis to factor on or no free slot. */
+int ngb_batch_repivot(ngb_batch *b, int s, int *set_out)
+{
+    ngb_circuit *c = b->c;
+    const int n = c->n;
+    int rc, w, sing = -1, keep_target = c->lu_target;
+    double *Ax;
+    int *Pnum, *Lp, *Up, *Offp, *Li = NULL, *Ui = NULL, *Offi = NULL, *P, *Q, *R;
+    unsigned long long sig;
+    if (!c->klu_P) { ngb_set_error("zero pivot in sample %d and no symbolic analysis to re-pivot on (ngbCircuitSetSymbolic)", s); return NGB_E_UNSUPP; }
+    Ax = (double *)xcalloc((size_t)c->nnz, sizeof(double));
+    Pnum = (int *)xcalloc((size_t)n, sizeof(int)); Lp = (int *)xcalloc((size_t)n + 1, sizeof(int));
+    Up = (int *)xcalloc((size_t)n + 1, sizeof(int)); Offp = (int *)xcalloc((size_t)n + 1, sizeof(int));
+    P = (int *)xdup(c->klu_P, sizeof(int) * (size_t)n); Q = (int *)xdup(c->klu_Q, sizeof(int) * (size_t)n);
+    R = (int *)xdup(c->klu_R, sizeof(int) * ((size_t)c->klu_nblocks + 1));
+    ngb_dev_d2h(Ax, b->Ax + (size_t)s * c->nnz, sizeof(double) * (size_t)c->nnz);
+    rc = ngb_pivot_factor(n, c->Ap, c->Ai, Ax, c->klu_nblocks, P, Q, R, c->pivtol > 0 ? c->pivtol : 0.001,
+                          Pnum, Lp, &Li, Up, &Ui, Offp, &Offi, &sing);
+    if (rc) { if (rc == NGB_E_SINGULAR) ngb_set_error("sample %d: matrix is singular (column %d)", s, sing); goto done; }
+    sig = lu_signature(n, Pnum, Lp, Li, Up, Ui);
+    for (w = 0; w < NGB_LU_SETS; w++) if (c->lu[w].valid && c->lu[w].sig == sig) break;
+    if (w == NGB_LU_SETS) {
+        for (w = NGB_LU_EVENTS; w < NGB_LU_SETS; w++) if (!c->lu[w].valid) break;
+        if (w == NGB_LU_SETS) { ngb_set_error("sample %d needs a %dth pivot order; %d pattern sets per circuit", s, NGB_LU_SETS + 1, NGB_LU_SETS); rc = NGB_E_UNSUPP; goto done; }
+        c->lu_target = w;
+        rc = ngbCircuitSetLuPattern(c, n, c->klu_nblocks, Q, R, Pnum, Lp, Li, Up, Ui, Offp, Offi);
+        c->lu_target = keep_target;
+        if (rc) goto done;
+    }
+    if (!b->dlu[w].valid) { sched_to_dev(b, c, w); packed_to_dev(b, c, w); b->dlu[w].valid = 1; if (b->failed) { rc = NGB_E_PANIC; goto done; } }
+    *set_out = w;
+done:
+    free(Ax); free(Pnum); free(Lp); free(Up); free(Offp); free(Li); free(Ui); free(Offi); free(P); free(Q); free(R);
+    return rc;
 }
 
 /* the circuit's LU pattern sets changed after the batch was created (a later SMPreorder in the

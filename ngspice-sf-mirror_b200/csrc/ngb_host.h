@@ -47,7 +47,8 @@ struct ngb_circuit {
     NgbLuPacked pk;                /* host arrays, level-contiguous 16-bit form */
     /* finished pattern sets, one per distinct pivoting factor of a run (NIiter re-pivots in the INITJCT
      * iteration, in the iteration after it, and in the first two iterations of the first time point); lu_target selects which one ngbCircuitSetLuPattern fills */
-    struct ngb_luset { NgbLuSched sch; NgbLuPacked pk; int npairs, nsolvepairs, lnz, unz, nzoff, valid; } lu[NGB_LU_SETS];
+    struct ngb_luset { NgbLuSched sch; NgbLuPacked pk; int npairs, nsolvepairs, lnz, unz, nzoff, valid;
+                      unsigned long long sig; /* hash of the factor (row order + L / U patterns): equal factors share a set */ } lu[NGB_LU_SETS];
     int lu_target;
     int lu_event[NGB_LU_EVENTS], lu_event_set;   /* pivoting event -> pattern set (ngbCircuitSetLuEvents) */
 };
@@ -89,6 +90,7 @@ void ngb_fill_srcctx(struct ngb_batch *b, NgbSrcCtx *x, int is_current);
 void ngb_fill_asmctx(struct ngb_batch *b, NgbAsmCtx *x);
 void ngb_fill_luctx(struct ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve, int which);
 int ngb_enqueue_load(struct ngb_batch *b);
+int ngb_batch_repivot(struct ngb_batch *b, int s, int *set_out);   /* own pivoting factor of sample s's matrix -> pattern set */
 void ngb_tran_free(struct ngb_batch *b);
 int ngb_pivot_factor(int n, const int *Ap, const int *Ai, const double *Ax, int nblocks, const int *P, const int *Q,
                      const int *R, double tol, int *Pnum, int *Lp, int **Li_out, int *Up, int **Ui_out,

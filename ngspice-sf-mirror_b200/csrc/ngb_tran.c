@@ -17,7 +17,9 @@ struct ngb_tran {
     NgbTranCtx x;              /* device pointers */
     int max_points, nsave;
     int *d_save_eq;
-    long ticks;
+    int *d_mask;               /* [S] samples of a repivot_suspended pass */
+    long ticks; int repivots;
+    int keep_set[NGB_LU_SETS]; /* pattern sets a re-pivoted sample was moved to: launched every step from then on */
     int stage;                 /* 0: some sample is still in the operating point; 1: all in the transient;
                                 * 2: all past the last pivoting event (only the final pattern set is in use) */
     /* CUDA graph of one Newton step, one per launch sequence (= per stage);
@@ -39,6 +41,7 @@ void ngb_tran_free(struct ngb_batch *b)
     ngb_dev_free(t->x.gm_startgmin); ngb_dev_free(t->x.gs_conv); ngb_dev_free(t->x.gs_raise); ngb_dev_free(t->x.gs_i);
     { int a; for (a = 0; a < t->x.gm_narr; a++) ngb_dev_free(t->x.gm_arr[a].old); }
     ngb_dev_free(t->d_save_eq); ngb_dev_free(t->x.isrc_break); ngb_dev_free(t->x.vsrc_break);
+    ngb_dev_free(t->x.susp); ngb_dev_free(t->d_mask);
     ngb_dev_graph_destroy(t->graph[0]); ngb_dev_graph_destroy(t->graph[1]); ngb_dev_graph_destroy(t->graph[2]);
     free(t);
     b->tran = NULL;
@@ -68,6 +71,7 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     x->out_time = (double *)dz(sizeof(double) * (size_t)S * max_points);
     x->out_val = (double *)dz(sizeof(double) * (size_t)S * max_points * (nsave ? nsave : 1));
     x->ndone = (int *)dz(sizeof(int) * 4); x->evstage = (int *)dz(sizeof(int) * S);
+    x->susp = (int *)dz(sizeof(int) * S); t->d_mask = (int *)dz(sizeof(int) * S);
     ngb_fill_srcctx(b, &x->isrc, 1); ngb_fill_srcctx(b, &x->vsrc, 0);
     x->isrc_break = (double *)dz(sizeof(double) * (size_t)(x->isrc.ninst > 0 ? x->isrc.ninst : 1) * S);
     x->vsrc_break = (double *)dz(sizeof(double) * (size_t)(x->vsrc.ninst > 0 ? x->vsrc.ninst : 1) * S);
@@ -189,6 +193,7 @@ static int enqueue_tick_direct(ngb_batch *b, int with_lu)
             int used = 0;
             if (!b->dlu[w].valid) continue;
             for (e = first; e < NGB_LU_EVENTS; e++) if (ev[e] == w) used = 1;
+            if (b->tran->keep_set[w]) used = 1;
             if (!used) continue;                                            /* no sample can be on this set any more */
             ngb_fill_luctx(b, &lx, 1, 1, w);
             if (b->tran->x.nluset == 1) lx.ctl.lusel = NULL;               /* one set: no per-sample selection */
@@ -204,6 +209,80 @@ static int enqueue_tick_direct(ngb_batch *b, int with_lu)
     return ngb_launch_tran_control(&b->tran->x);
 }
 
+
+/* Samples whose refactor met a zero pivot wait, inactive, with susp == 1 (ngb_tran.cuh).  The reference answers a
+ * zero pivot by factoring the same matrix again with pivoting inside the same iteration (niiter.c:162-195, KLU mode:
+ * SMPreorder without reloading, KLUloadDiagGmin = 0); here the host does that per sample with the library's own pivoting
+ * factor (ngb_pivot.c), moves the sample to the resulting pattern set and repeats the rest of its Newton step -- assembly
+ * (the failed attempt solved in place over the right-hand side), refactor + solve, BSIM4trunc, controller -- for these
+ * samples alone.  A sample whose matrix the pivoting factor finds singular gets susp == 2: its NIiter returns
+ * E_SINGULAR, which CKTop answers with its fallbacks and DCtran with a shorter step. */
+static int repivot_suspended(ngb_batch *b)
+{
+    struct ngb_tran *t = b->tran;
+    const int S = b->S;
+    int *susp = (int *)calloc((size_t)S, sizeof(int)), *mask = (int *)calloc((size_t)S, sizeof(int));
+    int s, r = NGB_OK, w, used[NGB_LU_SETS], g, zero4[1] = { 0 };
+    const double big = 1e300;
+    if (!susp || !mask) { free(susp); free(mask); return NGB_E_PANIC; }
+    memset(used, 0, sizeof used);
+    ngb_dev_sync();
+    ngb_dev_d2h(susp, t->x.susp, sizeof(int) * (size_t)S);
+    for (s = 0; s < S; s++) {
+        const int one = 1, zero = 0;
+        int state = 0, err = 0;
+        if (susp[s] != 1) continue;
+        mask[s] = 1;
+        r = ngb_batch_repivot(b, s, &w);
+        if (r == NGB_OK) {
+            ngb_dev_h2d(b->ctl.lusel + s, &w, sizeof(int));
+            used[w] = 1; t->keep_set[w] = 1; t->repivots++;
+        } else if (r == NGB_E_SINGULAR || r == NGB_E_UNSUPP) {
+            state = 2; err = NGB_E_SINGULAR; r = NGB_OK;            /* the controller takes it from here */
+        } else break;
+        ngb_dev_h2d(t->x.susp + s, &state, sizeof(int));
+        ngb_dev_h2d(b->ctl.err + s, &err, sizeof(int));
+        ngb_dev_h2d(b->ctl.active + s, &one, sizeof(int));
+        ngb_dev_h2d(b->nodeconv + s, &zero, sizeof(int));
+        ngb_dev_h2d(b->ctl.lte + s, &big, sizeof(double));
+        ngb_dev_h2d(b->ctl.lte2 + s, &big, sizeof(double));
+    }
+    if (r == NGB_OK) {
+        ngb_dev_h2d(t->d_mask, mask, sizeof(int) * (size_t)S);
+        ngb_dev_h2d(t->x.ndone + 3, zero4, sizeof(int));
+        /* per-sample pattern selection is needed from now on, and the captured launch sequences are stale */
+        t->x.nluset = 2;
+        for (g = 0; g < 3; g++) { ngb_dev_graph_destroy(t->graph[g]); t->graph[g] = NULL; t->graph_state[g] = 0; }
+        {
+            NgbAsmCtx ax;
+            ngb_fill_asmctx(b, &ax);
+            ax.ctl.active = t->d_mask;
+            r = ngb_launch_assemble(&ax);
+        }
+        for (w = 0; w < NGB_LU_SETS && r == NGB_OK; w++) {
+            NgbLuCtx lx;
+            if (!used[w]) continue;
+            ngb_fill_luctx(b, &lx, 1, 1, w);
+            lx.ctl.active = t->d_mask;
+            lx.V = NULL;
+            r = ngb_launch_lu(&lx);
+        }
+        if (r == NGB_OK && b->lte_deferred && b->c->b4_n) {
+            B4Ctx x;
+            ngb_fill_b4ctx(b, &x);
+            x.ctl.active = t->d_mask;
+            r = ngb_launch_bsim4_lte(&x);
+        }
+        if (r == NGB_OK) {
+            NgbTranCtx cx = t->x;
+            cx.only = t->d_mask;
+            r = ngb_launch_tran_control(&cx);
+        }
+        if (r == NGB_OK) r = ngb_dev_sync();
+    }
+    free(susp); free(mask);
+    return r;
+}
 
 /* one Newton step for the whole batch.  The launch sequence is the same every step, so it is captured
  * once into a CUDA graph and replayed (six to eight launches become one); steps sampled by the
@@ -248,6 +327,10 @@ int ngbTranRun(ngb_batch *b, int max_points, const int *save_eq, int nsave)
         for (i = 0; i < check_every; i++, tick++)
             if ((r = enqueue_tick(b, 1))) return r;
         ngb_dev_d2h(done, b->tran->x.ndone, sizeof(int) * 4);
+        if (done[3] > 0) {                                   /* zero pivots: re-pivot those samples (niiter.c:162-195) */
+            if ((r = repivot_suspended(b))) return r;
+            ngb_dev_d2h(done, b->tran->x.ndone, sizeof(int) * 4);
+        }
         b->tran->stage = (done[2] >= S) ? 2 : ((done[1] >= S) ? 1 : 0);
         ngb_dev_d2h(e, b->errflag, sizeof e);
         if (e[0]) { ngb_set_error("device load reported error %d", e[0]); return e[0]; }

@@ -43,7 +43,11 @@ typedef struct NgbTranCtx {
     double *out_time;          /* [S][max_points] */
     double *out_val;           /* [S][max_points][nsave] */
     int *evstage;              /* [S] see ngb_ev_advance */
-    int *ndone;                /* [0] samples in DONE or FAIL, [1] past the operating point, [2] past the last pivoting event */
+    int *ndone;                /* [0] samples in DONE or FAIL, [1] past the operating point, [2] past the last pivoting event,
+                                * [3] samples waiting for the host's pivoting factor (susp == 1) */
+    int *susp;                 /* [S] 0; 1: the refactor met a zero pivot, the sample waits (inactive) for the host to factor its matrix
+                                * again with pivoting, niiter.c:162-195; 2: that factor found the matrix singular -- NIiter returns E_SINGULAR */
+    const int *only;           /* not NULL: this launch handles only the samples with only[s] != 0 (the ones the host has just re-pivoted) */
     /* breakpoint-generating sources (VSRCaccept / ISRCaccept): tables of the load kernels plus the
      * per-sample VSRCbreak_time / ISRCbreak_time, [ninst][S], -1 at setup (vsrcset.c:34) */
     NgbSrcCtx isrc, vsrc;
@@ -358,12 +362,29 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
     const int S = c->S;
     int phase = c->phase[s];
     if (phase == NGB_PH_IDLE || phase == NGB_PH_DONE || phase == NGB_PH_FAIL) return;
+    if (c->only ? !c->only[s] : (c->susp && c->susp[s] == 1)) return;
     /* state copies requested for the load that just ran are done */
     const int sop_done = c->ctl.stateop[s];
     c->ctl.stateop[s] = 0;
     (void)sop_done;
 
-    if (c->ctl.err[s]) { ngb_finish(c, s, NGB_PH_FAIL, c->ctl.err[s]); return; }
+    int forced = -1;                         /* NIiter's return value when SMPluFac / SMPreorder failed */
+    if (c->ctl.err[s]) {
+        if (c->ctl.err[s] != NGB_E_SINGULAR || !c->susp) { ngb_finish(c, s, NGB_PH_FAIL, c->ctl.err[s]); return; }
+        if (c->susp[s] == 0 && !c->only) {
+            /* zero pivot in the refactor: the reference factors the same matrix again with pivoting and goes on with the
+             * iteration.  The sample stands still until the host has done that (ngb_tran.c: repivot_suspended) */
+            c->ctl.err[s] = 0; c->susp[s] = 1; c->ctl.active[s] = 0;
+#ifdef __CUDA_ARCH__
+            atomicAdd(c->ndone + 3, 1);
+#else
+            c->ndone[3] += 1;
+#endif
+            return;
+        }
+        /* the pivoting factor failed as well: "seems to be singular - pass the bad news up" (niiter.c:176-190) */
+        c->ctl.err[s] = 0; c->susp[s] = 0; forced = NGB_E_SINGULAR;
+    }
 
     if (phase == NGB_PH_OPUIC) {
         /* CKTop returned OK after one CKTload; DCtran sets up the transient (dctran.c:271-330) */
@@ -389,8 +410,10 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
     const int maxiter = (phase == NGB_PH_DCOP) ? ((c->gm_stage && c->gm_stage[s] == 1) ? 100 : NGB_MAX(c->max_iter_dc, 100))
                                                : NGB_MAX(c->max_iter_tran, 100);
     int niret = -1;                          /* -1: keep iterating, 0: converged, >0: error */
-    c->iterno[s] = iterno;
-    if (iterno > maxiter) {
+    if (forced >= 0) {
+        iterno -= 1;                          /* the failed iteration is not counted (STATnumIter += iterno before iterno++) */
+        niret = forced;
+    } else if ((c->iterno[s] = iterno) > maxiter) {
         niret = NGB_E_ITERLIM;
     } else {
         if ((noncon == 0) && (iterno != 1)) noncon = c->nodeconv[s] ? 1 : 0;   /* NIconvTest */
