@@ -156,7 +156,7 @@ ngb_circuit *ngbCircuitCreate(int neq, const int *node_type)
 {
     ngb_circuit *c = (ngb_circuit *)xcalloc(1, sizeof *c);
     int i;
-    c->neq = neq;
+    c->neq = neq; c->pivot_mode = -1;
     c->node_type = (int *)xcalloc((size_t)neq + 1, sizeof(int));
     for (i = 0; i <= neq; i++) c->node_type[i] = node_type ? node_type[i] : 3;
     /* defaults of cktntask.c:95-146 */
@@ -1689,44 +1689,61 @@ static void batch_free_lu(ngb_batch *b)
         }
 }
 
-/* The reference's answer to a zero pivot in a refactor (niiter.c:162-195): factor the SAME matrix again with pivoting.
- * Sample s's matrix is fetched, the own pivoting factor (ngb_pivot.c) runs on the circuit's symbolic analysis, and the
- * result is matched against the pattern sets already there or becomes a new one (slots NGB_LU_EVENTS .. NGB_LU_SETS-1),
- * uploaded for this batch.  Returns 0 with *set_out, E_SINGULAR when the matrix really is singular, E_UNSUPP when
- * there is no symbolic analysis to factor on or no free slot. */
-int ngb_batch_repivot(ngb_batch *b, int s, int *set_out)
+/* The reference's answer to a zero pivot in a refactor (niiter.c:162-195), and what it does at every pivoting event of a
+ * run: factor the sample's OWN matrix with pivoting.  ngb_repivot_compute runs the pivoting factor (ngb_pivot.c) on the
+ * circuit's symbolic analysis; ngb_repivot_commit matches the result against the pattern sets already there or makes
+ * it a new one, uploaded for this batch.  commit returns 0 with *set_out, E_SINGULAR when the matrix really is singular,
+ * E_UNSUPP when there is no symbolic analysis to factor on or no free slot. */
+void ngb_repivot_compute(const ngb_circuit *c, const double *Ax, NgbRepivot *r)
+{
+    const int n = c->n;
+    memset(r, 0, sizeof *r);
+    r->sing = -1;
+    if (!c->klu_P) { r->rc = NGB_E_UNSUPP; return; }
+    r->Pnum = (int *)malloc(sizeof(int) * (size_t)n); r->Lp = (int *)malloc(sizeof(int) * ((size_t)n + 1));
+    r->Up = (int *)malloc(sizeof(int) * ((size_t)n + 1)); r->Offp = (int *)malloc(sizeof(int) * ((size_t)n + 1));
+    if (!r->Pnum || !r->Lp || !r->Up || !r->Offp) { r->rc = NGB_E_PANIC; return; }
+    r->rc = ngb_pivot_factor(n, c->Ap, c->Ai, Ax, c->klu_nblocks, c->klu_P, c->klu_Q, c->klu_R, c->pivtol > 0 ? c->pivtol : 0.001,
+                             r->Pnum, r->Lp, &r->Li, r->Up, &r->Ui, r->Offp, &r->Offi, &r->sing);
+}
+void ngb_repivot_free(NgbRepivot *r)
+{
+    free(r->Pnum); free(r->Lp); free(r->Up); free(r->Offp); free(r->Li); free(r->Ui); free(r->Offi);
+    memset(r, 0, sizeof *r);
+}
+int ngb_repivot_commit(ngb_batch *b, NgbRepivot *r, int *set_out)
 {
     ngb_circuit *c = b->c;
-    const int n = c->n;
-    int rc, w, sing = -1, keep_target = c->lu_target;
-    double *Ax;
-    int *Pnum, *Lp, *Up, *Offp, *Li = NULL, *Ui = NULL, *Offi = NULL, *P, *Q, *R;
+    const int n = c->n, keep_target = c->lu_target;
+    int w, rc;
     unsigned long long sig;
-    if (!c->klu_P) { ngb_set_error("zero pivot in sample %d and no symbolic analysis to re-pivot on (ngbCircuitSetSymbolic)", s); return NGB_E_UNSUPP; }
-    Ax = (double *)xcalloc((size_t)c->nnz, sizeof(double));
-    Pnum = (int *)xcalloc((size_t)n, sizeof(int)); Lp = (int *)xcalloc((size_t)n + 1, sizeof(int));
-    Up = (int *)xcalloc((size_t)n + 1, sizeof(int)); Offp = (int *)xcalloc((size_t)n + 1, sizeof(int));
-    P = (int *)xdup(c->klu_P, sizeof(int) * (size_t)n); Q = (int *)xdup(c->klu_Q, sizeof(int) * (size_t)n);
-    R = (int *)xdup(c->klu_R, sizeof(int) * ((size_t)c->klu_nblocks + 1));
-    ngb_dev_d2h(Ax, b->Ax + (size_t)s * c->nnz, sizeof(double) * (size_t)c->nnz);
-    rc = ngb_pivot_factor(n, c->Ap, c->Ai, Ax, c->klu_nblocks, P, Q, R, c->pivtol > 0 ? c->pivtol : 0.001,
-                          Pnum, Lp, &Li, Up, &Ui, Offp, &Offi, &sing);
-    if (rc) { if (rc == NGB_E_SINGULAR) ngb_set_error("sample %d: matrix is singular (column %d)", s, sing); goto done; }
-    sig = lu_signature(n, Pnum, Lp, Li, Up, Ui);
+    if (r->rc) return r->rc;
+    sig = lu_signature(n, r->Pnum, r->Lp, r->Li, r->Up, r->Ui);
     for (w = 0; w < NGB_LU_SETS; w++) if (c->lu[w].valid && c->lu[w].sig == sig) break;
     if (w == NGB_LU_SETS) {
+        int *Q, *R;
         for (w = NGB_LU_EVENTS; w < NGB_LU_SETS; w++) if (!c->lu[w].valid) break;
-        if (w == NGB_LU_SETS) { ngb_set_error("sample %d needs a %dth pivot order; %d pattern sets per circuit", s, NGB_LU_SETS + 1, NGB_LU_SETS); rc = NGB_E_UNSUPP; goto done; }
+        if (w == NGB_LU_SETS) { ngb_set_error("a sample needs one pivot order more than the %d pattern sets of a circuit", NGB_LU_SETS); return NGB_E_UNSUPP; }
+        Q = (int *)xdup(c->klu_Q, sizeof(int) * (size_t)n); R = (int *)xdup(c->klu_R, sizeof(int) * ((size_t)c->klu_nblocks + 1));
         c->lu_target = w;
-        rc = ngbCircuitSetLuPattern(c, n, c->klu_nblocks, Q, R, Pnum, Lp, Li, Up, Ui, Offp, Offi);
+        rc = ngbCircuitSetLuPattern(c, n, c->klu_nblocks, Q, R, r->Pnum, r->Lp, r->Li, r->Up, r->Ui, r->Offp, r->Offi);
         c->lu_target = keep_target;
-        if (rc) goto done;
+        free(Q); free(R);
+        if (rc) return rc;
     }
-    if (!b->dlu[w].valid) { sched_to_dev(b, c, w); packed_to_dev(b, c, w); b->dlu[w].valid = 1; if (b->failed) { rc = NGB_E_PANIC; goto done; } }
+    if (!b->dlu[w].valid) { sched_to_dev(b, c, w); packed_to_dev(b, c, w); b->dlu[w].valid = 1; if (b->failed) return NGB_E_PANIC; }
     *set_out = w;
-done:
-    free(Ax); free(Pnum); free(Lp); free(Up); free(Offp); free(Li); free(Ui); free(Offi); free(P); free(Q); free(R);
-    return rc;
+    return NGB_OK;
+}
+
+/* 0: every sample refactors on the batch's pattern sets (one per pivoting event of the recorded run); 1: every sample's
+ * own matrix is factored with pivoting at the reference's pivoting events (niiter.c:107-111, 335, 343) -- needs the
+ * symbolic analysis; -1 (default): 1 when there is one */
+int ngbCircuitSetPivotMode(ngb_circuit *c, int mode)
+{
+    if (mode == 1 && !c->klu_P) { ngb_set_error("per-sample pivoting needs a symbolic analysis (ngbCircuitSetSymbolic / ngbCircuitAnalyze)"); return NGB_E_PANIC; }
+    c->pivot_mode = mode;
+    return NGB_OK;
 }
 
 /* the circuit's LU pattern sets changed after the batch was created (a later SMPreorder in the

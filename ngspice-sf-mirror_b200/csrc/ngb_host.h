@@ -42,6 +42,7 @@ struct ngb_circuit {
     int *klu_P;                    /* symbolic row permutation (ngbCircuitSetSymbolic / ngbCircuitAnalyze), NULL when only finished factors were imported */
     int *pat_Lp, *pat_Li, *pat_Up, *pat_Ui, *pat_Offp, *pat_Offi;    /* the factor last passed to ngbCircuitSetLuPattern */
     double pivtol;                 /* threshold of the own pivoting factor (CKTpivotRelTol) */
+    int pivot_mode;                /* ngbCircuitSetPivotMode: -1 default (1 when a symbolic analysis is there), 0 batch orders, 1 per sample */
     int lnz, unz, nzoff, npairs, nsolvepairs;
     NgbLuSched sch;                /* host arrays (set being built) */
     NgbLuPacked pk;                /* host arrays, level-contiguous 16-bit form */
@@ -90,7 +91,12 @@ void ngb_fill_srcctx(struct ngb_batch *b, NgbSrcCtx *x, int is_current);
 void ngb_fill_asmctx(struct ngb_batch *b, NgbAsmCtx *x);
 void ngb_fill_luctx(struct ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve, int which);
 int ngb_enqueue_load(struct ngb_batch *b);
-int ngb_batch_repivot(struct ngb_batch *b, int s, int *set_out);   /* own pivoting factor of sample s's matrix -> pattern set */
+/* own pivoting factor of one sample's matrix (ngb_repivot_compute: no shared state, may run on many host threads) and its
+ * placement among the circuit's pattern sets (ngb_repivot_commit: serial) */
+typedef struct NgbRepivot { int rc, sing; int *Pnum, *Lp, *Up, *Offp, *Li, *Ui, *Offi; } NgbRepivot;
+void ngb_repivot_compute(const struct ngb_circuit *c, const double *Ax, NgbRepivot *r);
+int ngb_repivot_commit(struct ngb_batch *b, NgbRepivot *r, int *set_out);
+void ngb_repivot_free(NgbRepivot *r);
 void ngb_tran_free(struct ngb_batch *b);
 int ngb_pivot_factor(int n, const int *Ap, const int *Ai, const double *Ax, int nblocks, const int *P, const int *Q,
                      const int *R, double tol, int *Pnum, int *Lp, int **Li_out, int *Up, int **Ui_out,

@@ -107,6 +107,9 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     }
     ngb_lu_events(c, x->lu_event);
     x->nluset = (x->lu_event[0] != x->lu_event[1] || x->lu_event[1] != x->lu_event[2] || x->lu_event[2] != x->lu_event[3]) ? 2 : 1;
+    x->pivot_events = (c->pivot_mode == 1 || (c->pivot_mode < 0 && c->klu_P && !getenv("NGB_BATCH_PIVOT"))) ? 1 : 0;
+    if (x->pivot_events) x->nluset = 2;              /* every sample selects its own pattern set */
+    memset(t->keep_set, 0, sizeof t->keep_set);
     x->maxorder = c->opt.maxorder; x->uic = c->opt.uic; x->max_iter_tran = c->opt.itl4; x->max_iter_dc = c->opt.itl1;
     if (x->minbreak == 0) x->minbreak = x->tmax * 5e-5;            /* dctran.c:163-164 */
 
@@ -129,7 +132,7 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
         /* NIiter under MODETRANOP|MODEUIC swaps rhs/rhsOld before its single CKTload */
         for (s = 0; s < S; s++) iv[s] = c->opt.uic ? 1 : 0;
         ngb_dev_h2d(b->ctl.xsel, iv, sizeof(int) * S);
-        for (s = 0; s < S; s++) iv[s] = x->lu_event[c->opt.uic ? 2 : 0];
+        for (s = 0; s < S; s++) iv[s] = x->pivot_events ? -1 : x->lu_event[c->opt.uic ? 2 : 0];   /* the first factor of a run pivots */
         ngb_dev_h2d(b->ctl.lusel, iv, sizeof(int) * S);
         memset(iv, 0, sizeof(int) * S);
         ngb_dev_h2d(b->ctl.head, iv, sizeof(int) * S);
@@ -192,7 +195,7 @@ static int enqueue_tick_direct(ngb_batch *b, int with_lu)
             NgbLuCtx lx;
             int used = 0;
             if (!b->dlu[w].valid) continue;
-            for (e = first; e < NGB_LU_EVENTS; e++) if (ev[e] == w) used = 1;
+            if (!b->tran->x.pivot_events) for (e = first; e < NGB_LU_EVENTS; e++) if (ev[e] == w) used = 1;
             if (b->tran->keep_set[w]) used = 1;
             if (!used) continue;                                            /* no sample can be on this set any more */
             ngb_fill_luctx(b, &lx, 1, 1, w);
@@ -220,32 +223,59 @@ static int enqueue_tick_direct(ngb_batch *b, int with_lu)
 static int repivot_suspended(ngb_batch *b)
 {
     struct ngb_tran *t = b->tran;
-    const int S = b->S;
-    int *susp = (int *)calloc((size_t)S, sizeof(int)), *mask = (int *)calloc((size_t)S, sizeof(int));
-    int s, r = NGB_OK, w, used[NGB_LU_SETS], g, zero4[1] = { 0 };
-    const double big = 1e300;
-    if (!susp || !mask) { free(susp); free(mask); return NGB_E_PANIC; }
+    const ngb_circuit *c = b->c;
+    const int S = b->S, nnz = c->nnz;
+    int *susp = (int *)calloc((size_t)S, sizeof(int)), *mask = (int *)calloc((size_t)S, sizeof(int)), *list = (int *)calloc((size_t)S, sizeof(int));
+    int s, k, m = 0, r = NGB_OK, w, used[NGB_LU_SETS], g, zero4[1] = { 0 };
+    double *Ax = NULL;
+    NgbRepivot *res = NULL;
+    if (!susp || !mask || !list) { r = NGB_E_PANIC; goto out; }
     memset(used, 0, sizeof used);
     ngb_dev_sync();
     ngb_dev_d2h(susp, t->x.susp, sizeof(int) * (size_t)S);
-    for (s = 0; s < S; s++) {
-        const int one = 1, zero = 0;
-        int state = 0, err = 0;
-        if (susp[s] != 1) continue;
-        mask[s] = 1;
-        r = ngb_batch_repivot(b, s, &w);
-        if (r == NGB_OK) {
-            ngb_dev_h2d(b->ctl.lusel + s, &w, sizeof(int));
-            used[w] = 1; t->keep_set[w] = 1; t->repivots++;
-        } else if (r == NGB_E_SINGULAR || r == NGB_E_UNSUPP) {
-            state = 2; err = NGB_E_SINGULAR; r = NGB_OK;            /* the controller takes it from here */
-        } else break;
-        ngb_dev_h2d(t->x.susp + s, &state, sizeof(int));
-        ngb_dev_h2d(b->ctl.err + s, &err, sizeof(int));
-        ngb_dev_h2d(b->ctl.active + s, &one, sizeof(int));
-        ngb_dev_h2d(b->nodeconv + s, &zero, sizeof(int));
-        ngb_dev_h2d(b->ctl.lte + s, &big, sizeof(double));
-        ngb_dev_h2d(b->ctl.lte2 + s, &big, sizeof(double));
+    for (s = 0; s < S; s++) if (susp[s] == 1) { list[m++] = s; mask[s] = 1; }
+    if (!m) goto out;
+    /* the matrices: one transfer when most of the batch waits (a pivoting event), sample by sample otherwise */
+    Ax = (double *)malloc(sizeof(double) * (size_t)nnz * (size_t)(m > S / 8 ? S : m));
+    res = (NgbRepivot *)calloc((size_t)m, sizeof(NgbRepivot));
+    if (!Ax || !res) { r = NGB_E_PANIC; goto out; }
+    if (m > S / 8) ngb_dev_d2h(Ax, b->Ax, sizeof(double) * (size_t)nnz * S);
+    else for (k = 0; k < m; k++) ngb_dev_d2h(Ax + (size_t)k * nnz, b->Ax + (size_t)list[k] * nnz, sizeof(double) * (size_t)nnz);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 16)
+#endif
+    for (k = 0; k < m; k++)
+        ngb_repivot_compute(c, Ax + (size_t)(m > S / 8 ? list[k] : k) * nnz, &res[k]);
+    {
+        int *lus = (int *)malloc(sizeof(int) * (size_t)S), *st = (int *)calloc((size_t)S, sizeof(int));
+        int *act = (int *)malloc(sizeof(int) * (size_t)S), *er = (int *)malloc(sizeof(int) * (size_t)S), *nc = (int *)malloc(sizeof(int) * (size_t)S);
+        double *l1 = (double *)malloc(sizeof(double) * (size_t)S), *l2 = (double *)malloc(sizeof(double) * (size_t)S);
+        if (!lus || !st || !act || !er || !nc || !l1 || !l2) r = NGB_E_PANIC;
+        else {
+            ngb_dev_d2h(lus, b->ctl.lusel, sizeof(int) * (size_t)S); ngb_dev_d2h(act, b->ctl.active, sizeof(int) * (size_t)S);
+            ngb_dev_d2h(er, b->ctl.err, sizeof(int) * (size_t)S); ngb_dev_d2h(nc, b->nodeconv, sizeof(int) * (size_t)S);
+            ngb_dev_d2h(l1, b->ctl.lte, sizeof(double) * (size_t)S); ngb_dev_d2h(l2, b->ctl.lte2, sizeof(double) * (size_t)S);
+            memcpy(st, susp, sizeof(int) * (size_t)S);
+            for (k = 0; k < m && r == NGB_OK; k++) {
+                s = list[k];
+                r = ngb_repivot_commit(b, &res[k], &w);
+                if (r == NGB_OK) { lus[s] = w; used[w] = 1; t->keep_set[w] = 1; t->repivots++; st[s] = 0; er[s] = 0; }
+                else if (r == NGB_E_UNSUPP && t->x.pivot_events && c->lu[t->x.lu_event[3]].valid && res[k].rc == NGB_OK) {
+                    /* no free pattern set: this sample keeps the batch's recorded order (round-1 behaviour) */
+                    w = t->x.lu_event[3]; lus[s] = w; used[w] = 1; t->keep_set[w] = 1; st[s] = 0; er[s] = 0; r = NGB_OK;
+                    if (!b->dlu[w].valid) r = NGB_E_PANIC;
+                }
+                else if (r == NGB_E_SINGULAR || r == NGB_E_UNSUPP) { st[s] = 2; er[s] = NGB_E_SINGULAR; if (lus[s] < 0) lus[s] = t->x.lu_event[3]; r = NGB_OK; }   /* the controller takes it from here */
+                act[s] = 1; nc[s] = 0; l1[s] = 1e300; l2[s] = 1e300;
+            }
+            if (r == NGB_OK) {
+                ngb_dev_h2d(b->ctl.lusel, lus, sizeof(int) * (size_t)S); ngb_dev_h2d(b->ctl.active, act, sizeof(int) * (size_t)S);
+                ngb_dev_h2d(b->ctl.err, er, sizeof(int) * (size_t)S); ngb_dev_h2d(b->nodeconv, nc, sizeof(int) * (size_t)S);
+                ngb_dev_h2d(b->ctl.lte, l1, sizeof(double) * (size_t)S); ngb_dev_h2d(b->ctl.lte2, l2, sizeof(double) * (size_t)S);
+                ngb_dev_h2d(t->x.susp, st, sizeof(int) * (size_t)S);
+            }
+        }
+        free(lus); free(st); free(act); free(er); free(nc); free(l1); free(l2);
     }
     if (r == NGB_OK) {
         ngb_dev_h2d(t->d_mask, mask, sizeof(int) * (size_t)S);
@@ -280,7 +310,9 @@ static int repivot_suspended(ngb_batch *b)
         }
         if (r == NGB_OK) r = ngb_dev_sync();
     }
-    free(susp); free(mask);
+out:
+    if (res) for (k = 0; k < m; k++) ngb_repivot_free(&res[k]);
+    free(res); free(Ax); free(susp); free(mask); free(list);
     return r;
 }
 
@@ -324,7 +356,9 @@ int ngbTranRun(ngb_batch *b, int max_points, const int *save_eq, int nsave)
     }
     while (tick < max_ticks) {
         int i;
-        for (i = 0; i < check_every; i++, tick++)
+        /* the pivoting events of a run sit in its first iterations: look after every step there */
+        const int burst = (b->tran->x.pivot_events && tick < 6) ? 1 : check_every;
+        for (i = 0; i < burst; i++, tick++)
             if ((r = enqueue_tick(b, 1))) return r;
         ngb_dev_d2h(done, b->tran->x.ndone, sizeof(int) * 4);
         if (done[3] > 0) {                                   /* zero pivots: re-pivot those samples (niiter.c:162-195) */

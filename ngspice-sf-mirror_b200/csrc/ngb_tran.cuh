@@ -48,6 +48,9 @@ typedef struct NgbTranCtx {
     int *susp;                 /* [S] 0; 1: the refactor met a zero pivot, the sample waits (inactive) for the host to factor its matrix
                                 * again with pivoting, niiter.c:162-195; 2: that factor found the matrix singular -- NIiter returns E_SINGULAR */
     const int *only;           /* not NULL: this launch handles only the samples with only[s] != 0 (the ones the host has just re-pivoted) */
+    int pivot_events;          /* 1: at every pivoting event of NIiter the sample's own matrix is factored with pivoting by the host
+                                * (ctl.lusel = -1: no refactor launch takes the sample, the controller parks it like a zero pivot);
+                                * 0: the sample moves to the batch's recorded pattern set of that event */
     /* breakpoint-generating sources (VSRCaccept / ISRCaccept): tables of the load kernels plus the
      * per-sample VSRCbreak_time / ISRCbreak_time, [ninst][S], -1 at setup (vsrcset.c:34) */
     NgbSrcCtx isrc, vsrc;
@@ -353,7 +356,7 @@ NGB_HD void ngb_gm_next_niiter(const NgbTranCtx *c, int s, int mode)
 {
     c->ctl.mode[s] = mode;
     c->iterno[s] = 0;
-    if ((mode & NGB_MODEINITJCT) && c->nluset > 1) c->ctl.lusel[s] = c->lu_event[0];
+    if ((mode & NGB_MODEINITJCT) && c->nluset > 1) c->ctl.lusel[s] = c->pivot_events ? -1 : c->lu_event[0];
 }
 
 /* One controller step for sample s, after the load (+ LU + solve) of this tick. */
@@ -369,6 +372,18 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
     (void)sop_done;
 
     int forced = -1;                         /* NIiter's return value when SMPluFac / SMPreorder failed */
+    if (c->pivot_events && !c->only && !c->ctl.err[s] && phase != NGB_PH_OPUIC && c->ctl.lusel[s] == -1) {
+        /* SMPreorder is due in this iteration (NISHOULDREORDER): the load and the assembly of this step are done, no
+         * refactor launch took the sample; it waits for the host's pivoting factor of its matrix */
+        c->susp[s] = 1; c->ctl.active[s] = 0;
+#ifdef __CUDA_ARCH__
+        atomicAdd(c->ndone + 3, 1);
+#else
+        c->ndone[3] += 1;
+#endif
+        c->ctl.stateop[s] = sop_done;        /* nothing of this step is consumed yet */
+        return;
+    }
     if (c->ctl.err[s]) {
         if (c->ctl.err[s] != NGB_E_SINGULAR || !c->susp) { ngb_finish(c, s, NGB_PH_FAIL, c->ctl.err[s]); return; }
         if (c->susp[s] == 0 && !c->only) {
@@ -422,12 +437,12 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
             if (noncon == 0) niret = NGB_OK;
         } else if (mode & NGB_MODEINITJCT) {
             mode = (mode & ~NGB_INITF) | NGB_MODEINITFIX;
-            if (c->nluset > 1) c->ctl.lusel[s] = c->lu_event[1];           /* NISHOULDREORDER, niiter.c:335 */
+            if (c->nluset > 1) c->ctl.lusel[s] = c->pivot_events ? -1 : c->lu_event[1];           /* NISHOULDREORDER, niiter.c:335 */
         } else if (mode & NGB_MODEINITFIX) {
             if (noncon == 0) mode = (mode & ~NGB_INITF) | NGB_MODEINITFLOAT;
         } else if (mode & (NGB_MODEINITTRAN | NGB_MODEINITPRED | NGB_MODEINITSMSIG)) {
             if ((mode & NGB_MODEINITTRAN) && iterno <= 1) {
-                if (c->nluset > 1) c->ctl.lusel[s] = c->lu_event[3];       /* NISHOULDREORDER, niiter.c:343-344 */
+                if (c->nluset > 1) c->ctl.lusel[s] = c->pivot_events ? -1 : c->lu_event[3];       /* NISHOULDREORDER, niiter.c:343-344 */
                 ngb_ev_advance(c, s, 2);
             }
             mode = (mode & ~NGB_INITF) | NGB_MODEINITFLOAT;
@@ -593,7 +608,7 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
         c->ctl.ag0[s] = 0; c->ctl.ag1[s] = 0;
         c->ctl.stateop[s] = NGB_OP_COPY01;
         /* NIiter re-pivots in the first iteration under MODEINITTRAN (niiter.c:107-111) */
-        if (c->nluset > 1) c->ctl.lusel[s] = c->lu_event[2];
+        if (c->nluset > 1) c->ctl.lusel[s] = c->pivot_events ? -1 : c->lu_event[2];
         ngb_ev_advance(c, s, 1);
         ngb_next_time(c, s);
         return;

@@ -102,7 +102,7 @@ typedef struct NgbSrcCtx {
 /* pivoting events of one run (niiter.c:107-111, 333-349): 0 the MODEINITJCT iteration, 1 the iteration after it (rest of the
  * operating point), 2 the first iteration under MODEINITTRAN, 3 the iteration after it (rest of the transient) */
 #define NGB_LU_EVENTS 4
-#define NGB_LU_SETS 8      /* 0..3: the pivoting events of a run; the rest: per-sample re-pivots after a zero pivot (ngb_tran.c) */
+#define NGB_LU_SETS 16     /* 0..3: the pivoting events of a run; the rest: per-sample re-pivots after a zero pivot (ngb_tran.c) */
 #define NGB_ASM_LONG 4096
 typedef struct NgbAsmCtx {
     int S, nnz, neq1;

@@ -67,7 +67,7 @@ def test_tran_hostsim_vbic(hostsim_lib):
 MIX_POINTS = [("2.0", "1k"), ("1.6", "200"), ("1.6", "5k"), ("2.4", "200"), ("2.4", "5k"),     # make_golden.py
               ("1.69098", "1348.2"),                          # the reference needs dynamic gmin stepping here (cktop.c:162)
               ("1.69412", "2364.7"), ("1.69412", "2383.5")]   # marginal: bound to the centre's pivot orders the batch needs it too
-MIX_SAME_ROUTE = 6          # the first six points take the reference's route: identical iteration counts
+MIX_SAME_ROUTE = 8          # with every sample pivoting on its own matrix (csrc/ngb_pivot.c) all eight points take the reference's route: identical iteration counts (bound to the centre's pivot orders, round 1, the last two did not)
 
 
 def _mix_sweep(lib, reps=1):
@@ -99,17 +99,17 @@ def test_tran_hostsim_mix_sweep(hostsim_lib):
     _mix_sweep(hostsim_lib)
 
 
-def _mix_source_stepping(lib, reps=1):
+def _mix_source_stepping(lib, reps=1, exact_count=True):
     """CKTop with gmin stepping switched off (`.option gminsteps=0`) in a batch: the sweep point whose plain Newton
     iteration fails goes into gillespie_src (cktop.c:481-660) per sample inside the device controller while its
     neighbours, which converge directly, run their transients undisturbed.  In the reference source stepping FAILS for
     this point too (tests/golden/make_golden.py, "mixsrc"; it is OPtran that rescues it there, and OPtran is not on this
-    path).  Inside the batch the zero-source matrix has an exact zero pivot under the centre's pivot orders; like the
-    reference (niiter.c:162-195) the library then factors that sample's matrix again with its own pivoting factor
-    (csrc/ngb_pivot.c) and goes on.  On the re-pivoted order source stepping SUCCEEDS for this sample (the route depends on
-    the pivot orders, and the reference pivots at every MODEINITJCT iteration of the ladder), so the sample ends with the
-    reference's number of accepted points and a waveform within Newton tolerance of the reference's (which started from
-    OPtran's operating point); without a symbolic analysis to re-pivot on it would end with E_SINGULAR."""
+    path).  Every sample's own matrix is factored with pivoting at the reference's pivoting events (csrc/ngb_pivot.c, the
+    default whenever klu_analyze's symbolic analysis travels with the pattern), so inside the batch the hard point takes the
+    reference's route step for step: source stepping fails with E_ITERLIM after exactly the reference's 759 CKTop
+    iterations (`exact_count`; the GPU's VBIC Jacobian differs in rounding, there the count may move).  Bound to the batch's
+    recorded pivot orders instead (round 1) the zero-source matrix had an exact zero pivot and the sample ended with
+    E_SINGULAR."""
     flat = ngt.read(f"{GOLDEN}/mix.flat.ngt")
     trace = ngt.read(f"{GOLDEN}/mix.trace.ngt.gz")
     wave = ngt.read(f"{GOLDEN}/mix.wave.ngt")
@@ -125,10 +125,9 @@ def _mix_source_stepping(lib, reps=1):
             _compare(res, t, v, ngt.read(f"{GOLDEN}/{('mix', '', 'mix1')[s % 3]}.wave.ngt"), s, exact=False, same_route=True)
         else:
             ref = ngt.read(f"{GOLDEN}/mixsrc.wave.ngt")
-            n = int(res.npoints[s])
-            assert int(res.err[s]) == 0 and int(res.accepted[s]) == int(ref["stats"][0]) and n == len(ref["time"]), (s, int(res.err[s]))
-            rng = np.max(np.abs(ref["values"]), axis=0)
-            assert (np.max(np.abs(v[s, :n, :] - ref["values"]), axis=0) / rng <= 5e-3).all()
+            assert int(res.accepted[s]) == 0 and int(res.err[s]) == 103, (s, int(res.err[s]))
+            if exact_count:
+                assert int(res.numiter[s]) == int(ref["stats"][5]) == 759, int(res.numiter[s])
     return res
 
 
@@ -239,7 +238,7 @@ def test_op_fallback_options_refused(hostsim_lib):
 
 @pytest.mark.gpu
 def test_tran_gpu_mix_source_stepping(cuda_lib):
-    _mix_source_stepping(cuda_lib, reps=12)     # 36 samples: the stepping sample shares its warps with direct ones
+    _mix_source_stepping(cuda_lib, reps=12, exact_count=False)     # 36 samples: the stepping sample shares its warps with direct ones
 
 
 @pytest.mark.gpu
