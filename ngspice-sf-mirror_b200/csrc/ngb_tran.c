@@ -41,7 +41,7 @@ void ngb_tran_free(struct ngb_batch *b)
     ngb_dev_free(t->x.gm_startgmin); ngb_dev_free(t->x.gs_conv); ngb_dev_free(t->x.gs_raise); ngb_dev_free(t->x.gs_i);
     { int a; for (a = 0; a < t->x.gm_narr; a++) ngb_dev_free(t->x.gm_arr[a].old); }
     ngb_dev_free(t->d_save_eq); ngb_dev_free(t->x.isrc_break); ngb_dev_free(t->x.vsrc_break);
-    ngb_dev_free(t->x.susp); ngb_dev_free(t->d_mask);
+    ngb_dev_free(t->x.susp); ngb_dev_free(t->d_mask); ngb_dev_free(t->x.ipass);
     ngb_dev_graph_destroy(t->graph[0]); ngb_dev_graph_destroy(t->graph[1]); ngb_dev_graph_destroy(t->graph[2]);
     free(t);
     b->tran = NULL;
@@ -67,11 +67,15 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     x->accepted = (int *)dz(sizeof(int) * S); x->rejected = (int *)dz(sizeof(int) * S);
     x->numiter = (int *)dz(sizeof(int) * S); x->timepts = (int *)dz(sizeof(int) * S);
     x->save_delta = (double *)dz(sizeof(double) * S); x->old_delta = (double *)dz(sizeof(double) * S);
-    x->breaks = (double *)dz(sizeof(double) * NGB_MAXBRK * S);
+    x->maxbrk = c->vs_n + c->is_n + 4;                      /* one pending corner per source at most, both ends, one spare */
+    if (x->maxbrk < NGB_MAXBRK) x->maxbrk = NGB_MAXBRK;
+    x->breaks = (double *)dz(sizeof(double) * (size_t)x->maxbrk * S);
     x->out_time = (double *)dz(sizeof(double) * (size_t)S * max_points);
     x->out_val = (double *)dz(sizeof(double) * (size_t)S * max_points * (nsave ? nsave : 1));
     x->ndone = (int *)dz(sizeof(int) * 4); x->evstage = (int *)dz(sizeof(int) * S);
     x->susp = (int *)dz(sizeof(int) * S); t->d_mask = (int *)dz(sizeof(int) * S);
+    x->ipass = (int *)dz(sizeof(int) * S);
+    { int i2; x->had_nodeset = 0; for (i2 = 0; i2 < c->ov_n; i2++) if (c->ov_kind[i2] == 0) x->had_nodeset = 1; }
     ngb_fill_srcctx(b, &x->isrc, 1); ngb_fill_srcctx(b, &x->vsrc, 0);
     x->isrc_break = (double *)dz(sizeof(double) * (size_t)(x->isrc.ninst > 0 ? x->isrc.ninst : 1) * S);
     x->vsrc_break = (double *)dz(sizeof(double) * (size_t)(x->vsrc.ninst > 0 ? x->vsrc.ninst : 1) * S);
@@ -116,7 +120,7 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     /* initial per-sample state: DCtran entry (dctran.c:117-236) */
     {
         int *iv = (int *)calloc((size_t)S, sizeof(int));
-        double *dv = (double *)calloc((size_t)S * NGB_MAXBRK, sizeof(double));
+        double *dv = (double *)calloc((size_t)S * x->maxbrk, sizeof(double));
         const int mode0 = (c->opt.uic ? NGB_MODEUIC : 0) | NGB_MODETRANOP | NGB_MODEINITJCT;
         for (s = 0; s < S; s++) iv[s] = mode0;
         ngb_dev_h2d(b->ctl.mode, iv, sizeof(int) * S);
@@ -140,8 +144,8 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
         ngb_dev_h2d(b->ctl.err, iv, sizeof(int) * S);
         ngb_dev_h2d(b->ctl.stateop, iv, sizeof(int) * S);
         ngb_dev_h2d(b->nodeconv, iv, sizeof(int) * S);
-        for (i = 0; i < NGB_MAXBRK; i++) for (s = 0; s < S; s++) dv[(size_t)i * S + s] = (i == 0) ? 0.0 : c->opt.tstop;
-        ngb_dev_h2d(x->breaks, dv, sizeof(double) * NGB_MAXBRK * S);
+        for (i = 0; i < x->maxbrk; i++) for (s = 0; s < S; s++) dv[(size_t)i * S + s] = (i == 0) ? 0.0 : c->opt.tstop;
+        ngb_dev_h2d(x->breaks, dv, sizeof(double) * (size_t)x->maxbrk * S);
         memset(dv, 0, sizeof(double) * S);
         ngb_dev_h2d(b->ctl.time, dv, sizeof(double) * S);
         ngb_dev_h2d(b->ctl.delta, dv, sizeof(double) * S);

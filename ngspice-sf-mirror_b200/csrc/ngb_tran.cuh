@@ -25,7 +25,7 @@
 #define NGB_PH_TRAN   3      /* Newton iteration of a transient time point                     */
 #define NGB_PH_DONE   4
 #define NGB_PH_FAIL   5
-#define NGB_MAXBRK    16
+#define NGB_MAXBRK    16      /* smallest breakpoint table; the transient driver sizes it by the sources that set breakpoints */
 
 typedef struct NgbTranCtx {
     NgbCtl ctl;
@@ -36,7 +36,9 @@ typedef struct NgbTranCtx {
     /* per-sample controller state, [S] */
     int *phase, *iterno, *firsttime, *nbreak, *npts, *brkflag;
     int *accepted, *rejected, *numiter, *timepts;
-    double *save_delta, *old_delta, *breaks;   /* breaks [NGB_MAXBRK][S] */
+    double *save_delta, *old_delta, *breaks;   /* breaks [maxbrk][S] */
+    int maxbrk;                /* rows of the breakpoint table: every PULSE / PWL source keeps one pending breakpoint (CKTsetBreak grows
+                                * its table without limit, cktsetbk.c), + the two ends + one in flight */
     /* outputs */
     int max_points, nsave;
     const int *save_eq;        /* [nsave] */
@@ -48,6 +50,9 @@ typedef struct NgbTranCtx {
     int *susp;                 /* [S] 0; 1: the refactor met a zero pivot, the sample waits (inactive) for the host to factor its matrix
                                 * again with pivoting, niiter.c:162-195; 2: that factor found the matrix singular -- NIiter returns E_SINGULAR */
     const int *only;           /* not NULL: this launch handles only the samples with only[s] != 0 (the ones the host has just re-pivoted) */
+    int *ipass;                /* [S] NIiter's `ipass`: set by every MODEINITFIX iteration; with nodesets in the circuit the first
+                                * MODEINITFLOAT iteration of an operating point then counts as not converged (niiter.c:307-331) */
+    int had_nodeset;           /* CKThadNodeset (cktic.c:46): some node carries a .nodeset */
     int pivot_events;          /* 1: at every pivoting event of NIiter the sample's own matrix is factored with pivoting by the host
                                 * (ctl.lusel = -1: no refactor launch takes the sample, the controller parks it like a zero pivot);
                                 * 0: the sample moves to the batch's recorded pattern set of that event */
@@ -118,7 +123,7 @@ NGB_HD int ngb_set_break(const NgbTranCtx *c, int s, double time, double now)
         if (TBRK(i) > time) {
             if ((TBRK(i) - time) <= c->minbreak) { TBRK(i) = time; return NGB_OK; }
             if (i > 0 && time - TBRK(i - 1) <= c->minbreak) return NGB_OK;
-            if (nb >= NGB_MAXBRK) return NGB_E_PANIC;
+            if (nb >= c->maxbrk) return NGB_E_PANIC;
             for (int j = nb; j > i; j--) TBRK(j) = TBRK(j - 1);
             TBRK(i) = time;
             c->nbreak[s] = nb + 1;
@@ -126,7 +131,7 @@ NGB_HD int ngb_set_break(const NgbTranCtx *c, int s, double time, double now)
         }
     }
     if (time - TBRK(nb - 1) <= c->minbreak) return NGB_OK;
-    if (nb >= NGB_MAXBRK) return NGB_E_PANIC;
+    if (nb >= c->maxbrk) return NGB_E_PANIC;
     TBRK(nb) = time;
     c->nbreak[s] = nb + 1;
     return NGB_OK;
@@ -356,6 +361,7 @@ NGB_HD void ngb_gm_next_niiter(const NgbTranCtx *c, int s, int mode)
 {
     c->ctl.mode[s] = mode;
     c->iterno[s] = 0;
+    c->ipass[s] = 0;
     if ((mode & NGB_MODEINITJCT) && c->nluset > 1) c->ctl.lusel[s] = c->pivot_events ? -1 : c->lu_event[0];
 }
 
@@ -422,7 +428,10 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
     int mode = c->ctl.mode[s];
     int noncon = c->ctl.noncon[s];
     /* NIiter raises maxIter to 100 (niiter.c:37); the gmin steps run with CKTdcTrcvMaxIter (itl2, default 50) */
-    const int maxiter = (phase == NGB_PH_DCOP) ? ((c->gm_stage && c->gm_stage[s] == 1) ? 100 : NGB_MAX(c->max_iter_dc, 100))
+    /* the steps of the ladders (dynamic_gmin 1, new_gmin 3, gillespie_src 10-12) run with CKTdcTrcvMaxIter (itl2), the plain NIiter
+     * (0) and the closing NIiter of the gmin ladders (2, 4) with CKTdcMaxIter (itl1): cktop.c:34, 201, 259, 388, 447, 506-585 */
+    const int gst = (phase == NGB_PH_DCOP && c->gm_stage) ? c->gm_stage[s] : 0;
+    const int maxiter = (phase == NGB_PH_DCOP) ? ((gst == 1 || gst == 3 || gst >= 10) ? NGB_MAX(c->itl2, 100) : NGB_MAX(c->max_iter_dc, 100))
                                                : NGB_MAX(c->max_iter_tran, 100);
     int niret = -1;                          /* -1: keep iterating, 0: converged, >0: error */
     if (forced >= 0) {
@@ -434,12 +443,17 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
         if ((noncon == 0) && (iterno != 1)) noncon = c->nodeconv[s] ? 1 : 0;   /* NIconvTest */
         else noncon = 1;
         if (mode & NGB_MODEINITFLOAT) {
+            if ((mode & NGB_MODEDC) && c->had_nodeset) {
+                if (c->ipass[s]) noncon = c->ipass[s];
+                c->ipass[s] = 0;
+            }
             if (noncon == 0) niret = NGB_OK;
         } else if (mode & NGB_MODEINITJCT) {
             mode = (mode & ~NGB_INITF) | NGB_MODEINITFIX;
             if (c->nluset > 1) c->ctl.lusel[s] = c->pivot_events ? -1 : c->lu_event[1];           /* NISHOULDREORDER, niiter.c:335 */
         } else if (mode & NGB_MODEINITFIX) {
             if (noncon == 0) mode = (mode & ~NGB_INITF) | NGB_MODEINITFLOAT;
+            c->ipass[s] = 1;
         } else if (mode & (NGB_MODEINITTRAN | NGB_MODEINITPRED | NGB_MODEINITSMSIG)) {
             if ((mode & NGB_MODEINITTRAN) && iterno <= 1) {
                 if (c->nluset > 1) c->ctl.lusel[s] = c->pivot_events ? -1 : c->lu_event[3];       /* NISHOULDREORDER, niiter.c:343-344 */

@@ -423,6 +423,11 @@ if __name__ == "__main__":
             ["a8", "x", "y4", "cq", "e2", "vdd#branch", "v33#branch"])
     if "latch" in which:
         run("latch", latch_netlist(), "0-40,100,101,200", ["q", "qb", "a", "b", "vdd#branch", "vm#branch"])
+    if "latchns" in which:
+        # the same latch with its .nodeset ON the operating point: releasing the nodeset rows changes nothing, the first
+        # MODEINITFLOAT iteration passes the node test -- and NIiter still asks for one more (ipass, niiter.c:307-331)
+        run("latchns", latch_netlist().replace(".nodeset v(q)=2 v(qb)=0", ".nodeset v(q)=1.88128234 v(qb)=0.0409630224"),
+            "0-40,100,101,200", ["q", "qb", "a", "b", "vdd#branch", "vm#branch"])
     if "srcs" in which:
         run("srcs", srcs_netlist(), "0-20,100,101,300", ["y", "b2", "c2", "d2", "e2", "f", "g", "h", "k", "v1#branch"])
     if "b3ring" in which:

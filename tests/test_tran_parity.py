@@ -42,7 +42,7 @@ def _compare(res, t, v, wave, s, exact, tol=1e-9, same_route=True):
 
 # invsrc / invgmin: the inverter with `.option noopiter` (+ `gminsteps=0`): CKTop goes straight to gillespie_src /
 # dynamic_gmin (cktop.c:42-96), which run per sample inside the device controller
-@pytest.mark.parametrize("name", ["ro17", "ro17k", "inv", "dio", "b3ring", "latch", "srcs", "invsrc", "invgmin", "invshunt"])       # invshunt: gshunt=1e-9 ends the ladder and stays on the diagonal
+@pytest.mark.parametrize("name", ["ro17", "ro17k", "inv", "dio", "b3ring", "latch", "latchns", "srcs", "invsrc", "invgmin", "invshunt"])   # latchns: .nodeset on the operating point (the ipass rule of niiter.c:307-331)       # invshunt: gshunt=1e-9 ends the ladder and stays on the diagonal
 def test_tran_hostsim_bit_identical(hostsim_lib, name):
     res, t, v, wave = _run(hostsim_lib, name)
     _compare(res, t, v, wave, 0, exact=True)
