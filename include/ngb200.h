@@ -208,6 +208,13 @@ int ngbTranStats(ngb_batch *b, int *accepted, int *rejected, int *numiter, int *
 int ngbTranErrors(ngb_batch *b, int *err /* [S] */);
 long ngbTranWaveBytes(ngb_batch *b);
 int ngbTranWaves(ngb_batch *b, double *times /* [S][max_points] */, double *values /* [S][max_points][nsave] */);
+/* `.meas tran` on the device (the output path of src/frontend/outitf.c:633 + com_measure2.c:378-663 for this workload):
+ * clause k is the count[k]-th RISE (kind 0) / FALL (1) / CROSS (2) of equation eq[k] through val[k], linearly
+ * interpolated between the two accepted points around it, points before td[k] ignored -- evaluated as the points are
+ * produced, so no waveform has to be stored or copied (max_points = 0, nsave = 0 is allowed then).  A
+ * `TRIG .. TARG ..` measurement is two clauses; its result is the difference.  ngbTranMeasures: out [n][S], NaN = not found */
+int ngbTranSetMeasures(ngb_batch *b, int n, const int *eq, const int *kind, const int *count, const double *val, const double *td);
+int ngbTranMeasures(ngb_batch *b, double *out);
 long ngbTranTicks(ngb_batch *b);              /* Newton steps the batch needed */
 void *ngbTranDevWaves(ngb_batch *b, int which /* 0 times, 1 values */);   /* device pointers for a collective gather */
 /* per-thread BSIM4 parameter rows for model-parameter mismatch: prow_t [ninst*S] into new tables */

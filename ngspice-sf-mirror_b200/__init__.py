@@ -354,6 +354,15 @@ class Batch:
     def lufac_solve(self):
         self.lib.check(self.lib.L.ngbLuFacSolve(self.h), "ngbLuFacSolve")
 
+    def set_measures(self, clauses):
+        """`.meas tran` clauses evaluated on the device while the points are produced (com_measure2.c:378-663):
+        clauses = [(equation, kind 0 RISE / 1 FALL / 2 CROSS, count, level, td), ...]; [] removes them"""
+        n = len(clauses)
+        eq = _i32([c[0] for c in clauses]); kind = _i32([c[1] for c in clauses]); cnt = _i32([c[2] for c in clauses])
+        val = _f64([c[3] for c in clauses]); td = _f64([c[4] for c in clauses])
+        self.lib.check(self.lib.L.ngbTranSetMeasures(self.h, n, _ip(eq), _ip(kind), _ip(cnt), _dp(val), _dp(td)), "ngbTranSetMeasures")
+        self.nmeas = n
+
     # DCtran for the whole batch, resident on the device
     def tran(self, max_points, save_eq):
         """Run the transient analysis (options tstep/tstop/tmax/uic of the circuit) for every
@@ -374,6 +383,12 @@ class TranResult:
         self.ticks = int(L.ngbTranTicks(batch.h))
         self.err = np.zeros(S, np.int32)          # DCtran's return value per sample (0 = completed)
         batch.lib.check(L.ngbTranErrors(batch.h, _ip(self.err)), "ngbTranErrors")
+
+    def measures(self):
+        """[nclauses][S] measured times, NaN where the transition did not occur"""
+        out = np.zeros((self.b.nmeas, self.b.S))
+        self.b.lib.check(self.b.lib.L.ngbTranMeasures(self.b.h, _dp(out)), "ngbTranMeasures")
+        return out
 
     def waves(self):
         S = self.b.S

@@ -1780,6 +1780,7 @@ void ngbBatchDestroy(ngb_batch *b)
 {
     int i;
     if (!b) return;
+    free(b->ms_eq); free(b->ms_kind); free(b->ms_count); free(b->ms_val); free(b->ms_td);
     for (i = 0; i < b->narr; i++)
         if (strcmp(b->arr[i].name, "b4.mtab") && strcmp(b->arr[i].name, "b4.ptab")) ngb_dev_free(b->arr[i].ptr);
     ngb_dev_free(b->d_node_type); ngb_dev_free(b->d_tgt_ptr); ngb_dev_free(b->d_tgt_rows); ngb_dev_free(b->d_slot_diag); ngb_dev_free(b->d_long_tgt);

@@ -78,6 +78,8 @@ struct ngb_batch {
     struct { const char *name; void *ptr; size_t bytes; } arr[NGB_MAX_ARR];
     int narr;
     struct ngb_tran *tran;
+    /* measurement clauses for the next ngbTranRun (ngbTranSetMeasures) */
+    int ms_n; int *ms_eq, *ms_kind, *ms_count; double *ms_val, *ms_td;
 };
 
 void ngb_set_error(const char *fmt, ...);

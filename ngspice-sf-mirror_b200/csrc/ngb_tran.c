@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include "ngb_dev.h"
 #include "ngb_host.h"
 #include "../../include/ngb200.h"
@@ -18,6 +19,7 @@ struct ngb_tran {
     int max_points, nsave;
     int *d_save_eq;
     int *d_mask;               /* [S] samples of a repivot_suspended pass */
+    int *d_ms_eq, *d_ms_kind, *d_ms_count; double *d_ms_val, *d_ms_td;
     long ticks; int repivots;
     int keep_set[NGB_LU_SETS]; /* pattern sets a re-pivoted sample was moved to: launched every step from then on */
     int stage;                 /* 0: some sample is still in the operating point; 1: all in the transient;
@@ -42,6 +44,8 @@ void ngb_tran_free(struct ngb_batch *b)
     { int a; for (a = 0; a < t->x.gm_narr; a++) ngb_dev_free(t->x.gm_arr[a].old); }
     ngb_dev_free(t->d_save_eq); ngb_dev_free(t->x.isrc_break); ngb_dev_free(t->x.vsrc_break);
     ngb_dev_free(t->x.susp); ngb_dev_free(t->d_mask); ngb_dev_free(t->x.ipass);
+    ngb_dev_free(t->d_ms_eq); ngb_dev_free(t->d_ms_kind); ngb_dev_free(t->d_ms_count); ngb_dev_free(t->d_ms_val); ngb_dev_free(t->d_ms_td);
+    ngb_dev_free(t->x.ms_i); ngb_dev_free(t->x.ms_d);
     ngb_dev_graph_destroy(t->graph[0]); ngb_dev_graph_destroy(t->graph[1]); ngb_dev_graph_destroy(t->graph[2]);
     free(t);
     b->tran = NULL;
@@ -75,6 +79,23 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     x->ndone = (int *)dz(sizeof(int) * 4); x->evstage = (int *)dz(sizeof(int) * S);
     x->susp = (int *)dz(sizeof(int) * S); t->d_mask = (int *)dz(sizeof(int) * S);
     x->ipass = (int *)dz(sizeof(int) * S);
+    if (b->ms_n > 0) {
+        const int nm = b->ms_n;
+        double *nanv = (double *)malloc(sizeof(double) * 3 * (size_t)nm * S);
+        int m2; size_t q;
+        t->d_ms_eq = (int *)dz(sizeof(int) * nm); t->d_ms_kind = (int *)dz(sizeof(int) * nm); t->d_ms_count = (int *)dz(sizeof(int) * nm);
+        t->d_ms_val = (double *)dz(sizeof(double) * nm); t->d_ms_td = (double *)dz(sizeof(double) * nm);
+        x->ms_i = (int *)dz(sizeof(int) * 4 * (size_t)nm * S); x->ms_d = (double *)dz(sizeof(double) * 3 * (size_t)nm * S);
+        if (!nanv || !x->ms_i || !x->ms_d) { free(nanv); ngb_set_error("measurement buffers: out of memory"); return NGB_E_PANIC; }
+        ngb_dev_h2d(t->d_ms_eq, b->ms_eq, sizeof(int) * nm); ngb_dev_h2d(t->d_ms_kind, b->ms_kind, sizeof(int) * nm);
+        ngb_dev_h2d(t->d_ms_count, b->ms_count, sizeof(int) * nm);
+        ngb_dev_h2d(t->d_ms_val, b->ms_val, sizeof(double) * nm); ngb_dev_h2d(t->d_ms_td, b->ms_td, sizeof(double) * nm);
+        for (m2 = 0; m2 < nm; m2++)
+            for (q = 0; q < 3 * (size_t)S; q++) nanv[(size_t)m2 * 3 * S + q] = (q >= 2 * (size_t)S) ? NAN : 0.0;   /* m_measured = NAN until found */
+        ngb_dev_h2d(x->ms_d, nanv, sizeof(double) * 3 * (size_t)nm * S);
+        free(nanv);
+        x->nmeas = nm; x->ms_eq = t->d_ms_eq; x->ms_kind = t->d_ms_kind; x->ms_count = t->d_ms_count; x->ms_val = t->d_ms_val; x->ms_td = t->d_ms_td;
+    }
     { int i2; x->had_nodeset = 0; for (i2 = 0; i2 < c->ov_n; i2++) if (c->ov_kind[i2] == 0) x->had_nodeset = 1; }
     ngb_fill_srcctx(b, &x->isrc, 1); ngb_fill_srcctx(b, &x->vsrc, 0);
     x->isrc_break = (double *)dz(sizeof(double) * (size_t)(x->isrc.ninst > 0 ? x->isrc.ninst : 1) * S);
@@ -352,7 +373,12 @@ int ngbTranRun(ngb_batch *b, int max_points, const int *save_eq, int nsave)
     if (b->c->opt.tstop <= 0 || b->c->opt.tstep <= 0) { ngb_set_error("transient parameters not set"); return NGB_E_PANIC; }
     if ((r = tran_setup(b, max_points, save_eq, nsave))) return r;
     ngb_dev_memset(b->errflag, 0, sizeof(int) * 4);
-    max_ticks = 64L * max_points + 1024;
+    {   /* safety cap on the Newton steps of the run: 64 per stored point, or (nothing stored, measurements only) per print step x 16 */
+        long pts = max_points;
+        const double steps = b->c->opt.tstop / b->c->opt.tstep;
+        if (b->ms_n > 0 && steps * 16 > (double)pts) pts = (long)(steps * 16);
+        max_ticks = 64L * pts + 1024;
+    }
     if (b->c->opt.uic) {
         /* CKTop under UIC: one CKTload, no factorisation (niiter.c:41-47) */
         if ((r = enqueue_tick(b, 0))) return r;
@@ -414,3 +440,33 @@ int ngbTranWaves(ngb_batch *b, double *times, double *values)
 }
 long ngbTranTicks(ngb_batch *b) { return b->tran ? b->tran->ticks : 0; }
 void *ngbTranDevWaves(ngb_batch *b, int which) { return b->tran ? (which ? (void *)b->tran->x.out_val : (void *)b->tran->x.out_time) : NULL; }
+
+/* `.meas tran` clauses for the next ngbTranRun, evaluated on the device while the points are produced (com_measure_when,
+ * src/frontend/com_measure2.c:378-663): clause k watches equation eq[k] for its count[k]-th RISE (kind 0) / FALL (1) /
+ * CROSS (2) through val[k], ignoring points before td[k].  n = 0 removes them */
+int ngbTranSetMeasures(ngb_batch *b, int n, const int *eq, const int *kind, const int *count, const double *val, const double *td)
+{
+    int k;
+    free(b->ms_eq); free(b->ms_kind); free(b->ms_count); free(b->ms_val); free(b->ms_td);
+    b->ms_eq = b->ms_kind = b->ms_count = NULL; b->ms_val = b->ms_td = NULL; b->ms_n = 0;
+    if (n <= 0) return NGB_OK;
+    for (k = 0; k < n; k++)
+        if (eq[k] < 1 || eq[k] >= b->neq1 || kind[k] < 0 || kind[k] > 2 || count[k] < 1) { ngb_set_error("measurement clause %d is malformed", k); return NGB_E_PANIC; }
+    b->ms_eq = (int *)malloc(sizeof(int) * (size_t)n); b->ms_kind = (int *)malloc(sizeof(int) * (size_t)n); b->ms_count = (int *)malloc(sizeof(int) * (size_t)n);
+    b->ms_val = (double *)malloc(sizeof(double) * (size_t)n); b->ms_td = (double *)malloc(sizeof(double) * (size_t)n);
+    if (!b->ms_eq || !b->ms_kind || !b->ms_count || !b->ms_val || !b->ms_td) return NGB_E_PANIC;
+    memcpy(b->ms_eq, eq, sizeof(int) * (size_t)n); memcpy(b->ms_kind, kind, sizeof(int) * (size_t)n); memcpy(b->ms_count, count, sizeof(int) * (size_t)n);
+    memcpy(b->ms_val, val, sizeof(double) * (size_t)n); memcpy(b->ms_td, td, sizeof(double) * (size_t)n);
+    b->ms_n = n;
+    return NGB_OK;
+}
+/* the measured times, out [n][S]; NaN where the transition did not occur (m_measured = NAN, com_measure2.c:659) */
+int ngbTranMeasures(ngb_batch *b, double *out)
+{
+    struct ngb_tran *t = b->tran;
+    int m;
+    if (!t || !t->x.nmeas) { ngb_set_error("no measurement clauses were set for the last ngbTranRun"); return NGB_E_PANIC; }
+    for (m = 0; m < t->x.nmeas; m++)
+        ngb_dev_d2h(out + (size_t)m * b->S, t->x.ms_d + ((size_t)m * 3 + 2) * b->S, sizeof(double) * (size_t)b->S);
+    return NGB_OK;
+}

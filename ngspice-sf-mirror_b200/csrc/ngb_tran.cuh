@@ -50,6 +50,17 @@ typedef struct NgbTranCtx {
     int *susp;                 /* [S] 0; 1: the refactor met a zero pivot, the sample waits (inactive) for the host to factor its matrix
                                 * again with pivoting, niiter.c:162-195; 2: that factor found the matrix singular -- NIiter returns E_SINGULAR */
     const int *only;           /* not NULL: this launch handles only the samples with only[s] != 0 (the ones the host has just re-pivoted) */
+    /* measurement clauses evaluated while the points are produced (com_measure_when, com_measure2.c:378-663): the n-th
+     * RISE / FALL / CROSS of one saved quantity through a constant, linearly interpolated between the two output points
+     * around it.  A `.meas tran x TRIG .. TARG ..` is two clauses (result = second - first).  No waveform has to be kept */
+    int nmeas;
+    const int *ms_eq;          /* [nmeas] equation whose CKTrhsOld value is watched */
+    const int *ms_kind;        /* [nmeas] 0 RISE, 1 FALL, 2 CROSS */
+    const int *ms_count;       /* [nmeas] which one (1 = first) */
+    const double *ms_val;      /* [nmeas] the level (VAL=) */
+    const double *ms_td;       /* [nmeas] points before this time are not looked at (TD=) */
+    int *ms_i;                 /* [nmeas][4][S] first, section, rise+fall count packed: see ngb_measure_point */
+    double *ms_d;              /* [nmeas][3][S] previous value, previous time, result (NaN until found) */
     int *ipass;                /* [S] NIiter's `ipass`: set by every MODEINITFIX iteration; with nodesets in the circuit the first
                                 * MODEINITFLOAT iteration of an operating point then counts as not converged (niiter.c:307-331) */
     int had_nodeset;           /* CKThadNodeset (cktic.c:46): some node carries a .nodeset */
@@ -268,6 +279,40 @@ NGB_HD int ngb_src_accept(const NgbTranCtx *c, const NgbSrcCtx *sc, double *brk,
     return NGB_OK;
 }
 
+/* one output point (time, value of the watched equation) for measurement clause m of sample s: the loop body of
+ * com_measure_when for a real vector against a constant (com_measure2.c:455-660, the branch without a second vector);
+ * `first` counts the points looked at: the second one only initialises the side (and may count a transition without
+ * measuring it -- mirrored), later ones count transitions and take the measurement when the requested count is met */
+NGB_HD void ngb_measure_point(const NgbTranCtx *c, int m, int s, double scale, double value)
+{
+    const int S = c->S;
+    int *mi = c->ms_i + (size_t)m * 4 * S;
+    double *md = c->ms_d + (size_t)m * 3 * S;
+    int first = mi[s], section = mi[(size_t)S + s], rise = mi[(size_t)2 * S + s], fall = mi[(size_t)3 * S + s];
+    const double val = c->ms_val[m];
+    const double prevValue = md[s], prevScale = md[(size_t)S + s];
+    if (first < 0) return;                                   /* measured */
+    if (scale < c->ms_td[m]) return;
+    if (first == 1) {
+        rise = fall = 0;
+        if (value < val) { section = 0; if (prevValue >= val) fall = 1; }
+        else { section = 1; if (prevValue < val) rise = 1; }
+    }
+    if (first > 1) {
+        if (section == 0 && value >= val) { section = 1; rise++; }
+        else if (section == 1 && value <= val) { section = 0; fall++; }
+        const int kind = c->ms_kind[m], want = c->ms_count[m];
+        const int have = kind == 0 ? rise : (kind == 1 ? fall : rise + fall);
+        if (have == want) {
+            md[(size_t)2 * S + s] = prevScale + (val - prevValue) * (scale - prevScale) / (value - prevValue);
+            mi[s] = -1;
+            return;
+        }
+    }
+    mi[s] = first + 1; mi[(size_t)S + s] = section; mi[(size_t)2 * S + s] = rise; mi[(size_t)3 * S + s] = fall;
+    md[s] = value; md[(size_t)S + s] = scale;
+}
+
 /* the nextTime: label of dctran.c:355-665 -- accept the point, output, breakpoints, rotate */
 NGB_HD void ngb_next_time(const NgbTranCtx *c, int s)
 {
@@ -294,6 +339,10 @@ NGB_HD void ngb_next_time(const NgbTranCtx *c, int s)
                 c->out_val[((size_t)s * c->max_points + n) * c->nsave + k] = xo[(size_t)c->save_eq[k] * S + s];
         }
         c->npts[s] = n + 1;
+        if (c->nmeas) {
+            const double *xo = c->x + (size_t)c->ctl.xsel[s] * c->neq1 * S;
+            for (int m = 0; m < c->nmeas; m++) ngb_measure_point(c, m, s, time, xo[(size_t)c->ms_eq[m] * S + s]);
+        }
     }
     if (ngb_almost_equal_ulps(time, c->tstop, 100)) { ngb_finish(c, s, NGB_PH_DONE, 0); return; }
 

@@ -349,6 +349,31 @@ def run(name, netlist, calls, save):
     print(name, "points", arr.shape[0], "stats", stats)
 
 
+MEAS_CLAUSES = [   # (name, text of the measurement, clauses as (node, kind, count, val, td)): kinds 0 RISE 1 FALL 2 CROSS
+    ("tdiff", "TRIG v(18) VAL=0.5 RISE=1 TARG v(18) VAL=0.5 RISE=3", [("18", 0, 1, 0.5, 0.0), ("18", 0, 3, 0.5, 0.0)]),
+    ("tfall", "WHEN v(9)=1.0 FALL=2", [("9", 1, 2, 1.0, 0.0)]),
+    ("tcross", "WHEN v(2)=1.2 CROSS=5", [("2", 2, 5, 1.2, 0.0)]),
+    ("tdel", "WHEN v(18)=0.5 RISE=1 TD=6n", [("18", 0, 1, 0.5, 6e-9)]),
+    ("tnone", "WHEN v(18)=0.5 RISE=40", [("18", 0, 40, 0.5, 0.0)]),
+]
+
+
+def run_meas(name, netlist):
+    """`.meas tran` results of the stock reference binary (com_measure2.c) for the device-side measurement clauses"""
+    os.makedirs(TMP, exist_ok=True)
+    cir = os.path.join(TMP, name + "_meas.cir")
+    ctl = ".control\nset numdgt=17\nrun\n" + "".join(f"meas tran {nm} {txt}\nprint {nm}\n" for nm, txt, _ in MEAS_CLAUSES) + ".endc\n"
+    open(cir, "w").write(netlist.replace(".end\n", ctl + ".end\n"))
+    p = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ngspice"), "-b", cir], capture_output=True, text=True)
+    out = {}
+    for nm, _, cl in MEAS_CLAUSES:
+        m = re.search(rf"^{nm} = (\S+)$", p.stdout, re.M)      # the `print` line carries all 17 digits
+        out[nm] = {"value": float(m.group(1)) if m else None,
+                   "clauses": [dict(node=c[0], kind=c[1], count=c[2], val=c[3], td=c[4]) for c in cl]}
+    json.dump(out, open(os.path.join(HERE, name + ".meas.json"), "w"), indent=1)
+    print(name, "meas", {k: v["value"] for k, v in out.items()})
+
+
 def run_op_only(name, netlist):
     """a run whose operating point FAILS in the reference: circuit, pattern sets and the statistics only -- `op_loads` is
     the number of CKTload calls under MODETRANOP, i.e. the Newton iterations of CKTop's plain NIiter and all its fallbacks"""
@@ -375,6 +400,8 @@ if __name__ == "__main__":
         run("ro17", ro_netlist(17), "0-3,100,101,5000,5001", ["18", "2", "9", "vdd#branch"])
     if "ro17k" in which:
         run("ro17k", ro_netlist(17, tran=".tran .1ns 20ns uic", kick=True), "1,2", ["18", "2", "9", "vdd#branch"])
+    if "ro17kmeas" in which:
+        run_meas("ro17k", ro_netlist(17, tran=".tran .1ns 20ns uic", kick=True))
     if "ro17mc" in which:
         # four Monte-Carlo samples with per-instance Vth mismatch (delvto ~ N(0, 15 mV), numpy seed 7)
         rng = np.random.default_rng(7)
