@@ -215,6 +215,14 @@ int ngbTranWaves(ngb_batch *b, double *times /* [S][max_points] */, double *valu
  * `TRIG .. TARG ..` measurement is two clauses; its result is the difference.  ngbTranMeasures: out [n][S], NaN = not found */
 int ngbTranSetMeasures(ngb_batch *b, int n, const int *eq, const int *kind, const int *count, const double *val, const double *td);
 int ngbTranMeasures(ngb_batch *b, double *out);
+/* which BSIM4 load kernel the batch runs (csrc/bsim4_variants.h): key[0] = the variant key packed from the model selectors
+ * and rbodyMod / rgateMod of its instances (0xffffffff when they differ), key[1] = 1 when the kernel specialised on that key
+ * is in use.  ngbBatchSetBsim4Generic(b, 1) (or NGB_B4_GENERIC=1 in the environment) forces the generic kernel: same bits */
+int ngbBatchBsim4Variant(ngb_batch *b, unsigned key[2]);
+void ngbBatchSetBsim4Generic(ngb_batch *b, int on);
+/* per-stage device time of the Newton steps sampled by ngbProfile (ms summed over the sampled steps; returns their number):
+ * [1] small device loads, [2] BSIM4 load, [3] assembly, [4] refactor + solve, [5] BSIM4trunc, [6] controller */
+int ngbProfileStages(double ms[8]);
 long ngbTranTicks(ngb_batch *b);              /* Newton steps the batch needed */
 void *ngbTranDevWaves(ngb_batch *b, int which /* 0 times, 1 values */);   /* device pointers for a collective gather */
 /* per-thread BSIM4 parameter rows for model-parameter mismatch: prow_t [ninst*S] into new tables */

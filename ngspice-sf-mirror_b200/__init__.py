@@ -332,6 +332,16 @@ class Batch:
         assert g.shape[1] == self.S
         self.lib.check(self.lib.L.ngbBatchSetResistors(self.h, _dp(g)), "ngbBatchSetResistors")
 
+    def bsim4_variant(self):
+        """(variant key of the batch's BSIM4 instances, True when the kernel specialised on it is in use) -- csrc/bsim4_variants.h"""
+        k = (ctypes.c_uint * 2)()
+        self.lib.check(self.lib.L.ngbBatchBsim4Variant(self.h, k), "ngbBatchBsim4Variant")
+        return int(k[0]), bool(k[1])
+
+    def set_bsim4_generic(self, on=True):
+        """run the generic BSIM4 load kernel whatever the variant key (same bits; parity tests and measurements)"""
+        self.lib.L.ngbBatchSetBsim4Generic(self.h, 1 if on else 0)
+
     def set_op_full(self, on=True):
         self.lib.L.ngbBatchSetOpFull(self.h, 1 if on else 0)
 

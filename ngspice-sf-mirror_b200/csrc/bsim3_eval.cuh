@@ -1710,7 +1710,8 @@ NGB_HD int b3_load_thread(const B3Ctx *c, size_t t)
             }
             for (int k = 0; k < 3; k++) {
                 const int q = qk[k];
-                cq[k] = ngb_integrate_trap(order, ag0, ag1, B3ST(0, q), B3ST(1, q), (order == 2) ? B3ST(1, q + 1) : 0.0);
+                cq[k] = ngb_integrate(c->ctl.gear, order, ag0, ag1, c->ctl.gear ? NGB_LDG(&c->ctl.ag2[s]) : 0.0, B3ST(0, q), B3ST(1, q),
+                                      (c->ctl.gear && order == 2) ? B3ST(2, q) : 0.0, (order == 2) ? B3ST(1, q + 1) : 0.0);
                 B3ST(0, q + 1) = cq[k];
                 if (c->ctl.lte)
                     ngb_lte_state(&c->ctl, s, c->state, B3ST_COUNT, (size_t)c->T, t, head, q, order);

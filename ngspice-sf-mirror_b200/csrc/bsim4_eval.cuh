@@ -59,6 +59,7 @@ typedef struct B4Ctx {
     const double *ptab;        /* [nrows][B4P_COUNT] bin rows                            */
     const int *prow;           /* parameter row per thread ([T]) or per instance ([ninst]) */
     int prow_per_thread;       /* 1: prow[t], 0: prow[inst]                              */
+    unsigned variant;          /* variant key of the batch (bsim4_variants.h), NGB_B4_GENERIC when its instances differ */
     const double *inst;        /* [B4I_COUNT][T]                                         */
     const int *flags;          /* [ninst] packed B4F_*                                   */
     const int *nodes;          /* [B4N_COUNT][ninst] equation numbers (0 = ground)       */
@@ -114,10 +115,18 @@ typedef struct B4W {
     double cggb, cgsb, cgdb, cdgb, cdsb, cddb, cbgb, cbsb, cbdb;
 } B4W;
 
+#include "bsim4_variants.h"
 #define B4M(f) NGB_LDG(&Mrow[B4M_##f])
 #define B4P(f) NGB_LDG(&Prow[B4P_##f])
 #define B4I(f) NGB_LDG(&c->inst[(size_t)B4I_##f * c->T + t])
+/* selectors: compile-time constants of the variant key VK in a specialised instantiation, read from the parameter
+ * row / instance flags in the generic one (bsim4_variants.h) */
+#define B4SEL(f) ((VK == NGB_B4_GENERIC) ? (int)B4M(f) : B4K_FIELD(VK, f))
+#define B4SEL_RBODY(fl) ((VK == NGB_B4_GENERIC) ? B4F_RBODY(fl) : B4K_FIELD(VK, rbodyMod))
+#define B4SEL_RGATE(fl) ((VK == NGB_B4_GENERIC) ? B4F_RGATE(fl) : B4K_FIELD(VK, rgateMod))
+#define B4SEL_GEAR() ((VK == NGB_B4_GENERIC) ? c->ctl.gear : B4K_FIELD(VK, gear))
 
+#ifdef __cplusplus      /* the plain-C host files only need the declarations above */
 /* DEXP of b4ld.c:49-60 */
 NGB_HD void b4_dexp(double A, double *B, double *C)
 {
@@ -243,13 +252,14 @@ NGB_HD_SHARED void b4_tat(double vts, double vj, double Nvtmr, double *Tn, doubl
 #define B4ST(h, k) b4st##h[(size_t)(k) * c->T]
 
 /* Phase A: terminal voltages by INITF mode and Newton step limiting (b4ld.c:257-698). */
+template <unsigned VK>
 NGB_HD void b4_fetch_limit(const B4Ctx *c, size_t t, int inst, int s, int head, int mode_ckt,
                            const double *Mrow, int flags, B4W *w)
 {
-    const int rbodyMod = B4F_RBODY(flags), rgateMod = B4F_RGATE(flags);
+    const int rbodyMod = B4SEL_RBODY(flags), rgateMod = B4SEL_RGATE(flags);
     const int off = flags & B4F_OFF;
     const double type = B4M(type);
-    const int rdsMod = (int)B4M(rdsMod);
+    const int rdsMod = B4SEL(rdsMod);
     const int S = c->S;
     B4ST_BASES(head);
     double vds, vgs, vbs, vges, vgms, vdbs, vsbs, vses, vdes, qdef;
@@ -421,13 +431,14 @@ NGB_HD void b4_fetch_limit(const B4Ctx *c, size_t t, int inst, int s, int head, 
 
 /* Phase B+C: junction diodes, threshold voltage, effective gate drive, mobility, Vdsat,
  * drain current and its output-resistance corrections (b4ld.c:700-2189). */
+template <unsigned VK>
 NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, const double *Prow,
                        int flags, B4W *w)
 {
     const double gmin = NGB_LDG(&c->ctl.gmin[s]);
     const double nf = B4I(nf);
     const double vtm = B4M(vtm), vtm0 = B4M(vtm0);
-    const int mtrlMod = (int)B4M(mtrlMod);
+    const int mtrlMod = B4SEL(mtrlMod);
     const double coxe = B4M(coxe);
     double T0, T1, T2, T3, T4, T5, T6, T7, T8, T9, T10, T11, T12, T13, T14;
     double dT0_dVg, dT0_dVd, dT0_dVb, dT1_dVg, dT1_dVd, dT1_dVb, dT2_dVg, dT2_dVd, dT2_dVb;
@@ -439,7 +450,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     NGB_CTA_ALIGN();
     /* ---- source/drain junction diodes (DC) ---- */
     {
-        const int dioMod = (int)B4M(dioMod);
+        const int dioMod = B4SEL(dioMod);
         const double weffCJnf = B4P(weffCJ) * nf;
         double Isat, Nvtm, jg, jc;
 
@@ -633,7 +644,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
     }
 
     /* Vth correction for pocket implant */
-    const int tempMod = (int)B4M(tempMod);
+    const int tempMod = B4SEL(tempMod);
     if (B4P(dvtp0) > 0.0) {
         double dDITS_Sft_dVd, dDITS_Sft_dVb;
         T0 = -B4P(dvtp1) * Vds;
@@ -757,7 +768,7 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
         dWeff_dVb *= T0;
     }
 
-    const int rdsMod = (int)B4M(rdsMod);
+    const int rdsMod = B4SEL(rdsMod);
     double Rds, dRds_dVg, dRds_dVb;
     if (rdsMod == 1) {
         Rds = dRds_dVg = dRds_dVb = 0.0;
@@ -854,10 +865,10 @@ NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, cons
 
     NGB_CTA_ALIGN();
     /* ---- mobility ---- */
-    const int mobMod = (int)B4M(mobMod);
+    const int mobMod = B4SEL(mobMod);
     const double ua = B4P(ua), ub = B4P(ub), uc = B4P(uc), ud = B4P(ud);
     double dDenomi_dVg, dDenomi_dVd, dDenomi_dVb, Denomi;
-    if (mtrlMod && ((int)B4M(mtrlCompatMod) == 0))
+    if (mtrlMod && (B4SEL(mtrlCompatMod) == 0))
         T14 = 2.0 * type * (B4M(phig) - B4M(easub) - 0.5 * B4M(Eg0) + 0.45);
     else
         T14 = 0.0;
@@ -1642,13 +1653,14 @@ NGB_HD_SHARED void b4_ig_edge(double vg, double vfbsd_tot, double Aechvb, double
 
 /* Phase D: gate resistance network, bias-dependent S/D resistance, GIDL/GISL, gate
  * tunnelling, finger scaling (b4ld.c:2191-2976). */
+template <unsigned VK>
 NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const double *Prow,
                           int flags, B4W *w)
 {
-    const int rgateMod = B4F_RGATE(flags);
+    const int rgateMod = B4SEL_RGATE(flags);
     const double nf = B4I(nf);
-    const int mtrlMod = (int)B4M(mtrlMod);
-    const int igcMod = (int)B4M(igcMod), igbMod = (int)B4M(igbMod);
+    const int mtrlMod = B4SEL(mtrlMod);
+    const int igcMod = B4SEL(igcMod), igbMod = B4SEL(igbMod);
     const double toxe = w->toxe;
     const double vds = w->vds, vgs = w->vgs, vgd = w->vgd, vbs = w->vbs, vbd = w->vbd;
     const double Vgsteff = w->Vgsteff, dVgsteff_dVg = w->dVgsteff_dVg;
@@ -1694,7 +1706,7 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
 
     NGB_CTA_ALIGN();
     /* ---- bias-dependent external S/D resistance ---- */
-    if ((int)B4M(rdsMod)) {
+    if (B4SEL(rdsMod)) {
         double vgs_eff, dvgs_eff_dvg, vgd_eff, dvgd_eff_dvg, dT0_dvg, dT1_dvb, dT3_dvg, dT3_dvb;
         double Rs, dRs_dvg, dRs_dvb, Rd, dRd_dvg, dRd_dvb;
         double dgstot_dvd, dgstot_dvg, dgstot_dvb, dgstot_dvs;
@@ -1784,7 +1796,7 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
         if (mtrlMod == 0) T0 = 3.0 * toxe;
         else T0 = B4M(epsrsub) * toxe / w->epsrox;
 
-        if ((int)B4M(gidlMod) == 0) {
+        if (B4SEL(gidlMod) == 0) {
             if (mtrlMod == 0) T1 = (vds - w->vgs_eff - B4P(egidl)) / T0;
             else T1 = (vds - w->vgs_eff - B4P(egidl) + vfbsd_add) / T0;
             b4_gidl0(T1, w->dvgs_eff_dvg, T0, B4P(agidl), B4P(bgidl), B4P(cgidl), weffCJ, vbd,
@@ -1857,7 +1869,7 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
         dVoxdepinv_dVb += dVgsteff_dVb;
     }
 
-    const double tmpV = ((int)B4M(tempMod) < 2) ? w->Vtm : w->Vtm0;
+    const double tmpV = (B4SEL(tempMod) < 2) ? w->Vtm : w->Vtm0;
     if (igcMod) {
         const double type = B4M(type), vth0 = B4I(vth0);
         double Igc, dIgc_dVg, dIgc_dVd, dIgc_dVb, Pigcd, dPigcd_dVg, dPigcd_dVd, dPigcd_dVb;
@@ -2145,6 +2157,7 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
 }
 
 /* VgsteffCV selection shared by capMod 1 and 2 (b4ld.c:3351-3457) */
+template <unsigned VK>
 NGB_HD void b4_vgsteff_cv(const double *Mrow, const double *Prow, const B4W *w,
                           double *pVgsteff, double *pdVg, double *pdVd, double *pdVb)
 {
@@ -2152,7 +2165,7 @@ NGB_HD void b4_vgsteff_cv(const double *Mrow, const double *Prow, const B4W *w,
     const double dVgs_eff_dVg = w->dVgs_eff_dVg, dVth_dVd = w->dVth_dVd, dVth_dVb = w->dVth_dVb;
     double Vgsteff, dVgsteff_dVg, dVgsteff_dVd, dVgsteff_dVb, T0, T1, T2, T3, T4, T5, T9, T10, T11;
     double dT9_dVg, dT9_dVd, dT9_dVb, dT10_dVg, dT10_dVd, dT10_dVb, ExpVgst;
-    if ((int)B4M(cvchargeMod) == 0) {
+    if (B4SEL(cvchargeMod) == 0) {
         const double noff = n * B4P(noff);
         const double dnoff_dVd = B4P(noff) * dn_dVd;
         const double dnoff_dVb = B4P(noff) * dn_dVb;
@@ -2243,11 +2256,12 @@ NGB_HD void b4_vgsteff_cv(const double *Mrow, const double *Prow, const B4W *w,
 
 /* Phase E: intrinsic terminal charges and trans-capacitances (b4ld.c:3014-3913).
  * Returns 0 when charges are not computed (xpart<0 or no charge computation). */
+template <unsigned VK>
 NGB_HD int b4_charges(const B4Ctx *c, size_t t, const double *Mrow, const double *Prow,
                       int ChargeComputationNeeded, B4W *w)
 {
     const double xpart = B4M(xpart);
-    const int capMod = (int)B4M(capMod);
+    const int capMod = B4SEL(capMod);
     const double nf = B4I(nf);
     const double coxe = B4M(coxe);
     const double phi = B4P(phi), k1ox = B4P(k1ox);
@@ -2509,7 +2523,7 @@ NGB_HD int b4_charges(const B4Ctx *c, size_t t, const double *Mrow, const double
         if (Vbseff < 0.0) { VbseffCV = Vbseff; dVbseffCV_dVb = 1.0; }
         else { VbseffCV = phi - Phis; dVbseffCV_dVb = -dPhis_dVb; }
 
-        b4_vgsteff_cv(Mrow, Prow, w, &Vgsteff, &dVgsteff_dVg, &dVgsteff_dVd, &dVgsteff_dVb);
+        b4_vgsteff_cv<VK>(Mrow, Prow, w, &Vgsteff, &dVgsteff_dVg, &dVgsteff_dVd, &dVgsteff_dVb);
 
         if (capMod == 1) {
             const double Vfb = vfbzb;
@@ -2990,21 +3004,22 @@ NGB_HD int b4_prologue(const B4Ctx *c, size_t t, int first, B4Pro *p, int *err)
     return 1;
 }
 
-NGB_HD int b4_finish(const B4Ctx *c, size_t t, const B4Pro *pro, const B4W *wp);
+template <unsigned VK> NGB_HD int b4_finish(const B4Ctx *c, size_t t, const B4Pro *pro, const B4W *wp);
 
+template <unsigned VK>
 NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
 {
     B4Pro p;
     B4W w;
     int err;
     if (!b4_prologue(c, t, 1, &p, &err)) return err;
-    b4_fetch_limit(c, t, p.inst, p.s, p.head, p.mode_ckt, p.Mrow, p.flags, &w);
-    b4_core_dc(c, t, p.s, p.Mrow, p.Prow, p.flags, &w);
+    b4_fetch_limit<VK>(c, t, p.inst, p.s, p.head, p.mode_ckt, p.Mrow, p.flags, &w);
+    b4_core_dc<VK>(c, t, p.s, p.Mrow, p.Prow, p.flags, &w);
     /* the parasitics and the intrinsic charges only read what the core phase left; the charges first (12 values for the
      * finish phase alive across the parasitics instead of 52 across the charges) was measured 6 % SLOWER on B200 */
-    b4_parasitics(c, t, p.Mrow, p.Prow, p.flags, &w);
-    b4_charges(c, t, p.Mrow, p.Prow, p.charge, &w);
-    return b4_finish(c, t, &p, &w);
+    b4_parasitics<VK>(c, t, p.Mrow, p.Prow, p.flags, &w);
+    b4_charges<VK>(c, t, p.Mrow, p.Prow, p.charge, &w);
+    return b4_finish<VK>(c, t, &p, &w);
 }
 
 #define B4FIN_NAME b4_finish
@@ -3014,6 +3029,17 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
 #undef B4FIN_NAME
 #undef B4FIN_W
 #undef BW
+
+#ifndef __CUDACC__
+/* host build (tests/hostsim): the same dispatch the CUDA launcher does over its kernel instantiations */
+static inline int b4_load_thread_variant(const B4Ctx *c, size_t t)
+{
+#define X(k) if (c->variant == (k)) return b4_load_thread<(k)>(c, t);
+    NGB_B4_VARIANT_KEYS(X)
+#undef X
+    return b4_load_thread<NGB_B4_GENERIC>(c, t);
+}
+#endif
 /* ---- BSIM4trunc out of the load ------------------------------------------------------------------
  * The reference calls DEVtrunc once per converged time point (CKTtrunc, dctran.c:794); evaluated inside every
  * load it was a fifth of the kernel's instructions (10 copies of CKTterr, 70 of the 313 divisions).  With
@@ -3051,5 +3077,7 @@ NGB_HD void b4_lte_inst(const B4Ctx *c, int inst, int s, double *m1, double *m2)
     if (rgateMod == 3) B4_LTE1(B4ST_qgmid);
 #undef B4_LTE1
 }
+
+#endif /* __cplusplus */
 
 #endif

@@ -92,11 +92,24 @@ NGB_HD double ngb_integrate_trap(int order, double ag0, double ag1, double q0, d
     if (order == 1) return ag0 * q0 + ag1 * q1;
     return -c1 * ag1 + ag0 * (q0 - q1);
 }
+/* NIintegrate for both methods (niinteg.c:17-80): GEAR accumulates ag[order]*q[order] ... ag[0]*q[0] from the oldest
+ * charge down, starting from zero; DCtran never raises the order above 2 (dctran.c:794-826), so q2 is the oldest */
+NGB_HD double ngb_integrate(int gear, int order, double ag0, double ag1, double ag2, double q0, double q1, double q2, double c1)
+{
+    if (gear) {
+        double cc = 0;
+        if (order == 2) cc += ag2 * q2;
+        cc += ag1 * q1;
+        cc += ag0 * q0;
+        return cc;
+    }
+    return ngb_integrate_trap(order, ag0, ag1, q0, q1, c1);
+}
 
 /* CKTterr (src/spicelib/analysis/cktterr.c:10-79), TRAPEZOIDAL: the step size the local
  * truncation error of one charge state allows.  q[0..order+1] = CKTstates[i][qcap],
  * cc0/cc1 = CKTstate0/1[ccap], dold = CKTdeltaOld. */
-NGB_HD double ngb_terr(int order, const double *q, double cc0, double cc1, const double *dold,
+NGB_HD double ngb_terr(int gear, int order, const double *q, double cc0, double cc1, const double *dold,
                        double delta, double reltol, double abstol, double chgtol, double trtol)
 {
     double diff[4], deltmp[3], volttol, chargetol, tol, factor, del, a, b;
@@ -115,7 +128,7 @@ NGB_HD double ngb_terr(int order, const double *q, double cc0, double cc1, const
         if (--j < 0) break;
         for (i = 0; i <= j; i++) deltmp[i] = deltmp[i + 1] + dold[i];
     }
-    factor = (order == 1) ? .5 : .08333333333;
+    factor = (order == 1) ? .5 : (gear ? .2222222222 : .08333333333);       /* gearCoeff / trapCoeff, cktterr.c:23-35 */
     a = factor * fabs(diff[0]);
     del = trtol * tol / ((abstol > a) ? abstol : a);
     if (order == 2) del = sqrt(del);
@@ -146,9 +159,9 @@ NGB_HD void ngb_lte_values(const NgbCtl *k, int s, const double *state, int nsta
     for (i = 0; i < 3; i++) dold[i] = NGB_LDG(&k->delta_old[(size_t)i * S + s]);
     for (i = 0; i < 4; i++) q[i] = (i <= order + 1 || (order == 1 && nh >= 4)) && i < nh ? LST(i, kq) : 0.0;
     /* literal orders: the difference tables unroll into registers */
-    *d1 = (order == 1) ? ngb_terr(1, q, cc0, cc1, dold, delta, k->reltol, k->abstol, k->chgtol, k->trtol)
-                       : ngb_terr(2, q, cc0, cc1, dold, delta, k->reltol, k->abstol, k->chgtol, k->trtol);
-    *d2 = (order == 1 && nh >= 4) ? ngb_terr(2, q, cc0, cc1, dold, delta, k->reltol, k->abstol, k->chgtol, k->trtol) : 1e300;
+    *d1 = (order == 1) ? ngb_terr(k->gear, 1, q, cc0, cc1, dold, delta, k->reltol, k->abstol, k->chgtol, k->trtol)
+                       : ngb_terr(k->gear, 2, q, cc0, cc1, dold, delta, k->reltol, k->abstol, k->chgtol, k->trtol);
+    *d2 = (order == 1 && nh >= 4) ? ngb_terr(k->gear, 2, q, cc0, cc1, dold, delta, k->reltol, k->abstol, k->chgtol, k->trtol) : 1e300;
 #undef LST
 }
 
@@ -170,10 +183,10 @@ void ngb_lte_state(const NgbCtl *k, int s, const double *state, int nstate, size
     const double cc0 = LST(0, kq + 1), cc1 = LST(1, kq + 1);
     for (i = 0; i < 3; i++) dold[i] = NGB_LDG(&k->delta_old[(size_t)i * S + s]);
     for (i = 0; i <= order + 1 && i < nh; i++) q[i] = LST(i, kq);
-    ngb_atomic_min_pos(&k->lte[s], ngb_terr(order, q, cc0, cc1, dold, delta, k->reltol, k->abstol, k->chgtol, k->trtol));
+    ngb_atomic_min_pos(&k->lte[s], ngb_terr(k->gear, order, q, cc0, cc1, dold, delta, k->reltol, k->abstol, k->chgtol, k->trtol));
     if (order == 1 && nh >= 4) {
         q[3] = LST(3, kq);
-        ngb_atomic_min_pos(&k->lte2[s], ngb_terr(2, q, cc0, cc1, dold, delta, k->reltol, k->abstol, k->chgtol, k->trtol));
+        ngb_atomic_min_pos(&k->lte2[s], ngb_terr(k->gear, 2, q, cc0, cc1, dold, delta, k->reltol, k->abstol, k->chgtol, k->trtol));
     }
 #undef LST
 }

@@ -329,20 +329,22 @@ NGB_HD int ngb_dio_thread(const NgbDioCtx *c, size_t t)
                 const int order = NGB_LDG(&c->ctl.order[s]);
                 const double ag0 = NGB_LDG(&c->ctl.ag0[s]), ag1 = NGB_LDG(&c->ctl.ag1[s]);
                 double q0, q1, cc, geq;
+                const int gear = c->ctl.gear;
+                const double ag2 = gear ? NGB_LDG(&c->ctl.ag2[s]) : 0.0;
                 if (order != 1 && order != 2) return NGB_E_ORDER;
                 if (mode & NGB_MODEINITTRAN) {
                     ST(1, DIOST_capCharge) = ST(0, DIOST_capCharge);
                     if (sepsw) ST(1, DIOST_capChargeSW) = ST(0, DIOST_capChargeSW);
                 }
                 q0 = ST(0, DIOST_capCharge); q1 = ST(1, DIOST_capCharge);
-                cc = ngb_integrate_trap(order, ag0, ag1, q0, q1, (order == 2) ? ST(1, DIOST_capCurrent) : 0.0);
+                cc = ngb_integrate(gear, order, ag0, ag1, ag2, q0, q1, (gear && order == 2) ? ST(2, DIOST_capCharge) : 0.0, (order == 2) ? ST(1, DIOST_capCurrent) : 0.0);
                 ST(0, DIOST_capCurrent) = cc;
                 geq = ag0 * capd;
                 gd = gd + geq;
                 cd = cd + cc;
                 if (sepsw) {
                     const double qs0 = ST(0, DIOST_capChargeSW), qs1 = ST(1, DIOST_capChargeSW);
-                    const double ccs = ngb_integrate_trap(order, ag0, ag1, qs0, qs1, (order == 2) ? ST(1, DIOST_capCurrentSW) : 0.0);
+                    const double ccs = ngb_integrate(gear, order, ag0, ag1, ag2, qs0, qs1, (gear && order == 2) ? ST(2, DIOST_capChargeSW) : 0.0, (order == 2) ? ST(1, DIOST_capCurrentSW) : 0.0);
                     ST(0, DIOST_capCurrentSW) = ccs;
                     gdsw = gdsw + ag0 * capdsw;
                     cdsw = cdsw + ccs;

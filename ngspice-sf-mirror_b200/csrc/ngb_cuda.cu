@@ -43,12 +43,14 @@ extern "C" void ngb_set_error(const char *fmt, ...);
     ngb_set_error("%s failed: %s", #call, cudaGetErrorString(e_)); return NGB_E_PANIC; } } while (0)
 
 /* ------------------------------------------------------------------ kernels */
+/* one instantiation per variant key of bsim4_variants.h plus the generic one */
+template <unsigned VK>
 __global__ void __launch_bounds__(NGB_B4_CTA, NGB_B4_MINBLOCKS)
 ngb_k_bsim4_load(const B4Ctx c, int *errflag)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)c.T) return;
-    const int e = b4_load_thread(&c, t);
+    const int e = b4_load_thread<VK>(&c, t);
     if (e) atomicMax(errflag, e);
 }
 
@@ -346,6 +348,50 @@ int ngb_dev_set_stream(void *stream)
 }
 
 static thread_local int g_capturing = 0, g_prof_force = 0;
+
+/* per-stage timing of sampled Newton steps (the steps ngb_dev_profile_due sends kernel by kernel, on one stream): an
+ * event after every stage; the time between two marks is booked on the later one */
+#define NGB_STAGE_SLOTS 8
+#define NGB_STAGE_TICKS 256
+static thread_local cudaEvent_t g_stage_ev[NGB_STAGE_TICKS][NGB_STAGE_SLOTS];
+static thread_local unsigned g_stage_mask[NGB_STAGE_TICKS];
+static thread_local int g_stage_created = 0, g_stage_cur = -1, g_stage_n = 0;
+void ngb_dev_stage_begin(void)
+{
+    g_stage_cur = -1;
+    if (!g_prof_on || !g_prof_force || g_capturing || g_stage_n >= NGB_STAGE_TICKS) return;
+    if (!g_stage_created) {
+        for (int i = 0; i < NGB_STAGE_TICKS; i++) for (int k = 0; k < NGB_STAGE_SLOTS; k++) cudaEventCreate(&g_stage_ev[i][k]);
+        g_stage_created = 1;
+    }
+    g_stage_cur = g_stage_n++;
+    g_stage_mask[g_stage_cur] = 1u;
+    cudaEventRecord(g_stage_ev[g_stage_cur][0], g_stream);
+}
+void ngb_dev_stage_mark(int slot)
+{
+    if (g_stage_cur < 0 || slot <= 0 || slot >= NGB_STAGE_SLOTS) return;
+    cudaEventRecord(g_stage_ev[g_stage_cur][slot], g_stream);
+    g_stage_mask[g_stage_cur] |= 1u << slot;
+}
+/* ms[slot] summed over the sampled steps; returns their number */
+int ngb_dev_stage_read(double ms[NGB_STAGE_SLOTS])
+{
+    if (g_stream) cudaStreamSynchronize(g_stream);
+    for (int k = 0; k < NGB_STAGE_SLOTS; k++) ms[k] = 0.0;
+    for (int i = 0; i < g_stage_n; i++) {
+        int prev = 0;
+        for (int k = 1; k < NGB_STAGE_SLOTS; k++) {
+            if (!(g_stage_mask[i] >> k & 1u)) continue;
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, g_stage_ev[i][prev], g_stage_ev[i][k]) == cudaSuccess) ms[k] += t;
+            prev = k;
+        }
+    }
+    const int n = g_stage_n;
+    g_stage_n = 0; g_stage_cur = -1;
+    return n;
+}
 int ngb_dev_profile_due(void)
 {
     if (!g_prof_on || g_prof_n >= NGB_PROF_MAX) return 0;
@@ -458,7 +504,13 @@ int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag)
     const int rec = !g_capturing && g_prof_on && g_prof_n < NGB_PROF_MAX && (g_prof_force || (g_prof_seen++ % g_prof_every == 0));
     g_prof_force = 0;
     if (rec) cudaEventRecord(g_prof_ev[2 * g_prof_n], g_cur);
-    ngb_k_bsim4_load<<<grid, NGB_B4_CTA, 0, g_cur>>>(*c, errflag);
+    {
+        int launched = 0;
+#define X(k) if (!launched && c->variant == (k)) { ngb_k_bsim4_load<(k)><<<grid, NGB_B4_CTA, 0, g_cur>>>(*c, errflag); launched = 1; }
+        NGB_B4_VARIANT_KEYS(X)
+#undef X
+        if (!launched) ngb_k_bsim4_load<NGB_B4_GENERIC><<<grid, NGB_B4_CTA, 0, g_cur>>>(*c, errflag);
+    }
     if (rec) { cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], g_cur); g_prof_n++; }
     return post_launch("bsim4_load");
 }

@@ -32,6 +32,9 @@ int   ngb_dev_profile_read(double *ms_sum, long *count);
 /* returns 1 when the sampled-launch timing wants THIS Newton step (the caller then launches it kernel by
  * kernel instead of replaying a graph) */
 int   ngb_dev_profile_due(void);
+void  ngb_dev_stage_begin(void);                /* per-stage timing of the sampled steps: see ngb_cuda.cu */
+void  ngb_dev_stage_mark(int slot);
+int   ngb_dev_stage_read(double ms[8]);
 int   ngb_dev_fp64_peak(double out[3]);     /* measured DFMA and DADD/DMUL flop/s of this GPU */
 /* CUDA graph of one Newton step: begin capture on the launch stream, end + instantiate, replay */
 int   ngb_dev_graph_begin(void);

@@ -31,6 +31,8 @@ int ngbSetStream(void *cuda_stream) { return ngb_dev_set_stream(cuda_stream); }
 int ngbSync(void) { return ngb_dev_sync(); }
 void ngbProfile(int enable, int every) { ngb_dev_profile(enable, every); }
 int ngbProfileRead(double *ms_sum, long *count) { return ngb_dev_profile_read(ms_sum, count); }
+int ngbProfileStages(double ms[8]) { return ngb_dev_stage_read(ms); }
+static unsigned b4_batch_key(const ngb_circuit *c, const double *mtab, int nrows, const int *prow_inst);
 int ngbMeasureFp64Peak(double out[3]) { return ngb_dev_fp64_peak(out); }
 
 /* ------------------------------------------------------------------ field names */
@@ -213,8 +215,9 @@ int ngbCircuitSetOptions(ngb_circuit *c, const double d[15], const int i[5])
     o->temp = d[5]; o->vt0 = d[6]; o->xmu = d[7]; o->tstep = d[8]; o->tstop = d[9]; o->tmax = d[10];
     o->tstart = d[11]; o->delmin = d[12]; o->minbreak = d[13]; o->gmin = d[14];
     o->method = i[0]; o->maxorder = i[1]; o->itl4 = i[2]; o->itl1 = i[3]; o->uic = i[4];
-    if (o->method != NGB_TRAPEZOIDAL) { ngb_set_error("integration method %d not supported (TRAP only)", o->method); return NGB_E_METHOD; }
-    if (o->maxorder > 2) { ngb_set_error("maxord %d not supported with TRAP", o->maxorder); return NGB_E_ORDER; }
+    if (o->method != NGB_TRAPEZOIDAL && o->method != NGB_GEAR) { ngb_set_error("integration method %d unknown (1 TRAPEZOIDAL, 2 GEAR)", o->method); return NGB_E_METHOD; }
+    /* DCtran never raises CKTorder above 2 (dctran.c:794-826), so maxord > 2 only lengthens the state ring (cktsetup.c:192) */
+    if (o->maxorder > 2) { ngb_set_error("maxord %d not supported (the state ring holds maxord + 2 <= 4 vectors)", o->maxorder); return NGB_E_ORDER; }
     return NGB_OK;
 }
 
@@ -1534,6 +1537,8 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
     k->err = (int *)dalloc(b, "ctl.err", sizeof(int) * (size_t)S);
     k->ag0 = (double *)dalloc(b, "ctl.ag0", sizeof(double) * (size_t)S);
     k->ag1 = (double *)dalloc(b, "ctl.ag1", sizeof(double) * (size_t)S);
+    k->ag2 = (double *)dalloc(b, "ctl.ag2", sizeof(double) * (size_t)S);
+    if (k->ag2) ngb_dev_memset(k->ag2, 0, sizeof(double) * (size_t)S);
     k->delta = (double *)dalloc(b, "ctl.delta", sizeof(double) * (size_t)S);
     k->delta_old = (double *)dalloc(b, "ctl.delta_old", sizeof(double) * 7 * (size_t)S);
     k->time = (double *)dalloc(b, "ctl.time", sizeof(double) * (size_t)S);
@@ -1547,6 +1552,7 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
     if (k->lusel) ngb_dev_memset(k->lusel, 0, sizeof(int) * (size_t)S);
     k->nhist = c->opt.maxorder + 2;
     if (k->nhist > NGB_NHIST) k->nhist = NGB_NHIST;
+    k->gear = c->opt.method == NGB_GEAR;
     k->reltol = c->opt.reltol; k->abstol = c->opt.abstol; k->chgtol = c->opt.chgtol; k->trtol = c->opt.trtol;
     {
         int *one = (int *)xcalloc((size_t)S, sizeof(int)); double *dv = (double *)xcalloc((size_t)S, sizeof(double));
@@ -1586,6 +1592,8 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
         b->b4_state = (double *)dalloc(b, "b4.state", sizeof(double) * NGB_NHIST * B4ST_COUNT * T);
         b->b4_op = (double *)dalloc(b, "b4.op", sizeof(double) * B4O_COUNT * T);
         b->b4_mtab = (double *)dev_dup(c->b4_mtab, sizeof(double) * (size_t)c->b4_nrows * B4M_COUNT);
+        b->b4_key = b4_batch_key(c, c->b4_mtab, c->b4_nrows, c->b4_prow);
+        { const char *e = getenv("NGB_B4_GENERIC"); b->b4_force_generic = (e && atoi(e)) ? 1 : 0; }
         b->b4_ptab = (double *)dev_dup(c->b4_ptab, sizeof(double) * (size_t)c->b4_nrows * B4P_COUNT);
         reg(b, "b4.mtab", b->b4_mtab, sizeof(double) * (size_t)c->b4_nrows * B4M_COUNT);
         reg(b, "b4.ptab", b->b4_ptab, sizeof(double) * (size_t)c->b4_nrows * B4P_COUNT);
@@ -1852,8 +1860,44 @@ int ngbBatchSetBsim4Rows(ngb_batch *b, const int *prow_t, int nrows, const doubl
     b->b4_prow_t = (int *)dev_dup(prow_t, sizeof(int) * T);
     b->b4_mtab = (double *)dev_dup(mtab, sizeof(double) * (size_t)nrows * B4M_COUNT);
     b->b4_ptab = (double *)dev_dup(ptab, sizeof(double) * (size_t)nrows * B4P_COUNT);
+    b->b4_key = b4_batch_key(b->c, mtab, nrows, NULL);
     return (b->b4_prow_t && b->b4_mtab && b->b4_ptab) ? NGB_OK : NGB_E_PANIC;
 }
+
+/* the variant key of a batch (bsim4_variants.h): the selectors of every model row in use and of every instance must agree */
+static unsigned b4_batch_key(const ngb_circuit *c, const double *mtab, int nrows, const int *prow_inst)
+{
+    unsigned key = NGB_B4_GENERIC;
+    int i, first = 1;
+    if (!c->b4_n) return key;
+    for (i = 0; i < (prow_inst ? c->b4_n : nrows); i++) {
+        const double *M = mtab + (size_t)(prow_inst ? prow_inst[i] : i) * B4M_COUNT;
+        const int fl = c->b4_flags[prow_inst ? i : 0];
+        const int v[13] = { (int)M[B4M_mobMod], (int)M[B4M_capMod], (int)M[B4M_cvchargeMod], (int)M[B4M_dioMod], (int)M[B4M_rdsMod],
+                            (int)M[B4M_igcMod], (int)M[B4M_igbMod], (int)M[B4M_gidlMod], (int)M[B4M_tempMod], (int)M[B4M_mtrlMod],
+                            (int)M[B4M_mtrlCompatMod], B4F_RBODY(fl), B4F_RGATE(fl) };
+        unsigned k;
+        if (!(B4K_FITS(mobMod, v[0]) && B4K_FITS(capMod, v[1]) && B4K_FITS(cvchargeMod, v[2]) && B4K_FITS(dioMod, v[3]) &&
+              B4K_FITS(rdsMod, v[4]) && B4K_FITS(igcMod, v[5]) && B4K_FITS(igbMod, v[6]) && B4K_FITS(gidlMod, v[7]) &&
+              B4K_FITS(tempMod, v[8]) && B4K_FITS(mtrlMod, v[9]) && B4K_FITS(mtrlCompatMod, v[10]))) return NGB_B4_GENERIC;
+        k = NGB_B4_KEY(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], c->opt.method == NGB_GEAR);
+        if (first) { key = k; first = 0; }
+        else if (k != key) return NGB_B4_GENERIC;
+    }
+    if (!prow_inst)          /* per-thread rows: the flags are still per instance */
+        for (i = 1; i < c->b4_n; i++)
+            if (B4F_RBODY(c->b4_flags[i]) != B4F_RBODY(c->b4_flags[0]) || B4F_RGATE(c->b4_flags[i]) != B4F_RGATE(c->b4_flags[0])) return NGB_B4_GENERIC;
+    return key;
+}
+/* which BSIM4 load kernel the batch runs: key[0] = the batch's variant key (0xffffffff: instances differ), key[1] = 1 when
+ * the library carries a specialised instantiation for it and it is in use */
+int ngbBatchBsim4Variant(ngb_batch *b, unsigned key[2])
+{
+    key[0] = b->b4_key;
+    key[1] = (b->b4_key != NGB_B4_GENERIC && !b->b4_force_generic && b4_variant_built(b->b4_key)) ? 1u : 0u;
+    return NGB_OK;
+}
+void ngbBatchSetBsim4Generic(ngb_batch *b, int on) { b->b4_force_generic = on ? 1 : 0; }
 
 /* ------------------------------------------------------------------ hot path launches */
 void ngb_fill_b4ctx(ngb_batch *b, B4Ctx *x)
@@ -1863,6 +1907,7 @@ void ngb_fill_b4ctx(ngb_batch *b, B4Ctx *x)
     x->ninst = c->b4_n; x->S = b->S; x->T = c->b4_n * b->S;
     x->mtab = b->b4_mtab; x->ptab = b->b4_ptab;
     x->prow = b->b4_prow_t ? b->b4_prow_t : b->b4_prow; x->prow_per_thread = b->b4_prow_t ? 1 : 0;
+    x->variant = (!b->b4_force_generic && b4_variant_built(b->b4_key)) ? b->b4_key : NGB_B4_GENERIC;
     x->inst = b->b4_inst; x->flags = b->b4_flags; x->nodes = b->b4_nodes; x->spos = b->b4_spos;
     x->stamp = b->stamp; x->state = b->b4_state; x->op = b->b4_op; x->op_full = b->op_full;
     x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl; x->temp = c->opt.temp; x->vt0 = c->opt.vt0;
@@ -1954,12 +1999,15 @@ int ngb_enqueue_load(ngb_batch *b)
     if (!r && c->cap_n) { NgbCapCtx x; ngb_dev_branch(3); ngb_fill_capctx(b, &x); r = ngb_launch_cap_load(&x, b->errflag); }
     if (!r && c->is_n) { NgbSrcCtx x; ngb_dev_branch(3); ngb_fill_srcctx(b, &x, 1); r = ngb_launch_src_load(&x); }
     if (!r && c->vs_n) { NgbSrcCtx x; ngb_dev_branch(3); ngb_fill_srcctx(b, &x, 0); r = ngb_launch_src_load(&x); }
+    ngb_dev_stage_mark(1);
     if (!r && c->b4_n) { B4Ctx x; ngb_dev_branch(-1); ngb_fill_b4ctx(b, &x); r = ngb_launch_bsim4_load(&x, b->errflag); }
     {
         const int rj = ngb_dev_branch_end();
         if (r || rj) return r ? r : rj;
     }
+    ngb_dev_stage_mark(2);
     { NgbAsmCtx x; ngb_fill_asmctx(b, &x); if ((r = ngb_launch_assemble(&x))) return r; }
+    ngb_dev_stage_mark(3);
     return NGB_OK;
 }
 

@@ -77,7 +77,11 @@ NGB_HD int ngb_cap_thread(const NgbCapCtx *c, size_t t)
                 if (mode & NGB_MODEINITTRAN) CST(1, 0) = q0;
             }
             q1 = CST(1, 0);
-            cc = ngb_integrate_trap(order, ag0, ag1, q0, q1, (order == 2) ? CST(1, 1) : 0.0);
+            {
+                const int gear = c->ctl.gear;
+                cc = ngb_integrate(gear, order, ag0, ag1, gear ? NGB_LDG(&c->ctl.ag2[s]) : 0.0, q0, q1,
+                                   (gear && order == 2) ? CST(2, 0) : 0.0, (order == 2) ? CST(1, 1) : 0.0);
+            }
             CST(0, 1) = cc;
             ceq = cc - ag0 * q0;
             geq = ag0 * cap;
@@ -283,7 +287,15 @@ NGB_HD void ngb_asm_thread(const NgbAsmCtx *c, size_t u)
 #ifdef __CUDA_ARCH__
     if (hi - lo > NGB_ASM_LONG && c->nlong) return;       /* ngb_asm_long_group's job */
 #endif
-    for (int p = lo; p < hi; p++)
+    /* a gather: four independent loads in flight, added in list order (the summation order is the contract) */
+    int p = lo;
+    for (; p + 4 <= hi; p += 4) {
+        const int r0 = NGB_LDG(&c->tgt_rows[p]), r1 = NGB_LDG(&c->tgt_rows[p + 1]), r2 = NGB_LDG(&c->tgt_rows[p + 2]), r3 = NGB_LDG(&c->tgt_rows[p + 3]);
+        const double a0 = NGB_LDG(&c->stamp[(size_t)r0 * S + s]), a1 = NGB_LDG(&c->stamp[(size_t)r1 * S + s]);
+        const double a2 = NGB_LDG(&c->stamp[(size_t)r2 * S + s]), a3 = NGB_LDG(&c->stamp[(size_t)r3 * S + s]);
+        acc += a0; acc += a1; acc += a2; acc += a3;
+    }
+    for (; p < hi; p++)
         acc += NGB_LDG(&c->stamp[(size_t)NGB_LDG(&c->tgt_rows[p]) * S + s]);
     ngb_asm_store(c, tg, s, acc);
 }

@@ -211,6 +211,7 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
 static int enqueue_tick_direct(ngb_batch *b, int with_lu)
 {
     int r;
+    ngb_dev_stage_begin();
     if ((r = ngb_enqueue_load(b))) return r;
     if (with_lu) {
         const int *ev = b->tran->x.lu_event;
@@ -228,13 +229,17 @@ static int enqueue_tick_direct(ngb_batch *b, int with_lu)
             lx.V = NULL;                       /* fused factor+solve: the factors never leave shared memory */
             if ((r = ngb_launch_lu(&lx))) return r;
         }
+        ngb_dev_stage_mark(4);
     }
     if (with_lu && b->lte_deferred && b->c->b4_n) {     /* BSIM4trunc for the samples whose iteration can have converged */
         B4Ctx x;
         ngb_fill_b4ctx(b, &x);
         if ((r = ngb_launch_bsim4_lte(&x))) return r;
+        ngb_dev_stage_mark(5);
     }
-    return ngb_launch_tran_control(&b->tran->x);
+    r = ngb_launch_tran_control(&b->tran->x);
+    ngb_dev_stage_mark(6);
+    return r;
 }
 
 

@@ -148,9 +148,37 @@ NGB_HD int ngb_set_break(const NgbTranCtx *c, int s, double time, double now)
     return NGB_OK;
 }
 
-/* NIcomCof, TRAPEZOIDAL */
+/* NIcomCof (nicomcof.c:20-121): TRAPEZOIDAL in closed form; GEAR solves the (order+1)-square system the reference
+ * sets up -- powers of (sum of the last steps)/delta -- by the same elimination, in the same order */
 NGB_HD void ngb_comcof(const NgbTranCtx *c, int s, int order, double delta)
 {
+    if (c->ctl.gear) {
+        double mat[3][3] = { { 0 } }, ag[3] = { 0, 0, 0 }, arg = 0, arg1;
+        int i, j, k;
+        const int S = c->S;
+        ag[1] = -1 / delta;
+        for (i = 0; i <= order; i++) mat[0][i] = 1;
+        for (i = 1; i <= order; i++) mat[i][0] = 0;
+        for (i = 1; i <= order; i++) {
+            arg += c->ctl.delta_old[(size_t)(i - 1) * S + s];
+            arg1 = 1;
+            for (j = 1; j <= order; j++) { arg1 *= arg / delta; mat[j][i] = arg1; }
+        }
+        for (i = 1; i <= order; i++)
+            for (j = i + 1; j <= order; j++) {
+                mat[j][i] /= mat[i][i];
+                for (k = i + 1; k <= order; k++) mat[j][k] -= mat[j][i] * mat[i][k];
+            }
+        for (i = 1; i <= order; i++)
+            for (j = i + 1; j <= order; j++) ag[j] = ag[j] - mat[j][i] * ag[i];
+        ag[order] /= mat[order][order];
+        for (i = order - 1; i >= 0; i--) {
+            for (j = i + 1; j <= order; j++) ag[i] = ag[i] - mat[i][j] * ag[j];
+            ag[i] /= mat[i][i];
+        }
+        c->ctl.ag0[s] = ag[0]; c->ctl.ag1[s] = ag[1]; c->ctl.ag2[s] = ag[2];
+        return;
+    }
     if (order == 1) {
         c->ctl.ag0[s] = 1 / delta;
         c->ctl.ag1[s] = -1 / delta;

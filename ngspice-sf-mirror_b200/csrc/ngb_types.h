@@ -29,6 +29,7 @@ typedef struct NgbCtl {
     int *xsel;            /* which x buffer is CKTrhsOld (pointer SWAP of niiter.c:362)  */
     int *err;             /* sticky NGB_E_* per sample                                  */
     double *ag0, *ag1;    /* CKTag[0..1]                                                */
+    double *ag2;          /* CKTag[2]: GEAR order 2 (nicomcof.c:52-121)                  */
     double *delta;        /* CKTdelta                                                   */
     double *delta_old;    /* CKTdeltaOld[7][S]                                          */
     double *time;         /* CKTtime                                                    */
@@ -43,6 +44,7 @@ typedef struct NgbCtl {
                              1 = the re-pivoting of the first transient iteration (niiter.c:107-111)   */
     /* shared scalars */
     int nhist;            /* state vectors in the ring: CKTmaxOrder + 2 (cktsetup.c:192)  */
+    int gear;             /* CKTintegrateMethod == GEAR                                   */
     double reltol, abstol, chgtol, trtol;
 } NgbCtl;
 

@@ -473,7 +473,9 @@ NGB_HD int vbic_load_thread(const NgbVbicCtx *c, size_t t)
 
     const int order = NGB_LDG(&c->ctl.order[s]);
     const double ag0 = NGB_LDG(&c->ctl.ag0[s]), ag1 = NGB_LDG(&c->ctl.ag1[s]);
-#define INTEGRATE(q) ngb_integrate_trap(order, ag0, ag1, VST(0, q), VST(1, q), (order == 2) ? VST(1, (q) + 1) : 0.0)
+    const int gear = c->ctl.gear;
+    const double ag2 = gear ? NGB_LDG(&c->ctl.ag2[s]) : 0.0;
+#define INTEGRATE(q) ngb_integrate(gear, order, ag0, ag1, ag2, VST(0, q), VST(1, q), (gear && order == 2) ? VST(2, q) : 0.0, (order == 2) ? VST(1, (q) + 1) : 0.0)
     if ((mode & (NGB_MODEDCTRANCURVE | NGB_MODETRAN | NGB_MODEAC)) || ((mode & NGB_MODETRANOP) && (mode & NGB_MODEUIC)) ||
         (mode & NGB_MODEINITSMSIG)) {
         VST(0, VBS_qbe) = o.Qbe.v;   VST(0, VBS_qbex) = o.Qbex.v; VST(0, VBS_qbc) = o.Qbc.v; VST(0, VBS_qbcx) = o.Qbcx.v;

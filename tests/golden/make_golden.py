@@ -309,7 +309,7 @@ def run(name, netlist, calls, save):
     os.makedirs(TMP, exist_ok=True)
     cir = os.path.join(TMP, name + ".cir")
     open(cir, "w").write(netlist)
-    if name in ("ro17", "ro101", "ro17k", "inv", "dio", "b3ring", "arr", "vbic", "mix", "latch", "srcs", "mixsrc", "invsrc", "invgmin", "invshunt"):
+    if name in ("ro17", "ro101", "ro17k", "ro17kg", "invg", "inv", "dio", "b3ring", "arr", "vbic", "mix", "latch", "srcs", "mixsrc", "invsrc", "invgmin", "invshunt"):
         # the netlist itself is kept too: the CPU-baseline arm of bench.py feeds it to oracle/_ref/ngspice
         os.makedirs(os.path.join(HERE, "netlists"), exist_ok=True)
         open(os.path.join(HERE, "netlists", name + ".cir"), "w").write(netlist)
@@ -400,6 +400,14 @@ if __name__ == "__main__":
         run("ro17", ro_netlist(17), "0-3,100,101,5000,5001", ["18", "2", "9", "vdd#branch"])
     if "ro17k" in which:
         run("ro17k", ro_netlist(17, tran=".tran .1ns 20ns uic", kick=True), "1,2", ["18", "2", "9", "vdd#branch"])
+    if "gear" in which:
+        # `.option method=gear` (NIcomCof / NIintegrate / CKTterr GEAR branches: nicomcof.c:52-121, niinteg.c:42-71, cktterr.c:61)
+        gear = lambda n: n.replace(".option", ".option method=gear", 1)
+        run("ro17kg", gear(ro_netlist(17, tran=".tran .1ns 20ns uic", kick=True)), "1,2", ["18", "2", "9", "vdd#branch"])
+        run("invg", gear(inv_netlist()), "0-3", ["out", "in", "vdd#branch", "vin#branch"])
+        run("diog", gear(dio_netlist()), "0-3", ["out", "z", "w", "u", "vin#branch"])
+        run("b3ringg", gear(b3_netlist(5)), "0-3", ["out", "buf", "n2", "vdd#branch"])
+        run("mixg", gear(mix_netlist(*MIX_POINTS[0])), "0-3", ["a8", "x", "y4", "cq", "e2", "vdd#branch", "v33#branch"])
     if "ro17kmeas" in which:
         run_meas("ro17k", ro_netlist(17, tran=".tran .1ns 20ns uic", kick=True))
     if "ro17mc" in which:

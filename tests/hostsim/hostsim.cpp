@@ -28,6 +28,9 @@ int ngb_dev_set_stream(void *) { return 0; }
 void ngb_dev_profile(int, int) {}
 int ngb_dev_profile_read(double *ms, long *n) { if (ms) *ms = 0; if (n) *n = 0; return 0; }
 int ngb_dev_profile_due(void) { return 0; }
+void ngb_dev_stage_begin(void) {}
+void ngb_dev_stage_mark(int) {}
+int ngb_dev_stage_read(double *ms) { for (int k = 0; k < 8; k++) ms[k] = 0; return 0; }
 int ngb_dev_fp64_peak(double out[3]) { out[0] = out[1] = out[2] = 0; return NGB_E_PANIC; }
 int ngb_dev_branch_begin(void) { return 0; }
 void ngb_dev_branch(int) {}
@@ -40,7 +43,7 @@ void ngb_dev_graph_destroy(void *) {}
 int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag)
 {
     g_launches++;
-    for (size_t t = 0; t < (size_t)c->T; t++) { int e = b4_load_thread(c, t); if (e && errflag && !errflag[0]) errflag[0] = e; }
+    for (size_t t = 0; t < (size_t)c->T; t++) { int e = b4_load_thread_variant(c, t); if (e && errflag && !errflag[0]) errflag[0] = e; }
     return 0;
 }
 int ngb_launch_bsim4_lte(const B4Ctx *c)

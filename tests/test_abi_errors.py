@@ -33,10 +33,11 @@ def test_pwl_source_needs_its_corner_list(hostsim_lib):
     _fails(hostsim_lib, flat, 1, "has no corner list")
 
 
-def test_gear_and_high_order_refused(hostsim_lib):
-    """NIintegrate's GEAR branch (niinteg.c:52-76) and TRAP orders above 2 are not on this path"""
+def test_unknown_method_and_high_order_refused(hostsim_lib):
+    """integration methods other than TRAPEZOIDAL / GEAR do not exist (niinteg.c:76); orders above 2 are never taken by
+    DCtran (dctran.c:794-826) and maxord > 2 would only lengthen the state ring"""
     flat = _flat("inv")
-    flat["opt/method"][...] = 2
+    flat["opt/method"][...] = 3
     _fails(hostsim_lib, flat, 105, "method")
     flat = _flat("inv")
     flat["opt/maxorder"][...] = 3

@@ -48,6 +48,40 @@ def test_tran_hostsim_bit_identical(hostsim_lib, name):
     _compare(res, t, v, wave, 0, exact=True)
 
 
+@pytest.mark.parametrize("name", ["ro17kg", "invg", "diog", "b3ringg"])
+def test_tran_hostsim_gear_bit_identical(hostsim_lib, name):
+    """`.option method=gear`: NIcomCof's GEAR system, NIintegrate's accumulation and CKTterr's GEAR coefficients
+    (nicomcof.c:52-121, niinteg.c:42-71, cktterr.c:23-62) for BSIM4, BSIM3, diodes and capacitors"""
+    res, t, v, wave = _run(hostsim_lib, name)
+    _compare(res, t, v, wave, 0, exact=True)
+
+
+def test_tran_hostsim_gear_mix_cell(hostsim_lib):
+    """GEAR on the cell with every model family (VBIC: 1e-9, see test_tran_hostsim_vbic)"""
+    res, t, v, wave = _run(hostsim_lib, "mixg")
+    _compare(res, t, v, wave, 0, exact=False)
+
+
+def test_bsim4_variant_kernels_same_bits(hostsim_lib):
+    """the load specialised on the model selectors (csrc/bsim4_variants.h) and the generic one: same accepted points, same bits.
+    The GEAR run of the same card has no specialised instantiation and reports so"""
+    outs = []
+    for generic in (False, True):
+        flat = ngt.read(f"{GOLDEN}/ro17k.flat.ngt"); trace = ngt.read(f"{GOLDEN}/ro17k.trace.ngt.gz"); wave = ngt.read(f"{GOLDEN}/ro17k.wave.ngt")
+        circ = pkg.Circuit.from_flat(hostsim_lib, flat, lu_pattern=run_patterns(trace))
+        b = pkg.Batch(circ, 2)
+        b.set_bsim4_generic(generic)
+        key, special = b.bsim4_variant()
+        assert key != 0xffffffff and special == (not generic)
+        res = b.tran(8192, wave["save_eq"])
+        outs.append((res.accepted.copy(), res.numiter.copy()) + res.waves())
+        _compare(res, outs[-1][2], outs[-1][3], wave, 1, exact=True)
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
+    flat = ngt.read(f"{GOLDEN}/ro17kg.flat.ngt"); trace = ngt.read(f"{GOLDEN}/ro17kg.trace.ngt.gz")
+    b = pkg.Batch(pkg.Circuit.from_flat(hostsim_lib, flat, lu_pattern=run_patterns(trace)), 1)
+    assert b.bsim4_variant()[1] is False
+
+
 @pytest.mark.parametrize("name", ["invsrc", "invgmin"])
 def test_tran_hostsim_fallback_batch(hostsim_lib, name):
     """the `.option noopiter` start state is set up for every sample of a batch, not only the first"""
@@ -293,6 +327,33 @@ def test_tran_gpu_matches_reference(cuda_lib, name, exact):
     _compare(res, t, v, wave, 0, exact=False)
     if exact:
         _compare(res, t, v, wave, 0, exact=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ro17kg", "invg", "diog", "b3ringg", "mixg"])
+def test_tran_gpu_gear_matches_reference(cuda_lib, name):
+    """`.option method=gear` on the device (1e-9, identical step and iteration counts); these runs also take the GENERIC
+    BSIM4 load kernel (no specialised instantiation carries gear = 1)"""
+    res, t, v, wave = _run(cuda_lib, name)
+    _compare(res, t, v, wave, 0, exact=False)
+
+
+@pytest.mark.gpu
+def test_bsim4_variant_kernels_same_bits_gpu(cuda_lib):
+    """specialised against generic load kernel on the device: bit-identical waveforms for 64 mismatch samples"""
+    flat = ngt.read(f"{GOLDEN}/ro17k.flat.ngt"); trace = ngt.read(f"{GOLDEN}/ro17k.trace.ngt.gz"); wave = ngt.read(f"{GOLDEN}/ro17k.wave.ngt")
+    circ = pkg.Circuit.from_flat(cuda_lib, flat, lu_pattern=run_patterns(trace))
+    dv = pkg.mc.draw_delvto(64, 34, seed=11)
+    outs = []
+    for generic in (False, True):
+        b = pkg.Batch(circ, 64)
+        b.put("b4.inst", pkg.mc.bsim4_inst_with_delvto(cuda_lib, flat, dv))
+        b.set_bsim4_generic(generic)
+        assert b.bsim4_variant()[1] == (not generic)
+        res = b.tran(2048, wave["save_eq"])
+        assert (res.err == 0).all()
+        outs.append((res.accepted.copy(), res.rejected.copy(), res.numiter.copy()) + res.waves())
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
 
 
 @pytest.mark.gpu
