@@ -499,17 +499,21 @@ static int post_launch(const char *what)
 int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag)
 {
     if (c->T <= 0) return 0;
-    const unsigned grid = (unsigned)(((size_t)c->T + NGB_B4_CTA - 1) / NGB_B4_CTA);
+    /* the kernel is bound by per-warp latency, not throughput: a batch that does not fill the GPU with 256-thread CTAs
+     * (fewer than two per SM) is spread over all SMs in smaller ones -- fewer warps share an SM's L1 and instruction cache */
+    int cta = NGB_B4_CTA;
+    while (cta > 64 && ((size_t)c->T + cta - 1) / cta < 2 * (size_t)g_sm_count) cta >>= 1;
+    const unsigned grid = (unsigned)(((size_t)c->T + cta - 1) / cta);
     /* sampled timing: forced by ngb_dev_profile_due (transient driver) or by this launch's own turn */
     const int rec = !g_capturing && g_prof_on && g_prof_n < NGB_PROF_MAX && (g_prof_force || (g_prof_seen++ % g_prof_every == 0));
     g_prof_force = 0;
     if (rec) cudaEventRecord(g_prof_ev[2 * g_prof_n], g_cur);
     {
         int launched = 0;
-#define X(k) if (!launched && c->variant == (k)) { ngb_k_bsim4_load<(k)><<<grid, NGB_B4_CTA, 0, g_cur>>>(*c, errflag); launched = 1; }
+#define X(k) if (!launched && c->variant == (k)) { ngb_k_bsim4_load<(k)><<<grid, cta, 0, g_cur>>>(*c, errflag); launched = 1; }
         NGB_B4_VARIANT_KEYS(X)
 #undef X
-        if (!launched) ngb_k_bsim4_load<NGB_B4_GENERIC><<<grid, NGB_B4_CTA, 0, g_cur>>>(*c, errflag);
+        if (!launched) ngb_k_bsim4_load<NGB_B4_GENERIC><<<grid, cta, 0, g_cur>>>(*c, errflag);
     }
     if (rec) { cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], g_cur); g_prof_n++; }
     return post_launch("bsim4_load");

@@ -8,7 +8,10 @@ lib = pkg.library()
 flat = ngt.read(f"{GOLDEN}/ro17k.flat.ngt"); trace = ngt.read(f"{GOLDEN}/ro17k.trace.ngt.gz"); wave = ngt.read(f"{GOLDEN}/ro17k.wave.ngt")
 circ = pkg.Circuit.from_flat(lib, flat, lu_pattern=first_pattern(trace))
 b = pkg.Batch(circ, S)
+import os
 dv = pkg.mc.draw_delvto(S, 34, seed=5)
+if os.environ.get("NGB_DV0"):
+    dv = dv * 0.0
 b.put("b4.inst", pkg.mc.bsim4_inst_with_delvto(lib, flat, dv))
 t0 = time.time(); res = b.tran(1024, wave["save_eq"][:1]); dt = time.time() - t0
 print(f"S={S} ticks {res.ticks} time {dt:.3f}s us/tick {dt / res.ticks * 1e6:.1f} iters {int(res.numiter.astype(np.int64).sum())} "
