@@ -193,6 +193,51 @@ def cpu_reference_run(workload, nproc, samples_per_proc, seed0=1000, draws=None,
     return evals / wall, nsamp / wall, wall, f"{nsamp} full transients ({samples_per_proc} per process x {nproc} processes)", raws
 
 
+def measure_when(t, v, kind, count, val, td):
+    """com_measure_when for one real vector against a constant (src/frontend/com_measure2.c:455-660): the checker's
+    restatement, applied to the REFERENCE's waveforms"""
+    first = 0; section = -1; rise = fall = 0
+    pv = pt = 0.0
+    for scale, value in zip(t, v):
+        if scale < td:
+            continue
+        if first == 1:
+            rise = fall = 0
+            if value < val:
+                section = 0
+                if pv >= val:
+                    fall = 1
+            else:
+                section = 1
+                if pv < val:
+                    rise = 1
+        if first > 1:
+            if section == 0 and value >= val:
+                section = 1; rise += 1
+            elif section == 1 and value <= val:
+                section = 0; fall += 1
+            have = rise if kind == 0 else (fall if kind == 1 else rise + fall)
+            if have == count:
+                return pt + (val - pv) * (scale - pt) / (value - pv)
+        first += 1
+        pv, pt = value, scale
+    return float("nan")
+
+
+def meas_check(raws, tdiff_gpu, out_name, clauses):
+    worst = 0.0; same = True
+    for k, raw in enumerate(raws):
+        t, vecs = read_rawfile(raw, [out_name])
+        m = [measure_when(t, vecs[out_name], c[1], c[2], c[3], c[4]) for c in clauses]
+        ref = m[1] - m[0]
+        got = float(tdiff_gpu[k])
+        if not (ref == got or (np.isnan(ref) and np.isnan(got))):
+            same = False
+            worst = max(worst, abs(got - ref) / abs(ref) if ref == ref and ref != 0 else float("inf"))
+    return {"meas": "tdiff = TRIG v(out) VAL=0.5 RISE=10 TARG RISE=20 (ro_17_4.cir:54), device-side", "meas_identical": same,
+            "meas_max_rel_err": worst}
+
+
 def parity_check(raws, t_gpu, v_gpu, npoints, out_name):
     """the reference's rawfiles against the GPU waveforms of the same draws: identical number of accepted time points
     and, per point, |t - t_ref| and |v - v_ref| within 1e-9 * max(|ref|, vntol-scale) (SURVEY.md section 8(d));
@@ -329,18 +374,26 @@ def bench_ours(args):
     h2d_bytes = pinned.numel() * 8
     if args.workload != "ro101":
         h2d_bytes += prow_t.nbytes + mtab_all.nbytes + ptab_all.nbytes
-    d2h_bytes = (out_t.numel() + out_v.numel()) * 8
+    # what the example asks of every run (examples/mos/ro_17_4.cir:54): `meas tran tdiff TRIG v(18) VAL=0.5 RISE=10 TARG
+    # v(18) VAL=0.5 RISE=20`.  The end-to-end pass evaluates it on the device while the points are produced
+    # (ngbTranSetMeasures) and reads back two doubles per sample; no waveform is stored or copied in that pass
+    meas_clauses = [(int(save_eq[0]), 0, 10, 0.5, 0.0), (int(save_eq[0]), 0, 20, 0.5, 0.0)]
+    meas_out = torch.empty((2, S), dtype=torch.float64).pin_memory()
+    d2h_bytes = meas_out.numel() * 8
+    tdiff = [None]
 
     def step(e2e):
         if e2e:
             batch.put("b4.inst", pinned.numpy())
             if args.workload != "ro101":
                 batch.set_bsim4_rows(prow_t, mtab_all, ptab_all)
-        res = batch.tran(max_points, save_eq)
-        if e2e:
-            lib.check(lib.L.ngbTranWaves(batch.h, ctypes.cast(out_t.data_ptr(), ctypes.POINTER(ctypes.c_double)),
-                                         ctypes.cast(out_v.data_ptr(), ctypes.POINTER(ctypes.c_double))), "ngbTranWaves")
-        return res
+            batch.set_measures(meas_clauses)
+            res = batch.tran(0, [])
+            lib.check(lib.L.ngbTranMeasures(batch.h, ctypes.cast(meas_out.data_ptr(), ctypes.POINTER(ctypes.c_double))), "ngbTranMeasures")
+            tdiff[0] = meas_out.numpy()[1] - meas_out.numpy()[0]
+            batch.set_measures([])
+            return res
+        return batch.tran(max_points, save_eq)
 
     def barrier():
         if world > 1:
@@ -380,6 +433,11 @@ def bench_ours(args):
     with ClockSampler(local) as clk:
         ms, wall, iters, ticks, launches, prof, res, failed, cut = timed(False, True)
     clocks = clk.summary()
+    # the waveforms of the device-timed pass are what the parity check compares with the reference's rawfiles (read
+    # back here, outside both timed regions)
+    lib.check(lib.L.ngbTranWaves(batch.h, ctypes.cast(out_t.data_ptr(), ctypes.POINTER(ctypes.c_double)),
+                                 ctypes.cast(out_v.data_ptr(), ctypes.POINTER(ctypes.c_double))), "ngbTranWaves")
+    npoints_wave = res.npoints.copy()
     ms_e2e, wall_e2e, iters_e2e, _, _, _, res_e2e, failed_e2e, _ = timed(True, False)
 
     # max over ranks of the device time; totals over ranks
@@ -390,19 +448,14 @@ def bench_ours(args):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(ww, op=dist.ReduceOp.SUM)
-        # result waveforms gathered over NCCL/NVLink (the only collective on this path)
-        dv_ptr = lib.L.ngbTranDevWaves(batch.h, 1)
+        # the measurement results gathered over NCCL/NVLink (the only collective on this path, off the timed region)
         gathered = None
         try:
-            class _Arr:
-                pass
-            a = _Arr()
-            a.__cuda_array_interface__ = {"shape": (S, max_points), "typestr": "<f8", "data": (int(dv_ptr), False), "version": 3}
-            wv = torch.as_tensor(a, device="cuda")
+            wv = torch.from_numpy(np.ascontiguousarray(tdiff[0])).to("cuda")
             lst = [torch.empty_like(wv) for _ in range(world)] if rank == 0 else None
             dist.gather(wv, lst, dst=0)
-            gathered = True
-        except Exception as e:                         # the gather is off the timed path; report but do not fail the bench
+            gathered = True if rank != 0 else int(sum(int(torch.isfinite(x).sum()) for x in lst))   # samples with a period measured
+        except Exception as e:                         # report but do not fail the bench
             gathered = str(e)
     ms_max, ms_e2e_max = tt.tolist()
     iters_tot, iters_e2e_tot, samples_tot, failed_tot, cut_tot, samples_e2e_tot = ww.tolist()
@@ -429,7 +482,10 @@ def bench_ours(args):
         if cpu is not None:
             names = bytes(np.asarray(flat["node/names_bytes"]).astype(np.uint8)).decode().split("\n")
             out_name = "v(%s)" % [ln.split()[1] for ln in names if ln and int(ln.split()[0]) == int(save_eq[0])][0].lower()
-            parity = parity_check(cpu[4], out_t.numpy(), out_v.numpy(), res_e2e.npoints, out_name)
+            parity = parity_check(cpu[4], out_t.numpy(), out_v.numpy(), npoints_wave, out_name)
+            # the measurement of the end-to-end pass against com_measure_when applied to the reference's own waveforms
+            parity.update(meas_check(cpu[4], tdiff[0], out_name, meas_clauses))
+            parity["ok"] = bool(parity["ok"] and parity["meas_identical"])
             for f in cpu[4]:
                 try:
                     os.remove(f)

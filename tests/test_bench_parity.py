@@ -28,15 +28,20 @@ def _draws_vs_reference(lib, S, seed):
     b = pkg.Batch(circ, S)
     b.put("b4.inst", inst)
     b.set_bsim4_rows(prow_t, mtab, ptab)
+    clauses = [(int(wave["save_eq"][0]), 0, 10, 0.5, 0.0), (int(wave["save_eq"][0]), 0, 20, 0.5, 0.0)]     # ro_17_4.cir:54
+    b.set_measures(clauses)
     res = b.tran(6144, wave["save_eq"][:1])
     assert not res.err.any()
     t, v = res.waves()
+    ms = res.measures()
     cpu = bench.cpu_reference_run("mc_ro17", min(S, os.cpu_count() or 1), (S + (os.cpu_count() or 1) - 1) // (os.cpu_count() or 1) if S > (os.cpu_count() or 1) else 1,
                                   draws=[(dv_raw[s], float(tables["levels"][level[s]])) for s in range(S)], keep_raw=True,
                                   inst_names=[n.lower() for n in pkg.mc.instance_names(flat)])
     raws = cpu[4][:S]
     try:
-        return bench.parity_check(raws, t, v, res.npoints, "v(18)")
+        r = bench.parity_check(raws, t, v, res.npoints, "v(18)")
+        r.update(bench.meas_check(raws, ms[1] - ms[0], "v(18)", clauses))
+        return r
     finally:
         for f in raws:
             if os.path.exists(f):
@@ -45,7 +50,7 @@ def _draws_vs_reference(lib, S, seed):
 
 def test_bench_parity_hostsim(hostsim_lib):
     r = _draws_vs_reference(hostsim_lib, 2, seed=777)
-    assert r["accepted_identical"] and r["bit_identical"], r
+    assert r["accepted_identical"] and r["bit_identical"] and r["meas_identical"], r
 
 
 @pytest.mark.gpu
@@ -53,4 +58,4 @@ def test_bench_parity_gpu_distinct_draws(cuda_lib):
     """32 distinct (delvto, toxe level) draws in one batch, each against its own reference run"""
     n = 32
     r = _draws_vs_reference(cuda_lib, n, seed=4242)
-    assert r["ok"] and r["accepted_identical"], r
+    assert r["ok"] and r["accepted_identical"] and r["meas_max_rel_err"] <= 1e-9, r
