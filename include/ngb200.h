@@ -123,6 +123,7 @@ int ngbCircuitSetIsourcePwl(ngb_circuit *c, int inst, int ncoef, const double *c
  * pattern, the slot map and the per-target contribution lists */
 int ngbCircuitFinalize(ngb_circuit *c);
 int ngbCircuitPatternSize(const ngb_circuit *c, int *n, int *nnz, int *nstamp_rows);
+int ngbCircuitGetPatternEquations(const ngb_circuit *c, int *eq /* [n] equation number of pattern index k */);
 int ngbCircuitGetPattern(const ngb_circuit *c, int *Ap, int *Ai, int *diag_slot /* [n] */);
 int ngbCircuitGetBsim4Slots(const ngb_circuit *c, int *slots /* [70][ninst], -1 = ground/absent */);
 

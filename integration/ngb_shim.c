@@ -16,8 +16,18 @@
  *   SMPluFac    -> ngbLuFac     (row scaling + refactor on the GPU; 102 == E_SINGULAR like KLU)
  *   SMPsolve    -> ngbSolve     (triangular solves on the GPU)
  *
- * The shim is inactive -- every call goes to the reference -- when the circuit holds a device type
- * the library does not implement, when the matrix is not in KLU mode, or with NGB_SHIM=0.
+ * TABLE MODE (NGB_SHIM_TABLE=1, and automatically whenever the circuit holds a device type the library does not
+ * implement): the library is installed through the SPICEdev plugin table instead (devdefs.h:50-129, dev.c:142-209).
+ * DEVices[t]->DEVload of every device type the library implements is replaced; the reference's own CKTload then runs
+ * UNCHANGED -- it clears the matrix, walks DEVices[] (cktload.c:70-91), applies the .nodeset / .ic rows and counts
+ * CKTnoncon.  The first replaced DEVload of a pass evaluates ALL the replaced types in one ngbLoad and adds their
+ * assembled contributions into the KLU matrix and CKTrhs, the others return OK; device types without a replacement
+ * (BJT, inductors, controlled sources, ...) keep their CPU DEVload and stamp the same matrix.  With such types present
+ * the factorisation stays on the host KLU (their entries are not in the device pattern); without, SMPluFac / SMPsolve
+ * run on the device on the matrix and right-hand side the host CKTload finished.
+ *
+ * The shim is inactive -- every call goes to the reference -- when the matrix is not in KLU mode, when a replaced
+ * device type uses an option outside the GPU path, or with NGB_SHIM=0.
  * NGB_SHIM_LU=0 keeps the LU on the host (device load only).
  */
 #include "ngspice/ngspice.h"
@@ -63,6 +73,10 @@ static struct {
     int *sb4, *sb3, *sbd, *sbq, *sbc;          /* state bases per instance */
     double *buf; size_t buf_len;
     long loads, facs, solves;
+    /* table mode */
+    int table, mixed, leader;                  /* leader: the first replaced device type in DEVices order */
+    int *slot_map;                             /* our CSC slot -> slot of the reference's KLU matrix (NULL: identical patterns) */
+    int (*orig_load[8])(GENmodel *, CKTcircuit *); int orig_type[8], norig;
 } G;
 
 static void *xc(size_t n, size_t sz) { void *p = calloc(n ? n : 1, sz); if (!p) { fprintf(stderr, "ngb_shim: out of memory\n"); exit(1); } return p; }
@@ -304,6 +318,7 @@ static int flatten_linear(CKTcircuit *ckt)
     return rc;
 }
 
+static void table_install(CKTcircuit *ckt);
 static int shim_attach(CKTcircuit *ckt)
 {
     const char *e = getenv("NGB_SHIM");
@@ -319,11 +334,13 @@ static int shim_attach(CKTcircuit *ckt)
     K = ckt->CKTmatrix->SMPkluMatrix;
     G.tB4 = CKTtypelook("BSIM4"); G.tB3 = CKTtypelook("BSIM3"); G.tDIO = CKTtypelook("Diode"); G.tVBIC = CKTtypelook("VBIC"); G.tRES = CKTtypelook("Resistor");
     G.tCAP = CKTtypelook("Capacitor"); G.tVSRC = CKTtypelook("Vsource"); G.tISRC = CKTtypelook("Isource");
+    e = getenv("NGB_SHIM_TABLE");
+    G.table = (e && !strcmp(e, "1")) ? 1 : 0;
     for (t = 0; t < DEVmaxnum; t++)
         if (DEVices[t] && ckt->CKThead[t] && DEVices[t]->DEVload &&
             t != G.tB4 && t != G.tB3 && t != G.tDIO && t != G.tVBIC && t != G.tRES && t != G.tCAP && t != G.tVSRC && t != G.tISRC) {
-            fprintf(stderr, "ngb_shim: device type %s is not on the GPU path\n", DEVices[t]->DEVpublic.name);
-            return shim_fail("unsupported device type in the circuit");
+            fprintf(stderr, "ngb_shim: device type %s stays on the CPU (its own DEVload)\n", DEVices[t]->DEVpublic.name);
+            G.table = 1; G.mixed = 1;
         }
     ntype = (int *)xc((size_t)neq + 1, sizeof(int));
     for (node = ckt->CKTnodes; node; node = node->next) if (node->number >= 0 && node->number <= neq) ntype[node->number] = node->type;
@@ -343,7 +360,8 @@ static int shim_attach(CKTcircuit *ckt)
         fprintf(stderr, "ngb_shim: %s\n", ngbLastError());
         return shim_fail("circuit uses an option outside the GPU path");
     }
-    {   /* .nodeset / .ic rows (cktload.c:118-172): nodesets first, then initial conditions, each in node order */
+    if (!G.table) {   /* .nodeset / .ic rows (cktload.c:118-172): nodesets first, then initial conditions, each in node order;
+                       * in table mode the reference's CKTload applies them itself */
         int nov = 0, pass, i = 0, *oeq, *okind; double *oval;
         for (node = ckt->CKTnodes; node; node = node->next) nov += (node->nsGiven ? 1 : 0) + (node->icGiven ? 1 : 0);
         if (nov) {
@@ -357,11 +375,30 @@ static int shim_attach(CKTcircuit *ckt)
         }
     }
     ngbCircuitPatternSize(G.C, &n, &nnz, &nrows);
-    if (n != (int)K->KLUmatrixN || nnz != (int)K->KLUmatrixNZ) return shim_fail("CSC pattern differs from SMPconvertCOOtoCSC's");
+    if (!G.mixed && (n != (int)K->KLUmatrixN || nnz != (int)K->KLUmatrixNZ)) return shim_fail("CSC pattern differs from SMPconvertCOOtoCSC's");
     {
         int *Ap = (int *)xc((size_t)n + 1, sizeof(int)), *Ai = (int *)xc((size_t)nnz, sizeof(int)), *dg = (int *)xc((size_t)n, sizeof(int)), same;
         ngbCircuitGetPattern(G.C, Ap, Ai, dg);
-        same = !memcmp(Ap, K->KLUmatrixAp, sizeof(int) * ((size_t)n + 1)) && !memcmp(Ai, K->KLUmatrixAi, sizeof(int) * (size_t)nnz);
+        same = n == (int)K->KLUmatrixN && nnz == (int)K->KLUmatrixNZ &&
+               !memcmp(Ap, K->KLUmatrixAp, sizeof(int) * ((size_t)n + 1)) && !memcmp(Ai, K->KLUmatrixAi, sizeof(int) * (size_t)nnz);
+        if (!same && G.mixed) {
+            /* the replaced types' entries are a subset of the reference's pattern: find every slot of ours in it */
+            int col, q, bad = 0, *eqn = (int *)xc((size_t)n, sizeof(int));
+            ngbCircuitGetPatternEquations(G.C, eqn);          /* our index k is equation eqn[k]; the reference's is equation - 1 */
+            G.slot_map = (int *)xc((size_t)nnz, sizeof(int));
+            for (col = 0; col < n && !bad; col++)
+                for (q = Ap[col]; q < Ap[col + 1]; q++) {
+                    const int kc = eqn[col] - 1, kr = eqn[Ai[q]] - 1;
+                    int lo, hi = -1;
+                    if (kc < (int)K->KLUmatrixN)
+                        for (lo = K->KLUmatrixAp[kc]; lo < K->KLUmatrixAp[kc + 1]; lo++) if (K->KLUmatrixAi[lo] == kr) { hi = lo; break; }
+                    if (hi < 0) { bad = 1; break; }
+                    G.slot_map[q] = hi;
+                }
+            free(eqn);
+            if (bad) { free(Ap); free(Ai); free(dg); return shim_fail("an entry of the replaced device types is missing from the reference's CSC pattern"); }
+            same = 1;
+        }
         free(Ap); free(Ai); free(dg);
         if (!same) return shim_fail("CSC pattern differs from SMPconvertCOOtoCSC's");
     }
@@ -370,9 +407,11 @@ static int shim_attach(CKTcircuit *ckt)
     if (!G.B) { fprintf(stderr, "ngb_shim: %s\n", ngbLastError()); return shim_fail("batch creation failed"); }
     G.neq = neq; G.nnz = nnz;
     e = getenv("NGB_SHIM_LU");
-    G.use_lu = !(e && !strcmp(e, "0"));
+    G.use_lu = !(e && !strcmp(e, "0")) && !G.mixed;       /* CPU device types: their entries are not in the device pattern */
     G.active = 1;
-    fprintf(stderr, "ngb_shim: CKTload%s on %s (%d BSIM4, %d BSIM3, %d diodes, %d VBIC, %d unknowns, %d nonzeros)\n",
+    if (G.table) table_install(ckt);
+    fprintf(stderr, "ngb_shim: %s%s on %s (%d BSIM4, %d BSIM3, %d diodes, %d VBIC, %d unknowns, %d nonzeros)\n",
+            G.table ? "CKTload through the SPICEdev table (DEVload of the replaced types)" : "CKTload",
             G.use_lu ? " + SMPluFac + SMPsolve" : "", ngbBackend(), G.n4, G.n3, G.nd, G.nq, n, nnz);
     return 1;
 }
@@ -406,18 +445,16 @@ static void states_up(const char *name, int K, int n, const int *base)
     }
 }
 
-int __wrap_CKTload(CKTcircuit *ckt)
+/* CKTload's state -> device, ngbLoad, results back.  into_matrix = 0: Ax and CKTrhs are the device's (wrap mode, every
+ * device type on the device); 1: the assembled contributions are ADDED to what the reference's CKTload holds (table mode) */
+static int device_load(CKTcircuit *ckt, int into_matrix)
 {
     int iv, rc; double dv;
-    double startTime;
-    if (!G.tried) shim_attach(ckt);
-    if (!G.active || ckt != G.ckt) return __real_CKTload(ckt);
-    startTime = SPfrontEnd->IFseconds();
 #define PUT_I(name, v) do { iv = (v); ngbBatchUpload(G.B, name, &iv, sizeof(int), 0); } while (0)
 #define PUT_D(name, v) do { dv = (v); ngbBatchUpload(G.B, name, &dv, sizeof(double), 0); } while (0)
     PUT_I("ctl.mode", (int)ckt->CKTmode); PUT_I("ctl.active", 1); PUT_I("ctl.head", 0); PUT_I("ctl.order", ckt->CKTorder);
     PUT_I("ctl.xsel", 0); PUT_I("ctl.stateop", 0); PUT_I("ctl.err", 0);
-    PUT_D("ctl.ag0", ckt->CKTag[0]); PUT_D("ctl.ag1", ckt->CKTag[1]); PUT_D("ctl.delta", ckt->CKTdelta); PUT_D("ctl.time", ckt->CKTtime);
+    PUT_D("ctl.ag0", ckt->CKTag[0]); PUT_D("ctl.ag1", ckt->CKTag[1]); PUT_D("ctl.ag2", ckt->CKTag[2]); PUT_D("ctl.delta", ckt->CKTdelta); PUT_D("ctl.time", ckt->CKTtime);
     PUT_D("ctl.gmin", ckt->CKTgmin); PUT_D("ctl.srcfact", ckt->CKTsrcFact);
     PUT_D("ctl.diag_gmin", 0.0);        /* LoadGmin_CSC stays with whoever factors; see __wrap_SMPluFac */
     ngbBatchUpload(G.B, "ctl.delta_old", ckt->CKTdeltaOld, sizeof(double) * 7, 0);
@@ -429,9 +466,19 @@ int __wrap_CKTload(CKTcircuit *ckt)
     states_down("cap.state", 2, G.nc, G.sbc);
     rc = ngbLoad(G.B);
     if (rc) { fprintf(stderr, "ngb_shim: ngbLoad failed (%d): %s\n", rc, ngbLastError()); return rc; }
-    ngbBatchDownload(G.B, "Ax", ckt->CKTmatrix->SMPkluMatrix->KLUmatrixAx, (long)(sizeof(double) * (size_t)G.nnz), 0);
-    ngbBatchDownload(G.B, "x", ckt->CKTrhs, (long)(sizeof(double) * ((size_t)G.neq + 1)), (long)(sizeof(double) * ((size_t)G.neq + 1)));
-    ckt->CKTrhs[0] = 0.0;
+    if (!into_matrix) {
+        ngbBatchDownload(G.B, "Ax", ckt->CKTmatrix->SMPkluMatrix->KLUmatrixAx, (long)(sizeof(double) * (size_t)G.nnz), 0);
+        ngbBatchDownload(G.B, "x", ckt->CKTrhs, (long)(sizeof(double) * ((size_t)G.neq + 1)), (long)(sizeof(double) * ((size_t)G.neq + 1)));
+        ckt->CKTrhs[0] = 0.0;
+    } else {
+        double *Ax = ckt->CKTmatrix->SMPkluMatrix->KLUmatrixAx, *buf = scratch((size_t)G.nnz + (size_t)G.neq + 1);
+        int k;
+        ngbBatchDownload(G.B, "Ax", buf, (long)(sizeof(double) * (size_t)G.nnz), 0);
+        ngbBatchDownload(G.B, "x", buf + G.nnz, (long)(sizeof(double) * ((size_t)G.neq + 1)), (long)(sizeof(double) * ((size_t)G.neq + 1)));
+        if (G.slot_map) for (k = 0; k < G.nnz; k++) Ax[G.slot_map[k]] += buf[k];
+        else for (k = 0; k < G.nnz; k++) Ax[k] += buf[k];
+        for (k = 1; k <= G.neq; k++) ckt->CKTrhs[k] += buf[G.nnz + k];
+    }
     states_up("b4.state", B4ST_COUNT, G.n4, G.sb4);
     states_up("b3.state", B3ST_COUNT, G.n3, G.sb3);
     states_up("dio.state", DIOST_COUNT, G.nd, G.sbd);
@@ -441,8 +488,49 @@ int __wrap_CKTload(CKTcircuit *ckt)
     ckt->CKTnoncon += iv;
     G.dev_factored = 0;
     G.loads++;
-    ckt->CKTstat->STATloadTime += SPfrontEnd->IFseconds() - startTime;
     return OK;
+}
+
+/* ------------------------------------------------------------------ table mode: DEVices[t]->DEVload replacements */
+static int table_load(int type, GENmodel *head, CKTcircuit *ckt)
+{
+    int k;
+    if (!G.active || ckt != G.ckt) {          /* another circuit: the type's own DEVload */
+        for (k = 0; k < G.norig; k++) if (G.orig_type[k] == type) return G.orig_load[k](head, ckt);
+        return E_PANIC;
+    }
+    if (type != G.leader) return OK;          /* evaluated together with the leader's pass */
+    return device_load(ckt, 1);
+}
+#define TABLE_FN(nm, field) static int table_load_##nm(GENmodel *m, CKTcircuit *ckt) { return table_load(G.field, m, ckt); }
+TABLE_FN(b4, tB4) TABLE_FN(b3, tB3) TABLE_FN(dio, tDIO) TABLE_FN(vbic, tVBIC) TABLE_FN(res, tRES) TABLE_FN(cap, tCAP) TABLE_FN(vsrc, tVSRC) TABLE_FN(isrc, tISRC)
+
+static void table_install(CKTcircuit *ckt)
+{
+    struct { int type; int (*fn)(GENmodel *, CKTcircuit *); } rep[8] = {
+        { G.tB4, table_load_b4 }, { G.tB3, table_load_b3 }, { G.tDIO, table_load_dio }, { G.tVBIC, table_load_vbic },
+        { G.tRES, table_load_res }, { G.tCAP, table_load_cap }, { G.tVSRC, table_load_vsrc }, { G.tISRC, table_load_isrc } };
+    int k;
+    G.leader = -1; G.norig = 0;
+    for (k = 0; k < 8; k++) {
+        const int t = rep[k].type;
+        if (t < 0 || !DEVices[t] || !ckt->CKThead[t]) continue;
+        G.orig_type[G.norig] = t; G.orig_load[G.norig] = DEVices[t]->DEVload; G.norig++;
+        DEVices[t]->DEVload = rep[k].fn;
+        if (G.leader < 0 || t < G.leader) G.leader = t;
+    }
+}
+
+int __wrap_CKTload(CKTcircuit *ckt)
+{
+    int rc;
+    double startTime;
+    if (!G.tried) shim_attach(ckt);
+    if (!G.active || ckt != G.ckt || G.table) return __real_CKTload(ckt);      /* table mode: the reference's CKTload, replaced DEVloads inside */
+    startTime = SPfrontEnd->IFseconds();
+    rc = device_load(ckt, 0);
+    ckt->CKTstat->STATloadTime += SPfrontEnd->IFseconds() - startTime;
+    return rc;
 }
 
 /* pattern + pivot order of the pivoting factor that just ran on the host -> device schedule */
@@ -487,7 +575,9 @@ int __wrap_SMPreorder(SMPmatrix *M, double PivTol, double PivRel, double Gmin)
         G.dev_factored = 0;
         if (G.have_lu && !gmin_loaded) {
             /* the device refactors the same Ax on the new order, so the solve that follows runs there too */
-            int rc = ngbLuFac(G.B);
+            int rc;
+            if (G.table) ngbBatchUpload(G.B, "Ax", M->SMPkluMatrix->KLUmatrixAx, (long)(sizeof(double) * (size_t)G.nnz), 0);
+            rc = ngbLuFac(G.B);
             if (rc == 0) { G.dev_factored = 1; G.facs++; }
         }
     }
@@ -498,7 +588,9 @@ int __wrap_SMPluFac(SMPmatrix *M, double PivTol, double Gmin)
 {
     if (G.active && G.use_lu && G.have_lu && M == G.ckt->CKTmatrix &&
         !(Gmin != 0.0 && M->SMPkluMatrix->KLUloadDiagGmin)) {      /* gmin stepping: the host factors (it owns LoadGmin_CSC) */
-        int rc = ngbLuFac(G.B);
+        int rc;
+        if (G.table) ngbBatchUpload(G.B, "Ax", M->SMPkluMatrix->KLUmatrixAx, (long)(sizeof(double) * (size_t)G.nnz), 0);   /* what the host CKTload finished */
+        rc = ngbLuFac(G.B);
         G.facs++;
         if (rc == 0) { G.dev_factored = 1; return 0; }
         G.dev_factored = 0;
@@ -512,7 +604,9 @@ int __wrap_SMPluFac(SMPmatrix *M, double PivTol, double Gmin)
 void __wrap_SMPsolve(SMPmatrix *M, double RHS[], double Spare[])
 {
     if (G.active && G.use_lu && G.dev_factored && M == G.ckt->CKTmatrix && RHS == G.ckt->CKTrhs) {
-        int rc = ngbSolve(G.B);
+        int rc;
+        if (G.table) ngbBatchUpload(G.B, "x", RHS, (long)(sizeof(double) * ((size_t)G.neq + 1)), (long)(sizeof(double) * ((size_t)G.neq + 1)));
+        rc = ngbSolve(G.B);
         if (rc) { fprintf(stderr, "ngb_shim: ngbSolve failed (%d): %s\n", rc, ngbLastError()); }
         ngbBatchDownload(G.B, "x", RHS, (long)(sizeof(double) * ((size_t)G.neq + 1)), (long)(sizeof(double) * ((size_t)G.neq + 1)));
         RHS[0] = 0.0;

@@ -824,6 +824,14 @@ int ngbCircuitGetPattern(const ngb_circuit *c, int *Ap, int *Ai, int *diag)
     if (diag) memcpy(diag, c->diag_slot, sizeof(int) * (size_t)c->n);
     return NGB_OK;
 }
+/* equation number (1-based, CKTnode number) of every column / row index of the pattern: columns without entries are not
+ * in it, so in a circuit whose other device types are stamped elsewhere (the shim's table mode) index k is not equation k + 1 */
+int ngbCircuitGetPatternEquations(const ngb_circuit *c, int *eq)
+{
+    if (!c->finalized) return NGB_E_PANIC;
+    memcpy(eq, c->col2eq, sizeof(int) * (size_t)c->n);
+    return NGB_OK;
+}
 int ngbCircuitGetBsim4Slots(const ngb_circuit *c, int *slots)
 {
     if (!c->finalized) return NGB_E_PANIC;

@@ -32,13 +32,13 @@ def _run(exe, name, tmp, env=None):
     return _payload(raw), p.stdout + p.stderr
 
 
-def _check(exe, name, expect_backend, env=None):
+def _check(exe, name, expect_backend, env=None, expect="ngb_shim: CKTload"):
     if not (os.path.exists(REF) and os.path.exists(exe)):
         pytest.skip("oracle/_ref binaries not built (oracle/build_ref.sh needs /root/reference)")
     with tempfile.TemporaryDirectory(prefix="ngb_shim_") as tmp:
         (h0, v0), _ = _run(REF, name, tmp)
         (h1, v1), log = _run(exe, name, tmp, env)
-    assert f"ngb_shim: CKTload" in log and expect_backend in log, log[-1500:]     # the shim really took the hot path
+    assert expect in log and expect_backend in log, log[-1500:]     # the shim really took the hot path
     assert h0 == h1
     assert v0.shape == v1.shape
     _check.nvars = int([ln for ln in h0.splitlines() if ln.startswith("No. Variables")][0].split(":")[1])
@@ -89,3 +89,42 @@ def test_dropin_gpu_rawfile(name):
         assert np.max(np.abs(v0 - v1) / np.maximum(np.abs(v0), 1e-6)) <= 1e-9
     else:
         assert np.array_equal(v0, v1)
+
+
+# ---- table mode: the library installed through DEVices[t]->DEVload (devdefs.h:57, cktload.c:70-91) -------------------
+TABLE_NETLISTS = ["inv", "ro17k", "latch", "dio", "b3ring", "invgmin"]
+
+
+def _table_identical(exe, backend, name):
+    """every device type replaced: the reference's own CKTload (clear, DEVices loop, nodesets) around one ngbLoad whose assembled
+    contributions are added to the cleared matrix -- the same bits as the stock binary"""
+    v0, v1 = _check(exe, name, backend, env={"NGB_SHIM_TABLE": "1"}, expect="SPICEdev table")
+    assert np.array_equal(v0, v1)
+
+
+def _table_mixed(exe, backend):
+    """mixcpu: BSIM4 inverter + diode + R/C/V on the library, BJT / inductor / VCCS on their own CPU DEVload, all stamping the
+    same KLU matrix (host factorisation).  Sums over device types are taken in another order than the reference's, so the
+    bar is north_star's: identical accepted points, 1e-9 per vector"""
+    v0, v1 = _check(exe, "mixcpu", backend, expect="SPICEdev table")
+    assert _vbic_close(v0, v1) <= 1e-9
+
+
+@pytest.mark.parametrize("name", TABLE_NETLISTS)
+def test_dropin_table_hostsim_identical(name):
+    _table_identical(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb_hostsim"), "hostsim", name)
+
+
+def test_dropin_table_hostsim_mixed_device_set():
+    _table_mixed(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb_hostsim"), "hostsim")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["inv", "ro17k", "latch"])
+def test_dropin_table_gpu_identical(name):
+    _table_identical(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb"), "cuda-sm_100a", name)
+
+
+@pytest.mark.gpu
+def test_dropin_table_gpu_mixed_device_set():
+    _table_mixed(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb"), "cuda-sm_100a")
