@@ -21,7 +21,15 @@ def _run(lib, name, S=1, inst=None, max_points=8192):
         b.put("b4.inst", inst)
     res = b.tran(max_points, wave["save_eq"])
     t, v = res.waves()
+    wave["_scale"] = _scales(flat, wave)
     return res, t, v, wave
+
+
+def _scales(flat, wave):
+    """|v - v_ref| <= tol * max(|v_ref|, scale) at every accepted point, scale = vntol (1e-6 V) for node
+    voltages and abstol (1e-12 A) for branch currents"""
+    nt = np.asarray(flat["node/type"])[np.asarray(wave["save_eq"])]
+    return np.where(nt == 3, 1e-6, 1e-12)
 
 
 def _compare(res, t, v, wave, s, exact, tol=1e-9, same_route=True):
@@ -35,8 +43,9 @@ def _compare(res, t, v, wave, s, exact, tol=1e-9, same_route=True):
         assert np.array_equal(v[s, :n, :], wave["values"])
     else:
         assert np.max(np.abs(t[s, :n] - wave["time"]) / np.maximum(wave["time"], 1e-300)) <= tol     # t = 0 is the first point without UIC
-        rng = np.max(np.abs(wave["values"]), axis=0)
-        err = np.max(np.abs(v[s, :n, :] - wave["values"]), axis=0) / rng
+        # per point, not per vector range
+        scale = wave.get("_scale", np.full(wave["values"].shape[1], 1e-6))
+        err = np.max(np.abs(v[s, :n, :] - wave["values"]) / np.maximum(np.abs(wave["values"]), scale[None, :]), axis=0)
         assert (err <= tol).all(), err
 
 
@@ -59,7 +68,7 @@ def test_tran_hostsim_gear_bit_identical(hostsim_lib, name):
 def test_tran_hostsim_gear_mix_cell(hostsim_lib):
     """GEAR on the cell with every model family (VBIC: 1e-9, see test_tran_hostsim_vbic)"""
     res, t, v, wave = _run(hostsim_lib, "mixg")
-    _compare(res, t, v, wave, 0, exact=False)
+    _compare(res, t, v, wave, 0, exact=False, tol=1e-8)      # per point; 4.6e-9 where v(y4) crosses zero (VBIC Jacobian rounding)
 
 
 def test_bsim4_variant_kernels_same_bits(hostsim_lib):
@@ -119,7 +128,8 @@ def _mix_sweep(lib, reps=1):
     t, v = res.waves()
     for s in range(len(pts)):
         k = s % len(MIX_POINTS)
-        _compare(res, t, v, ngt.read(f"{GOLDEN}/mix{k if k else ''}.wave.ngt"), s, exact=False, same_route=k < MIX_SAME_ROUTE)
+        w = ngt.read(f"{GOLDEN}/mix{k if k else ''}.wave.ngt"); w["_scale"] = _scales(flat, w)
+        _compare(res, t, v, w, s, exact=False, same_route=k < MIX_SAME_ROUTE)
 
 
 def test_tran_hostsim_mix_cell(hostsim_lib):
@@ -156,7 +166,8 @@ def _mix_source_stepping(lib, reps=1, exact_count=True):
     t, v = res.waves()
     for s in range(len(pts)):
         if s % 3 != 1:
-            _compare(res, t, v, ngt.read(f"{GOLDEN}/{('mix', '', 'mix1')[s % 3]}.wave.ngt"), s, exact=False, same_route=True)
+            w = ngt.read(f"{GOLDEN}/{('mix', '', 'mix1')[s % 3]}.wave.ngt"); w["_scale"] = _scales(flat, w)
+            _compare(res, t, v, w, s, exact=False, same_route=True)
         else:
             ref = ngt.read(f"{GOLDEN}/mixsrc.wave.ngt")
             assert int(res.accepted[s]) == 0 and int(res.err[s]) == 103, (s, int(res.err[s]))
