@@ -153,7 +153,7 @@ def cpu_reference_run(workload, nproc, samples_per_proc, seed0=1000, draws=None,
             else:
                 rng = np.random.default_rng(seed0 + p * samples_per_proc + k)
                 dv = rng.normal(0.0, 0.015, size=ninst) if workload != "ro101" else np.zeros(ninst)
-                tox = TOX_LEVELS[int(rng.integers(0, len(TOX_LEVELS)))] if workload != "ro101" else None
+                tox = 1.4e-9 * (1.0 + 0.03 * float(rng.normal())) if workload != "ro101" else None      # continuous, like the GPU arm's default
             lines, i = [], 0
             for ln in base.splitlines():
                 if ln[:2].lower() in ("mp", "mn") and " l=" in ln:
@@ -306,9 +306,11 @@ def workload_config(args):
                 "samples_per_gpu": 1, "bsim4_instances": 202, "unknowns": 911,
                 "l2": "working set smaller than L2 by nature (single circuit); no flush"}
     return {"workload": "Monte Carlo transient, 17-stage BSIM4 ring oscillator (ro_17_4.cir cards, version 4.8.3), "
-                        ".tran .1ns 150ns uic from alternating `.ic` stage voltages, per-instance delvto mismatch sigma 15 mV and per-sample toxe from 8 levels of N(1.4 nm, 3 %)",
+                        ".tran .1ns 150ns uic from alternating `.ic` stage voltages, per-instance delvto mismatch sigma 15 mV and per-sample toxe "
+                        + ("~ N(1.4 nm, 3 %), continuous (rows by the library's BSIM4temp)" if getattr(args, "tox", "continuous") == "continuous" else "from 8 levels of N(1.4 nm, 3 %)"),
             "samples_per_gpu": args.samples, "bsim4_instances": 34, "unknowns": 155,
-            "layout": "draws unsorted" if os.environ.get("NGB_BENCH_UNSORTED") else "samples laid out level by level (same draws)",
+            "layout": ("per-sample parameter rows, " + ("row-major" if os.environ.get("NGB_BENCH_ROWMAJOR") else "field-major")) if getattr(args, "tox", "continuous") == "continuous"
+                      else ("draws unsorted" if os.environ.get("NGB_BENCH_UNSORTED") else "samples laid out level by level (same draws)"),
             "l2": "inputs larger than L2: per-step working set (parameters+states+stamps+matrices) ~%.0f MB" %
                   (args.samples * 34 * (51 + 4 * 29 + 38 + 52) * 8 / 1e6 + args.samples * 904 * 8 / 1e6)}
 
@@ -359,14 +361,28 @@ def bench_ours(args):
     else:
         dv_raw = pkg.mc.draw_delvto(S, ninst, sigma=0.015, seed=1000 + rank)
         dv = pkg.mc.delvto_as_parsed(dv_raw)          # what the reference's number parser makes of the netlist text
-        tox_tables = ngt.read(f"{GOLDEN}/ro17tox.tables.ngt")
-        level = np.random.default_rng(5000 + rank).integers(0, len(tox_tables["levels"]), size=S)
-        if not os.environ.get("NGB_BENCH_UNSORTED"):
-            # same draws, laid out level by level: a warp's 32 samples then share their parameter rows
-            order = pkg.mc.group_by_level(level)
-            level, dv, dv_raw = level[order], dv[order], dv_raw[order]
-        inst_host, prow_t, mtab_all, ptab_all = pkg.mc.bsim4_with_tox_levels(lib, flat, tox_tables, level, dv)
-        batch.set_bsim4_rows(prow_t, mtab_all, ptab_all)
+        field_major = False
+        if args.tox == "continuous":
+            # every sample its own oxide thickness ~ N(1.4 nm, 3 %): the model / bin / instance rows of each sample come from
+            # the library's own BSIM4temp (csrc/ngb_b4temp.c) on the nominal card; per-sample rows, field-major on the device
+            b4t = ngt.read(f"{GOLDEN}/b4temp.tables.ngt.gz")
+            raw = {"model": b4t["ro17k/b4t/model"], "inst": b4t["ro17k/b4t/inst"], "inst_model": b4t["ro17k/b4t/inst_model"],
+                   "temp": b4t["ro17k/b4t/temp"][0, 0], "vt0": b4t["ro17k/opt/vt0"][0]}
+            tox_raw = 1.4e-9 * (1.0 + 0.03 * np.random.default_rng(5000 + rank).normal(size=S))
+            tox = np.array([pkg.mc.spice_number(f"{x:.17g}") for x in tox_raw])     # what the reference's parser makes of the card text
+            inst_host, prow_t, mtab_all, ptab_all = pkg.mc.bsim4_with_toxe(lib, raw, tox, dv)
+            field_major = not os.environ.get("NGB_BENCH_ROWMAJOR")
+            tox_of = lambda p: float(tox_raw[p])
+        else:
+            tox_tables = ngt.read(f"{GOLDEN}/ro17tox.tables.ngt")
+            level = np.random.default_rng(5000 + rank).integers(0, len(tox_tables["levels"]), size=S)
+            if not os.environ.get("NGB_BENCH_UNSORTED"):
+                # same draws, laid out level by level: a warp's 32 samples then share their parameter rows
+                order = pkg.mc.group_by_level(level)
+                level, dv, dv_raw = level[order], dv[order], dv_raw[order]
+            inst_host, prow_t, mtab_all, ptab_all = pkg.mc.bsim4_with_tox_levels(lib, flat, tox_tables, level, dv)
+            tox_of = lambda p: float(tox_tables["levels"][level[p]])
+        batch.set_bsim4_rows(prow_t, mtab_all, ptab_all, field_major=field_major)
     pinned = torch.empty(inst_host.shape, dtype=torch.float64).pin_memory()
     pinned.numpy()[...] = inst_host
     out_t = torch.empty((S, max_points), dtype=torch.float64).pin_memory()
@@ -386,7 +402,7 @@ def bench_ours(args):
         if e2e:
             batch.put("b4.inst", pinned.numpy())
             if args.workload != "ro101":
-                batch.set_bsim4_rows(prow_t, mtab_all, ptab_all)
+                batch.set_bsim4_rows(prow_t, mtab_all, ptab_all, field_major=field_major)
             batch.set_measures(meas_clauses)
             res = batch.tran(0, [])
             lib.check(lib.L.ngbTranMeasures(batch.h, ctypes.cast(meas_out.data_ptr(), ctypes.POINTER(ctypes.c_double))), "ngbTranMeasures")
@@ -475,7 +491,7 @@ def bench_ours(args):
         if args.workload == "ro101":
             draws = [(np.zeros(ninst), None)] * k
         else:
-            draws = [(dv_raw[p], float(tox_tables["levels"][level[p]])) for p in range(k)]
+            draws = [(dv_raw[p], tox_of(p)) for p in range(k)]
         cpu = cpu_reference_run(args.workload, k, 1, draws=draws, keep_raw=True,
                                 inst_names=[n.lower() for n in pkg.mc.instance_names(flat)])
         parity = None
@@ -713,7 +729,7 @@ def sweep_cpu_baseline(nproc, per_proc=128):
             f = os.path.join(tmp, f"p{p}_{k}.cir")
             open(f, "w").write(text)
             files.append(f)
-        cmd = " ; ".join(f"{exe} -b -r {f}.raw {f} > {f}.log 2>&1" + ("" if keep_raw else f" ; rm -f {f}.raw") for f in files)
+        cmd = " ; ".join(f"{exe} -b -r {f}.raw {f} > {f}.log 2>&1 ; rm -f {f}.raw" for f in files)
         procs.append((subprocess.Popen(["bash", "-c", cmd]), files))
     iters = 0
     for pr, files in procs:
@@ -865,6 +881,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --samples per GPU (default, the driver's scaling run); strong: --samples in total, samples / N per GPU "
                          "(BASELINE config 3 as written: 4096 samples, batch = 4096 / N)")
+    ap.add_argument("--tox", default="continuous", choices=["continuous", "levels"],
+                    help="per-sample oxide thickness: continuous N(1.4 nm, 3 %%) through the library's BSIM4temp (default), or round 1's 8 recorded levels")
     ap.add_argument("--samples", type=int, default=None, help="Monte-Carlo samples (default 4096) or sweep points (default 8192) per GPU")
     args = ap.parse_args()
     if args.samples is None:

@@ -216,6 +216,18 @@ int ngbTranWaves(ngb_batch *b, double *times /* [S][max_points] */, double *valu
  * `TRIG .. TARG ..` measurement is two clauses; its result is the difference.  ngbTranMeasures: out [n][S], NaN = not found */
 int ngbTranSetMeasures(ngb_batch *b, int n, const int *eq, const int *kind, const int *count, const double *val, const double *td);
 int ngbTranMeasures(ngb_batch *b, double *out);
+/* BSIM4temp inside the library (csrc/ngb_b4temp.c; b4temp.c:69-2408 + the clamps of b4check.c + b4geo.c): the load's model /
+ * bin / instance tables from model cards and instance geometry, for any parameter value (continuous model-parameter
+ * mismatch).  Tables are indexed by the name lists of csrc/bsim4_temp_fields.h: ngbBsim4TempLayout gives their lengths
+ * {model, size, instance, binned}, ngbBsim4TempFieldName(list 0 model / 1 size / 2 instance, i) the names.
+ *   temp: circuit temperature (K); vt0: CONSTvt0
+ *   model [nmodel][NM] in/out (cards after BSIM4setup, `...Given` flags 0 / 1), inst [ninst][NI] in/out, inst_model [ninst]
+ *   out: prow [ninst], *nrows, mtab [<= ninst rows][78], ptab [<= ninst rows][143], itab [51][ninst] -- what ngbCircuitAddBsim4
+ *   and ngbBatchSetBsim4Rows take.  Returns 0, or NGB_E_PANIC where the reference stops with a fatal parameter error */
+void ngbBsim4TempLayout(int layout[4]);
+const char *ngbBsim4TempFieldName(int list, int i);
+int ngbBsim4Temp(double temp, double vt0, int nmodel, double *model, int ninst, const int *inst_model, double *inst,
+                 int *prow, int *nrows, double *mtab, double *ptab, double *itab);
 /* which BSIM4 load kernel the batch runs (csrc/bsim4_variants.h): key[0] = the variant key packed from the model selectors
  * and rbodyMod / rgateMod of its instances (0xffffffff when they differ), key[1] = 1 when the kernel specialised on that key
  * is in use.  ngbBatchSetBsim4Generic(b, 1) (or NGB_B4_GENERIC=1 in the environment) forces the generic kernel: same bits */
@@ -227,6 +239,7 @@ int ngbProfileStages(double ms[8]);
 long ngbTranTicks(ngb_batch *b);              /* Newton steps the batch needed */
 void *ngbTranDevWaves(ngb_batch *b, int which /* 0 times, 1 values */);   /* device pointers for a collective gather */
 /* per-thread BSIM4 parameter rows for model-parameter mismatch: prow_t [ninst*S] into new tables */
+int ngbBatchSetBsim4RowsT(ngb_batch *b, const int *prow_t, int nrows, const double *mtab_t /* [78][nrows] */, const double *ptab_t /* [143][nrows] */);
 int ngbBatchSetBsim4Rows(ngb_batch *b, const int *prow_t, int nrows, const double *mtab, const double *ptab);
 
 #ifdef __cplusplus

@@ -59,6 +59,7 @@ typedef struct B4Ctx {
     const double *ptab;        /* [nrows][B4P_COUNT] bin rows                            */
     const int *prow;           /* parameter row per thread ([T]) or per instance ([ninst]) */
     int prow_per_thread;       /* 1: prow[t], 0: prow[inst]                              */
+    int row_stride;            /* 1: mtab / ptab are [row][field]; nrows: they are [field][row] (per-sample rows, ngbBatchSetBsim4RowsT) */
     unsigned variant;          /* variant key of the batch (bsim4_variants.h), NGB_B4_GENERIC when its instances differ */
     const double *inst;        /* [B4I_COUNT][T]                                         */
     const int *flags;          /* [ninst] packed B4F_*                                   */
@@ -116,8 +117,11 @@ typedef struct B4W {
 } B4W;
 
 #include "bsim4_variants.h"
-#define B4M(f) NGB_LDG(&Mrow[B4M_##f])
-#define B4P(f) NGB_LDG(&Prow[B4P_##f])
+/* model / bin parameter f of this thread's row: rows are table rows ([row][field], stride 1 between fields) or, for per-sample
+ * rows in field-major storage, columns ([field][row], stride nrows); a specialised instantiation knows which at compile time */
+#define B4ROWSTRIDE ((size_t)(((VK == NGB_B4_GENERIC) || B4K_FIELD(VK, rowsT)) ? c->row_stride : 1))
+#define B4M(f) NGB_LDG(&Mrow[B4M_##f * B4ROWSTRIDE])
+#define B4P(f) NGB_LDG(&Prow[B4P_##f * B4ROWSTRIDE])
 #define B4I(f) NGB_LDG(&c->inst[(size_t)B4I_##f * c->T + t])
 /* selectors: compile-time constants of the variant key VK in a specialised instantiation, read from the parameter
  * row / instance flags in the generic one (bsim4_variants.h) */
@@ -2158,7 +2162,7 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
 
 /* VgsteffCV selection shared by capMod 1 and 2 (b4ld.c:3351-3457) */
 template <unsigned VK>
-NGB_HD void b4_vgsteff_cv(const double *Mrow, const double *Prow, const B4W *w,
+NGB_HD void b4_vgsteff_cv(const B4Ctx *c, const double *Mrow, const double *Prow, const B4W *w,
                           double *pVgsteff, double *pdVg, double *pdVd, double *pdVb)
 {
     const double n = w->n, dn_dVd = w->dn_dVd, dn_dVb = w->dn_dVb, Vtm = w->Vtm, Vgst = w->Vgst;
@@ -2523,7 +2527,7 @@ NGB_HD int b4_charges(const B4Ctx *c, size_t t, const double *Mrow, const double
         if (Vbseff < 0.0) { VbseffCV = Vbseff; dVbseffCV_dVb = 1.0; }
         else { VbseffCV = phi - Phis; dVbseffCV_dVb = -dPhis_dVb; }
 
-        b4_vgsteff_cv<VK>(Mrow, Prow, w, &Vgsteff, &dVgsteff_dVg, &dVgsteff_dVd, &dVgsteff_dVb);
+        b4_vgsteff_cv<VK>(c, Mrow, Prow, w, &Vgsteff, &dVgsteff_dVg, &dVgsteff_dVd, &dVgsteff_dVb);
 
         if (capMod == 1) {
             const double Vfb = vfbzb;
@@ -2980,8 +2984,8 @@ NGB_HD int b4_prologue(const B4Ctx *c, size_t t, int first, B4Pro *p, int *err)
     const int prow = c->prow_per_thread ? NGB_LDG(&c->prow[t]) : NGB_LDG(&c->prow[inst]);
     p->inst = inst; p->s = s; p->head = head; p->mode_ckt = mode_ckt;
     p->flags = NGB_LDG(&c->flags[inst]);
-    p->Mrow = c->mtab + (size_t)prow * B4M_COUNT;
-    p->Prow = c->ptab + (size_t)prow * B4P_COUNT;
+    p->Mrow = c->mtab + ((c->row_stride > 1) ? (size_t)prow : (size_t)prow * B4M_COUNT);
+    p->Prow = c->ptab + ((c->row_stride > 1) ? (size_t)prow : (size_t)prow * B4P_COUNT);
 
     if (mode_ckt & NGB_MODEINITSMSIG) { *err = NGB_E_UNSUPP; return 0; }
 

@@ -59,6 +59,38 @@ def bsim4_with_tox_levels(lib, flat, tables, level, delvto):
     return inst, prow_t, mtab, ptab
 
 
+def bsim4_with_toxe(lib, raw, toxe, delvto, temp=None, vt0=None):
+    """Continuous model-parameter mismatch: sample s has oxide thickness toxe[s] (both model cards, a die-level variation)
+    and per-instance threshold shifts delvto[s]; its model / bin / instance rows are computed by the library's own BSIM4temp
+    (csrc/ngb_b4temp.c) from the nominal raw tables `raw` = {"model", "inst", "inst_model", "temp", "vt0"} (oracle dump keys
+    b4t/*).  Returns (inst [NI][ninst][S], prow_t [ninst*S], mtab [R*S][NM], ptab [R*S][NP]) like bsim4_with_tox_levels; R rows
+    per sample (one per distinct model and size), numbered r * S + s: the samples of one parameter set are consecutive rows
+    (what Batch.set_bsim4_rows(field_major=True) wants)."""
+    from .b4temp import Bsim4Temp
+    T = Bsim4Temp(lib)
+    toxe = np.asarray(toxe, dtype=np.float64)
+    S, ninst = delvto.shape
+    temp = float(raw["temp"]) if temp is None else temp
+    vt0 = float(raw["vt0"]) if vt0 is None else vt0
+    inst_out = np.empty((len(lib.fields["inst"]), ninst, S))
+    prow_t = np.empty((ninst, S), np.int32)
+    mt = pt = None
+    R = None
+    for s in range(S):
+        model = np.array(raw["model"], dtype=np.float64, copy=True); inst = np.array(raw["inst"], dtype=np.float64, copy=True)
+        T.set_model(model, "toxe", toxe[s])
+        inst[:, T.icol["delvto"]] = delvto[s]
+        prow, mtab, ptab, itab = T.run(temp, vt0, model, inst, raw["inst_model"])
+        if R is None:
+            R = mtab.shape[0]
+            mt = np.empty((R, S, mtab.shape[1])); pt = np.empty((R, S, ptab.shape[1]))
+        assert mtab.shape[0] == R
+        inst_out[:, :, s] = itab
+        prow_t[:, s] = prow * S + s
+        mt[:, s, :] = mtab; pt[:, s, :] = ptab
+    return inst_out, prow_t.reshape(-1), mt.reshape(R * S, -1), pt.reshape(R * S, -1)
+
+
 def group_by_level(level):
     """Batch layout for model-parameter mismatch: positions of the samples ordered by parameter level (stable),
     so that the 32 consecutive samples a warp evaluates read the SAME model / bin rows (one cache line per

@@ -42,6 +42,7 @@
 #include <string.h>
 
 #include "../ngspice-sf-mirror_b200/csrc/bsim4_fields.h"
+#include "../ngspice-sf-mirror_b200/csrc/bsim4_temp_fields.h"
 #include "../ngspice-sf-mirror_b200/csrc/dio_fields.h"
 #include "../ngspice-sf-mirror_b200/csrc/vbic_types.h"
 #include "../ngspice-sf-mirror_b200/csrc/bsim3_fields.h"
@@ -178,6 +179,33 @@ static void dump_bsim4(FILE *f, CKTcircuit *ckt, KLUmatrix *K)
 #define X(nm) ptab[(size_t)r * B4P_COUNT + (k++)] = (double)pParam->BSIM4##nm;
         NGB_B4_BIN_FIELDS(X)
 #undef X
+    }
+    {   /* the raw tables BSIM4temp works on (csrc/ngb_b4temp.c restates it): every model-card and instance quantity it reads or
+         * writes, by the generated name lists.  Taken after CKTtemp: the inputs are unchanged by it, re-running it is idempotent */
+        int nmodel = 0, mi = 0, *imodel = (int *)calloc((size_t)n, sizeof(int));
+        double *tm, *ti;
+        for (model = (BSIM4model *)ckt->CKThead[b4_type]; model; model = BSIM4nextModel(model)) nmodel++;
+        tm = (double *)calloc((size_t)nmodel * B4TM_COUNT, sizeof(double));
+        ti = (double *)calloc((size_t)n * B4TI_COUNT, sizeof(double));
+        i = 0;
+        for (model = (BSIM4model *)ckt->CKThead[b4_type]; model; model = BSIM4nextModel(model), mi++) {
+            int k = 0;
+#define X(nm) tm[(size_t)mi * B4TM_COUNT + (k++)] = (double)model->BSIM4##nm;
+            NGB_B4T_MODEL_FIELDS(X)
+#undef X
+            for (here = BSIM4instances(model); here; here = BSIM4nextInstance(here), i++) {
+                k = 0;
+                imodel[i] = mi;
+#define X(nm) ti[(size_t)i * B4TI_COUNT + (k++)] = (double)here->BSIM4##nm;
+                NGB_B4T_INST_FIELDS(X)
+#undef X
+            }
+        }
+        put_d2(f, "b4t/model", tm, nmodel, B4TM_COUNT);
+        put_d2(f, "b4t/inst", ti, n, B4TI_COUNT);
+        put_i1(f, "b4t/inst_model", imodel, n);
+        { double tk = ckt->CKTtemp; put_d2(f, "b4t/temp", &tk, 1, 1); }
+        free(tm); free(ti); free(imodel);
     }
     put_is(f, "b4/ninst", n);
     put_i2(f, "b4/nodes", nodes, B4N_COUNT, n);

@@ -492,6 +492,58 @@ if __name__ == "__main__":
         for i in range(2):
             run(f"ro17tox{i}", with_toxe(ro_netlist(17, tran=".tran .1ns 20ns uic", kick=True, delvto=dv[i]), levels[lev[i]]),
                 "1", ["18", "2", "9", "vdd#branch"])
+    if "b4temp" in which:
+        # BSIM4temp in / out tables (csrc/ngb_b4temp.c restates b4temp.c + b4geo.c + the clamps of b4check.c): the raw model cards
+        # and instances the reference's BSIM4temp worked on, and the load tables it left, for cards that walk its branches
+        def inv_variant(card_edit=lambda c: c, inst="", opts="", temp=None):
+            n = inv_netlist()
+            a = n.index(".model"); b = n.rindex(".end")
+            cards = card_edit(n[a:b])
+            n = n[:a] + cards + n[b:]
+            if inst:
+                n = re.sub(r"^(m[pn] .*)$", lambda m: m.group(1) + " " + inst, n, flags=re.M)
+            n = n.replace(".option klu", ".option klu " + opts + (f" temp={temp}" if temp is not None else ""))
+            return n
+        def setp(card, **kw):
+            out = card
+            for k, v in kw.items():
+                pat = re.compile(r"(?im)^(\+?\s*" + k + r"\s*=\s*)\S+.*$")
+                if pat.search(out):
+                    out = pat.sub(lambda m: m.group(1) + str(v), out)
+                else:
+                    out = re.sub(r"(?im)^(\.model .*)$", lambda m: m.group(1) + f"\n+ {k} = {v}", out)
+            return out
+        cases = {
+            "ro17k": ro_netlist(17, tran=".tran .1ns 0.2ns uic", kick=True),
+            "ro17hot": ro_netlist(17, tran=".tran .1ns 0.2ns uic", kick=True).replace(".option xmu", ".option temp=100 xmu"),
+            "ro17tox": with_toxe(ro_netlist(17, tran=".tran .1ns 0.2ns uic", kick=True, delvto=np.random.default_rng(3).normal(0, 0.015, 34)), 1.4e-9 * 1.043),
+            "inv": inv_variant(),
+            "inv_hot_tm1": inv_variant(lambda c: setp(c, tempmod=1, at=2e-4, ua1=1e-3, ub1=-1e-3, uc1=5e-4, ud1=2e-4, prt=1e-3), temp=85),
+            "inv_hot_tm2": inv_variant(lambda c: setp(c, tempmod=2, at=2e-4, ua1=1e-3, ub1=-1e-3, uc1=5e-4, ud1=2e-4, prt=1e-3), temp=-20),
+            "inv_hot_tm3": inv_variant(lambda c: setp(c, tempmod=3, at=2e-4, ua1=1e-3, ub1=-1e-3, uc1=5e-4, ud1=2e-4, prt=1e-3), temp=125),
+            "inv_rds_geo": inv_variant(lambda c: setp(c, rdsmod=1, rsh=7.0), inst="nf=4 rgeomod=3 geomod=5 min=1"),
+            "inv_geo9": inv_variant(lambda c: setp(c, rsh=5.0, permod=0), inst="nf=4 rgeomod=1 geomod=9 pd=2e-6 ps=3e-6"),
+            "inv_geo2": inv_variant(lambda c: setp(c, rsh=5.0), inst="nf=3 rgeomod=4 geomod=2 nrd=1.5 nrs=0.5 ad=2e-12 as=3e-12"),
+            "inv_stress": inv_variant(lambda c: setp(c, ku0=-4e-6, kvsat=0.2, kvth0=-2e-8, stk2=1e-9, steta0=2e-9, tku0=0.1, wpemod=1, kvth0we=0.01, k2we=0.002, ku0we=-0.003),
+                                      inst="nf=2 sa=0.4e-6 sb=0.5e-6 sd=0.3e-6 sc=1e-6 mulu0=0.97 delvto=0.011"),
+            "inv_rbody2": inv_variant(lambda c: setp(c, rbps0=60.0, rbpd0=70.0, rbsbx0=120.0, rbsby0=110.0, rbdbx0=130.0, rbdby0=90.0, rbpbx0=40.0, rbpby0=45.0),
+                                      inst="rbodymod=2 rgatemod=2 ngcon=2 xgw=1e-7"),
+            "inv_dio0": inv_variant(lambda c: setp(c, diomod=0, xjbvs=0.5, xjbvd=0.7, bvs=8.0, bvd=9.0)),
+            "inv_dio2": inv_variant(lambda c: setp(c, diomod=2, xjbvs=0.5, xjbvd=0.7, bvs=8.0, bvd=9.0, ijthsrev=0.2, ijthdrev=0.3), temp=60),
+            "inv_bin": inv_variant(lambda c: setp(c, binunit=1, lvth0=0.004, wvth0=-0.003, pvth0=0.0005, lu0=1e-3, wk2=0.001, lvsat=900.0, pua=1e-12, lnfactor=0.02)),
+            "inv_mob3": inv_variant(lambda c: setp(c, mobmod=3, vtl=2.0e5, xn=2.5, lc=5e-9, lambda_=None) if False else setp(c, mobmod=3, vtl=2.0e5, xn=2.5, lc=5e-9)),
+            "inv_k1k2": inv_variant(lambda c: setp(c, k1=0.45, k2=-0.02, dvtp4=0.3, dvtp5=0.01, dvtp2=0.02, dvtp3=0.1)),
+        }
+        out = {}
+        for nm, net in cases.items():
+            run("_b4t", net, "0", [])
+            fl = ngt.read(os.path.join(HERE, "_b4t.flat.ngt"))
+            for k in ("b4t/model", "b4t/inst", "b4t/inst_model", "b4t/temp", "b4/mtab", "b4/ptab", "b4/inst", "b4/prow", "opt/vt0"):
+                out[f"{nm}/{k}"] = fl[k]
+            for ext in (".flat.ngt", ".trace.ngt.gz", ".wave.ngt"):
+                os.remove(os.path.join(HERE, "_b4t" + ext))
+        out["cases"] = np.frombuffer("\n".join(cases).encode(), dtype=np.uint8).astype(np.int32)
+        ngt.write(os.path.join(HERE, "b4temp.tables.ngt.gz"), out)
     if "b3cap" in which:
         # every capMod / xpart combination of BSIM3 on a short 3-stage version of the same ring
         for cm in (0, 1, 2, 3):

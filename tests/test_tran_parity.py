@@ -441,6 +441,50 @@ def test_tran_gpu_tox_and_vth_mismatch(cuda_lib):
         _compare(res, t, v, ngt.read(f"{GOLDEN}/ro17tox{s}.wave.ngt"), s, exact=True)
 
 
+def _tox_batch_own_temp(lib, field_major, copies=1):
+    """the same two samples, but their model / bin / instance rows come from the library's own BSIM4temp (csrc/ngb_b4temp.c)
+    applied to the NOMINAL card with each sample's toxe and delvto -- nothing recorded per oxide thickness -- and the rows are
+    stored per sample, field-major on the device when `field_major`"""
+    base = ngt.read(f"{GOLDEN}/ro17k.flat.ngt")
+    trace = ngt.read(f"{GOLDEN}/ro17k.trace.ngt.gz")
+    tab = ngt.read(f"{GOLDEN}/b4temp.tables.ngt.gz")
+    raw = {"model": tab["ro17k/b4t/model"], "inst": tab["ro17k/b4t/inst"], "inst_model": tab["ro17k/b4t/inst_model"],
+           "temp": tab["ro17k/b4t/temp"][0, 0], "vt0": tab["ro17k/opt/vt0"][0]}
+    levels = ngt.read(f"{GOLDEN}/ro17tox.tables.ngt")["levels"]
+    dv_netlist = np.load(f"{GOLDEN}/ro17tox.delvto.npy"); level = np.load(f"{GOLDEN}/ro17tox.level.npy")
+    col = {}
+    for k in range(1, 18):
+        col[f"mp{k}"] = 2 * (k - 1); col[f"mn{k}"] = 2 * (k - 1) + 1
+    order = [col[n.lower()] for n in pkg.mc.instance_names(base)]
+    dv = np.tile(pkg.mc.delvto_as_parsed(dv_netlist[:, order]), (copies, 1))
+    toxe = np.tile(np.array([pkg.mc.spice_number(f"{levels[k]:.17g}") for k in level]), copies)
+    inst, prow_t, mtab, ptab = pkg.mc.bsim4_with_toxe(lib, raw, toxe, dv)
+    circ = pkg.Circuit.from_flat(lib, base, lu_pattern=run_patterns(trace))
+    b = pkg.Batch(circ, 2 * copies)
+    b.put("b4.inst", inst)
+    b.set_bsim4_rows(prow_t, mtab, ptab, field_major=field_major)
+    assert b.bsim4_variant()[1]            # a specialised kernel exists for both layouts of this card
+    wave0 = ngt.read(f"{GOLDEN}/ro17tox0.wave.ngt")
+    res = b.tran(1024, wave0["save_eq"])
+    t, v = res.waves()
+    return res, t, v
+
+
+@pytest.mark.parametrize("field_major", [False, True])
+def test_tran_hostsim_continuous_tox_own_bsim4temp(hostsim_lib, field_major):
+    res, t, v = _tox_batch_own_temp(hostsim_lib, field_major)
+    for s in range(2):
+        _compare(res, t, v, ngt.read(f"{GOLDEN}/ro17tox{s}.wave.ngt"), s, exact=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("field_major", [False, True])
+def test_tran_gpu_continuous_tox_own_bsim4temp(cuda_lib, field_major):
+    res, t, v = _tox_batch_own_temp(cuda_lib, field_major, copies=48)       # 96 samples: three warps per instance
+    for s in range(96):
+        _compare(res, t, v, ngt.read(f"{GOLDEN}/ro17tox{s % 2}.wave.ngt"), s, exact=True)
+
+
 B3_CAP_CASES = [f"b3c{cm}x{tag}" for cm in (0, 1, 2, 3) for tag in ("0", "5", "1")]
 
 

@@ -11,5 +11,5 @@ PKG=ngspice-sf-mirror_b200; CSRC=$PKG/csrc
 python3 tools/nvcc_outline.py --outline-entries bsim4,ngb_k_b4_ --inline-div ${NGB_INLINE_DIV:-none} --share-rcp ${NGB_SHARE_RCP:-0} -- nvcc \
   -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -Xcompiler -fPIC -std=c++17 -Xptxas -v \
   -I$CSRC -Iinclude "$@" -c $CSRC/ngb_cuda.cu -o $out/ngb_cuda.o 2> $out/ptxas.log || { cat $out/ptxas.log; exit 1; }
-nvcc -shared -o $out/libngb200.so $out/ngb_cuda.o $CSRC/ngb_host.o $CSRC/ngb_tran.o $CSRC/ngb_pivot.o -lcudart -lgomp
+nvcc -shared -o $out/libngb200.so $out/ngb_cuda.o $CSRC/ngb_host.o $CSRC/ngb_tran.o $CSRC/ngb_pivot.o $CSRC/ngb_b4temp.o -lcudart -lgomp
 grep -A2 "ngb_k_bsim4_load\|ngb_k_lu_packed" $out/ptxas.log | grep -v "^--" | grep "registers\|spill" | tr '\n' ' '; echo
