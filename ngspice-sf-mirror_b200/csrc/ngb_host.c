@@ -1870,6 +1870,26 @@ static int set_bsim4_rows(ngb_batch *b, const int *prow_t, int nrows, const doub
     b->b4_mtab = (double *)dev_dup(mtab, sizeof(double) * (size_t)nrows * B4M_COUNT);
     b->b4_ptab = (double *)dev_dup(ptab, sizeof(double) * (size_t)nrows * B4P_COUNT);
     b->b4_row_stride = field_major ? nrows : 1;
+    memset(b->b4_mvary, 0, sizeof b->b4_mvary); memset(b->b4_pvary, 0, sizeof b->b4_pvary);
+    if (field_major) {
+        /* rows must be numbered r * S + s (the samples of parameter set r are consecutive): the kernel reads the columns
+         * that do not differ between the samples of a set once per warp, at the set's first row */
+        const int S = b->S;
+        size_t q; int f, r, s2;
+        if (nrows % S) { ngb_set_error("field-major BSIM4 rows: the row count %d is not a multiple of the %d samples", nrows, S); return NGB_E_PANIC; }
+        for (q = 0; q < T; q++)
+            if (prow_t[q] < 0 || prow_t[q] >= nrows || prow_t[q] % S != (int)(q % (size_t)S)) {
+                ngb_set_error("field-major BSIM4 rows must be numbered r * S + s (thread %ld has row %d)", (long)q, prow_t[q]); return NGB_E_PANIC;
+            }
+        for (f = 0; f < B4M_COUNT; f++)
+            for (r = 0; r < nrows / S && !((b->b4_mvary[f >> 6] >> (f & 63)) & 1ull); r++)
+                for (s2 = 1; s2 < S; s2++)
+                    if (memcmp(&mtab[(size_t)f * nrows + (size_t)r * S + s2], &mtab[(size_t)f * nrows + (size_t)r * S], sizeof(double))) { b->b4_mvary[f >> 6] |= 1ull << (f & 63); break; }
+        for (f = 0; f < B4P_COUNT; f++)
+            for (r = 0; r < nrows / S && !((b->b4_pvary[f >> 6] >> (f & 63)) & 1ull); r++)
+                for (s2 = 1; s2 < S; s2++)
+                    if (memcmp(&ptab[(size_t)f * nrows + (size_t)r * S + s2], &ptab[(size_t)f * nrows + (size_t)r * S], sizeof(double))) { b->b4_pvary[f >> 6] |= 1ull << (f & 63); break; }
+    }
     b->b4_key = b4_batch_key(b->c, mtab, nrows, NULL, field_major ? nrows : 1);
     if (field_major && b->b4_key != NGB_B4_GENERIC) b->b4_key = NGB_B4_KEY_ROWST(b->b4_key);
     return (b->b4_prow_t && b->b4_mtab && b->b4_ptab) ? NGB_OK : NGB_E_PANIC;
@@ -1933,6 +1953,7 @@ void ngb_fill_b4ctx(ngb_batch *b, B4Ctx *x)
     x->prow = b->b4_prow_t ? b->b4_prow_t : b->b4_prow; x->prow_per_thread = b->b4_prow_t ? 1 : 0;
     x->variant = (!b->b4_force_generic && b4_variant_built(b->b4_key)) ? b->b4_key : NGB_B4_GENERIC;
     x->row_stride = b->b4_row_stride > 0 ? b->b4_row_stride : 1;
+    memcpy(x->mvary, b->b4_mvary, sizeof x->mvary); memcpy(x->pvary, b->b4_pvary, sizeof x->pvary);
     x->inst = b->b4_inst; x->flags = b->b4_flags; x->nodes = b->b4_nodes; x->spos = b->b4_spos;
     x->stamp = b->stamp; x->state = b->b4_state; x->op = b->b4_op; x->op_full = b->op_full;
     x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl; x->temp = c->opt.temp; x->vt0 = c->opt.vt0;
