@@ -368,7 +368,8 @@ def bench_ours(args):
             b4t = ngt.read(f"{GOLDEN}/b4temp.tables.ngt.gz")
             raw = {"model": b4t["ro17k/b4t/model"], "inst": b4t["ro17k/b4t/inst"], "inst_model": b4t["ro17k/b4t/inst_model"],
                    "temp": b4t["ro17k/b4t/temp"][0, 0], "vt0": b4t["ro17k/opt/vt0"][0]}
-            tox_raw = 1.4e-9 * (1.0 + 0.03 * np.random.default_rng(5000 + rank).normal(size=S))
+            sigma = float(os.environ.get("NGB_BENCH_TOX_SIGMA", "0.03"))       # 1e-9: distinct rows, identical dynamics (measures the row access alone)
+            tox_raw = 1.4e-9 * (1.0 + sigma * np.random.default_rng(5000 + rank).normal(size=S))
             tox = np.array([pkg.mc.spice_number(f"{x:.17g}") for x in tox_raw])     # what the reference's parser makes of the card text
             inst_host, prow_t, mtab_all, ptab_all = pkg.mc.bsim4_with_toxe(lib, raw, tox, dv)
             field_major = not os.environ.get("NGB_BENCH_ROWMAJOR")

@@ -21,6 +21,9 @@
 #ifndef NGB_B4_MINBLOCKS
 #define NGB_B4_MINBLOCKS 2      /* 128 registers/thread, 16 warps/SM: measured 1.5x faster than 255 registers */
 #endif
+#ifndef NGB_LU_CTA_DEFAULT
+#define NGB_LU_CTA_DEFAULT 256
+#endif
 #include "ngb_dev.h"
 #include "ngb_kernels.cuh"
 #include "vbic_eval.cuh"
@@ -616,8 +619,13 @@ int ngb_launch_lu(const NgbLuCtx *c)
             return post_launch("lu_packed");
         }
         if (blob + bytes1 <= (size_t)g_smem_optin) {
-            if (v2) ngb_k_lu_packed<1><<<(unsigned)c->S, 256, blob + bytes1, g_stream>>>(*c, 1, 256, per);
-            else ngb_k_lu_packed<0><<<(unsigned)c->S, 256, blob + bytes1, g_stream>>>(*c, 1, 256, per);
+            /* few samples: one CTA per sample.  The levels of a circuit matrix are narrow (RO-101: 27 values and 19 products
+             * per level on average), so the width that pays is small: NGB_LU_CTA threads (default below), one warp
+             * synchronises with __syncwarp instead of a CTA barrier */
+            static int cta = 0;
+            if (!cta) { const char *e = getenv("NGB_LU_CTA"); cta = e ? atoi(e) : NGB_LU_CTA_DEFAULT; if (cta < 32 || cta > 1024 || (cta & 31)) cta = NGB_LU_CTA_DEFAULT; }
+            if (v2) ngb_k_lu_packed<1><<<(unsigned)c->S, cta, blob + bytes1, g_stream>>>(*c, 1, cta, per);
+            else ngb_k_lu_packed<0><<<(unsigned)c->S, cta, blob + bytes1, g_stream>>>(*c, 1, cta, per);
             return post_launch("lu_packed");
         }
     }
