@@ -228,6 +228,9 @@ void ngbBsim4TempLayout(int layout[4]);
 const char *ngbBsim4TempFieldName(int list, int i);
 int ngbBsim4Temp(double temp, double vt0, int nmodel, double *model, int ninst, const int *inst_model, double *inst,
                  int *prow, int *nrows, double *mtab, double *ptab, double *itab);
+/* direct ngbLoad calls: also evaluate DEVtrunc's step bounds into ctl.lte / ctl.lte2 (off by default -- the caller's own CKTtrunc
+ * works on the host state vectors; ngbTranRun has its own arrangement, BSIM4trunc in a launch after the solve) */
+void ngbBatchSetLoadLte(ngb_batch *b, int on);
 /* which BSIM4 load kernel the batch runs (csrc/bsim4_variants.h): key[0] = the variant key packed from the model selectors
  * and rbodyMod / rgateMod of its instances (0xffffffff when they differ), key[1] = 1 when the kernel specialised on that key
  * is in use.  ngbBatchSetBsim4Generic(b, 1) (or NGB_B4_GENERIC=1 in the environment) forces the generic kernel: same bits */

@@ -2057,15 +2057,24 @@ int ngb_enqueue_load(ngb_batch *b)
     return NGB_OK;
 }
 
+/* CKTload alone.  The truncation-error bounds (DEVtrunc -> CKTterr) are NOT evaluated here unless asked for with
+ * ngbBatchSetLoadLte: at this level the caller's own CKTtrunc runs DEVtrunc on the host state vectors (the shim), and inside
+ * the load they cost five CKTterr bodies per instance plus an atomic minimum per charge on ctl.lte[sample] -- with one
+ * sample and a million instances (config 4) a million threads on one address, 3x the whole load (measured) */
 int ngbLoad(ngb_batch *b)
 {
     int r;
+    double *l1 = b->ctl.lte, *l2 = b->ctl.lte2;
     ngb_dev_memset(b->errflag, 0, sizeof(int) * 4);
     ngb_launch_clear_i32(b->ctl.noncon, 0, b->S);          /* CKTnoncon = 0 (niiter.c:71) */
-    if ((r = ngb_enqueue_load(b))) return r;
+    if (!b->load_lte) b->ctl.lte = b->ctl.lte2 = NULL;
+    r = ngb_enqueue_load(b);
+    b->ctl.lte = l1; b->ctl.lte2 = l2;
+    if (r) return r;
     if ((r = ngb_dev_sync())) return r;
     return check_errflag(b);
 }
+void ngbBatchSetLoadLte(ngb_batch *b, int on) { b->load_lte = on ? 1 : 0; }
 static int lu_call(ngb_batch *b, int f, int s)
 {
     NgbLuCtx x; int r;

@@ -79,6 +79,7 @@ struct ngb_batch {
     int narr;
     struct ngb_tran *tran;
     unsigned long long b4_mvary[2], b4_pvary[3];   /* field-major rows: columns that differ between the samples of a parameter set */
+    int load_lte;              /* ngbBatchSetLoadLte: direct ngbLoad calls evaluate DEVtrunc's bounds inside the load (off by default) */
     int b4_row_stride;         /* 1, or the row count of field-major per-sample tables (ngbBatchSetBsim4RowsT) */
     unsigned b4_key;           /* variant key of the BSIM4 instances (bsim4_variants.h); NGB_B4_GENERIC when they differ */
     int b4_force_generic;      /* ngbBatchSetBsim4Generic / NGB_B4_GENERIC=1: run the generic kernel whatever the key */
