@@ -309,7 +309,7 @@ def workload_config(args):
                         ".tran .1ns 150ns uic from alternating `.ic` stage voltages, per-instance delvto mismatch sigma 15 mV and per-sample toxe "
                         + ("~ N(1.4 nm, 3 %), continuous (rows by the library's BSIM4temp)" if getattr(args, "tox", "continuous") == "continuous" else "from 8 levels of N(1.4 nm, 3 %)"),
             "samples_per_gpu": args.samples, "bsim4_instances": 34, "unknowns": 155,
-            "layout": ("per-sample parameter rows, " + ("row-major" if os.environ.get("NGB_BENCH_ROWMAJOR") else "field-major")) if getattr(args, "tox", "continuous") == "continuous"
+            "layout": "per-sample parameter rows" if getattr(args, "tox", "continuous") == "continuous"
                       else ("draws unsorted" if os.environ.get("NGB_BENCH_UNSORTED") else "samples laid out level by level (same draws)"),
             "l2": "inputs larger than L2: per-step working set (parameters+states+stamps+matrices) ~%.0f MB" %
                   (args.samples * 34 * (51 + 4 * 29 + 38 + 52) * 8 / 1e6 + args.samples * 904 * 8 / 1e6)}
@@ -361,10 +361,9 @@ def bench_ours(args):
     else:
         dv_raw = pkg.mc.draw_delvto(S, ninst, sigma=0.015, seed=1000 + rank)
         dv = pkg.mc.delvto_as_parsed(dv_raw)          # what the reference's number parser makes of the netlist text
-        field_major = False
         if args.tox == "continuous":
             # every sample its own oxide thickness ~ N(1.4 nm, 3 %): the model / bin / instance rows of each sample come from
-            # the library's own BSIM4temp (csrc/ngb_b4temp.c) on the nominal card; per-sample rows, field-major on the device
+            # the library's own BSIM4temp (csrc/ngb_b4temp.c) on the nominal card; per-sample table rows
             b4t = ngt.read(f"{GOLDEN}/b4temp.tables.ngt.gz")
             raw = {"model": b4t["ro17k/b4t/model"], "inst": b4t["ro17k/b4t/inst"], "inst_model": b4t["ro17k/b4t/inst_model"],
                    "temp": b4t["ro17k/b4t/temp"][0, 0], "vt0": b4t["ro17k/opt/vt0"][0]}
@@ -372,7 +371,6 @@ def bench_ours(args):
             tox_raw = 1.4e-9 * (1.0 + sigma * np.random.default_rng(5000 + rank).normal(size=S))
             tox = np.array([pkg.mc.spice_number(f"{x:.17g}") for x in tox_raw])     # what the reference's parser makes of the card text
             inst_host, prow_t, mtab_all, ptab_all = pkg.mc.bsim4_with_toxe(lib, raw, tox, dv)
-            field_major = not os.environ.get("NGB_BENCH_ROWMAJOR")
             tox_of = lambda p: float(tox_raw[p])
         else:
             tox_tables = ngt.read(f"{GOLDEN}/ro17tox.tables.ngt")
@@ -383,7 +381,7 @@ def bench_ours(args):
                 level, dv, dv_raw = level[order], dv[order], dv_raw[order]
             inst_host, prow_t, mtab_all, ptab_all = pkg.mc.bsim4_with_tox_levels(lib, flat, tox_tables, level, dv)
             tox_of = lambda p: float(tox_tables["levels"][level[p]])
-        batch.set_bsim4_rows(prow_t, mtab_all, ptab_all, field_major=field_major)
+        batch.set_bsim4_rows(prow_t, mtab_all, ptab_all)
     pinned = torch.empty(inst_host.shape, dtype=torch.float64).pin_memory()
     pinned.numpy()[...] = inst_host
     out_t = torch.empty((S, max_points), dtype=torch.float64).pin_memory()
@@ -403,7 +401,7 @@ def bench_ours(args):
         if e2e:
             batch.put("b4.inst", pinned.numpy())
             if args.workload != "ro101":
-                batch.set_bsim4_rows(prow_t, mtab_all, ptab_all, field_major=field_major)
+                batch.set_bsim4_rows(prow_t, mtab_all, ptab_all)
             batch.set_measures(meas_clauses)
             res = batch.tran(0, [])
             lib.check(lib.L.ngbTranMeasures(batch.h, ctypes.cast(meas_out.data_ptr(), ctypes.POINTER(ctypes.c_double))), "ngbTranMeasures")

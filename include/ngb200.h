@@ -242,7 +242,6 @@ int ngbProfileStages(double ms[8]);
 long ngbTranTicks(ngb_batch *b);              /* Newton steps the batch needed */
 void *ngbTranDevWaves(ngb_batch *b, int which /* 0 times, 1 values */);   /* device pointers for a collective gather */
 /* per-thread BSIM4 parameter rows for model-parameter mismatch: prow_t [ninst*S] into new tables */
-int ngbBatchSetBsim4RowsT(ngb_batch *b, const int *prow_t, int nrows, const double *mtab_t /* [78][nrows] */, const double *ptab_t /* [143][nrows] */);
 int ngbBatchSetBsim4Rows(ngb_batch *b, const int *prow_t, int nrows, const double *mtab, const double *ptab);
 
 #ifdef __cplusplus

@@ -350,17 +350,12 @@ class Batch:
     def load(self):
         self.lib.check(self.lib.L.ngbLoad(self.h), "ngbLoad (CKTload)")
 
-    def set_bsim4_rows(self, prow_t, mtab, ptab, field_major=False):
+    def set_bsim4_rows(self, prow_t, mtab, ptab):
         """per-(instance, sample) model/bin parameter rows: Monte-Carlo with model-parameter mismatch.  mtab [nrows][NM],
-        ptab [nrows][NP].  field_major: store the tables transposed on the device ([field][row]); with rows numbered so that
-        consecutive samples of an instance have consecutive rows (mc.bsim4_with_toxe) a warp reads each parameter coalesced"""
+        ptab [nrows][NP], prow_t [ninst * S] (sample fastest)"""
         pr, mt, pt = _i32(prow_t), _f64(mtab), _f64(ptab)
         assert mt.shape[1] == self.lib.layout[0] and pt.shape[1] == self.lib.layout[1] and mt.shape[0] == pt.shape[0]
-        if field_major:
-            mtT, ptT = np.ascontiguousarray(mt.T), np.ascontiguousarray(pt.T)
-            self.lib.check(self.lib.L.ngbBatchSetBsim4RowsT(self.h, _ip(pr), int(mt.shape[0]), _dp(mtT), _dp(ptT)), "ngbBatchSetBsim4RowsT")
-        else:
-            self.lib.check(self.lib.L.ngbBatchSetBsim4Rows(self.h, _ip(pr), int(mt.shape[0]), _dp(mt), _dp(pt)), "ngbBatchSetBsim4Rows")
+        self.lib.check(self.lib.L.ngbBatchSetBsim4Rows(self.h, _ip(pr), int(mt.shape[0]), _dp(mt), _dp(pt)), "ngbBatchSetBsim4Rows")
 
     def lufac(self):
         self.lib.check(self.lib.L.ngbLuFac(self.h), "ngbLuFac (SMPluFac)")

@@ -59,8 +59,6 @@ typedef struct B4Ctx {
     const double *ptab;        /* [nrows][B4P_COUNT] bin rows                            */
     const int *prow;           /* parameter row per thread ([T]) or per instance ([ninst]) */
     int prow_per_thread;       /* 1: prow[t], 0: prow[inst]                              */
-    int row_stride;            /* 1: mtab / ptab are [row][field]; nrows: they are [field][row] (per-sample rows, ngbBatchSetBsim4RowsT) */
-    unsigned long long mvary[2], pvary[3];   /* field-major rows: bit f set = column f differs between the samples of a parameter set */
     unsigned variant;          /* variant key of the batch (bsim4_variants.h), NGB_B4_GENERIC when its instances differ */
     const double *inst;        /* [B4I_COUNT][T]                                         */
     const int *flags;          /* [ninst] packed B4F_*                                   */
@@ -118,16 +116,8 @@ typedef struct B4W {
 } B4W;
 
 #include "bsim4_variants.h"
-/* model / bin parameter f of this thread's row: rows are table rows ([row][field], stride 1 between fields) or, for per-sample
- * rows in field-major storage, columns ([field][row], stride nrows); a specialised instantiation knows which at compile time */
-#define B4ROWSTRIDE ((size_t)(((VK == NGB_B4_GENERIC) || B4K_FIELD(VK, rowsT)) ? c->row_stride : 1))
-/* field-major per-sample rows: Mrow / Prow point at the row of the instance's FIRST sample (rows are numbered r * S + s);
- * only the columns that differ between the samples of a parameter set (mvary / pvary, found by the host) are read at this
- * sample's own row, b4so doubles further -- every other parameter stays a warp-uniform load of one line */
-#define B4MVARY(f) ((c->mvary[B4M_##f >> 6] >> (B4M_##f & 63)) & 1ull)
-#define B4PVARY(f) ((c->pvary[B4P_##f >> 6] >> (B4P_##f & 63)) & 1ull)
-#define B4M(f) NGB_LDG(&Mrow[B4M_##f * B4ROWSTRIDE + (B4MVARY(f) ? b4so : (size_t)0)])
-#define B4P(f) NGB_LDG(&Prow[B4P_##f * B4ROWSTRIDE + (B4PVARY(f) ? b4so : (size_t)0)])
+#define B4M(f) NGB_LDG(&Mrow[B4M_##f])
+#define B4P(f) NGB_LDG(&Prow[B4P_##f])
 #define B4I(f) NGB_LDG(&c->inst[(size_t)B4I_##f * c->T + t])
 /* selectors: compile-time constants of the variant key VK in a specialised instantiation, read from the parameter
  * row / instance flags in the generic one (bsim4_variants.h) */
@@ -264,7 +254,7 @@ NGB_HD_SHARED void b4_tat(double vts, double vj, double Nvtmr, double *Tn, doubl
 /* Phase A: terminal voltages by INITF mode and Newton step limiting (b4ld.c:257-698). */
 template <unsigned VK>
 NGB_HD void b4_fetch_limit(const B4Ctx *c, size_t t, int inst, int s, int head, int mode_ckt,
-                           const double *Mrow, int flags, B4W *w, size_t b4so)
+                           const double *Mrow, int flags, B4W *w)
 {
     const int rbodyMod = B4SEL_RBODY(flags), rgateMod = B4SEL_RGATE(flags);
     const int off = flags & B4F_OFF;
@@ -443,7 +433,7 @@ NGB_HD void b4_fetch_limit(const B4Ctx *c, size_t t, int inst, int s, int head, 
  * drain current and its output-resistance corrections (b4ld.c:700-2189). */
 template <unsigned VK>
 NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, const double *Prow,
-                       int flags, B4W *w, size_t b4so)
+                       int flags, B4W *w)
 {
     const double gmin = NGB_LDG(&c->ctl.gmin[s]);
     const double nf = B4I(nf);
@@ -1665,7 +1655,7 @@ NGB_HD_SHARED void b4_ig_edge(double vg, double vfbsd_tot, double Aechvb, double
  * tunnelling, finger scaling (b4ld.c:2191-2976). */
 template <unsigned VK>
 NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const double *Prow,
-                          int flags, B4W *w, size_t b4so)
+                          int flags, B4W *w)
 {
     const int rgateMod = B4SEL_RGATE(flags);
     const double nf = B4I(nf);
@@ -2168,8 +2158,8 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
 
 /* VgsteffCV selection shared by capMod 1 and 2 (b4ld.c:3351-3457) */
 template <unsigned VK>
-NGB_HD void b4_vgsteff_cv(const B4Ctx *c, const double *Mrow, const double *Prow, const B4W *w,
-                          double *pVgsteff, double *pdVg, double *pdVd, double *pdVb, size_t b4so)
+NGB_HD void b4_vgsteff_cv(const double *Mrow, const double *Prow, const B4W *w,
+                          double *pVgsteff, double *pdVg, double *pdVd, double *pdVb)
 {
     const double n = w->n, dn_dVd = w->dn_dVd, dn_dVb = w->dn_dVb, Vtm = w->Vtm, Vgst = w->Vgst;
     const double dVgs_eff_dVg = w->dVgs_eff_dVg, dVth_dVd = w->dVth_dVd, dVth_dVb = w->dVth_dVb;
@@ -2268,7 +2258,7 @@ NGB_HD void b4_vgsteff_cv(const B4Ctx *c, const double *Mrow, const double *Prow
  * Returns 0 when charges are not computed (xpart<0 or no charge computation). */
 template <unsigned VK>
 NGB_HD int b4_charges(const B4Ctx *c, size_t t, const double *Mrow, const double *Prow,
-                      int ChargeComputationNeeded, B4W *w, size_t b4so)
+                      int ChargeComputationNeeded, B4W *w)
 {
     const double xpart = B4M(xpart);
     const int capMod = B4SEL(capMod);
@@ -2533,7 +2523,7 @@ NGB_HD int b4_charges(const B4Ctx *c, size_t t, const double *Mrow, const double
         if (Vbseff < 0.0) { VbseffCV = Vbseff; dVbseffCV_dVb = 1.0; }
         else { VbseffCV = phi - Phis; dVbseffCV_dVb = -dPhis_dVb; }
 
-        b4_vgsteff_cv<VK>(c, Mrow, Prow, w, &Vgsteff, &dVgsteff_dVg, &dVgsteff_dVd, &dVgsteff_dVb, b4so);
+        b4_vgsteff_cv<VK>(Mrow, Prow, w, &Vgsteff, &dVgsteff_dVg, &dVgsteff_dVd, &dVgsteff_dVb);
 
         if (capMod == 1) {
             const double Vfb = vfbzb;
@@ -2972,7 +2962,6 @@ NGB_HD_SHARED void b4_junction_cv(double vj, double cz, double czsw, double czsw
 /* what every phase of one evaluation starts from (cheap to recompute, so the split kernels do) */
 typedef struct B4Pro {
     int inst, s, head, mode_ckt, flags, charge;
-    size_t so;                 /* sample offset of the varying columns (field-major rows), 0 otherwise */
     const double *Mrow, *Prow;
 } B4Pro;
 
@@ -2991,9 +2980,8 @@ NGB_HD int b4_prologue(const B4Ctx *c, size_t t, int first, B4Pro *p, int *err)
     const int prow = c->prow_per_thread ? NGB_LDG(&c->prow[t]) : NGB_LDG(&c->prow[inst]);
     p->inst = inst; p->s = s; p->head = head; p->mode_ckt = mode_ckt;
     p->flags = NGB_LDG(&c->flags[inst]);
-    /* field-major: the row of the parameter set's first sample (rows are r * S + s) */
-    p->Mrow = c->mtab + ((c->row_stride > 1) ? (size_t)(prow - s) : (size_t)prow * B4M_COUNT);
-    p->Prow = c->ptab + ((c->row_stride > 1) ? (size_t)(prow - s) : (size_t)prow * B4P_COUNT);
+    p->Mrow = c->mtab + (size_t)prow * B4M_COUNT;
+    p->Prow = c->ptab + (size_t)prow * B4P_COUNT;
 
     if (mode_ckt & NGB_MODEINITSMSIG) { *err = NGB_E_UNSUPP; return 0; }
 
@@ -3025,14 +3013,12 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
     B4W w;
     int err;
     if (!b4_prologue(c, t, 1, &p, &err)) return err;
-    const size_t b4so = (B4ROWSTRIDE > 1) ? (size_t)p.s : (size_t)0;
-    p.so = b4so;
-    b4_fetch_limit<VK>(c, t, p.inst, p.s, p.head, p.mode_ckt, p.Mrow, p.flags, &w, b4so);
-    b4_core_dc<VK>(c, t, p.s, p.Mrow, p.Prow, p.flags, &w, b4so);
+    b4_fetch_limit<VK>(c, t, p.inst, p.s, p.head, p.mode_ckt, p.Mrow, p.flags, &w);
+    b4_core_dc<VK>(c, t, p.s, p.Mrow, p.Prow, p.flags, &w);
     /* the parasitics and the intrinsic charges only read what the core phase left; the charges first (12 values for the
      * finish phase alive across the parasitics instead of 52 across the charges) was measured 6 % SLOWER on B200 */
-    b4_parasitics<VK>(c, t, p.Mrow, p.Prow, p.flags, &w, b4so);
-    b4_charges<VK>(c, t, p.Mrow, p.Prow, p.charge, &w, b4so);
+    b4_parasitics<VK>(c, t, p.Mrow, p.Prow, p.flags, &w);
+    b4_charges<VK>(c, t, p.Mrow, p.Prow, p.charge, &w);
     return b4_finish<VK>(c, t, &p, &w);
 }
 

@@ -42,10 +42,6 @@
 #define B4K_rgateMod_W        2
 #define B4K_gear_SH          21   /* 1: CKTintegrateMethod == GEAR */
 #define B4K_gear_W            1
-#define B4K_rowsT_SH         22   /* 1: per-sample model / bin rows stored field-major ([field][row], ngbBatchSetBsim4RowsT): a warp's
-                                   *    32 samples read 32 consecutive doubles per parameter instead of 32 table rows */
-#define B4K_rowsT_W           1
-#define NGB_B4_KEY_ROWST(key) ((key) | B4K_PACK(rowsT, 1))
 
 #define NGB_B4_GENERIC 0xffffffffu
 
@@ -64,8 +60,7 @@
  *   (the QA cards of tests/bsim4/{nmos,pmos}/parameters resolve to the same key)
  * more keys: add a line here (each costs ~15 s of compile time and ~230 KB of code) */
 #define NGB_B4_VARIANT_KEYS(X) \
-    X(NGB_B4_KEY(0, 2, 0, 1, 0, 1, 1, 0, 0, 0, 0, 1, 1, 0)) \
-    X(NGB_B4_KEY_ROWST(NGB_B4_KEY(0, 2, 0, 1, 0, 1, 1, 0, 0, 0, 0, 1, 1, 0)))
+    X(NGB_B4_KEY(0, 2, 0, 1, 0, 1, 1, 0, 0, 0, 0, 1, 1, 0))
 
 /* the variant a batch runs: its key when the library carries that instantiation, NGB_B4_GENERIC otherwise */
 static inline int b4_variant_built(unsigned key)

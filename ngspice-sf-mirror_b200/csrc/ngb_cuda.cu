@@ -123,26 +123,43 @@ ngb_k_assemble(const NgbAsmCtx c, size_t total)
     ngb_asm_thread(&c, u);
 }
 
-/* long contribution lists: one CTA per (long target, sample) */
+/* long contribution lists (ngb_types.h): level 1 sums chunks of stamp rows, the next levels chunks of chunk totals */
 __global__ void __launch_bounds__(256)
-ngb_k_assemble_long(const NgbAsmCtx c)
+ngb_k_assemble_long1(const NgbAsmCtx c, int li, double *part, int nchunk)
 {
-    __shared__ double part[256];
-    const int li = blockIdx.x / c.S, s = blockIdx.x - li * c.S;
+    const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= (size_t)nchunk * c.S) return;
+    const int ch = (int)(u / (size_t)c.S), s = (int)(u - (size_t)ch * c.S);
     if (!c.ctl.active[s]) return;
     const int tg = c.long_tgt[li];
-    const int lo = c.tgt_ptr[tg], hi = c.tgt_ptr[tg + 1];
-    const int chunk = (hi - lo + 255) / 256;
-    const int a = lo + threadIdx.x * chunk, b = min(a + chunk, hi);
+    const int lo = c.tgt_ptr[tg] + ch * NGB_ASM_CHUNK, hi = min(lo + NGB_ASM_CHUNK, c.tgt_ptr[tg + 1]);
     double acc = 0.0;
-    for (int p = a; p < b; p++) acc += c.stamp[(size_t)c.tgt_rows[p] * c.S + s];
-    part[threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double tot = 0.0;
-        for (int k = 0; k < 256; k++) tot += part[k];
-        ngb_asm_store(&c, tg, s, tot);
+    int p = lo;
+    for (; p + 4 <= hi; p += 4) {
+        const double a0 = c.stamp[(size_t)c.tgt_rows[p] * c.S + s], a1 = c.stamp[(size_t)c.tgt_rows[p + 1] * c.S + s];
+        const double a2 = c.stamp[(size_t)c.tgt_rows[p + 2] * c.S + s], a3 = c.stamp[(size_t)c.tgt_rows[p + 3] * c.S + s];
+        acc += a0; acc += a1; acc += a2; acc += a3;
     }
+    for (; p < hi; p++) acc += c.stamp[(size_t)c.tgt_rows[p] * c.S + s];
+    part[(size_t)ch * c.S + s] = acc;
+}
+__global__ void __launch_bounds__(256)
+ngb_k_assemble_long2(const NgbAsmCtx c, int li, const double *in, double *out, int n_in, int n_out)
+{
+    const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= (size_t)n_out * c.S) return;
+    const int g = (int)(u / (size_t)c.S), s = (int)(u - (size_t)g * c.S);
+    if (!c.ctl.active[s]) return;
+    const int lo = g * NGB_ASM_CHUNK, hi = min(lo + NGB_ASM_CHUNK, n_in);
+    double acc = 0.0;
+    int i = lo;
+    for (; i + 4 <= hi; i += 4) {
+        const double a0 = in[(size_t)i * c.S + s], a1 = in[(size_t)(i + 1) * c.S + s], a2 = in[(size_t)(i + 2) * c.S + s], a3 = in[(size_t)(i + 3) * c.S + s];
+        acc += a0; acc += a1; acc += a2; acc += a3;
+    }
+    for (; i < hi; i++) acc += in[(size_t)i * c.S + s];
+    if (n_out == 1) ngb_asm_store(&c, c.long_tgt[li], s, acc);
+    else out[(size_t)g * c.S + s] = acc;
 }
 
 /* one warp per sample: warp w of the CTA owns sample blockIdx.x * warps + w */
@@ -574,10 +591,21 @@ int ngb_launch_assemble(const NgbAsmCtx *c)
     const size_t total = (size_t)(c->nnz + c->neq1) * c->S;
     const unsigned grid = (unsigned)((total + 255) / 256);
     ngb_k_assemble<<<grid, 256, 0, g_stream>>>(*c, total);
-    if (c->nlong > 0) {
+    for (int li = 0; li < c->nlong; li++) {
         const int e = post_launch("assemble");
         if (e) return e;
-        ngb_k_assemble_long<<<(unsigned)(c->nlong * c->S), 256, 0, g_stream>>>(*c);
+        int n = (c->long_len_host[li] + NGB_ASM_CHUNK - 1) / NGB_ASM_CHUNK, half = 0;
+        if (!c->long_part || (size_t)n * c->S > (size_t)c->long_cap) { ngb_set_error("long-target scratch too small"); return NGB_E_PANIC; }
+        ngb_k_assemble_long1<<<(unsigned)(((size_t)n * c->S + 255) / 256), 256, 0, g_stream>>>(*c, li, c->long_part, n);
+        while (n > 1 || half == 0) {           /* at least one second-level pass: it is the one that stores the total */
+            const int m = (n + NGB_ASM_CHUNK - 1) / NGB_ASM_CHUNK;
+            const int e2 = post_launch("assemble_long");
+            if (e2) return e2;
+            ngb_k_assemble_long2<<<(unsigned)(((size_t)m * c->S + 255) / 256), 256, 0, g_stream>>>(*c, li, c->long_part + (size_t)half * c->long_cap,
+                                                                                                 c->long_part + (size_t)(1 - half) * c->long_cap, n, m);
+            n = m; half = 1 - half;
+            if (m == 1) break;
+        }
     }
     if (c->nov > 0) {
         const int e = post_launch("assemble");

@@ -32,7 +32,7 @@ int ngbSync(void) { return ngb_dev_sync(); }
 void ngbProfile(int enable, int every) { ngb_dev_profile(enable, every); }
 int ngbProfileRead(double *ms_sum, long *count) { return ngb_dev_profile_read(ms_sum, count); }
 int ngbProfileStages(double ms[8]) { return ngb_dev_stage_read(ms); }
-static unsigned b4_batch_key(const ngb_circuit *c, const double *mtab, int nrows, const int *prow_inst, int stride);
+static unsigned b4_batch_key(const ngb_circuit *c, const double *mtab, int nrows, const int *prow_inst);
 int ngbMeasureFp64Peak(double out[3]) { return ngb_dev_fp64_peak(out); }
 
 /* ------------------------------------------------------------------ field names */
@@ -1585,6 +1585,16 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
     b->d_tgt_rows = (int *)dev_dup(c->tgt_rows, sizeof(int) * (size_t)c->tgt_ptr[c->ntgt]);
     b->d_slot_diag = (int *)dev_dup(c->slot_diag, sizeof(int) * (size_t)c->nnz);
     b->d_long_tgt = (int *)dev_dup(c->long_tgt, sizeof(int) * (size_t)c->nlong);
+    if (c->nlong) {
+        int k2, mx = 0;
+        b->long_len = (int *)xcalloc((size_t)c->nlong, sizeof(int));
+        for (k2 = 0; k2 < c->nlong; k2++) {
+            b->long_len[k2] = c->tgt_ptr[c->long_tgt[k2] + 1] - c->tgt_ptr[c->long_tgt[k2]];
+            if ((b->long_len[k2] + NGB_ASM_CHUNK - 1) / NGB_ASM_CHUNK > mx) mx = (b->long_len[k2] + NGB_ASM_CHUNK - 1) / NGB_ASM_CHUNK;
+        }
+        b->long_cap = mx * S;
+        b->long_part = (double *)ngb_dev_malloc(sizeof(double) * 2 * (size_t)b->long_cap);
+    }
     /* constant stamp rows (resistors, source incidence): written once */
     if (c->nconst) {
         double *row = (double *)xcalloc((size_t)S, sizeof(double));
@@ -1600,8 +1610,7 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
         b->b4_state = (double *)dalloc(b, "b4.state", sizeof(double) * NGB_NHIST * B4ST_COUNT * T);
         b->b4_op = (double *)dalloc(b, "b4.op", sizeof(double) * B4O_COUNT * T);
         b->b4_mtab = (double *)dev_dup(c->b4_mtab, sizeof(double) * (size_t)c->b4_nrows * B4M_COUNT);
-        b->b4_key = b4_batch_key(c, c->b4_mtab, c->b4_nrows, c->b4_prow, 1);
-        b->b4_row_stride = 1;
+        b->b4_key = b4_batch_key(c, c->b4_mtab, c->b4_nrows, c->b4_prow);
         { const char *e = getenv("NGB_B4_GENERIC"); b->b4_force_generic = (e && atoi(e)) ? 1 : 0; }
         b->b4_ptab = (double *)dev_dup(c->b4_ptab, sizeof(double) * (size_t)c->b4_nrows * B4P_COUNT);
         reg(b, "b4.mtab", b->b4_mtab, sizeof(double) * (size_t)c->b4_nrows * B4M_COUNT);
@@ -1800,6 +1809,7 @@ void ngbBatchDestroy(ngb_batch *b)
     free(b->ms_eq); free(b->ms_kind); free(b->ms_count); free(b->ms_val); free(b->ms_td);
     for (i = 0; i < b->narr; i++)
         if (strcmp(b->arr[i].name, "b4.mtab") && strcmp(b->arr[i].name, "b4.ptab")) ngb_dev_free(b->arr[i].ptr);
+    free(b->long_len); ngb_dev_free(b->long_part);
     ngb_dev_free(b->d_node_type); ngb_dev_free(b->d_tgt_ptr); ngb_dev_free(b->d_tgt_rows); ngb_dev_free(b->d_slot_diag); ngb_dev_free(b->d_long_tgt);
     ngb_dev_free(b->b4_mtab); ngb_dev_free(b->b4_ptab); ngb_dev_free(b->b4_prow); ngb_dev_free(b->b4_flags);
     ngb_dev_free(b->b4_nodes); ngb_dev_free(b->b4_spos); ngb_dev_free(b->b4_prow_t);
@@ -1862,64 +1872,29 @@ int ngbBatchSetResistors(ngb_batch *b, const double *g)
 }
 
 /* per-thread parameter rows (Monte-Carlo with model-parameter mismatch): prow [ninst*S] */
-static int set_bsim4_rows(ngb_batch *b, const int *prow_t, int nrows, const double *mtab, const double *ptab, int field_major)
+int ngbBatchSetBsim4Rows(ngb_batch *b, const int *prow_t, int nrows, const double *mtab, const double *ptab)
 {
     const size_t T = (size_t)b->c->b4_n * b->S;
     ngb_dev_free(b->b4_prow_t); ngb_dev_free(b->b4_mtab); ngb_dev_free(b->b4_ptab);
     b->b4_prow_t = (int *)dev_dup(prow_t, sizeof(int) * T);
     b->b4_mtab = (double *)dev_dup(mtab, sizeof(double) * (size_t)nrows * B4M_COUNT);
     b->b4_ptab = (double *)dev_dup(ptab, sizeof(double) * (size_t)nrows * B4P_COUNT);
-    b->b4_row_stride = field_major ? nrows : 1;
-    memset(b->b4_mvary, 0, sizeof b->b4_mvary); memset(b->b4_pvary, 0, sizeof b->b4_pvary);
-    if (field_major) {
-        /* rows must be numbered r * S + s (the samples of parameter set r are consecutive): the kernel reads the columns
-         * that do not differ between the samples of a set once per warp, at the set's first row */
-        const int S = b->S;
-        size_t q; int f, r, s2;
-        if (nrows % S) { ngb_set_error("field-major BSIM4 rows: the row count %d is not a multiple of the %d samples", nrows, S); return NGB_E_PANIC; }
-        for (q = 0; q < T; q++)
-            if (prow_t[q] < 0 || prow_t[q] >= nrows || prow_t[q] % S != (int)(q % (size_t)S)) {
-                ngb_set_error("field-major BSIM4 rows must be numbered r * S + s (thread %ld has row %d)", (long)q, prow_t[q]); return NGB_E_PANIC;
-            }
-        for (f = 0; f < B4M_COUNT; f++)
-            for (r = 0; r < nrows / S && !((b->b4_mvary[f >> 6] >> (f & 63)) & 1ull); r++)
-                for (s2 = 1; s2 < S; s2++)
-                    if (memcmp(&mtab[(size_t)f * nrows + (size_t)r * S + s2], &mtab[(size_t)f * nrows + (size_t)r * S], sizeof(double))) { b->b4_mvary[f >> 6] |= 1ull << (f & 63); break; }
-        for (f = 0; f < B4P_COUNT; f++)
-            for (r = 0; r < nrows / S && !((b->b4_pvary[f >> 6] >> (f & 63)) & 1ull); r++)
-                for (s2 = 1; s2 < S; s2++)
-                    if (memcmp(&ptab[(size_t)f * nrows + (size_t)r * S + s2], &ptab[(size_t)f * nrows + (size_t)r * S], sizeof(double))) { b->b4_pvary[f >> 6] |= 1ull << (f & 63); break; }
-    }
-    b->b4_key = b4_batch_key(b->c, mtab, nrows, NULL, field_major ? nrows : 1);
-    if (field_major && b->b4_key != NGB_B4_GENERIC) b->b4_key = NGB_B4_KEY_ROWST(b->b4_key);
+    b->b4_key = b4_batch_key(b->c, mtab, nrows, NULL);
     return (b->b4_prow_t && b->b4_mtab && b->b4_ptab) ? NGB_OK : NGB_E_PANIC;
-}
-int ngbBatchSetBsim4Rows(ngb_batch *b, const int *prow_t, int nrows, const double *mtab, const double *ptab)
-{
-    return set_bsim4_rows(b, prow_t, nrows, mtab, ptab, 0);
-}
-/* the same with the tables stored field-major: mtab_t [B4M_COUNT][nrows], ptab_t [B4P_COUNT][nrows].  For per-sample rows
- * (continuous model-parameter mismatch, ngbBsim4Temp per sample) number the rows so that consecutive samples of an instance
- * have consecutive rows: a warp then reads each parameter as one coalesced line instead of one table row per lane */
-int ngbBatchSetBsim4RowsT(ngb_batch *b, const int *prow_t, int nrows, const double *mtab_t, const double *ptab_t)
-{
-    return set_bsim4_rows(b, prow_t, nrows, mtab_t, ptab_t, 1);
 }
 
 /* the variant key of a batch (bsim4_variants.h): the selectors of every model row in use and of every instance must agree */
-static unsigned b4_batch_key(const ngb_circuit *c, const double *mtab, int nrows, const int *prow_inst, int stride)
+static unsigned b4_batch_key(const ngb_circuit *c, const double *mtab, int nrows, const int *prow_inst)
 {
     unsigned key = NGB_B4_GENERIC;
     int i, first = 1;
     if (!c->b4_n) return key;
     for (i = 0; i < (prow_inst ? c->b4_n : nrows); i++) {
-        const size_t row = (size_t)(prow_inst ? prow_inst[i] : i);
-        const double *M = mtab + (stride > 1 ? row : row * B4M_COUNT);
-        const size_t q = (size_t)(stride > 1 ? stride : 1);              /* field-major tables: field f of a row is q doubles on */
+        const double *M = mtab + (size_t)(prow_inst ? prow_inst[i] : i) * B4M_COUNT;
         const int fl = c->b4_flags[prow_inst ? i : 0];
-        const int v[13] = { (int)M[B4M_mobMod * q], (int)M[B4M_capMod * q], (int)M[B4M_cvchargeMod * q], (int)M[B4M_dioMod * q], (int)M[B4M_rdsMod * q],
-                            (int)M[B4M_igcMod * q], (int)M[B4M_igbMod * q], (int)M[B4M_gidlMod * q], (int)M[B4M_tempMod * q], (int)M[B4M_mtrlMod * q],
-                            (int)M[B4M_mtrlCompatMod * q], B4F_RBODY(fl), B4F_RGATE(fl) };
+        const int v[13] = { (int)M[B4M_mobMod], (int)M[B4M_capMod], (int)M[B4M_cvchargeMod], (int)M[B4M_dioMod], (int)M[B4M_rdsMod],
+                            (int)M[B4M_igcMod], (int)M[B4M_igbMod], (int)M[B4M_gidlMod], (int)M[B4M_tempMod], (int)M[B4M_mtrlMod],
+                            (int)M[B4M_mtrlCompatMod], B4F_RBODY(fl), B4F_RGATE(fl) };
         unsigned k;
         if (!(B4K_FITS(mobMod, v[0]) && B4K_FITS(capMod, v[1]) && B4K_FITS(cvchargeMod, v[2]) && B4K_FITS(dioMod, v[3]) &&
               B4K_FITS(rdsMod, v[4]) && B4K_FITS(igcMod, v[5]) && B4K_FITS(igbMod, v[6]) && B4K_FITS(gidlMod, v[7]) &&
@@ -1952,8 +1927,6 @@ void ngb_fill_b4ctx(ngb_batch *b, B4Ctx *x)
     x->mtab = b->b4_mtab; x->ptab = b->b4_ptab;
     x->prow = b->b4_prow_t ? b->b4_prow_t : b->b4_prow; x->prow_per_thread = b->b4_prow_t ? 1 : 0;
     x->variant = (!b->b4_force_generic && b4_variant_built(b->b4_key)) ? b->b4_key : NGB_B4_GENERIC;
-    x->row_stride = b->b4_row_stride > 0 ? b->b4_row_stride : 1;
-    memcpy(x->mvary, b->b4_mvary, sizeof x->mvary); memcpy(x->pvary, b->b4_pvary, sizeof x->pvary);
     x->inst = b->b4_inst; x->flags = b->b4_flags; x->nodes = b->b4_nodes; x->spos = b->b4_spos;
     x->stamp = b->stamp; x->state = b->b4_state; x->op = b->b4_op; x->op_full = b->op_full;
     x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl; x->temp = c->opt.temp; x->vt0 = c->opt.vt0;
@@ -2008,7 +1981,7 @@ void ngb_fill_asmctx(ngb_batch *b, NgbAsmCtx *x)
     const ngb_circuit *c = b->c;
     memset(x, 0, sizeof *x);
     x->S = b->S; x->nnz = c->nnz; x->neq1 = b->neq1; x->tgt_ptr = b->d_tgt_ptr; x->tgt_rows = b->d_tgt_rows;
-    x->slot_diag = b->d_slot_diag; x->long_tgt = b->d_long_tgt; x->nlong = c->nlong; x->stamp = b->stamp; x->Ax = b->Ax; x->x = b->x; x->add_diag_gmin = 1; x->ctl = b->ctl;
+    x->slot_diag = b->d_slot_diag; x->long_tgt = b->d_long_tgt; x->nlong = c->nlong; x->long_len_host = b->long_len; x->long_part = b->long_part; x->long_cap = b->long_cap; x->stamp = b->stamp; x->Ax = b->Ax; x->x = b->x; x->add_diag_gmin = 1; x->ctl = b->ctl;
     x->nov = c->ov_n; x->ov_eq = b->ov_eq; x->ov_kind = b->ov_kind; x->ov_cur = b->ov_cur; x->ov_diag = b->ov_diag;
     x->ov_zptr = b->ov_zptr; x->ov_zslot = b->ov_zslot; x->ov_val = b->ov_val;
 }

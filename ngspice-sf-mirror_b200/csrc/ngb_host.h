@@ -63,6 +63,7 @@ struct ngb_batch {
     double *x, *Ax, *stamp;
     int *errflag;
     int *d_node_type, *d_tgt_ptr, *d_tgt_rows, *d_slot_diag, *d_long_tgt;
+    int *long_len; double *long_part; int long_cap;      /* long assembly targets: lengths (host), chunk-total scratch (device) */
     int lte_deferred;                 /* transient driver: BSIM4trunc in its own launch after the solve */
     double *b4_inst, *b4_state, *b4_op, *b4_mtab, *b4_ptab; int *b4_prow, *b4_prow_t, *b4_flags, *b4_nodes, *b4_spos;
     double *cap_par, *cap_state; int *cap_nodes, *cap_spos;
@@ -78,9 +79,7 @@ struct ngb_batch {
     struct { const char *name; void *ptr; size_t bytes; } arr[NGB_MAX_ARR];
     int narr;
     struct ngb_tran *tran;
-    unsigned long long b4_mvary[2], b4_pvary[3];   /* field-major rows: columns that differ between the samples of a parameter set */
     int load_lte;              /* ngbBatchSetLoadLte: direct ngbLoad calls evaluate DEVtrunc's bounds inside the load (off by default) */
-    int b4_row_stride;         /* 1, or the row count of field-major per-sample tables (ngbBatchSetBsim4RowsT) */
     unsigned b4_key;           /* variant key of the BSIM4 instances (bsim4_variants.h); NGB_B4_GENERIC when they differ */
     int b4_force_generic;      /* ngbBatchSetBsim4Generic / NGB_B4_GENERIC=1: run the generic kernel whatever the key */
     /* measurement clauses for the next ngbTranRun (ngbTranSetMeasures) */

@@ -106,13 +106,18 @@ typedef struct NgbSrcCtx {
 #define NGB_LU_EVENTS 4
 #define NGB_LU_SETS 16     /* 0..3: the pivoting events of a run; the rest: per-sample re-pivots after a zero pivot (ngb_tran.c) */
 #define NGB_ASM_LONG 4096
+#define NGB_ASM_CHUNK 256
 typedef struct NgbAsmCtx {
     int S, nnz, neq1;
     const int *tgt_ptr, *tgt_rows;
     const int *slot_diag;   /* [nnz] 1 if the slot is a diagonal entry (LoadGmin_CSC)    */
-    /* targets with more than NGB_ASM_LONG contributions (supply rails of a large flat circuit) are left
-     * to a second launch that sums them as 256 in-order chunks, then the chunk totals in order */
+    /* targets with more than NGB_ASM_LONG contributions (supply rails of a large flat circuit) are left to a tree of
+     * launches: chunks of NGB_ASM_CHUNK consecutive contributions summed in order by one thread each, then chunks of chunk
+     * totals, ... -- deterministic, every level fully parallel (a rail of 10^6 contributions: 3 907 + 16 + 1 threads) */
     const int *long_tgt; int nlong;
+    const int *long_len_host;   /* HOST pointer [nlong]: contributions per long target (launch geometry) */
+    double *long_part;          /* [2][long_cap] chunk totals, ping-pong between levels */
+    int long_cap;
     const double *stamp;
     double *Ax;             /* [S][nnz]                                                  */
     double *x;              /* rhs is assembled into x[1 - xsel]                         */

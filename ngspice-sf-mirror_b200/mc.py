@@ -64,8 +64,9 @@ def bsim4_with_toxe(lib, raw, toxe, delvto, temp=None, vt0=None):
     and per-instance threshold shifts delvto[s]; its model / bin / instance rows are computed by the library's own BSIM4temp
     (csrc/ngb_b4temp.c) from the nominal raw tables `raw` = {"model", "inst", "inst_model", "temp", "vt0"} (oracle dump keys
     b4t/*).  Returns (inst [NI][ninst][S], prow_t [ninst*S], mtab [R*S][NM], ptab [R*S][NP]) like bsim4_with_tox_levels; R rows
-    per sample (one per distinct model and size), numbered r * S + s: the samples of one parameter set are consecutive rows
-    (what Batch.set_bsim4_rows(field_major=True) wants)."""
+    per sample (one per distinct model and size), numbered r * S + s.  (Measured on B200, profiles/r02_experiments.md: per-sample
+    rows cost the load kernel 17 % against rows shared by a warp; storing them field-major, or only the columns that differ
+    between samples, was slower than these plain table rows.)"""
     from .b4temp import Bsim4Temp
     T = Bsim4Temp(lib)
     toxe = np.asarray(toxe, dtype=np.float64)

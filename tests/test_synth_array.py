@@ -61,3 +61,26 @@ def test_synthetic_array_scales(hostsim_lib):
     circ = pkg.Circuit.from_flat(hostsim_lib, fl)
     pat = circ.pattern()
     assert pat["n"] == 10 * 600 + 4 and int(fl["b4/ninst"][0]) == 1200
+
+
+@pytest.mark.gpu
+def test_long_rail_assembly_tree_gpu(cuda_lib, hostsim_lib):
+    """a 48 x 48 array: the supply rail's matrix entries and right-hand side collect 2 304+ contributions per transistor
+    type -- more than NGB_ASM_LONG = 4 096 in total --, summed on the device by the chunk tree (ngb_k_assemble_long1 / 2).
+    Against the host build's strictly sequential sums: every Ax / rhs entry within 1e-12 relative (other summation order
+    in those few rows, identical everywhere else)"""
+    base = ngt.read(f"{GOLDEN}/ro17k.flat.ngt")
+    fl = synth.inverter_array(base, 48, 48)
+    names = fl.pop("node/names")
+    rng = np.random.default_rng(5)
+    xval = {n: float(rng.uniform(0.0, 2.0)) for n in names[1:]}
+    A1, r1 = _load_by_name(hostsim_lib, fl, names, xval)
+    A2, r2 = _load_by_name(cuda_lib, fl, names, xval)
+    assert A1.keys() == A2.keys()
+    same = 0
+    for k in A1:
+        assert abs(A1[k] - A2[k]) <= 1e-12 * max(abs(A1[k]), 1e-30), (k, A1[k], A2[k])
+        same += A1[k] == A2[k]
+    for k in r1:
+        assert abs(r1[k] - r2[k]) <= 1e-12 * max(abs(r1[k]), 1e-18), k
+    assert same >= len(A1) - 64          # only the rail rows may differ in the last place

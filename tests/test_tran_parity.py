@@ -441,10 +441,9 @@ def test_tran_gpu_tox_and_vth_mismatch(cuda_lib):
         _compare(res, t, v, ngt.read(f"{GOLDEN}/ro17tox{s}.wave.ngt"), s, exact=True)
 
 
-def _tox_batch_own_temp(lib, field_major, copies=1):
+def _tox_batch_own_temp(lib, copies=1):
     """the same two samples, but their model / bin / instance rows come from the library's own BSIM4temp (csrc/ngb_b4temp.c)
-    applied to the NOMINAL card with each sample's toxe and delvto -- nothing recorded per oxide thickness -- and the rows are
-    stored per sample, field-major on the device when `field_major`"""
+    applied to the NOMINAL card with each sample's toxe and delvto -- nothing recorded per oxide thickness -- one set of rows per sample"""
     base = ngt.read(f"{GOLDEN}/ro17k.flat.ngt")
     trace = ngt.read(f"{GOLDEN}/ro17k.trace.ngt.gz")
     tab = ngt.read(f"{GOLDEN}/b4temp.tables.ngt.gz")
@@ -462,25 +461,23 @@ def _tox_batch_own_temp(lib, field_major, copies=1):
     circ = pkg.Circuit.from_flat(lib, base, lu_pattern=run_patterns(trace))
     b = pkg.Batch(circ, 2 * copies)
     b.put("b4.inst", inst)
-    b.set_bsim4_rows(prow_t, mtab, ptab, field_major=field_major)
-    assert b.bsim4_variant()[1]            # a specialised kernel exists for both layouts of this card
+    b.set_bsim4_rows(prow_t, mtab, ptab)
+    assert b.bsim4_variant()[1]            # the specialised kernel serves per-sample rows too
     wave0 = ngt.read(f"{GOLDEN}/ro17tox0.wave.ngt")
     res = b.tran(1024, wave0["save_eq"])
     t, v = res.waves()
     return res, t, v
 
 
-@pytest.mark.parametrize("field_major", [False, True])
-def test_tran_hostsim_continuous_tox_own_bsim4temp(hostsim_lib, field_major):
-    res, t, v = _tox_batch_own_temp(hostsim_lib, field_major)
+def test_tran_hostsim_continuous_tox_own_bsim4temp(hostsim_lib):
+    res, t, v = _tox_batch_own_temp(hostsim_lib)
     for s in range(2):
         _compare(res, t, v, ngt.read(f"{GOLDEN}/ro17tox{s}.wave.ngt"), s, exact=True)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("field_major", [False, True])
-def test_tran_gpu_continuous_tox_own_bsim4temp(cuda_lib, field_major):
-    res, t, v = _tox_batch_own_temp(cuda_lib, field_major, copies=48)       # 96 samples: three warps per instance
+def test_tran_gpu_continuous_tox_own_bsim4temp(cuda_lib):
+    res, t, v = _tox_batch_own_temp(cuda_lib, copies=48)       # 96 samples: three warps per instance
     for s in range(96):
         _compare(res, t, v, ngt.read(f"{GOLDEN}/ro17tox{s % 2}.wave.ngt"), s, exact=True)
 
