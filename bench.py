@@ -309,7 +309,7 @@ def workload_config(args):
                         ".tran .1ns 150ns uic from alternating `.ic` stage voltages, per-instance delvto mismatch sigma 15 mV and per-sample toxe "
                         + ("~ N(1.4 nm, 3 %), continuous (rows by the library's BSIM4temp)" if getattr(args, "tox", "continuous") == "continuous" else "from 8 levels of N(1.4 nm, 3 %)"),
             "samples_per_gpu": args.samples, "bsim4_instances": 34, "unknowns": 155,
-            "layout": "per-sample parameter rows" if getattr(args, "tox", "continuous") == "continuous"
+            "layout": ("per-sample parameter rows, " + ("draws unsorted" if os.environ.get("NGB_BENCH_UNSORTED") else "samples laid out by toxe (same draws)")) if getattr(args, "tox", "continuous") == "continuous"
                       else ("draws unsorted" if os.environ.get("NGB_BENCH_UNSORTED") else "samples laid out level by level (same draws)"),
             "l2": "inputs larger than L2: per-step working set (parameters+states+stamps+matrices) ~%.0f MB" %
                   (args.samples * 34 * (51 + 4 * 29 + 38 + 52) * 8 / 1e6 + args.samples * 904 * 8 / 1e6)}
@@ -369,6 +369,11 @@ def bench_ours(args):
                    "temp": b4t["ro17k/b4t/temp"][0, 0], "vt0": b4t["ro17k/opt/vt0"][0]}
             sigma = float(os.environ.get("NGB_BENCH_TOX_SIGMA", "0.03"))       # 1e-9: distinct rows, identical dynamics (measures the row access alone)
             tox_raw = 1.4e-9 * (1.0 + sigma * np.random.default_rng(5000 + rank).normal(size=S))
+            if not os.environ.get("NGB_BENCH_UNSORTED"):
+                # same draws, laid out by oxide thickness: the 32 samples a warp evaluates then oscillate at nearly the same
+                # period and stay in step for longer (the load kernel's cost is the divergence between them)
+                order = np.argsort(tox_raw, kind="stable")
+                tox_raw, dv, dv_raw = tox_raw[order], dv[order], dv_raw[order]
             tox = np.array([pkg.mc.spice_number(f"{x:.17g}") for x in tox_raw])     # what the reference's parser makes of the card text
             inst_host, prow_t, mtab_all, ptab_all = pkg.mc.bsim4_with_toxe(lib, raw, tox, dv)
             tox_of = lambda p: float(tox_raw[p])
