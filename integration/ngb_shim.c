@@ -221,7 +221,8 @@ static int flatten_vbic(CKTcircuit *ckt)
         for (h = VBICinstances(m); h; h = VBICnextInstance(h), i++) {
             double p[VBIC_NP];
             const int nd[VBN_COUNT] = { h->VBICcollNode, h->VBICbaseNode, h->VBICemitNode, h->VBICsubsNode, h->VBICcollCXNode,
-                h->VBICcollCINode, h->VBICbaseBXNode, h->VBICbaseBINode, h->VBICemitEINode, h->VBICbaseBPNode, h->VBICsubsSINode };
+                h->VBICcollCINode, h->VBICbaseBXNode, h->VBICbaseBINode, h->VBICemitEINode, h->VBICbaseBPNode, h->VBICsubsSINode,
+                        (h->VBIC_selfheat && h->VBICtempNode > 0) ? h->VBICtempNode : 0, h->VBIC_excessPhase ? h->VBICxf1Node : 0, h->VBIC_excessPhase ? h->VBICxf2Node : 0 };
             static const struct { int k; size_t off; } upd[] = {
 #define U(kk, f) { kk, offsetof(VBICinstance, f) }
                 U(1, VBICtextCollResist), U(2, VBICtintCollResist), U(3, VBICtepiSatVoltage), U(4, VBICtepiDoping), U(6, VBICtextBaseResist),
@@ -242,7 +243,7 @@ static int flatten_vbic(CKTcircuit *ckt)
             aux[(size_t)VBA_type * n + i] = m->VBICtype; aux[(size_t)VBA_tVcrit * n + i] = h->VBICtVcrit;
             aux[(size_t)VBA_icVBE * n + i] = h->VBICicVBE; aux[(size_t)VBA_icVCE * n + i] = h->VBICicVCE;
             aux[(size_t)VBA_scale * n + i] = h->VBICarea * h->VBICm; aux[(size_t)VBA_temp * n + i] = h->VBICtemp;
-            flags[i] = (h->VBICoff ? VBF_OFF : 0) | (h->VBIC_selfheat ? VBF_SELFHEAT : 0) | (h->VBIC_excessPhase ? VBF_EXCESS : 0);
+            flags[i] = (h->VBICoff ? VBF_OFF : 0) | ((h->VBIC_selfheat && h->VBICtempNode > 0) ? VBF_SELFHEAT : 0) | (h->VBIC_excessPhase ? VBF_EXCESS : 0);
             G.sbq[i] = h->VBICstate;
         }
     rc = ngbCircuitAddVbic(G.C, n, nodes, flags, par, aux);

@@ -184,7 +184,10 @@ class Circuit:
         if n:
             par = _f64(flat["vbic/par"]); aux = _f64(flat["vbic/aux"])
             assert par.shape[0] == lib.vbic_layout[0] and aux.shape[0] == lib.vbic_layout[1]
-            lib.check(lib.L.ngbCircuitAddVbic(c.h, int(n), _ip(_i32(flat["vbic/nodes"])), _ip(_i32(flat["vbic/flags"])),
+            vnodes = np.asarray(flat["vbic/nodes"])
+            if vnodes.shape[0] < lib.vbic_layout[2]:        # fixtures recorded before the thermal / excess-phase node roles existed
+                vnodes = np.concatenate([vnodes, np.zeros((lib.vbic_layout[2] - vnodes.shape[0], vnodes.shape[1]), vnodes.dtype)], axis=0)
+            lib.check(lib.L.ngbCircuitAddVbic(c.h, int(n), _ip(_i32(vnodes)), _ip(_i32(flat["vbic/flags"])),
                                               _dp(par), _dp(aux)), "ngbCircuitAddVbic")
         n = sc(flat, "vsrc/n", 0)
         if n:

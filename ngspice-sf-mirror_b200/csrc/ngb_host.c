@@ -353,6 +353,9 @@ int ngbCircuitAddBsim3(ngb_circuit *c, int ninst, const int *nodes, const int *f
 #define ei VBN_ei
 #define bp VBN_bp
 #define si VBN_si
+#define temp VBN_temp
+#define xf1 VBN_xf1
+#define xf2 VBN_xf2
 static const int vb_struct_r[] = {
 #define T(r, cc) r,
     NGB_VBIC_STRUCT(T)
@@ -366,16 +369,35 @@ static const int vb_struct_c[] = {
 static const int vb_stamp_r[] = {
 #define SR(n, v) n,
 #define SM(r, cc, v) r,
-    NGB_VBIC_STAMPS(SR, SM)
+    NGB_VBIC_STAMPS(SR, SM, SR, SM, SR, SM, SR, SM)
 #undef SR
 #undef SM
 };
 static const int vb_stamp_c[] = {           /* -1: right-hand side */
 #define SR(n, v) -1,
 #define SM(r, cc, v) cc,
-    NGB_VBIC_STAMPS(SR, SM)
+    NGB_VBIC_STAMPS(SR, SM, SR, SM, SR, SM, SR, SM)
 #undef SR
 #undef SM
+};
+static const int vb_stamp_need[] = {        /* instance flags a stamp statement exists for (0: every instance) */
+#define F0(a, v) 0,
+#define F0M(a, b, v) 0,
+#define FX(a, v) VBF_EXCESS,
+#define FXM(a, b, v) VBF_EXCESS,
+#define FS(a, v) VBF_SELFHEAT,
+#define FSM(a, b, v) VBF_SELFHEAT,
+#define FSX(a, v) (VBF_SELFHEAT | VBF_EXCESS),
+#define FSXM(a, b, v) (VBF_SELFHEAT | VBF_EXCESS),
+    NGB_VBIC_STAMPS(F0, F0M, FX, FXM, FS, FSM, FSX, FSXM)
+#undef F0
+#undef F0M
+#undef FX
+#undef FXM
+#undef FS
+#undef FSM
+#undef FSX
+#undef FSXM
 };
 #undef coll
 #undef base
@@ -388,17 +410,23 @@ static const int vb_stamp_c[] = {           /* -1: right-hand side */
 #undef ei
 #undef bp
 #undef si
+#undef temp
+#undef xf1
+#undef xf2
 void ngbVbicLayout(int out[5]) { out[0] = VBIC_NP; out[1] = VBA_COUNT; out[2] = VBN_COUNT; out[3] = VBS_COUNT; out[4] = VBIC_NSTAMPS; }
 
 int ngbCircuitAddVbic(ngb_circuit *c, int n, const int *nodes, const int *flags, const double *par, const double *aux)
 {
     int i;
     if (c->finalized || c->vb_n) return NGB_E_PANIC;
-    for (i = 0; i < n; i++)
-        if (flags[i] & VBF_UNSUPPORTED) {
-            ngb_set_error("VBIC instance %d: self-heating (0x2) / excess phase (0x4) not on this path (flags 0x%x)", i, flags[i]);
-            return NGB_E_UNSUPP;
+    for (i = 0; i < n; i++) {
+        /* the thermal node and the filter nodes exist exactly for the instances that carry the flag (vbicsetup.c:470-523) */
+        const int tn = nodes[VBN_temp * n + i], x1 = nodes[VBN_xf1 * n + i], x2 = nodes[VBN_xf2 * n + i];
+        if (((flags[i] & VBF_SELFHEAT) != 0) != (tn > 0) || ((flags[i] & VBF_EXCESS) != 0) != (x1 > 0 && x2 > 0)) {
+            ngb_set_error("VBIC instance %d: flags 0x%x do not match its thermal / excess-phase nodes (%d, %d, %d)", i, flags[i], tn, x1, x2);
+            return NGB_E_PANIC;
         }
+    }
     c->vb_n = n;
     c->vb_nodes = (int *)xdup(nodes, sizeof(int) * VBN_COUNT * (size_t)n);
     c->vb_flags = (int *)xdup(flags, sizeof(int) * (size_t)n);
@@ -774,6 +802,7 @@ int ngbCircuitFinalize(ngb_circuit *c)
     for (i = 0; i < c->vb_n; i++)
         for (k = 0; k < VBIC_NSTAMPS; k++) {
             const int rr = c->vb_nodes[vb_stamp_r[k] * c->vb_n + i];
+            if ((c->vb_flags[i] & vb_stamp_need[k]) != vb_stamp_need[k]) { c->vb_spos[k * c->vb_n + i] = -1; continue; }   /* statement absent for this instance */
             if (vb_stamp_c[k] < 0) c->vb_spos[k * c->vb_n + i] = new_row(c, &cb, (rr > 0 && c->eq2col[rr] >= 0) ? c->nnz + rr : -1);
             else c->vb_spos[k * c->vb_n + i] = new_row(c, &cb, slot_lookup(c, rr, c->vb_nodes[vb_stamp_c[k] * c->vb_n + i]));
         }

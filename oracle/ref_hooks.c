@@ -524,7 +524,8 @@ static void dump_vbic(FILE *f, CKTcircuit *ckt)
                 for (h = VBICinstances(m); h; h = VBICnextInstance(h), i++) {
                     double p[VBIC_NP];
                     const int nd[VBN_COUNT] = { h->VBICcollNode, h->VBICbaseNode, h->VBICemitNode, h->VBICsubsNode, h->VBICcollCXNode,
-                        h->VBICcollCINode, h->VBICbaseBXNode, h->VBICbaseBINode, h->VBICemitEINode, h->VBICbaseBPNode, h->VBICsubsSINode };
+                        h->VBICcollCINode, h->VBICbaseBXNode, h->VBICbaseBINode, h->VBICemitEINode, h->VBICbaseBPNode, h->VBICsubsSINode,
+                        (h->VBIC_selfheat && h->VBICtempNode > 0) ? h->VBICtempNode : 0, h->VBIC_excessPhase ? h->VBICxf1Node : 0, h->VBIC_excessPhase ? h->VBICxf2Node : 0 };
                     for (k = 0; k < VBN_COUNT; k++) nodes[(size_t)k * n + i] = nd[k];
                     memcpy(p, &m->VBICtnom, sizeof p);
                     p[0] = h->VBICtemp - CONSTCtoK + p[105];
@@ -541,7 +542,7 @@ static void dump_vbic(FILE *f, CKTcircuit *ckt)
                     aux[(size_t)VBA_type * n + i] = m->VBICtype; aux[(size_t)VBA_tVcrit * n + i] = h->VBICtVcrit;
                     aux[(size_t)VBA_icVBE * n + i] = h->VBICicVBE; aux[(size_t)VBA_icVCE * n + i] = h->VBICicVCE;
                     aux[(size_t)VBA_scale * n + i] = h->VBICarea * h->VBICm; aux[(size_t)VBA_temp * n + i] = h->VBICtemp;
-                    flags[i] = (h->VBICoff ? VBF_OFF : 0) | (h->VBIC_selfheat ? VBF_SELFHEAT : 0) | (h->VBIC_excessPhase ? VBF_EXCESS : 0);
+                    flags[i] = (h->VBICoff ? VBF_OFF : 0) | ((h->VBIC_selfheat && h->VBICtempNode > 0) ? VBF_SELFHEAT : 0) | (h->VBIC_excessPhase ? VBF_EXCESS : 0);
                     sb[i] = h->VBICstate;
                     nb += (size_t)snprintf(names + nb, 64, "%s\n", h->VBICname);
                 }

@@ -309,7 +309,7 @@ def run(name, netlist, calls, save):
     os.makedirs(TMP, exist_ok=True)
     cir = os.path.join(TMP, name + ".cir")
     open(cir, "w").write(netlist)
-    if name in ("ro17", "ro101", "ro17k", "ro17kg", "invg", "inv", "dio", "b3ring", "arr", "vbic", "mix", "latch", "srcs", "mixsrc", "invsrc", "invgmin", "invshunt"):
+    if name in ("ro17", "ro101", "ro17k", "ro17kg", "invg", "vbicsh", "vbicxf", "vbicshxf", "inv", "dio", "b3ring", "arr", "vbic", "mix", "latch", "srcs", "mixsrc", "invsrc", "invgmin", "invshunt"):
         # the netlist itself is kept too: the CPU-baseline arm of bench.py feeds it to oracle/_ref/ngspice
         os.makedirs(os.path.join(HERE, "netlists"), exist_ok=True)
         open(os.path.join(HERE, "netlists", name + ".cir"), "w").write(netlist)
@@ -408,6 +408,21 @@ if __name__ == "__main__":
         run("diog", gear(dio_netlist()), "0-3", ["out", "z", "w", "u", "vin#branch"])
         run("b3ringg", gear(b3_netlist(5)), "0-3", ["out", "buf", "n2", "vdd#branch"])
         run("mixg", gear(mix_netlist(*MIX_POINTS[0])), "0-3", ["a8", "x", "y4", "cq", "e2", "vdd#branch", "v33#branch"])
+    if "vbicth" in which:
+        # VBIC self-heating (RTH / CTH on both cards: thermal node, d/dVrth stamps, DEVlimitlog) and excess phase (TD: the
+        # xf1 / xf2 filter nodes), alone and together -- tests/vbic/CEamp.cir's card has both
+        base = vbic_netlist()
+        # the thermal node is the fifth terminal `dt` (without it RTH is not connected, vbicsetup.c)
+        withdt = base.replace("q1 c b 0 0 n1", "q1 c b 0 0 t1 n1").replace("q2 0 c e2 vp p1", "q2 0 c e2 vp t2 p1") \
+                     .replace("q3 o1 in t 0 n1 area=2", "q3 o1 in t 0 t3 n1 area=2").replace("q4 o2 r t 0 n1 area=2 m=1.5", "q4 o2 r t 0 t4 n1 area=2 m=1.5")
+        assert withdt.count(" t1 ") == 1 and withdt.count(" t4 ") == 1
+        sh = withdt.replace("+ is=1e-16 ibei=1e-18", "+ rth=300 cth=1e-9 is=1e-16 ibei=1e-18").replace("+ is=2e-16 ibei=2e-18", "+ rth=500 cth=5e-10 is=2e-16 ibei=2e-18")
+        xf = base.replace("+ is=1e-16 ibei=1e-18", "+ td=5e-12 is=1e-16 ibei=1e-18")
+        both = sh.replace("+ rth=300 cth=1e-9", "+ td=5e-12 rth=300 cth=1e-9")
+        save = ["c", "e2", "o1", "o2", "b", "vcc#branch"]
+        run("vbicsh", sh, "0-3", save + ["t1", "t2", "t4"])
+        run("vbicxf", xf, "0-3", save)
+        run("vbicshxf", both, "0-3", save + ["t1", "t2", "t4"])
     if "ro17kmeas" in which:
         run_meas("ro17k", ro_netlist(17, tran=".tran .1ns 20ns uic", kick=True))
     if "ro17mc" in which:

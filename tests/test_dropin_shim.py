@@ -64,7 +64,7 @@ def _vbic_close(v0, v1):
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(a), floor[None, :])))
 
 
-@pytest.mark.parametrize("name", ["vbic", "mix"])
+@pytest.mark.parametrize("name", ["vbic", "mix", "vbicsh", "vbicxf", "vbicshxf"])
 def test_dropin_hostsim_vbic_rawfile(name):
     v0, v1 = _check(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb_hostsim"), name, "hostsim")
     # per point; the mixed cell holds a ring oscillator whose edges carry the VBIC rounding difference through zero crossings (5.7e-9)
@@ -78,7 +78,7 @@ def test_dropin_hostsim_load_only_identical():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["vbic", "mix"])
+@pytest.mark.parametrize("name", ["vbic", "mix", "vbicshxf"])
 def test_dropin_gpu_vbic_rawfile(name):
     v0, v1 = _check(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb"), name, "cuda-sm_100a")
     assert _vbic_close(v0, v1) <= (1e-8 if name == "mix" else 1e-9)      # see test_dropin_hostsim_vbic_rawfile

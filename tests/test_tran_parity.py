@@ -99,6 +99,16 @@ def test_tran_hostsim_fallback_batch(hostsim_lib, name):
         _compare(res, t, v, wave, s, exact=True)
 
 
+@pytest.mark.parametrize("name", ["vbicsh", "vbicxf", "vbicshxf"])
+def test_tran_hostsim_vbic_selfheating_excess_phase(hostsim_lib, name):
+    """VBIC electro-thermal (RTH / CTH, thermal node `dt`, DEVlimitlog) and excess phase (TD, the xf1 / xf2 filter nodes), alone
+    and together (vbicload.c:668-672, 703-748, 1268-1478): identical accepted / rejected / iteration counts, node voltages,
+    branch current AND the temperature rise of three devices within 1e-9 per point.  The d/dVrth partials are the tenth
+    component of the same dual number the other partials come from"""
+    res, t, v, wave = _run(hostsim_lib, name)
+    _compare(res, t, v, wave, 0, exact=False)
+
+
 def test_tran_hostsim_vbic(hostsim_lib):
     """VBIC stages (DC operating point + PULSE transient): identical accepted / rejected / iteration
     counts and 1e-9 on the waveforms.  Not bit-identical by construction: the Jacobian entries come from
@@ -338,6 +348,14 @@ def test_tran_gpu_matches_reference(cuda_lib, name, exact):
     _compare(res, t, v, wave, 0, exact=False)
     if exact:
         _compare(res, t, v, wave, 0, exact=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["vbicsh", "vbicxf", "vbicshxf"])
+def test_tran_gpu_vbic_selfheating_excess_phase(cuda_lib, name):
+    res, t, v, wave = _run(cuda_lib, name, S=33)
+    for s in (0, 32):
+        _compare(res, t, v, wave, s, exact=False)
 
 
 @pytest.mark.gpu
