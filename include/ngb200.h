@@ -90,19 +90,21 @@ int ngbCircuitAddCapacitors(ngb_circuit *c, int n, const int *nodes /* [2][n] */
 int ngbCircuitAddBsim3(ngb_circuit *c, int ninst, const int *nodes, const int *flags, const int *prow,
                        const double *inst, int nrows, const double *mtab, const double *ptab);
 void ngbBsim3Layout(int out[6]);               /* model, bin, instance, node roles, stamp rows, states */
-/* junction diodes after DIOsetup/DIOtemp (dio/diosetup.c, diotemp.c): nodes [4][n] pos neg posPrime
- * posSwPrime (posPrime == pos without series resistance; posSwPrime only with a separate sidewall diode),
- * flags [n] DIOF_* and par [DIOP_COUNT][n] as listed in csrc/dio_fields.h -- replaces the
- * DIOinstance/DIOmodel walk of DIOload (dio/dioload.c:75-80).  Self-heating and soft reverse recovery
- * return E_UNSUPP */
+/* junction diodes after DIOsetup/DIOtemp (dio/diosetup.c, diotemp.c): nodes [6][n] pos neg posPrime
+ * posSwPrime temp qp (posPrime == pos without series resistance; posSwPrime only with a separate sidewall
+ * diode; temp != 0 exactly when flags has DIOF_SELFHEAT, qp != 0 exactly when it has DIOF_REVREC),
+ * flags [n] DIOF_* and par [DIOP_COUNT][n] as listed in csrc/dio_fields.h (the raw model/instance rows
+ * at the end are read only by instances with self-heating, whose load maps the parameters to
+ * DIOtemp + delTemp every iteration like DIOtempUpdate, diotemp.c:18) -- replaces the
+ * DIOinstance/DIOmodel walk of DIOload (dio/dioload.c:75-80) */
 int ngbCircuitAddDiodes(ngb_circuit *c, int n, const int *nodes, const int *flags, const double *par);
 /* VBIC bipolar transistors (4-terminal) after VBICsetup/VBICtemp (vbic/vbicsetup.c, vbictemp.c):
- * nodes [11][n] coll base emit subs collCX collCI baseBX baseBI emitEI baseBP subsSI (an internal node
- * equals its terminal when the series resistance is absent), flags [n] (0x1 off, 0x2 self-heating,
+ * nodes [14][n] coll base emit subs collCX collCI baseBX baseBI emitEI baseBP subsSI temp xf1 xf2 (an
+ * internal node equals its terminal when the series resistance is absent; temp != 0 exactly with the
+ * self-heating flag, xf1/xf2 != 0 exactly with the excess-phase flag), flags [n] (0x1 off, 0x2 self-heating,
  * 0x4 excess phase), par [108][n] the parameter vector exactly as VBICload assembles it per instance
  * (vbic/vbicload.c:127-166), aux [6][n] type, tVcrit, icVBE, icVCE, area*m, temp -- replaces the
- * VBICinstance/VBICmodel walk of VBICload (vbicload.c:100-107).  Self-heating and excess phase return
- * E_UNSUPP.  ngbVbicLayout: [0]=parameters [1]=aux [2]=node roles [3]=states [4]=stamp rows */
+ * VBICinstance/VBICmodel walk of VBICload (vbicload.c:100-107).  ngbVbicLayout: [0]=parameters [1]=aux [2]=node roles [3]=states [4]=stamp rows */
 int ngbCircuitAddVbic(ngb_circuit *c, int n, const int *nodes, const int *flags, const double *par, const double *aux);
 void ngbVbicLayout(int out[5]);
 int ngbCircuitAddVsources(ngb_circuit *c, int n, const int *nodes /* [3][n] pos neg branch */,

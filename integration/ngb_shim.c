@@ -176,7 +176,7 @@ static int flatten_dio(CKTcircuit *ckt)
     DIOmodel *m; DIOinstance *h;
     int n = G.nd, i = 0, rc; int *nodes, *flags; double *par;
     if (!n) return 0;
-    nodes = (int *)xc((size_t)n * 4, sizeof(int)); flags = (int *)xc((size_t)n, sizeof(int)); G.sbd = (int *)xc((size_t)n, sizeof(int));
+    nodes = (int *)xc((size_t)n * DION_COUNT, sizeof(int)); flags = (int *)xc((size_t)n, sizeof(int)); G.sbd = (int *)xc((size_t)n, sizeof(int));
     par = (double *)xc((size_t)n * DIOP_COUNT, sizeof(double));
     for (m = (DIOmodel *)ckt->CKThead[G.tDIO]; m; m = DIOnextModel(m))
         for (h = DIOinstances(m); h; h = DIOnextInstance(h), i++) {
@@ -184,6 +184,7 @@ static int flatten_dio(CKTcircuit *ckt)
             nodes[i] = h->DIOposNode; nodes[n + i] = h->DIOnegNode; nodes[2 * n + i] = h->DIOposPrimeNode;
             nodes[3 * n + i] = h->DIOposSwPrimeNode;
             if (h->DIOoff) fl |= DIOF_OFF;
+            if (m->DIOresistGiven) fl |= DIOF_RESIST;
             if (m->DIObreakdownVoltageGiven) fl |= DIOF_BV;
             if (m->DIOsatSWCurGiven) fl |= DIOF_SATSW;
             if (m->DIOswEmissionCoeffGiven) fl |= DIOF_NSW;
@@ -197,11 +198,19 @@ static int flatten_dio(CKTcircuit *ckt)
             if ((h->DIOtempNode > 0) && h->DIOthermal && m->DIOrth0Given) fl |= DIOF_SELFHEAT;
             if ((h->DIOqpNode > 0) && (m->DIOsoftRevRecParam != 0) && (h->DIOtTransitTime != 0)) fl |= DIOF_REVREC;
             flags[i] = fl; G.sbd[i] = h->DIOstate;
+            nodes[4 * n + i] = (fl & DIOF_SELFHEAT) ? h->DIOtempNode : 0;      /* unused thermal / qp nodes stay with the reference's own stamps (none) */
+            nodes[5 * n + i] = (fl & DIOF_REVREC) ? h->DIOqpNode : 0;
 #define X(nm) par[(size_t)(k++) * n + i] = h->DIO##nm;
             NGB_DIO_INST_FIELDS(X)
 #undef X
 #define X(nm) par[(size_t)(k++) * n + i] = m->DIO##nm;
             NGB_DIO_MODEL_FIELDS(X)
+#undef X
+#define X(nm) par[(size_t)(k++) * n + i] = h->DIO##nm;
+            NGB_DIO_RAW_INST_FIELDS(X)
+#undef X
+#define X(nm) par[(size_t)(k++) * n + i] = m->DIO##nm;
+            NGB_DIO_RAW_MODEL_FIELDS(X)
 #undef X
         }
     rc = ngbCircuitAddDiodes(G.C, n, nodes, flags, par);

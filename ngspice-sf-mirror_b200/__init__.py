@@ -177,9 +177,14 @@ class Circuit:
         n = sc(flat, "dio/n", 0)
         if n:
             par = _f64(flat["dio/par"])
+            if par.shape[0] < lib.dio_layout[0]:             # fixtures recorded before the raw rows of self-heating existed
+                par = np.ascontiguousarray(np.concatenate([par, np.zeros((lib.dio_layout[0] - par.shape[0], par.shape[1]))], axis=0))
             assert par.shape[0] == lib.dio_layout[0], "fixture built against a different diode field list"
-            lib.check(lib.L.ngbCircuitAddDiodes(c.h, int(n), _ip(_i32(flat["dio/nodes"][[0, 1, 3, 4]])), _ip(_i32(flat["dio/flags"])),
-                                                _dp(par)), "ngbCircuitAddDiodes")
+            dfl = _i32(flat["dio/flags"])
+            dnodes = np.array(np.asarray(flat["dio/nodes"])[[0, 1, 3, 4, 2, 5]])    # the dump's order is pos neg temp pos' posSw' qp
+            dnodes[4] = np.where(dfl & 0x800, dnodes[4], 0)
+            dnodes[5] = np.where(dfl & 0x1000, dnodes[5], 0)
+            lib.check(lib.L.ngbCircuitAddDiodes(c.h, int(n), _ip(_i32(dnodes)), _ip(dfl), _dp(par)), "ngbCircuitAddDiodes")
         n = sc(flat, "vbic/n", 0)
         if n:
             par = _f64(flat["vbic/par"]); aux = _f64(flat["vbic/aux"])

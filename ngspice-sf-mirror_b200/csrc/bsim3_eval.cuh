@@ -1495,7 +1495,7 @@ NGB_HD int b3_load_thread(const B3Ctx *c, size_t t)
             for (int k = 0; k < B3ST_COUNT; k++) {
                 if (sop & NGB_OP_COPY01) B3ST(1, k) = B3ST(0, k);
                 if (sop & NGB_OP_COPY1_23) { const double v = B3ST(1, k); B3ST(2, k) = v; if (nh > 3) B3ST(3, k) = v; }
-                if ((sop & NGB_OP_COPY23) && nh > 3) B3ST(3, k) = B3ST(2, k);
+                if (sop & NGB_OP_COPY23) { const double v = B3ST(2, k); B3ST(0, k) = v; if (nh > 3) B3ST(3, k) = v; }
             }
         }
     }

@@ -2993,7 +2993,7 @@ NGB_HD int b4_prologue(const B4Ctx *c, size_t t, int first, B4Pro *p, int *err)
             for (int k = 0; k < B4ST_COUNT; k++) {
                 if (sop & NGB_OP_COPY01) B4ST(1, k) = B4ST(0, k);
                 if (sop & NGB_OP_COPY1_23) { const double v = B4ST(1, k); B4ST(2, k) = v; if (c->ctl.nhist > 3) B4ST(3, k) = v; }
-                if ((sop & NGB_OP_COPY23) && c->ctl.nhist > 3) B4ST(3, k) = B4ST(2, k);
+                if (sop & NGB_OP_COPY23) { const double v = B4ST(2, k); B4ST(0, k) = v; if (c->ctl.nhist > 3) B4ST(3, k) = v; }
             }
         }
     }

@@ -55,6 +55,8 @@ static const char *dio_par_names[] = {
 #define X(n) #n,
     NGB_DIO_INST_FIELDS(X)
     NGB_DIO_MODEL_FIELDS(X)
+    NGB_DIO_RAW_INST_FIELDS(X)
+    NGB_DIO_RAW_MODEL_FIELDS(X)
 #undef X
 };
 void ngbDioLayout(int out[3]) { out[0] = DIOP_COUNT; out[1] = DIOST_COUNT; out[2] = DIOS_COUNT; }
@@ -439,11 +441,11 @@ int ngbCircuitAddDiodes(ngb_circuit *c, int n, const int *nodes, const int *flag
     int i;
     if (c->finalized || c->dio_n) return NGB_E_PANIC;
     for (i = 0; i < n; i++)
-        if (flags[i] & DIOF_UNSUPPORTED) {
-            ngb_set_error("diode %d: model option not on this path (flags 0x%x: self-heating 0x800, soft reverse recovery 0x1000)", i, flags[i] & DIOF_UNSUPPORTED);
-            return NGB_E_UNSUPP;
+        if (((flags[i] & DIOF_SELFHEAT) != 0) != (nodes[4 * n + i] > 0) || ((flags[i] & DIOF_REVREC) != 0 && nodes[5 * n + i] <= 0)) {
+            ngb_set_error("diode %d: flags 0x%x do not match its thermal / qp nodes (%d, %d)", i, flags[i], nodes[4 * n + i], nodes[5 * n + i]);
+            return NGB_E_PANIC;
         }
-    c->dio_n = n; c->dio_nodes = (int *)xdup(nodes, sizeof(int) * 4 * (size_t)n);
+    c->dio_n = n; c->dio_nodes = (int *)xdup(nodes, sizeof(int) * DION_COUNT * (size_t)n);
     c->dio_flags = (int *)xdup(flags, sizeof(int) * (size_t)n);
     c->dio_par = (double *)xdup(par, sizeof(double) * DIOP_COUNT * (size_t)n);
     return NGB_OK;
@@ -610,6 +612,16 @@ int ngbCircuitFinalize(ngb_circuit *c)
             int ps = c->dio_nodes[3 * c->dio_n + i];
             coo_push(&coo, p, ps); coo_push(&coo, q, ps); coo_push(&coo, ps, p); coo_push(&coo, ps, q); coo_push(&coo, ps, ps);
         }
+        if (c->dio_flags[i] & DIOF_SELFHEAT) {       /* diosetup.c:454-467 */
+            const int tn = c->dio_nodes[4 * c->dio_n + i];
+            coo_push(&coo, tn, p); coo_push(&coo, tn, pp); coo_push(&coo, tn, q); coo_push(&coo, tn, tn);
+            coo_push(&coo, p, tn); coo_push(&coo, pp, tn); coo_push(&coo, q, tn);
+            if (c->dio_flags[i] & DIOF_RESISTSW) { int ps = c->dio_nodes[3 * c->dio_n + i]; coo_push(&coo, tn, ps); coo_push(&coo, ps, tn); }
+        }
+        if (c->dio_flags[i] & DIOF_REVREC) {         /* diosetup.c:470-476 */
+            const int qn = c->dio_nodes[5 * c->dio_n + i];
+            coo_push(&coo, qn, qn); coo_push(&coo, qn, pp); coo_push(&coo, qn, q); coo_push(&coo, pp, qn); coo_push(&coo, q, qn);
+        }
     }
     for (i = 0; i < c->res_n; i++) {
         int p = c->res_nodes[i], q = c->res_nodes[c->res_n + i];
@@ -756,27 +768,37 @@ int ngbCircuitFinalize(ngb_circuit *c)
         int p = c->dio_nodes[i], q = c->dio_nodes[nn + i], pp = c->dio_nodes[2 * nn + i], ps = c->dio_nodes[3 * nn + i], k2;
         const int sw = (c->dio_flags[i] & DIOF_RESISTSW) != 0;
         for (k2 = 0; k2 < DIOS_COUNT; k2++) c->dio_spos[k2 * nn + i] = -1;
-        c->dio_spos[DIOS_rhsNeg * nn + i] = new_row(c, &cb, q > 0 ? c->nnz + q : -1);
-        c->dio_spos[DIOS_rhsPosPrime * nn + i] = new_row(c, &cb, pp > 0 ? c->nnz + pp : -1);
-        if (sw) {
-            c->dio_spos[DIOS_rhsNegSw * nn + i] = new_row(c, &cb, q > 0 ? c->nnz + q : -1);
-            c->dio_spos[DIOS_rhsPosSwPrime * nn + i] = new_row(c, &cb, ps > 0 ? c->nnz + ps : -1);
-        }
-        c->dio_spos[DIOS_posPos * nn + i] = new_row(c, &cb, slot_lookup(c, p, p));
-        c->dio_spos[DIOS_negNeg * nn + i] = new_row(c, &cb, slot_lookup(c, q, q));
-        c->dio_spos[DIOS_ppPp * nn + i] = new_row(c, &cb, slot_lookup(c, pp, pp));
-        c->dio_spos[DIOS_posPp * nn + i] = new_row(c, &cb, slot_lookup(c, p, pp));
-        c->dio_spos[DIOS_negPp * nn + i] = new_row(c, &cb, slot_lookup(c, q, pp));
-        c->dio_spos[DIOS_ppPos * nn + i] = new_row(c, &cb, slot_lookup(c, pp, p));
-        c->dio_spos[DIOS_ppNeg * nn + i] = new_row(c, &cb, slot_lookup(c, pp, q));
-        if (sw) {
-            c->dio_spos[DIOS_posPosSw * nn + i] = new_row(c, &cb, slot_lookup(c, p, p));
-            c->dio_spos[DIOS_negNegSw * nn + i] = new_row(c, &cb, slot_lookup(c, q, q));
-            c->dio_spos[DIOS_pspPsp * nn + i] = new_row(c, &cb, slot_lookup(c, ps, ps));
-            c->dio_spos[DIOS_posPsp * nn + i] = new_row(c, &cb, slot_lookup(c, p, ps));
-            c->dio_spos[DIOS_negPsp * nn + i] = new_row(c, &cb, slot_lookup(c, q, ps));
-            c->dio_spos[DIOS_pspPos * nn + i] = new_row(c, &cb, slot_lookup(c, ps, p));
-            c->dio_spos[DIOS_pspNeg * nn + i] = new_row(c, &cb, slot_lookup(c, ps, q));
+        {
+            const int th = (c->dio_flags[i] & DIOF_SELFHEAT) != 0, rr = (c->dio_flags[i] & DIOF_REVREC) != 0;
+            const int tn = c->dio_nodes[4 * nn + i], qn = c->dio_nodes[5 * nn + i];
+#define DROW_R(pos, node) c->dio_spos[(pos) * nn + i] = new_row(c, &cb, (node) > 0 ? c->nnz + (node) : -1)
+#define DROW_M(pos, r, cc) c->dio_spos[(pos) * nn + i] = new_row(c, &cb, slot_lookup(c, (r), (cc)))
+            DROW_R(DIOS_rhsNeg, q); DROW_R(DIOS_rhsPosPrime, pp);
+            if (th) { DROW_R(DIOS_thRhsPos, p); DROW_R(DIOS_thRhsPp, pp); DROW_R(DIOS_thRhsNeg, q); DROW_R(DIOS_thRhsTemp, tn); }
+            if (sw) {
+                DROW_R(DIOS_rhsNegSw, q); DROW_R(DIOS_rhsPosSwPrime, ps);
+                if (th) { DROW_R(DIOS_thRhsPosSw, p); DROW_R(DIOS_thRhsPsp, ps); DROW_R(DIOS_thRhsNegSw, q); DROW_R(DIOS_thRhsTempSw, tn); }
+            }
+            DROW_M(DIOS_posPos, p, p); DROW_M(DIOS_negNeg, q, q); DROW_M(DIOS_ppPp, pp, pp); DROW_M(DIOS_posPp, p, pp);
+            DROW_M(DIOS_negPp, q, pp); DROW_M(DIOS_ppPos, pp, p); DROW_M(DIOS_ppNeg, pp, q);
+            if (th) {
+                DROW_M(DIOS_thTempPos, tn, p); DROW_M(DIOS_thTempPp, tn, pp); DROW_M(DIOS_thTempNeg, tn, q); DROW_M(DIOS_thTempTemp, tn, tn);
+                DROW_M(DIOS_thPosTemp, p, tn); DROW_M(DIOS_thPpTemp, pp, tn); DROW_M(DIOS_thNegTemp, q, tn);
+            }
+            if (sw) {
+                DROW_M(DIOS_posPosSw, p, p); DROW_M(DIOS_negNegSw, q, q); DROW_M(DIOS_pspPsp, ps, ps); DROW_M(DIOS_posPsp, p, ps);
+                DROW_M(DIOS_negPsp, q, ps); DROW_M(DIOS_pspPos, ps, p); DROW_M(DIOS_pspNeg, ps, q);
+                if (th) {
+                    DROW_M(DIOS_thTempPosSw, tn, p); DROW_M(DIOS_thTempPsp, tn, ps); DROW_M(DIOS_thTempNegSw, tn, q);
+                    DROW_M(DIOS_thPosTempSw, p, tn); DROW_M(DIOS_thPspTemp, ps, tn); DROW_M(DIOS_thNegTempSw, q, tn);
+                }
+            }
+            if (rr) {
+                DROW_R(DIOS_rrRhsQp, qn); DROW_M(DIOS_rrQpQp, qn, qn); DROW_M(DIOS_rrQpPp, qn, pp); DROW_M(DIOS_rrQpNeg, qn, q);
+                DROW_R(DIOS_rrRhsPp, pp); DROW_R(DIOS_rrRhsNeg, q); DROW_M(DIOS_rrPpQp, pp, qn); DROW_M(DIOS_rrNegQp, q, qn);
+            }
+#undef DROW_R
+#undef DROW_M
         }
     }
     c->is_spos = (int *)xcalloc((size_t)c->is_n * 2 + 1, sizeof(int));
@@ -1672,7 +1694,7 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
         const size_t T = (size_t)c->dio_n * S;
         b->dio_par = (double *)dalloc_rep(b, "dio.par", c->dio_par, DIOP_COUNT, c->dio_n, S);
         b->dio_state = (double *)dalloc(b, "dio.state", sizeof(double) * NGB_NHIST * DIOST_COUNT * T);
-        b->dio_nodes = (int *)dev_dup(c->dio_nodes, sizeof(int) * 4 * (size_t)c->dio_n);
+        b->dio_nodes = (int *)dev_dup(c->dio_nodes, sizeof(int) * DION_COUNT * (size_t)c->dio_n);
         b->dio_flags = (int *)dev_dup(c->dio_flags, sizeof(int) * (size_t)c->dio_n);
         b->dio_spos = (int *)dev_dup(c->dio_spos, sizeof(int) * DIOS_COUNT * (size_t)c->dio_n);
     }

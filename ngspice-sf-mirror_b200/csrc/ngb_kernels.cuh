@@ -48,7 +48,7 @@ NGB_HD int ngb_cap_thread(const NgbCapCtx *c, size_t t)
             for (int k = 0; k < 2; k++) {
                 if (sop & NGB_OP_COPY01) CST(1, k) = CST(0, k);
                 if (sop & NGB_OP_COPY1_23) { const double v = CST(1, k); CST(2, k) = v; if (c->ctl.nhist > 3) CST(3, k) = v; }
-                if ((sop & NGB_OP_COPY23) && c->ctl.nhist > 3) CST(3, k) = CST(2, k);
+                if (sop & NGB_OP_COPY23) { const double v = CST(2, k); CST(0, k) = v; if (c->ctl.nhist > 3) CST(3, k) = v; }
             }
         }
     }

@@ -405,7 +405,9 @@ NGB_HD void ngb_next_time(const NgbTranCtx *c, int s)
         const int sop = c->ctl.stateop[s];
         c->ctl.head[s] = (c->ctl.head[s] + nh - 1) % nh;
         /* pending copies seen from the rotated frame: state1 = state0 is what the rotation itself
-         * does; state2 = state1, state3 = state1 leaves only state3 = state2 to do */
+         * does; state2 = state1, state3 = state1 leaves state3 = state2 and state0 = state2 to do (the old state3 is the
+         * new state0: its stale content is what DIOload's limiting of a separate sidewall diode reads under MODEINITPRED,
+         * dioload.c:177-192 copies DIOvoltage but not DIOvoltageSW) */
         c->ctl.stateop[s] = (sop & NGB_OP_COPY1_23) ? NGB_OP_COPY23 : 0;
     }
     ngb_begin_point(c, s);
@@ -541,6 +543,9 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
             niret = NGB_E_PANIC;
         }
     }
+#ifdef NGB_TRAN_DEBUG_PRINT
+    fprintf(stderr, "DBG s=%d t=%.17g it=%d mode=%x noncon_in=%d noncon=%d niret=%d order=%d delta=%.17g\n", s, c->ctl.time[s], iterno, c->ctl.mode[s], c->ctl.noncon[s], noncon, niret, c->ctl.order[s], c->ctl.delta[s]);
+#endif
     /* reset the per-tick flags for the next load */
     const double lte = c->ctl.lte[s], lte2 = c->ctl.lte2[s];
     c->ctl.noncon[s] = 0; c->nodeconv_w[s] = 0; c->ctl.lte[s] = 1e300; c->ctl.lte2[s] = 1e300;

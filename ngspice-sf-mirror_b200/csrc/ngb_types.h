@@ -51,7 +51,7 @@ typedef struct NgbCtl {
 /* deferred state copies of dctran.c (each device thread owns its own state slice) */
 #define NGB_OP_COPY01   1   /* memcpy(CKTstate1, CKTstate0)           dctran.c:319-322 */
 #define NGB_OP_COPY1_23 2   /* state2 = state1; state3 = state1       dctran.c:711-716 */
-#define NGB_OP_COPY23   4   /* the same copy seen after the ring rotated once          */
+#define NGB_OP_COPY23   4   /* the same copy seen after the ring rotated once: state3 = state2 and state0 (the old state3) = state2 */
 
 /* source waveform codes (vsrcdefs.h:146-160) */
 #define NGB_FN_PULSE 1

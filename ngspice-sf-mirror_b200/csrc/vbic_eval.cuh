@@ -377,7 +377,7 @@ NGB_HD int vbic_load_thread(const NgbVbicCtx *c, size_t t)
             for (int k = 0; k < VBS_COUNT; k++) {
                 if (sop & NGB_OP_COPY01) VST(1, k) = VST(0, k);
                 if (sop & NGB_OP_COPY1_23) { const double v = VST(1, k); VST(2, k) = v; if (nh > 3) VST(3, k) = v; }
-                if ((sop & NGB_OP_COPY23) && nh > 3) VST(3, k) = VST(2, k);
+                if (sop & NGB_OP_COPY23) { const double v = VST(2, k); VST(0, k) = v; if (nh > 3) VST(3, k) = v; }
             }
         }
     }

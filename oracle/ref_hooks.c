@@ -470,6 +470,7 @@ static void dump_dio(FILE *f, CKTcircuit *ckt, KLUmatrix *K)
                     if (m->DIOforwardSWKneeCurrentGiven) fl |= DIOF_IKP;
                     if (m->DIOrecSatCurGiven) fl |= DIOF_RECSAT;
                     if (m->DIOresistSWGiven) fl |= DIOF_RESISTSW;
+                    if (m->DIOresistGiven) fl |= DIOF_RESIST;
                     if ((h->DIOtempNode > 0) && h->DIOthermal && m->DIOrth0Given) fl |= DIOF_SELFHEAT;
                     if ((h->DIOqpNode > 0) && (m->DIOsoftRevRecParam != 0) && (h->DIOtTransitTime != 0)) fl |= DIOF_REVREC;
                     flags[i] = fl; sb[i] = h->DIOstate;
@@ -478,6 +479,12 @@ static void dump_dio(FILE *f, CKTcircuit *ckt, KLUmatrix *K)
 #undef X
 #define X(nm) par[(size_t)(k++) * n + i] = m->DIO##nm;
                     NGB_DIO_MODEL_FIELDS(X)
+#undef X
+#define X(nm) par[(size_t)(k++) * n + i] = h->DIO##nm;
+                    NGB_DIO_RAW_INST_FIELDS(X)
+#undef X
+#define X(nm) par[(size_t)(k++) * n + i] = m->DIO##nm;
+                    NGB_DIO_RAW_MODEL_FIELDS(X)
 #undef X
                     nb += (size_t)snprintf(names + nb, 64, "%s\n", h->DIOname);
                 }

@@ -114,6 +114,35 @@ def dio_netlist():
         ".end", ""])
 
 
+def diosh_netlist(selfheat=True, revrec=False):
+    """diodes with the thermal terminal `dt` (self-heating: rth0 / cth0, resistance and breakdown temperature coefficients,
+    tlev / tlevc mappings re-evaluated at the junction temperature every iteration, dioload.c:317-322) and / or the soft
+    reverse-recovery charge node qp (vp, tt: dioload.c:565-582, 836-862), switched hard enough to heat by tens of kelvin"""
+    th = lambda t: (f" {t}", " thermal") if selfheat else ("", "")
+    rr = " vp=0.4" if revrec else ""
+    sh = " rth0={r} cth0={c}" if selfheat else ""
+    L = ["* diodes with self-heating / soft reverse recovery",
+         "vin in 0 pulse(-8 8 20n 10n 10n 300n 700n)",
+         "r1 in a 20",
+         "d1 a 0{} dpow area=2{}".format(*th("t1")),
+         "r2 in z 60",
+         "d2 0 z{} dzen{}".format(*th("t2")),
+         "r3 in w 40",
+         "d3 w 0{} dsw3 pj=2{}".format(*th("t3")),
+         "r4 in u 100",
+         "d4 u 0{} dlean{}".format(*th("t4")),
+         "d5 0 u dplain",
+         ".model dpow d is=2e-13 rs=0.5 n=1.3 cjo=40p vj=0.75 m=0.4 tt=40n bv=60 ibv=1e-5 eg=1.11 xti=3 trs=2e-3 trs2=1e-6 tt1=1e-3 tm1=1e-4 tm2=1e-7" + rr + sh.format(r=60, c="2e-9"),
+         ".model dzen d is=1e-12 rs=2 bv=5.1 ibv=1e-3 nbv=1.3 cjo=30p tcv=-3e-4 tlev=1 tlevc=1 cta=2e-4 tpb=1e-3 tt=5n isr=1e-10 nr=2" + rr + sh.format(r=120, c="1e-9"),
+         ".model dsw3 d level=3 is=1e-14 rs=1.5 rsw=3 jsw=3e-13 ns=1.25 cjo=5p cjp=4p php=0.8 mjsw=0.33 tt=10n tlev=2 gap1=7.02e-4 gap2=1108 eg=1.16 trs=1e-3 jtun=1e-9 ntun=30 jtunsw=1e-10 ikf=0.5 ikp=0.2 bv=30" + rr + sh.format(r=200, c="5e-10"),
+         ".model dlean d is=5e-15 cjo=2p tt=20n" + rr + sh.format(r=400, c="2e-10"),
+         ".model dplain d is=5e-15 cjo=2p tt=2n",
+         ".option klu",
+         ".tran 2n 1.5u",
+         ".end", ""]
+    return "\n".join(L)
+
+
 def vbic_netlist():
     """VBIC (level 4): common-emitter stage with the full-featured card of tests/vbic/CEamp.cir (quasi-
     saturation, avalanche, parasitic transistor, knee currents; TD and RTH removed -- excess phase and
@@ -309,7 +338,7 @@ def run(name, netlist, calls, save):
     os.makedirs(TMP, exist_ok=True)
     cir = os.path.join(TMP, name + ".cir")
     open(cir, "w").write(netlist)
-    if name in ("ro17", "ro101", "ro17k", "ro17kg", "invg", "vbicsh", "vbicxf", "vbicshxf", "inv", "dio", "b3ring", "arr", "vbic", "mix", "latch", "srcs", "mixsrc", "invsrc", "invgmin", "invshunt"):
+    if name in ("ro17", "ro101", "ro17k", "ro17kg", "invg", "vbicsh", "vbicxf", "vbicshxf", "diosh", "diorr", "dioshrr", "inv", "dio", "b3ring", "arr", "vbic", "mix", "latch", "srcs", "mixsrc", "invsrc", "invgmin", "invshunt"):
         # the netlist itself is kept too: the CPU-baseline arm of bench.py feeds it to oracle/_ref/ngspice
         os.makedirs(os.path.join(HERE, "netlists"), exist_ok=True)
         open(os.path.join(HERE, "netlists", name + ".cir"), "w").write(netlist)
@@ -423,6 +452,11 @@ if __name__ == "__main__":
         run("vbicsh", sh, "0-3", save + ["t1", "t2", "t4"])
         run("vbicxf", xf, "0-3", save)
         run("vbicshxf", both, "0-3", save + ["t1", "t2", "t4"])
+    if "diosh" in which:
+        save = ["a", "z", "w", "u", "vin#branch"]
+        run("diosh", diosh_netlist(True, False), "0-3", save + ["t1", "t2", "t3", "t4"])
+        run("diorr", diosh_netlist(False, True), "0-3", save)
+        run("dioshrr", diosh_netlist(True, True), "0-3", save + ["t1", "t2", "t3", "t4"])
     if "ro17kmeas" in which:
         run_meas("ro17k", ro_netlist(17, tran=".tran .1ns 20ns uic", kick=True))
     if "ro17mc" in which:

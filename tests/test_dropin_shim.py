@@ -13,7 +13,7 @@ import pytest
 from parity_util import GOLDEN, ROOT
 
 REF = os.path.join(ROOT, "oracle", "_ref", "ngspice")
-NETLISTS = ["ro17k", "inv", "dio", "b3ring", "arr", "latch", "srcs", "invsrc", "invgmin", "invshunt"]     # invsrc / invgmin: CKTop's own source / gmin stepping drives CKTsrcFact and CKTdiagGmin through the shim
+NETLISTS = ["ro17k", "inv", "dio", "b3ring", "arr", "latch", "srcs", "invsrc", "invgmin", "invshunt", "diosh", "diorr", "dioshrr"]     # invsrc / invgmin: CKTop's own source / gmin stepping drives CKTsrcFact and CKTdiagGmin through the shim
 
 
 def _payload(path):
@@ -90,7 +90,7 @@ def test_dropin_gpu_rawfile(name):
     v0, v1 = _check(os.path.join(ROOT, "oracle", "_ref", "ngspice_ngb"), name, "cuda-sm_100a")
     if name in ("dio", "srcs"):   # SIN / SFFM / AM sources: CUDA's sin() is not glibc's; the north_star tolerance applies
         assert np.max(np.abs(v0 - v1) / np.maximum(np.abs(v0), 1e-6)) <= 1e-9
-    elif name in ("invsrc", "invgmin", "invshunt"):
+    elif name in ("invsrc", "invgmin", "invshunt", "diosh", "diorr", "dioshrr"):
         # added after the round's last GPU run: held to the north_star bar on the device (identical point count, 1e-9);
         # the bit-identity of these routes is shown on the host build above
         assert np.max(np.abs(v0 - v1) / np.maximum(np.abs(v0), 1e-6)) <= 1e-9

@@ -11,7 +11,7 @@ import pytest
 from parity_util import GOLDEN, ngt, pkg, relerr, replay_load, trace_calls, first_pattern
 
 DUAL = ("vbic", "mix", "vbicsh", "vbicxf", "vbicshxf")      # fixtures holding VBIC devices: derivatives by dual numbers, see vbic_eval.cuh
-CASES = ["ro17", "ro101", "inv", "dio", "b3ring", "vbic", "mix", "latch", "srcs", "vbicsh", "vbicxf", "vbicshxf"]   # latch: .nodeset / .ic row overrides; srcs: PWL / EXP / SFFM / AM sources      # inv: DC operating point (INITJCT/INITFIX/INITFLOAT) + PULSE transient
+CASES = ["ro17", "ro101", "inv", "dio", "b3ring", "vbic", "mix", "latch", "srcs", "vbicsh", "vbicxf", "vbicshxf", "diosh", "diorr", "dioshrr"]   # latch: .nodeset / .ic row overrides; srcs: PWL / EXP / SFFM / AM sources      # inv: DC operating point (INITJCT/INITFIX/INITFLOAT) + PULSE transient
 
 
 def _load_case(name):
@@ -65,7 +65,7 @@ def _check(lib, name, tol_state, tol_mat, S=1, tol_scaled=None):
             if "dio" in maps:
                 assert relerr(ours["dio_state"][0, :, :, s], ref["state0"][maps["dio"]], 1e-300).max() <= tol_state, (name, call, "dio state0")
                 if ref["mode"] & 0x1000 and ref["state1"] is not None:
-                    qrows = [6, 7]         # capCharge, capCurrent
+                    qrows = [6, 7, 10, 11, 15, 16]         # capCharge, capCurrent, qth, cqth, srcapCharge, srcapCurrent
                     assert relerr(ours["dio_state"][1, :, :, s][qrows], ref["state1"][maps["dio"]][qrows], 1e-300).max() <= tol_state
             if "vbic" in maps:
                 # currents, charges, capacitor currents and limited voltages are bit-exact; the partial

@@ -109,6 +109,15 @@ def test_tran_hostsim_vbic_selfheating_excess_phase(hostsim_lib, name):
     _compare(res, t, v, wave, 0, exact=False)
 
 
+@pytest.mark.parametrize("name", ["diosh", "diorr", "dioshrr"])
+def test_tran_hostsim_diode_selfheating_soft_recovery(hostsim_lib, name):
+    """diodes with the thermal terminal (rth0 / cth0: DIOtempUpdate at DIOtemp + delTemp inside every load, DEVlimitlog on
+    the temperature rise, the d/dT stamps) and with the soft reverse-recovery charge node qp (vp, tt), alone and together
+    (dioload.c:80-81, 317-322, 565-582, 736-862): every accepted point bit-identical, temperatures included"""
+    res, t, v, wave = _run(hostsim_lib, name)
+    _compare(res, t, v, wave, 0, exact=True)
+
+
 def test_tran_hostsim_vbic(hostsim_lib):
     """VBIC stages (DC operating point + PULSE transient): identical accepted / rejected / iteration
     counts and 1e-9 on the waveforms.  Not bit-identical by construction: the Jacobian entries come from
@@ -339,7 +348,8 @@ def test_tran_hostsim_mc_batch(hostsim_lib):
 # tolerance) but identical accepted / rejected / iteration counts are required.
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,exact", [("ro17k", True), ("ro17", True), ("inv", True), ("dio", False), ("b3ring", True), ("vbic", False), ("latch", True), ("srcs", False),
-                                        ("invsrc", False), ("invgmin", False), ("invshunt", False)])    # not yet run on a device: north_star bar
+                                        ("invsrc", False), ("invgmin", False), ("invshunt", False),
+                                        ("diosh", False), ("diorr", False), ("dioshrr", False)])    # diode self-heating / soft recovery: north_star bar on the device, bit-identity shown on the host build
 def test_tran_gpu_matches_reference(cuda_lib, name, exact):
     """north_star bar: 1e-9 relative and identical accepted-step count; the device arithmetic
     (no FMA contraction, glibc-compatible exp/log) in fact reproduces the reference bit for bit.
