@@ -71,6 +71,22 @@ ngb_k_bsim4_lte(const B4Ctx c)
     if (lane == 0) { ngb_atomic_min_pos(&c.ctl.lte[s], m1); ngb_atomic_min_pos(&c.ctl.lte2[s], m2); }
 }
 
+/* the same bounds with one CTA per sample and one (instance, charge) pair per thread: a converged sample's 34 x 5 CKTterr
+ * bodies run side by side instead of ten deep per lane (the minimum is exact in any order) */
+__global__ void __launch_bounds__(256)
+ngb_k_bsim4_lte_cta(const B4Ctx c)
+{
+    const int s = blockIdx.x;
+    if (!b4_lte_wanted(&c, s)) return;
+    double m1 = 1e300, m2 = 1e300;
+    for (int task = threadIdx.x; task < c.ninst * 6; task += blockDim.x) b4_lte_task(&c, task / 6, task % 6, s, &m1, &m2);
+    for (int o = 16; o > 0; o >>= 1) {
+        m1 = fmin(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+        m2 = fmin(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    }
+    if ((threadIdx.x & 31) == 0 && (m1 < 1e300 || m2 < 1e300)) { ngb_atomic_min_pos(&c.ctl.lte[s], m1); ngb_atomic_min_pos(&c.ctl.lte2[s], m2); }
+}
+
 __global__ void __launch_bounds__(256)
 ngb_k_cap_load(const NgbCapCtx c, int *errflag)
 {
@@ -121,6 +137,67 @@ ngb_k_assemble(const NgbAsmCtx c, size_t total)
     const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= total) return;
     ngb_asm_thread(&c, u);
+}
+
+/* batches: a CTA takes a tile of 32 targets x 32 samples.  The gather reads the stamp rows with the lanes on the samples
+ * (the rows are sample-fastest), the matrix values leave through shared memory with the lanes on the targets: Ax is
+ * sample-major for the LU kernel, and written straight from the gather every lane of a store hits another 32-byte sector.
+ * Right-hand-side targets are sample-fastest like the stamp rows and are stored from the gather. */
+__global__ void __launch_bounds__(256)
+ngb_k_assemble_tiled(const NgbAsmCtx c, int ntile_s)
+{
+    __shared__ double tile[32][33];
+    const int ts = (int)(blockIdx.x % (unsigned)ntile_s), tt = (int)(blockIdx.x / (unsigned)ntile_s);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int S = c.S, ntg = c.nnz + c.neq1;
+    {
+        const int s = ts * 32 + lane;
+        const bool act = s < S && c.ctl.active[s];
+        /* most targets collect one or two stamp rows: the first row of each of the thread's four targets is fetched
+         * before any sum starts (four independent DRAM loads in flight), the rest of a list follows in list order */
+        int lo[4], hi[4];
+        double acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int tg = tt * 32 + w * 4 + j;
+            lo[j] = hi[j] = 0;
+            if (act && tg < ntg) {
+                lo[j] = c.tgt_ptr[tg]; hi[j] = c.tgt_ptr[tg + 1];
+                if (hi[j] - lo[j] > NGB_ASM_LONG && c.nlong) hi[j] = lo[j] = -1;       /* ngb_k_assemble_long*'s job */
+            } else lo[j] = hi[j] = -1;
+        }
+        int r[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) r[j] = (lo[j] < hi[j]) ? c.tgt_rows[lo[j]] : -1;
+        double a[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) a[j] = (r[j] >= 0) ? c.stamp[(size_t)r[j] * S + s] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int tg = tt * 32 + w * 4 + j;
+            if (lo[j] < 0) continue;
+            acc[j] = 0.0;
+            if (r[j] >= 0) acc[j] += a[j];
+            for (int p = lo[j] + 1; p < hi[j]; p++) acc[j] += c.stamp[(size_t)c.tgt_rows[p] * S + s];
+            if (tg >= c.nnz) { ngb_asm_store(&c, tg, s, acc[j]); continue; }
+            if (c.add_diag_gmin && c.slot_diag[tg]) {              /* LoadGmin_CSC, as in ngb_asm_store */
+                const double dg = c.ctl.diag_gmin[s];
+                if (dg != 0.0) acc[j] += dg;
+            }
+            tile[w * 4 + j][lane] = acc[j];
+        }
+    }
+    __syncthreads();
+    {
+        const int tg = tt * 32 + lane;
+        if (tg >= c.nnz) return;
+        if (c.nlong && c.tgt_ptr[tg + 1] - c.tgt_ptr[tg] > NGB_ASM_LONG) return;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int sl = w * 4 + j, s = ts * 32 + sl;
+            if (s < S && c.ctl.active[s]) c.Ax[(size_t)s * c.nnz + tg] = tile[lane][sl];
+        }
+    }
 }
 
 /* long contribution lists (ngb_types.h): level 1 sums chunks of stamp rows, the next levels chunks of chunk totals */
@@ -541,7 +618,13 @@ int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag)
 int ngb_launch_bsim4_lte(const B4Ctx *c)
 {
     if (c->T <= 0) return 0;
-    ngb_k_bsim4_lte<<<(unsigned)(((size_t)c->S * 32 + 127) / 128), 128, 0, g_stream>>>(*c);
+    static int wide = -1;
+    if (wide < 0) { const char *e = getenv("NGB_LTE_CTA"); wide = (e && atoi(e)) ? 1 : 0; }
+    if (wide && c->ninst * 6 >= 64) {
+        const int cta = c->ninst * 6 >= 192 ? 256 : (c->ninst * 6 >= 96 ? 128 : 64);
+        ngb_k_bsim4_lte_cta<<<(unsigned)c->S, cta, 0, g_stream>>>(*c);
+    } else
+        ngb_k_bsim4_lte<<<(unsigned)(((size_t)c->S * 32 + 127) / 128), 128, 0, g_stream>>>(*c);
     return post_launch("bsim4_lte");
 }
 int ngb_launch_cap_load(const NgbCapCtx *c, int *errflag)
@@ -590,7 +673,14 @@ int ngb_launch_assemble(const NgbAsmCtx *c)
 {
     const size_t total = (size_t)(c->nnz + c->neq1) * c->S;
     const unsigned grid = (unsigned)((total + 255) / 256);
-    ngb_k_assemble<<<grid, 256, 0, g_stream>>>(*c, total);
+    static int tiled = -1;
+    if (tiled < 0) { const char *e = getenv("NGB_ASM_TILED"); tiled = (e && atoi(e)) ? 1 : 0; }
+    if (tiled && c->S >= 32) {
+        const int nts = (c->S + 31) / 32, ntt = (c->nnz + c->neq1 + 31) / 32;
+        ngb_k_assemble_tiled<<<(unsigned)nts * (unsigned)ntt, 256, 0, g_stream>>>(*c, nts);
+    } else {
+        ngb_k_assemble<<<grid, 256, 0, g_stream>>>(*c, total);
+    }
     for (int li = 0; li < c->nlong; li++) {
         const int e = post_launch("assemble");
         if (e) return e;
