@@ -3078,28 +3078,6 @@ NGB_HD void b4_lte_inst(const B4Ctx *c, int inst, int s, double *m1, double *m2)
 #undef B4_LTE1
 }
 
-/* one (instance, charge) pair: k = 0..5 for qb qg qd qbs qbd qgmid (the list of BSIM4trunc, b4trunc.c) */
-NGB_HD void b4_lte_task(const B4Ctx *c, int inst, int k, int s, double *m1, double *m2)
-{
-    const size_t t = (size_t)inst * c->S + s;
-    const int order = NGB_LDG(&c->ctl.order[s]);
-    const int flags = NGB_LDG(&c->flags[inst]);
-    int kq;
-    double d1, d2;
-    if (order != 1 && order != 2) return;
-    switch (k) {
-    case 0: kq = B4ST_qb; break;
-    case 1: kq = B4ST_qg; break;
-    case 2: kq = B4ST_qd; break;
-    case 3: if (!B4F_RBODY(flags)) return; kq = B4ST_qbs; break;
-    case 4: if (!B4F_RBODY(flags)) return; kq = B4ST_qbd; break;
-    default: if (B4F_RGATE(flags) != 3) return; kq = B4ST_qgmid; break;
-    }
-    ngb_lte_values(&c->ctl, s, c->state, B4ST_COUNT, (size_t)c->T, t, NGB_LDG(&c->ctl.head[s]), kq, order, &d1, &d2);
-    if (d1 < *m1) *m1 = d1;
-    if (d2 < *m2) *m2 = d2;
-}
-
 #endif /* __cplusplus */
 
 #endif

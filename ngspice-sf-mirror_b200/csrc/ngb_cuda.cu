@@ -71,20 +71,20 @@ ngb_k_bsim4_lte(const B4Ctx c)
     if (lane == 0) { ngb_atomic_min_pos(&c.ctl.lte[s], m1); ngb_atomic_min_pos(&c.ctl.lte2[s], m2); }
 }
 
-/* the same bounds with one CTA per sample and one (instance, charge) pair per thread: a converged sample's 34 x 5 CKTterr
- * bodies run side by side instead of ten deep per lane (the minimum is exact in any order) */
+/* the same bounds with the load's own thread layout (thread = instance x sample, lanes on consecutive samples): every state
+ * read is coalesced over the converged samples of a warp (a warp per sample reads 8 useful bytes per 32-byte sector); one
+ * atomic minimum per instance and sample.  Default for batches (NGB_LTE_FLAT=0: the warp-per-sample kernel) */
 __global__ void __launch_bounds__(256)
-ngb_k_bsim4_lte_cta(const B4Ctx c)
+ngb_k_bsim4_lte_flat(const B4Ctx c)
 {
-    const int s = blockIdx.x;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)c.T) return;
+    const int inst = (int)(t / (size_t)c.S), s = (int)(t - (size_t)inst * c.S);
     if (!b4_lte_wanted(&c, s)) return;
     double m1 = 1e300, m2 = 1e300;
-    for (int task = threadIdx.x; task < c.ninst * 6; task += blockDim.x) b4_lte_task(&c, task / 6, task % 6, s, &m1, &m2);
-    for (int o = 16; o > 0; o >>= 1) {
-        m1 = fmin(m1, __shfl_xor_sync(0xffffffffu, m1, o));
-        m2 = fmin(m2, __shfl_xor_sync(0xffffffffu, m2, o));
-    }
-    if ((threadIdx.x & 31) == 0 && (m1 < 1e300 || m2 < 1e300)) { ngb_atomic_min_pos(&c.ctl.lte[s], m1); ngb_atomic_min_pos(&c.ctl.lte2[s], m2); }
+    b4_lte_inst(&c, inst, s, &m1, &m2);
+    if (m1 < 1e300) ngb_atomic_min_pos(&c.ctl.lte[s], m1);
+    if (m2 < 1e300) ngb_atomic_min_pos(&c.ctl.lte2[s], m2);
 }
 
 __global__ void __launch_bounds__(256)
@@ -618,12 +618,11 @@ int ngb_launch_bsim4_load(const B4Ctx *c, int *errflag)
 int ngb_launch_bsim4_lte(const B4Ctx *c)
 {
     if (c->T <= 0) return 0;
-    static int wide = -1;
-    if (wide < 0) { const char *e = getenv("NGB_LTE_CTA"); wide = (e && atoi(e)) ? 1 : 0; }
-    if (wide && c->ninst * 6 >= 64) {
-        const int cta = c->ninst * 6 >= 192 ? 256 : (c->ninst * 6 >= 96 ? 128 : 64);
-        ngb_k_bsim4_lte_cta<<<(unsigned)c->S, cta, 0, g_stream>>>(*c);
-    } else
+    static int flat = -1;
+    if (flat < 0) { const char *e = getenv("NGB_LTE_FLAT"); flat = (e && !atoi(e)) ? 0 : 1; }
+    if (flat && c->S >= 32)
+        ngb_k_bsim4_lte_flat<<<(unsigned)(((size_t)c->T + 255) / 256), 256, 0, g_stream>>>(*c);
+    else
         ngb_k_bsim4_lte<<<(unsigned)(((size_t)c->S * 32 + 127) / 128), 128, 0, g_stream>>>(*c);
     return post_launch("bsim4_lte");
 }
@@ -674,7 +673,7 @@ int ngb_launch_assemble(const NgbAsmCtx *c)
     const size_t total = (size_t)(c->nnz + c->neq1) * c->S;
     const unsigned grid = (unsigned)((total + 255) / 256);
     static int tiled = -1;
-    if (tiled < 0) { const char *e = getenv("NGB_ASM_TILED"); tiled = (e && atoi(e)) ? 1 : 0; }
+    if (tiled < 0) { const char *e = getenv("NGB_ASM_TILED"); tiled = (e && !atoi(e)) ? 0 : 1; }
     if (tiled && c->S >= 32) {
         const int nts = (c->S + 31) / 32, ntt = (c->nnz + c->neq1 + 31) / 32;
         ngb_k_assemble_tiled<<<(unsigned)nts * (unsigned)ntt, 256, 0, g_stream>>>(*c, nts);

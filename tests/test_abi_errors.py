@@ -80,3 +80,14 @@ def test_too_few_output_points_is_not_an_overrun(hostsim_lib):
     for s in range(2):
         assert int(res.accepted[s]) == int(wave["stats"][0]) and int(res.npoints[s]) == len(wave["time"])
         assert np.array_equal(t[s], wave["time"][:100]) and np.array_equal(v[s], wave["values"][:100])
+
+
+def test_diode_thermal_flag_needs_its_node(hostsim_lib):
+    """the thermal node exists exactly for the instances with self-heating, the qp node for those with soft recovery
+    (diosetup.c:419-430): flags and node table of ngbCircuitAddDiodes must say the same"""
+    flat = _flat("diosh")
+    flat["dio/nodes"][2, :] = 0              # the dump's row 2 is DIOtempNode
+    _fails(hostsim_lib, flat, 1, "thermal / qp nodes")
+    flat = _flat("diorr")
+    flat["dio/nodes"][5, :] = 0              # DIOqpNode
+    _fails(hostsim_lib, flat, 1, "thermal / qp nodes")
