@@ -14,7 +14,9 @@
 #include <cstdio>
 #include <cstdlib>
 
-#define NGB_GROUP_SYNC() do { if (nl <= 32) __syncwarp(ngb_gsync_mask); else __syncthreads(); } while (0)
+#include <cooperative_groups.h>
+/* a group is a warp, a CTA, or (nl > 1024: ngb_k_lu_grid, cooperative launch) the whole grid */
+#define NGB_GROUP_SYNC() do { if (nl <= 32) __syncwarp(ngb_gsync_mask); else if (nl <= 1024) __syncthreads(); else cooperative_groups::this_grid().sync(); } while (0)
 #ifndef NGB_B4_CTA
 #define NGB_B4_CTA 256
 #endif
@@ -253,6 +255,17 @@ __global__ void ngb_k_lu_warp(const NgbLuCtx c, int per_sample_doubles)
 }
 
 /* one CTA per sample (larger matrices) */
+/* one circuit too large for a CTA's shared memory (config 4's arrays): the whole grid works on one sample at a time, values,
+ * scale factors and solve tasks in global memory, a grid-wide barrier between the levels of the schedule.  Same body,
+ * same order of operations as every other LU kernel here */
+__global__ void __launch_bounds__(256)
+ngb_k_lu_grid(const NgbLuCtx c)
+{
+    const int nl = (int)(gridDim.x * blockDim.x), lane = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    for (int s = 0; s < c.S; s++)
+        ngb_lu_sample(&c, s, lane, nl, c.gV + (size_t)s * c.sch.nV, c.gRs + (size_t)s * c.sch.n, c.gZ + (size_t)s * c.sch.ntask);
+}
+
 __global__ void ngb_k_lu_block(const NgbLuCtx c)
 {
     extern __shared__ double smem[];
@@ -754,9 +767,15 @@ int ngb_launch_lu(const NgbLuCtx *c)
     } else if (bytes1 <= (size_t)g_smem_optin) {
         ngb_k_lu_block<<<(unsigned)c->S, 256, bytes1, g_stream>>>(*c);
     } else {
-        ngb_set_error("LU of order %d (%d values) does not fit shared memory; the multi-CTA LU is not built yet",
-                      c->sch.n, c->sch.nV);
-        return NGB_E_UNSUPP;
+        /* grid-wide LU: one CTA per SM (every CTA must be resident for the barrier; the levels of a circuit matrix are
+         * narrower than 148 x 256 lanes anyway) */
+        NgbLuCtx cc = *c;
+        void *args[1] = { (void *)&cc };
+        if (!c->gV || !c->gRs || !c->gZ) { ngb_set_error("grid-wide LU without its work arrays"); return NGB_E_PANIC; }
+        if (cudaLaunchCooperativeKernel((const void *)ngb_k_lu_grid, dim3((unsigned)g_sm_count), dim3(256), args, 0, g_stream) != cudaSuccess) {
+            ngb_set_error("cooperative launch of the grid-wide LU failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return NGB_E_PANIC;
+        }
     }
     return post_launch("lu");
 }

@@ -1740,10 +1740,12 @@ ngb_batch *ngbBatchCreate(ngb_circuit *c, int S, int device)
             if (c->lu[w].valid) {
                 sched_to_dev(b, c, w); packed_to_dev(b, c, w); b->dlu[w].valid = 1;
                 if (c->lu[w].sch.nV > nVmax) nVmax = c->lu[w].sch.nV;
+                if (c->lu[w].sch.ntask > b->lu_ntask_cap) b->lu_ntask_cap = c->lu[w].sch.ntask;
             }
         b->lu_which = c->lu[0].valid ? 0 : 1;
         b->V = (double *)dalloc(b, "lu.V", sizeof(double) * (size_t)nVmax * S);
         b->Rs = (double *)dalloc(b, "lu.Rs", sizeof(double) * (size_t)c->n * S);
+        b->Zw = (double *)dalloc(b, "lu.Z", sizeof(double) * (size_t)b->lu_ntask_cap * S);
         b->nodeconv = (int *)dalloc(b, "lu.nodeconv", sizeof(int) * (size_t)S);
         b->singular = (int *)dalloc(b, "lu.singular", sizeof(int) * (size_t)S);
         b->have_lu = 1;
@@ -1829,7 +1831,7 @@ int ngbBatchRefreshLu(ngb_batch *b)
 {
     const ngb_circuit *c = b->c;
     const int S = b->S;
-    int w, nVmax = 0;
+    int w, nVmax = 0, ntmax = 0;
     if (!c->have_lu) { ngb_set_error("no LU pattern on the circuit"); return NGB_E_PANIC; }
     ngb_dev_sync();
     batch_free_lu(b);
@@ -1837,15 +1839,18 @@ int ngbBatchRefreshLu(ngb_batch *b)
         if (c->lu[w].valid) {
             sched_to_dev(b, c, w); packed_to_dev(b, c, w); b->dlu[w].valid = 1;
             if (c->lu[w].sch.nV > nVmax) nVmax = c->lu[w].sch.nV;
+            if (c->lu[w].sch.ntask > ntmax) ntmax = c->lu[w].sch.ntask;
         }
     b->lu_which = c->lu[0].valid ? 0 : 1;
-    if (!b->have_lu || (size_t)nVmax * S * sizeof(double) > (size_t)ngbBatchArrayBytes(b, "lu.V")) {
+    if (!b->have_lu || (size_t)nVmax * S * sizeof(double) > (size_t)ngbBatchArrayBytes(b, "lu.V") || ntmax > b->lu_ntask_cap) {
         int i;
         for (i = 0; i < b->narr; i++)                       /* drop the old, smaller work arrays from the registry */
             if (!strcmp(b->arr[i].name, "lu.V") || !strcmp(b->arr[i].name, "lu.Rs") || !strcmp(b->arr[i].name, "lu.nodeconv") ||
-                !strcmp(b->arr[i].name, "lu.singular")) { ngb_dev_free(b->arr[i].ptr); b->arr[i] = b->arr[--b->narr]; i--; }
+                !strcmp(b->arr[i].name, "lu.singular") || !strcmp(b->arr[i].name, "lu.Z")) { ngb_dev_free(b->arr[i].ptr); b->arr[i] = b->arr[--b->narr]; i--; }
+        if (ntmax > b->lu_ntask_cap) b->lu_ntask_cap = ntmax;
         b->V = (double *)dalloc(b, "lu.V", sizeof(double) * (size_t)nVmax * S);
         b->Rs = (double *)dalloc(b, "lu.Rs", sizeof(double) * (size_t)c->n * S);
+        b->Zw = (double *)dalloc(b, "lu.Z", sizeof(double) * (size_t)b->lu_ntask_cap * S);
         b->nodeconv = (int *)dalloc(b, "lu.nodeconv", sizeof(int) * (size_t)S);
         b->singular = (int *)dalloc(b, "lu.singular", sizeof(int) * (size_t)S);
     }
@@ -2044,6 +2049,7 @@ void ngb_fill_luctx(ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve, int 
     x->do_factor = do_factor; x->do_solve = do_solve; x->node_type = b->d_node_type;
     x->reltol = c->opt.reltol; x->abstol = c->opt.abstol; x->vntol = c->opt.vntol;
     x->nodeconv = b->nodeconv; x->singular_col = b->singular; x->ctl = b->ctl;
+    x->gV = b->V; x->gRs = b->Rs; x->gZ = b->Zw;
 }
 
 static int check_errflag(ngb_batch *b)

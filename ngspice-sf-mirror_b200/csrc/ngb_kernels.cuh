@@ -401,6 +401,20 @@ NGB_HD void ngb_lu_sample(const NgbLuCtx *c, int s, int lane, int nl, double *V,
             NGB_GROUP_SYNC();
         }
         /* zero pivot -> E_SINGULAR (klu_refactor.c:390-404) */
+#ifdef __CUDA_ARCH__
+        if (nl > 1024) {             /* grid-wide group: the scan over n pivots is shared out */
+            if (lane == 0) c->singular_col[s] = 0x7fffffff;
+            NGB_GROUP_SYNC();
+            for (int k = lane; k < n; k += nl)
+                if (V[NGB_LDG(&h->diag_v[k])] == 0.0) atomicMin(&c->singular_col[s], k);
+            NGB_GROUP_SYNC();
+            if (lane == 0) {
+                const int sc = c->singular_col[s];
+                c->singular_col[s] = (sc == 0x7fffffff) ? -1 : sc;
+                if (sc != 0x7fffffff) c->ctl.err[s] = NGB_E_SINGULAR;
+            }
+        } else
+#endif
         if (lane == 0) {
             int sc = -1;
             for (int k = 0; k < n; k++)
@@ -408,14 +422,14 @@ NGB_HD void ngb_lu_sample(const NgbLuCtx *c, int s, int lane, int nl, double *V,
             c->singular_col[s] = sc;
             if (sc >= 0) c->ctl.err[s] = NGB_E_SINGULAR;
         }
-        if (c->V) {
+        if (c->V && c->V + (size_t)s * nV != V) {       /* (the grid-wide LU works in these arrays) */
             double *Vg = c->V + (size_t)s * nV;
             for (int e = lane; e < nV; e += nl) Vg[e] = V[e];
             double *Rg = c->Rs + (size_t)s * n;
             for (int i = lane; i < n; i += nl) Rg[i] = Rs[i];
         }
         NGB_GROUP_SYNC();
-    } else {
+    } else if (c->V + (size_t)s * nV != V) {
         const double *Vg = c->V + (size_t)s * nV;
         for (int e = lane; e < nV; e += nl) V[e] = Vg[e];
         const double *Rg = c->Rs + (size_t)s * n;

@@ -212,6 +212,8 @@ typedef struct NgbLuCtx {
     double reltol, abstol, vntol;
     int *nodeconv;          /* [S] 1 if some node failed                                 */
     int *singular_col;      /* [S] -1 or first zero pivot column                         */
+    /* work arrays of the grid-wide LU (a circuit too large for one CTA's shared memory): values, scale factors, solve tasks */
+    double *gV, *gRs, *gZ;  /* [S][nV], [S][n], [S][ntask]                               */
     NgbCtl ctl;
 } NgbLuCtx;
 

@@ -522,6 +522,19 @@ if __name__ == "__main__":
         synth = importlib.import_module("ngspice-sf-mirror_b200.synth")
         run("arr", synth.inverter_array_netlist(4, 4, ro_cards()), "0-30,100,101,400,401",
             ["out_0_0", "out_3_3", "in_2_1", "vdd#branch"])
+    if "arr16" in which:
+        # 16x16 array (512 BSIM4, 2 564 unknowns): past what one CTA's shared memory holds, the grid-wide LU's case.  Kept:
+        # the circuit (compressed), the pivoting factors of the run, the waveforms -- not the per-call trace (5 MB)
+        import importlib
+        synth = importlib.import_module("ngspice-sf-mirror_b200.synth")
+        run("arr16", synth.inverter_array_netlist(16, 16, ro_cards()), "0-12", ["out_0_0", "out_15_15", "in_2_1", "vdd#branch"])
+        flat = ngt.read(os.path.join(HERE, "arr16.flat.ngt")); trace = ngt.read(os.path.join(HERE, "arr16.trace.ngt.gz"))
+        pats = {k: v for k, v in trace.items() if "/pat/" in k}
+        for k in list(pats):
+            pats[k.split("/")[0] + "/mode"] = trace[k.split("/")[0] + "/mode"]
+        ngt.write(os.path.join(HERE, "arr16.flat.ngt.gz"), flat)
+        ngt.write(os.path.join(HERE, "arr16.pat.ngt.gz"), pats)
+        os.remove(os.path.join(HERE, "arr16.flat.ngt")); os.remove(os.path.join(HERE, "arr16.trace.ngt.gz"))
     if "ro17tox" in which:
         # model-parameter mismatch: BSIM4temp results for 8 discrete oxide-thickness levels (what `altermod
         # toxe=...` + CKTtemp produce), plus two complete reference transients with toxe AND delvto mismatch

@@ -84,3 +84,39 @@ def test_long_rail_assembly_tree_gpu(cuda_lib, hostsim_lib):
     for k in r1:
         assert abs(r1[k] - r2[k]) <= 1e-12 * max(abs(r1[k]), 1e-18), k
     assert same >= len(A1) - 64          # only the rail rows may differ in the last place
+
+
+def _arr16(lib):
+    from parity_util import run_patterns
+    flat = ngt.read(f"{GOLDEN}/arr16.flat.ngt.gz"); pats = ngt.read(f"{GOLDEN}/arr16.pat.ngt.gz"); wave = ngt.read(f"{GOLDEN}/arr16.wave.ngt")
+    circ = pkg.Circuit.from_flat(lib, flat, lu_pattern=run_patterns(pats))
+    b = pkg.Batch(circ, 1)
+    res = b.tran(1024, wave["save_eq"])
+    t, v = res.waves()
+    n = int(res.npoints[0])
+    acc, rej, nit = (int(x) for x in wave["stats"][:3])
+    assert int(res.err[0]) == 0 and n == len(wave["time"])
+    assert (int(res.accepted[0]), int(res.rejected[0]), int(res.numiter[0])) == (acc, rej, nit)
+    return circ, t[0, :n], v[0, :n], wave
+
+
+def test_array16_dc_op_and_transient_hostsim(hostsim_lib):
+    """BASELINE config 4 at 16 x 16 (512 BSIM4, 2 564 unknowns, 20 188 LU values): DC operating point (84 iterations) and
+    `.tran 10p 1n` through the library's own NIiter / DCtran with KLU's pivot orders -- bit-identical to the reference"""
+    circ, t, v, wave = _arr16(hostsim_lib)
+    assert circ.lu_info()["nV"] > 20000
+    assert np.array_equal(t, wave["time"]) and np.array_equal(v, wave["values"])
+
+
+@pytest.mark.gpu
+def test_array16_dc_op_and_transient_gpu(cuda_lib):
+    """the same on the device: this matrix does not fit one CTA's shared memory, so refactor + solve run in the grid-wide LU
+    kernel (ngb_k_lu_grid: values in global memory, a grid barrier per level).  Identical step / iteration counts, 1e-9 per
+    point"""
+    circ, t, v, wave = _arr16(cuda_lib)
+    assert np.max(np.abs(t - wave["time"]) / np.maximum(wave["time"], 1e-300)) <= 1e-9
+    flat = ngt.read(f"{GOLDEN}/arr16.flat.ngt.gz")
+    scale = np.where(np.asarray(flat["node/type"])[np.asarray(wave["save_eq"])] == 3, 1e-6, 1e-12)     # vntol / abstol
+    err = np.max(np.abs(v - wave["values"]) / np.maximum(np.abs(wave["values"]), scale[None, :]), axis=0)
+    assert (err <= 1e-9).all(), err
+    print("arr16 gpu bit-identical:", bool(np.array_equal(v, wave["values"])))
