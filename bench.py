@@ -712,6 +712,184 @@ def bench_array(args):
         dist.destroy_process_group()
 
 
+def array_tran_reference(nx, ny, save):
+    """the reference on the same netlist (one process: a single circuit has no second thread in the serial build): wall time of
+    the whole run, its own counters, and the saved waveforms from the rawfile"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ngspice")
+    if not os.path.exists(exe):
+        return None
+    synth = importlib.import_module("ngspice-sf-mirror_b200.synth")
+    src = open(os.path.join(GOLDEN, "netlists", "ro17.cir")).read()
+    cards = src[src.index(".model"):src.rindex(".end")]
+    tmp = tempfile.mkdtemp(prefix="ngb_cpu_arrtran_")
+    cir = os.path.join(tmp, "arr.cir"); raw = os.path.join(tmp, "arr.raw")
+    open(cir, "w").write(synth.inverter_array_netlist(nx, ny, cards).replace(".option klu", ".option klu acct"))
+    t0 = time.time()
+    out = subprocess.run([exe, "-b", "-r", raw, cir], capture_output=True, text=True).stdout
+    wall = time.time() - t0
+    st = {}
+    for ln in out.splitlines():
+        for key, tag in (("iters", "Total iterations"), ("load", "Matrix load time"), ("lu", "Matrix factor time"), ("reorder", "Matrix reorder time"),
+                         ("solve", "Matrix solve time"), ("tran", "Transient analysis time"), ("analysis", "Total analysis time"), ("accepted", "Accepted timepoints"), ("rejected", "Rejected timepoints")):
+            if ln.startswith(tag):
+                try:
+                    st[key] = float(ln.split("=")[-1].split()[0])
+                except ValueError:
+                    pass
+    data = open(raw, "rb").read()
+    i = data.index(b"Binary:\n"); head = data[:i].decode(errors="replace")
+    nv = int([ln for ln in head.splitlines() if ln.startswith("No. Variables")][0].split(":")[1])
+    npts = int([ln for ln in head.splitlines() if ln.startswith("No. Points")][0].split(":")[1])
+    names = [ln.split()[1].lower() for ln in head.splitlines() if ln.startswith("\t") and len(ln.split()) >= 3 and ln.split()[0].isdigit()]
+    arr = np.frombuffer(data, dtype=np.float64, count=nv * npts, offset=i + 8).reshape(npts, nv)
+    cols = [names.index(f"v({n.lower()})") for n in save]
+    return {"wall": wall, "stats": st, "time": arr[:, 0].copy(), "values": arr[:, cols].copy()}
+
+
+def bench_array_tran(args):
+    """BASELINE config 4 with the LU: DC operating point + `.tran 10p 1n` of an nx-by-ny array, one circuit (S = 1).  The matrix does
+    not fit a CTA's shared memory, so refactor + solve run in the grid-wide LU kernel; ordering and pivoting are the library's own
+    (ngbCircuitAnalyze / ngbCircuitFactor: minimum degree, not KLU's AMD), so the result agrees with the reference to rounding along
+    the same time grid, not bit for bit (with KLU's orders it is bit-identical: tests/test_synth_array.py)."""
+    import torch
+    pkg = importlib.import_module("ngspice-sf-mirror_b200")
+    ngt = pkg.ngt
+    synth = importlib.import_module("ngspice-sf-mirror_b200.synth")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", "0")); rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = pkg.library()
+    lib.check(lib.L.ngbInit(local), "ngbInit")
+    stream = torch.cuda.Stream(device=local)
+    lib.check(lib.L.ngbSetStream(ctypes.c_void_p(stream.cuda_stream)), "ngbSetStream")
+    nx = int(round(args.cells ** 0.5)); ny = (args.cells + nx - 1) // nx
+    base = ngt.read(f"{GOLDEN}/ro17k.flat.ngt")
+    flat = synth.inverter_array(base, nx, ny)
+    names = flat.pop("node/names")
+    ninst = int(flat["b4/ninst"][0])
+    t_setup = time.time()
+    circ = pkg.Circuit.from_flat(lib, flat)
+    pat = circ.pattern()
+    one = lambda v, dt: np.array([v], dtype=dt)
+    b0 = pkg.Batch(circ, 1, device=local)            # the matrix of the first iteration (MODETRANOP | MODEINITJCT from zero): what the first pivoting factor sees
+    b0.put("ctl.mode", one(0x20 | 0x200, np.int32)); b0.put("ctl.active", one(1, np.int32)); b0.put("ctl.order", one(1, np.int32))
+    b0.put("ctl.gmin", one(1e-12, np.float64)); b0.put("ctl.srcfact", one(1.0, np.float64))
+    b0.load()
+    Ax0 = np.ascontiguousarray(b0.get("Ax", (1, -1))[0])
+    del b0
+    lib.check(lib.L.ngbCircuitAnalyze(circ.h), "ngbCircuitAnalyze")
+    lib.L.ngbCircuitFactor.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.c_double]
+    lib.check(lib.L.ngbCircuitFactor(circ.h, Ax0.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.c_double(1e-3)), "ngbCircuitFactor")
+    info = circ.lu_info()
+    batch = pkg.Batch(circ, 1, device=local)
+    t_setup = time.time() - t_setup
+    save_names = ["out_0_0", f"out_{ny - 1}_{nx - 1}", "in_2_1"]
+    save = np.array([names.index(n) for n in save_names], np.int32)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    last = {}
+
+    def step(e2e):
+        res = batch.tran(1024, save)
+        if e2e:
+            last["t"], last["v"] = res.waves()
+        last["res"] = res
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+
+    def timed(e2e, profile):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if profile:
+            lib.L.ngbProfile(1, 16)
+        barrier(); n0 = lib.launch_count()
+        a.record(stream)
+        for _ in range(args.steps):
+            step(e2e)
+        b.record(stream)
+        barrier()
+        prof = None
+        if profile:
+            msum, cnt = ctypes.c_double(), ctypes.c_long()
+            lib.L.ngbProfileRead(ctypes.byref(msum), ctypes.byref(cnt)); lib.L.ngbProfile(0, 1)
+            prof = (msum.value, cnt.value)
+        return a.elapsed_time(b), lib.launch_count() - n0, prof
+
+    with ClockSampler(local) as clk:
+        ms, launches, prof = timed(False, True)
+    clocks = clk.summary()
+    ms_e2e, _, _ = timed(True, False)
+    res = last["res"]
+    numiter = int(res.numiter[0]); npts = int(res.npoints[0])
+    tt = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = tt.tolist()
+    if rank == 0:
+        hbm_peak, which = peaks()
+        k_ms = prof[0] / max(prof[1], 1)
+        achieved = ninst * B4_BYTES_PER_EVAL / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        evals = ninst * numiter
+        ref = array_tran_reference(nx, ny, save_names)
+        line = {
+            "metric": "BSIM4 instance-evals/s", "value": world * evals * args.steps / (ms * 1e-3), "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"flat {nx}x{ny} BSIM4 inverter array with RC links (config 4 at reduced size), one circuit per GPU (replicas): "
+                                   "DC operating point + .tran 10p 1n per step, device loads + assembly + grid-wide LU + NIiter / DCtran on the device; "
+                                   "ordering and pivoting by the library (minimum degree, own pivoting factor)",
+                       "bsim4_instances": ninst, "unknowns": pat["n"], "nnz": pat["nnz"], "lu_values": info["nV"], "lu_levels": info["nlev"] + info["nslev"],
+                       "lu_products": info["npairs"], "setup_s_not_timed": t_setup,
+                       "l2": "working set (states, stamps, matrix, factors) smaller than L2 below ~64 x 64; no flush"},
+            "newton_iterations": numiter, "accepted_points": int(res.accepted[0]), "rejected_points": int(res.rejected[0]),
+            "us_per_newton_iteration": ms / args.steps / max(numiter, 1) * 1e3,
+            "e2e": {"value": world * evals * args.steps / (ms_e2e * 1e-3), "unit": "evals/s",
+                    "h2d_bytes_per_step": int(save.nbytes), "d2h_bytes_per_step": int(npts * (len(save) + 1) * 8)},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak if hbm_peak else None, "traffic": None,
+                         "kernel": "ngb_k_bsim4_load", "avg_launch_ms": k_ms, "timed_launches": prof[1],
+                         "units_per_launch": ninst, "bytes_per_unit": B4_BYTES_PER_EVAL, "peak_source": which,
+                         "kernel_share_of_step": k_ms * numiter / (ms / args.steps) if ms else None},
+        }
+        if ref is not None:
+            st = ref["stats"]
+            it_ref = int(st.get("iters", 0))
+            line["cpu_baseline"] = {"value": ninst * it_ref / (st.get("analysis") or ref["wall"]), "unit": "evals/s", "cores": 1, "kind": "reference",
+                                    "sample": f"the same {nx}x{ny} netlist, one reference process, its own 'Total analysis time' (DC op + transient, no parse); its counters: "
+                                              f"load {st.get('load')} s, LU {st.get('lu')} + {st.get('reorder')} s, solve {st.get('solve')} s, {it_ref} iterations",
+                                    "us_per_newton_iteration": (st.get("load", 0) + st.get("lu", 0) + st.get("reorder", 0) + st.get("solve", 0)) / max(it_ref, 1) * 1e6,
+                                    "analysis_s": st.get("analysis")}
+            t, v = last["t"][0, :npts], last["v"][0, :npts]
+            same_grid = npts == len(ref["time"])
+            pc = {"accepted_identical": int(res.accepted[0]) == int(st.get("accepted", -1)) and int(res.rejected[0]) == int(st.get("rejected", -1)),
+                  "points_identical": bool(same_grid), "iterations": [numiter, it_ref], "tolerance": 1e-6,
+                  "note": "own pivot order: rounding-level differences move the LTE-chosen steps of the first, nearly static points by ~1e-4 relative, "
+                          "so the waveforms are compared at the reference's time points by linear interpolation, 1e-6 of the supply"}
+            err = 0.0
+            for k in range(v.shape[1]):
+                err = max(err, float(np.max(np.abs(np.interp(ref["time"], t, v[:, k]) - ref["values"][:, k]))) / 2.0)
+            pc["max_err_interpolated"] = err
+            if same_grid:
+                pc["max_rel_err_time"] = float(np.max(np.abs(t - ref["time"]) / np.maximum(ref["time"], 1e-300)))
+                pc["max_err_same_index"] = float(np.max(np.abs(v - ref["values"])))
+            pc["ok"] = bool(pc["accepted_identical"] and err <= 1e-3)
+            line["parity_check"] = pc
+        print(json.dumps(line))
+        if ref is not None and not line["parity_check"]["ok"]:
+            raise SystemExit("bench.py: array transient differs from the reference")
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------ config 5: mixed-model parameter sweep
 SWEEP_GRID = 256                      # 256 x 256 = 65 536 points of (vdd, r1); 8 192 points per GPU on 8 GPUs
 SWEEP_COUNTS = {"bsim4": 16, "bsim3": 8, "vbic": 2, "diode": 3}
@@ -897,8 +1075,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mc_ro17", choices=["mc_ro17", "ro101", "array", "sweep"])
-    ap.add_argument("--cells", type=int, default=500000, help="inverters of the array workload (2 transistors each)")
+    ap.add_argument("--workload", default="mc_ro17", choices=["mc_ro17", "ro101", "array", "array_tran", "sweep"])
+    ap.add_argument("--cells", type=int, default=None, help="inverters of the array workloads (2 transistors each): default 500 000 (array), 4 096 (array_tran)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --samples per GPU (default, the driver's scaling run); strong: --samples in total, samples / N per GPU "
                          "(BASELINE config 3 as written: 4096 samples, batch = 4096 / N)")
@@ -908,8 +1086,12 @@ def main():
     args = ap.parse_args()
     if args.samples is None:
         args.samples = 8192 if args.workload == "sweep" else 4096
+    if args.cells is None:
+        args.cells = 4096 if args.workload == "array_tran" else 500000
     if args.workload == "sweep":
         bench_sweep(args)
+    elif args.workload == "array_tran":
+        bench_array_tran(args)
     elif args.impl == "reference":
         bench_reference(args)
     elif args.workload == "array":

@@ -303,13 +303,44 @@ int ngbCircuitSetSymbolic(ngb_circuit *c, int n, int nblocks, const int *P, cons
 /* Own symbolic analysis: ONE block (no block triangular form) and a greedy minimum-degree ordering of the pattern of
  * A + A' applied to rows and columns alike, ties to the lower index.  It is not klu_analyze's BTF + AMD result, so a
  * run on it agrees with the reference to rounding, not bit for bit; bit-identical runs import klu_analyze's P, Q, R
- * through ngbCircuitSetSymbolic.  Quadratic in the order: refused above 20 000. */
+ * through ngbCircuitSetSymbolic.  The next node comes from a binary heap of (degree, index)
+ * pairs with lazy deletion (an entry whose degree is out of date is skipped when it surfaces). */
+typedef struct { int deg, idx; } NpHeapItem;
+static int np_less(NpHeapItem a, NpHeapItem b) { return a.deg < b.deg || (a.deg == b.deg && a.idx < b.idx); }
+static int np_heap_push(NpHeapItem **h, int *len, int *cap, int deg, int idx)
+{
+    int i;
+    if (*len == *cap) {
+        NpHeapItem *t = (NpHeapItem *)realloc(*h, sizeof(NpHeapItem) * (size_t)(*cap ? 2 * *cap : 1024));
+        if (!t) return 1;
+        *h = t; *cap = *cap ? 2 * *cap : 1024;
+    }
+    i = (*len)++;
+    (*h)[i].deg = deg; (*h)[i].idx = idx;
+    while (i > 0 && np_less((*h)[i], (*h)[(i - 1) / 2])) { NpHeapItem t = (*h)[i]; (*h)[i] = (*h)[(i - 1) / 2]; (*h)[(i - 1) / 2] = t; i = (i - 1) / 2; }
+    return 0;
+}
+static NpHeapItem np_heap_pop(NpHeapItem *h, int *len)
+{
+    NpHeapItem top = h[0];
+    int i = 0;
+    h[0] = h[--(*len)];
+    for (;;) {
+        int l = 2 * i + 1, r = l + 1, m = i;
+        if (l < *len && np_less(h[l], h[m])) m = l;
+        if (r < *len && np_less(h[r], h[m])) m = r;
+        if (m == i) break;
+        { NpHeapItem t = h[i]; h[i] = h[m]; h[m] = t; }
+        i = m;
+    }
+    return top;
+}
 int ngbCircuitAnalyze(ngb_circuit *c)
 {
     const int n = c->n;
     int i, j, k, p, rc = NGB_OK;
+    NpHeapItem *heap = NULL; int hlen = 0, hcap = 0;
     if (!c->finalized) { ngb_set_error("circuit not finalized"); return NGB_E_PANIC; }
-    if (n > 20000) { ngb_set_error("own ordering is quadratic in the order (%d unknowns): import klu_analyze's result instead", n); return NGB_E_UNSUPP; }
     /* adjacency as sorted-free integer lists with a mark array */
     int **adj = (int **)calloc((size_t)n, sizeof(int *)), *deg = (int *)calloc((size_t)n, sizeof(int)), *cap = (int *)calloc((size_t)n, sizeof(int));
     int *mark = (int *)malloc(sizeof(int) * (size_t)n), *gone = (int *)calloc((size_t)n, sizeof(int));
@@ -329,9 +360,14 @@ int ngbCircuitAnalyze(ngb_circuit *c)
         deg[i] = m;
     }
     for (i = 0; i < n; i++) mark[i] = -1;
+    for (i = 0; i < n; i++) if (np_heap_push(&heap, &hlen, &hcap, deg[i], i)) { rc = NGB_E_PANIC; goto done; }
     for (k = 0; k < n; k++) {
         int best = -1;
-        for (i = 0; i < n; i++) if (!gone[i] && (best < 0 || deg[i] < deg[best])) best = i;
+        while (hlen > 0) {           /* lowest degree, ties to the lower index */
+            const NpHeapItem it = np_heap_pop(heap, &hlen);
+            if (!gone[it.idx] && deg[it.idx] == it.deg) { best = it.idx; break; }
+        }
+        if (best < 0) { rc = NGB_E_PANIC; goto done; }
         ord[k] = best; gone[best] = 1;
         /* eliminate: the remaining neighbours of `best` become a clique */
         for (p = 0; p < deg[best]; p++) {
@@ -347,13 +383,14 @@ int ngbCircuitAnalyze(ngb_circuit *c)
                 mark[b2] = -2 - a;
                 NP_ADD(a, b2);
             }
+            if (np_heap_push(&heap, &hlen, &hcap, deg[a], a)) { rc = NGB_E_PANIC; goto done; }
         }
     }
 #undef NP_ADD
     rc = ngbCircuitSetSymbolic(c, n, 1, ord, ord, R);
 done:
     if (adj) for (i = 0; i < n; i++) free(adj[i]);
-    free(adj); free(deg); free(cap); free(mark); free(gone); free(ord);
+    free(adj); free(deg); free(cap); free(mark); free(gone); free(ord); free(heap);
     return rc;
 }
 

@@ -120,3 +120,44 @@ def test_array16_dc_op_and_transient_gpu(cuda_lib):
     err = np.max(np.abs(v - wave["values"]) / np.maximum(np.abs(wave["values"]), scale[None, :]), axis=0)
     assert (err <= 1e-9).all(), err
     print("arr16 gpu bit-identical:", bool(np.array_equal(v, wave["values"])))
+
+
+def _oracle_array(n, tmp):
+    """the reference itself (oracle/_ref/ngspice_dump, prebuilt) run on an n x n array netlist: circuit dump, pivoting
+    factors and waveforms, written under tmp (tests/golden/make_golden.py's own routine)"""
+    import os, sys
+    sys.path.insert(0, os.path.join(GOLDEN))
+    import make_golden as M
+    if not os.path.exists(M.DUMP):
+        pytest.skip("oracle/_ref/ngspice_dump not built")
+    src = open(os.path.join(GOLDEN, "netlists", "ro17.cir")).read()
+    cards = src[src.index(".model"):src.rindex(".end")]
+    M.HERE = tmp; M.TMP = os.path.join(tmp, "work")
+    name = f"arr{n}"
+    M.run(name, synth.inverter_array_netlist(n, n, cards), "0-1", ["out_0_0", f"out_{n - 1}_{n - 1}", "in_2_1", "vdd#branch"])
+    return (ngt.read(os.path.join(tmp, name + ".flat.ngt")), ngt.read(os.path.join(tmp, name + ".trace.ngt.gz")),
+            ngt.read(os.path.join(tmp, name + ".wave.ngt")))
+
+
+@pytest.mark.gpu
+def test_array48_gpu_against_the_oracle(cuda_lib, tmp_path):
+    """BASELINE config 4 at 48 x 48 (4 608 BSIM4, 23 044 unknowns, supply-rail rows past NGB_ASM_LONG): the reference runs the
+    netlist here, the device repeats DC operating point + `.tran 10p 1n` with the grid-wide LU on KLU's pivot orders.
+    Identical accepted / rejected / iteration counts; 1e-9 per point (the rail rows are summed by a chunk tree on the device,
+    so their last place may differ)"""
+    from parity_util import run_patterns
+    flat, trace, wave = _oracle_array(48, str(tmp_path))
+    circ = pkg.Circuit.from_flat(cuda_lib, flat, lu_pattern=run_patterns(trace))
+    b = pkg.Batch(circ, 1)
+    res = b.tran(1024, wave["save_eq"])
+    t, v = res.waves()
+    n = int(res.npoints[0])
+    acc, rej, nit = (int(x) for x in wave["stats"][:3])
+    assert int(res.err[0]) == 0 and n == len(wave["time"])
+    assert (int(res.accepted[0]), int(res.rejected[0]), int(res.numiter[0])) == (acc, rej, nit)
+    assert np.max(np.abs(t[0, :n] - wave["time"]) / np.maximum(wave["time"], 1e-300)) <= 1e-9
+    scale = np.where(np.asarray(flat["node/type"])[np.asarray(wave["save_eq"])] == 3, 1e-6, 1e-12)
+    err = np.max(np.abs(v[0, :n] - wave["values"]) / np.maximum(np.abs(wave["values"]), scale[None, :]), axis=0)
+    assert (err <= 1e-9).all(), err
+    print("arr48 gpu: unknowns", circ.neq, "LU values", circ.lu_info()["nV"], "max rel err", float(err.max()),
+          "bit-identical", bool(np.array_equal(v[0, :n], wave["values"])))
