@@ -62,6 +62,11 @@ def inverter_array(base, nx, ny, vdd=2.0, tstep=1e-11, tstop=1e-9):
     flat["node/type"] = nt
     flat["tran/tstep"] = np.array([tstep]); flat["tran/tstop"] = np.array([tstop]); flat["tran/tmax"] = np.array([tstep])
     flat["tran/tstart"] = np.array([0.0]); flat["tran/uic"] = np.array([0], np.int32)
+    # the options the base fixture's own netlist set or DCtran derived from ITS .tran line (the oscillator example runs with
+    # xmu = 0.49): the array netlist has `.option klu` only
+    flat["opt/xmu"] = np.array([0.5])
+    flat["opt/delmin"] = np.array([1e-11 * tstep])           # CKTdelmin = 1e-11 * CKTmaxStep (dctran.c:137)
+    flat["opt/minbreak"] = np.array([tstep * 5e-5])          # CKTminBreak = CKTmaxStep * 5e-5 (dctran.c:186)
     flat["b4/ninst"] = np.array([2 * N], np.int32)
     flat["b4/nodes"] = nodes.astype(np.int32)
     flat["b4/flags"] = np.concatenate([np.full(N, base["b4/flags"][ip]), np.full(N, base["b4/flags"][inn])]).astype(np.int32)
