@@ -534,6 +534,37 @@ int ngb_dev_graph_launch(void *exec, int nodes)
 }
 void ngb_dev_graph_destroy(void *exec) { if (exec) cudaGraphExecDestroy((cudaGraphExec_t)exec); }
 
+/* L2 persistence for a block that every launch re-reads (per-sample parameter rows): an access-policy window on the launch
+ * streams, inherited by the kernel nodes of captured graphs.  NGB_L2_PERSIST=0 switches it off */
+void ngb_dev_l2_persist(const void *p, size_t bytes)
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("NGB_L2_PERSIST"); on = (e && !atoi(e)) ? 0 : 1; }
+    if (!on || !g_stream) return;
+    int dev = 0, maxwin = 0, maxpersist = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&maxwin, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    cudaDeviceGetAttribute(&maxpersist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof av);
+    if (p && bytes && maxwin > 0 && maxpersist > 0) {
+        size_t win = bytes < (size_t)maxwin ? bytes : (size_t)maxwin;
+        size_t carve = win < (size_t)maxpersist ? win : (size_t)maxpersist;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+        av.accessPolicyWindow.base_ptr = const_cast<void *>(p);
+        av.accessPolicyWindow.num_bytes = win;
+        av.accessPolicyWindow.hitRatio = (float)((double)carve / (double)win);
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    } else {
+        av.accessPolicyWindow.num_bytes = 0;
+        cudaCtxResetPersistingL2Cache();
+    }
+    cudaStreamSetAttribute(g_stream, cudaStreamAttributeAccessPolicyWindow, &av);
+    for (int i = 0; i < NGB_SIDE; i++) if (g_side_ready) cudaStreamSetAttribute(g_side[i], cudaStreamAttributeAccessPolicyWindow, &av);
+    cudaGetLastError();
+}
+
 /* fork / join around the device-type loads of one CKTload.  A step whose bsim4_load is being timed
  * (ngb_dev_profile_due) stays on one stream so that the kernel is measured alone. */
 int ngb_dev_branch_begin(void)

@@ -20,6 +20,7 @@ const char *ngb_dev_backend(void);              /* "cuda-sm_100a" or "hostsim" *
 int   ngb_dev_init(int device);
 void *ngb_dev_malloc(size_t bytes);             /* zero-filled */
 void  ngb_dev_free(void *p);
+void  ngb_dev_l2_persist(const void *p, size_t bytes);   /* access-policy window (L2 persisting) of the launch streams; NULL: none */
 int   ngb_dev_h2d(void *dst, const void *src, size_t bytes);
 int   ngb_dev_d2h(void *dst, const void *src, size_t bytes);
 int   ngb_dev_memset(void *dst, int byte, size_t bytes);

@@ -67,6 +67,7 @@ struct ngb_batch {
     double *Zw; int lu_ntask_cap;     /* solve-task scratch of the grid-wide LU, [S][lu_ntask_cap] */
     int lte_deferred;                 /* transient driver: BSIM4trunc in its own launch after the solve */
     double *b4_inst, *b4_state, *b4_op, *b4_mtab, *b4_ptab; int *b4_prow, *b4_prow_t, *b4_flags, *b4_nodes, *b4_spos;
+    void *b4_rows_block;              /* per-sample rows (ngbBatchSetBsim4Rows): b4_mtab and b4_ptab live in this one allocation */
     double *cap_par, *cap_state; int *cap_nodes, *cap_spos;
     double *b3_inst, *b3_state, *b3_von, *b3_mtab, *b3_ptab; int *b3_prow, *b3_flags, *b3_nodes, *b3_spos;
     double *vb_par, *vb_aux, *vb_state; int *vb_nodes, *vb_flags, *vb_spos;

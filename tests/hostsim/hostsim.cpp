@@ -18,6 +18,7 @@ const char *ngb_dev_backend(void) { return "hostsim"; }
 int ngb_dev_init(int) { return 0; }
 void *ngb_dev_malloc(size_t bytes) { return calloc(bytes ? bytes : 1, 1); }
 void ngb_dev_free(void *p) { free(p); }
+void ngb_dev_l2_persist(const void *, size_t) {}
 int ngb_dev_h2d(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
 int ngb_dev_d2h(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
 int ngb_dev_memset(void *d, int v, size_t n) { memset(d, v, n); return 0; }
