@@ -242,6 +242,9 @@ void ngbBatchSetBsim4Generic(ngb_batch *b, int on);
  * [1] small device loads, [2] BSIM4 load, [3] assembly, [4] refactor + solve, [5] BSIM4trunc, [6] controller */
 int ngbProfileStages(double ms[8]);
 long ngbTranTicks(ngb_batch *b);              /* Newton steps the batch needed */
+/* samples x events the host had to factor with pivoting in the last run (a zero pivot, or a pivoting event whose recorded
+ * order failed the device's check of KLU's pivot rule on the sample's own matrix) */
+int ngbTranRepivots(ngb_batch *b);
 void *ngbTranDevWaves(ngb_batch *b, int which /* 0 times, 1 values */);   /* device pointers for a collective gather */
 /* per-thread BSIM4 parameter rows for model-parameter mismatch: prow_t [ninst*S] into new tables */
 int ngbBatchSetBsim4Rows(ngb_batch *b, const int *prow_t, int nrows, const double *mtab, const double *ptab);

@@ -401,6 +401,7 @@ class TranResult:
         batch.lib.check(L.ngbTranStats(batch.h, *[_ip(v) for v in a]), "ngbTranStats")
         self.accepted, self.rejected, self.numiter, self.npoints = a
         self.ticks = int(L.ngbTranTicks(batch.h))
+        self.repivots = int(L.ngbTranRepivots(batch.h))     # samples x events factored with pivoting on the host
         self.err = np.zeros(S, np.int32)          # DCtran's return value per sample (0 = completed)
         batch.lib.check(L.ngbTranErrors(batch.h, _ip(self.err)), "ngbTranErrors")
 

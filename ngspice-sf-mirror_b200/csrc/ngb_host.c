@@ -179,7 +179,7 @@ static void free_sched(NgbLuSched *h)
 #define F(p) free((void *)h->p)
     F(lev_ptr); F(lev_ent); F(e_aslot); F(e_arow); F(e_div); F(e_pptr); F(pair_l); F(pair_u);
     F(diag_v); F(row_ptr); F(row_slot); F(slev_ptr); F(slev_task); F(t_kind); F(t_init); F(t_div);
-    F(t_pptr); F(t_val); F(t_src); F(b_eq); F(out_task); F(out_eq);
+    F(t_pptr); F(t_val); F(t_src); F(b_eq); F(out_task); F(out_eq); F(vchk);
 #undef F
     memset(h, 0, sizeof *h);
 }
@@ -1205,6 +1205,40 @@ static unsigned long long lu_signature(int n, const int *Pnum, const int *Lp, co
     return h;
 }
 
+/* What lpivot's rule asks of every L entry for THIS pivot order to come out of a pivoting factor of the same matrix
+ * (NgbLuSched.vchk).  The preferred row of a column is dynamic -- a displaced diagonal becomes the diagonal of the column whose
+ * row was taken (klu_kernel.c:845-858, ngb_pivot.c) -- so the pivot sequence is replayed block by block.  Needs klu_analyze's
+ * row permutation (ngbCircuitSetSymbolic); NULL without it */
+static int *lu_pivot_checks(const ngb_circuit *c, int n, int nblocks, const int *R, const int *Pnum, const int *Lp, const int *Li, int unz, int nV)
+{
+    int *chk, *PSinv, *Pblk, *Pinv, *diagrow, *pivrow, b, k, p;
+    if (!c->klu_P || c->klu_nblocks != nblocks) return NULL;
+    chk = (int *)xcalloc((size_t)nV, sizeof(int)); PSinv = (int *)xcalloc((size_t)n, sizeof(int));
+    Pblk = (int *)xcalloc((size_t)n, sizeof(int)); Pinv = (int *)xcalloc((size_t)n, sizeof(int));
+    diagrow = (int *)xcalloc((size_t)n, sizeof(int)); pivrow = (int *)xcalloc((size_t)n, sizeof(int));
+    for (k = 0; k < n; k++) PSinv[c->klu_P[k]] = k;
+    for (b = 0; b < nblocks; b++) {
+        const int k1 = R[b], k2 = R[b + 1], nk = k2 - k1;
+        if (nk <= 1) continue;
+        for (k = 0; k < nk; k++) { Pblk[k] = k; Pinv[k] = -k - 2; }
+        for (k = 0; k < nk; k++) {
+            const int pr = PSinv[Pnum[k1 + k]] - k1, dr = Pblk[k];
+            if (pr < 0 || pr >= nk) { free(chk); chk = NULL; goto out; }        /* order and symbolic analysis do not belong together */
+            diagrow[k1 + k] = dr; pivrow[k1 + k] = pr;
+            if (pr != dr && Pinv[dr] < 0) { const int kbar = -Pinv[pr] - 2; Pblk[kbar] = dr; Pinv[dr] = -kbar - 2; }
+            Pblk[k] = pr; Pinv[pr] = k;
+        }
+        for (k = k1; k < k2; k++)
+            for (p = Lp[k]; p < Lp[k + 1]; p++) {
+                const int i = PSinv[Pnum[Li[p]]] - k1;              /* the entry's row in the block's symbolic numbering */
+                chk[unz + p] = (pivrow[k] == diagrow[k]) ? 1 : (i == diagrow[k] ? 3 : 2);
+            }
+    }
+out:
+    free(PSinv); free(Pblk); free(Pinv); free(diagrow); free(pivrow);
+    return chk;
+}
+
 int ngbCircuitSetLuPattern(ngb_circuit *c, int n, int nblocks, const int *Q, const int *R, const int *Pnum,
                            const int *Lp, const int *Li, const int *Up, const int *Ui,
                            const int *Offp, const int *Offi)
@@ -1425,6 +1459,7 @@ int ngbCircuitSetLuPattern(ngb_circuit *c, int n, int nblocks, const int *Q, con
         h->b_eq = b_eq; h->out_task = ot; h->out_eq = oe;
     }
     free(Pinv); free(pos); free(level);
+    h->vchk = lu_pivot_checks(c, n, nblocks, R, Pnum, Lp, Li, unz, nV);
     build_packed(c);
     {   /* move the finished set into its slot */
         struct ngb_luset *L = &c->lu[c->lu_target];
@@ -1553,6 +1588,7 @@ static void sched_to_dev(ngb_batch *b, const ngb_circuit *cc, int w)
     D(row_ptr, h->n + 1); D(row_slot, h->nnz); D(slev_ptr, h->nslev + 1); D(slev_task, h->ntask);
     D(t_kind, h->ntask); D(t_init, h->ntask); D(t_div, h->ntask); D(t_pptr, h->ntask + 1);
     D(t_val, c->nsolvepairs); D(t_src, c->nsolvepairs); D(b_eq, h->n); D(out_task, h->n); D(out_eq, h->n);
+    if (h->vchk) D(vchk, h->nV);
 #undef D
 }
 static void packed_to_dev(ngb_batch *b, const ngb_circuit *c, int w)
@@ -1572,7 +1608,7 @@ static void sched_dev_free(NgbLuSched *d)
 #define F(p) ngb_dev_free((void *)d->p)
     F(lev_ptr); F(lev_ent); F(e_aslot); F(e_arow); F(e_div); F(e_pptr); F(pair_l); F(pair_u);
     F(diag_v); F(row_ptr); F(row_slot); F(slev_ptr); F(slev_task); F(t_kind); F(t_init); F(t_div);
-    F(t_pptr); F(t_val); F(t_src); F(b_eq); F(out_task); F(out_eq);
+    F(t_pptr); F(t_val); F(t_src); F(b_eq); F(out_task); F(out_eq); F(vchk);
 #undef F
     memset(d, 0, sizeof *d);
 }
@@ -2059,6 +2095,7 @@ void ngb_fill_luctx(ngb_batch *b, NgbLuCtx *x, int do_factor, int do_solve, int 
     x->reltol = c->opt.reltol; x->abstol = c->opt.abstol; x->vntol = c->opt.vntol;
     x->nodeconv = b->nodeconv; x->singular_col = b->singular; x->ctl = b->ctl;
     x->gV = b->V; x->gRs = b->Rs; x->gZ = b->Zw;
+    x->verify = b->lu_verify; x->pivtol = c->pivtol > 0 ? c->pivtol : 0.001;
 }
 
 static int check_errflag(ngb_batch *b)

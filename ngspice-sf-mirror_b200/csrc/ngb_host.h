@@ -64,6 +64,7 @@ struct ngb_batch {
     int *errflag;
     int *d_node_type, *d_tgt_ptr, *d_tgt_rows, *d_slot_diag, *d_long_tgt;
     int *long_len; double *long_part; int long_cap;      /* long assembly targets: lengths (host), chunk-total scratch (device) */
+    int *lu_verify;                   /* [S] device, owned by the transient driver: pivoting event due (NgbLuCtx.verify) */
     double *Zw; int lu_ntask_cap;     /* solve-task scratch of the grid-wide LU, [S][lu_ntask_cap] */
     int lte_deferred;                 /* transient driver: BSIM4trunc in its own launch after the solve */
     double *b4_inst, *b4_state, *b4_op, *b4_mtab, *b4_ptab; int *b4_prow, *b4_prow_t, *b4_flags, *b4_nodes, *b4_spos;

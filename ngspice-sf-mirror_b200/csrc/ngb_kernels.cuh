@@ -352,6 +352,30 @@ NGB_HD void ngb_override_thread(const NgbAsmCtx *c, int s)
 #define NGB_GROUP_SYNC() ((void)0)     /* hostsim: one "thread" per group */
 #endif
 
+/* A pivoting event (SMPreorder) is due for sample s and the refactor has just run on the recorded order of that event: is
+ * this order the one a pivoting factor of THIS matrix would produce?  lpivot (klu_kernel.c:370-470) takes the diagonal when
+ * |x_d| >= tol * max|x_i|, else the first largest entry; on the normalised L entries l = x / pivot that reads |l| * tol <= 1
+ * (code 1), |l| < 1 (code 2: another pivot won, ties go to the host) and |l_d| < tol (code 3: the diagonal lost).  Decisions
+ * within 1e-9 of the threshold, infinities and NaN count as "no": the sample then reports E_SINGULAR with singular_col = -2
+ * and gets the host's pivoting factor (ngb_tran.c: repivot_suspended), exactly like a zero pivot.  V: the group's value array,
+ * ext: internal -> schedule numbering of the packed kernels (NULL: identity) */
+NGB_HD void ngb_lu_verify_order(const NgbLuCtx *c, int s, int lane, int nl, const double *V, const int *ext)
+{
+    const int *chk = c->sch.vchk;
+    const int nV = c->sch.nV;
+    const double tol = c->pivtol, one = 1.0 - 1e-9;
+    int bad = 0;
+    if (!chk) bad = (lane == 0);
+    else
+        for (int e = lane; e < nV; e += nl) {
+            const int code = NGB_LDG(&chk[ext ? NGB_LDG(&ext[e]) : e]);
+            if (!code) continue;
+            const double a = fabs(V[e]);
+            if (code == 1 ? !(a * tol <= one) : (code == 2 ? !(a <= one) : !(a <= tol * one))) bad = 1;
+        }
+    if (bad) { c->singular_col[s] = -2; c->ctl.err[s] = NGB_E_SINGULAR; }
+}
+
 /* Whole SMPluFac/SMPsolve/NIconvTest sequence for sample s, executed by a group of `nl`
  * threads (`lane` = index in the group).  V, Rs, Z are group-private scratch (shared memory
  * on the device): V[nV], Rs[n], Z[ntask]. */
@@ -422,6 +446,7 @@ NGB_HD void ngb_lu_sample(const NgbLuCtx *c, int s, int lane, int nl, double *V,
             c->singular_col[s] = sc;
             if (sc >= 0) c->ctl.err[s] = NGB_E_SINGULAR;
         }
+        if (c->verify && NGB_LDG(&c->verify[s])) { NGB_GROUP_SYNC(); ngb_lu_verify_order(c, s, lane, nl, V, NULL); }
         if (c->V && c->V + (size_t)s * nV != V) {       /* (the grid-wide LU works in these arrays) */
             double *Vg = c->V + (size_t)s * nV;
             for (int e = lane; e < nV; e += nl) Vg[e] = V[e];
@@ -564,6 +589,7 @@ NGB_HD void ngb_lu_sample_packed(const NgbLuCtx *c, const unsigned short *sb, in
         }
         for (int k = lane; k < n; k += nl)
             if (V[sb[h->o_diag + k]] == 0.0) { c->singular_col[s] = k; c->ctl.err[s] = NGB_E_SINGULAR; }
+        if (c->verify && NGB_LDG(&c->verify[s])) ngb_lu_verify_order(c, s, lane, nl, V, h->ext);
         if (c->V) {
             double *Vg = c->V + (size_t)s * nV;
             for (int e = lane; e < nV; e += nl) Vg[NGB_LDG(&h->ext[e])] = V[e];
@@ -757,6 +783,7 @@ NGB_UNROLL4
         }
         for (int k = lane; k < n; k += nl)
             if (V[diag[k]] == 0.0) { c->singular_col[s] = k; c->ctl.err[s] = NGB_E_SINGULAR; }
+        if (c->verify && NGB_LDG(&c->verify[s])) ngb_lu_verify_order(c, s, lane, nl, V, h->ext);
         if (c->V) {
             double *Vg = c->V + (size_t)s * nV;
             for (int e = lane; e < nV; e += nl) Vg[NGB_LDG(&h->ext[e])] = V[e];

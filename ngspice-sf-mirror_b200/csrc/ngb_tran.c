@@ -38,7 +38,7 @@ void ngb_tran_free(struct ngb_batch *b)
     ngb_dev_free(t->x.phase); ngb_dev_free(t->x.iterno); ngb_dev_free(t->x.firsttime); ngb_dev_free(t->x.nbreak);
     ngb_dev_free(t->x.npts); ngb_dev_free(t->x.brkflag); ngb_dev_free(t->x.accepted); ngb_dev_free(t->x.rejected);
     ngb_dev_free(t->x.numiter); ngb_dev_free(t->x.timepts); ngb_dev_free(t->x.save_delta); ngb_dev_free(t->x.old_delta);
-    ngb_dev_free(t->x.breaks); ngb_dev_free(t->x.out_time); ngb_dev_free(t->x.out_val); ngb_dev_free(t->x.ndone); ngb_dev_free(t->x.evstage);
+    ngb_dev_free(t->x.breaks); ngb_dev_free(t->x.out_time); ngb_dev_free(t->x.out_val); ngb_dev_free(t->x.ndone); ngb_dev_free(t->x.evstage); ngb_dev_free(t->x.verify);
     ngb_dev_free(t->x.gm_stage); ngb_dev_free(t->x.gm_factor); ngb_dev_free(t->x.gm_oldgmin); ngb_dev_free(t->x.gm_xold);
     ngb_dev_free(t->x.gm_startgmin); ngb_dev_free(t->x.gs_conv); ngb_dev_free(t->x.gs_raise); ngb_dev_free(t->x.gs_i);
     { int a; for (a = 0; a < t->x.gm_narr; a++) ngb_dev_free(t->x.gm_arr[a].old); }
@@ -78,6 +78,7 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     x->out_val = (double *)dz(sizeof(double) * (size_t)S * max_points * (nsave ? nsave : 1));
     x->ndone = (int *)dz(sizeof(int) * 4); x->evstage = (int *)dz(sizeof(int) * S);
     x->susp = (int *)dz(sizeof(int) * S); t->d_mask = (int *)dz(sizeof(int) * S);
+    x->verify = (int *)dz(sizeof(int) * S); b->lu_verify = x->verify;
     x->ipass = (int *)dz(sizeof(int) * S);
     if (b->ms_n > 0) {
         const int nm = b->ms_n;
@@ -134,6 +135,14 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
     x->nluset = (x->lu_event[0] != x->lu_event[1] || x->lu_event[1] != x->lu_event[2] || x->lu_event[2] != x->lu_event[3]) ? 2 : 1;
     x->pivot_events = (c->pivot_mode == 1 || (c->pivot_mode < 0 && c->klu_P && !getenv("NGB_BATCH_PIVOT"))) ? 1 : 0;
     if (x->pivot_events) x->nluset = 2;              /* every sample selects its own pattern set */
+    /* pivoting events: the device checks the recorded order of the event on the sample's own matrix (NgbLuSched.vchk) and only
+     * the samples for which KLU's rule would choose differently go to the host (NGB_HOST_PIVOT=1: all of them, as before) */
+    x->dev_verify = 0;
+    if (x->pivot_events && !getenv("NGB_HOST_PIVOT")) {
+        int e, ok = 1;
+        for (e = 0; e < NGB_LU_EVENTS; e++) if (!c->lu[x->lu_event[e]].valid || !c->lu[x->lu_event[e]].sch.vchk) ok = 0;
+        x->dev_verify = ok;
+    }
     memset(t->keep_set, 0, sizeof t->keep_set);
     x->maxorder = c->opt.maxorder; x->uic = c->opt.uic; x->max_iter_tran = c->opt.itl4; x->max_iter_dc = c->opt.itl1;
     if (x->minbreak == 0) x->minbreak = x->tmax * 5e-5;            /* dctran.c:163-164 */
@@ -157,8 +166,10 @@ static int tran_setup(ngb_batch *b, int max_points, const int *save_eq, int nsav
         /* NIiter under MODETRANOP|MODEUIC swaps rhs/rhsOld before its single CKTload */
         for (s = 0; s < S; s++) iv[s] = c->opt.uic ? 1 : 0;
         ngb_dev_h2d(b->ctl.xsel, iv, sizeof(int) * S);
-        for (s = 0; s < S; s++) iv[s] = x->pivot_events ? -1 : x->lu_event[c->opt.uic ? 2 : 0];   /* the first factor of a run pivots */
+        for (s = 0; s < S; s++) iv[s] = (x->pivot_events && !x->dev_verify) ? -1 : x->lu_event[c->opt.uic ? 2 : 0];   /* the first factor of a run pivots */
         ngb_dev_h2d(b->ctl.lusel, iv, sizeof(int) * S);
+        for (s = 0; s < S; s++) iv[s] = x->dev_verify ? 1 : 0;
+        ngb_dev_h2d(x->verify, iv, sizeof(int) * S);
         memset(iv, 0, sizeof(int) * S);
         ngb_dev_h2d(b->ctl.head, iv, sizeof(int) * S);
         ngb_dev_h2d(b->ctl.noncon, iv, sizeof(int) * S);
@@ -221,7 +232,7 @@ static int enqueue_tick_direct(ngb_batch *b, int with_lu)
             NgbLuCtx lx;
             int used = 0;
             if (!b->dlu[w].valid) continue;
-            if (!b->tran->x.pivot_events) for (e = first; e < NGB_LU_EVENTS; e++) if (ev[e] == w) used = 1;
+            if (!b->tran->x.pivot_events || b->tran->x.dev_verify) for (e = first; e < NGB_LU_EVENTS; e++) if (ev[e] == w) used = 1;
             if (b->tran->keep_set[w]) used = 1;
             if (!used) continue;                                            /* no sample can be on this set any more */
             ngb_fill_luctx(b, &lx, 1, 1, w);
@@ -324,7 +335,7 @@ static int repivot_suspended(ngb_batch *b)
             if (!used[w]) continue;
             ngb_fill_luctx(b, &lx, 1, 1, w);
             lx.ctl.active = t->d_mask;
-            lx.V = NULL;
+            lx.V = NULL; lx.verify = NULL;           /* these samples' orders come from the pivoting factor itself */
             r = ngb_launch_lu(&lx);
         }
         if (r == NGB_OK && b->lte_deferred && b->c->b4_n) {
@@ -444,6 +455,7 @@ int ngbTranWaves(ngb_batch *b, double *times, double *values)
     return NGB_OK;
 }
 long ngbTranTicks(ngb_batch *b) { return b->tran ? b->tran->ticks : 0; }
+int ngbTranRepivots(ngb_batch *b) { return b->tran ? b->tran->repivots : 0; }
 void *ngbTranDevWaves(ngb_batch *b, int which) { return b->tran ? (which ? (void *)b->tran->x.out_val : (void *)b->tran->x.out_time) : NULL; }
 
 /* `.meas tran` clauses for the next ngbTranRun, evaluated on the device while the points are produced (com_measure_when,

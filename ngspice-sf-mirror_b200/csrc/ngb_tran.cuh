@@ -50,6 +50,9 @@ typedef struct NgbTranCtx {
     int *susp;                 /* [S] 0; 1: the refactor met a zero pivot, the sample waits (inactive) for the host to factor its matrix
                                 * again with pivoting, niiter.c:162-195; 2: that factor found the matrix singular -- NIiter returns E_SINGULAR */
     const int *only;           /* not NULL: this launch handles only the samples with only[s] != 0 (the ones the host has just re-pivoted) */
+    int *verify;               /* [S] a pivoting event is due in the sample's next iteration and the LU kernel is to check the event's
+                                * recorded pivot order against KLU's rule on the sample's own matrix (NgbLuCtx.verify) */
+    int dev_verify;            /* 1: pivoting events are answered that way; only samples that fail the check go to the host */
     /* measurement clauses evaluated while the points are produced (com_measure_when, com_measure2.c:378-663): the n-th
      * RISE / FALL / CROSS of one saved quantity through a constant, linearly interpolated between the two output points
      * around it.  A `.meas tran x TRIG .. TARG ..` is two clauses (result = second - first).  No waveform has to be kept */
@@ -413,6 +416,11 @@ NGB_HD void ngb_next_time(const NgbTranCtx *c, int s)
     ngb_begin_point(c, s);
 }
 
+/* the pattern set a pivoting event sends the sample to: without per-sample pivoting the set the recorded run's factor produced;
+ * with it either that set plus the request to verify its order on the sample's matrix in the LU kernel, or -1 (the sample waits
+ * for the host's pivoting factor) */
+#define NGB_EVENT_LUSEL(c, s, e) (!(c)->pivot_events ? (c)->lu_event[e] : ((c)->dev_verify ? ((c)->verify[s] = 1, (c)->lu_event[e]) : -1))
+
 /* CKTstate0 and CKTrhsOld of sample s: op 0 zero them, 1 save to the Old copies, 2 restore from them (cktop.c:182-186, 210-214, 244-248) */
 NGB_HD void ngb_gm_states(const NgbTranCtx *c, int s, int op)
 {
@@ -441,7 +449,7 @@ NGB_HD void ngb_gm_next_niiter(const NgbTranCtx *c, int s, int mode)
     c->ctl.mode[s] = mode;
     c->iterno[s] = 0;
     c->ipass[s] = 0;
-    if ((mode & NGB_MODEINITJCT) && c->nluset > 1) c->ctl.lusel[s] = c->pivot_events ? -1 : c->lu_event[0];
+    if ((mode & NGB_MODEINITJCT) && c->nluset > 1) c->ctl.lusel[s] = NGB_EVENT_LUSEL(c, s, 0);
 }
 
 /* One controller step for sample s, after the load (+ LU + solve) of this tick. */
@@ -451,6 +459,7 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
     int phase = c->phase[s];
     if (phase == NGB_PH_IDLE || phase == NGB_PH_DONE || phase == NGB_PH_FAIL) return;
     if (c->only ? !c->only[s] : (c->susp && c->susp[s] == 1)) return;
+    if (c->verify) c->verify[s] = 0;         /* the check, if one was due, ran in this step's LU launch */
     /* state copies requested for the load that just ran are done */
     const int sop_done = c->ctl.stateop[s];
     c->ctl.stateop[s] = 0;
@@ -497,6 +506,7 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
         c->ctl.ag0[s] = 0; c->ctl.ag1[s] = 0;
         c->ctl.stateop[s] = NGB_OP_COPY01;
         c->ctl.noncon[s] = 0; c->nodeconv_w[s] = 0; c->ctl.lte[s] = 1e300; c->ctl.lte2[s] = 1e300;
+        if (c->nluset > 1) c->ctl.lusel[s] = NGB_EVENT_LUSEL(c, s, 2);        /* the first factor of the run is still ahead */
         ngb_ev_advance(c, s, 1);
         ngb_next_time(c, s);
         return;
@@ -529,13 +539,13 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
             if (noncon == 0) niret = NGB_OK;
         } else if (mode & NGB_MODEINITJCT) {
             mode = (mode & ~NGB_INITF) | NGB_MODEINITFIX;
-            if (c->nluset > 1) c->ctl.lusel[s] = c->pivot_events ? -1 : c->lu_event[1];           /* NISHOULDREORDER, niiter.c:335 */
+            if (c->nluset > 1) c->ctl.lusel[s] = NGB_EVENT_LUSEL(c, s, 1);           /* NISHOULDREORDER, niiter.c:335 */
         } else if (mode & NGB_MODEINITFIX) {
             if (noncon == 0) mode = (mode & ~NGB_INITF) | NGB_MODEINITFLOAT;
             c->ipass[s] = 1;
         } else if (mode & (NGB_MODEINITTRAN | NGB_MODEINITPRED | NGB_MODEINITSMSIG)) {
             if ((mode & NGB_MODEINITTRAN) && iterno <= 1) {
-                if (c->nluset > 1) c->ctl.lusel[s] = c->pivot_events ? -1 : c->lu_event[3];       /* NISHOULDREORDER, niiter.c:343-344 */
+                if (c->nluset > 1) c->ctl.lusel[s] = NGB_EVENT_LUSEL(c, s, 3);       /* NISHOULDREORDER, niiter.c:343-344 */
                 ngb_ev_advance(c, s, 2);
             }
             mode = (mode & ~NGB_INITF) | NGB_MODEINITFLOAT;
@@ -704,7 +714,7 @@ NGB_HD void ngb_tran_control(const NgbTranCtx *c, int s)
         c->ctl.ag0[s] = 0; c->ctl.ag1[s] = 0;
         c->ctl.stateop[s] = NGB_OP_COPY01;
         /* NIiter re-pivots in the first iteration under MODEINITTRAN (niiter.c:107-111) */
-        if (c->nluset > 1) c->ctl.lusel[s] = c->pivot_events ? -1 : c->lu_event[2];
+        if (c->nluset > 1) c->ctl.lusel[s] = NGB_EVENT_LUSEL(c, s, 2);
         ngb_ev_advance(c, s, 1);
         ngb_next_time(c, s);
         return;

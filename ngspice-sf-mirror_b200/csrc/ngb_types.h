@@ -145,6 +145,9 @@ typedef struct NgbLuSched {
     const int *e_pptr;      /* [nV+1] into pair_l / pair_u                               */
     const int *pair_l, *pair_u;
     const int *diag_v;      /* [n] value id of Udiag[k]                                  */
+    const int *vchk;        /* [nV] or NULL: what KLU's pivot rule (lpivot, klu_kernel.c:370-470) asks of an L entry for this
+                             * pivot order to be the one klu_factor would choose: 0 nothing, 1 column with its diagonal as pivot
+                             * (|l| * tol <= 1), 2 column with another pivot (|l| < 1), 3 the displaced diagonal (|l| < tol) */
     const int *row_ptr;     /* [n+1] CSR view of A for the row scale factors             */
     const int *row_slot;
     /* triangular solves as 2n row tasks */
@@ -212,6 +215,10 @@ typedef struct NgbLuCtx {
     double reltol, abstol, vntol;
     int *nodeconv;          /* [S] 1 if some node failed                                 */
     int *singular_col;      /* [S] -1 or first zero pivot column                         */
+    const int *verify;      /* [S] or NULL: 1 = a pivoting event (SMPreorder) is due for the sample in this iteration: after the
+                             * refactor on this set's order, check that the order is what the pivoting factor would choose
+                             * (sch.vchk); if not, report E_SINGULAR with singular_col = -2 and the host factors with pivoting */
+    double pivtol;
     /* work arrays of the grid-wide LU (a circuit too large for one CTA's shared memory): values, scale factors, solve tasks */
     double *gV, *gRs, *gZ;  /* [S][nV], [S][n], [S][ntask]                               */
     NgbCtl ctl;

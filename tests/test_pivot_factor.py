@@ -91,3 +91,29 @@ def test_own_analysis_gives_a_usable_factor(hostsim_lib):
     assert int(res.err[0]) == 0 and n == len(wave["time"])
     rng = np.max(np.abs(wave["values"]), axis=0)
     assert (np.max(np.abs(v[0, :n, :] - wave["values"]), axis=0) / rng <= 1e-9).all()
+
+
+def test_pivot_events_verified_without_the_host(hostsim_lib, monkeypatch):
+    """At the reference's pivoting events the LU launch checks the event's recorded pivot order against KLU's rule on the
+    sample's own matrix (NgbLuSched.vchk: lpivot, klu_kernel.c:370-470) and only a sample that fails goes to the host's
+    pivoting factor.  The recorded run itself never does; eight sweep points of the mixed cell need it once per point
+    instead of four times -- same iteration counts, same bits as with every event factored on the host"""
+    import hashlib
+    from parity_util import run_patterns
+    flat = ngt.read(f"{GOLDEN}/mix.flat.ngt"); trace = ngt.read(f"{GOLDEN}/mix.trace.ngt.gz"); wave = ngt.read(f"{GOLDEN}/mix.wave.ngt")
+    pts = [("2.0", "1k"), ("1.6", "200"), ("1.6", "5k"), ("2.4", "200"), ("2.4", "5k"), ("1.69098", "1348.2"), ("1.69412", "2364.7"), ("1.69412", "2383.5")]
+
+    def run(points):
+        circ = pkg.Circuit.from_flat(hostsim_lib, flat, lu_pattern=run_patterns(trace))
+        b = pkg.Batch(circ, len(points))
+        pkg.sweep.apply(b, flat, dc={"vdd": [p[0] for p in points]}, res={"r1": [p[1] for p in points]})
+        res = b.tran(8192, wave["save_eq"])
+        return res, hashlib.md5(res.waves()[1].tobytes()).hexdigest()
+
+    res, _ = run(pts[:1])
+    assert res.repivots == 0 and int(res.numiter[0]) == int(wave["stats"][2])
+    dev, h_dev = run(pts)
+    monkeypatch.setenv("NGB_HOST_PIVOT", "1")
+    host, h_host = run(pts)
+    assert h_dev == h_host and np.array_equal(dev.numiter, host.numiter)
+    assert 0 < dev.repivots < host.repivots and host.repivots >= 4 * len(pts)
