@@ -115,7 +115,8 @@ def spice_number(text):
     ip, fp, ex, suf = m_.group(2), m_.group(3) or "", m_.group(4), m_.group(5)
     m = 0.0
     for ch in ip + fp:
-        m = 10.0 * m + (ord(ch) - 48)
+        m = (10.0 * m + ord(ch)) - 48.0          # `mantis = 10 * mantis + *here - '0'`: the character code is added first (inpeval.c:69), which
+                                                 # rounds differently from 10 m + digit once the mantissa passes 2^53 (17-digit tokens)
     if m_.group(3) is None and ex is None and not suf:
         return m * sign
     e = -len(fp) + (int(ex) if ex else 0)

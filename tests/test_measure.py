@@ -96,3 +96,15 @@ def test_measure_device(cuda_lib):
     gold, clauses, owner, save, res = _run(cuda_lib, 64, 0)
     ms = res.measures()
     assert (res.err == 0).all() and np.array_equal(ms[:, :1].repeat(64, 1), ms, equal_nan=True)
+
+
+def test_spice_number_follows_the_reference_parser():
+    """pkg.mc.spice_number restates INPevaluate (inpeval.c:65-201): digits accumulate in a double as `10 * mantis + c - '0'`
+    -- the character code is added before '0' is subtracted, which matters once the mantissa passes 2^53 -- and the result is
+    mantis * pow(10, exponent), not the nearest double.  Values recorded from the reference's own parse of `delvto=<text>`
+    (oracle/_ref/ngspice_dump, b4t/inst) for two 17-digit tokens the plain 10 m + digit recurrence gets wrong by one ulp"""
+    from parity_util import pkg
+    assert pkg.mc.spice_number("0.0095290870168629038") == 0.009529087016862904
+    assert pkg.mc.spice_number("0.0087862920898565608") == 0.00878629208985656
+    assert pkg.mc.spice_number("1.2905820754597296e-09") == 1.2905820754597296e-09
+    assert pkg.mc.spice_number("150ns") == 150 * 1e-9 and pkg.mc.spice_number("2") == 2.0
