@@ -908,8 +908,10 @@ def sweep_points(rank, world, n):
     return [vt[i // SWEEP_GRID] for i in idx], [rt[i % SWEEP_GRID] for i in idx]
 
 
-def sweep_cpu_baseline(nproc, per_proc=128):
-    """the reference on the same sweep: `nproc` processes, each running `per_proc` grid points one after the other"""
+def sweep_cpu_baseline(nproc, per_proc=128, own=None):
+    """the reference on the same sweep: `nproc` processes, each running `per_proc` grid points one after the other.
+    own = (vdd tokens, r tokens) of the calling rank's points: the reference then simulates every (len / n)-th of THOSE points
+    and keeps its rawfiles -- the parity check of the benchmarked run; the return value gets a fifth element [(point, rawfile)]"""
     exe = os.path.join(ROOT, "oracle", "_ref", "ngspice")
     if not os.path.exists(exe):
         return None
@@ -921,17 +923,24 @@ def sweep_cpu_baseline(nproc, per_proc=128):
     rt = pkg.sweep.grid_tokens(200.0, 5000.0, SWEEP_GRID, fmt="{:.5g}")
     tmp = tempfile.mkdtemp(prefix="ngb_sweep_")
     procs = []
+    kept = []
     t0 = time.time()
     for p in range(nproc):
         files = []
         for k in range(per_proc):
-            i = (p * per_proc + k) * stride + (p * 37 + k * 11) % SWEEP_GRID      # spread over the grid
-            text = base.replace("vdd dd 0 dc 2.0", f"vdd dd 0 dc {vt[(i // SWEEP_GRID) % SWEEP_GRID]}").replace("r1 a8 x 1k", f"r1 a8 x {rt[i % SWEEP_GRID]}")
+            if own is not None:
+                q = ((p * per_proc + k) * len(own[0])) // n                      # evenly through this rank's share
+                vtok, rtok = own[0][q], own[1][q]
+            else:
+                i = (p * per_proc + k) * stride + (p * 37 + k * 11) % SWEEP_GRID      # spread over the grid
+                q, vtok, rtok = -1, vt[(i // SWEEP_GRID) % SWEEP_GRID], rt[i % SWEEP_GRID]
+            text = base.replace("vdd dd 0 dc 2.0", f"vdd dd 0 dc {vtok}").replace("r1 a8 x 1k", f"r1 a8 x {rtok}")
             text = text.replace(".option klu", ".option klu acct")
             f = os.path.join(tmp, f"p{p}_{k}.cir")
             open(f, "w").write(text)
             files.append(f)
-        cmd = " ; ".join(f"{exe} -b -r {f}.raw {f} > {f}.log 2>&1 ; rm -f {f}.raw" for f in files)
+            kept.append((q, f + ".raw"))
+        cmd = " ; ".join(f"{exe} -b -r {f}.raw {f} > {f}.log 2>&1" + ("" if own is not None else f" ; rm -f {f}.raw") for f in files)
         procs.append((subprocess.Popen(["bash", "-c", cmd]), files))
     iters = 0
     for pr, files in procs:
@@ -942,7 +951,36 @@ def sweep_cpu_baseline(nproc, per_proc=128):
             for ln in open(f + ".log", errors="replace"):
                 if ln.startswith("Total iterations"):
                     iters += int(ln.split("=")[-1].strip().split()[0])
-    return n / wall, iters, wall, f"{n} grid points ({per_proc} per process x {nproc} processes), DC op + 200-step transient each"
+    return n / wall, iters, wall, f"{n} grid points ({per_proc} per process x {nproc} processes), DC op + 200-step transient each", kept
+
+
+def sweep_parity(kept, save_names, npts, t_gpu, v_gpu, tol=1e-8):
+    """the reference's rawfiles of the rank's own grid points against the waveforms of the end-to-end pass: per accepted point
+    |v - v_ref| <= tol * max(|v_ref|, 1e-6 V) (1e-8: the VBIC Jacobian comes from dual numbers and the
+    cell's ring oscillator carries that rounding through zero crossings, tests/test_tran_parity.py)"""
+    same, within, worst, worst_t, n = 0, 0, 0.0, 0.0, 0
+    for q, raw in kept:
+        try:
+            tt, vv = read_rawfile(raw, [f"v({s})" for s in save_names])
+        except Exception:
+            continue
+        finally:
+            try:
+                os.remove(raw)
+            except OSError:
+                pass
+        n += 1
+        k = len(tt)
+        if int(npts[q]) != k:
+            continue
+        same += 1
+        ref = np.stack([vv[f"v({s})"] for s in save_names], axis=1)
+        e = float(np.max(np.abs(v_gpu[q, :k, :] - ref) / np.maximum(np.abs(ref), 1e-6)))
+        et = float(np.max(np.abs(t_gpu[q, :k] - tt) / np.maximum(tt, 1e-300)))
+        worst = max(worst, e); worst_t = max(worst_t, et)
+        within += (e <= tol and et <= 1e-9)
+    return {"points": n, "same_point_count": same, "within_tolerance": int(within), "tolerance": tol, "max_rel_err": worst,
+            "max_rel_err_time": worst_t, "ok": bool(n > 0 and same == n and within == n)}
 
 
 def bench_sweep(args):
@@ -993,11 +1031,14 @@ def bench_sweep(args):
     h2d_bytes = vpar.nbytes + gtab.nbytes
     d2h_bytes = (out_t.numel() + out_v.numel()) * 8
 
+    last_res = [None]
+
     def step(e2e):
         if e2e:
             batch.put("vsrc.par", vpar)
             batch.set_resistors(gtab)
         res = batch.tran(max_points, save_eq)
+        last_res[0] = res
         if e2e:
             lib.check(lib.L.ngbTranWaves(batch.h, ctypes.cast(out_t.data_ptr(), ctypes.POINTER(ctypes.c_double)),
                                          ctypes.cast(out_v.data_ptr(), ctypes.POINTER(ctypes.c_double))), "ngbTranWaves")
@@ -1046,7 +1087,12 @@ def bench_sweep(args):
         # (BSIM4 2 000 B, BSIM3 1 400 B, VBIC 3 400 B, diode 700 B per evaluation)
         bytes_step = SWEEP_COUNTS["bsim4"] * 2000 + SWEEP_COUNTS["bsim3"] * 1400 + SWEEP_COUNTS["vbic"] * 3400 + SWEEP_COUNTS["diode"] * 700
         achieved = iters_tot * bytes_step / (ms_max * 1e-3) / 1e9 / world          # per GPU
-        cpu = sweep_cpu_baseline(os.cpu_count() or 1)
+        cpu = sweep_cpu_baseline(os.cpu_count() or 1, own=(vdd_tok, r_tok))
+        parity = None
+        if cpu is not None:
+            names = bytes(np.asarray(flat["node/names_bytes"]).astype(np.uint8)).decode().split("\n")
+            eq_name = {int(ln.split()[0]): ln.split()[1].lower() for ln in names if ln.strip()}
+            parity = sweep_parity(cpu[4], [eq_name[int(e)] for e in save_eq], last_res[0].npoints, out_t.numpy(), out_v.numpy())
         line = {
             "metric": "sweep points/s", "value": points_tot / (ms_max * 1e-3), "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -1061,6 +1107,7 @@ def bench_sweep(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = {"value": cpu[0], "unit": "points/s", "cores": os.cpu_count() or 1, "kind": "reference", "sample": cpu[3]}
+            line["parity_check"] = parity
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
