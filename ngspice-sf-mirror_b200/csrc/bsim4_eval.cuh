@@ -249,7 +249,20 @@ NGB_HD_SHARED void b4_tat(double vts, double vj, double Nvtmr, double *Tn, doubl
     double *const b4st2 = c->state + (size_t)(((head_) + 2 >= b4nh_) ? (head_) + 2 - b4nh_ : (head_) + 2) * b4hs_ + t; \
     double *const b4st3 = c->state + (size_t)(((head_) + 3 >= b4nh_) ? (head_) + 3 - b4nh_ : (head_) + 3) * b4hs_ + t; \
     (void)b4st1; (void)b4st2; (void)b4st3; (void)b4st0
+#if defined(__CUDA_ARCH__) && defined(NGB_B4_STREAM)
+/* experiment switch: the states are read once and written once per evaluation and do not come back before the next
+ * Newton step (the step's working set is larger than L2), so their loads / stores can carry the streaming (evict-first)
+ * policy and leave L1 to the spilled values */
+struct B4StRef {
+    double *p;
+    __device__ __forceinline__ operator double() const { return __ldcs(p); }
+    __device__ __forceinline__ double operator=(double v) const { if (NGB_B4_STREAM > 1) __stcs(p, v); else *p = v; return v; }
+    __device__ __forceinline__ double operator=(const B4StRef &o) const { const double v = o; *this = v; return v; }
+};
+#define B4ST(h, k) (B4StRef{ &b4st##h[(size_t)(k) * c->T] })
+#else
 #define B4ST(h, k) b4st##h[(size_t)(k) * c->T]
+#endif
 
 /* Phase A: terminal voltages by INITF mode and Newton step limiting (b4ld.c:257-698). */
 template <unsigned VK>
@@ -3013,6 +3026,21 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
     B4W w;
     int err;
     if (!b4_prologue(c, t, 1, &p, &err)) return err;
+#if defined(__CUDA_ARCH__) && defined(NGB_B4_PREFETCH)
+    {   /* experiment switch: the per-thread columns this evaluation will read (instance parameters, the two newest
+         * state planes) are asked for at once, so that the loads scattered over the 14 k instructions behind find them
+         * in L2 instead of waiting for DRAM one after the other */
+        B4ST_BASES(p.head);
+#pragma unroll
+        for (int k = 0; k < B4ST_COUNT; k++) {
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(&b4st0[(size_t)k * c->T]));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(&b4st1[(size_t)k * c->T]));
+        }
+#pragma unroll
+        for (int f = 0; f < B4I_COUNT; f++)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(&c->inst[(size_t)f * c->T + t]));
+    }
+#endif
     b4_fetch_limit<VK>(c, t, p.inst, p.s, p.head, p.mode_ckt, p.Mrow, p.flags, &w);
     b4_core_dc<VK>(c, t, p.s, p.Mrow, p.Prow, p.flags, &w);
     /* the parasitics and the intrinsic charges only read what the core phase left; the charges first (12 values for the
