@@ -211,6 +211,12 @@ int ngbTranStats(ngb_batch *b, int *accepted, int *rejected, int *numiter, int *
 int ngbTranErrors(ngb_batch *b, int *err /* [S] */);
 long ngbTranWaveBytes(ngb_batch *b);
 int ngbTranWaves(ngb_batch *b, double *times /* [S][max_points] */, double *values /* [S][max_points][nsave] */);
+/* batch-aware binary rawfile of the stored waveforms (replaces the per-point OUTpData -> fileAddRealValue path of
+ * src/frontend/outitf.c:633-765 and its header writers fileInit :881-923 / fileInit_pass2 :997-1029 for a batch): samples
+ * first_sample .. first_sample + nsamples - 1 as consecutive `Transient Analysis` plots of one file, each with the reference's
+ * header lines and `Binary:` rows {time, saved equations}.  names / types [nsave]: e.g. "v(out)" / "voltage"; date NULL = now */
+int ngbTranWriteRaw(ngb_batch *b, const char *path, const char *title, const char *date, const char *const *names,
+                    const char *const *types, int first_sample, int nsamples);
 /* `.meas tran` on the device (the output path of src/frontend/outitf.c:633 + com_measure2.c:378-663 for this workload):
  * clause k is the count[k]-th RISE (kind 0) / FALL (1) / CROSS (2) of equation eq[k] through val[k], linearly
  * interpolated between the two accepted points around it, points before td[k] ignored -- evaluated as the points are

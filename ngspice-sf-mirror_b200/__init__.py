@@ -411,6 +411,16 @@ class TranResult:
         self.b.lib.check(self.b.lib.L.ngbTranMeasures(self.b.h, _dp(out)), "ngbTranMeasures")
         return out
 
+    def write_raw(self, path, names, types=None, title="", date=None, first_sample=0, nsamples=None):
+        """binary rawfile with one `Transient Analysis` plot per sample (header and rows as `ngspice -b -r` writes them,
+        outitf.c:881-1092); names = the saved equations' vector names in the order given to tran()"""
+        n = self.b.S - first_sample if nsamples is None else nsamples
+        types = types or ["current" if x.startswith("i(") else "voltage" for x in names]
+        assert len(names) == self.nsave and len(types) == self.nsave
+        arr = lambda xs: (ctypes.c_char_p * len(xs))(*[x.encode() for x in xs])
+        self.b.lib.check(self.b.lib.L.ngbTranWriteRaw(self.b.h, path.encode(), title.encode(), date.encode() if date else None,
+                                                      arr(names), arr(types), int(first_sample), int(n)), "ngbTranWriteRaw")
+
     def waves(self):
         S = self.b.S
         t = np.zeros((S, self.max_points)); v = np.zeros((S, self.max_points, max(self.nsave, 1)))

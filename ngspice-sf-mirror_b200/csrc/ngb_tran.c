@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <time.h>
 #include "ngb_dev.h"
 #include "ngb_host.h"
 #include "../../include/ngb200.h"
@@ -453,6 +454,60 @@ int ngbTranWaves(ngb_batch *b, double *times, double *values)
     if (times) ngb_dev_d2h(times, t->x.out_time, sizeof(double) * (size_t)b->S * t->max_points);
     if (values && t->nsave) ngb_dev_d2h(values, t->x.out_val, sizeof(double) * (size_t)b->S * t->max_points * t->nsave);
     return NGB_OK;
+}
+/* Batch-aware binary rawfile of the last ngbTranRun: one plot per sample, one after the other in ONE file (the way the
+ * reference lays out the plots of several analyses in a rawfile; `load` reads them as tran1, tran2, ...).  Each plot is what
+ * `ngspice -b -r` writes for a transient run -- the header of fileInit (src/frontend/outitf.c:881-923: Title / Date /
+ * Command / Plotname / Flags / No. Variables / No. Points padded to 8 columns / Variables), the variable lines of
+ * fileInit_pass2 (:997-1029: "\t<index>\t<name>\t<type>", index 0 is `time`), `Binary:` and then the points row by row as
+ * raw doubles (fileStartPoint / fileAddRealValue / fileEndPoint, :1048-1092).  names / types: the nsave saved equations in
+ * the order given to ngbTranRun ("v(out)" / "voltage", "i(vdd)" / "current"); date NULL = now in the reference's datestring
+ * format (src/misc/misc_time.c).  The waveforms come from the device in two copies, whatever the number of samples. */
+int ngbTranWriteRaw(ngb_batch *b, const char *path, const char *title, const char *date, const char *const *names, const char *const *types,
+                    int first_sample, int nsamples)
+{
+    struct ngb_tran *t = b ? b->tran : NULL;
+    const int S = b ? b->S : 0;
+    int s, k, r = NGB_OK, *npts = NULL;
+    double *tm = NULL, *val = NULL, *row = NULL;
+    char datebuf[64];
+    FILE *fp;
+    if (!t || t->max_points <= 0) { ngb_set_error("no stored waveforms: run ngbTranRun with max_points > 0 first"); return NGB_E_PANIC; }
+    if (!path || !names || !types || first_sample < 0 || nsamples < 1 || first_sample + nsamples > S) { ngb_set_error("ngbTranWriteRaw: bad arguments"); return NGB_E_PANIC; }
+    if (!date) {
+        time_t now = time(NULL);
+        struct tm tmv;
+        localtime_r(&now, &tmv);
+        strftime(datebuf, sizeof datebuf, "%a %b %e %H:%M:%S  %Y", &tmv);          /* asctime without its newline */
+        date = datebuf;
+    }
+    npts = (int *)malloc(sizeof(int) * (size_t)S);
+    tm = (double *)malloc(sizeof(double) * (size_t)S * t->max_points);
+    val = (double *)malloc(sizeof(double) * (size_t)S * t->max_points * (size_t)(t->nsave ? t->nsave : 1));
+    row = (double *)malloc(sizeof(double) * (size_t)(t->nsave + 1));
+    if (!npts || !tm || !val || !row) { r = NGB_E_PANIC; ngb_set_error("out of memory"); goto out; }
+    ngb_dev_d2h(npts, t->x.npts, sizeof(int) * (size_t)S);
+    if ((r = ngbTranWaves(b, tm, val))) goto out;
+    if (!(fp = fopen(path, "wb"))) { ngb_set_error("cannot open %s", path); r = NGB_E_PANIC; goto out; }
+    for (s = first_sample; s < first_sample + nsamples; s++) {
+        const int n = npts[s] < t->max_points ? npts[s] : t->max_points;     /* points past max_points were not stored */
+        int p;
+        fprintf(fp, "Title: %s\nDate: %s\nCommand: ngb200, sample %d of %d\nPlotname: Transient Analysis\nFlags: real\n",
+                title ? title : "", date, s, S);
+        fprintf(fp, "No. Variables: %d\nNo. Points: %-8d\nVariables:\n\t0\ttime\ttime\n", t->nsave + 1, n);
+        for (k = 0; k < t->nsave; k++) fprintf(fp, "\t%d\t%s\t%s\n", k + 1, names[k], types[k]);
+        fprintf(fp, "Binary:\n");
+        for (p = 0; p < n; p++) {
+            row[0] = tm[(size_t)s * t->max_points + p];
+            for (k = 0; k < t->nsave; k++) row[k + 1] = val[((size_t)s * t->max_points + p) * t->nsave + k];
+            if (fwrite(row, sizeof(double), (size_t)t->nsave + 1, fp) != (size_t)t->nsave + 1) { ngb_set_error("write to %s failed", path); r = NGB_E_PANIC; break; }
+        }
+        if (r) break;
+    }
+    if (fclose(fp) && !r) { ngb_set_error("write to %s failed", path); r = NGB_E_PANIC; }
+out:
+    free(npts); free(tm); free(val); free(row);
+    return r;
 }
 long ngbTranTicks(ngb_batch *b) { return b->tran ? b->tran->ticks : 0; }
 int ngbTranRepivots(ngb_batch *b) { return b->tran ? b->tran->repivots : 0; }
