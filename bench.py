@@ -33,7 +33,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 B4_BYTES_PER_EVAL = 2000.0          # algorithmic bytes per BSIM4 instance-eval
@@ -319,7 +318,8 @@ def workload_config(args):
 def bench_ours(args):
     import torch
     import torch.distributed as dist
-    from parity_util import ngt, pkg, first_pattern, run_patterns
+    pkg = importlib.import_module("ngspice-sf-mirror_b200"); ngt = pkg.ngt
+    first_pattern, run_patterns = ngt.first_pattern, ngt.run_patterns
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -900,7 +900,7 @@ SWEEP_COUNTS = {"bsim4": 16, "bsim3": 8, "vbic": 2, "diode": 3}
 
 def sweep_points(rank, world, n):
     """the (vdd, r1) netlist tokens of this rank's share of the grid: consecutive rows of the 256 x 256 grid"""
-    from parity_util import pkg
+    pkg = importlib.import_module("ngspice-sf-mirror_b200")
     vt = pkg.sweep.grid_tokens(1.6, 2.4, SWEEP_GRID)
     rt = pkg.sweep.grid_tokens(200.0, 5000.0, SWEEP_GRID, fmt="{:.5g}")
     first = (rank * n) % (SWEEP_GRID * SWEEP_GRID)
@@ -918,7 +918,7 @@ def sweep_cpu_baseline(nproc, per_proc=128, own=None):
     base = open(os.path.join(GOLDEN, "netlists", "mix.cir")).read()
     n = nproc * per_proc
     stride = (SWEEP_GRID * SWEEP_GRID) // n
-    from parity_util import pkg
+    pkg = importlib.import_module("ngspice-sf-mirror_b200")
     vt = pkg.sweep.grid_tokens(1.6, 2.4, SWEEP_GRID)
     rt = pkg.sweep.grid_tokens(200.0, 5000.0, SWEEP_GRID, fmt="{:.5g}")
     tmp = tempfile.mkdtemp(prefix="ngb_sweep_")
@@ -988,7 +988,8 @@ def sweep_parity(kept, save_names, npts, t_gpu, v_gpu, tol=1e-7):
 def bench_sweep(args):
     import torch
     import torch.distributed as dist
-    from parity_util import ngt, pkg, run_patterns
+    pkg = importlib.import_module("ngspice-sf-mirror_b200"); ngt = pkg.ngt
+    run_patterns = ngt.run_patterns
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -49,3 +49,29 @@ def scalar(d, key, default=None):
     if key not in d:
         return default
     return d[key].reshape(-1)[0].item()
+
+
+# ---- LU pattern sets out of a recorded reference run (`*.trace.ngt.gz`, written by oracle/ref_hooks.c through
+# tests/golden/make_golden.py): what Circuit.from_flat(lu_pattern=...) takes when a run has to follow KLU's own orders
+def first_pattern(trace):
+    ks = sorted({int(k.split("/")[0][1:]) for k in trace if k.endswith("/pat/n")})
+    k = ks[0]
+    pre = f"c{k}/pat/"
+    return {kk[len(pre):]: v for kk, v in trace.items() if kk.startswith(pre)}
+
+
+def run_patterns(trace):
+    """the pivoting factors of a complete run, in the order the reference computed them (recorded by
+    oracle/ref_hooks.c at every SMPreorder): the INITJCT iteration and the one after it, then the first two
+    iterations of the first time point -- two factors for a UIC run.  Circuit.set_lu_pattern maps them onto
+    pattern sets (identical factors share one)."""
+    ks = sorted({int(k.split("/")[0][1:]) for k in trace if k.endswith("/pat/n")})
+    uic = bool(int(trace[f"c{ks[0]}/mode"][0]) & 0x1000) or not (int(trace[f"c{ks[0]}/mode"][0]) & 0x200)
+    want = 2 if uic else 4
+    return [pattern_at(trace, k) for k in ks[:want]]
+
+
+def pattern_at(trace, call):
+    pre = f"c{call}/pat/"
+    d = {kk[len(pre):]: v for kk, v in trace.items() if kk.startswith(pre)}
+    return d or None
