@@ -17,6 +17,12 @@
 #include <cooperative_groups.h>
 /* a group is a warp, a CTA, or (nl > 1024: ngb_k_lu_grid, cooperative launch) the whole grid */
 #define NGB_GROUP_SYNC() do { if (nl <= 32) __syncwarp(ngb_gsync_mask); else if (nl <= 1024) __syncthreads(); else cooperative_groups::this_grid().sync(); } while (0)
+/* programmatic dependent launch (sm_90+): a kernel launched with the attribute may be scheduled while its predecessor in
+ * the stream is still draining; it must pass NGB_PDL_WAIT() before it touches anything the predecessor wrote (the wait
+ * returns when the predecessor grid has completed and its writes are visible).  NGB_PDL_TRIGGER() lets the successor be
+ * scheduled from that point on.  Both are no-ops in a launch without the attribute. */
+#define NGB_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define NGB_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #ifndef NGB_B4_CTA
 #define NGB_B4_CTA 256
 #endif
@@ -42,6 +48,23 @@ static int g_device = -1;
 static std::atomic<long> g_launches{0};
 static int g_smem_optin = 0, g_sm_count = 148;
 
+/* NGB_PDL=1: the LU, BSIM4trunc and controller launches of a Newton step carry the programmatic-stream-serialization
+ * attribute (their kernels wait with griddepcontrol.wait); 2: the batch assembly as well.  0 / unset: plain launches */
+static int g_pdl = -1;
+template <typename... KArgs, typename... Args>
+static void ngb_launch_dep(int level, void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args)
+{
+    if (g_pdl < 0) { const char *e = getenv("NGB_PDL"); g_pdl = e ? atoi(e) : 0; }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    if (g_pdl >= level) { cfg.attrs = at; cfg.numAttrs = 1; }
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 extern "C" void ngb_set_error(const char *fmt, ...);
 
 #define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -53,6 +76,7 @@ template <unsigned VK>
 __global__ void __launch_bounds__(NGB_B4_CTA, NGB_B4_MINBLOCKS)
 ngb_k_bsim4_load(const B4Ctx c, int *errflag)
 {
+    NGB_PDL_TRIGGER();
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)c.T) return;
     const int e = b4_load_thread<VK>(&c, t);
@@ -79,6 +103,8 @@ ngb_k_bsim4_lte(const B4Ctx c)
 __global__ void __launch_bounds__(256)
 ngb_k_bsim4_lte_flat(const B4Ctx c)
 {
+    NGB_PDL_WAIT();
+    NGB_PDL_TRIGGER();
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)c.T) return;
     const int inst = (int)(t / (size_t)c.S), s = (int)(t - (size_t)inst * c.S);
@@ -148,6 +174,8 @@ ngb_k_assemble(const NgbAsmCtx c, size_t total)
 __global__ void __launch_bounds__(256)
 ngb_k_assemble_tiled(const NgbAsmCtx c, int ntile_s)
 {
+    NGB_PDL_WAIT();
+    NGB_PDL_TRIGGER();
     __shared__ double tile[32][33];
     const int ts = (int)(blockIdx.x % (unsigned)ntile_s), tt = (int)(blockIdx.x / (unsigned)ntile_s);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -292,6 +320,10 @@ __global__ void ngb_k_lu_packed(const NgbLuCtx c, int groups, int tpg, int per_s
         unsigned *dst = reinterpret_cast<unsigned *>(smem);
         for (int i = threadIdx.x; i < blob_u16 / 2; i += blockDim.x) dst[i] = __ldg(&src[i]);
     }
+    /* the schedule is the circuit's, not the step's: under programmatic dependent launch its copy overlaps the tail of
+     * the assembly; everything below reads what the assembly wrote */
+    NGB_PDL_WAIT();
+    NGB_PDL_TRIGGER();
     __syncthreads();
     const int g = threadIdx.x / tpg, lane = threadIdx.x - g * tpg;
     const int s = blockIdx.x * groups + g;
@@ -314,6 +346,7 @@ __global__ void ngb_k_lu_packed(const NgbLuCtx c, int groups, int tpg, int per_s
 __global__ void __launch_bounds__(128)
 ngb_k_tran_control(const NgbTranCtx c)
 {
+    NGB_PDL_WAIT();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < c.S) ngb_tran_control(&c, s);
 }
@@ -665,7 +698,7 @@ int ngb_launch_bsim4_lte(const B4Ctx *c)
     static int flat = -1;
     if (flat < 0) { const char *e = getenv("NGB_LTE_FLAT"); flat = (e && !atoi(e)) ? 0 : 1; }
     if (flat && c->S >= 32)
-        ngb_k_bsim4_lte_flat<<<(unsigned)(((size_t)c->T + 255) / 256), 256, 0, g_stream>>>(*c);
+        ngb_launch_dep(1, ngb_k_bsim4_lte_flat, (unsigned)(((size_t)c->T + 255) / 256), 256u, 0, g_stream, *c);
     else
         ngb_k_bsim4_lte<<<(unsigned)(((size_t)c->S * 32 + 127) / 128), 128, 0, g_stream>>>(*c);
     return post_launch("bsim4_lte");
@@ -720,7 +753,7 @@ int ngb_launch_assemble(const NgbAsmCtx *c)
     if (tiled < 0) { const char *e = getenv("NGB_ASM_TILED"); tiled = (e && !atoi(e)) ? 0 : 1; }
     if (tiled && c->S >= 32) {
         const int nts = (c->S + 31) / 32, ntt = (c->nnz + c->neq1 + 31) / 32;
-        ngb_k_assemble_tiled<<<(unsigned)nts * (unsigned)ntt, 256, 0, g_stream>>>(*c, nts);
+        ngb_launch_dep(2, ngb_k_assemble_tiled, (unsigned)nts * (unsigned)ntt, 256u, 0, g_stream, *c, nts);
     } else {
         ngb_k_assemble<<<grid, 256, 0, g_stream>>>(*c, total);
     }
@@ -775,8 +808,8 @@ int ngb_launch_lu(const NgbLuCtx *c)
             const unsigned grid = (unsigned)((c->S + groups - 1) / groups);
             static int tpg = 0;
             if (!tpg) { const char *e = getenv("NGB_LU_TPG"); tpg = e ? atoi(e) : 32; if (tpg != 4 && tpg != 8 && tpg != 16) tpg = 32; }
-            if (v2) ngb_k_lu_packed<1><<<grid, (groups * tpg + 31) / 32 * 32, blob + bytes1 * groups, g_stream>>>(*c, groups, tpg, per);
-            else ngb_k_lu_packed<0><<<grid, (groups * tpg + 31) / 32 * 32, blob + bytes1 * groups, g_stream>>>(*c, groups, tpg, per);
+            if (v2) ngb_launch_dep(1, ngb_k_lu_packed<1>, grid, (unsigned)((groups * tpg + 31) / 32 * 32), blob + bytes1 * groups, g_stream, *c, groups, tpg, per);
+            else ngb_launch_dep(1, ngb_k_lu_packed<0>, grid, (unsigned)((groups * tpg + 31) / 32 * 32), blob + bytes1 * groups, g_stream, *c, groups, tpg, per);
             return post_launch("lu_packed");
         }
         if (blob + bytes1 <= (size_t)g_smem_optin) {
@@ -819,7 +852,7 @@ int ngb_launch_clear_i32(int *p, int value, int n)
 
 int ngb_launch_tran_control(const NgbTranCtx *c)
 {
-    ngb_k_tran_control<<<(unsigned)((c->S + 127) / 128), 128, 0, g_stream>>>(*c);
+    ngb_launch_dep(1, ngb_k_tran_control, (unsigned)((c->S + 127) / 128), 128u, 0, g_stream, *c);
     return post_launch("tran_control");
 }
 int ngb_launch_fill_f64(double *p, double value, int n)
