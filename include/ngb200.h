@@ -242,6 +242,10 @@ void ngbBatchSetLoadLte(ngb_batch *b, int on);
 /* which BSIM4 load kernel the batch runs (csrc/bsim4_variants.h): key[0] = the variant key packed from the model selectors
  * and rbodyMod / rgateMod of its instances (0xffffffff when they differ), key[1] = 1 when the kernel specialised on that key
  * is in use.  ngbBatchSetBsim4Generic(b, 1) (or NGB_B4_GENERIC=1 in the environment) forces the generic kernel: same bits */
+/* per-sample parameter rows (ngbBatchSetBsim4Rows) are read as an overlay: only the columns that differ between the samples
+ * of an instance at the thread's own row, the rest at the warp-uniform row of sample 0.  Returns 1 and the number of such
+ * model / bin columns, or 0 (counts -1) without per-sample rows or with NGB_B4_OVERLAY=0 */
+int ngbBatchBsim4Overlay(ngb_batch *b, int *model_columns, int *bin_columns);
 int ngbBatchBsim4Variant(ngb_batch *b, unsigned key[2]);
 void ngbBatchSetBsim4Generic(ngb_batch *b, int on);
 /* per-stage device time of the Newton steps sampled by ngbProfile (ms summed over the sampled steps; returns their number):

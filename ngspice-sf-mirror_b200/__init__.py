@@ -347,6 +347,12 @@ class Batch:
         self.lib.check(self.lib.L.ngbBatchBsim4Variant(self.h, k), "ngbBatchBsim4Variant")
         return int(k[0]), bool(k[1])
 
+    def bsim4_overlay(self):
+        """(model columns, bin columns) read per sample when the rows of set_bsim4_rows are read as an overlay, else None"""
+        nm, nb = ctypes.c_int(), ctypes.c_int()
+        on = self.lib.L.ngbBatchBsim4Overlay(self.h, ctypes.byref(nm), ctypes.byref(nb))
+        return (nm.value, nb.value) if on else None
+
     def set_bsim4_generic(self, on=True):
         """run the generic BSIM4 load kernel whatever the variant key (same bits; parity tests and measurements)"""
         self.lib.L.ngbBatchSetBsim4Generic(self.h, 1 if on else 0)

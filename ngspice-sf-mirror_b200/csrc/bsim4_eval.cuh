@@ -59,6 +59,10 @@ typedef struct B4Ctx {
     const double *ptab;        /* [nrows][B4P_COUNT] bin rows                            */
     const int *prow;           /* parameter row per thread ([T]) or per instance ([ninst]) */
     int prow_per_thread;       /* 1: prow[t], 0: prow[inst]                              */
+    int overlay;               /* per-thread rows read as an OVERLAY: Mrow / Prow are the rows of the instance's sample 0 and only the
+                                * columns that differ between the samples of an instance are read at the thread's own row (below) */
+    int mvary[B4M_COUNT];      /* byte pitch of a model row for the columns that differ between samples, 0 for the others */
+    int pvary[B4P_COUNT];      /* same for the bin rows                                  */
     unsigned variant;          /* variant key of the batch (bsim4_variants.h), NGB_B4_GENERIC when its instances differ */
     const double *inst;        /* [B4I_COUNT][T]                                         */
     const int *flags;          /* [ninst] packed B4F_*                                   */
@@ -116,8 +120,15 @@ typedef struct B4W {
 } B4W;
 
 #include "bsim4_variants.h"
-#define B4M(f) NGB_LDG(&Mrow[B4M_##f])
-#define B4P(f) NGB_LDG(&Prow[B4P_##f])
+/* Per-sample parameter rows as an overlay (the generic kernel always, a specialised one when its key says so): of the 221
+ * model / bin parameters a process-variation draw changes a handful (oxide thickness: 15), so 32 lanes reading 32 whole rows
+ * is 32 sectors per load where one would do.  The host finds the columns that differ between the samples of an instance
+ * (ngb_host.c: b4_find_vary); Mrow / Prow point at the rows of the instance's sample 0, b4dr is the distance in rows to the
+ * thread's own rows, and a load costs one integer multiply-add with a kernel-constant operand: columns that do not vary
+ * are read at the warp-uniform address, the others at the lane's row. */
+#define B4OVL ((VK == NGB_B4_GENERIC) || B4K_FIELD(VK, rowsO))
+#define B4M(f) NGB_LDG(B4OVL ? (const double *)((const char *)&Mrow[B4M_##f] + (ptrdiff_t)b4dr * c->mvary[B4M_##f]) : &Mrow[B4M_##f])
+#define B4P(f) NGB_LDG(B4OVL ? (const double *)((const char *)&Prow[B4P_##f] + (ptrdiff_t)b4dr * c->pvary[B4P_##f]) : &Prow[B4P_##f])
 #define B4I(f) NGB_LDG(&c->inst[(size_t)B4I_##f * c->T + t])
 /* selectors: compile-time constants of the variant key VK in a specialised instantiation, read from the parameter
  * row / instance flags in the generic one (bsim4_variants.h) */
@@ -267,7 +278,7 @@ struct B4StRef {
 /* Phase A: terminal voltages by INITF mode and Newton step limiting (b4ld.c:257-698). */
 template <unsigned VK>
 NGB_HD void b4_fetch_limit(const B4Ctx *c, size_t t, int inst, int s, int head, int mode_ckt,
-                           const double *Mrow, int flags, B4W *w)
+                           const double *Mrow, int b4dr, int flags, B4W *w)
 {
     const int rbodyMod = B4SEL_RBODY(flags), rgateMod = B4SEL_RGATE(flags);
     const int off = flags & B4F_OFF;
@@ -445,7 +456,7 @@ NGB_HD void b4_fetch_limit(const B4Ctx *c, size_t t, int inst, int s, int head, 
 /* Phase B+C: junction diodes, threshold voltage, effective gate drive, mobility, Vdsat,
  * drain current and its output-resistance corrections (b4ld.c:700-2189). */
 template <unsigned VK>
-NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, const double *Prow,
+NGB_HD void b4_core_dc(const B4Ctx *c, size_t t, int s, const double *Mrow, const double *Prow, int b4dr,
                        int flags, B4W *w)
 {
     const double gmin = NGB_LDG(&c->ctl.gmin[s]);
@@ -1667,7 +1678,7 @@ NGB_HD_SHARED void b4_ig_edge(double vg, double vfbsd_tot, double Aechvb, double
 /* Phase D: gate resistance network, bias-dependent S/D resistance, GIDL/GISL, gate
  * tunnelling, finger scaling (b4ld.c:2191-2976). */
 template <unsigned VK>
-NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const double *Prow,
+NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const double *Prow, int b4dr,
                           int flags, B4W *w)
 {
     const int rgateMod = B4SEL_RGATE(flags);
@@ -2171,7 +2182,7 @@ NGB_HD void b4_parasitics(const B4Ctx *c, size_t t, const double *Mrow, const do
 
 /* VgsteffCV selection shared by capMod 1 and 2 (b4ld.c:3351-3457) */
 template <unsigned VK>
-NGB_HD void b4_vgsteff_cv(const double *Mrow, const double *Prow, const B4W *w,
+NGB_HD void b4_vgsteff_cv(const B4Ctx *c, const double *Mrow, const double *Prow, int b4dr, const B4W *w,
                           double *pVgsteff, double *pdVg, double *pdVd, double *pdVb)
 {
     const double n = w->n, dn_dVd = w->dn_dVd, dn_dVb = w->dn_dVb, Vtm = w->Vtm, Vgst = w->Vgst;
@@ -2270,7 +2281,7 @@ NGB_HD void b4_vgsteff_cv(const double *Mrow, const double *Prow, const B4W *w,
 /* Phase E: intrinsic terminal charges and trans-capacitances (b4ld.c:3014-3913).
  * Returns 0 when charges are not computed (xpart<0 or no charge computation). */
 template <unsigned VK>
-NGB_HD int b4_charges(const B4Ctx *c, size_t t, const double *Mrow, const double *Prow,
+NGB_HD int b4_charges(const B4Ctx *c, size_t t, const double *Mrow, const double *Prow, int b4dr,
                       int ChargeComputationNeeded, B4W *w)
 {
     const double xpart = B4M(xpart);
@@ -2536,7 +2547,7 @@ NGB_HD int b4_charges(const B4Ctx *c, size_t t, const double *Mrow, const double
         if (Vbseff < 0.0) { VbseffCV = Vbseff; dVbseffCV_dVb = 1.0; }
         else { VbseffCV = phi - Phis; dVbseffCV_dVb = -dPhis_dVb; }
 
-        b4_vgsteff_cv<VK>(Mrow, Prow, w, &Vgsteff, &dVgsteff_dVg, &dVgsteff_dVd, &dVgsteff_dVb);
+        b4_vgsteff_cv<VK>(c, Mrow, Prow, b4dr, w, &Vgsteff, &dVgsteff_dVg, &dVgsteff_dVd, &dVgsteff_dVb);
 
         if (capMod == 1) {
             const double Vfb = vfbzb;
@@ -2975,6 +2986,7 @@ NGB_HD_SHARED void b4_junction_cv(double vj, double cz, double czsw, double czsw
 /* what every phase of one evaluation starts from (cheap to recompute, so the split kernels do) */
 typedef struct B4Pro {
     int inst, s, head, mode_ckt, flags, charge;
+    int dr;                    /* overlay: rows from the instance's sample-0 rows (Mrow / Prow) to the thread's own */
     const double *Mrow, *Prow;
 } B4Pro;
 
@@ -2993,8 +3005,12 @@ NGB_HD int b4_prologue(const B4Ctx *c, size_t t, int first, B4Pro *p, int *err)
     const int prow = c->prow_per_thread ? NGB_LDG(&c->prow[t]) : NGB_LDG(&c->prow[inst]);
     p->inst = inst; p->s = s; p->head = head; p->mode_ckt = mode_ckt;
     p->flags = NGB_LDG(&c->flags[inst]);
-    p->Mrow = c->mtab + (size_t)prow * B4M_COUNT;
-    p->Prow = c->ptab + (size_t)prow * B4P_COUNT;
+    {
+        const int prow0 = c->overlay ? NGB_LDG(&c->prow[t - (size_t)s]) : prow;
+        p->dr = prow - prow0;
+        p->Mrow = c->mtab + (size_t)prow0 * B4M_COUNT;
+        p->Prow = c->ptab + (size_t)prow0 * B4P_COUNT;
+    }
 
     if (mode_ckt & NGB_MODEINITSMSIG) { *err = NGB_E_UNSUPP; return 0; }
 
@@ -3041,12 +3057,12 @@ NGB_HD int b4_load_thread(const B4Ctx *c, size_t t)
             asm volatile("prefetch.global.L2 [%0];" :: "l"(&c->inst[(size_t)f * c->T + t]));
     }
 #endif
-    b4_fetch_limit<VK>(c, t, p.inst, p.s, p.head, p.mode_ckt, p.Mrow, p.flags, &w);
-    b4_core_dc<VK>(c, t, p.s, p.Mrow, p.Prow, p.flags, &w);
+    b4_fetch_limit<VK>(c, t, p.inst, p.s, p.head, p.mode_ckt, p.Mrow, p.dr, p.flags, &w);
+    b4_core_dc<VK>(c, t, p.s, p.Mrow, p.Prow, p.dr, p.flags, &w);
     /* the parasitics and the intrinsic charges only read what the core phase left; the charges first (12 values for the
      * finish phase alive across the parasitics instead of 52 across the charges) was measured 6 % SLOWER on B200 */
-    b4_parasitics<VK>(c, t, p.Mrow, p.Prow, p.flags, &w);
-    b4_charges<VK>(c, t, p.Mrow, p.Prow, p.charge, &w);
+    b4_parasitics<VK>(c, t, p.Mrow, p.Prow, p.dr, p.flags, &w);
+    b4_charges<VK>(c, t, p.Mrow, p.Prow, p.dr, p.charge, &w);
     return b4_finish<VK>(c, t, &p, &w);
 }
 

@@ -42,6 +42,8 @@
 #define B4K_rgateMod_W        2
 #define B4K_gear_SH          21   /* 1: CKTintegrateMethod == GEAR */
 #define B4K_gear_W            1
+#define B4K_rowsO_SH         22   /* 1: per-sample parameter rows read as an overlay (bsim4_eval.cuh, B4OVL) */
+#define B4K_rowsO_W           1
 
 #define NGB_B4_GENERIC 0xffffffffu
 
@@ -60,7 +62,8 @@
  *   (the QA cards of tests/bsim4/{nmos,pmos}/parameters resolve to the same key)
  * more keys: add a line here (each costs ~15 s of compile time and ~230 KB of code) */
 #define NGB_B4_VARIANT_KEYS(X) \
-    X(NGB_B4_KEY(0, 2, 0, 1, 0, 1, 1, 0, 0, 0, 0, 1, 1, 0))
+    X(NGB_B4_KEY(0, 2, 0, 1, 0, 1, 1, 0, 0, 0, 0, 1, 1, 0)) \
+    X(NGB_B4_KEY(0, 2, 0, 1, 0, 1, 1, 0, 0, 0, 0, 1, 1, 0) | B4K_PACK(rowsO, 1))
 
 /* the variant a batch runs: its key when the library carries that instantiation, NGB_B4_GENERIC otherwise */
 static inline int b4_variant_built(unsigned key)

@@ -74,7 +74,7 @@ extern "C" void ngb_set_error(const char *fmt, ...);
 /* one instantiation per variant key of bsim4_variants.h plus the generic one */
 template <unsigned VK>
 __global__ void __launch_bounds__(NGB_B4_CTA, NGB_B4_MINBLOCKS)
-ngb_k_bsim4_load(const B4Ctx c, int *errflag)
+ngb_k_bsim4_load(const __grid_constant__ B4Ctx c, int *errflag)
 {
     NGB_PDL_TRIGGER();
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,7 +84,7 @@ ngb_k_bsim4_load(const B4Ctx c, int *errflag)
 }
 
 __global__ void __launch_bounds__(128)
-ngb_k_bsim4_lte(const B4Ctx c)
+ngb_k_bsim4_lte(const __grid_constant__ B4Ctx c)
 {
     const int s = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (s >= c.S || !b4_lte_wanted(&c, s)) return;
@@ -101,7 +101,7 @@ ngb_k_bsim4_lte(const B4Ctx c)
  * read is coalesced over the converged samples of a warp (a warp per sample reads 8 useful bytes per 32-byte sector); one
  * atomic minimum per instance and sample.  Default for batches (NGB_LTE_FLAT=0: the warp-per-sample kernel) */
 __global__ void __launch_bounds__(256)
-ngb_k_bsim4_lte_flat(const B4Ctx c)
+ngb_k_bsim4_lte_flat(const __grid_constant__ B4Ctx c)
 {
     NGB_PDL_WAIT();
     NGB_PDL_TRIGGER();
@@ -116,7 +116,7 @@ ngb_k_bsim4_lte_flat(const B4Ctx c)
 }
 
 __global__ void __launch_bounds__(256)
-ngb_k_cap_load(const NgbCapCtx c, int *errflag)
+ngb_k_cap_load(const __grid_constant__ NgbCapCtx c, int *errflag)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)c.T) return;
@@ -125,7 +125,7 @@ ngb_k_cap_load(const NgbCapCtx c, int *errflag)
 }
 
 __global__ void __launch_bounds__(256, 2)
-ngb_k_bsim3_load(const B3Ctx c, int *errflag)
+ngb_k_bsim3_load(const __grid_constant__ B3Ctx c, int *errflag)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)c.T) return;
@@ -134,7 +134,7 @@ ngb_k_bsim3_load(const B3Ctx c, int *errflag)
 }
 
 __global__ void __launch_bounds__(128)
-ngb_k_vbic_load(const NgbVbicCtx c, int *errflag)
+ngb_k_vbic_load(const __grid_constant__ NgbVbicCtx c, int *errflag)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)c.T) return;
@@ -143,7 +143,7 @@ ngb_k_vbic_load(const NgbVbicCtx c, int *errflag)
 }
 
 __global__ void __launch_bounds__(256)
-ngb_k_dio_load(const NgbDioCtx c, int *errflag)
+ngb_k_dio_load(const __grid_constant__ NgbDioCtx c, int *errflag)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)c.T) return;
@@ -152,7 +152,7 @@ ngb_k_dio_load(const NgbDioCtx c, int *errflag)
 }
 
 __global__ void __launch_bounds__(256)
-ngb_k_src_load(const NgbSrcCtx c)
+ngb_k_src_load(const __grid_constant__ NgbSrcCtx c)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)c.T) return;

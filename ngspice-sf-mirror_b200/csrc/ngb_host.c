@@ -1965,6 +1965,35 @@ int ngbBatchSetResistors(ngb_batch *b, const double *g)
 }
 
 /* per-thread parameter rows (Monte-Carlo with model-parameter mismatch): prow [ninst*S] */
+/* which columns of the per-sample rows differ between the samples of an instance: the load reads only those at the thread's
+ * own row and every other one at the row of the instance's sample 0 (the same value, at a warp-uniform address).  Row pairs are
+ * compared once per distinct (row of sample 0, row of sample s) pair of consecutive instances -- the instances of a card share
+ * their rows -- so the cost is one pass over the table, not over the threads */
+static void b4_find_vary(ngb_batch *b, const int *prow_t, const double *mtab, const double *ptab)
+{
+    const int n = b->c->b4_n, S = b->S;
+    int i, s, f, seen[16], nseen = 0;
+    memset(b->b4_mvary, 0, sizeof b->b4_mvary);
+    memset(b->b4_pvary, 0, sizeof b->b4_pvary);
+    for (i = 0; i < n; i++) {
+        const int *pr = prow_t + (size_t)i * S;
+        {   /* same rows as an instance already looked at (the transistors of one card) */
+            int k, dup = 0;
+            for (k = 0; k < nseen && !dup; k++) dup = !memcmp(pr, prow_t + (size_t)seen[k] * S, sizeof(int) * (size_t)S);
+            if (dup) continue;
+            if (nseen < 16) seen[nseen++] = i;
+        }
+        for (s = 1; s < S; s++) {
+            const double *m0 = mtab + (size_t)pr[0] * B4M_COUNT, *m1 = mtab + (size_t)pr[s] * B4M_COUNT;
+            const double *p0 = ptab + (size_t)pr[0] * B4P_COUNT, *p1 = ptab + (size_t)pr[s] * B4P_COUNT;
+            if (pr[s] == pr[0]) continue;
+            /* bit patterns, not values: -0.0 and NaN payloads are different parameters too */
+            for (f = 0; f < B4M_COUNT; f++) if (memcmp(&m0[f], &m1[f], sizeof(double))) b->b4_mvary[f] = (int)(sizeof(double) * B4M_COUNT);
+            for (f = 0; f < B4P_COUNT; f++) if (memcmp(&p0[f], &p1[f], sizeof(double))) b->b4_pvary[f] = (int)(sizeof(double) * B4P_COUNT);
+        }
+    }
+}
+
 int ngbBatchSetBsim4Rows(ngb_batch *b, const int *prow_t, int nrows, const double *mtab, const double *ptab)
 {
     const size_t T = (size_t)b->c->b4_n * b->S;
@@ -1981,6 +2010,14 @@ int ngbBatchSetBsim4Rows(ngb_batch *b, const int *prow_t, int nrows, const doubl
     ngb_dev_h2d(b->b4_ptab, ptab, pb);
     ngb_dev_l2_persist(b->b4_rows_block, mb + pb);
     b->b4_key = b4_batch_key(b->c, mtab, nrows, NULL);
+    {   /* overlay reading of the rows (bsim4_eval.cuh, B4OVL) unless NGB_B4_OVERLAY=0 */
+        const char *e = getenv("NGB_B4_OVERLAY");
+        b->b4_overlay = (e && !atoi(e)) ? 0 : 1;
+        if (b->b4_overlay) {
+            b4_find_vary(b, prow_t, mtab, ptab);
+            if (b->b4_key != NGB_B4_GENERIC) b->b4_key |= B4K_PACK(rowsO, 1);
+        }
+    }
     return NGB_OK;
 }
 
@@ -2017,6 +2054,19 @@ int ngbBatchBsim4Variant(ngb_batch *b, unsigned key[2])
     key[1] = (b->b4_key != NGB_B4_GENERIC && !b->b4_force_generic && b4_variant_built(b->b4_key)) ? 1u : 0u;
     return NGB_OK;
 }
+/* per-sample rows read as an overlay: how many model / bin columns differ between the samples of an instance (those are read
+ * at the thread's own row, all others at the row of sample 0); returns 0 and leaves the counts at -1 when the batch has no
+ * per-sample rows or the overlay is switched off (NGB_B4_OVERLAY=0) */
+int ngbBatchBsim4Overlay(ngb_batch *b, int *model_columns, int *bin_columns)
+{
+    int f, nm = 0, np = 0;
+    *model_columns = *bin_columns = -1;
+    if (!b->b4_prow_t || !b->b4_overlay) return 0;
+    for (f = 0; f < B4M_COUNT; f++) nm += b->b4_mvary[f] != 0;
+    for (f = 0; f < B4P_COUNT; f++) np += b->b4_pvary[f] != 0;
+    *model_columns = nm; *bin_columns = np;
+    return 1;
+}
 void ngbBatchSetBsim4Generic(ngb_batch *b, int on) { b->b4_force_generic = on ? 1 : 0; }
 
 /* ------------------------------------------------------------------ hot path launches */
@@ -2028,6 +2078,10 @@ void ngb_fill_b4ctx(ngb_batch *b, B4Ctx *x)
     x->mtab = b->b4_mtab; x->ptab = b->b4_ptab;
     x->prow = b->b4_prow_t ? b->b4_prow_t : b->b4_prow; x->prow_per_thread = b->b4_prow_t ? 1 : 0;
     x->variant = (!b->b4_force_generic && b4_variant_built(b->b4_key)) ? b->b4_key : NGB_B4_GENERIC;
+    if (b->b4_prow_t && b->b4_overlay) {
+        x->overlay = 1;
+        memcpy(x->mvary, b->b4_mvary, sizeof x->mvary); memcpy(x->pvary, b->b4_pvary, sizeof x->pvary);
+    }
     x->inst = b->b4_inst; x->flags = b->b4_flags; x->nodes = b->b4_nodes; x->spos = b->b4_spos;
     x->stamp = b->stamp; x->state = b->b4_state; x->op = b->b4_op; x->op_full = b->op_full;
     x->x = b->x; x->neq1 = b->neq1; x->ctl = b->ctl; x->temp = c->opt.temp; x->vt0 = c->opt.vt0;

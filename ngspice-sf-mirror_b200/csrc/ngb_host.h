@@ -84,6 +84,8 @@ struct ngb_batch {
     struct ngb_tran *tran;
     int load_lte;              /* ngbBatchSetLoadLte: direct ngbLoad calls evaluate DEVtrunc's bounds inside the load (off by default) */
     unsigned b4_key;           /* variant key of the BSIM4 instances (bsim4_variants.h); NGB_B4_GENERIC when they differ */
+    int b4_overlay;            /* per-sample rows are read as an overlay over the rows of sample 0 (ngbBatchSetBsim4Rows) */
+    int b4_mvary[B4M_COUNT], b4_pvary[B4P_COUNT];   /* byte pitch of a row for the columns that differ between samples, else 0 */
     int b4_force_generic;      /* ngbBatchSetBsim4Generic / NGB_B4_GENERIC=1: run the generic kernel whatever the key */
     /* measurement clauses for the next ngbTranRun (ngbTranSetMeasures) */
     int ms_n; int *ms_eq, *ms_kind, *ms_count; double *ms_val, *ms_td;
