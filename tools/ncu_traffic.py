@@ -21,8 +21,9 @@ def num(m, key):
     return x * scale
 
 
-out = {"source": "ncu --set full --clock-control none, one launch each (launch 30 of the kernel), Monte-Carlo ro17k batch of 4096 samples "
-                 "(tests/gpu_profile_run.py 4096, tools/gpu_r2_profiles.sh); summaries in profiles/r02_*_ncu_details.txt"}
+out = {"source": "ncu --set full --clock-control none, one launch each; ngb_k_bsim4_load: launch 15 000 of the default bench's transient "
+                 "(tools/gpu_r2_final.sh: 4096 samples, per-sample parameter rows, every sample at its own phase); LU and assembly: launch 30 of the "
+                 "lock-step batch (tests/gpu_profile_run.py 4096, tools/gpu_r2_profiles.sh); summaries in profiles/r02_*_ncu_details.txt"}
 for key, rep, units in (("ngb_k_bsim4_load", "r02_b4load.ncu-rep", 139264), ("ngb_k_lu_packed", "r02_lu.ncu-rep", 4096), ("ngb_k_assemble", "r02_asm.ncu-rep", 4096)):
     p = os.path.join(d, rep)
     if not os.path.exists(p):
