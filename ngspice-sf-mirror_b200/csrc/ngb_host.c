@@ -2008,7 +2008,12 @@ int ngbBatchSetBsim4Rows(ngb_batch *b, const int *prow_t, int nrows, const doubl
     if (!b->b4_prow_t || !b->b4_rows_block) return NGB_E_PANIC;
     ngb_dev_h2d(b->b4_mtab, mtab, sizeof(double) * (size_t)nrows * B4M_COUNT);
     ngb_dev_h2d(b->b4_ptab, ptab, pb);
-    ngb_dev_l2_persist(b->b4_rows_block, mb + pb);
+    {   /* what stays in L2 between the launches of a step: the parameter rows (default), or -- NGB_L2_PERSIST=2, experiment --
+         * the stamp rows the loads write and the assembly reads back */
+        const char *e = getenv("NGB_L2_PERSIST");
+        if (e && atoi(e) == 2) ngb_dev_l2_persist(b->stamp, sizeof(double) * (size_t)b->c->nstamp_rows * b->S);
+        else ngb_dev_l2_persist(b->b4_rows_block, mb + pb);
+    }
     b->b4_key = b4_batch_key(b->c, mtab, nrows, NULL);
     {   /* overlay reading of the rows (bsim4_eval.cuh, B4OVL) unless NGB_B4_OVERLAY=0 */
         const char *e = getenv("NGB_B4_OVERLAY");
