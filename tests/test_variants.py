@@ -68,3 +68,31 @@ def test_per_sample_rows_as_overlay_same_bits_gpu(cuda_lib, monkeypatch):
     for r, t, v in ((r0, t0, v0), (rg, tg, vg)):
         assert np.array_equal(r.npoints, r1.npoints) and np.array_equal(r.numiter, r1.numiter)
         assert np.array_equal(t, t1) and np.array_equal(v, v1)
+
+
+def test_overlay_rows_in_any_order_hostsim(hostsim_lib, monkeypatch):
+    """the overlay addresses a thread's rows by their distance from the rows of the instance's sample 0: the same tables with
+    their rows permuted (negative distances, sample 0 no longer at the lowest row) give the same bits"""
+    from parity_util import run_patterns
+    base = ngt.read(f"{GOLDEN}/ro17k.flat.ngt"); trace = ngt.read(f"{GOLDEN}/ro17k.trace.ngt.gz")
+    tab = ngt.read(f"{GOLDEN}/b4temp.tables.ngt.gz")
+    raw = {"model": tab["ro17k/b4t/model"], "inst": tab["ro17k/b4t/inst"], "inst_model": tab["ro17k/b4t/inst_model"],
+           "temp": tab["ro17k/b4t/temp"][0, 0], "vt0": tab["ro17k/opt/vt0"][0]}
+    S = 4
+    toxe = 1.4e-9 * (1.0 + 0.03 * np.random.default_rng(3).normal(size=S))
+    dv = pkg.mc.draw_delvto(S, 34, seed=12)
+    inst, prow_t, mtab, ptab = pkg.mc.bsim4_with_toxe(hostsim_lib, raw, toxe, dv)
+    circ = pkg.Circuit.from_flat(hostsim_lib, base, lu_pattern=run_patterns(trace))
+    out = []
+    perm = np.random.default_rng(4).permutation(mtab.shape[0])
+    inv = np.empty_like(perm); inv[perm] = np.arange(len(perm))
+    for p_rows, m, p in ((prow_t, mtab, ptab), (inv[prow_t].astype(np.int32), mtab[perm], ptab[perm])):
+        b = pkg.Batch(circ, S)
+        b.put("b4.inst", inst)
+        b.set_bsim4_rows(p_rows, m, p)
+        assert b.bsim4_overlay() == (3, 12)
+        res = b.tran(512, [18])
+        out.append((res.npoints.copy(), res.numiter.copy()) + res.waves())
+    assert (inv[prow_t].reshape(34, S)[:, 1:] < inv[prow_t].reshape(34, S)[:, :1]).any()       # some distances are negative
+    for a, c in zip(out[0], out[1]):
+        assert np.array_equal(a, c)
