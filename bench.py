@@ -308,7 +308,7 @@ def workload_config(args):
                         ".tran .1ns 150ns uic from alternating `.ic` stage voltages, per-instance delvto mismatch sigma 15 mV and per-sample toxe "
                         + ("~ N(1.4 nm, 3 %), continuous (rows by the library's BSIM4temp)" if getattr(args, "tox", "continuous") == "continuous" else "from 8 levels of N(1.4 nm, 3 %)"),
             "samples_per_gpu": args.samples, "bsim4_instances": 34, "unknowns": 155,
-            "layout": ("per-sample parameter rows, " + ("draws unsorted" if os.environ.get("NGB_BENCH_UNSORTED") else "samples laid out by toxe (same draws)")) if getattr(args, "tox", "continuous") == "continuous"
+            "layout": ("per-sample parameter rows" + ("" if os.environ.get("NGB_B4_OVERLAY") == "0" else " read as an overlay (only the columns that differ between samples per lane)") + ", " + ("draws unsorted" if os.environ.get("NGB_BENCH_UNSORTED") else "samples laid out by toxe (same draws)")) if getattr(args, "tox", "continuous") == "continuous"
                       else ("draws unsorted" if os.environ.get("NGB_BENCH_UNSORTED") else "samples laid out level by level (same draws)"),
             "l2": "inputs larger than L2: per-step working set (parameters+states+stamps+matrices) ~%.0f MB" %
                   (args.samples * 34 * (51 + 4 * 29 + 38 + 52) * 8 / 1e6 + args.samples * 904 * 8 / 1e6)}
