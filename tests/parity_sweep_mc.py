@@ -6,7 +6,7 @@ runs draws LO..HI-1 of bench.py's rank-0 Monte-Carlo batch (per-instance delvto,
 toxe exactly like the bench) through the library (host build of the kernel bodies by default) as ONE batch and through the
 stock reference, one process per draw, and compares every accepted point of v(out) bit for bit.
 Round 2: draws 0..4095 as one batch on the B200 (`0 4096 cuda`, 273 s): all 4 096 bit-identical; draws 16..255 on the host build
-likewise; after the overlay reads of the per-sample rows (end of round 2): draws 2000..2031 on the host build, 32 of 32 bit-identical;
+likewise; after the overlay reads of the per-sample rows (end of round 2): draws 2000..2031 on the host build and draws 100..1155 on the B200 (three calls, 1 056 draws), all bit-identical;
 bench.py itself checks draws 0..cores-1 in every run."""
 import os
 import sys
